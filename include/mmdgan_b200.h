@@ -1,0 +1,202 @@
+/* mmdgan_b200 -- C ABI of the B200-native MMD-GAN (SNGan + repulsive MMD) training hot path.
+ *
+ * The reference (richardwth/MMD-GAN) has no FFI layer of its own: every device kernel on this path is a TensorFlow-1.8
+ * library call.  Each entry point below therefore names the reference CALL SITE it replaces (file:line under
+ * /root/reference).  The Python host mirror in mmd-gan_b200/ (layer_func / math_func / my_sngan) binds these symbols
+ * with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: extern "C"; every function returns int (0 = ok, < 0 = MMDGAN_E*); mmdgan_last_error() gives the
+ * thread-local message; all tensor arguments are caller-owned DEVICE pointers to contiguous fp32 (16-byte aligned);
+ * `stream` is a cudaStream_t passed as void*; no allocation, no synchronisation and no host copies inside, so every
+ * call is CUDA-graph capturable; workspaces are sized by the *_workspace() queries and provided by the caller.
+ *
+ * Internal activation format ("planes"): NHWC, [plane][N*H*W][C] with C a multiple of 4.  Plane 0 holds the fp32
+ * value, plane 1 (at + *_plane elements) holds lo = rn_tf32(x - trunc_tf32(x)); the tensor-core kernels multiply
+ * x*w + x_lo*w + x*w_lo (npass = 3) to obtain fp32-grade products from the tf32 pipe.  npass = 1 is plain tf32.
+ */
+#ifndef MMDGAN_B200_H
+#define MMDGAN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMDGAN_OK 0
+#define MMDGAN_EINVAL (-1) /* bad argument (null pointer, unsupported size, unknown loss type) */
+#define MMDGAN_ESHAPE (-2) /* inconsistent shapes / alignment */
+#define MMDGAN_EARCH (-3)  /* not an sm_100 device */
+#define MMDGAN_ECUDA (-4)  /* CUDA runtime / driver error */
+#define MMDGAN_ENCCL (-5)  /* collective error (reserved) */
+
+const char* mmdgan_last_error(void);
+int mmdgan_version(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), MMDGAN_EARCH otherwise */
+int mmdgan_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Layout at the boundary.  Replaces the NCHW float32 batch contract of ReadTFRecords
+ * (GeneralTools/input_func.py:837-868) and tf.concat of real + generated batches (DeepLearning/my_sngan.py:244-256):
+ * the real batch is written straight into rows [0, B) of the discriminator's 2B input buffer. */
+int mmdgan_nchw_to_nhwc(const float* src, float* dst, long long dst_plane, int N, int C, int H, int W, int Cpad, void* stream);
+int mmdgan_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int Cpad, void* stream);
+int mmdgan_make_lo_plane(const float* hi, float* lo, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Weight packing: canonical reference layouts (conv [k,k,Cin,Cout] layer_func.py:584, transposed conv
+ * [k,k,Cout,Cin] layer_func.py:595, dense [in,out] layer_func.py:577) -> K-major GEMM operand [planes][classes *
+ * rows_pad][kpad].  dst_plane = 0 writes one rn-tf32 plane (npass = 1). */
+#define MMDGAN_PACK_CONV_FWD 0
+#define MMDGAN_PACK_CONV_DGRAD_S1 1
+#define MMDGAN_PACK_CONV_DGRAD_S2 2
+#define MMDGAN_PACK_TC_FWD 3
+#define MMDGAN_PACK_TC_DGRAD 4
+#define MMDGAN_PACK_DENSE_FWD 5
+#define MMDGAN_PACK_DENSE_DGRAD 6
+typedef struct mmdgan_pack_desc {
+    const float* w;
+    float* out;
+    long long plane;
+    int mode, k, Cin, Cout, Cs, rows_pad, kpad, classes;
+    int in_C, in_HW, out_C, out_HW; /* dense: NCHW-flatten <-> NHWC-flatten feature permutation (HW <= 1: identity) */
+} mmdgan_pack_desc;
+int mmdgan_pack_weights(const mmdgan_pack_desc* d, void* stream);
+int mmdgan_permute_features(const float* src, float* dst, int n, int C, int HW, int inverse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Gather-GEMM on tcgen05 tensor cores: tf.matmul / tf.nn.conv2d / tf.nn.conv2d_transpose forward
+ * (GeneralTools/layer_func.py:909-928) and their input gradients (DeepLearning/my_sngan.py:301-304), with the
+ * kernel * (act_k / sigma) scaling (layer_func.py:884-887), bias add (946-952), activation (104-167) or activation
+ * derivative, tf32 hi/lo split and per-tile column sums fused into the epilogue. */
+typedef struct mmdgan_gemm_class {
+    int oy, ox, ooy, oox, wrow, pad0, pad1, pad2;
+} mmdgan_gemm_class;
+typedef struct mmdgan_gemm_desc {
+    const float* src;
+    long long src_plane;
+    int Nimg, Hs, Ws, Cs;
+    int Hg, Wg, sy, sx, TH, TW;
+    const float* w; /* packed weights */
+    long long w_plane;
+    long long w_rows; /* classes * rows_pad */
+    int kpad, classes;
+    float* dst;
+    long long dst_plane;
+    int Hd, Wd, Cd, osy, osx, Ncols;
+    float alpha_k;
+    const float* sigma; /* alpha = sigma ? alpha_k / *sigma : alpha_k */
+    const float* bias;
+    int act;            /* 0 linear, 1 lrelu(0.1), 2 relu, 3 tanh */
+    const float* aux;   /* multiply by act'(aux) evaluated from the layer output */
+    int aux_mode;
+    long long aux_wrap_at, aux_wrap_len;
+    float* colsum;      /* [tiles_m * classes][Ncols] or null */
+    float* colsumsq;
+    long long colsum_rows;
+    int out_mode;       /* 0 raw + lo plane, 1 rn-tf32 single plane, 2 raw single plane */
+    int bn;             /* N tile: 16, 32, 64, 128 */
+    int npass;          /* 3 (fp32-grade tf32x3) or 1 (tf32) */
+    mmdgan_gemm_class cls[4];
+} mmdgan_gemm_desc;
+int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream);
+/* number of M tiles (rows of the colsum workspace per class) */
+int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg);
+
+/* Weight gradient: W[r][(t,c)] = sum_p P[p][r] * G[g(p,t)][c] (filter gradients of the ops above and the
+ * d(sigma)/dW term of SpectralNorm, GeneralTools/math_func.py:661-672).  out: [splits][Cp][TH*TW*Cs]. */
+typedef struct mmdgan_wgrad_desc {
+    const float* plain; /* [planes][P][Cp] */
+    long long plain_plane;
+    long long P;
+    int Cp;
+    const float* g;     /* gathered activation planes [Nimg*Hs*Ws][Cs] */
+    long long g_plane;
+    int Nimg, Hs, Ws, Cs;
+    int Hg, Wg, sy, sx, TH, TW, oy, ox;
+    int splits;
+    float* out;
+    int bn, npass;
+} mmdgan_wgrad_desc;
+int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream);
+
+/* split-K partials -> canonical gradient; canon index = base + r*sr + t*st + c*sc for column t*Cg + c.
+ * dots (optional, [mmdgan_wgrad_reduce_blocks()] doubles) receives per-block partial <G, W>. */
+typedef struct mmdgan_wred_desc {
+    const float* partials;
+    int splits, R, NC, Cg, Cvalid, Rvalid;
+    int r_perm_C, r_perm_HW, c_perm_C, c_perm_HW; /* optional NHWC-flatten -> NCHW-flatten permutation of r / c */
+    long long base, sr, st, sc;
+    const float* w;
+    float* out;
+    double* dots;
+} mmdgan_wred_desc;
+int mmdgan_wgrad_reduce(const mmdgan_wred_desc* d, void* stream);
+int mmdgan_wgrad_reduce_blocks(long long total);
+/* grad = m*G - (m/sigma)*<G,W>*S with m = act_k/sigma: gradient through kernel * act_k / SpectralNorm(kernel) */
+int mmdgan_sn_grad_combine(float* g, const float* s, const double* dots, int ndots, const float* sigma, float act_k, long long n,
+                           void* stream);
+int mmdgan_scale_by_sigma(float* g, const float* sigma, float act_k, long long n, void* stream);
+/* sigma = ||v||, out = v / (sigma + eps) as planes: SpectralNorm._l2_norm / _l2_normalize_ (math_func.py:639-659) */
+int mmdgan_sn_normalize(const float* v, long long n, float eps, float* sigma_out, float* out, long long out_plane, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Reductions of per-tile partial sums (bias gradients; deterministic order, double accumulation) */
+int mmdgan_reduce_tiles(const float* partials, int T, int C, float scale, float* out, void* stream);
+int mmdgan_colsum_small(const float* x, int rows, int C, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batch normalisation: tf.layers.batch_normalization(axis=1, training, fused=True) (layer_func.py:953-966) */
+int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
+                       float* invstd, float* moving_mean, float* moving_var, void* stream);
+int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
+                    long long total, int act, float* out, long long out_plane, void* stream);
+int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, int C, long long rows, int rows_per_block, int act, float* psum, float* psumx,
+                         void* stream);
+int mmdgan_bn_bwd_apply(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
+                        const float* beta, const float* dbeta, const float* dgamma, int C, long long rows, int act, float* out,
+                        long long out_plane, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused pairwise squared distance -> Gaussian kernel(s) -> rep / rmb / mmd_g / mgb losses + score gradients
+ * (GeneralTools/math_func.py:767-858, 1048-1069, 1288-1473, 2160-2193, 2505-2550).  Row-block form for data
+ * parallelism: local rows are rows [row0, row0+b) of the Bg global rows. */
+typedef struct mmdgan_mmd_desc {
+    const float* gen_loc;
+    const float* real_loc;
+    const float* gen_all;
+    const float* real_all;
+    int b, Bg, row0, d;
+    int n_sigma;
+    float sigma[8];
+    float cD[3];
+    int bmode[3];
+    float bval[3];
+    float* sums;   /* [6] */
+    float* losses; /* [2] loss_gen, loss_dis */
+    float* dLg_dgen;
+    float* dLg_dreal; /* may be null */
+    float* dLd_dgen;
+    float* dLd_dreal;
+    void* workspace; /* mmdgan_mmd_workspace(b) bytes, zeroed once before the first call */
+} mmdgan_mmd_desc;
+/* fills n_sigma / sigma / cD / bmode / bval for loss_type in {"rep","rmb","mmd_g","mgb"} and rep_weights (w0, w1);
+ * returns MMDGAN_EINVAL for unknown types or w0 - w1 != 1 (the reference's assert, math_func.py:1340) */
+int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, float w1);
+size_t mmdgan_mmd_workspace(int b);
+int mmdgan_mmd_fwd_bwd(const mmdgan_mmd_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * tf.train.AdamOptimizer(lr, beta1, beta2, eps).apply_gradients over one flat parameter buffer
+ * (GeneralTools/graph_func.py:518-527; DeepLearning/my_sngan.py:424-426).  *step holds t for this update. */
+int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float beta1, float beta2, float eps,
+                const int* step, void* stream);
+int mmdgan_incr_step(int* step, void* stream);
+/* device-side replacement of the per-step `assert not any(isnan(loss))` (GeneralTools/graph_func.py:856) */
+int mmdgan_nan_flag(const float* x, int n, int* flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDGAN_B200_H */

@@ -1,0 +1,388 @@
+// Gather-GEMM on the sm_100a tensor cores: the conv / transposed-conv / dense forward and input-gradient passes.
+//
+//   D[m][n] = epilogue( alpha * sum_k A[m][k] * Bw[n][k] )
+//
+// A (activations, NHWC, hi/lo planes) is gathered tap by tap into 128-byte-swizzled K-major shared-memory tiles by
+// four producer warps with 16-byte cp.async (zero fill implements SAME padding and tile tails); Bw (weights, K-major
+// [rows][Kpad]) is staged by TMA; one elected thread issues tcgen05.mma kind::tf32 with the accumulator in TMEM.
+// With NPASS == 3 every k-block is multiplied three times (x*w + x_lo*w + x*w_lo) which recovers fp32-grade products
+// from the tf32 pipe (parity mode); NPASS == 1 is the plain tf32 speed mode.  The producer warps turn into the
+// epilogue: TMEM -> registers -> shared staging -> coalesced float4 stores with bias / activation / activation
+// derivative / tf32 hi-lo split and per-tile column sums (bias gradients, batch-norm statistics) fused in.
+//
+// Replaces the tf.matmul / tf.nn.conv2d / tf.nn.conv2d_transpose call sites of the reference
+// (GeneralTools/layer_func.py:909-928) and their gradients (DeepLearning/my_sngan.py:301-304).
+#include "conv_gemm.cuh"
+#include "tc_common.cuh"
+#include <stdio.h>
+
+namespace mg {
+
+static constexpr int kBM = 128;
+static constexpr int kRowBytes = 128;  // 32 fp32 = one swizzle row
+static constexpr int kProducerThreads = 128;
+static constexpr int kThreads = 192;
+static constexpr unsigned long long kWatchdogNs = 4000000000ull;
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded wait: a pipeline bug must fail loudly instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned code) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = gtime_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (gtime_ns() - t0 > kWatchdogNs) {
+            if (err) atomicExch(err, code);
+            printf("mmdgan: mbarrier watchdog (code %u) block (%d,%d,%d) thread %d\n", code, blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+template <int BN, int NPASS>
+struct GemmCfg {
+    static constexpr int NPL = (NPASS == 3) ? 2 : 1;
+    static constexpr int A_BYTES = kBM * kRowBytes;  // per plane
+    static constexpr int B_BYTES = BN * kRowBytes;
+    static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+    static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
+    static constexpr int PITCH = BN * 4 + 16;  // staging row pitch in bytes
+    static constexpr int STAGING_BYTES = kBM * PITCH;
+    static constexpr int RED_BYTES = 2 * kProducerThreads * 16;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES + RED_BYTES ? PIPE_BYTES : STAGING_BYTES + RED_BYTES;
+    static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return v > 0.f ? v : 0.1f * v;
+    if (act == 2) return v > 0.f ? v : 0.f;
+    if (act == 3) return tanhf(v);
+    return v;
+}
+__device__ __forceinline__ float act_grad_from_output(float a, int mode) {
+    if (mode == 1) return a > 0.f ? 1.f : 0.1f;
+    if (mode == 2) return a > 0.f ? 1.f : 0.f;
+    if (mode == 3) return 1.f - a * a;
+    return 1.f;
+}
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ ConvGemmParams p) {
+    using Cfg = GemmCfg<BN, NPASS>;
+    constexpr int NPL = Cfg::NPL;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int LAG = Cfg::LAG;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* accum_bar = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x;
+    const int tile_n = blockIdx.y;
+    const GemmClass cls = p.cls[blockIdx.z];
+    const int ksteps = p.ksteps;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmB0);
+        if (NPL == 2) tma_prefetch_desc(&tmB1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], kProducerThreads + 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto stage_a = [&](int s, int pl) -> uint8_t* { return smem + s * Cfg::STAGE_BYTES + pl * Cfg::A_BYTES; };
+    auto stage_b = [&](int s, int pl) -> uint8_t* {
+        return smem + s * Cfg::STAGE_BYTES + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+    };
+
+    if (warp < 4) {
+        // ======================= A producers (gather) =======================
+        const int t = threadIdx.x;
+        const int chunk = t & 7;
+        const int rbase = t >> 3;  // rows rbase + 16*i
+        const uint32_t swz_off = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
+        int by[8], bx[8], ib[8];  // by < -30000 marks an invalid row
+        const int HgWg = p.Hg * p.Wg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int m = tile_m * kBM + rbase + 16 * i;
+            if (m < p.M) {
+                int n = m / HgWg;
+                int rem = m - n * HgWg;
+                int y = rem / p.Wg;
+                int x = rem - y * p.Wg;
+                by[i] = y * p.sy + cls.oy;
+                bx[i] = x * p.sx + cls.ox;
+                ib[i] = n * p.Hs * p.Ws;
+            } else {
+                by[i] = -1000000;
+                bx[i] = 0;
+                ib[i] = 0;
+            }
+        }
+        const int upt = p.Cs >> 2;
+        const int ntaps = p.TH * p.TW;
+        for (int j = 0; j < ksteps; ++j) {
+            const int s = j % STAGES;
+            const uint32_t ph = (j / STAGES) & 1;
+            mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 1);
+            const int u = j * 8 + chunk;
+            const int tap = u / upt;
+            const int cq = u - tap * upt;
+            const int a = tap / p.TW;
+            const int b = tap - a * p.TW;
+            const bool tap_ok = tap < ntaps;
+            const uint32_t a0 = smem_u32(stage_a(s, 0)) + swz_off;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int yy = by[i] + a;
+                const int xx = bx[i] + b;
+                const bool ok = tap_ok && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
+                const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 4) : 0;
+                const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 16 * i) * kRowBytes);
+                cp_async16(dsta, p.src + off, ok ? 16u : 0u);
+                if (NPL == 2) cp_async16(dsta + Cfg::A_BYTES, p.src + p.src_plane + off, ok ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (j >= LAG) {
+                cp_async_wait<LAG>();
+                fence_proxy_async_smem();
+                mbar_arrive(&full_bar[(j - LAG) % STAGES]);
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        for (int j = (ksteps > LAG ? ksteps - LAG : 0); j < ksteps; ++j) mbar_arrive(&full_bar[j % STAGES]);
+    } else if (warp == 4) {
+        // ======================= B producer (TMA) =======================
+        if (lane == 0) {
+            const int row0 = cls.wrow + tile_n * BN;
+            for (int j = 0; j < ksteps; ++j) {
+                const int s = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 2);
+                mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES);
+                tma_load_2d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * 32, row0);
+                if (NPL == 2) tma_load_2d(smem_u32(stage_b(s, 1)), &tmB1, &full_bar[s], j * 32, row0);
+            }
+        }
+    } else {
+        // ======================= MMA issuer =======================
+        constexpr uint32_t idesc = idesc_tf32(kBM, BN, 0, 0);
+        for (int j = 0; j < ksteps; ++j) {
+            const int s = j % STAGES;
+            const uint32_t ph = (j / STAGES) & 1;
+            mbar_wait_wd(&full_bar[s], ph, p.err, 3);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const int pa = (pass == 1) ? 1 : 0;
+                    const int pb = (pass == 2) ? 1 : 0;
+                    const uint32_t abase = smem_u32(stage_a(s, pa));
+                    const uint32_t bbase = smem_u32(stage_b(s, pb));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t ad = smem_desc_sw128(abase + kk * 32, 16, 1024);
+                        const uint64_t bd = smem_desc_sw128(bbase + kk * 32, 16, 1024);
+                        umma_tf32(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kk > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(accum_bar);
+        __syncwarp();
+    }
+
+    // ======================= epilogue (warps 0-3) =======================
+    if (warp < 4) {
+        mbar_wait_wd(accum_bar, 0, p.err, 4);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        uint8_t* stg = smem;  // pipeline buffers are free: every MMA has completed
+        {
+            float v[32];
+            if (BN >= 32) {
+#pragma unroll 1
+                for (int cc = 0; cc < BN / 32; ++cc) {
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 32, v);
+                    tmem_ld_wait();
+                    float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH + cc * 128);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            } else {
+                tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
+                tmem_ld_wait();
+                float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+
+        constexpr int QPR = BN / 4;  // float4 per row
+        const int t = threadIdx.x;
+        const int colq = t % QPR;
+        const int col = tile_n * BN + colq * 4;
+        const bool col_ok = col < p.Ncols;
+        const float alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int HgWg = p.Hg * p.Wg;
+        constexpr int ITERS = (kBM * QPR) / kProducerThreads;
+#pragma unroll 2
+        for (int it = 0; it < ITERS; ++it) {
+            const int e = t + it * kProducerThreads;
+            const int r = e / QPR;
+            const int m = tile_m * kBM + r;
+            if (m >= p.M || !col_ok) continue;
+            const int n = m / HgWg;
+            const int rem = m - n * HgWg;
+            const int y = rem / p.Wg;
+            const int x = rem - y * p.Wg;
+            const long long prow = (static_cast<long long>(n) * p.Hd + (y * p.osy + cls.ooy)) * p.Wd + (x * p.osx + cls.oox);
+            float4 v = *reinterpret_cast<const float4*>(stg + r * Cfg::PITCH + colq * 16);
+            v.x = apply_act(fmaf(v.x, alpha, bias4.x), p.act);
+            v.y = apply_act(fmaf(v.y, alpha, bias4.y), p.act);
+            v.z = apply_act(fmaf(v.z, alpha, bias4.z), p.act);
+            v.w = apply_act(fmaf(v.w, alpha, bias4.w), p.act);
+            if (p.aux) {
+                const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
+                const float4 a4 = *reinterpret_cast<const float4*>(p.aux + arow * p.Cd + col);
+                v.x *= act_grad_from_output(a4.x, p.aux_mode);
+                v.y *= act_grad_from_output(a4.y, p.aux_mode);
+                v.z *= act_grad_from_output(a4.z, p.aux_mode);
+                v.w *= act_grad_from_output(a4.w, p.aux_mode);
+            }
+            if (p.out_mode == 1) {
+                v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
+            }
+            float* o = p.dst + prow * p.Cd + col;
+            *reinterpret_cast<float4*>(o) = v;
+            if (p.out_mode == 0)
+                *reinterpret_cast<float4*>(o + p.dst_plane) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+            if (prow < p.colsum_rows) {
+                cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+                cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
+                cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
+            }
+        }
+        if (p.colsum) {
+            float4* red = reinterpret_cast<float4*>(smem + Cfg::STAGING_BYTES);
+            red[t] = cs;
+            red[kProducerThreads + t] = cq;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t < QPR && col_ok) {
+                float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = t; k < kProducerThreads; k += QPR) {
+                    const float4 a1 = red[k], a2 = red[kProducerThreads + k];
+                    s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+                    s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
+                }
+                const long long tl = static_cast<long long>(blockIdx.z) * gridDim.x + blockIdx.x;
+                *reinterpret_cast<float4*>(p.colsum + tl * p.Ncols + col) = s1;
+                if (p.colsumsq) *reinterpret_cast<float4*>(p.colsumsq + tl * p.Ncols + col) = s2;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr) return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2D fp32 tensor map [rows][cols] (cols contiguous), box {32 cols, box_rows}, 128-byte swizzle, zero OOB fill
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_stride_elems) * 4};
+    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <int BN, int NPASS>
+static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes,
+                      cudaStream_t st) {
+    using Cfg = GemmCfg<BN, NPASS>;
+    CUtensorMap t0, t1;
+    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, BN)) return -4;
+    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, BN)) return -4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+            cudaSuccess)
+            return -4;
+        attr_done = true;
+    }
+    dim3 grid((p.M + kBM - 1) / kBM, (p.Ncols + BN - 1) / BN, classes);
+    conv_gemm_kernel<BN, NPASS><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// w: [planes][w_rows][kpad]; w_rows = classes * rows_per_class (rows_per_class a multiple of the N tile)
+int launch_conv_gemm(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes,
+                     int bn, int npass, cudaStream_t st) {
+#define MG_CASE(B, N) \
+    if (bn == B && npass == N) return launch_cfg<B, N>(p, w, w_plane, w_rows, kpad, classes, st);
+    MG_CASE(16, 3) MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3)
+    MG_CASE(16, 1) MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1)
+#undef MG_CASE
+    return -1;
+}
+
+}  // namespace mg

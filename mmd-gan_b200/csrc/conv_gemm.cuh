@@ -1,0 +1,110 @@
+// Parameter blocks of the two tensor-core kernels (shared between the kernels and the C-ABI wrappers in api.cu).
+#pragma once
+#include <stdint.h>
+
+namespace mg {
+
+// One "class" of a gather-GEMM launch (blockIdx.z).  A k4/s2 transposed convolution is four classes, one per output
+// parity; everything else is one class.
+struct GemmClass {
+    int oy, ox;    // source pixel = (y*sy + a + oy, x*sx + b + ox) for tap (a, b)
+    int ooy, oox;  // destination pixel = (y*osy + ooy, x*osx + oox)
+    int wrow;      // first row of this class in the weight matrix
+    int pad0, pad1, pad2;
+};
+
+// D[m][n] = act(alpha * sum_k A[m][k] * Bw[n][k] + bias[n]) (* act'(aux[m][n])),  m = (img, y, x) on an Hg x Wg grid,
+// k = (tap, channel); A is gathered from an NHWC activation, Bw is a K-major weight matrix read by TMA.
+struct ConvGemmParams {
+    const float* src;      // [planes][Nimg*Hs*Ws][Cs]
+    long long src_plane;   // elements between the hi and lo plane
+    int Nimg, Hs, Ws, Cs;  // Cs multiple of 4
+    int Hg, Wg, sy, sx, TH, TW;
+    int M;       // Nimg*Hg*Wg
+    int ksteps;  // padded K / 32
+    float* dst;  // [planes][Nimg*Hd*Wd][Cd]
+    long long dst_plane;
+    int Hd, Wd, Cd, osy, osx;
+    int Ncols;               // valid output columns (multiple of 4)
+    float alpha_k;           // alpha = sigma ? alpha_k / *sigma : alpha_k
+    const float* sigma;
+    const float* bias;       // [Ncols] or null
+    int act;                 // 0 linear, 1 lrelu(0.1), 2 relu, 3 tanh
+    const float* aux;        // [rows][Cd] activation whose derivative multiplies the result, or null
+    int aux_mode;            // 1 lrelu', 2 relu', 3 tanh' (all evaluated from the layer OUTPUT)
+    long long aux_wrap_at;   // destination rows >= aux_wrap_at read aux at row - aux_wrap_len
+    long long aux_wrap_len;
+    float* colsum;           // [gridDim.x*gridDim.z][Ncols] per-tile column sums of the written values, or null
+    float* colsumsq;         // same for squares, or null
+    long long colsum_rows;   // only destination rows < colsum_rows are counted
+    int out_mode;            // 0: raw + lo plane, 1: rn-tf32 single plane, 2: raw single plane
+    unsigned int* err;       // device error flag (watchdog)
+    GemmClass cls[4];
+};
+
+// W[r][(t, c)] = sum_p P[p][r] * G[g(p, t)][c]:  P plain [pixels][Cp] (TMA, MN-major), G gathered NHWC activation.
+// blockIdx.z = split of the pixel range; every split writes its own partial tile.
+struct WgradParams {
+    const float* g;        // gathered activation [planes][Nimg*Hs*Ws][Cs]
+    long long g_plane;
+    int Nimg, Hs, Ws, Cs;
+    int Hg, Wg, sy, sx, TH, TW, oy, ox;   // pixel p = (img, y, x) on the plain operand's Hg x Wg grid
+    long long P;           // number of plain pixels = Nimg*Hg*Wg
+    long long p_per_split; // pixels per blockIdx.z (multiple of 32)
+    int Cp;                // plain channels (rows of the result)
+    int Ncols;             // TH*TW*Cs
+    float* out;            // [splits][Cp][Ncols]
+    unsigned int* err;
+};
+
+
+// mmd.cu
+struct MmdParams {
+    const float* gen_loc;   // [b][d]
+    const float* real_loc;  // [b][d]
+    const float* gen_all;   // [Bg][d]
+    const float* real_all;  // [Bg][d]
+    int b, Bg, row0, d;
+    int n_sigma;
+    float c_s[8];      // 1 / (2 sigma^2)
+    float cD[3];       // loss_dis = cD[0] e_gg^b + cD[1] e_gr^b + cD[2] e_rr^b
+    int bmode[3];      // 0 none, 1 lower bound (max), 2 upper bound (min)   [gg, gr, rr]
+    float bval[3];
+    float* sums;       // [6]  e_gg, e_gr, e_rr, e_gg^b, e_gr^b, e_rr^b over the LOCAL rows (already times 1/(Bg(Bg-1)))
+    float* losses;     // [2]  loss_gen, loss_dis from the local sums (the global losses when b == Bg)
+    float* dLg_dgen;   // [b][d]
+    float* dLg_dreal;  // [b][d] (may be null)
+    float* dLd_dgen;   // [b][d]
+    float* dLd_dreal;  // [b][d]
+    float* partials;   // [gridDim.x][6] workspace
+    unsigned int* counter;  // workspace, zero before the first launch; the kernel leaves it zero
+};
+
+// elementwise.cu
+// Canonical (reference) layouts: conv [k][k][Cin][Cout], transposed conv [k][k][Cout][Cin], dense [in][out].
+// Packed operand: [planes][classes*rows_pad][kpad], element (class, row, col) as documented per mode.
+struct PackParams {
+    const float* w;   // canonical
+    float* out;       // packed hi plane
+    long long plane;  // lo plane offset (0: single rn-tf32 plane)
+    int mode;         // PACK_* enum
+    int k;            // spatial kernel size
+    int Cin, Cout;    // of the layer op (dense: in / out features)
+    int Cs;           // channels per tap in the packed K index (>= source channels, multiple of 4)
+    int rows_pad, kpad, classes;
+    int in_C, in_HW, out_C, out_HW;  // dense only: NCHW-flatten <-> NHWC-flatten permutation of features
+};
+// Split-K weight-gradient partials [splits][R][NC] -> canonical layout, canon index = base + r*sr + t*st + c*sc with
+// column = t*Cg + c.  Also emits per-block partial <G, W> (for the spectral-norm term) when dots != null.
+struct WredParams {
+    const float* partials;
+    int splits, R, NC, Cg, Cvalid;   // channels c < Cvalid are real (Cg may be padded)
+    int Rvalid;                      // rows r < Rvalid are real (R may be padded)
+    int r_perm_C, r_perm_HW, c_perm_C, c_perm_HW;  // optional NHWC-flatten -> NCHW-flatten feature permutation (HW <= 1: none)
+    long long base, sr, st, sc;
+    const float* w;       // canonical weights (for the dot) or null
+    float* out;           // canonical gradient
+    double* dots;         // [gridDim.x] or null
+};
+
+}  // namespace mg

@@ -1,0 +1,437 @@
+// HBM-bound helper kernels of the SNGan step: layout changes at the boundary (NCHW <-> NHWC hi/lo planes), weight
+// packing into the GEMM operand layouts, batch-norm statistics / apply / backward, reductions of per-tile partial
+// sums (bias gradients, split-K weight gradients), the spectral-norm combine and the fused multi-tensor TF-Adam.
+// All reductions use fixed orders (no floating-point atomics) so a step is bit-reproducible run to run.
+//
+// Reference call sites replaced: tf.layers.batch_normalization (GeneralTools/layer_func.py:953-966),
+// tf.nn.bias_add gradients, SpectralNorm._l2_normalize_ (GeneralTools/math_func.py:653-659), the kernel * multiplier
+// product and its gradient (layer_func.py:884-918), tf.train.AdamOptimizer.apply_gradients (graph_func.py:525-526).
+#include "tc_common.cuh"
+#include "conv_gemm.cuh"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mg {
+
+static inline int nblocks(long long n, int bs) { return static_cast<int>((n + bs - 1) / bs); }
+
+// ------------------------------------------------------------------------------------------------ layout
+// src NCHW [N][C][H][W] -> dst planes [N][H][W][Cp] (channels >= C zero); lo plane at dst + plane (skipped if 0)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, long long plane, int N, int C, int H,
+                                    int W, int Cp) {
+    const long long total = static_cast<long long>(N) * H * W * Cp;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % Cp);
+        long long r = i / Cp;
+        const int w = static_cast<int>(r % W);
+        r /= W;
+        const int h = static_cast<int>(r % H);
+        const int n = static_cast<int>(r / H);
+        const float v = c < C ? src[((static_cast<long long>(n) * C + c) * H + h) * W + w] : 0.f;
+        dst[i] = v;
+        if (plane) dst[i + plane] = tf32_lo(v);
+    }
+}
+// src [N][H][W][Cp] (hi plane) -> dst NCHW [N][C][H][W]
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C, int H, int W, int Cp) {
+    const long long total = static_cast<long long>(N) * C * H * W;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int w = static_cast<int>(i % W);
+        long long r = i / W;
+        const int h = static_cast<int>(r % H);
+        r /= H;
+        const int c = static_cast<int>(r % C);
+        const int n = static_cast<int>(r / C);
+        dst[i] = src[((static_cast<long long>(n) * H + h) * W + w) * Cp + c];
+    }
+}
+__global__ void make_lo_plane_kernel(const float* __restrict__ hi, float* __restrict__ lo, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        lo[i] = tf32_lo(hi[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+enum { PACK_CONV_FWD = 0, PACK_CONV_DGRAD_S1 = 1, PACK_CONV_DGRAD_S2 = 2, PACK_TC_FWD = 3, PACK_TC_DGRAD = 4,
+       PACK_DENSE_FWD = 5, PACK_DENSE_DGRAD = 6 };
+
+__device__ __forceinline__ int perm_feature(int j, int C, int HW) {  // internal (hw*C + c) -> canonical (c*HW + hw)
+    if (HW <= 1) return j;
+    const int hw = j / C, c = j - hw * C;
+    return c * HW + hw;
+}
+
+__global__ void pack_weights_kernel(const PackParams p) {
+    const long long per_class = static_cast<long long>(p.rows_pad) * p.kpad;
+    const long long total = per_class * p.classes;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int cls = static_cast<int>(i / per_class);
+        const long long f = i - cls * per_class;
+        const int row = static_cast<int>(f / p.kpad);
+        const int col = static_cast<int>(f - static_cast<long long>(row) * p.kpad);
+        const int tap = col / p.Cs, ch = col - tap * p.Cs;
+        const int ph = cls >> 1, pw = cls & 1;
+        float v = 0.f;
+        switch (p.mode) {
+            case PACK_CONV_FWD: {  // row = co, col = (kh*k+kw)*Cs + ci
+                const int kh = tap / p.k, kw = tap - kh * p.k;
+                if (row < p.Cout && tap < p.k * p.k && ch < p.Cin)
+                    v = p.w[((static_cast<long long>(kh) * p.k + kw) * p.Cin + ch) * p.Cout + row];
+                break;
+            }
+            case PACK_CONV_DGRAD_S1: {  // row = ci, col = (a*k+b)*Cs + co, kh = k-1-a
+                const int a = tap / p.k, b = tap - a * p.k;
+                if (row < p.Cin && tap < p.k * p.k && ch < p.Cout)
+                    v = p.w[((static_cast<long long>(p.k - 1 - a) * p.k + (p.k - 1 - b)) * p.Cin + row) * p.Cout + ch];
+                break;
+            }
+            case PACK_CONV_DGRAD_S2: {  // k4 s2, class (ph,pw): row = ci, col = (a*2+b)*Cs + co, kh = 3-ph-2a
+                const int a = tap >> 1, b = tap & 1;
+                if (row < p.Cin && tap < 4 && ch < p.Cout)
+                    v = p.w[((static_cast<long long>(3 - ph - 2 * a) * 4 + (3 - pw - 2 * b)) * p.Cin + row) * p.Cout + ch];
+                break;
+            }
+            case PACK_TC_FWD: {  // canon [k][k][Cout][Cin], class (ph,pw): row = co, col = (a*2+b)*Cs + ci
+                const int a = tap >> 1, b = tap & 1;
+                if (row < p.Cout && tap < 4 && ch < p.Cin)
+                    v = p.w[((static_cast<long long>(3 - ph - 2 * a) * 4 + (3 - pw - 2 * b)) * p.Cout + row) * p.Cin + ch];
+                break;
+            }
+            case PACK_TC_DGRAD: {  // row = ci, col = (kh*k+kw)*Cs + co
+                const int kh = tap / p.k, kw = tap - kh * p.k;
+                if (row < p.Cin && tap < p.k * p.k && ch < p.Cout)
+                    v = p.w[((static_cast<long long>(kh) * p.k + kw) * p.Cout + ch) * p.Cin + row];
+                break;
+            }
+            case PACK_DENSE_FWD: {  // row = out', col = in'
+                if (row < p.Cout && col < p.Cin)
+                    v = p.w[static_cast<long long>(perm_feature(col, p.in_C, p.in_HW)) * p.Cout + perm_feature(row, p.out_C, p.out_HW)];
+                break;
+            }
+            case PACK_DENSE_DGRAD: {  // row = in', col = out'
+                if (row < p.Cin && col < p.Cout)
+                    v = p.w[static_cast<long long>(perm_feature(row, p.in_C, p.in_HW)) * p.Cout + perm_feature(col, p.out_C, p.out_HW)];
+                break;
+            }
+        }
+        if (p.plane) {
+            p.out[i] = v;
+            p.out[i + p.plane] = tf32_lo(v);
+        } else {
+            p.out[i] = tf32_rn(v);
+        }
+    }
+}
+
+// out[j'] = src[perm(j')]: canonical per-feature vector (bias / gamma / beta) -> internal NHWC-flatten order
+__global__ void permute_features_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int C, int HW, int inverse) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (inverse) dst[perm_feature(j, C, HW)] = src[j];
+    else dst[j] = src[perm_feature(j, C, HW)];
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+// out[c] (op)= scale * sum_t partials[t][C] over T tiles, accumulated in double in tile order
+__global__ void reduce_tiles_kernel(const float* __restrict__ partials, int T, int C, float scale, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int t = 0; t < T; ++t) s += static_cast<double>(partials[static_cast<long long>(t) * C + c]);
+    out[c] = static_cast<float>(s * scale);
+}
+// column sums of x[rows][C] (small matrices: score gradients)
+__global__ void colsum_small_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += static_cast<double>(x[static_cast<long long>(r) * C + c]);
+    out[c] = static_cast<float>(s);
+}
+
+__global__ void wgrad_reduce_kernel(const WredParams p) {
+    __shared__ double red[256];
+    const long long total = static_cast<long long>(p.R) * p.NC;
+    double dot = 0.0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / p.NC);
+        const int col = static_cast<int>(i - static_cast<long long>(r) * p.NC);
+        const int t = col / p.Cg, c = col - t * p.Cg;
+        if (c >= p.Cvalid || r >= p.Rvalid) continue;
+        float s = 0.f;
+        for (int z = 0; z < p.splits; ++z) s += p.partials[static_cast<long long>(z) * total + i];
+        const long long ci = p.base + perm_feature(r, p.r_perm_C, p.r_perm_HW) * p.sr + t * p.st +
+                             perm_feature(c, p.c_perm_C, p.c_perm_HW) * p.sc;
+        p.out[ci] = s;
+        if (p.w) dot += static_cast<double>(s) * static_cast<double>(p.w[ci]);
+    }
+    if (p.dots) {
+        red[threadIdx.x] = dot;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) p.dots[blockIdx.x] = red[0];
+    }
+}
+// grad = m * G - (m / sigma) * <G, W> * S,  m = act_k / sigma  (layer_func.py:884-918 differentiated)
+__global__ void sn_grad_combine_kernel(float* __restrict__ g, const float* __restrict__ s, const double* __restrict__ dots, int ndots,
+                                       const float* __restrict__ sigma, float act_k, long long n) {
+    __shared__ double dsum;
+    if (threadIdx.x == 0) {
+        double d = 0.0;
+        for (int i = 0; i < ndots; ++i) d += dots[i];
+        dsum = d;
+    }
+    __syncthreads();
+    const float sg = *sigma;
+    const float m = act_k / sg;
+    const float coef = static_cast<float>(static_cast<double>(m) / static_cast<double>(sg) * dsum);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        g[i] = m * g[i] - coef * s[i];
+}
+__global__ void scale_by_sigma_kernel(float* __restrict__ g, const float* __restrict__ sigma, float act_k, long long n) {
+    const float m = act_k / *sigma;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        g[i] *= m;
+}
+
+// ------------------------------------------------------------------------------------------------ spectral norm
+// sigma = ||v||, out planes = v / (sigma + eps); one block (v has at most a few 10^4 elements)
+__global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, float eps, float* __restrict__ sigma_out,
+                                    float* __restrict__ out, long long plane) {
+    __shared__ double red[1024];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += static_cast<double>(v[i]) * static_cast<double>(v[i]);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const float nrm = static_cast<float>(sqrt(red[0]));
+    if (threadIdx.x == 0 && sigma_out) *sigma_out = nrm;
+    const float inv = 1.0f / (nrm + eps);
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float y = v[i] * inv;
+        out[i] = y;
+        if (plane) out[i + plane] = tf32_lo(y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ batch norm
+// statistics from per-tile partial sums; moving stats as tf.layers.batch_normalization(fused=True): biased variance
+// normalises, the Bessel-corrected one feeds the moving average (momentum 0.99)
+__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int T, int C, long long rows, float eps,
+                                   float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int t = 0; t < T; ++t) {
+        s += static_cast<double>(psum[static_cast<long long>(t) * C + c]);
+        q += static_cast<double>(psq[static_cast<long long>(t) * C + c]);
+    }
+    const double mu = s / rows;
+    double var = q / rows - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[c] = static_cast<float>(mu);
+    invstd[c] = static_cast<float>(1.0 / sqrt(var + eps));
+    if (moving_mean) {
+        const double var_u = rows > 1 ? var * (static_cast<double>(rows) / (rows - 1)) : var;
+        moving_mean[c] = moving_mean[c] * momentum + static_cast<float>(mu) * (1.0f - momentum);
+        moving_var[c] = moving_var[c] * momentum + static_cast<float>(var_u) * (1.0f - momentum);
+    }
+}
+// a = act(gamma * (z - mean) * invstd + beta) -> hi/lo planes; z [rows][C] raw
+__global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int C, long long total, int act,
+                                float* __restrict__ out, long long plane) {
+    for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+        const int c = static_cast<int>(i % C);
+        const float4 zv = *reinterpret_cast<const float4*>(z + i);
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+        float4 y;
+        y.x = fmaf((zv.x - mu.x) * is.x, g.x, b.x);
+        y.y = fmaf((zv.y - mu.y) * is.y, g.y, b.y);
+        y.z = fmaf((zv.z - mu.z) * is.z, g.z, b.z);
+        y.w = fmaf((zv.w - mu.w) * is.w, g.w, b.w);
+        if (act == 2) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        *reinterpret_cast<float4*>(out + i) = y;
+        if (plane) *reinterpret_cast<float4*>(out + i + plane) = make_float4(tf32_lo(y.x), tf32_lo(y.y), tf32_lo(y.z), tf32_lo(y.w));
+    }
+}
+// per-block partial sums of dy and dy*xhat per channel; dy = da * act'(bn output); block handles a row slab
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     int C, long long rows, int rows_per_block, int act, float* __restrict__ psum,
+                                     float* __restrict__ psumx) {
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float mu = mean[c], is = invstd[c], g = gamma[c], b = beta[c];
+        float s = 0.f, sx = 0.f;
+        for (long long r = r0; r < r1; ++r) {
+            const float xh = (z[r * C + c] - mu) * is;
+            float dy = da[r * C + c];
+            if (act == 2 && fmaf(xh, g, b) <= 0.f) dy = 0.f;
+            s += dy;
+            sx = fmaf(dy, xh, sx);
+        }
+        psum[static_cast<long long>(blockIdx.x) * C + c] = s;
+        psumx[static_cast<long long>(blockIdx.x) * C + c] = sx;
+    }
+}
+// dz = gamma * invstd * (dy - mean(dy) - xhat * mean(dy*xhat)) -> hi/lo planes
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ dbeta, const float* __restrict__ dgamma, int C, long long rows, int act,
+                                    float* __restrict__ out, long long plane) {
+    const long long total = rows * C;
+    const float inv_rows = 1.0f / static_cast<float>(rows);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const float is = invstd[c], g = gamma[c];
+        const float xh = (z[i] - mean[c]) * is;
+        float dy = da[i];
+        if (act == 2 && fmaf(xh, g, beta[c]) <= 0.f) dy = 0.f;
+        const float v = g * is * (dy - dbeta[c] * inv_rows - xh * dgamma[c] * inv_rows);
+        out[i] = v;
+        if (plane) out[i + plane] = tf32_lo(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// tf.train.AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; theta -= lr_t*m/(sqrt(v)+eps).
+// step_ptr holds t (already incremented for this update) so that a captured CUDA graph can be replayed.
+__global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, long long n,
+                            float lr, float b1, float b2, float eps, const int* __restrict__ step_ptr) {
+    const double t = static_cast<double>(*step_ptr);
+    const float lr_t = static_cast<float>(static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(b2), t)) /
+                                          (1.0 - pow(static_cast<double>(b1), t)));
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+__global__ void incr_step_kernel(int* step) { *step += 1; }
+// sets flag[0] = 1 if any of the n values is NaN (the reference's per-step host assert, graph_func.py:856, kept on device)
+__global__ void nan_flag_kernel(const float* __restrict__ x, int n, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && isnan(x[i])) atomicExch(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static const int kBS = 256;
+static inline int grid_for(long long n) {
+    long long g = (n + kBS - 1) / kBS;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+#define MG_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : -4)
+
+int l_nchw_to_nhwc(const float* src, float* dst, long long plane, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+    nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(N) * H * W * Cp), kBS, 0, st>>>(src, dst, plane, N, C, H, W, Cp);
+    return MG_CHECK_LAUNCH();
+}
+int l_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+    nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * C * H * W), kBS, 0, st>>>(src, dst, N, C, H, W, Cp);
+    return MG_CHECK_LAUNCH();
+}
+int l_make_lo_plane(const float* hi, float* lo, long long n, cudaStream_t st) {
+    make_lo_plane_kernel<<<grid_for(n), kBS, 0, st>>>(hi, lo, n);
+    return MG_CHECK_LAUNCH();
+}
+int l_pack_weights(const PackParams& p, cudaStream_t st) {
+    pack_weights_kernel<<<grid_for(static_cast<long long>(p.rows_pad) * p.kpad * p.classes), kBS, 0, st>>>(p);
+    return MG_CHECK_LAUNCH();
+}
+int l_permute_features(const float* src, float* dst, int n, int C, int HW, int inverse, cudaStream_t st) {
+    permute_features_kernel<<<nblocks(n, kBS), kBS, 0, st>>>(src, dst, n, C, HW, inverse);
+    return MG_CHECK_LAUNCH();
+}
+int l_reduce_tiles(const float* partials, int T, int C, float scale, float* out, cudaStream_t st) {
+    reduce_tiles_kernel<<<nblocks(C, 128), 128, 0, st>>>(partials, T, C, scale, out);
+    return MG_CHECK_LAUNCH();
+}
+int l_colsum_small(const float* x, int rows, int C, float* out, cudaStream_t st) {
+    colsum_small_kernel<<<nblocks(C, 128), 128, 0, st>>>(x, rows, C, out);
+    return MG_CHECK_LAUNCH();
+}
+int wgrad_reduce_blocks(long long total) {
+    long long g = (total + 256 * 8 - 1) / (256 * 8);
+    if (g > 1024) g = 1024;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+int l_wgrad_reduce(const WredParams& p, cudaStream_t st) {
+    wgrad_reduce_kernel<<<wgrad_reduce_blocks(static_cast<long long>(p.R) * p.NC), 256, 0, st>>>(p);
+    return MG_CHECK_LAUNCH();
+}
+int l_sn_grad_combine(float* g, const float* s, const double* dots, int ndots, const float* sigma, float act_k, long long n,
+                      cudaStream_t st) {
+    sn_grad_combine_kernel<<<grid_for(n), kBS, 0, st>>>(g, s, dots, ndots, sigma, act_k, n);
+    return MG_CHECK_LAUNCH();
+}
+int l_scale_by_sigma(float* g, const float* sigma, float act_k, long long n, cudaStream_t st) {
+    scale_by_sigma_kernel<<<grid_for(n), kBS, 0, st>>>(g, sigma, act_k, n);
+    return MG_CHECK_LAUNCH();
+}
+int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, float* out, long long plane, cudaStream_t st) {
+    sn_normalize_kernel<<<1, 1024, 0, st>>>(v, n, eps, sigma_out, out, plane);
+    return MG_CHECK_LAUNCH();
+}
+int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
+                  float* invstd, float* mm, float* mv, cudaStream_t st) {
+    bn_finalize_kernel<<<nblocks(C, 128), 128, 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv);
+    return MG_CHECK_LAUNCH();
+}
+int l_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C, long long total,
+               int act, float* out, long long plane, cudaStream_t st) {
+    bn_apply_kernel<<<grid_for(total / 4), kBS, 0, st>>>(z, mean, invstd, gamma, beta, C, total, act, out, plane);
+    return MG_CHECK_LAUNCH();
+}
+int l_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    int C, long long rows, int rows_per_block, int act, float* psum, float* psumx, cudaStream_t st) {
+    const int blocks = static_cast<int>((rows + rows_per_block - 1) / rows_per_block);
+    bn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, C, rows, rows_per_block, act, psum, psumx);
+    return MG_CHECK_LAUNCH();
+}
+int l_bn_bwd_apply(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                   const float* dbeta, const float* dgamma, int C, long long rows, int act, float* out, long long plane,
+                   cudaStream_t st) {
+    bn_bwd_apply_kernel<<<grid_for(rows * C), kBS, 0, st>>>(da, z, mean, invstd, gamma, beta, dbeta, dgamma, C, rows, act, out, plane);
+    return MG_CHECK_LAUNCH();
+}
+int l_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float b1, float b2, float eps, const int* step,
+           cudaStream_t st) {
+    adam_kernel<<<grid_for(n), kBS, 0, st>>>(w, m, v, g, n, lr, b1, b2, eps, step);
+    return MG_CHECK_LAUNCH();
+}
+int l_incr_step(int* step, cudaStream_t st) {
+    incr_step_kernel<<<1, 1, 0, st>>>(step);
+    return MG_CHECK_LAUNCH();
+}
+int l_nan_flag(const float* x, int n, int* flag, cudaStream_t st) {
+    nan_flag_kernel<<<nblocks(n, 128), 128, 0, st>>>(x, n, flag);
+    return MG_CHECK_LAUNCH();
+}
+
+}  // namespace mg

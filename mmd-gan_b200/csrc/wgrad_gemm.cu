@@ -1,0 +1,281 @@
+// Weight-gradient GEMM on the sm_100a tensor cores (contraction over pixels, split over blockIdx.z).
+//
+//   W[r][(t, c)] = sum_p P[p][r] * G[g(p, t)][c]
+//
+// P is a plain [pixels][Cp] activation / gradient matrix, G an NHWC activation gathered tap by tap.  With NHWC
+// storage the contracted dimension (pixels) is the strided one, so BOTH operands are MN-major: P tiles are staged by
+// TMA (32 pixels x 32 channels boxes, 128-byte swizzle), G tiles by 16-byte cp.async with the same swizzle, and the
+// tcgen05.mma instruction descriptor carries the two transpose bits.  NPASS == 3 is the fp32-grade tf32x3 mode.
+// Every split writes its own partial tile; the reduction over splits is fused into the gradient-finalise kernel.
+//
+// Replaces the filter gradients TF derives for tf.nn.conv2d / conv2d_transpose / matmul
+// (DeepLearning/my_sngan.py:301-304) and the d(sigma)/dW term of SpectralNorm (GeneralTools/math_func.py:661-672).
+#include "conv_gemm.cuh"
+#include "tc_common.cuh"
+#include <stdio.h>
+
+namespace mg {
+
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows);
+
+static constexpr int kWBM = 128;
+static constexpr int kWProducers = 128;
+static constexpr int kWThreads = 192;
+static constexpr unsigned long long kWWatchdogNs = 4000000000ull;
+
+__device__ __forceinline__ unsigned long long w_gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void w_mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned code) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = w_gtime_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (w_gtime_ns() - t0 > kWWatchdogNs) {
+            if (err) atomicExch(err, code);
+            printf("mmdgan: wgrad mbarrier watchdog (code %u) block (%d,%d,%d) thread %d\n", code, blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+template <int BN, int NPASS>
+struct WgradCfg {
+    static constexpr int NPL = (NPASS == 3) ? 2 : 1;
+    static constexpr int A_BYTES = 4 * 4096;          // 4 channel chunks x (32 pixels x 128 B)
+    static constexpr int B_BYTES = (BN / 32) * 4096;  // BN/32 column chunks x (32 pixels x 128 B)
+    static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+    static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
+                  const __grid_constant__ WgradParams p) {
+    using Cfg = WgradCfg<BN, NPASS>;
+    constexpr int NPL = Cfg::NPL;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int LAG = Cfg::LAG;
+    constexpr int NCH = BN / 32;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* accum_bar = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x;
+    const int tile_n = blockIdx.y;
+    const long long p_begin = static_cast<long long>(blockIdx.z) * p.p_per_split;
+    long long p_end = p_begin + p.p_per_split;
+    if (p_end > p.P) p_end = p.P;
+    const int ksteps = p_end > p_begin ? static_cast<int>((p_end - p_begin + 31) / 32) : 0;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmP0);
+        if (NPL == 2) tma_prefetch_desc(&tmP1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], kWProducers + 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto stage_a = [&](int s, int pl) -> uint8_t* { return smem + s * Cfg::STAGE_BYTES + pl * Cfg::A_BYTES; };
+    auto stage_b = [&](int s, int pl) -> uint8_t* {
+        return smem + s * Cfg::STAGE_BYTES + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+    };
+
+    if (warp < 4) {
+        // ======================= G producers (gather, MN-major) =======================
+        const int t = threadIdx.x;
+        const int chunk = t & 7;
+        const int rbase = t >> 3;  // pixel rows rbase, rbase + 16 of the k-step
+        const int upt = p.Cs >> 2;
+        const int ntaps = p.TH * p.TW;
+        int ta[NCH], tb[NCH], tcq[NCH];
+        bool tok[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            const int u = (tile_n * NCH + q) * 8 + chunk;
+            const int tap = u / upt;
+            tcq[q] = u - tap * upt;
+            ta[q] = tap / p.TW;
+            tb[q] = tap - ta[q] * p.TW;
+            tok[q] = tap < ntaps;
+        }
+        const int HgWg = p.Hg * p.Wg;
+        for (int j = 0; j < ksteps; ++j) {
+            const int s = j % STAGES;
+            const uint32_t ph = (j / STAGES) & 1;
+            w_mbar_wait(&empty_bar[s], ph ^ 1, p.err, 11);
+            const uint32_t b0 = smem_u32(stage_b(s, 0));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = rbase + 16 * i;
+                const long long pp = p_begin + static_cast<long long>(j) * 32 + r;
+                const bool pok = pp < p_end;
+                int n = 0, y = 0, x = 0;
+                if (pok) {
+                    n = static_cast<int>(pp / HgWg);
+                    const int rem = static_cast<int>(pp - static_cast<long long>(n) * HgWg);
+                    y = rem / p.Wg;
+                    x = rem - y * p.Wg;
+                }
+                const int by = y * p.sy + p.oy;
+                const int bx = x * p.sx + p.ox;
+                const uint32_t drow = b0 + static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    const int yy = by + ta[q];
+                    const int xx = bx + tb[q];
+                    const bool ok = pok && tok[q] && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
+                    const long long off =
+                        ok ? (static_cast<long long>(n * p.Hs * p.Ws + yy * p.Ws + xx) * p.Cs + tcq[q] * 4) : 0;
+                    cp_async16(drow + q * 4096, p.g + off, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async16(drow + q * 4096 + Cfg::B_BYTES, p.g + p.g_plane + off, ok ? 16u : 0u);
+                }
+            }
+            cp_async_commit();
+            if (j >= LAG) {
+                cp_async_wait<LAG>();
+                fence_proxy_async_smem();
+                mbar_arrive(&full_bar[(j - LAG) % STAGES]);
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        for (int j = (ksteps > LAG ? ksteps - LAG : 0); j < ksteps; ++j) mbar_arrive(&full_bar[j % STAGES]);
+    } else if (warp == 4) {
+        // ======================= P producer (TMA, MN-major) =======================
+        if (lane == 0) {
+            for (int j = 0; j < ksteps; ++j) {
+                const int s = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                w_mbar_wait(&empty_bar[s], ph ^ 1, p.err, 12);
+                mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::A_BYTES);
+                const int prow = static_cast<int>(p_begin + static_cast<long long>(j) * 32);
+#pragma unroll
+                for (int mc = 0; mc < 4; ++mc) {
+                    tma_load_2d(smem_u32(stage_a(s, 0)) + mc * 4096, &tmP0, &full_bar[s], tile_m * kWBM + mc * 32, prow);
+                    if (NPL == 2)
+                        tma_load_2d(smem_u32(stage_a(s, 1)) + mc * 4096, &tmP1, &full_bar[s], tile_m * kWBM + mc * 32, prow);
+                }
+            }
+        }
+    } else {
+        // ======================= MMA issuer =======================
+        constexpr uint32_t idesc = idesc_tf32(kWBM, BN, 1, 1);
+        for (int j = 0; j < ksteps; ++j) {
+            const int s = j % STAGES;
+            const uint32_t ph = (j / STAGES) & 1;
+            w_mbar_wait(&full_bar[s], ph, p.err, 13);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const int pa = (pass == 1) ? 1 : 0;
+                    const int pb = (pass == 2) ? 1 : 0;
+                    const uint32_t abase = smem_u32(stage_a(s, pa));
+                    const uint32_t bbase = smem_u32(stage_b(s, pb));
+#pragma unroll
+                    for (int kg = 0; kg < 4; ++kg) {
+                        const uint64_t ad = smem_desc_sw128(abase + kg * 1024, 4096, 1024);
+                        const uint64_t bd = smem_desc_sw128(bbase + kg * 1024, 4096, 1024);
+                        umma_tf32(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kg > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(accum_bar);
+        __syncwarp();
+    }
+
+    // ======================= epilogue: partial tile -> global =======================
+    if (warp < 4) {
+        const int r_out = tile_m * kWBM + warp * 32 + lane;
+        float* orow = p.out + (static_cast<long long>(blockIdx.z) * p.Cp + r_out) * p.Ncols;
+        if (ksteps > 0) {
+            w_mbar_wait(accum_bar, 0, p.err, 14);
+            tc_fence_after();
+        }
+        float v[32];
+#pragma unroll 1
+        for (int cc = 0; cc < NCH; ++cc) {
+            if (ksteps > 0) {
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = 0.f;
+            }
+            const int col0 = tile_n * BN + cc * 32;
+            if (r_out < p.Cp) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int col = col0 + q * 4;
+                    if (col < p.Ncols)
+                        *reinterpret_cast<float4*>(orow + col) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int BN, int NPASS>
+static int launch_wcfg(const WgradParams& p, const float* plain, long long plain_plane, int splits, cudaStream_t st) {
+    using Cfg = WgradCfg<BN, NPASS>;
+    CUtensorMap t0, t1;
+    if (make_tmap_2d(&t0, plain, p.P, p.Cp, p.Cp, 32)) return -4;
+    if (make_tmap_2d(&t1, plain + (NPASS == 3 ? plain_plane : 0), p.P, p.Cp, p.Cp, 32)) return -4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(wgrad_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+            cudaSuccess)
+            return -4;
+        attr_done = true;
+    }
+    dim3 grid((p.Cp + kWBM - 1) / kWBM, (p.Ncols + BN - 1) / BN, splits);
+    wgrad_gemm_kernel<BN, NPASS><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+int launch_wgrad_gemm(const WgradParams& p, const float* plain, long long plain_plane, int splits, int bn, int npass,
+                      cudaStream_t st) {
+#define MG_CASE(B, N) \
+    if (bn == B && npass == N) return launch_wcfg<B, N>(p, plain, plain_plane, splits, st);
+    MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3)
+    MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1)
+#undef MG_CASE
+    return -1;
+}
+
+}  // namespace mg

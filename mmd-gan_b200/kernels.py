@@ -1,0 +1,390 @@
+"""Torch-tensor level wrappers over the C ABI (include/mmdgan_b200.h): device memory and streams come from PyTorch,
+every computation is a kernel of libmmdgan_b200.so.  No fallback: a missing library or a non-CUDA tensor raises.
+
+Activation tensors ("planes") are [npl, rows, C] float32 CUDA tensors, NHWC row order, npl = 2 for the tf32x3
+(fp32-grade) mode and 1 for plain tf32; see the header for the hi/lo plane format.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, WgradDesc, WredDesc, PackDesc, MmdDesc, check
+
+ACT = {'linear': 0, None: 0, 'lrelu': 1, 'relu': 2, 'tanh': 3}
+PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRAD, PACK_DENSE_FWD, PACK_DENSE_DGRAD = range(7)
+
+
+def lib():
+    return _lib.load()
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32):
+        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32 tensor, got {} on {}'.format(t.dtype, t.device))
+    if not t.is_contiguous():
+        raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'tensor must be contiguous')
+    return C.c_void_p(t.data_ptr())
+
+
+def plane_stride(t):
+    return t.stride(0) if t.shape[0] == 2 else 0
+
+
+def pad4(c):
+    return (c + 3) // 4 * 4
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def pick_bn(ncols, lo=16):
+    bn = lo
+    while bn < 128 and bn < ncols:
+        bn *= 2
+    return bn
+
+
+def new_planes(rows, c, npass=3, device='cuda'):
+    return torch.zeros((2 if npass == 3 else 1, rows, c), dtype=torch.float32, device=device)
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def nchw_to_planes(x, dst, npass=3):
+    """x [N,C,H,W] (or [N,F]) -> dst planes [npl, N*H*W, Cpad]."""
+    if x.dim() == 2:
+        n, c = x.shape
+        h = w = 1
+    else:
+        n, c, h, w = x.shape
+    check(lib().mmdgan_nchw_to_nhwc(_ptr(x), _ptr(dst), plane_stride(dst) if npass == 3 else 0, n, c, h, w, dst.shape[2], stream()))
+    return dst
+
+
+def planes_to_nchw(src, n, c, h, w):
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
+    check(lib().mmdgan_nhwc_to_nchw(_ptr(src), _ptr(out), n, c, h, w, src.shape[2], stream()))
+    return out
+
+
+def make_lo_plane(t):
+    if t.shape[0] == 2:
+        check(lib().mmdgan_make_lo_plane(_ptr(t[0]), _ptr(t[1]), t[0].numel(), stream()))
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ linear ops
+class LinearOp(object):
+    """One parametric op of the layer DSL ('d' / 'c' / 'tc', GeneralTools/layer_func.py:909-928) lowered to the
+    gather-GEMM (forward, input gradient) and weight-gradient GEMM launches.
+
+    in_shape / out_shape are the reference's per-sample NCHW shapes ([F] or [C,H,W]).  in_flat / out_flat = (C, HW)
+    say that a dense layer's features are a flattened NCHW tensor whose internal storage is NHWC (the reshape at
+    my_test_cifar.py:15 / :36), so the feature permutation is folded into the packed weights.
+    """
+
+    def __init__(self, op, in_shape, out_shape, kernel=3, strides=1, npass=3, in_flat=None, out_flat=None, device='cuda'):
+        self.op, self.k, self.s, self.npass, self.device = op, kernel, strides, npass, device
+        self.npl = 2 if npass == 3 else 1
+        if op == 'd':
+            self.Cin, self.Cout = in_shape[0], out_shape[0]
+            self.Hin = self.Win = self.Hout = self.Wout = 1
+            self.in_flat = in_flat or (self.Cin, 1)
+            self.out_flat = out_flat or (self.Cout, 1)
+        elif op in ('c', 'tc'):
+            self.Cin, self.Hin, self.Win = in_shape
+            self.Cout, self.Hout, self.Wout = out_shape
+            if not ((kernel == 3 and strides == 1) or (kernel == 4 and strides == 2)) or (op == 'tc' and strides != 2):
+                raise NotImplementedError('{}: kernel {} / strides {} is not on the hot path'.format(op, kernel, strides))
+            if op == 'c':
+                assert self.Hout * strides == self.Hin and self.Wout * strides == self.Win
+            else:
+                assert self.Hin * strides == self.Hout and self.Win * strides == self.Wout
+        else:
+            raise AttributeError('layer op {} not supported.'.format(op))
+        self.Cs_in, self.Cs_out = pad4(self.Cin), pad4(self.Cout)
+        self.pad = 1 if op != 'd' else 0
+        k = kernel
+        # ---- forward / dgrad operand geometry
+        if op == 'd':
+            self.f = dict(mode=PACK_DENSE_FWD, classes=1, taps=1, Cs=self.Cs_in, ncols=self.Cs_out)
+            self.d = dict(mode=PACK_DENSE_DGRAD, classes=1, taps=1, Cs=self.Cs_out, ncols=self.Cs_in)
+        elif op == 'c':
+            self.f = dict(mode=PACK_CONV_FWD, classes=1, taps=k * k, Cs=self.Cs_in, ncols=self.Cs_out)
+            if strides == 1:
+                self.d = dict(mode=PACK_CONV_DGRAD_S1, classes=1, taps=k * k, Cs=self.Cs_out, ncols=self.Cs_in)
+            else:
+                self.d = dict(mode=PACK_CONV_DGRAD_S2, classes=4, taps=4, Cs=self.Cs_out, ncols=self.Cs_in)
+        else:
+            self.f = dict(mode=PACK_TC_FWD, classes=4, taps=4, Cs=self.Cs_in, ncols=self.Cs_out)
+            self.d = dict(mode=PACK_TC_DGRAD, classes=1, taps=k * k, Cs=self.Cs_out, ncols=self.Cs_in)
+        for g in (self.f, self.d):
+            g['bn'] = pick_bn(g['ncols'])
+            g['rows_pad'] = round_up(g['ncols'], g['bn'])
+            g['kpad'] = round_up(g['taps'] * g['Cs'], 32)
+            g['w'] = torch.zeros((self.npl, g['classes'] * g['rows_pad'], g['kpad']), dtype=torch.float32, device=device)
+        # ---- weight-gradient orientation: the small channel count goes to the N side
+        if op == 'd':
+            self.w_swapped = self.Cs_out < 32
+        elif op == 'c':
+            self.w_swapped = (self.Cs_out < 32 and strides == 1)
+        else:
+            self.w_swapped = False
+        self.canon_shape = ([self.Cin, self.Cout] if op == 'd' else
+                            [k, k, self.Cin, self.Cout] if op == 'c' else [k, k, self.Cout, self.Cin])
+        self.canon_numel = int(math.prod(self.canon_shape))
+
+    # -------------------------------------------------------------------------------------------- packing
+    def pack(self, w_canon):
+        """canonical weights -> forward and input-gradient GEMM operands (unscaled; act_k / sigma is an epilogue alpha)."""
+        for g in (self.f, self.d):
+            d = PackDesc()
+            d.w, d.out = _ptr(w_canon), _ptr(g['w'])
+            d.plane = plane_stride(g['w'])
+            d.mode, d.k, d.Cin, d.Cout, d.Cs = g['mode'], self.k, self.Cin, self.Cout, g['Cs']
+            d.rows_pad, d.kpad, d.classes = g['rows_pad'], g['kpad'], g['classes']
+            if self.op == 'd':
+                d.in_C, d.in_HW = self.in_flat
+                d.out_C, d.out_HW = self.out_flat
+            else:
+                d.in_C = d.in_HW = d.out_C = d.out_HW = 1
+            check(lib().mmdgan_pack_weights(C.byref(d), stream()))
+
+    # -------------------------------------------------------------------------------------------- GEMM launches
+    def _gemm(self, g, src, nimg, dst, geom, sigma, alpha_k, bias, act, aux, aux_mode, aux_wrap, colsum, colsumsq,
+              colsum_rows, out_mode):
+        d = GemmDesc()
+        d.src, d.src_plane = _ptr(src), plane_stride(src)
+        d.Nimg = nimg
+        (d.Hs, d.Ws, d.Hg, d.Wg, d.sy, d.sx, d.TH, d.TW, d.Hd, d.Wd, d.osy, d.osx) = geom['dims']
+        d.Cs = g['Cs']
+        assert src.shape[2] == g['Cs'], 'source channels {} != {}'.format(src.shape[2], g['Cs'])
+        assert src.shape[1] >= nimg * d.Hs * d.Ws
+        d.w, d.w_plane, d.w_rows = _ptr(g['w']), plane_stride(g['w']), g['w'].shape[1]
+        d.kpad, d.classes = g['kpad'], g['classes']
+        d.dst, d.dst_plane = _ptr(dst), plane_stride(dst)
+        d.Cd, d.Ncols = dst.shape[2], g['ncols']
+        assert dst.shape[1] >= nimg * d.Hd * d.Wd and dst.shape[2] >= g['ncols']
+        d.alpha_k = float(alpha_k)
+        d.sigma, d.bias, d.act = _ptr(sigma), _ptr(bias), act
+        d.aux, d.aux_mode = _ptr(aux), aux_mode
+        d.aux_wrap_at, d.aux_wrap_len = aux_wrap if aux_wrap else (0, 0)
+        d.colsum, d.colsumsq, d.colsum_rows = _ptr(colsum), _ptr(colsumsq), colsum_rows
+        d.out_mode, d.bn, d.npass = out_mode, g['bn'], self.npass
+        if out_mode == 0 and dst.shape[0] != 2:
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 needs a two-plane destination')
+        for i, (oy, ox, ooy, oox) in enumerate(geom['cls']):
+            d.cls[i].oy, d.cls[i].ox, d.cls[i].ooy, d.cls[i].oox = oy, ox, ooy, oox
+            d.cls[i].wrow = i * g['rows_pad']
+        check(lib().mmdgan_gather_gemm(C.byref(d), stream()))
+
+    def _fwd_geom(self):
+        if self.op == 'd':
+            return dict(dims=(1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1), cls=[(0, 0, 0, 0)])
+        if self.op == 'c':
+            return dict(dims=(self.Hin, self.Win, self.Hout, self.Wout, self.s, self.s, self.k, self.k, self.Hout, self.Wout, 1, 1),
+                        cls=[(-self.pad, -self.pad, 0, 0)])
+        return dict(dims=(self.Hin, self.Win, self.Hin, self.Win, 1, 1, 2, 2, self.Hout, self.Wout, 2, 2),
+                    cls=[(ph - 1, pw - 1, ph, pw) for ph in (0, 1) for pw in (0, 1)])
+
+    def _dgrad_geom(self):
+        if self.op == 'd':
+            return dict(dims=(1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1), cls=[(0, 0, 0, 0)])
+        if self.op == 'c' and self.s == 1:
+            o = -(self.k - 1 - self.pad)
+            return dict(dims=(self.Hout, self.Wout, self.Hin, self.Win, 1, 1, self.k, self.k, self.Hin, self.Win, 1, 1),
+                        cls=[(o, o, 0, 0)])
+        if self.op == 'c':
+            return dict(dims=(self.Hout, self.Wout, self.Hout, self.Wout, 1, 1, 2, 2, self.Hin, self.Win, 2, 2),
+                        cls=[(ph - 1, pw - 1, ph, pw) for ph in (0, 1) for pw in (0, 1)])
+        return dict(dims=(self.Hout, self.Wout, self.Hin, self.Win, 2, 2, 4, 4, self.Hin, self.Win, 1, 1), cls=[(-1, -1, 0, 0)])
+
+    def fwd_tiles(self, nimg):
+        g = self._fwd_geom()['dims']
+        return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.f['classes']
+
+    def dgrad_tiles(self, nimg):
+        g = self._dgrad_geom()['dims']
+        return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.d['classes']
+
+    def forward(self, src, nimg, dst, sigma=None, alpha_k=1.0, bias=None, act=0, colsum=None, colsumsq=None, out_mode=0):
+        self._gemm(self.f, src, nimg, dst, self._fwd_geom(), sigma, alpha_k, bias, act, None, 0, None, colsum, colsumsq, 0, out_mode)
+
+    def dgrad(self, dy, nimg, dst, sigma=None, alpha_k=1.0, aux=None, aux_mode=0, aux_wrap=None, colsum=None, colsum_rows=0,
+              out_mode=0):
+        self._gemm(self.d, dy, nimg, dst, self._dgrad_geom(), sigma, alpha_k, None, 0, aux, aux_mode, aux_wrap, colsum, None,
+                   colsum_rows, out_mode)
+
+    # -------------------------------------------------------------------------------------------- weight gradient
+    def wgrad_plan(self, nimg):
+        """(R, NC, bn, splits, P) of the weight-gradient launch for nimg samples."""
+        if self.op == 'd':
+            P = nimg
+            R, NC = (self.Cs_in, self.Cs_out) if self.w_swapped else (self.Cs_out, self.Cs_in)
+        elif self.op == 'c':
+            if self.w_swapped:
+                P, R, NC = nimg * self.Hin * self.Win, self.Cs_in, self.k * self.k * self.Cs_out
+            else:
+                P, R, NC = nimg * self.Hout * self.Wout, self.Cs_out, self.k * self.k * self.Cs_in
+        else:
+            P, R, NC = nimg * self.Hin * self.Win, self.Cs_in, self.k * self.k * self.Cs_out
+        bn = pick_bn(NC, lo=32)
+        tiles = ((R + 127) // 128) * ((NC + bn - 1) // bn)
+        ksteps = (P + 31) // 32
+        splits = max(1, min((296 + tiles - 1) // tiles, max(1, ksteps // 8)))
+        return R, NC, bn, splits, P
+
+    def wgrad(self, x_in, dy, nimg, partials, splits=None):
+        """partials [splits, R, NC] <- weight-gradient GEMM of (layer input x_in, output gradient dy)."""
+        R, NC, bn, sp, P = self.wgrad_plan(nimg)
+        splits = splits or sp
+        d = WgradDesc()
+        if self.op == 'd':
+            plain, gath = (x_in, dy) if self.w_swapped else (dy, x_in)
+            geo = (1, 1, 1, 1, 1, 1, 1, 1, 0, 0)
+        elif self.op == 'c':
+            if self.w_swapped:
+                plain, gath = x_in, dy
+                o = -(self.k - 1 - self.pad)
+                geo = (self.Hout, self.Wout, self.Hin, self.Win, 1, 1, self.k, self.k, o, o)
+            else:
+                plain, gath = dy, x_in
+                geo = (self.Hin, self.Win, self.Hout, self.Wout, self.s, self.s, self.k, self.k, -self.pad, -self.pad)
+        else:
+            plain, gath = x_in, dy
+            geo = (self.Hout, self.Wout, self.Hin, self.Win, 2, 2, 4, 4, -1, -1)
+        d.plain, d.plain_plane, d.P, d.Cp = _ptr(plain), plane_stride(plain), P, R
+        assert plain.shape[2] == R and plain.shape[1] >= P
+        d.g, d.g_plane = _ptr(gath), plane_stride(gath)
+        d.Nimg = nimg
+        d.Hs, d.Ws, d.Hg, d.Wg, d.sy, d.sx, d.TH, d.TW, d.oy, d.ox = geo
+        d.Cs = gath.shape[2]
+        assert d.TH * d.TW * d.Cs == NC
+        d.splits, d.out, d.bn, d.npass = splits, _ptr(partials), bn, self.npass
+        assert partials.numel() >= splits * R * NC
+        check(lib().mmdgan_wgrad_gemm(C.byref(d), stream()))
+        return splits
+
+    def wgrad_reduce(self, partials, splits, nimg, out_canon, w_canon=None, dots=None):
+        """split partials -> gradient in the canonical (reference) weight layout; optional per-block <G, W>."""
+        R, NC, _, _, _ = self.wgrad_plan(nimg)
+        d = WredDesc()
+        d.partials, d.splits, d.R, d.NC = _ptr(partials), splits, R, NC
+        d.r_perm_C = d.c_perm_C = 1
+        d.r_perm_HW = d.c_perm_HW = 1
+        ci, co = self.Cin, self.Cout
+        if self.op == 'd':
+            if self.w_swapped:      # r = in', c = out'
+                d.Cg, d.Cvalid, d.Rvalid = self.Cs_out, co, ci
+                d.base, d.sr, d.st, d.sc = 0, co, 0, 1
+                (d.r_perm_C, d.r_perm_HW), (d.c_perm_C, d.c_perm_HW) = self.in_flat, self.out_flat
+            else:                   # r = out', c = in'
+                d.Cg, d.Cvalid, d.Rvalid = self.Cs_in, ci, co
+                d.base, d.sr, d.st, d.sc = 0, 1, 0, co
+                (d.r_perm_C, d.r_perm_HW), (d.c_perm_C, d.c_perm_HW) = self.out_flat, self.in_flat
+        elif self.op == 'c':
+            if self.w_swapped:      # r = ci, t mirrored, c = co
+                d.Cg, d.Cvalid, d.Rvalid = self.Cs_out, co, ci
+                d.base, d.sr, d.st, d.sc = (self.k * self.k - 1) * ci * co, co, -ci * co, 1
+            else:                   # r = co, t = (kh,kw), c = ci
+                d.Cg, d.Cvalid, d.Rvalid = self.Cs_in, ci, co
+                d.base, d.sr, d.st, d.sc = 0, 1, ci * co, co
+        else:                       # tc: r = ci, t = (kh,kw), c = co ; canon [k,k,Cout,Cin]
+            d.Cg, d.Cvalid, d.Rvalid = self.Cs_out, co, ci
+            d.base, d.sr, d.st, d.sc = 0, 1, co * ci, ci
+        d.w, d.out, d.dots = _ptr(w_canon), _ptr(out_canon), _ptr(dots)
+        check(lib().mmdgan_wgrad_reduce(C.byref(d), stream()))
+        return lib().mmdgan_wgrad_reduce_blocks(R * NC)
+
+
+# ------------------------------------------------------------------------------------------------ small wrappers
+def reduce_tiles(partials, T, Cc, out, scale=1.0):
+    check(lib().mmdgan_reduce_tiles(_ptr(partials), T, Cc, float(scale), _ptr(out), stream()))
+
+
+def colsum_small(x, rows, Cc, out):
+    check(lib().mmdgan_colsum_small(_ptr(x), rows, Cc, _ptr(out), stream()))
+
+
+def sn_normalize(v, n, out, sigma_out=None, eps=1e-10):
+    check(lib().mmdgan_sn_normalize(_ptr(v), n, float(eps), _ptr(sigma_out), _ptr(out), plane_stride(out), stream()))
+
+
+def sn_grad_combine(g, s, dots, ndots, sigma, act_k, n):
+    check(lib().mmdgan_sn_grad_combine(_ptr(g), _ptr(s), _ptr(dots), ndots, _ptr(sigma), float(act_k), n, stream()))
+
+
+def scale_by_sigma(g, sigma, act_k, n):
+    check(lib().mmdgan_scale_by_sigma(_ptr(g), _ptr(sigma), float(act_k), n, stream()))
+
+
+def permute_features(src, dst, n, Cc, HW, inverse=False):
+    check(lib().mmdgan_permute_features(_ptr(src), _ptr(dst), n, Cc, HW, 1 if inverse else 0, stream()))
+
+
+def bn_finalize(psum, psq, T, Cc, rows, mean, invstd, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99):
+    check(lib().mmdgan_bn_finalize(_ptr(psum), _ptr(psq), T, Cc, rows, float(eps), float(momentum), _ptr(mean), _ptr(invstd),
+                                   _ptr(moving_mean), _ptr(moving_var), stream()))
+
+
+def bn_apply(z, mean, invstd, gamma, beta, Cc, total, act, out):
+    check(lib().mmdgan_bn_apply(_ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), Cc, total, act, _ptr(out),
+                                plane_stride(out), stream()))
+
+
+def bn_bwd_reduce(da, z, mean, invstd, gamma, beta, Cc, rows, rows_per_block, act, psum, psumx):
+    check(lib().mmdgan_bn_bwd_reduce(_ptr(da), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), Cc, rows,
+                                     rows_per_block, act, _ptr(psum), _ptr(psumx), stream()))
+
+
+def bn_bwd_apply(da, z, mean, invstd, gamma, beta, dbeta, dgamma, Cc, rows, act, out):
+    check(lib().mmdgan_bn_bwd_apply(_ptr(da), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(dbeta),
+                                    _ptr(dgamma), Cc, rows, act, _ptr(out), plane_stride(out), stream()))
+
+
+def adam(w, m, v, g, n, lr, step, beta1=0.5, beta2=0.999, eps=1e-8):
+    check(lib().mmdgan_adam(_ptr(w), _ptr(m), _ptr(v), _ptr(g), n, float(lr), float(beta1), float(beta2), float(eps), _ptr(step),
+                            stream()))
+
+
+def incr_step(step):
+    check(lib().mmdgan_incr_step(_ptr(step), stream()))
+
+
+def nan_flag(x, n, flag):
+    check(lib().mmdgan_nan_flag(_ptr(x), n, _ptr(flag), stream()))
+
+
+# ------------------------------------------------------------------------------------------------ MMD
+class MmdKernel(object):
+    """Configured fused MMD loss kernel (mmdgan_mmd_fwd_bwd); owns its small workspace."""
+
+    def __init__(self, loss_type, rep_weights=(0.0, -1.0), b=64, device='cuda'):
+        self.desc = MmdDesc()
+        check(lib().mmdgan_mmd_configure(C.byref(self.desc), loss_type.encode(), float(rep_weights[0]), float(rep_weights[1])))
+        self.b = b
+        self.ws = torch.zeros(int(lib().mmdgan_mmd_workspace(b)) // 4 + 4, dtype=torch.float32, device=device)
+        self.sums = torch.zeros(6, dtype=torch.float32, device=device)
+        self.losses = torch.zeros(2, dtype=torch.float32, device=device)
+
+    def __call__(self, gen_loc, real_loc, dLg_dgen, dLd_dgen, dLd_dreal, dLg_dreal=None, gen_all=None, real_all=None, row0=0):
+        d = self.desc
+        b, dim = gen_loc.shape
+        assert b <= self.b
+        gen_all = gen_loc if gen_all is None else gen_all
+        real_all = real_loc if real_all is None else real_all
+        d.gen_loc, d.real_loc, d.gen_all, d.real_all = _ptr(gen_loc), _ptr(real_loc), _ptr(gen_all), _ptr(real_all)
+        d.b, d.Bg, d.row0, d.d = b, gen_all.shape[0], row0, dim
+        d.sums, d.losses = _ptr(self.sums), _ptr(self.losses)
+        d.dLg_dgen, d.dLg_dreal, d.dLd_dgen, d.dLd_dreal = _ptr(dLg_dgen), _ptr(dLg_dreal), _ptr(dLd_dgen), _ptr(dLd_dreal)
+        d.workspace = _ptr(self.ws)
+        check(lib().mmdgan_mmd_fwd_bwd(C.byref(d), stream()))
+        return self.losses

@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a real B200 (run by the driver with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from mmdgan_b200 import kernels
+    from mmdgan_b200._lib import check
+    check(kernels.lib().mmdgan_check_device())
+    return torch.device('cuda:0')
