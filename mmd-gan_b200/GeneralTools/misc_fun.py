@@ -1,0 +1,26 @@
+"""Configuration flags, mirroring GeneralTools/misc_fun.py:25-60 of the reference (plain object, mutated by scripts)."""
+
+
+class SetFlag(object):
+    def __init__(self):
+        # machine config (misc_fun.py:27-30)
+        self.num_gpus = 1
+        self.EPSI = 1e-10
+        self.SILENT_MODE = False
+        # directory setup (misc_fun.py:38-41)
+        self.DEFAULT_IN = 'MMD-GAN/Data/'
+        self.DEFAULT_OUT = 'MMD-GAN/Results/'
+        # model setup (misc_fun.py:49-53): three of these change the hot-path maths
+        self.IMAGE_FORMAT = 'channels_first'
+        self.IMAGE_FORMAT_ALIAS = 'NCHW'
+        self.WEIGHT_INITIALIZER = 'default'
+        self.SPECTRAL_NORM_MODE = 'default'   # 'default' = 'PICO'; 'sn_paper' = PIM (not built yet: raises)
+        # B200 engine knobs (new): 3 = fp32-grade tf32x3 tensor-core products (parity mode), 1 = plain tf32
+        self.TENSOR_PASSES = 3
+
+    def print(self, info, force_print=False):
+        if (not self.SILENT_MODE) or force_print:
+            print(info)
+
+
+FLAGS = SetFlag()

@@ -341,8 +341,10 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2D fp32 tensor map [rows][cols] (cols contiguous), box {32 cols, box_rows}, 128-byte swizzle, zero OOB fill
-int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows) {
+// 2D fp32 tensor map [rows][cols] (cols contiguous), box {32 cols, box_rows}, 128-byte swizzle (16-byte chunks, or
+// 32-byte chunks for MN-major tf32 operands), zero OOB fill
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows,
+                 int swizzle32b) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -350,7 +352,8 @@ int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long co
     cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
 }
@@ -360,8 +363,8 @@ static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane
                       cudaStream_t st) {
     using Cfg = GemmCfg<BN, NPASS>;
     CUtensorMap t0, t1;
-    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, BN)) return -4;
-    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, BN)) return -4;
+    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, BN, 0)) return -4;
+    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, BN, 0)) return -4;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=

@@ -125,14 +125,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 layout): start address [0,14) in 16-byte units, leading-dim byte offset
 // [16,30), stride-dim byte offset [32,46), version (=1) [46,48), layout type [61,64) (2 = 128-byte swizzle).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only
+// swizzle the hardware accepts for MN-major tf32 operands).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= 1ull << 46;
-    d |= 2ull << 61;
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
 }
 // Instruction descriptor for kind::tf32 with fp32 accumulation: c_format F32 (1) at [4,6), a/b format TF32 (2) at
 // [7,10)/[10,13), a/b major (0 = K-major, 1 = MN-major) at 15/16, N>>3 at [17,23), M>>4 at [24,29).

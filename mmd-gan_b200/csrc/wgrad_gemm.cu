@@ -16,7 +16,8 @@
 
 namespace mg {
 
-int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows);
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows,
+                 int swizzle32b);
 
 static constexpr int kWBM = 128;
 static constexpr int kWProducers = 128;
@@ -144,7 +145,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                 }
                 const int by = y * p.sy + p.oy;
                 const int bx = x * p.sx + p.ox;
-                const uint32_t drow = b0 + static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+                // 32-byte-chunk swizzle: chunk pair index (chunk >> 1) ^ (row & 3), the 16-byte half keeps its place
+                const uint32_t drow = b0 + static_cast<uint32_t>(r * 128 + ((((chunk >> 1) ^ (r & 3)) << 1 | (chunk & 1)) << 4));
 #pragma unroll
                 for (int q = 0; q < NCH; ++q) {
                     const int yy = by + ta[q];
@@ -200,8 +202,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                     const uint32_t bbase = smem_u32(stage_b(s, pb));
 #pragma unroll
                     for (int kg = 0; kg < 4; ++kg) {
-                        const uint64_t ad = smem_desc_sw128(abase + kg * 1024, 4096, 1024);
-                        const uint64_t bd = smem_desc_sw128(bbase + kg * 1024, 4096, 1024);
+                        const uint64_t ad = smem_desc(abase + kg * 1024, 4096, 512, 1u);
+                        const uint64_t bd = smem_desc(bbase + kg * 1024, 4096, 512, 1u);
                         umma_tf32(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kg > 0) ? 1u : 0u);
                     }
                 }
@@ -254,8 +256,8 @@ template <int BN, int NPASS>
 static int launch_wcfg(const WgradParams& p, const float* plain, long long plain_plane, int splits, cudaStream_t st) {
     using Cfg = WgradCfg<BN, NPASS>;
     CUtensorMap t0, t1;
-    if (make_tmap_2d(&t0, plain, p.P, p.Cp, p.Cp, 32)) return -4;
-    if (make_tmap_2d(&t1, plain + (NPASS == 3 ? plain_plane : 0), p.P, p.Cp, p.Cp, 32)) return -4;
+    if (make_tmap_2d(&t0, plain, p.P, p.Cp, p.Cp, 32, 1)) return -4;
+    if (make_tmap_2d(&t1, plain + (NPASS == 3 ? plain_plane : 0), p.P, p.Cp, p.Cp, 32, 1)) return -4;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(wgrad_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=

@@ -1,0 +1,605 @@
+"""SNGanEngine -- the fused SNGan training step on one B200 (one process per GPU).
+
+Implements what one `sess.run([loss_list, op_list, UPDATE_OPS, global_step])` of the reference does
+(GeneralTools/graph_func.py:851-854 driving DeepLearning/my_sngan.py:259-323, 412-426): from ONE forward pass at the
+current weights it produces loss_gen / loss_dis, the discriminator gradients of loss_dis, the generator gradients of
+loss_gen (through D), applies both TF-Adam updates simultaneously, updates the batch-norm moving statistics and
+every spectral-norm `in_rand`.
+
+Data layout in HBM (all fp32): activations NHWC as hi/lo planes [2][N*H*W][C] (see include/mmdgan_b200.h);
+parameters, gradients and Adam slots as one flat buffer per net in the reference's canonical variable layouts;
+packed GEMM operands per layer, refreshed after every update.  The generator's last conv writes straight into rows
+[B, 2B) of the discriminator input (no tf.concat copy); the discriminator backward runs on a 3B "virtual batch"
+(rows: dL_D/d s_real, dL_D/d s_gen, dL_G/d s_gen) so that one dgrad chain serves both losses, while the weight
+gradients use the first 2B rows only.
+
+Multi-GPU (torch.distributed, NCCL): the batch is sharded; scores are all-gathered, each rank evaluates its row block
+of the kernel matrices (exact gradients for its own rows, global 1/(B(B-1)) normalisation), and ONE all-reduce sums
+the flat gradient buffers (+ the six kernel sums).  Batch-norm statistics stay per rank (documented in DESIGN.md).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .GeneralTools.layer_func import Net, Routine
+from .GeneralTools.misc_fun import FLAGS
+
+ALIGN = 64  # floats; every variable starts on a 256-byte boundary inside the flat buffers
+
+
+def _trunc_normal(gen, shape, std):
+    t = torch.empty(shape, dtype=torch.float64)
+    torch.nn.init.trunc_normal_(t, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=gen)
+    return t * std
+
+
+def _fans(shape):
+    if len(shape) == 2:
+        return shape[0], shape[1]
+    rf = int(np.prod(shape[:-2]))
+    return shape[-2] * rf, shape[-1] * rf
+
+
+def weight_initializer(gen, shape, act_fun):
+    """GeneralTools/layer_func.py:14-66 with FLAGS.WEIGHT_INITIALIZER == 'default' (TF-1.8 variance scaling)."""
+    if FLAGS.WEIGHT_INITIALIZER != 'default':
+        raise NotImplementedError('The initializer {} is not implemented.'.format(FLAGS.WEIGHT_INITIALIZER))
+    fan_in, fan_out = _fans(shape)
+    if act_fun == 'relu':
+        return _trunc_normal(gen, shape, math.sqrt(2.0 / fan_in))
+    if act_fun == 'lrelu':
+        return _trunc_normal(gen, shape, math.sqrt(2.0 / 1.01 / fan_in))
+    limit = math.sqrt(3.0 / ((fan_in + fan_out) / 2.0))
+    return (torch.rand(shape, dtype=torch.float64, generator=gen) * 2.0 - 1.0) * limit
+
+
+class _LayerRT(object):
+    """Run-time record of one layer: geometry, parameter views, packed operands and work buffers."""
+    pass
+
+
+class NetRuntime(object):
+    """Parameters + per-layer kernel plans of one Net for a fixed number of samples per forward pass."""
+
+    def __init__(self, routine, nimg_fwd, nimg_bwd, npass, device, gen):
+        self.routine = routine
+        self.net = routine.net
+        self.name = self.net.net_name
+        self.npass = npass
+        self.device = device
+        self.layers = []
+        layers = routine.ordered_layers()
+        # ---- variables in creation order: kernel, bias, gamma, beta per layer
+        self.var_offsets = OrderedDict()
+        off = 0
+        inits = OrderedDict()
+        self.state_init = OrderedDict()
+        for ly in layers:
+            d = ly.design
+            ks = ly.kernel_shape
+            inits[ly.kernel_name] = weight_initializer(gen, ks, d['act'])
+            if 'bias' in ly.ops:
+                inits[ly.bias_name] = _trunc_normal(gen, [ly.op_output_shape[1]], 1e-5)      # layer_func.py:745-747
+            if 'BN' in ly.ops:
+                c = ly.op_output_shape[1]
+                inits[ly.bn_name('gamma')] = torch.ones(c, dtype=torch.float64)
+                inits[ly.bn_name('beta')] = torch.zeros(c, dtype=torch.float64)
+                self.state_init[ly.bn_name('moving_mean')] = torch.zeros(c, dtype=torch.float64)
+                self.state_init[ly.bn_name('moving_variance')] = torch.ones(c, dtype=torch.float64)
+            if d.get('w_nm') == 's':
+                self.state_init[ly.sn_name] = _trunc_normal(gen, ly.sn_x_shape, 1.0)          # math_func.py:565-567
+        for name, t in inits.items():
+            self.var_offsets[name] = (off, list(t.shape))
+            off += (t.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.n_flat = off
+        self.w = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        for name, t in inits.items():
+            self.view(self.w, name).copy_(t.reshape(-1).float())
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+        # ---- per-layer runtime
+        for idx, ly in enumerate(layers):
+            self.layers.append(self._build_layer(idx, ly, nimg_fwd, nimg_bwd))
+        for name, t in self.state_init.items():
+            self.set_state(name, t.float())
+        self.refresh()
+
+    # -------------------------------------------------------------------------------------------- variables
+    def view(self, flat, name):
+        off, shape = self.var_offsets[name]
+        return flat[off:off + int(np.prod(shape))]
+
+    def num_params(self):
+        return sum(int(np.prod(s)) for _, s in self.var_offsets.values())
+
+    def get_variable(self, name):
+        """Canonical (reference-layout) copy of a trainable variable."""
+        off, shape = self.var_offsets[name]
+        return self.view(self.w, name).reshape(shape).clone()
+
+    def get_grad(self, name):
+        off, shape = self.var_offsets[name]
+        return self.view(self.g, name).reshape(shape).clone()
+
+    def set_variable(self, name, value):
+        self.view(self.w, name).copy_(torch.as_tensor(value).reshape(-1).float())
+
+    def _feat_perm(self, L):
+        return L.lop.out_flat if L.op == 'd' else (L.Cout, 1)
+
+    def get_state(self, name):
+        """BN moving statistics / SN in_rand in the reference's layout ([C] / NCHW)."""
+        for L in self.layers:
+            if L.has_bn and name in (L.ly.bn_name('moving_mean'), L.ly.bn_name('moving_variance')):
+                src = L.mm if name.endswith('moving_mean') else L.mv
+                out = torch.empty(L.Cout, device=self.device)
+                c, hw = self._feat_perm(L)
+                K.permute_features(src, out, L.Cout, c, hw, inverse=True)
+                return out
+            if L.has_sn and name == L.ly.sn_name:
+                shp = L.ly.sn_x_shape
+                if len(shp) == 2:
+                    c, hw = L.sn_flat
+                    out = torch.empty(shp[1], device=self.device)
+                    K.permute_features(L.sn_x[0].reshape(-1)[:shp[1]].contiguous(), out, shp[1], c, hw, inverse=True)
+                    return out.reshape(shp)
+                return K.planes_to_nchw(L.sn_x, 1, shp[1], shp[2], shp[3])
+        raise KeyError(name)
+
+    def set_state(self, name, value):
+        value = torch.as_tensor(value).float().to(self.device).contiguous()
+        for L in self.layers:
+            if L.has_bn and name in (L.ly.bn_name('moving_mean'), L.ly.bn_name('moving_variance')):
+                dst = L.mm if name.endswith('moving_mean') else L.mv
+                c, hw = self._feat_perm(L)
+                K.permute_features(value.reshape(-1), dst, L.Cout, c, hw)
+                return
+            if L.has_sn and name == L.ly.sn_name:
+                shp = L.ly.sn_x_shape
+                if len(shp) == 2:
+                    c, hw = L.sn_flat
+                    tmp = torch.empty(shp[1], device=self.device)
+                    K.permute_features(value.reshape(-1), tmp, shp[1], c, hw)
+                    L.sn_x.zero_()
+                    L.sn_x[0].reshape(-1)[:shp[1]].copy_(tmp)
+                    K.make_lo_plane(L.sn_x)
+                else:
+                    K.nchw_to_planes(value.reshape(shp), L.sn_x, self.npass)
+                return
+        raise KeyError(name)
+
+    def state_names(self):
+        return list(self.state_init.keys())
+
+    # -------------------------------------------------------------------------------------------- layers
+    def _build_layer(self, idx, ly, nf, nb):
+        L = _LayerRT()
+        d = ly.design
+        dev, npass = self.device, self.npass
+        L.ly, L.idx, L.op = ly, idx, d['op']
+        L.act, L.act_code = d['act'], K.ACT[d['act']]
+        L.has_bias, L.has_bn, L.has_sn = 'bias' in ly.ops, 'BN' in ly.ops, d.get('w_nm') == 's'
+        L.act_k = float(d['act_k']) if L.has_sn else 1.0
+        ins, outs = ly.op_input_shape[1:], ly.op_output_shape[1:]
+        in_flat = out_flat = None
+        if L.op == 'd':
+            prev = self.layers[idx - 1] if idx > 0 else None
+            # the input features of a dense layer that follows a conv layer are an NCHW-flatten of an NHWC buffer
+            if prev is not None and prev.op != 'd':
+                in_flat = (prev.Cout, prev.Hout * prev.Wout)
+            if d['out_reshape'] is not None and len(d['out_reshape']) == 3:
+                c, h, w = d['out_reshape']
+                out_flat = (c, h * w)
+        L.lop = K.LinearOp(L.op, ins, outs, d.get('kernel', 1), d.get('strides', 1), npass=npass, in_flat=in_flat,
+                           out_flat=out_flat, device=dev)
+        lop = L.lop
+        L.Cin, L.Cout, L.Hin, L.Win, L.Hout, L.Wout = lop.Cin, lop.Cout, lop.Hin, lop.Win, lop.Hout, lop.Wout
+        L.rows_in, L.rows_out = L.Hin * L.Win, L.Hout * L.Wout      # per sample
+        L.Cs_in, L.Cs_out = lop.Cs_in, lop.Cs_out
+        # ---- parameter-derived internal vectors (channel padded, feature permuted)
+        z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+        if L.has_bias:
+            L.bias_int = z(L.Cs_out)
+        if L.has_bn:
+            L.gamma_int, L.beta_int = z(L.Cs_out), z(L.Cs_out)
+            L.mm, L.mv, L.mean, L.invstd = z(L.Cs_out), z(L.Cs_out), z(L.Cs_out), z(L.Cs_out)
+            L.dgamma_int, L.dbeta_int = z(L.Cs_out), z(L.Cs_out)
+        # ---- activations (forward batch nf) and gradients (backward batch nb)
+        L.a = None            # output activation planes; set by the owner (may alias the D input buffer)
+        if L.has_bn:
+            L.zraw = torch.zeros((1, nf * L.rows_out, L.Cs_out), dtype=torch.float32, device=dev)
+            Tt = lop.fwd_tiles(nf)
+            L.ps, L.pq, L.T_fwd = z(Tt * L.Cs_out), z(Tt * L.Cs_out), Tt
+            L.da_raw = torch.zeros((1, nb * L.rows_out, L.Cs_out), dtype=torch.float32, device=dev)
+            L.rpb = max(1, (nb * L.rows_out + 295) // 296)
+            nblk = (nb * L.rows_out + L.rpb - 1) // L.rpb
+            L.bp1, L.bp2, L.nblk = z(nblk * L.Cs_out), z(nblk * L.Cs_out), nblk
+        L.dz = None           # gradient w.r.t. the op output (pre-bias / pre-BN), planes; set by the owner
+        # weight-gradient workspace
+        R, NC, bn, splits, P = lop.wgrad_plan(nf)
+        L.wg_splits = splits
+        L.wg_parts = z(splits * R * NC)
+        L.n_dots = K.lib().mmdgan_wgrad_reduce_blocks(R * NC)
+        L.dots = torch.zeros(L.n_dots, dtype=torch.float64, device=dev)
+        # column-sum workspace of the dgrad that PRODUCES this layer's dz (bias gradient), sized by the owner
+        L.cs = None
+        L.cs_T = 0
+        # ---- spectral norm state (batch-1 power iteration)
+        if L.has_sn:
+            x_is_input = ly.use_u if L.op != 'tc' else (not ly.use_u)
+            L.sn_x_is_input = x_is_input
+            r_x, c_x = (L.rows_in, L.Cs_in) if x_is_input else (L.rows_out, L.Cs_out)
+            r_y, c_y = (L.rows_out, L.Cs_out) if x_is_input else (L.rows_in, L.Cs_in)
+            L.sn_x = K.new_planes(r_x, c_x, npass, dev)
+            L.sn_xnew = K.new_planes(r_x, c_x, npass, dev)
+            L.sn_y = K.new_planes(r_y, c_y, npass, dev)
+            L.sn_v = torch.zeros((1, r_y, c_y), dtype=torch.float32, device=dev)
+            L.sn_w = torch.zeros((1, r_x, c_x), dtype=torch.float32, device=dev)
+            L.sigma = torch.ones(1, dtype=torch.float32, device=dev)
+            Rs, NCs, _, sps, _ = lop.wgrad_plan(1)
+            L.sn_splits = sps
+            L.sn_parts = z(sps * Rs * NCs)
+            L.sn_S = z(lop.canon_numel)
+            if L.op == 'd':
+                L.sn_flat = (lop.in_flat if x_is_input else lop.out_flat)
+        return L
+
+    def refresh(self):
+        """canonical parameters -> packed GEMM operands and internal (padded / permuted) vectors."""
+        for L in self.layers:
+            L.lop.pack(self.view(self.w, L.ly.kernel_name))
+            c, hw = self._feat_perm(L)
+            if L.has_bias:
+                K.permute_features(self.view(self.w, L.ly.bias_name), L.bias_int, L.Cout, c, hw)
+            if L.has_bn:
+                K.permute_features(self.view(self.w, L.ly.bn_name('gamma')), L.gamma_int, L.Cout, c, hw)
+                K.permute_features(self.view(self.w, L.ly.bn_name('beta')), L.beta_int, L.Cout, c, hw)
+
+
+class SNGanEngine(object):
+    def __init__(self, architecture, batch_size, loss_type='rep', rep_weights=(0.0, -1.0), lr_list=(5e-4, 2e-4),
+                 seed=2, npass=None, device='cuda', world_size=1, rank=0, process_group=None, use_graph=True):
+        from ._lib import check as _check
+        _check(K.lib().mmdgan_check_device())
+        self.arch = architecture
+        self.B = int(batch_size)                 # per-GPU batch of real images (= batch of codes)
+        self.loss_type = loss_type
+        self.rep_weights = list(rep_weights)
+        self.lr_dis, self.lr_gen = float(lr_list[0]), float(lr_list[1])
+        self.npass = FLAGS.TENSOR_PASSES if npass is None else npass
+        self.device = torch.device(device)
+        self.world_size, self.rank, self.pg = world_size, rank, process_group
+        self.use_graph = use_graph
+        self.om = 0 if self.npass == 3 else 1      # plane outputs: raw + lo plane, or one rn-tf32 plane
+        self.code_size = architecture['code'][0][0]
+        self.channels, self.height, self.width = architecture['input'][0]
+        self.score_size = architecture['discriminator'][-1]['out']
+        B = self.B
+        # ---- nets as the reference builds them (my_sngan.py:85-108)
+        g_net = Net(architecture['generator'], net_name='gen', data_format=FLAGS.IMAGE_FORMAT, num_class=0)
+        self.Gen = Routine(g_net)
+        self.Gen.add_input_layers([64, self.code_size], [0])
+        self.Gen.seq_links(list(range(g_net.num_layers)))
+        self.Gen.add_output_layers([g_net.num_layers - 1])
+        d_net = Net(architecture['discriminator'], net_name='dis', data_format=FLAGS.IMAGE_FORMAT, num_class=0)
+        self.Dis = Routine(d_net)
+        self.Dis.add_input_layers([64] + list(architecture['input'][0]), [0])
+        self.Dis.seq_links(list(range(d_net.num_layers)))
+        self.Dis.add_output_layers([d_net.num_layers - 1])
+        gen = torch.Generator().manual_seed(seed)
+        self.G = NetRuntime(self.Gen, B, B, self.npass, self.device, gen)
+        self.D = NetRuntime(self.Dis, 2 * B, 3 * B, self.npass, self.device, gen)
+        self._alloc_buffers()
+        self.mmd = K.MmdKernel(loss_type, self.rep_weights, b=B, device=self.device)
+        self.global_step = 0
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._graphs = None
+        self._warm = False
+        self._stream = torch.cuda.Stream(device=self.device)
+        # pinned staging for the end-to-end path
+        self._pin_data = torch.empty((B, self.channels, self.height, self.width), dtype=torch.float32).pin_memory()
+        self._pin_code = torch.empty((B, self.code_size), dtype=torch.float32).pin_memory()
+        self._pin_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+        self._dev_data = torch.empty_like(self._pin_data, device=self.device)
+        self._dev_code = torch.empty_like(self._pin_code, device=self.device)
+        self.kernel_launches_per_step = None
+
+    # -------------------------------------------------------------------------------------------- buffers
+    def _alloc_buffers(self):
+        B, dev, npass = self.B, self.device, self.npass
+        HW = self.height * self.width
+        self.code_planes = K.new_planes(B, K.pad4(self.code_size), npass, dev)
+        # D input: rows [0, B*HW) real, [B*HW, 2B*HW) generated
+        self.x_all = K.new_planes(2 * B * HW, K.pad4(self.channels), npass, dev)
+        # generator activations
+        for i, L in enumerate(self.G.layers):
+            last = i == len(self.G.layers) - 1
+            L.a = self.x_all[:, B * HW:, :] if last else K.new_planes(B * L.rows_out, L.Cs_out, npass, dev)
+            L.dz = K.new_planes(B * L.rows_out, L.Cs_out, npass, dev)
+        # discriminator activations (2B) and gradients (3B virtual batch)
+        for i, L in enumerate(self.D.layers):
+            last = i == len(self.D.layers) - 1
+            if last:
+                L.a = torch.zeros((1, 2 * B, L.Cs_out), dtype=torch.float32, device=dev)      # scores, fp32
+                L.raw_out = True
+            else:
+                L.a = K.new_planes(2 * B * L.rows_out, L.Cs_out, npass, dev)
+            L.dz = K.new_planes(3 * B * L.rows_out, L.Cs_out, npass, dev)
+        # column-sum workspaces: the dgrad of layer i+1 produces dz of layer i
+        for net, nb in ((self.G, B), (self.D, 3 * B)):
+            for i, L in enumerate(net.layers[:-1]):
+                nxt = net.layers[i + 1]
+                L.cs_T = nxt.lop.dgrad_tiles(nb)
+                L.cs = torch.zeros(L.cs_T * nxt.lop.d['ncols'], dtype=torch.float32, device=dev)
+        # the generator's last layer gets its dz (and bias column sums) from the dgrad of D's first layer on B fakes
+        gl, d0 = self.G.layers[-1], self.D.layers[0]
+        gl.cs_T = d0.lop.dgrad_tiles(B)
+        gl.cs = torch.zeros(gl.cs_T * d0.lop.d['ncols'], dtype=torch.float32, device=dev)
+        self.tmp_vec = torch.zeros(max(max(L.Cs_out for L in self.G.layers), max(L.Cs_out for L in self.D.layers)) + 64,
+                                   dtype=torch.float32, device=dev)
+        if self.world_size > 1:
+            d = self.D.layers[-1].Cs_out
+            self.s_gather = torch.zeros((self.world_size, 2 * B, d), dtype=torch.float32, device=dev)
+            self.gen_all = torch.zeros((self.world_size * B, d), dtype=torch.float32, device=dev)
+            self.real_all = torch.zeros((self.world_size * B, d), dtype=torch.float32, device=dev)
+
+    # -------------------------------------------------------------------------------------------- forward passes
+    @staticmethod
+    def _as_rows(planes, rows, c):
+        """Reinterpret [npl, r0, c0] planes as [npl, rows, c] (same memory; NHWC flatten / unflatten)."""
+        npl = planes.shape[0]
+        assert planes.shape[1] * planes.shape[2] == rows * c
+        return planes.as_strided((npl, rows, c), (planes.stride(0), c, 1), planes.storage_offset())
+
+    def _net_forward(self, net, src, nimg, is_training=True, sigma_on=True):
+        for L in net.layers:
+            lop = L.lop
+            src = self._as_rows(src, nimg * L.rows_in, L.Cs_in)
+            sig = L.sigma if (L.has_sn and sigma_on) else None
+            if L.has_bn:
+                lop.forward(src, nimg, L.zraw, sigma=sig, alpha_k=L.act_k, out_mode=2, colsum=L.ps, colsumsq=L.pq)
+                if is_training:
+                    K.bn_finalize(L.ps, L.pq, L.T_fwd, L.Cs_out, nimg * L.rows_out, L.mean, L.invstd, L.mm, L.mv)
+                    K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
+                               L.act_code, L.a)
+                else:
+                    raise NotImplementedError('{}: inference-mode batch norm is built in Routine runner'.format(L.ly.layer_scope))
+            else:
+                out_mode = 2 if getattr(L, 'raw_out', False) else self.om
+                lop.forward(src, nimg, L.a, sigma=sig, alpha_k=L.act_k, bias=L.bias_int if L.has_bias else None,
+                            act=L.act_code, out_mode=out_mode)
+            src = L.a
+        return src
+
+    def _sn_power_iteration(self):
+        """One PICO power iteration per spectrally-normalised layer (math_func.py:661-672): sigma = ||F(x)||,
+        x' = l2n(F^T(l2n(F(x)))) and S = d(sigma)/dW = wgrad(x, u)."""
+        for L in self.D.layers + self.G.layers:
+            if not L.has_sn:
+                continue
+            lop = L.lop
+            if L.sn_x_is_input:
+                lop.forward(L.sn_x, 1, L.sn_v, out_mode=2)
+                K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
+                lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2)
+                K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
+                lop.wgrad(L.sn_x, L.sn_y, 1, L.sn_parts, L.sn_splits)
+            else:
+                lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2)
+                K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
+                lop.forward(L.sn_y, 1, L.sn_w, out_mode=2)
+                K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
+                lop.wgrad(L.sn_y, L.sn_x, 1, L.sn_parts, L.sn_splits)
+            lop.wgrad_reduce(L.sn_parts, L.sn_splits, 1, L.sn_S)
+
+    # -------------------------------------------------------------------------------------------- step pieces
+    def _phase_forward(self):
+        B, HW = self.B, self.height * self.width
+        K.nchw_to_planes(self._dev_code, self.code_planes, self.npass)
+        K.nchw_to_planes(self._dev_data, self.x_all[:, :B * HW, :], self.npass)
+        self._sn_power_iteration()
+        self._net_forward(self.G, self.code_planes, B)
+        self._net_forward(self.D, self.x_all, 2 * B)
+
+    def _phase_loss(self):
+        B = self.B
+        s = self.D.layers[-1].a[0]                      # [2B, d]: rows [0,B) real, [B,2B) generated (my_sngan.py:279)
+        seed = self.D.layers[-1].dz                     # [2, 3B, d]
+        if self.world_size > 1:
+            self.mmd(s[B:], s[:B], seed[0, 2 * B:], seed[0, B:2 * B], seed[0, :B], gen_all=self.gen_all, real_all=self.real_all,
+                     row0=self.rank * B)
+        else:
+            self.mmd(s[B:], s[:B], seed[0, 2 * B:], seed[0, B:2 * B], seed[0, :B])
+        K.make_lo_plane(seed)
+
+    def _bias_grad_from_colsum(self, net, L, ncols_per_row_group):
+        """bias gradient of layer L from the per-tile column sums of the dgrad that produced L.dz."""
+        groups = ncols_per_row_group // L.Cs_out          # > 1 when dz was produced as a flattened dense input
+        K.reduce_tiles(L.cs, L.cs_T * groups, L.Cs_out, self.tmp_vec)
+        c, hw = net._feat_perm(L)
+        K.permute_features(self.tmp_vec, net.view(net.g, L.ly.bias_name), L.Cout, c, hw, inverse=True)
+
+    def _weight_grad(self, net, L, x_in, dz, nimg):
+        lop = L.lop
+        x_in = self._as_rows(x_in, x_in.shape[1] * x_in.shape[2] // L.Cs_in, L.Cs_in)
+        lop.wgrad(x_in, dz, nimg, L.wg_parts, L.wg_splits)
+        gview = net.view(net.g, L.ly.kernel_name)
+        if L.has_sn:
+            nd = lop.wgrad_reduce(L.wg_parts, L.wg_splits, nimg, gview, w_canon=net.view(net.w, L.ly.kernel_name), dots=L.dots)
+            K.sn_grad_combine(gview, L.sn_S, L.dots, nd, L.sigma, L.act_k, lop.canon_numel)
+        else:
+            lop.wgrad_reduce(L.wg_parts, L.wg_splits, nimg, gview)
+
+    def _phase_backward(self):
+        B, HW = self.B, self.height * self.width
+        D, G = self.D, self.G
+        # ================= discriminator: loss_dis -> D variables (rows [0,2B)), loss_gen -> dx_fake (rows [2B,3B))
+        last = D.layers[-1]
+        if last.has_bias:
+            K.colsum_small(last.dz[0], 2 * B, last.Cs_out, self.tmp_vec)
+            c, hw = D._feat_perm(last)
+            K.permute_features(self.tmp_vec, D.view(D.g, last.ly.bias_name), last.Cout, c, hw, inverse=True)
+        for i in range(len(D.layers) - 1, -1, -1):
+            L = D.layers[i]
+            x_in = D.layers[i - 1].a if i > 0 else self.x_all
+            self._weight_grad(D, L, x_in, L.dz, 2 * B)
+            sig = L.sigma if L.has_sn else None
+            if i > 0:
+                P = D.layers[i - 1]
+                dzp = self._as_rows(P.dz, 3 * B * L.rows_in, L.Cs_in)
+                aux = self._as_rows(P.a, 2 * B * L.rows_in, L.Cs_in)[0]
+                L.lop.dgrad(L.dz, 3 * B, dzp, sigma=sig, alpha_k=L.act_k, aux=aux, aux_mode=P.act_code,
+                            aux_wrap=(2 * B * L.rows_in, B * L.rows_in), colsum=P.cs if P.has_bias else None,
+                            colsum_rows=2 * B * L.rows_in, out_mode=self.om)
+                if P.has_bias:
+                    self._bias_grad_from_colsum(D, P, L.Cs_in)
+            else:
+                gl = G.layers[-1]
+                L.lop.dgrad(L.dz[:, 2 * B * L.rows_out:, :], B, gl.dz, sigma=sig, alpha_k=L.act_k,
+                            aux=self.x_all[0, B * HW:, :], aux_mode=gl.act_code, colsum=gl.cs if gl.has_bias else None,
+                            out_mode=self.om)
+                if gl.has_bias:
+                    self._bias_grad_from_colsum(G, gl, L.Cs_in)
+        # ================= generator: loss_gen -> G variables
+        for i in range(len(G.layers) - 1, -1, -1):
+            L = G.layers[i]
+            x_in = G.layers[i - 1].a if i > 0 else self.code_planes
+            self._weight_grad(G, L, x_in, L.dz, B)
+            if i == 0:
+                break
+            P = G.layers[i - 1]
+            if P.has_bn:
+                da = self._as_rows(P.da_raw, B * L.rows_in, L.Cs_in)
+                L.lop.dgrad(L.dz, B, da, out_mode=2)
+                rows = B * P.rows_out
+                K.bn_bwd_reduce(P.da_raw, P.zraw, P.mean, P.invstd, P.gamma_int, P.beta_int, P.Cs_out, rows, P.rpb, P.act_code,
+                                P.bp1, P.bp2)
+                K.reduce_tiles(P.bp1, P.nblk, P.Cs_out, P.dbeta_int)
+                K.reduce_tiles(P.bp2, P.nblk, P.Cs_out, P.dgamma_int)
+                K.bn_bwd_apply(P.da_raw, P.zraw, P.mean, P.invstd, P.gamma_int, P.beta_int, P.dbeta_int, P.dgamma_int, P.Cs_out,
+                               rows, P.act_code, P.dz)
+                c, hw = G._feat_perm(P)
+                K.permute_features(P.dbeta_int, G.view(G.g, P.ly.bn_name('beta')), P.Cout, c, hw, inverse=True)
+                K.permute_features(P.dgamma_int, G.view(G.g, P.ly.bn_name('gamma')), P.Cout, c, hw, inverse=True)
+            else:
+                dzp = self._as_rows(P.dz, B * L.rows_in, L.Cs_in)
+                aux = self._as_rows(P.a, B * L.rows_in, L.Cs_in)[0] if P.act_code != 0 else None
+                fused_cs = P.has_bias and P.op != 'd'
+                L.lop.dgrad(L.dz, B, dzp, aux=aux, aux_mode=P.act_code, colsum=P.cs if fused_cs else None, out_mode=self.om)
+                if fused_cs:
+                    self._bias_grad_from_colsum(G, P, L.Cs_in)
+                elif P.has_bias:
+                    # a dense layer's bias is per FEATURE: sum its [B, F] gradient over the batch only
+                    K.colsum_small(P.dz[0], B, P.Cs_out, self.tmp_vec)
+                    c, hw = G._feat_perm(P)
+                    K.permute_features(self.tmp_vec, G.view(G.g, P.ly.bias_name), P.Cout, c, hw, inverse=True)
+
+    def _phase_update(self):
+        """Both Adam updates from the same forward pass, then UPDATE_OPS (my_sngan.py:424-426; graph_func.py:848-854)."""
+        for net, lr in ((self.D, self.lr_dis), (self.G, self.lr_gen)):
+            K.incr_step(net.step)
+            K.adam(net.w, net.m, net.v, net.g, net.n_flat, lr, net.step)
+            net.refresh()
+        for L in self.D.layers + self.G.layers:
+            if L.has_sn:
+                L.sn_x.copy_(L.sn_xnew)
+        K.nan_flag(self.mmd.losses, 2, self.nan_flag)
+
+    # -------------------------------------------------------------------------------------------- collectives
+    def _gather_scores(self):
+        import torch.distributed as dist
+        s = self.D.layers[-1].a[0]
+        dist.all_gather_into_tensor(self.s_gather.view(-1, s.shape[1]), s, group=self.pg)
+        B = self.B
+        self.real_all.copy_(self.s_gather[:, :B, :].reshape(-1, s.shape[1]))
+        self.gen_all.copy_(self.s_gather[:, B:, :].reshape(-1, s.shape[1]))
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.D.g, group=self.pg)
+        dist.all_reduce(self.G.g, group=self.pg)
+        dist.all_reduce(self.mmd.sums, group=self.pg)
+        s, cD = self.mmd.sums, self.mmd.desc.cD
+        self.mmd.losses[0] = s[0] + s[2] - 2.0 * s[1]
+        self.mmd.losses[1] = cD[0] * s[3] + cD[1] * s[4] + cD[2] * s[5]
+
+    # -------------------------------------------------------------------------------------------- public API
+    def _run_phases(self):
+        self._phase_forward()
+        if self.world_size > 1:
+            self._gather_scores()
+        self._phase_loss()
+        self._phase_backward()
+        if self.world_size > 1:
+            self._allreduce_grads()
+        self._phase_update()
+
+    def _capture(self):
+        """Capture the step (or, multi-GPU, its three collective-free segments) into CUDA graphs."""
+        torch.cuda.synchronize(self.device)
+        segs = ([[self._phase_forward], [self._phase_loss, self._phase_backward], [self._phase_update]]
+                if self.world_size > 1 else [[self._phase_forward, self._phase_loss, self._phase_backward, self._phase_update]])
+        graphs = []
+        for fns in segs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                for fn in fns:
+                    fn()
+            graphs.append(g)
+        self._graphs = graphs
+
+    def step_device(self):
+        """One training step on the batch already staged in self._dev_data / self._dev_code (device resident)."""
+        if not self.use_graph or not self._warm:
+            # the first step always runs eagerly (it also sets the kernels' shared-memory attributes)
+            n0 = K.LAUNCHES[0]
+            self._run_phases()
+            self.kernel_launches_per_step = K.LAUNCHES[0] - n0
+            self._warm = True
+        else:
+            if self._graphs is None:
+                self._capture()
+            if self.world_size > 1:
+                self._graphs[0].replay()
+                self._gather_scores()
+                self._graphs[1].replay()
+                self._allreduce_grads()
+                self._graphs[2].replay()
+            else:
+                self._graphs[0].replay()
+        self.global_step += 1
+
+    def stage(self, data_x, code_x):
+        """Put one batch on the device ({'x': NCHW float32 in [-1, 1]} contract of input_func.py:837-868)."""
+        self._dev_data.copy_(data_x, non_blocking=True)
+        self._dev_code.copy_(code_x, non_blocking=True)
+
+    def step(self, data_x, code_x, check_nan=True):
+        """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis]."""
+        self._pin_data.copy_(data_x)
+        self._pin_code.copy_(code_x)
+        self.stage(self._pin_data, self._pin_code)
+        self.step_device()
+        self._pin_loss.copy_(self.mmd.losses, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        lg, ld = float(self._pin_loss[0]), float(self._pin_loss[1])
+        if check_nan:
+            assert not (math.isnan(lg) or math.isnan(ld)), \
+                'Model diverged with loss = {} at step {}'.format([lg, ld], self.global_step)    # graph_func.py:856
+        return lg, ld
+
+    def losses(self):
+        return self.mmd.losses.clone()
+
+    def generate(self, code_x):
+        """Generated images NCHW for the staged codes, training-mode batch norm (the step's own forward)."""
+        B, HW = self.B, self.height * self.width
+        self._dev_code.copy_(code_x)
+        K.nchw_to_planes(self._dev_code, self.code_planes, self.npass)
+        self._net_forward(self.G, self.code_planes, B)
+        return K.planes_to_nchw(self.x_all[:, B * HW:, :], B, self.channels, self.height, self.width)

@@ -10,14 +10,22 @@ import math
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, WgradDesc, WredDesc, PackDesc, MmdDesc, check
+from ._lib import GemmDesc, WgradDesc, WredDesc, PackDesc, MmdDesc
 
 ACT = {'linear': 0, None: 0, 'lrelu': 1, 'relu': 2, 'tanh': 3}
 PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRAD, PACK_DENSE_FWD, PACK_DENSE_DGRAD = range(7)
 
 
+LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
+
+
 def lib():
     return _lib.load()
+
+
+def check(rc):
+    LAUNCHES[0] += 1
+    return _lib.check(rc)
 
 
 def stream():
@@ -29,7 +37,11 @@ def _ptr(t):
         return None
     if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32):
         raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32 tensor, got {} on {}'.format(t.dtype, t.device))
-    if not t.is_contiguous():
+    if t.dim() == 3:
+        # planes [npl, rows, C]: every plane must be a dense [rows, C] block; the plane stride is free (row views)
+        if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'plane tensor must have dense [rows, C] planes')
+    elif not t.is_contiguous():
         raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'tensor must be contiguous')
     return C.c_void_p(t.data_ptr())
 
@@ -369,7 +381,7 @@ class MmdKernel(object):
 
     def __init__(self, loss_type, rep_weights=(0.0, -1.0), b=64, device='cuda'):
         self.desc = MmdDesc()
-        check(lib().mmdgan_mmd_configure(C.byref(self.desc), loss_type.encode(), float(rep_weights[0]), float(rep_weights[1])))
+        _lib.check(lib().mmdgan_mmd_configure(C.byref(self.desc), loss_type.encode(), float(rep_weights[0]), float(rep_weights[1])))
         self.b = b
         self.ws = torch.zeros(int(lib().mmdgan_mmd_workspace(b)) // 4 + 4, dtype=torch.float32, device=device)
         self.sums = torch.zeros(6, dtype=torch.float32, device=device)

@@ -11,7 +11,7 @@ from oracle import net as onet
 
 pytestmark = pytest.mark.gpu
 
-TOL3 = 2e-5
+TOL3 = 5e-5
 TOL1 = 3e-3
 
 
