@@ -292,10 +292,31 @@ def sn_pim_x_shape(sp):
     return [1, w_rows] if w_rows <= sp.kernel_shape[3] else [1, sp.kernel_shape[3]]
 
 
-def activation(x, act):
+class _KinkWithMask(torch.autograd.Function):
+    """relu / leaky-relu whose DERIVATIVE branch is chosen by an external boolean mask instead of sign(x).
+
+    Test helper: for an input within rounding noise of the kink, an fp32 implementation and this float64 oracle may
+    legitimately land on different sides (either is correct to the working precision).  Parity tests pass the
+    sign pattern of the implementation under test so that such ties do not masquerade as errors."""
+
+    @staticmethod
+    def forward(ctx, x, mask, slope):
+        ctx.save_for_backward(mask)
+        ctx.slope = slope
+        return torch.where(x > 0, x, x * slope)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return torch.where(mask, g, g * ctx.slope), None, None
+
+
+def activation(x, act, mask=None):
     """layer_func.py:104-167."""
     if act == 'linear':
         return x
+    if mask is not None and act in ('relu', 'lrelu'):
+        return _KinkWithMask.apply(x, mask.reshape(x.shape), 0.0 if act == 'relu' else LRELU_ALPHA)
     if act == 'relu':
         return F.relu(x)
     if act == 'lrelu':
@@ -305,7 +326,7 @@ def activation(x, act):
     raise NotImplementedError('Function {} is not implemented.'.format(act))
 
 
-def net_forward(specs, params, state, x, is_training=True, sn_mode='default', tf32=False, collect=None):
+def net_forward(specs, params, state, x, is_training=True, sn_mode='default', tf32=False, collect=None, act_masks=None):
     """Routine.__call__ over a sequential net of default layers (layer_func.py:1646-1685, 2451-2491).
 
     Returns (output, updates) where updates holds the UPDATE_OPS results (BN moving stats, SN in_rand).
@@ -345,7 +366,7 @@ def net_forward(specs, params, state, x, is_training=True, sn_mode='default', tf
             else:
                 shp = (1, -1) if x.dim() == 2 else (1, -1, 1, 1)
                 x = (x - mm.view(shp)) / torch.sqrt(mv.view(shp) + BN_EPS) * g.view(shp) + b.view(shp)
-        x = activation(x, sp.act)
+        x = activation(x, sp.act, None if act_masks is None else act_masks.get(sp.scope))
         if sp.design['out_reshape'] is not None:
             x = x.reshape([n] + list(sp.design['out_reshape']))
         if collect is not None:
@@ -398,13 +419,13 @@ class OracleSNGan(object):
         self.opt_gen = TFAdam(self.gen_params, lr_list[1])
         self.global_step = 0
 
-    def forward_losses(self, data_x, code_x, collect=None):
+    def forward_losses(self, data_x, code_x, collect=None, act_masks=None):
         gp = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in self.gen_params.items())
         dp = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in self.dis_params.items())
         b = data_x.shape[0]
-        x_gen, upd_g = net_forward(self.gen_specs, gp, self.gen_state, code_x, True, self.sn_mode, self.tf32, collect)
+        x_gen, upd_g = net_forward(self.gen_specs, gp, self.gen_state, code_x, True, self.sn_mode, self.tf32, collect, act_masks)
         both = torch.cat([data_x, x_gen], 0)                                  # my_sngan.py:244-256, 278
-        s_all, upd_d = net_forward(self.dis_specs, dp, self.dis_state, both, True, self.sn_mode, self.tf32, collect)
+        s_all, upd_d = net_forward(self.dis_specs, dp, self.dis_state, both, True, self.sn_mode, self.tf32, collect, act_masks)
         s_x, s_gen = s_all[:b], s_all[b:]                                     # my_sngan.py:279
         loss_gen, loss_dis = omm.gan_loss(s_gen, s_x, self.loss_type, batch_size=b, rep_weights=self.rep_weights)
         if collect is not None:
@@ -413,9 +434,9 @@ class OracleSNGan(object):
             collect['s_gen'] = s_gen
         return loss_gen, loss_dis, gp, dp, upd_g, upd_d
 
-    def grads(self, data_x, code_x, collect=None):
+    def grads(self, data_x, code_x, collect=None, act_masks=None):
         """Both gradient sets evaluated at the pre-update weights (my_sngan.py:301-304)."""
-        loss_gen, loss_dis, gp, dp, upd_g, upd_d = self.forward_losses(data_x, code_x, collect)
+        loss_gen, loss_dis, gp, dp, upd_g, upd_d = self.forward_losses(data_x, code_x, collect, act_masks)
         g_dis = torch.autograd.grad(loss_dis, list(dp.values()), retain_graph=True)
         g_gen = torch.autograd.grad(loss_gen, list(gp.values()))
         grads_dis = OrderedDict(zip(dp.keys(), [g.detach() for g in g_dis]))
