@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the fused SNGan training step (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cifar|stl|celeba|lsun]
+                  [--batch B] [--passes 3|1] [--no-cpu-baseline] [--no-roofline]
+
+Own arm: workload = BASELINE.json configs[1] (CIFAR-10 32x32 SNGAN + repulsive MMD, batch 256 per GPU, spectral norm
+on), synthetic data, random-init weights.  A "step" is one fused training step ([losses, dis_op, gen_op, UPDATE_OPS]).
+`value` is measured with the batch resident in HBM (CUDA-graph replay); `e2e` goes through SNGanEngine.step() with
+HOST tensors: pinned H2D of the batch and D2H of the two losses inside the timed region.  N > 1 (torchrun): the batch
+is sharded, weak scaling (256 images per GPU), scores all-gathered + one gradient all-reduce over NCCL.
+
+Reference arm (--impl reference): TensorFlow-1.8 cannot be installed in this image, so the reference's CPU path is the
+oracle (PyTorch-CPU restatement of the TF1 step, oracle/net.py) timed on the host cores; rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {'cifar': ('cifar', 256, 'rep', (5e-4, 2e-4)), 'stl': ('stl', 128, 'rmb', (2e-4, 2e-4)),
+             'celeba': ('celeba', 128, 'rep', (1e-4, 2e-4)), 'lsun': ('lsun', 128, 'rep', (2e-4, 1e-4))}
+# algorithmic cost per (real, fake) pair = 3G + 7D forward-equivalents, in GFLOP
+GFLOP_PER_PAIR = {'cifar': 3.642, 'stl': 8.195, 'celeba': 19.351, 'lsun': 19.351}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p.get('hbm_gbs', 6650.0), burst=p.get('bf16_tflops', 1590.0),
+                    sustained=p.get('bf16_tflops_sustained', p.get('bf16_tflops', 1590.0)), source='measured')
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, source='fallback')
+
+
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def synthetic_host_batches(arch, batch, n, seed):
+    import torch
+    c, h, w = arch['input'][0]
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        data = (torch.rand(batch, c, h, w, generator=g) * 2.0 - 1.0).pin_memory()      # uniform [-1, 1], input_func.py:839
+        code = torch.randn(batch, arch['code'][0][0], generator=g).pin_memory()
+        out.append((data, code))
+    return out
+
+
+def cpu_reference_throughput(arch_name, batch, loss_type, lr_list, steps, warmup, budget_s=200.0):
+    """The oracle (CPU restatement of the TF1 step) on the host cores.  Returns (img/s, ms/step, sample description, cores)."""
+    import torch
+    from oracle import architectures as oa
+    from oracle import net as onet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    arch = oa.ARCHITECTURES[arch_name]()
+    model = onet.OracleSNGan(arch, loss_type, lr_list=lr_list, dtype=torch.float32)
+    bs = batch
+    data, code = onet.synthetic_batch(arch, bs, seed=0)
+    t0 = time.perf_counter()
+    model.step(data, code)                       # probe (also the first warm-up step)
+    t_probe = time.perf_counter() - t0
+    while bs > 16 and t_probe * (bs / batch) * (steps + max(warmup - 1, 0)) > budget_s:
+        bs //= 2
+    if bs != batch:
+        data, code = data[:bs], code[:bs]
+    for _ in range(max(warmup - 1, 0)):
+        model.step(data, code)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.step(data, code)
+    dt = (time.perf_counter() - t0) / steps
+    sample = '{} steps of the same fused step at batch {} (workload batch {}), fp32, {} torch threads'.format(steps, bs, batch, cores)
+    return bs / dt, dt * 1e3, sample, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    name, batch, loss_type, lr = WORKLOADS[args.workload]
+    batch = args.batch or batch
+    ips, ms, sample, cores = cpu_reference_throughput(name, batch, loss_type, lr, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': 'images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '{} SNGAN + {} MMD, batch {}, spectral norm on'.format(name, loss_type, batch),
+                   'note': 'TensorFlow 1.8 is not installable here; the reference CPU path is the PyTorch-CPU restatement of the '
+                           'TF1 step (oracle/net.py) on the host cores'},
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import architectures as oa          # architecture dictionaries only (data, no oracle compute)
+    from mmdgan_b200 import kernels as K
+    from mmdgan_b200.engine import SNGanEngine
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    name, batch, loss_type, lr = WORKLOADS[args.workload]
+    batch = args.batch or batch
+    arch = oa.ARCHITECTURES[name]()
+    eng = SNGanEngine(arch, batch, loss_type=loss_type, lr_list=lr, npass=args.passes, device=dev, world_size=world, rank=rank,
+                      use_graph=True)
+    host = synthetic_host_batches(arch, batch, 4, seed=100 + rank)
+    pool = [(d.to(dev), c.to(dev)) for d, c in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput
+    for i in range(max(args.warmup, 3)):
+        eng.stage(*pool[i % len(pool)])
+        eng.step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        eng.stage(*pool[i % len(pool)])
+        eng.step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    # ---- end to end through the public API (host tensors in, host losses out)
+    for i in range(3):
+        eng.step(*host[i % len(host)])
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = None
+    for i in range(args.steps):
+        last = eng.step(*host[i % len(host)])
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    images = batch * world * args.steps
+    value = images / (ms_dev / 1e3)
+    e2e_value = images / (ms_e2e / 1e3)
+    h2d = batch * (arch['input'][0][0] * arch['input'][0][1] * arch['input'][0][2] + arch['code'][0][0]) * 4
+    peaks = read_peaks()
+
+    # ---- roofline of the dominant kernels: every tcgen05 GEMM launch of one step, timed with CUDA events (eager step)
+    roof = None
+    if not args.no_roofline:
+        evs = []
+        orig_gemm, orig_wgrad = K.LinearOp._gemm, K.LinearOp.wgrad
+
+        def timed(fn):
+            def wrapper(*a, **kw):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = fn(*a, **kw)
+                e.record()
+                evs.append((s, e))
+                return r
+            return wrapper
+        K.LinearOp._gemm, K.LinearOp.wgrad = timed(orig_gemm), timed(orig_wgrad)
+        try:
+            eng.stage(*pool[0])
+            torch.cuda.synchronize(dev)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            eng._run_phases()
+            t1.record()
+            torch.cuda.synchronize(dev)
+        finally:
+            K.LinearOp._gemm, K.LinearOp.wgrad = orig_gemm, orig_wgrad
+        gemm_ms = sum(s.elapsed_time(e) for s, e in evs)
+        flop_step = GFLOP_PER_PAIR[name] * 1e9 * batch
+        achieved = flop_step / (gemm_ms / 1e3) / 1e12
+        roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['sustained'],
+                'traffic': None, 'peak_source': peaks['source'] + ' bf16 sustained (MEASURED_PEAKS.json)',
+                'kernel': 'conv_gemm_kernel + wgrad_gemm_kernel: all {} tcgen05 launches of one step'.format(len(evs)),
+                'gemm_ms_per_step': gemm_ms, 'eager_step_ms': t0.elapsed_time(t1), 'share_of_graph_step': gemm_ms / (ms_dev / args.steps),
+                'note': 'algorithmic FLOPs = (3G+7D) x 2 x B; tensor_passes={} tf32 MMAs per algorithmic FLOP (tf32 dense peak is '
+                        'half the bf16 peak), so frac <= {:.3f} by construction in this precision mode'.format(
+                            args.passes, 0.5 / args.passes)}
+
+    if rank == 0:
+        line = {
+            'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'tf32x3' if args.passes == 3 else 'tf32', 'data': 'synthetic',
+            'config': {'workload': '{} {}x{} SNGAN + {} MMD, batch {} per GPU, spectral norm on'.format(
+                name, arch['input'][0][1], arch['input'][0][2], loss_type, batch),
+                'global_batch': batch * world, 'parallelism': 'dp{}'.format(world),
+                'l2': 'per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush',
+                'tensor_passes': args.passes, 'cuda_graph': True, 'loss_last_step': last},
+            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(eng.kernel_launches_per_step * args.steps),
+            'gpu_launches_per_step': int(eng.kernel_launches_per_step),
+            'clocks': clocks,
+        }
+        if roof:
+            line['roofline'] = roof
+        if world == 1 and not args.no_cpu_baseline:
+            ips, ms, sample, cores = cpu_reference_throughput(name, batch, loss_type, lr, steps=2, warmup=1, budget_s=40.0)
+            line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                                    'ms_per_step': ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cifar', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0)
+    ap.add_argument('--passes', type=int, default=3, choices=[1, 3])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-roofline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -581,9 +581,11 @@ class SNGanEngine(object):
 
     def step(self, data_x, code_x, check_nan=True):
         """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis]."""
-        self._pin_data.copy_(data_x)
-        self._pin_code.copy_(code_x)
-        self.stage(self._pin_data, self._pin_code)
+        if not (data_x.is_pinned() and code_x.is_pinned()):      # pageable host memory: stage through pinned buffers
+            self._pin_data.copy_(data_x)
+            self._pin_code.copy_(code_x)
+            data_x, code_x = self._pin_data, self._pin_code
+        self.stage(data_x, code_x)
         self.step_device()
         self._pin_loss.copy_(self.mmd.losses, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
