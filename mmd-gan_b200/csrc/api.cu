@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace mg {
 // conv_gemm.cu / wgrad_gemm.cu
@@ -141,6 +142,11 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     p.aux_wrap_at = d->aux_wrap_at > 0 ? d->aux_wrap_at : (1ll << 62); p.aux_wrap_len = d->aux_wrap_len;
     p.colsum = d->colsum; p.colsumsq = d->colsumsq; p.colsum_rows = d->colsum_rows > 0 ? d->colsum_rows : (1ll << 62);
     p.out_mode = d->out_mode; p.err = nullptr;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("MMDGAN_DEBUG"); dbg = e ? atoi(e) : 0; }
+        p.debug = dbg;
+    }
     for (int i = 0; i < 4; ++i) {
         p.cls[i].oy = d->cls[i].oy; p.cls[i].ox = d->cls[i].ox; p.cls[i].ooy = d->cls[i].ooy; p.cls[i].oox = d->cls[i].oox;
         p.cls[i].wrow = d->cls[i].wrow;

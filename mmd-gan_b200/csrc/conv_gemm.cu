@@ -55,8 +55,9 @@ struct GemmCfg {
     static constexpr int PITCH = BN * 4 + 16;  // staging row pitch in bytes
     static constexpr int STAGING_BYTES = kBM * PITCH;
     static constexpr int RED_BYTES = 2 * kProducerThreads * 16;
+    static constexpr int PROW_BYTES = kBM * 8;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES + RED_BYTES ? PIPE_BYTES : STAGING_BYTES + RED_BYTES;
+    static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES + RED_BYTES + PROW_BYTES ? PIPE_BYTES : STAGING_BYTES + RED_BYTES + PROW_BYTES;
     static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
@@ -81,7 +82,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
     using Cfg = GemmCfg<BN, NPASS>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr int LAG = Cfg::LAG;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -167,19 +167,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
                 const bool ok = tap_ok && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
                 const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 4) : 0;
                 const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 16 * i) * kRowBytes);
+                if (p.debug & 1) continue;
                 cp_async16(dsta, p.src + off, ok ? 16u : 0u);
                 if (NPL == 2) cp_async16(dsta + Cfg::A_BYTES, p.src + p.src_plane + off, ok ? 16u : 0u);
             }
-            cp_async_commit();
-            if (j >= LAG) {
-                cp_async_wait<LAG>();
-                fence_proxy_async_smem();
-                mbar_arrive(&full_bar[(j - LAG) % STAGES]);
-            }
+            // asynchronous publication: the stage's full barrier gets this thread's arrival when its copies land, so the
+            // producers run ahead by as many stages as there are free slots and the MMA warp never waits on this loop
+            cp_async_mbar_arrive_noinc(&full_bar[s]);
         }
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        for (int j = (ksteps > LAG ? ksteps - LAG : 0); j < ksteps; ++j) mbar_arrive(&full_bar[j % STAGES]);
     } else if (warp == 4) {
         // ======================= B producer (TMA) =======================
         if (lane == 0) {
@@ -200,10 +195,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
             mbar_wait_wd(&full_bar[s], ph, p.err, 3);
+            fence_proxy_async_smem();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll
                 for (int pass = 0; pass < NPASS; ++pass) {
+                    if ((p.debug & 2) && (j > 0 || pass > 0)) break;
                     const int pa = (pass == 1) ? 1 : 0;
                     const int pb = (pass == 2) ? 1 : 0;
                     const uint32_t abase = smem_u32(stage_a(s, pa));
@@ -248,6 +245,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
                 for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
         }
+        // destination pixel of this thread's row, computed once (two integer divisions) instead of per element
+        long long* prow_s = reinterpret_cast<long long*>(smem + Cfg::STAGING_BYTES + Cfg::RED_BYTES);
+        {
+            const int m = tile_m * kBM + row;
+            long long pr = -1;
+            if (m < p.M) {
+                const int hw = p.Hg * p.Wg;
+                const int n = m / hw;
+                const int rem = m - n * hw;
+                const int y = rem / p.Wg;
+                const int x = rem - y * p.Wg;
+                pr = (static_cast<long long>(n) * p.Hd + (y * p.osy + cls.ooy)) * p.Wd + (x * p.osx + cls.oox);
+            }
+            prow_s[row] = pr;
+        }
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");
 
@@ -260,19 +272,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int HgWg = p.Hg * p.Wg;
         constexpr int ITERS = (kBM * QPR) / kProducerThreads;
 #pragma unroll 2
         for (int it = 0; it < ITERS; ++it) {
             const int e = t + it * kProducerThreads;
             const int r = e / QPR;
-            const int m = tile_m * kBM + r;
-            if (m >= p.M || !col_ok) continue;
-            const int n = m / HgWg;
-            const int rem = m - n * HgWg;
-            const int y = rem / p.Wg;
-            const int x = rem - y * p.Wg;
-            const long long prow = (static_cast<long long>(n) * p.Hd + (y * p.osy + cls.ooy)) * p.Wd + (x * p.osx + cls.oox);
+            const long long prow = prow_s[r];
+            if (prow < 0 || !col_ok || (p.debug & 4)) continue;
             float4 v = *reinterpret_cast<const float4*>(stg + r * Cfg::PITCH + colq * 16);
             v.x = apply_act(fmaf(v.x, alpha, bias4.x), p.act);
             v.y = apply_act(fmaf(v.y, alpha, bias4.y), p.act);

@@ -135,13 +135,20 @@ __global__ void permute_features_kernel(const float* __restrict__ src, float* __
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
-// out[c] (op)= scale * sum_t partials[t][C] over T tiles, accumulated in double in tile order
+// out[c] = scale * sum_t partials[t][C] over T tiles; block = 32 columns x 32 row-slices, double accumulation, fixed order
 __global__ void reduce_tiles_kernel(const float* __restrict__ partials, int T, int C, float scale, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ double red[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
-    for (int t = 0; t < T; ++t) s += static_cast<double>(partials[static_cast<long long>(t) * C + c]);
-    out[c] = static_cast<float>(s * scale);
+    if (c < C)
+        for (int t = threadIdx.y; t < T; t += 32) s += static_cast<double>(partials[static_cast<long long>(t) * C + c]);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double a = 0.0;
+        for (int k = 0; k < 32; ++k) a += red[k][threadIdx.x];
+        out[c] = static_cast<float>(a * scale);
+    }
 }
 // column sums of x[rows][C] (small matrices: score gradients)
 __global__ void colsum_small_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ out) {
@@ -232,13 +239,20 @@ __global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, fl
 __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int T, int C, long long rows, float eps,
                                    float momentum, float* __restrict__ mean, float* __restrict__ invstd,
                                    float* __restrict__ moving_mean, float* __restrict__ moving_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ double rs[32][33], rq[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0, q = 0.0;
-    for (int t = 0; t < T; ++t) {
-        s += static_cast<double>(psum[static_cast<long long>(t) * C + c]);
-        q += static_cast<double>(psq[static_cast<long long>(t) * C + c]);
-    }
+    if (c < C)
+        for (int t = threadIdx.y; t < T; t += 32) {
+            s += static_cast<double>(psum[static_cast<long long>(t) * C + c]);
+            q += static_cast<double>(psq[static_cast<long long>(t) * C + c]);
+        }
+    rs[threadIdx.y][threadIdx.x] = s;
+    rq[threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y != 0 || c >= C) return;
+    s = 0.0; q = 0.0;
+    for (int k = 0; k < 32; ++k) { s += rs[k][threadIdx.x]; q += rq[k][threadIdx.x]; }
     const double mu = s / rows;
     double var = q / rows - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -368,7 +382,7 @@ int l_permute_features(const float* src, float* dst, int n, int C, int HW, int i
     return MG_CHECK_LAUNCH();
 }
 int l_reduce_tiles(const float* partials, int T, int C, float scale, float* out, cudaStream_t st) {
-    reduce_tiles_kernel<<<nblocks(C, 128), 128, 0, st>>>(partials, T, C, scale, out);
+    reduce_tiles_kernel<<<nblocks(C, 32), dim3(32, 32), 0, st>>>(partials, T, C, scale, out);
     return MG_CHECK_LAUNCH();
 }
 int l_colsum_small(const float* x, int rows, int C, float* out, cudaStream_t st) {
@@ -376,8 +390,8 @@ int l_colsum_small(const float* x, int rows, int C, float* out, cudaStream_t st)
     return MG_CHECK_LAUNCH();
 }
 int wgrad_reduce_blocks(long long total) {
-    long long g = (total + 256 * 8 - 1) / (256 * 8);
-    if (g > 1024) g = 1024;
+    long long g = (total + 256 * 2 - 1) / (256 * 2);
+    if (g > 2048) g = 2048;
     if (g < 1) g = 1;
     return static_cast<int>(g);
 }
@@ -400,7 +414,7 @@ int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, flo
 }
 int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                   float* invstd, float* mm, float* mv, cudaStream_t st) {
-    bn_finalize_kernel<<<nblocks(C, 128), 128, 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv);
+    bn_finalize_kernel<<<nblocks(C, 32), dim3(32, 32), 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C, long long total,

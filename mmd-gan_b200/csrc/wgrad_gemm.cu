@@ -63,7 +63,6 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
     using Cfg = WgradCfg<BN, NPASS>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr int LAG = Cfg::LAG;
     constexpr int NCH = BN / 32;
 
     extern __shared__ uint8_t smem_raw[];
@@ -158,16 +157,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                     if (NPL == 2) cp_async16(drow + q * 4096 + Cfg::B_BYTES, p.g + p.g_plane + off, ok ? 16u : 0u);
                 }
             }
-            cp_async_commit();
-            if (j >= LAG) {
-                cp_async_wait<LAG>();
-                fence_proxy_async_smem();
-                mbar_arrive(&full_bar[(j - LAG) % STAGES]);
-            }
+            cp_async_mbar_arrive_noinc(&full_bar[s]);   // asynchronous publication, see conv_gemm.cu
         }
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        for (int j = (ksteps > LAG ? ksteps - LAG : 0); j < ksteps; ++j) mbar_arrive(&full_bar[j % STAGES]);
     } else if (warp == 4) {
         // ======================= P producer (TMA, MN-major) =======================
         if (lane == 0) {
@@ -192,6 +183,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
             w_mbar_wait(&full_bar[s], ph, p.err, 13);
+            fence_proxy_async_smem();
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll

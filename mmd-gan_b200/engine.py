@@ -301,6 +301,8 @@ class SNGanEngine(object):
         self._graphs = None
         self._warm = False
         self._stream = torch.cuda.Stream(device=self.device)
+        self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(8)]
+        self.sn_fork = True
         # pinned staging for the end-to-end path
         self._pin_data = torch.empty((B, self.channels, self.height, self.width), dtype=torch.float32).pin_memory()
         self._pin_code = torch.empty((B, self.code_size), dtype=torch.float32).pin_memory()
@@ -376,34 +378,57 @@ class SNGanEngine(object):
             src = L.a
         return src
 
-    def _sn_power_iteration(self):
-        """One PICO power iteration per spectrally-normalised layer (math_func.py:661-672): sigma = ||F(x)||,
+    def _sn_layer(self, L):
+        """One PICO power iteration of one spectrally-normalised layer (math_func.py:661-672): sigma = ||F(x)||,
         x' = l2n(F^T(l2n(F(x)))) and S = d(sigma)/dW = wgrad(x, u)."""
-        for L in self.D.layers + self.G.layers:
-            if not L.has_sn:
-                continue
-            lop = L.lop
-            if L.sn_x_is_input:
-                lop.forward(L.sn_x, 1, L.sn_v, out_mode=2)
-                K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
-                lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2)
-                K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
-                lop.wgrad(L.sn_x, L.sn_y, 1, L.sn_parts, L.sn_splits)
-            else:
-                lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2)
-                K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
-                lop.forward(L.sn_y, 1, L.sn_w, out_mode=2)
-                K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
-                lop.wgrad(L.sn_y, L.sn_x, 1, L.sn_parts, L.sn_splits)
-            lop.wgrad_reduce(L.sn_parts, L.sn_splits, 1, L.sn_S)
+        lop = L.lop
+        if L.sn_x_is_input:
+            lop.forward(L.sn_x, 1, L.sn_v, out_mode=2)
+            K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
+            lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2)
+            K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
+            lop.wgrad(L.sn_x, L.sn_y, 1, L.sn_parts, L.sn_splits)
+        else:
+            lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2)
+            K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
+            lop.forward(L.sn_y, 1, L.sn_w, out_mode=2)
+            K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
+            lop.wgrad(L.sn_y, L.sn_x, 1, L.sn_parts, L.sn_splits)
+        lop.wgrad_reduce(L.sn_parts, L.sn_splits, 1, L.sn_S)
+
+    def _sn_power_iteration(self, fork=True):
+        """All spectral-norm layers; the per-layer chains are independent (batch-1, latency-bound), so they are forked
+        onto side streams and joined before the discriminator forward (they overlap the generator forward)."""
+        layers = [L for L in self.D.layers + self.G.layers if L.has_sn]
+        if not fork or not layers:
+            for L in layers:
+                self._sn_layer(L)
+            return []
+        main = torch.cuda.current_stream(self.device)
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        joins = []
+        for i, L in enumerate(layers):
+            st = self._side_streams[i % len(self._side_streams)]
+            st.wait_event(ev0)
+            with torch.cuda.stream(st):
+                self._sn_layer(L)
+        for st in self._side_streams[:len(layers)]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            joins.append(ev)
+        return joins
 
     # -------------------------------------------------------------------------------------------- step pieces
     def _phase_forward(self):
         B, HW = self.B, self.height * self.width
         K.nchw_to_planes(self._dev_code, self.code_planes, self.npass)
         K.nchw_to_planes(self._dev_data, self.x_all[:, :B * HW, :], self.npass)
-        self._sn_power_iteration()
+        joins = self._sn_power_iteration(fork=self.sn_fork)
         self._net_forward(self.G, self.code_planes, B)
+        main = torch.cuda.current_stream(self.device)
+        for ev in joins:
+            main.wait_event(ev)
         self._net_forward(self.D, self.x_all, 2 * B)
 
     def _phase_loss(self):
