@@ -1,0 +1,114 @@
+"""SNGan -- the reference's model class (DeepLearning/my_sngan.py) over the B200 engine.
+
+Same constructor and `training` signature as the reference (my_sngan.py:31-83, 364-471).  What `training` does per
+call: builds the nets from the architecture dictionary (init_net, 85-108), two Adam optimisers with constant learning
+rates lr_list = [lr_dis, lr_gen] (412-415), then runs `max_step` fused steps through agent.train; every step is the
+simultaneous update of my_sngan.py:424-426.  The data source replaces ReadTFRecords (input_func.py:721-965): `filename`
+may be an array / tensor of images (uint8 or float, NCHW), a callable batch function, or the string 'synthetic'.
+Only loss types 'rep' and 'rmb' (plus the fused siblings 'mmd_g', 'mgb') are on the hot path; penalties ('rep_gp',
+...) raise NotImplementedError.
+"""
+import numpy as np
+
+from ..GeneralTools.misc_fun import FLAGS
+from ..GeneralTools.graph_func import multi_opt_config
+
+
+class SNGan(object):
+    def __init__(self, architecture, num_class=0, loss_type='logistic', optimizer='adam', do_summary=True,
+                 do_summary_image=True, num_summary_image=8, image_transpose=False, **kwargs):
+        self.optimizer_type = ['sgd', 'momentum', 'adam', 'rmsprop']
+        self.data_format = FLAGS.IMAGE_FORMAT
+        self.architecture = architecture
+        self.loss_type = loss_type
+        self.optimizer = optimizer
+        self.num_class = num_class
+        self.channels = self.architecture['input'][0][0]
+        self.height = self.architecture['input'][0][1]
+        self.width = self.architecture['input'][0][2]
+        self.input_size = np.prod(self.architecture['input'][0], dtype=np.int32)
+        self.code_size = self.architecture['code'][0][0]
+        self.score_size = self.architecture['discriminator'][-1]['out']
+        self.do_summary = do_summary
+        self.do_summary_image = do_summary_image
+        self.num_summary_image = num_summary_image
+        self.loss_names = '<loss_gen>, <loss_dis>'
+        self.global_step = None
+        self.step_per_epoch = None
+        self.sample_same_class = False
+        self.force_print = True
+        self.rep_weights = kwargs['rep_weights'] if 'rep_weights' in kwargs else [0.0, -1.0]
+        self.penalty_weight = kwargs['mmd_g_scale'] if 'mmd_g_scale' in kwargs else 0.1
+        if num_class >= 2:
+            raise NotImplementedError('Conditional models (num_class >= 2) are not on the hot path.')
+        if image_transpose:
+            raise NotImplementedError('image_transpose is not on the hot path.')
+        if loss_type not in {'rep', 'rmb', 'mmd_g', 'fixed_g', 'mgb'}:
+            raise NotImplementedError('loss_type {} is not on the hot path (rep / rmb).'.format(loss_type))
+        self.engine = None
+        self.Gen = None
+        self.Dis = None
+
+    def init_net(self, batch_size=64, lr_list=(5e-4, 2e-4), seed=2, **engine_kwargs):
+        """my_sngan.py:85-108 (+ variable creation, which TF does lazily on first use)."""
+        from ..engine import SNGanEngine
+        if self.engine is None or self.engine.B != batch_size:
+            self.engine = SNGanEngine(self.architecture, batch_size, loss_type=self.loss_type, rep_weights=self.rep_weights,
+                                      lr_list=lr_list, seed=seed, **engine_kwargs)
+        self.engine.lr_dis, self.engine.lr_gen = float(lr_list[0]), float(lr_list[1])
+        self.Gen, self.Dis = self.engine.Gen, self.engine.Dis
+        return self.engine
+
+    def sample_codes(self, batch_size, code_x=None, code_y=None, name='codes'):
+        """my_sngan.py:111-149 for num_class < 2: N(0, 1) codes."""
+        import torch
+        if code_x is None:
+            code_x = torch.randn(batch_size, self.code_size)
+        else:
+            code_x = torch.as_tensor(code_x).float()
+            assert code_x.shape[0] == batch_size, 'Input code_x size {} does not match batch_size {}'.format(
+                code_x.shape[0], batch_size)
+        return {'x': code_x}
+
+    def _batch_fn(self, source, batch_size, num_instance):
+        import torch
+        if callable(source):
+            return source
+        if isinstance(source, str):
+            if source != 'synthetic':
+                raise NotImplementedError('TFRecord input ({}) is a "next" row (SURVEY.md section 8 f2); pass an image '
+                                          'array, a batch function or "synthetic".'.format(source))
+            g = torch.Generator().manual_seed(0)
+            pool = torch.rand(max(batch_size * 4, 256), self.channels, self.height, self.width, generator=g) * 2.0 - 1.0
+        else:
+            pool = torch.as_tensor(np.asarray(source))
+            if pool.dtype == torch.uint8:       # input_func.py:837-842: uint8 -> float32 -> x / 127.5 - 1
+                pool = pool.float() / 127.5 - 1.0
+            pool = pool.float()
+        n = pool.shape[0]
+
+        def fn(step):
+            idx = (torch.arange(batch_size) + step * batch_size) % n
+            return pool[idx], self.sample_codes(batch_size)['x']
+        return fn
+
+    def training(self, filename, agent, num_instance, lr_list, end_lr=1e-7, max_step=None, batch_size=64,
+                 sample_same_class=False, num_threads=7, gpu='/gpu:0', **engine_kwargs):
+        """my_sngan.py:364-471."""
+        self.step_per_epoch = int(np.floor(num_instance / batch_size))
+        self.sample_same_class = sample_same_class
+        FLAGS.print('Num Instance: {}; Num Class: {}; Batch: {}'.format(num_instance, self.num_class, batch_size))
+        _, opt_ops = multi_opt_config(lr_list, end_lr=end_lr, optimizer=self.optimizer)
+        assert all(o['kind'] == 'adam' for o in opt_ops)
+        engine = self.init_net(batch_size, lr_list, **engine_kwargs)
+        FLAGS.print('loss_list name: {}.'.format(self.loss_names))
+        batch_fn = self._batch_fn(filename, batch_size, num_instance)
+        losses = agent.train(engine, batch_fn, max_step, self.step_per_epoch, self.loss_names, force_print=self.force_print)
+        self.global_step = engine.global_step
+        self.force_print = False
+        return losses
+
+    def eval_sampling(self, *args, **kwargs):
+        raise NotImplementedError('eval_sampling / mdl_score need the Inception graph (out of scope, SURVEY.md 2.1 row 1b).')
+
+    mdl_score = eval_sampling

@@ -1,0 +1,145 @@
+"""Step loop, optimiser configuration and checkpointing, mirroring the hot-path part of GeneralTools/graph_func.py:
+  opt_config / multi_opt_config (graph_func.py:478-575): Adam(beta1 .5, beta2 .999, eps 1e-8), constant learning rate
+  prepare_folder (graph_func.py:161-180), Agent (1144-1219), MySession.full_run (820-946): the per-step loop with the
+  NaN assert (856), loss print every query_step (860-866) and one checkpoint at the last step (869-871).
+
+The TF session / graph / summary machinery has no equivalent here: a "session" is an SNGanEngine whose step is a
+replayed CUDA graph.  Checkpoints are .npz files keyed by the reference's variable names.
+"""
+import os
+import time
+
+import numpy as np
+
+from .misc_fun import FLAGS
+
+
+def opt_config(initial_lr, lr_decay_steps=None, end_lr=1e-7, optimizer='adam', name_suffix='', global_step=None,
+               target_step=1e5):
+    """graph_func.py:478-527.  Returns (learning_rate, optimiser hyper-parameters)."""
+    if optimizer in ['Adam', 'adam']:
+        return initial_lr, dict(kind='adam', lr=initial_lr, beta1=0.5, beta2=0.999, epsilon=1e-8, name='Adam' + name_suffix)
+    if optimizer in ['SGD', 'sgd', 'Momentum', 'momentum', 'RMSProp', 'rmsprop']:
+        raise NotImplementedError('Optimizer {} is not on the hot path (only adam is built).'.format(optimizer))
+    raise AttributeError('Optimizer {} not supported.'.format(optimizer))
+
+
+def multi_opt_config(lr_list, lr_decay_steps=None, end_lr=1e-7, optimizer='adam', global_step=None, target_step=1e5):
+    """graph_func.py:540-575."""
+    if isinstance(optimizer, str):
+        optimizer = [optimizer]
+    if len(lr_list) == 1:
+        return opt_config(lr_list[0], lr_decay_steps, end_lr, optimizer[0], '', global_step, target_step)
+    if len(optimizer) == 1:
+        optimizer = optimizer * len(lr_list)
+    combo = [opt_config(lr_list[i], lr_decay_steps, end_lr, optimizer[i], '_' + str(i), global_step, target_step)
+             for i in range(len(lr_list))]
+    return [c[0] for c in combo], [c[1] for c in combo]
+
+
+def prepare_folder(filename, sub_folder='', set_folder=True):
+    """graph_func.py:161-180: <DEFAULT_OUT>/<file>_ckpt/<sub_folder>/ and .../<file>_log/<sub_folder>/."""
+    ckpt_folder = os.path.join(FLAGS.DEFAULT_OUT, filename + '_ckpt', sub_folder)
+    summary_folder = os.path.join(FLAGS.DEFAULT_OUT, filename + '_log', sub_folder)
+    save_path = os.path.join(ckpt_folder, filename + '.ckpt')
+    if set_folder:
+        os.makedirs(ckpt_folder, exist_ok=True)
+        os.makedirs(summary_folder, exist_ok=True)
+    return ckpt_folder, summary_folder, save_path
+
+
+def save_checkpoint(engine, save_path, global_step):
+    """All global variables under the reference's names: weights, biases, BN gamma/beta/moving stats, SN in_rand, Adam
+    slots (<var>/Adam_i, <var>/Adam_i_1) and global_step (graph_func.py:708-717)."""
+    out = {'global_step': np.asarray(global_step, dtype=np.int32)}
+    for i, net in enumerate((engine.D, engine.G)):        # Adam_0 = discriminator, Adam_1 = generator (my_sngan.py:414)
+        for name in net.var_offsets:
+            out[name] = net.get_variable(name).cpu().numpy()
+            off, shape = net.var_offsets[name]
+            n = int(np.prod(shape))
+            out[name + '/Adam_{}'.format(i)] = net.m[off:off + n].reshape(shape).cpu().numpy()
+            out[name + '/Adam_{}_1'.format(i)] = net.v[off:off + n].reshape(shape).cpu().numpy()
+        for name in net.state_names():
+            out[name] = net.get_state(name).cpu().numpy()
+        out[net.name + '/adam_step'] = net.step.cpu().numpy()
+    path = '{}-{}.npz'.format(save_path, global_step)
+    np.savez(path, **out)
+    return path
+
+
+def get_ckpt(ckpt_folder, ckpt_file=None):
+    """graph_func.py:399-416: latest checkpoint in the folder (or the named one)."""
+    if ckpt_file is not None:
+        path = os.path.join(ckpt_folder, ckpt_file)
+        return path if os.path.exists(path) else None
+    if not os.path.isdir(ckpt_folder):
+        return None
+    cands = [f for f in os.listdir(ckpt_folder) if f.endswith('.npz') and '.ckpt-' in f]
+    if not cands:
+        return None
+    cands.sort(key=lambda f: int(f.rsplit('-', 1)[1].split('.')[0]))
+    return os.path.join(ckpt_folder, cands[-1])
+
+
+def load_checkpoint(engine, path):
+    import torch
+    z = np.load(path)
+    for i, net in enumerate((engine.D, engine.G)):
+        for name in net.var_offsets:
+            net.set_variable(name, torch.from_numpy(z[name]))
+            off, shape = net.var_offsets[name]
+            n = int(np.prod(shape))
+            net.m[off:off + n].copy_(torch.from_numpy(z[name + '/Adam_{}'.format(i)]).reshape(-1))
+            net.v[off:off + n].copy_(torch.from_numpy(z[name + '/Adam_{}_1'.format(i)]).reshape(-1))
+        for name in net.state_names():
+            net.set_state(name, torch.from_numpy(z[name]))
+        net.step.copy_(torch.from_numpy(z[net.name + '/adam_step']))
+        net.refresh()
+    engine.global_step = int(z['global_step'])
+    return engine.global_step
+
+
+class Agent(object):
+    """graph_func.py:1144-1219.  train() is MySession.full_run for the `imbalanced_update is None` case."""
+
+    def __init__(self, filename, sub_folder, load_ckpt=False, do_trace=False, do_save=True, debug_mode=False, debug_step=800,
+                 query_step=500, log_device=False, imbalanced_update=None, print_loss=True):
+        self.ckpt_folder, self.summary_folder, self.save_path = prepare_folder(filename, sub_folder=sub_folder)
+        self.load_ckpt = load_ckpt
+        self.do_trace = do_trace
+        self.do_save = do_save
+        self.debug = debug_mode
+        self.debug_step = debug_step
+        self.log_device = log_device
+        self.query_step = query_step
+        self.imbalanced_update = imbalanced_update
+        self.print_loss = print_loss
+        if imbalanced_update is not None:
+            raise NotImplementedError('Imbalanced update is not on the hot path (graph_func.py:876-908).')
+
+    def train(self, engine, batch_fn, max_step, step_per_epoch, loss_names='<loss_gen>, <loss_dis>', force_print=False):
+        """engine: SNGanEngine; batch_fn(step) -> (data NCHW float32 in [-1,1], codes [B, code_size]) host tensors."""
+        if self.load_ckpt:
+            path = get_ckpt(self.ckpt_folder)
+            if path is not None:
+                step = load_checkpoint(engine, path)
+                FLAGS.print('Model reloaded from {} (global step {}).'.format(path, step), force_print)
+            else:
+                FLAGS.print('No ckpt found; variables initialised.', force_print)
+        start_time = time.time()
+        loss_value = None
+        for step in range(max_step):
+            data_x, code_x = batch_fn(step)
+            loss_value = engine.step(data_x, code_x, check_nan=False)
+            # check if model produces nan outcome (graph_func.py:856)
+            assert not any(np.isnan(loss_value)), 'Model diverged with loss = {} at step {}'.format(loss_value, step)
+            gs = engine.global_step
+            if gs % self.query_step == (self.query_step - 1) and self.print_loss:
+                epoch = step // max(step_per_epoch, 1)
+                FLAGS.print('Epoch {}, global steps {}, loss_list {}'.format(
+                    epoch, gs, ['{}'.format(['<{:.2f}>'.format(l) for l in loss_value])]))
+            if step == max_step - 1 and self.do_save:
+                save_checkpoint(engine, self.save_path, gs)
+        duration = time.time() - start_time
+        FLAGS.print('Training for {} steps took {:.3f} sec.'.format(max_step, duration))     # graph_func.py:945-946
+        return loss_value

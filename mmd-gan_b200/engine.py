@@ -537,21 +537,15 @@ class SNGanEngine(object):
 
     # -------------------------------------------------------------------------------------------- collectives
     def _gather_scores(self):
-        import torch.distributed as dist
-        s = self.D.layers[-1].a[0]
-        dist.all_gather_into_tensor(self.s_gather.view(-1, s.shape[1]), s, group=self.pg)
-        B = self.B
-        self.real_all.copy_(self.s_gather[:, :B, :].reshape(-1, s.shape[1]))
-        self.gen_all.copy_(self.s_gather[:, B:, :].reshape(-1, s.shape[1]))
+        from . import parallel
+        parallel.gather_scores(self.D.layers[-1].a[0], self.B, self.s_gather, self.gen_all, self.real_all, self.pg)
 
     def _allreduce_grads(self):
-        import torch.distributed as dist
-        dist.all_reduce(self.D.g, group=self.pg)
-        dist.all_reduce(self.G.g, group=self.pg)
-        dist.all_reduce(self.mmd.sums, group=self.pg)
-        s, cD = self.mmd.sums, self.mmd.desc.cD
-        self.mmd.losses[0] = s[0] + s[2] - 2.0 * s[1]
-        self.mmd.losses[1] = cD[0] * s[3] + cD[1] * s[4] + cD[2] * s[5]
+        from . import parallel
+        parallel.allreduce_sum([self.D.g, self.G.g, self.mmd.sums], self.pg)
+        lg, ld = parallel.losses_from_sums(self.mmd.sums, [float(c) for c in self.mmd.desc.cD])
+        self.mmd.losses[0] = lg
+        self.mmd.losses[1] = ld
 
     # -------------------------------------------------------------------------------------------- public API
     def _run_phases(self):

@@ -1,0 +1,47 @@
+"""Data-parallel plumbing of the SNGan step (one process per GPU, torch.distributed; NCCL on NVLink, gloo in CPU tests).
+
+The reference is single-GPU (FLAGS.num_gpus is never read, misc_fun.py:28); this is new functionality specified in
+SURVEY.md section 8(e).  The batch dimension is sharded; the only batch-coupled quantities are
+  * the three B x B kernel matrices of the MMD loss -> every rank needs ALL scores: one all-gather of the [2b, d] local
+    score block (<= 128 KiB at global batch 1024), after which rank r evaluates rows [r*b, (r+1)*b) of each matrix
+    (mmdgan_mmd_fwd_bwd row-block form) and gets the exact gradients of its own rows;
+  * the parameter gradients and the six kernel sums -> one sum all-reduce per flat buffer (the local gradients are
+    already normalised by the GLOBAL 1/(B(B-1)), so the sum is the global-batch gradient; no averaging).
+Batch-norm statistics stay per rank (per-GPU batch), as documented in DESIGN.md.
+"""
+import torch
+import torch.distributed as dist
+
+
+def gather_scores(s_local, b, gather_buf, gen_all, real_all, group=None):
+    """s_local [2b, d] (rows [0,b) real, [b,2b) generated) -> real_all / gen_all [world*b, d] in global row order."""
+    world = dist.get_world_size(group)
+    d = s_local.shape[1]
+    flat = gather_buf.view(world * 2 * b, d)
+    try:
+        dist.all_gather_into_tensor(flat, s_local.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):       # backends without the flat variant
+        parts = [torch.empty_like(s_local) for _ in range(world)]
+        dist.all_gather(parts, s_local.contiguous(), group=group)
+        flat.copy_(torch.cat(parts, 0))
+    g = gather_buf.view(world, 2 * b, d)
+    real_all.copy_(g[:, :b, :].reshape(world * b, d))
+    gen_all.copy_(g[:, b:, :].reshape(world * b, d))
+    return gen_all, real_all
+
+
+def allreduce_sum(tensors, group=None):
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def losses_from_sums(sums, cD):
+    """sums = [e_gg, e_gr, e_rr, e_gg^b, e_gr^b, e_rr^b] (global, after the all-reduce) -> (loss_gen, loss_dis)."""
+    loss_gen = sums[0] + sums[2] - 2.0 * sums[1]
+    loss_dis = cD[0] * sums[3] + cD[1] * sums[4] + cD[2] * sums[5]
+    return loss_gen, loss_dis
+
+
+def row_block(rank, b):
+    """Global row range owned by `rank`."""
+    return rank * b, (rank + 1) * b

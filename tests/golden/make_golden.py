@@ -1,0 +1,86 @@
+"""Generates the committed golden fixtures from the float64 CPU oracle (run: python tests/golden/make_golden.py).
+
+The reference ships no golden vectors and TensorFlow 1.x cannot run here, so these fixtures are
+authored from the oracle with fixed seeds; tests/test_oracle_*.py pin the oracle itself against closed forms and
+finite differences.  Files: mmd_<loss>_<B>.npz, sn_<case>.npz, step_tiny_<loss>.npz.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import architectures as oa      # noqa: E402
+from oracle import mmd as omm               # noqa: E402
+from oracle import net as onet              # noqa: E402
+
+
+def mmd_case(loss_type, b, d=16, seed=0, w=(0.0, -1.0)):
+    rng = np.random.RandomState(seed + b)
+    gen = (rng.randn(b, d) * 0.35).astype(np.float32)
+    real = (rng.randn(b, d) * 0.35 + 0.1).astype(np.float32)
+    if b >= 4:
+        gen[1] = gen[0]                          # duplicate rows: exact zero distance at the clamp
+        real[2] = real[3] + np.float32(0.5) / 4  # a pair at distance^2 = 16 * (1/8)^2 = 0.25: exactly on the lower bound
+    out = omm.gan_loss_with_grads(gen, real, loss_type, rep_weights=w)
+    out.update(gen=gen, real=real, rep_weights=np.asarray(w))
+    return out
+
+
+def sn_case(op, cin, cout, hin, k, s, seed):
+    design = onet.update_layer_design({'name': 't', 'op': op, 'out': cout, 'kernel': k, 'strides': s, 'w_nm': 's', 'act_k': 1.5})
+    sp = onet.LayerSpec(design, [cin, hin, hin] if op != 'd' else [cin], 'n/t')
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(sp.kernel_shape, generator=g, dtype=torch.float64) * 0.2).requires_grad_(True)
+    x = torch.randn(sp.x_shape, generator=g, dtype=torch.float64)
+    sigma, x_upd = onet.spectral_norm(sp, w, x)
+    (dsdw,) = torch.autograd.grad(sigma, w)
+    return dict(op=op, cin=cin, cout=cout, hin=hin, k=k, s=s, use_u=np.asarray(sp.use_u), w=w.detach().numpy(), x=x.numpy(),
+                sigma=sigma.detach().numpy(), x_update=x_upd.numpy(), dsigma_dw=dsdw.numpy())
+
+
+def step_case(loss_type):
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    B = 8
+    m = onet.OracleSNGan(arch, loss_type, dtype=torch.float64, seed=3)
+    onet.warm_spectral_norm(m, 6)
+    data, code = onet.synthetic_batch(arch, B, seed=5, dtype=torch.float32)       # fp32-representable inputs
+    data, code = data.double(), code.double()
+    out = {'data': data.numpy().astype(np.float32), 'code': code.numpy().astype(np.float32)}
+    for k, v in list(m.gen_params.items()) + list(m.dis_params.items()):
+        out['before:' + k] = v.numpy()
+    for k, v in list(m.gen_state.items()) + list(m.dis_state.items()):
+        out['state_before:' + k] = v.numpy()
+    col = {}
+    lg, ld, gg, gd, _, _ = m.grads(data, code, col)
+    out['loss_gen'], out['loss_dis'] = lg.numpy(), ld.numpy()
+    out['scores'] = torch.cat([col['s_x'], col['s_gen']], 0).detach().numpy()
+    out['x_gen'] = col['x_gen'].detach().numpy()
+    for k, v in list(gg.items()) + list(gd.items()):
+        out['grad:' + k] = v.numpy()
+    m.step(data, code)
+    for k, v in list(m.gen_params.items()) + list(m.dis_params.items()):
+        out['after:' + k] = v.numpy()
+    for k, v in list(m.gen_state.items()) + list(m.dis_state.items()):
+        out['state_after:' + k] = v.numpy()
+    return out
+
+
+def main():
+    for lt in ('rep', 'rmb', 'mmd_g', 'mgb'):
+        for b in (2, 3, 64) if lt in ('rep', 'rmb') else (64,):
+            np.savez_compressed(os.path.join(HERE, 'mmd_{}_{}.npz'.format(lt, b)), **mmd_case(lt, b))
+    np.savez_compressed(os.path.join(HERE, 'mmd_rep_256.npz'), **mmd_case('rep', 256))
+    np.savez_compressed(os.path.join(HERE, 'mmd_rmb_w_1_0.npz'), **mmd_case('rmb', 32, w=(1.0, 0.0)))
+    cases = {'conv_k3s1_useu': ('c', 8, 16, 6, 3, 1), 'conv_k4s2_nouseu': ('c', 8, 16, 8, 4, 2), 'dense_nouseu': ('d', 64, 16, 1, 1, 1),
+             'dense_useu': ('d', 16, 32, 1, 1, 1), 'conv_image': ('c', 3, 8, 8, 3, 1)}
+    for i, (name, c) in enumerate(cases.items()):
+        np.savez_compressed(os.path.join(HERE, 'sn_{}.npz'.format(name)), **sn_case(*c, seed=10 + i))
+    for lt in ('rep', 'rmb'):
+        np.savez_compressed(os.path.join(HERE, 'step_tiny_{}.npz'.format(lt)), **step_case(lt))
+
+
+if __name__ == '__main__':
+    main()

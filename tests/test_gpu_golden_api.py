@@ -1,0 +1,122 @@
+"""GPU: the CUDA path against the COMMITTED golden fixtures (no oracle at run time), and the reference-facing Python
+API (GANLoss autograd, SpectralNorm, SNGan.training + Agent + checkpoint round trip)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a)).double().reshape(-1)
+    b = torch.as_tensor(np.asarray(b)).double().reshape(-1)
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'mmd_*.npz'))), ids=os.path.basename)
+def test_ganloss_autograd_against_golden(cuda, path):
+    from mmdgan_b200.GeneralTools.math_func import GANLoss
+    z = np.load(path)
+    lt = os.path.basename(path).split('_')[1]
+    lt = 'mmd_g' if lt == 'mmd' else lt
+    g = torch.from_numpy(z['gen']).cuda().requires_grad_(True)
+    r = torch.from_numpy(z['real']).cuda().requires_grad_(True)
+    loss_gen, loss_dis = GANLoss(False).apply(g, r, lt, batch_size=g.shape[0], d=g.shape[1], rep_weights=list(z['rep_weights']))
+    assert abs(float(loss_gen) - float(z['loss_gen'])) <= 1e-4 * abs(float(z['loss_gen'])) + 2e-6
+    assert abs(float(loss_dis) - float(z['loss_dis'])) <= 1e-4 * abs(float(z['loss_dis'])) + 2e-6
+    (2.0 * loss_gen + 3.0 * loss_dis).backward()
+    gscale = max(np.abs(z[k]).max() for k in ['dLg_dgen', 'dLd_dgen', 'dLd_ddata', 'dLg_ddata'])
+    assert np.abs(g.grad.cpu().numpy() - (2 * z['dLg_dgen'] + 3 * z['dLd_dgen'])).max() < 1e-4 * gscale + 1e-9
+    assert np.abs(r.grad.cpu().numpy() - (2 * z['dLg_ddata'] + 3 * z['dLd_ddata'])).max() < 1e-4 * gscale + 1e-9
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'sn_*.npz'))), ids=os.path.basename)
+def test_spectral_norm_class_against_golden(cuda, path):
+    from mmdgan_b200.GeneralTools.math_func import SpectralNorm
+    z = np.load(path)
+    op, k, s, cin, cout, hin = str(z['op']), int(z['k']), int(z['s']), int(z['cin']), int(z['cout']), int(z['hin'])
+    if op == 'd':
+        sn_def = {'op': 'd'}
+    else:
+        hout = hin // s
+        sn_def = {'op': op, 'strides': s, 'dilation': 1, 'padding': 'SAME', 'data_format': 'NCHW',
+                  'input_shape': [10, cin, hin, hin], 'output_shape': [10, cout, hout, hout]}
+    sn = SpectralNorm(sn_def, name_scope='SN', num_iter=1)
+    w = torch.from_numpy(z['w']).float().cuda()
+    sn._init_routine(w)
+    assert sn.use_u == bool(z['use_u'])                         # routing: bit-exact
+    sn.x = torch.from_numpy(z['x']).float().cuda()
+    sigma = sn.apply(w)
+    assert abs(float(sigma) - float(z['sigma'])) < 1e-4 * float(z['sigma'])
+    assert rel(sn.x.cpu().numpy(), z['x_update']) < 1e-4
+
+
+@pytest.mark.parametrize('loss_type', ['rep', 'rmb'])
+def test_engine_step_against_golden(cuda, loss_type):
+    from oracle import architectures as oa          # the architecture dictionary only
+    from mmdgan_b200.engine import SNGanEngine
+    z = np.load(os.path.join(GOLD, 'step_tiny_{}.npz'.format(loss_type)))
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    eng = SNGanEngine(arch, 8, loss_type=loss_type, use_graph=False)
+    for net in (eng.G, eng.D):
+        for name in net.var_offsets:
+            net.set_variable(name, torch.from_numpy(z['before:' + name]))
+        for name in net.state_names():
+            net.set_state(name, torch.from_numpy(z['state_before:' + name]))
+        net.refresh()
+    lg, ld = eng.step(torch.from_numpy(z['data']), torch.from_numpy(z['code']))
+    assert abs(lg - float(z['loss_gen'])) <= 1e-3 * abs(float(z['loss_gen'])) + 1e-7
+    assert abs(ld - float(z['loss_dis'])) <= 1e-3 * abs(float(z['loss_dis'])) + 1e-7
+    assert rel(eng.D.layers[-1].a[0].cpu().numpy(), z['scores']) < 1e-3
+    gmax = max(float(np.linalg.norm(z['grad:' + n])) for n in eng.D.var_offsets)
+    for net in (eng.G, eng.D):
+        for name in net.var_offsets:
+            ref = z['grad:' + name]
+            got = net.get_grad(name).cpu().numpy()
+            if np.linalg.norm(ref) < 1e-6 * gmax:
+                assert np.linalg.norm(got) < 1e-4 * gmax, name
+            else:
+                assert rel(got, ref) < 1e-3, (name, rel(got, ref))
+        for name in net.state_names():
+            assert rel(net.get_state(name).cpu().numpy(), z['state_after:' + name]) < 1e-3, name
+    # Adam step 1 moves every entry by ~lr * sign(g): compare the applied update normwise
+    num = den = 0.0
+    for net in (eng.G, eng.D):
+        for name in net.var_offsets:
+            got = net.get_variable(name).cpu().numpy().astype(np.float64)
+            num += np.linalg.norm(got - z['after:' + name]) ** 2
+            den += np.linalg.norm(z['after:' + name] - z['before:' + name]) ** 2
+    assert (num / den) ** 0.5 < 2e-2
+
+
+def test_sngan_training_api_and_checkpoint(cuda, tmp_path):
+    from oracle import architectures as oa
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200.GeneralTools.graph_func import Agent, get_ckpt
+    from mmdgan_b200.DeepLearning.my_sngan import SNGan
+    FLAGS.DEFAULT_OUT = str(tmp_path) + '/'
+    FLAGS.SILENT_MODE = True
+    arch = oa.tiny(act_k=2.6)
+    images = (np.random.RandomState(0).rand(64, 3, 8, 8) * 255).astype(np.uint8)
+    agent = Agent('toy', 'sngan_rep', load_ckpt=True, do_save=True, query_step=2, print_loss=True)
+    mdl = SNGan(arch, num_class=0, loss_type='rep', optimizer='adam', rep_weights=[0.0, -1.0])
+    torch.manual_seed(0)
+    losses = mdl.training(images, agent, 64, [5e-4, 2e-4], max_step=5, batch_size=16)
+    assert len(losses) == 2 and all(np.isfinite(losses)) and mdl.global_step == 5
+    path = get_ckpt(agent.ckpt_folder)
+    assert path is not None and path.endswith('toy.ckpt-5.npz')
+    z = np.load(path)
+    assert 'dis/l1_f/kernel/kernel' in z and 'dis/l1_f/kernel/SN/in_rand' in z and 'gen/l2_up/BN/BN/moving_mean' in z
+    assert 'dis/l1_f/kernel/kernel/Adam_0' in z and 'gen/l1/kernel/kernel/Adam_1_1' in z
+    # resume: a fresh model + agent reloads the state and continues from global step 5
+    mdl2 = SNGan(arch, num_class=0, loss_type='rep', optimizer='adam')
+    mdl2.training(images, agent, 64, [5e-4, 2e-4], max_step=2, batch_size=16)
+    assert mdl2.global_step == 7
+    with pytest.raises(NotImplementedError):
+        SNGan(arch, loss_type='hinge')
+    with pytest.raises(NotImplementedError):
+        mdl.training('cifar_NCHW/cifar', agent, 64, [5e-4, 2e-4], max_step=1, batch_size=16)

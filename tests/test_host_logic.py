@@ -1,0 +1,146 @@
+"""CPU: host-side logic of the product -- layer DSL mirror, kernel launch planning, C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import architectures as oa
+from oracle import net as onet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _routine(arch, key):
+    from mmdgan_b200.GeneralTools.layer_func import Net, Routine
+    net = Net(arch[key], key[:3], 'channels_first')
+    r = Routine(net)
+    r.add_input_layers([64, arch['code'][0][0]] if key == 'generator' else [64] + list(arch['input'][0]), [0])
+    r.seq_links(list(range(net.num_layers)))
+    r.add_output_layers([net.num_layers - 1])
+    return r
+
+
+@pytest.mark.parametrize('name', ['cifar', 'stl', 'celeba', 'lsun'])
+def test_layer_dsl_matches_oracle_shape_inference_and_sn_routing(name):
+    arch = oa.ARCHITECTURES[name]()
+    for key, scope, in_shape in (('generator', 'gen', [arch['code'][0][0]]), ('discriminator', 'dis', list(arch['input'][0]))):
+        layers = _routine(arch, key).ordered_layers()
+        specs = onet.build_net(arch[key], scope, in_shape)
+        assert len(layers) == len(specs)
+        for ly, sp in zip(layers, specs):
+            assert ly.kernel_shape == sp.kernel_shape
+            assert ly.op_output_shape[1:] == sp.op_out_shape and ly.output_shape[1:] == sp.out_shape
+            assert ly.kernel_name == sp.kernel_name
+            assert ('bias' in ly.ops) == sp.has_bias and ('BN' in ly.ops) == sp.has_bn
+            if sp.has_sn:
+                assert ly.use_u is sp.use_u and ly.sn_x_shape == sp.x_shape      # integer routing decision: exact
+                assert ly.sn_name == sp.sn_name
+
+
+def test_update_layer_design_defaults_and_errors():
+    from mmdgan_b200.GeneralTools.layer_func import update_layer_design, Net, Routine
+    d = update_layer_design({'name': 'l', 'out': 8})
+    assert (d['op'], d['kernel'], d['strides'], d['padding'], d['bias'], d['act'], d['act_k']) == ('c', 3, 1, 'SAME', 'b', 'linear', False)
+    assert update_layer_design({'name': 'l', 'out': 8, 'act_nm': 'bn'})['bias'] is None          # layer_func.py:1241-1242
+    assert 'kernel' not in update_layer_design({'name': 'l', 'out': 8, 'op': 'd'})
+    with pytest.raises(AttributeError):
+        update_layer_design({'name': 'l', 'out': 8, 'op': 'zz'})                                # layer_func.py:1275
+    r = Routine(Net([{'name': 'a', 'out': 8, 'type': 'res'}], 'n', 'channels_first'))
+    with pytest.raises(NotImplementedError):
+        r.add_input_layers([64, 3, 8, 8], [0])                                                  # layer_func.py:2067
+    r = Routine(Net([{'name': 'a', 'out': 8}], 'n', 'channels_first'))
+    r.add_input_layers([64, 3, 8, 8], [0])
+    with pytest.raises(AttributeError):
+        r.add_input_layers([64, 3, 8, 8], [0])                                                  # already added
+    with pytest.raises(NotImplementedError):
+        r({'x': torch.zeros(1)})                                                                # output layer not defined
+
+
+def test_linear_op_launch_plans():
+    from mmdgan_b200 import kernels as K
+    # D l3 of the CIFAR net: 128 -> 128 k3 s1 on 16x16
+    lop = K.LinearOp('c', [128, 16, 16], [128, 16, 16], 3, 1, device='cpu')
+    assert (lop.f['kpad'], lop.f['bn'], lop.f['rows_pad'], lop.f['classes']) == (1152, 128, 128, 1)
+    assert lop._fwd_geom()['cls'] == [(-1, -1, 0, 0)] and lop._dgrad_geom()['cls'] == [(-1, -1, 0, 0)]
+    R, NC, bn, splits, P = lop.wgrad_plan(512)
+    assert (R, NC, bn, P) == (128, 1152, 128, 512 * 256) and 1 <= splits <= P // 32
+    # stride-2 conv: input gradient = four parity classes of 2x2 taps
+    lop = K.LinearOp('c', [64, 32, 32], [128, 16, 16], 4, 2, device='cpu')
+    assert lop.d['classes'] == 4 and lop.d['taps'] == 4 and lop.d['kpad'] == 4 * 128
+    assert lop._dgrad_geom()['cls'] == [(-1, -1, 0, 0), (-1, 0, 0, 1), (0, -1, 1, 0), (0, 0, 1, 1)]
+    # image layers: 3 channels padded to 4, weight gradient puts the small side on N
+    lop = K.LinearOp('c', [64, 32, 32], [3, 32, 32], 3, 1, device='cpu')
+    assert lop.Cs_out == 4 and lop.w_swapped and lop.f['bn'] == 16 and lop.wgrad_plan(8)[:2] == (64, 36)
+    lop = K.LinearOp('c', [3, 32, 32], [64, 32, 32], 3, 1, device='cpu')
+    assert lop.Cs_in == 4 and not lop.w_swapped and lop.f['kpad'] == 64
+    # dense with NCHW-flatten permutation folded into the packed weights
+    lop = K.LinearOp('d', [8192], [16], in_flat=(512, 16), device='cpu')
+    assert lop.w_swapped and lop.in_flat == (512, 16) and lop.d['kpad'] == 32
+    with pytest.raises(NotImplementedError):
+        K.LinearOp('c', [8, 8, 8], [8, 8, 8], 5, 1, device='cpu')
+    with pytest.raises(AttributeError):
+        K.LinearOp('sc', [8, 8, 8], [8, 8, 8], 3, 1, device='cpu')
+
+
+def test_cabi_exports_every_declared_symbol():
+    from mmdgan_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'mmdgan_b200.h')).read()
+    declared = set(re.findall(r'\b(mmdgan_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    handle = _lib.load()
+    assert handle.mmdgan_version() >= 100
+
+
+def test_cabi_argument_validation_without_a_gpu():
+    from mmdgan_b200 import _lib
+    lib = _lib.load()
+    d = _lib.MmdDesc()
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rep', 0.0, -1.0) == 0
+    assert list(d.cD) == [-1.0, 0.0, 1.0] and list(d.bmode) == [0, 0, 0] and d.n_sigma == 1
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rmb', 0.0, -1.0) == 0
+    assert list(d.bmode) == [1, 0, 2] and list(d.bval) == [0.25, 0.0, 4.0]
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rmb', 1.0, 0.0) == 0 and list(d.bmode) == [1, 0, 2]
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rmb', 2.0, 1.0) == 0 and list(d.bmode) == [1, 0, 1]
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'mmd_g', 0.0, 0.0) == 0 and d.n_sigma == 5
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rep', 0.0, 0.0) == _lib.MMDGAN_EINVAL
+    assert b'w[0]-w[1] must be 1' in lib.mmdgan_last_error()
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'hinge', 0.0, -1.0) == _lib.MMDGAN_EINVAL
+    g = _lib.GemmDesc()
+    assert lib.mmdgan_gather_gemm(ctypes.byref(g), None) == _lib.MMDGAN_EINVAL          # null pointers: rejected before any CUDA call
+    assert lib.mmdgan_mmd_fwd_bwd(ctypes.byref(d), None) == _lib.MMDGAN_EINVAL
+    assert lib.mmdgan_adam(None, None, None, None, 10, 1e-3, 0.5, 0.999, 1e-8, None, None) == _lib.MMDGAN_EINVAL
+    assert lib.mmdgan_mmd_workspace(256) >= 64 * 6 * 4
+
+
+def test_product_fails_loudly_without_cuda():
+    """No CPU fallback: a CPU tensor reaching a kernel wrapper raises instead of silently computing."""
+    from mmdgan_b200 import kernels as K
+    from mmdgan_b200._lib import MmdganError
+    with pytest.raises(MmdganError):
+        K.make_lo_plane(torch.zeros(2, 4, 4))
+    from mmdgan_b200.GeneralTools.math_func import GANLoss
+    with pytest.raises(RuntimeError):
+        GANLoss().apply(torch.zeros(4, 16), torch.zeros(4, 16), 'rep', batch_size=4, d=16)
+    with pytest.raises(NotImplementedError):
+        GANLoss().apply(torch.zeros(4, 16), torch.zeros(4, 16), 'hinge', batch_size=4)
+
+
+def test_reference_style_matrix_functions_match_oracle():
+    from mmdgan_b200.GeneralTools import math_func as mf
+    from oracle import mmd as omm
+    g, r = torch.randn(6, 5, dtype=torch.float64), torch.randn(6, 5, dtype=torch.float64)
+    a, b = mf.get_squared_dist(g, r), omm.get_squared_dist(g, r)
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y)
+    assert torch.allclose(torch.stack(mf.mmd_g(*a, 6, custom_weights=[0.0, -1.0])), torch.stack(omm.mmd_g(*b, 6, custom_weights=[0.0, -1.0])))
+    assert torch.allclose(torch.stack(mf.mmd_g_bounded(*a, 6, lower_bound=0.25, upper_bound=4.0, custom_weights=[0.0, -1.0])),
+                          torch.stack(omm.mmd_g_bounded(*b, 6, lower_bound=0.25, upper_bound=4.0, custom_weights=[0.0, -1.0])))
+    assert mf.spatial_shape_after_conv([32, 32], 4, 2, 1, 'SAME') == [16, 16]
+    assert mf.spatial_shape_after_transpose_conv(6, 4, 2, 1, 'SAME') == 12
+    with pytest.raises(AttributeError):
+        mf.get_squared_dist(g, r, mode='zz')
