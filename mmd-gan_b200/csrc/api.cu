@@ -135,7 +135,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     memset(&p, 0, sizeof(p));
     p.src = d->src; p.src_plane = d->src_plane; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
     p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.TH = d->TH; p.TW = d->TW;
-    p.M = static_cast<int>(M); p.ksteps = d->kpad / 32;
+    p.M = static_cast<int>(M); p.ksteps = d->kpad / 16;
     p.dst = d->dst; p.dst_plane = d->dst_plane; p.Hd = d->Hd; p.Wd = d->Wd; p.Cd = d->Cd; p.osy = d->osy; p.osx = d->osx;
     p.Ncols = d->Ncols; p.alpha_k = d->alpha_k; p.sigma = d->sigma; p.bias = d->bias; p.act = d->act;
     p.aux = d->aux; p.aux_mode = d->aux_mode;

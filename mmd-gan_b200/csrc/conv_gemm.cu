@@ -19,7 +19,8 @@
 namespace mg {
 
 static constexpr int kBM = 128;
-static constexpr int kRowBytes = 128;  // 32 fp32 = one swizzle row
+static constexpr int kBK = 16;         // fp32 elements of K per pipeline stage
+static constexpr int kRowBytes = 64;   // 16 fp32 = one 64-byte swizzle row (SWIZZLE_64B): 32 KB stages, two CTAs per SM
 static constexpr int kProducerThreads = 128;
 static constexpr int kThreads = 192;
 static constexpr unsigned long long kWatchdogNs = 4000000000ull;
@@ -49,7 +50,8 @@ struct GemmCfg {
     static constexpr int A_BYTES = kBM * kRowBytes;  // per plane
     static constexpr int B_BYTES = BN * kRowBytes;
     static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
-    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    // budget for TWO resident CTAs per SM: the epilogue / prologue of one overlaps the main loop of the other
+    static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
     static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
     static constexpr int PITCH = BN * 4 + 16;  // staging row pitch in bytes
@@ -76,7 +78,7 @@ __device__ __forceinline__ float act_grad_from_output(float a, int mode) {
 }
 
 template <int BN, int NPASS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ ConvGemmParams p) {
     using Cfg = GemmCfg<BN, NPASS>;
@@ -125,14 +127,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
     if (warp < 4) {
         // ======================= A producers (gather) =======================
         const int t = threadIdx.x;
-        const int chunk = t & 7;
-        const int rbase = t >> 3;  // rows rbase + 16*i
-        const uint32_t swz_off = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
-        int by[8], bx[8], ib[8];  // by < -30000 marks an invalid row
+        const int chunk = t & 3;
+        const int rbase = t >> 2;  // rows rbase + 32*i
+        // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte address = (row >> 1) & 3
+        const uint32_t swz_off = static_cast<uint32_t>((chunk ^ ((rbase >> 1) & 3)) << 4);
+        int by[4], bx[4], ib[4];  // by < -30000 marks an invalid row
         const int HgWg = p.Hg * p.Wg;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int m = tile_m * kBM + rbase + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+            int m = tile_m * kBM + rbase + 32 * i;
             if (m < p.M) {
                 int n = m / HgWg;
                 int rem = m - n * HgWg;
@@ -153,7 +156,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
             mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 1);
-            const int u = j * 8 + chunk;
+            const int u = j * 4 + chunk;
             const int tap = u / upt;
             const int cq = u - tap * upt;
             const int a = tap / p.TW;
@@ -161,12 +164,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
             const bool tap_ok = tap < ntaps;
             const uint32_t a0 = smem_u32(stage_a(s, 0)) + swz_off;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 const int yy = by[i] + a;
                 const int xx = bx[i] + b;
                 const bool ok = tap_ok && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
                 const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 4) : 0;
-                const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 16 * i) * kRowBytes);
+                const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 32 * i) * kRowBytes);
                 if (p.debug & 1) continue;
                 cp_async16(dsta, p.src + off, ok ? 16u : 0u);
                 if (NPL == 2) cp_async16(dsta + Cfg::A_BYTES, p.src + p.src_plane + off, ok ? 16u : 0u);
@@ -184,8 +187,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
                 const uint32_t ph = (j / STAGES) & 1;
                 mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 2);
                 mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES);
-                tma_load_2d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * 32, row0);
-                if (NPL == 2) tma_load_2d(smem_u32(stage_b(s, 1)), &tmB1, &full_bar[s], j * 32, row0);
+                tma_load_2d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0);
+                if (NPL == 2) tma_load_2d(smem_u32(stage_b(s, 1)), &tmB1, &full_bar[s], j * kBK, row0);
             }
         }
     } else {
@@ -206,9 +209,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
                     const uint32_t abase = smem_u32(stage_a(s, pa));
                     const uint32_t bbase = smem_u32(stage_b(s, pb));
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t ad = smem_desc_sw128(abase + kk * 32, 16, 1024);
-                        const uint64_t bd = smem_desc_sw128(bbase + kk * 32, 16, 1024);
+                    for (int kk = 0; kk < kBK / 8; ++kk) {
+                        // K-major, SWIZZLE_64B (layout type 4): 8-row groups are 512 bytes apart; +32 bytes per K=8 slice
+                        const uint64_t ad = smem_desc(abase + kk * 32, 16, 512, 4u);
+                        const uint64_t bd = smem_desc(bbase + kk * 32, 16, 512, 4u);
                         umma_tf32(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kk > 0) ? 1u : 0u);
                     }
                 }
@@ -347,20 +351,20 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2D fp32 tensor map [rows][cols] (cols contiguous), box {32 cols, box_rows}, 128-byte swizzle (16-byte chunks, or
-// 32-byte chunks for MN-major tf32 operands), zero OOB fill
-int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows,
-                 int swizzle32b) {
+// 2D fp32 tensor map [rows][cols] (cols contiguous), box {box_cols, box_rows}, zero OOB fill
+// swizzle: 0 = 128B (16-byte chunks), 1 = 128B with 32-byte chunks (MN-major tf32 operands), 2 = 64B
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_cols,
+                 int box_rows, int swizzle) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_stride_elems) * 4};
-    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                               : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
@@ -369,8 +373,8 @@ static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane
                       cudaStream_t st) {
     using Cfg = GemmCfg<BN, NPASS>;
     CUtensorMap t0, t1;
-    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, BN, 0)) return -4;
-    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, BN, 0)) return -4;
+    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, kBK, BN, 2)) return -4;
+    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, kBK, BN, 2)) return -4;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=

@@ -16,10 +16,11 @@
 
 namespace mg {
 
-int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_rows,
-                 int swizzle32b);
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_cols,
+                 int box_rows, int swizzle);
 
 static constexpr int kWBM = 128;
+static constexpr int kWPix = 16;   // pixels (K) per pipeline stage: 32 KB stages at BN = 128, two CTAs per SM
 static constexpr int kWProducers = 128;
 static constexpr int kWThreads = 192;
 static constexpr unsigned long long kWWatchdogNs = 4000000000ull;
@@ -45,10 +46,11 @@ __device__ __forceinline__ void w_mbar_wait(uint64_t* bar, uint32_t parity, unsi
 template <int BN, int NPASS>
 struct WgradCfg {
     static constexpr int NPL = (NPASS == 3) ? 2 : 1;
-    static constexpr int A_BYTES = 4 * 4096;          // 4 channel chunks x (32 pixels x 128 B)
-    static constexpr int B_BYTES = (BN / 32) * 4096;  // BN/32 column chunks x (32 pixels x 128 B)
+    static constexpr int CHUNK_BYTES = kWPix * 128;             // one 32-channel chunk: kWPix pixels x 128 B
+    static constexpr int A_BYTES = 4 * CHUNK_BYTES;             // 4 channel chunks (M = 128)
+    static constexpr int B_BYTES = (BN / 32) * CHUNK_BYTES;     // BN/32 column chunks
     static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
-    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;   // two CTAs per SM
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
     static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
@@ -57,7 +59,7 @@ struct WgradCfg {
 };
 
 template <int BN, int NPASS>
-__global__ void __launch_bounds__(kWThreads, 1)
+__global__ void __launch_bounds__(kWThreads, 2)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                   const __grid_constant__ WgradParams p) {
     using Cfg = WgradCfg<BN, NPASS>;
@@ -80,7 +82,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
     const long long p_begin = static_cast<long long>(blockIdx.z) * p.p_per_split;
     long long p_end = p_begin + p.p_per_split;
     if (p_end > p.P) p_end = p.P;
-    const int ksteps = p_end > p_begin ? static_cast<int>((p_end - p_begin + 31) / 32) : 0;
+    const int ksteps = p_end > p_begin ? static_cast<int>((p_end - p_begin + kWPix - 1) / kWPix) : 0;
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmP0);
@@ -110,7 +112,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
         // ======================= G producers (gather, MN-major) =======================
         const int t = threadIdx.x;
         const int chunk = t & 7;
-        const int rbase = t >> 3;  // pixel rows rbase, rbase + 16 of the k-step
+        const int rbase = t >> 3;  // pixel row rbase (0..15) of the k-step
         const int upt = p.Cs >> 2;
         const int ntaps = p.TH * p.TW;
         int ta[NCH], tb[NCH], tcq[NCH];
@@ -131,9 +133,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
             w_mbar_wait(&empty_bar[s], ph ^ 1, p.err, 11);
             const uint32_t b0 = smem_u32(stage_b(s, 0));
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < kWPix / 16; ++i) {
                 const int r = rbase + 16 * i;
-                const long long pp = p_begin + static_cast<long long>(j) * 32 + r;
+                const long long pp = p_begin + static_cast<long long>(j) * kWPix + r;
                 const bool pok = pp < p_end;
                 int n = 0, y = 0, x = 0;
                 if (pok) {
@@ -153,8 +155,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                     const bool ok = pok && tok[q] && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
                     const long long off =
                         ok ? (static_cast<long long>(n * p.Hs * p.Ws + yy * p.Ws + xx) * p.Cs + tcq[q] * 4) : 0;
-                    cp_async16(drow + q * 4096, p.g + off, ok ? 16u : 0u);
-                    if (NPL == 2) cp_async16(drow + q * 4096 + Cfg::B_BYTES, p.g + p.g_plane + off, ok ? 16u : 0u);
+                    cp_async16(drow + q * Cfg::CHUNK_BYTES, p.g + off, ok ? 16u : 0u);
+                    if (NPL == 2) cp_async16(drow + q * Cfg::CHUNK_BYTES + Cfg::B_BYTES, p.g + p.g_plane + off, ok ? 16u : 0u);
                 }
             }
             cp_async_mbar_arrive_noinc(&full_bar[s]);   // asynchronous publication, see conv_gemm.cu
@@ -167,12 +169,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                 const uint32_t ph = (j / STAGES) & 1;
                 w_mbar_wait(&empty_bar[s], ph ^ 1, p.err, 12);
                 mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::A_BYTES);
-                const int prow = static_cast<int>(p_begin + static_cast<long long>(j) * 32);
+                const int prow = static_cast<int>(p_begin + static_cast<long long>(j) * kWPix);
 #pragma unroll
                 for (int mc = 0; mc < 4; ++mc) {
-                    tma_load_2d(smem_u32(stage_a(s, 0)) + mc * 4096, &tmP0, &full_bar[s], tile_m * kWBM + mc * 32, prow);
+                    tma_load_2d(smem_u32(stage_a(s, 0)) + mc * Cfg::CHUNK_BYTES, &tmP0, &full_bar[s], tile_m * kWBM + mc * 32, prow);
                     if (NPL == 2)
-                        tma_load_2d(smem_u32(stage_a(s, 1)) + mc * 4096, &tmP1, &full_bar[s], tile_m * kWBM + mc * 32, prow);
+                        tma_load_2d(smem_u32(stage_a(s, 1)) + mc * Cfg::CHUNK_BYTES, &tmP1, &full_bar[s], tile_m * kWBM + mc * 32, prow);
                 }
             }
         }
@@ -193,9 +195,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                     const uint32_t abase = smem_u32(stage_a(s, pa));
                     const uint32_t bbase = smem_u32(stage_b(s, pb));
 #pragma unroll
-                    for (int kg = 0; kg < 4; ++kg) {
-                        const uint64_t ad = smem_desc(abase + kg * 1024, 4096, 512, 1u);
-                        const uint64_t bd = smem_desc(bbase + kg * 1024, 4096, 512, 1u);
+                    for (int kg = 0; kg < kWPix / 8; ++kg) {
+                        const uint64_t ad = smem_desc(abase + kg * 1024, Cfg::CHUNK_BYTES, 512, 1u);
+                        const uint64_t bd = smem_desc(bbase + kg * 1024, Cfg::CHUNK_BYTES, 512, 1u);
                         umma_tf32(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kg > 0) ? 1u : 0u);
                     }
                 }
@@ -248,8 +250,8 @@ template <int BN, int NPASS>
 static int launch_wcfg(const WgradParams& p, const float* plain, long long plain_plane, int splits, cudaStream_t st) {
     using Cfg = WgradCfg<BN, NPASS>;
     CUtensorMap t0, t1;
-    if (make_tmap_2d(&t0, plain, p.P, p.Cp, p.Cp, 32, 1)) return -4;
-    if (make_tmap_2d(&t1, plain + (NPASS == 3 ? plain_plane : 0), p.P, p.Cp, p.Cp, 32, 1)) return -4;
+    if (make_tmap_2d(&t0, plain, p.P, p.Cp, p.Cp, 32, kWPix, 1)) return -4;
+    if (make_tmap_2d(&t1, plain + (NPASS == 3 ? plain_plane : 0), p.P, p.Cp, p.Cp, 32, kWPix, 1)) return -4;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(wgrad_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
