@@ -95,7 +95,7 @@ typedef struct mmdgan_gemm_desc {
     float* colsumsq;
     long long colsum_rows;
     int out_mode;       /* 0 raw + lo plane, 1 rn-tf32 single plane, 2 raw single plane */
-    int bn;             /* N tile: 16, 32, 64, 128 */
+    int bn;             /* N tile: 16, 32, 64, 128, 256 */
     int npass;          /* 3 (fp32-grade tf32x3) or 1 (tf32) */
     mmdgan_gemm_class cls[4];
 } mmdgan_gemm_desc;

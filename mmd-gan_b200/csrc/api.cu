@@ -118,7 +118,8 @@ int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg) {
 int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     if (!d || !d->src || !d->w || !d->dst) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: null pointer");
     if (d->npass != 1 && d->npass != 3) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass must be 1 or 3");
-    if (d->bn != 16 && d->bn != 32 && d->bn != 64 && d->bn != 128) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bn must be 16/32/64/128");
+    if (d->bn != 16 && d->bn != 32 && d->bn != 64 && d->bn != 128 && d->bn != 256)
+        return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bn must be 16/32/64/128/256");
     if (d->Nimg <= 0 || d->Hs <= 0 || d->Ws <= 0 || d->Cs <= 0 || (d->Cs & 3) || d->Hg <= 0 || d->Wg <= 0 || d->TH <= 0 || d->TW <= 0)
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad source shape");
     if (d->kpad <= 0 || (d->kpad & 31) || d->kpad < d->TH * d->TW * d->Cs)

@@ -54,7 +54,8 @@ struct GemmCfg {
     static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
     static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
-    static constexpr int PITCH = BN * 4 + 16;  // staging row pitch in bytes
+    static constexpr int EN = BN > 128 ? 128 : BN;   // epilogue column group
+    static constexpr int PITCH = EN * 4 + 16;        // staging row pitch in bytes
     static constexpr int STAGING_BYTES = kBM * PITCH;
     static constexpr int RED_BYTES = 2 * kProducerThreads * 16;
     static constexpr int PROW_BYTES = kBM * 8;
@@ -225,30 +226,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
     }
 
     // ======================= epilogue (warps 0-3) =======================
+    // processed in column groups of EN <= 128 so that the staging tile fits the (now idle) pipeline buffers
     if (warp < 4) {
+        constexpr int EN = Cfg::EN;
         mbar_wait_wd(accum_bar, 0, p.err, 4);
         tc_fence_after();
         const int row = warp * 32 + lane;
+        const int t = threadIdx.x;
         uint8_t* stg = smem;  // pipeline buffers are free: every MMA has completed
-        {
-            float v[32];
-            if (BN >= 32) {
-#pragma unroll 1
-                for (int cc = 0; cc < BN / 32; ++cc) {
-                    tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 32, v);
-                    tmem_ld_wait();
-                    float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH + cc * 128);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-            } else {
-                tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
-                tmem_ld_wait();
-                float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-        }
         // destination pixel of this thread's row, computed once (two integer divisions) instead of per element
         long long* prow_s = reinterpret_cast<long long*>(smem + Cfg::STAGING_BYTES + Cfg::RED_BYTES);
         {
@@ -264,67 +249,89 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
             }
             prow_s[row] = pr;
         }
-        tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-
-        constexpr int QPR = BN / 4;  // float4 per row
-        const int t = threadIdx.x;
-        const int colq = t % QPR;
-        const int col = tile_n * BN + colq * 4;
-        const bool col_ok = col < p.Ncols;
         const float alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
-        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int QPR = EN / 4;  // float4 per staged row
+        const int colq = t % QPR;
         constexpr int ITERS = (kBM * QPR) / kProducerThreads;
-#pragma unroll 2
-        for (int it = 0; it < ITERS; ++it) {
-            const int e = t + it * kProducerThreads;
-            const int r = e / QPR;
-            const long long prow = prow_s[r];
-            if (prow < 0 || !col_ok || (p.debug & 4)) continue;
-            float4 v = *reinterpret_cast<const float4*>(stg + r * Cfg::PITCH + colq * 16);
-            v.x = apply_act(fmaf(v.x, alpha, bias4.x), p.act);
-            v.y = apply_act(fmaf(v.y, alpha, bias4.y), p.act);
-            v.z = apply_act(fmaf(v.z, alpha, bias4.z), p.act);
-            v.w = apply_act(fmaf(v.w, alpha, bias4.w), p.act);
-            if (p.aux) {
-                const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
-                const float4 a4 = *reinterpret_cast<const float4*>(p.aux + arow * p.Cd + col);
-                v.x *= act_grad_from_output(a4.x, p.aux_mode);
-                v.y *= act_grad_from_output(a4.y, p.aux_mode);
-                v.z *= act_grad_from_output(a4.z, p.aux_mode);
-                v.w *= act_grad_from_output(a4.w, p.aux_mode);
-            }
-            if (p.out_mode == 1) {
-                v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
-            }
-            float* o = p.dst + prow * p.Cd + col;
-            *reinterpret_cast<float4*>(o) = v;
-            if (p.out_mode == 0)
-                *reinterpret_cast<float4*>(o + p.dst_plane) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-            if (prow < p.colsum_rows) {
-                cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-                cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
-                cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
-            }
-        }
-        if (p.colsum) {
-            float4* red = reinterpret_cast<float4*>(smem + Cfg::STAGING_BYTES);
-            red[t] = cs;
-            red[kProducerThreads + t] = cq;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (t < QPR && col_ok) {
-                float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int k = t; k < kProducerThreads; k += QPR) {
-                    const float4 a1 = red[k], a2 = red[kProducerThreads + k];
-                    s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
-                    s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
+#pragma unroll 1
+        for (int h = 0; h < BN / EN; ++h) {
+            {
+                float v[32];
+                if (EN >= 32) {
+#pragma unroll 1
+                    for (int cc = 0; cc < EN / 32; ++cc) {
+                        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + h * EN + cc * 32, v);
+                        tmem_ld_wait();
+                        float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH + cc * 128);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                } else {
+                    tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
+                    tmem_ld_wait();
+                    float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
-                const long long tl = static_cast<long long>(blockIdx.z) * gridDim.x + blockIdx.x;
-                *reinterpret_cast<float4*>(p.colsum + tl * p.Ncols + col) = s1;
-                if (p.colsumsq) *reinterpret_cast<float4*>(p.colsumsq + tl * p.Ncols + col) = s2;
             }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            const int col = tile_n * BN + h * EN + colq * 4;
+            const bool col_ok = col < p.Ncols;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+            for (int it = 0; it < ITERS; ++it) {
+                const int e = t + it * kProducerThreads;
+                const int r = e / QPR;
+                const long long prow = prow_s[r];
+                if (prow < 0 || !col_ok || (p.debug & 4)) continue;
+                float4 v = *reinterpret_cast<const float4*>(stg + r * Cfg::PITCH + colq * 16);
+                v.x = apply_act(fmaf(v.x, alpha, bias4.x), p.act);
+                v.y = apply_act(fmaf(v.y, alpha, bias4.y), p.act);
+                v.z = apply_act(fmaf(v.z, alpha, bias4.z), p.act);
+                v.w = apply_act(fmaf(v.w, alpha, bias4.w), p.act);
+                if (p.aux) {
+                    const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
+                    const float4 a4 = *reinterpret_cast<const float4*>(p.aux + arow * p.Cd + col);
+                    v.x *= act_grad_from_output(a4.x, p.aux_mode);
+                    v.y *= act_grad_from_output(a4.y, p.aux_mode);
+                    v.z *= act_grad_from_output(a4.z, p.aux_mode);
+                    v.w *= act_grad_from_output(a4.w, p.aux_mode);
+                }
+                if (p.out_mode == 1) {
+                    v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
+                }
+                float* o = p.dst + prow * p.Cd + col;
+                *reinterpret_cast<float4*>(o) = v;
+                if (p.out_mode == 0)
+                    *reinterpret_cast<float4*>(o + p.dst_plane) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                if (prow < p.colsum_rows) {
+                    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+                    cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
+                    cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
+                }
+            }
+            if (p.colsum) {
+                float4* red = reinterpret_cast<float4*>(smem + Cfg::STAGING_BYTES);
+                red[t] = cs;
+                red[kProducerThreads + t] = cq;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (t < QPR && col_ok) {
+                    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = t; k < kProducerThreads; k += QPR) {
+                        const float4 a1 = red[k], a2 = red[kProducerThreads + k];
+                        s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+                        s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
+                    }
+                    const long long tl = static_cast<long long>(blockIdx.z) * gridDim.x + blockIdx.x;
+                    *reinterpret_cast<float4*>(p.colsum + tl * p.Ncols + col) = s1;
+                    if (p.colsumsq) *reinterpret_cast<float4*>(p.colsumsq + tl * p.Ncols + col) = s2;
+                }
+            }
+            if (h + 1 < BN / EN) asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile is reused by the next group
         }
     }
     tc_fence_before();
@@ -392,8 +399,8 @@ int launch_conv_gemm(const ConvGemmParams& p, const float* w, long long w_plane,
                      int bn, int npass, cudaStream_t st) {
 #define MG_CASE(B, N) \
     if (bn == B && npass == N) return launch_cfg<B, N>(p, w, w_plane, w_rows, kpad, classes, st);
-    MG_CASE(16, 3) MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3)
-    MG_CASE(16, 1) MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1)
+    MG_CASE(16, 3) MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3) MG_CASE(256, 3)
+    MG_CASE(16, 1) MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1) MG_CASE(256, 1)
 #undef MG_CASE
     return -1;
 }

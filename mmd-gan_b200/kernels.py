@@ -16,6 +16,7 @@ ACT = {'linear': 0, None: 0, 'lrelu': 1, 'relu': 2, 'tanh': 3}
 PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRAD, PACK_DENSE_FWD, PACK_DENSE_DGRAD = range(7)
 
 
+GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
 
@@ -58,9 +59,9 @@ def round_up(a, b):
     return (a + b - 1) // b * b
 
 
-def pick_bn(ncols, lo=16):
+def pick_bn(ncols, lo=16, hi=128):
     bn = lo
-    while bn < 128 and bn < ncols:
+    while bn < hi and bn < ncols:
         bn *= 2
     return bn
 
@@ -190,7 +191,14 @@ class LinearOp(object):
         d.aux, d.aux_mode = _ptr(aux), aux_mode
         d.aux_wrap_at, d.aux_wrap_len = aux_wrap if aux_wrap else (0, 0)
         d.colsum, d.colsumsq, d.colsum_rows = _ptr(colsum), _ptr(colsumsq), colsum_rows
-        d.out_mode, d.bn, d.npass = out_mode, g['bn'], self.npass
+        bn = g['bn']
+        if GEMM_BN_MAX >= 256 and g['ncols'] % 256 == 0:
+            # 128 x 256 tiles halve the re-reads of the gathered operand, but leave only two pipeline stages per CTA and
+            # double the epilogue: measured to pay off only while the grid still fills the 2 x 148 CTA slots
+            tiles = ((nimg * d.Hg * d.Wg + 127) // 128) * (g['ncols'] // 256) * g['classes']
+            if tiles >= 190 and (g['ncols'] >= 512 or aux is None):
+                bn = 256
+        d.out_mode, d.bn, d.npass = out_mode, bn, self.npass
         if out_mode == 0 and dst.shape[0] != 2:
             raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 needs a two-plane destination')
         for i, (oy, ox, ooy, oox) in enumerate(geom['cls']):
