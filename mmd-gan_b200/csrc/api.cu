@@ -124,6 +124,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad source shape");
     if (d->kpad <= 0 || (d->kpad & 31) || d->kpad < d->TH * d->TW * d->Cs)
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: kpad %d does not cover %d taps x %d channels", d->kpad, d->TH * d->TW, d->Cs);
+    if (d->Cs > 16 && (d->Cs & 15)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: Cs must be < 16 or a multiple of 16");
     if (d->classes < 1 || d->classes > 4 || d->w_rows <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad class count");
     if (d->Ncols <= 0 || (d->Ncols & 3) || d->Cd < d->Ncols || (d->Cd & 3)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad output columns");
     if (!al16(d->src) || !al16(d->dst) || !al16(d->w) || (d->src_plane & 3) || (d->dst_plane & 3) || (d->w_plane & 3))

@@ -19,6 +19,7 @@
 namespace mg {
 
 static constexpr int kBM = 128;
+static constexpr int kPipeBudget = 96;  // KB of pipeline stages per CTA (two CTAs per SM)
 static constexpr int kBK = 16;         // fp32 elements of K per pipeline stage
 static constexpr int kRowBytes = 64;   // 16 fp32 = one 64-byte swizzle row (SWIZZLE_64B): 32 KB stages, two CTAs per SM
 static constexpr int kProducerThreads = 128;
@@ -51,7 +52,7 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * kRowBytes;
     static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
     // budget for TWO resident CTAs per SM: the epilogue / prologue of one overlaps the main loop of the other
-    static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (kPipeBudget * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
     static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
     static constexpr int EN = BN > 128 ? 128 : BN;   // epilogue column group
@@ -151,18 +152,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
                 ib[i] = 0;
             }
         }
-        const int upt = p.Cs >> 2;
+        // K order: (channel chunk of CW = min(Cs, 16), tap, channel within chunk) -- taps innermost, so consecutive
+        // k-steps re-read neighbouring pixels of the SAME 64-byte channel chunk and hit L1
+        const int cw4 = (p.Cs >= 16 ? 16 : p.Cs) >> 2;   // 16-byte units per (chunk, tap) group
+        const int ncc = p.Cs / (cw4 * 4);
         const int ntaps = p.TH * p.TW;
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
             mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 1);
             const int u = j * 4 + chunk;
-            const int tap = u / upt;
-            const int cq = u - tap * upt;
+            const int g = u / cw4;
+            const int cc = g / ntaps;
+            const int tap = g - cc * ntaps;
+            const int cq = cc * cw4 + (u - g * cw4);
             const int a = tap / p.TW;
             const int b = tap - a * p.TW;
-            const bool tap_ok = tap < ntaps;
+            const bool tap_ok = cc < ncc;
             const uint32_t a0 = smem_u32(stage_a(s, 0)) + swz_off;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {

@@ -72,7 +72,14 @@ __global__ void pack_weights_kernel(const PackParams p) {
         const long long f = i - cls * per_class;
         const int row = static_cast<int>(f / p.kpad);
         const int col = static_cast<int>(f - static_cast<long long>(row) * p.kpad);
-        const int tap = col / p.Cs, ch = col - tap * p.Cs;
+        // K order of the gather-GEMM: (channel chunk of CW = min(Cs, 16), tap, channel within the chunk)
+        const int cw = p.Cs >= 16 ? 16 : p.Cs;
+        const int ntaps = (p.mode == PACK_CONV_DGRAD_S2 || p.mode == PACK_TC_FWD) ? 4 : ((p.mode >= PACK_DENSE_FWD) ? 1 : p.k * p.k);
+        const int grp = col / cw;
+        const int cc = grp / ntaps;
+        int tap = grp - cc * ntaps;
+        const int ch = cc * cw + (col - grp * cw);
+        if (ch >= p.Cs) tap = 1 << 20;   // K padding
         const int ph = cls >> 1, pw = cls & 1;
         float v = 0.f;
         switch (p.mode) {

@@ -137,6 +137,14 @@ def test_step_parity_stl_architecture_rmb(cuda):
     check_step(orc, eng, arch, B, seed=13)
 
 
+def test_step_parity_celeba_lsun_architecture(cuda):
+    """my_test_celebA.py / my_test_lsun.py network: 64x64, 10 SN layers, 1024 channels, 16384-feature flatten."""
+    arch = oa.celeba(act_k=2.3)
+    B = 2
+    orc, eng = make_pair(arch, B, 'rep')
+    check_step(orc, eng, arch, B, seed=17)
+
+
 def test_three_full_steps_and_state(cuda):
     """Three simultaneous G/D updates: loss trajectory, Adam-updated variables, BN moving statistics, in_rand."""
     arch = oa.tiny(act_k=2.6)
