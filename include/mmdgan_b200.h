@@ -62,6 +62,16 @@ typedef struct mmdgan_pack_desc {
     int in_C, in_HW, out_C, out_HW; /* dense: NCHW-flatten <-> NHWC-flatten feature permutation (HW <= 1: identity) */
 } mmdgan_pack_desc;
 int mmdgan_pack_weights(const mmdgan_pack_desc* d, void* stream);
+/* every parameter-derived buffer of a net in ONE launch after an optimiser update: `jobs_device` is an array of jobs in
+ * DEVICE memory (kind 0 = pack weights, kind 1 = permute / pad a per-feature vector), built once at start-up */
+typedef struct mmdgan_refresh_job {
+    int kind, pad0;
+    mmdgan_pack_desc pack;
+    const float* src;
+    float* dst;
+    int n, C, HW, inverse;
+} mmdgan_refresh_job;
+int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long max_elems, void* stream);
 int mmdgan_permute_features(const float* src, float* dst, int n, int C, int HW, int inverse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -102,6 +112,11 @@ typedef struct mmdgan_gemm_desc {
 int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream);
 /* number of M tiles (rows of the colsum workspace per class) */
 int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg);
+
+/* out[m][n] = alpha * sum_k a[m][k] * wt[n][k] + bias[n] for N in {4,8,16,32} output columns (the critic's score layer,
+ * tf.matmul at layer_func.py:909-911 with 16 outputs): fp32 CUDA-core kernel, wt = hi plane of the packed forward operand */
+int mmdgan_dense_small_fwd(const float* a, int rows, int K, const float* wt, int kpad, int N, float alpha_k, const float* sigma,
+                           const float* bias, float* out, int ldo, void* stream);
 
 /* Weight gradient: W[r][(t,c)] = sum_p P[p][r] * G[g(p,t)][c] (filter gradients of the ops above and the
  * d(sigma)/dW term of SpectralNorm, GeneralTools/math_func.py:661-672).  out: [splits][Cp][TH*TW*Cs]. */

@@ -66,6 +66,11 @@ class PackDesc(C.Structure):
         ('in_C', C.c_int), ('in_HW', C.c_int), ('out_C', C.c_int), ('out_HW', C.c_int)]
 
 
+class RefreshJob(C.Structure):
+    _fields_ = [('kind', C.c_int), ('pad0', C.c_int), ('pack', PackDesc), ('src', C.c_void_p), ('dst', C.c_void_p),
+                ('n', C.c_int), ('C', C.c_int), ('HW', C.c_int), ('inverse', C.c_int)]
+
+
 class MmdDesc(C.Structure):
     _fields_ = [
         ('gen_loc', C.c_void_p), ('real_loc', C.c_void_p), ('gen_all', C.c_void_p), ('real_all', C.c_void_p),
@@ -88,6 +93,8 @@ SYMBOLS = {
     'mmdgan_make_lo_plane': (_I, [_P, _P, _LL, _P]),
     'mmdgan_pack_weights': (_I, [C.POINTER(PackDesc), _P]),
     'mmdgan_permute_features': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'mmdgan_refresh': (_I, [_P, _I, _LL, _P]),
+    'mmdgan_dense_small_fwd': (_I, [_P, _I, _I, _P, _I, _I, _F, _P, _P, _P, _I, _P]),
     'mmdgan_gather_gemm': (_I, [C.POINTER(GemmDesc), _P]),
     'mmdgan_gather_gemm_tiles': (_I, [_I, _I, _I]),
     'mmdgan_wgrad_gemm': (_I, [C.POINTER(WgradDesc), _P]),

@@ -39,6 +39,8 @@ int l_bn_bwd_apply(const float*, const float*, const float*, const float*, const
                    long long, int, float*, long long, cudaStream_t);
 int l_adam(float*, float*, float*, const float*, long long, float, float, float, float, const int*, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
+int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
+int l_dense_small_fwd(const float*, int, int, const float*, int, int, float, const float*, const float*, float*, int, cudaStream_t);
 int l_nan_flag(const float*, int, int*, cudaStream_t);
 }  // namespace mg
 
@@ -299,6 +301,21 @@ int mmdgan_mmd_fwd_bwd(const mmdgan_mmd_desc* d, void* stream) {
     p.counter = reinterpret_cast<unsigned int*>(d->workspace);
     p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + 16);
     return wrap(mg::launch_mmd(p, S(stream)), "mmdgan_mmd_fwd_bwd");
+}
+
+int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long max_elems, void* stream) {
+    if (!jobs_device) return fail(MMDGAN_EINVAL, "mmdgan_refresh: null pointer");
+    if (njobs <= 0) return MMDGAN_OK;
+    if (njobs > 65535 || max_elems <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_refresh: bad job count");
+    static_assert(sizeof(mmdgan_refresh_job) == sizeof(mg::RefreshJob), "job layout");
+    return wrap(mg::l_refresh(reinterpret_cast<const mg::RefreshJob*>(jobs_device), njobs, max_elems, S(stream)), "mmdgan_refresh");
+}
+int mmdgan_dense_small_fwd(const float* a, int rows, int K, const float* wt, int kpad, int N, float alpha_k, const float* sigma,
+                           const float* bias, float* out, int ldo, void* stream) {
+    if (!a || !wt || !out) return fail(MMDGAN_EINVAL, "mmdgan_dense_small_fwd: null pointer");
+    if (rows <= 0 || K <= 0 || (K & 3) || kpad < K || (kpad & 3) || ldo < N) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad shape");
+    if (N != 4 && N != 8 && N != 16 && N != 32) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: N must be 4/8/16/32");
+    return wrap(mg::l_dense_small_fwd(a, rows, K, wt, kpad, N, alpha_k, sigma, bias, out, ldo, S(stream)), "mmdgan_dense_small_fwd");
 }
 
 int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float beta1, float beta2, float eps,

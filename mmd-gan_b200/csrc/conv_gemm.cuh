@@ -95,6 +95,14 @@ struct PackParams {
     int rows_pad, kpad, classes;
     int in_C, in_HW, out_C, out_HW;  // dense only: NCHW-flatten <-> NHWC-flatten permutation of features
 };
+struct RefreshJob {
+    int kind;   // 0: pack weights, 1: permute / pad a per-feature vector
+    int pad0;
+    PackParams pack;
+    const float* src;
+    float* dst;
+    int n, C, HW, inverse;
+};
 // Split-K weight-gradient partials [splits][R][NC] -> canonical layout, canon index = base + r*sr + t*st + c*sc with
 // column = t*Cg + c.  Also emits per-block partial <G, W> (for the spectral-norm term) when dots != null.
 struct WredParams {

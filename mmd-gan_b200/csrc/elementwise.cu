@@ -63,11 +63,9 @@ __device__ __forceinline__ int perm_feature(int j, int C, int HW) {  // internal
     return c * HW + hw;
 }
 
-__global__ void pack_weights_kernel(const PackParams p) {
+__device__ __forceinline__ void pack_one(const PackParams& p, long long i) {
     const long long per_class = static_cast<long long>(p.rows_pad) * p.kpad;
-    const long long total = per_class * p.classes;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    {
         const int cls = static_cast<int>(i / per_class);
         const long long f = i - cls * per_class;
         const int row = static_cast<int>(f / p.kpad);
@@ -132,6 +130,12 @@ __global__ void pack_weights_kernel(const PackParams p) {
         }
     }
 }
+__global__ void pack_weights_kernel(const PackParams p) {
+    const long long total = static_cast<long long>(p.rows_pad) * p.kpad * p.classes;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        pack_one(p, i);
+}
 
 // out[j'] = src[perm(j')]: canonical per-feature vector (bias / gamma / beta) -> internal NHWC-flatten order
 __global__ void permute_features_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int C, int HW, int inverse) {
@@ -139,6 +143,61 @@ __global__ void permute_features_kernel(const float* __restrict__ src, float* __
     if (j >= n) return;
     if (inverse) dst[perm_feature(j, C, HW)] = src[j];
     else dst[j] = src[perm_feature(j, C, HW)];
+}
+
+// One launch refreshes every parameter-derived buffer of a net after an update: weight packing jobs and feature
+// permutation / padding jobs; blockIdx.y selects the job, the jobs live in device memory (built once at start-up).
+__device__ __forceinline__ void pack_one(const PackParams& p, long long i);
+__global__ void refresh_kernel(const RefreshJob* __restrict__ jobs) {
+    const RefreshJob& job = jobs[blockIdx.y];
+    if (job.kind == 0) {
+        const long long total = static_cast<long long>(job.pack.rows_pad) * job.pack.kpad * job.pack.classes;
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+             i += static_cast<long long>(gridDim.x) * blockDim.x)
+            pack_one(job.pack, i);
+    } else {
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < job.n; j += gridDim.x * blockDim.x) {
+            if (job.inverse) job.dst[perm_feature(j, job.C, job.HW)] = job.src[j];
+            else job.dst[j] = job.src[perm_feature(j, job.C, job.HW)];
+        }
+    }
+}
+
+// out[m][n] = alpha * sum_k A[m][k] * Wt[n][k] + bias[n] for a handful of output columns (the 16 critic scores):
+// fp32 FFMA, one block per row, float4 loads, warp-shuffle + shared-memory reduction.  The tensor-core tile would be
+// 94 % padding here (N = 16 of 128 lanes x 8192 deep on 4 CTAs).
+template <int N>
+__global__ void __launch_bounds__(256) dense_small_fwd_kernel(const float* __restrict__ a, int K, const float* __restrict__ wt, int kpad,
+                                                             float alpha_k, const float* __restrict__ sigma,
+                                                             const float* __restrict__ bias, float* __restrict__ out, int ldo) {
+    __shared__ float red[8][N];
+    const float* arow = a + static_cast<long long>(blockIdx.x) * K;
+    float acc[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc[n] = 0.f;
+    for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
+        const float4 x = *reinterpret_cast<const float4*>(arow + k);
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            const float4 w = *reinterpret_cast<const float4*>(wt + static_cast<long long>(n) * kpad + k);
+            acc[n] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[n]))));
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+#pragma unroll
+        for (int n = 0; n < N; ++n) red[warp][n] = acc[n];
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        const float alpha = sigma ? alpha_k / __ldg(sigma) : alpha_k;
+        out[static_cast<long long>(blockIdx.x) * ldo + threadIdx.x] = fmaf(s, alpha, bias ? bias[threadIdx.x] : 0.f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
@@ -176,8 +235,16 @@ __global__ void wgrad_reduce_kernel(const WredParams p) {
         const int col = static_cast<int>(i - static_cast<long long>(r) * p.NC);
         const int t = col / p.Cg, c = col - t * p.Cg;
         if (c >= p.Cvalid || r >= p.Rvalid) continue;
-        float s = 0.f;
-        for (int z = 0; z < p.splits; ++z) s += p.partials[static_cast<long long>(z) * total + i];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int z = 0;
+        for (; z + 4 <= p.splits; z += 4) {     // four independent loads in flight; the summation order stays fixed
+            s0 += p.partials[static_cast<long long>(z) * total + i];
+            s1 += p.partials[static_cast<long long>(z + 1) * total + i];
+            s2 += p.partials[static_cast<long long>(z + 2) * total + i];
+            s3 += p.partials[static_cast<long long>(z + 3) * total + i];
+        }
+        for (; z < p.splits; ++z) s0 += p.partials[static_cast<long long>(z) * total + i];
+        const float s = (s0 + s1) + (s2 + s3);
         const long long ci = p.base + perm_feature(r, p.r_perm_C, p.r_perm_HW) * p.sr + t * p.st +
                              perm_feature(c, p.c_perm_C, p.c_perm_HW) * p.sc;
         p.out[ci] = s;
@@ -196,13 +263,16 @@ __global__ void wgrad_reduce_kernel(const WredParams p) {
 // grad = m * G - (m / sigma) * <G, W> * S,  m = act_k / sigma  (layer_func.py:884-918 differentiated)
 __global__ void sn_grad_combine_kernel(float* __restrict__ g, const float* __restrict__ s, const double* __restrict__ dots, int ndots,
                                        const float* __restrict__ sigma, float act_k, long long n) {
-    __shared__ double dsum;
-    if (threadIdx.x == 0) {
-        double d = 0.0;
-        for (int i = 0; i < ndots; ++i) d += dots[i];
-        dsum = d;
-    }
+    __shared__ double red[256];
+    double d = 0.0;
+    for (int i = threadIdx.x; i < ndots; i += blockDim.x) d += dots[i];     // fixed order per thread, fixed tree below
+    red[threadIdx.x] = d;
     __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double dsum = red[0];
     const float sg = *sigma;
     const float m = act_k / sg;
     const float coef = static_cast<float>(static_cast<double>(m) / static_cast<double>(sg) * dsum);
@@ -444,6 +514,20 @@ int l_bn_bwd_apply(const float* da, const float* z, const float* mean, const flo
 int l_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float b1, float b2, float eps, const int* step,
            cudaStream_t st) {
     adam_kernel<<<grid_for(n), kBS, 0, st>>>(w, m, v, g, n, lr, b1, b2, eps, step);
+    return MG_CHECK_LAUNCH();
+}
+int l_refresh(const RefreshJob* jobs, int njobs, long long max_elems, cudaStream_t st) {
+    dim3 grid(grid_for(max_elems), njobs);
+    refresh_kernel<<<grid, kBS, 0, st>>>(jobs);
+    return MG_CHECK_LAUNCH();
+}
+int l_dense_small_fwd(const float* a, int rows, int K, const float* wt, int kpad, int N, float alpha_k, const float* sigma,
+                      const float* bias, float* out, int ldo, cudaStream_t st) {
+    if (N == 16) dense_small_fwd_kernel<16><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 8) dense_small_fwd_kernel<8><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 4) dense_small_fwd_kernel<4><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 32) dense_small_fwd_kernel<32><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
+    else return -1;
     return MG_CHECK_LAUNCH();
 }
 int l_incr_step(int* step, cudaStream_t st) {

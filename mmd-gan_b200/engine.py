@@ -71,6 +71,7 @@ class NetRuntime(object):
         self.npass = npass
         self.device = device
         self.layers = []
+        self._jobs = None
         layers = routine.ordered_layers()
         # ---- variables in creation order: kernel, bias, gamma, beta per layer
         self.var_offsets = OrderedDict()
@@ -250,15 +251,19 @@ class NetRuntime(object):
         return L
 
     def refresh(self):
-        """canonical parameters -> packed GEMM operands and internal (padded / permuted) vectors."""
-        for L in self.layers:
-            L.lop.pack(self.view(self.w, L.ly.kernel_name))
-            c, hw = self._feat_perm(L)
-            if L.has_bias:
-                K.permute_features(self.view(self.w, L.ly.bias_name), L.bias_int, L.Cout, c, hw)
-            if L.has_bn:
-                K.permute_features(self.view(self.w, L.ly.bn_name('gamma')), L.gamma_int, L.Cout, c, hw)
-                K.permute_features(self.view(self.w, L.ly.bn_name('beta')), L.beta_int, L.Cout, c, hw)
+        """canonical parameters -> packed GEMM operands and internal (padded / permuted) vectors, ONE launch per net."""
+        if self._jobs is None:
+            packs, perms = [], []
+            for L in self.layers:
+                packs += L.lop.pack_descs(self.view(self.w, L.ly.kernel_name))
+                c, hw = self._feat_perm(L)
+                if L.has_bias:
+                    perms.append((self.view(self.w, L.ly.bias_name), L.bias_int, L.Cout, c, hw))
+                if L.has_bn:
+                    perms.append((self.view(self.w, L.ly.bn_name('gamma')), L.gamma_int, L.Cout, c, hw))
+                    perms.append((self.view(self.w, L.ly.bn_name('beta')), L.beta_int, L.Cout, c, hw))
+            self._jobs = K.build_refresh_jobs(packs, perms, self.device)
+        K.refresh(*self._jobs)
 
 
 class SNGanEngine(object):

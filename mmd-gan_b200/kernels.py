@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, WgradDesc, WredDesc, PackDesc, MmdDesc
+from ._lib import GemmDesc, WgradDesc, WredDesc, PackDesc, MmdDesc, RefreshJob
 
 ACT = {'linear': 0, None: 0, 'lrelu': 1, 'relu': 2, 'tanh': 3}
 PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRAD, PACK_DENSE_FWD, PACK_DENSE_DGRAD = range(7)
@@ -156,6 +156,23 @@ class LinearOp(object):
         self.canon_numel = int(math.prod(self.canon_shape))
 
     # -------------------------------------------------------------------------------------------- packing
+    def pack_descs(self, w_canon):
+        """The two packing jobs (forward, input-gradient operand) of this op as PackDesc structures."""
+        out = []
+        for g in (self.f, self.d):
+            d = PackDesc()
+            d.w, d.out = _ptr(w_canon), _ptr(g['w'])
+            d.plane = plane_stride(g['w'])
+            d.mode, d.k, d.Cin, d.Cout, d.Cs = g['mode'], self.k, self.Cin, self.Cout, g['Cs']
+            d.rows_pad, d.kpad, d.classes = g['rows_pad'], g['kpad'], g['classes']
+            if self.op == 'd':
+                d.in_C, d.in_HW = self.in_flat
+                d.out_C, d.out_HW = self.out_flat
+            else:
+                d.in_C = d.in_HW = d.out_C = d.out_HW = 1
+            out.append(d)
+        return out
+
     def pack(self, w_canon):
         """canonical weights -> forward and input-gradient GEMM operands (unscaled; act_k / sigma is an epilogue alpha)."""
         for g in (self.f, self.d):
@@ -236,6 +253,12 @@ class LinearOp(object):
         return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.d['classes']
 
     def forward(self, src, nimg, dst, sigma=None, alpha_k=1.0, bias=None, act=0, colsum=None, colsumsq=None, out_mode=0):
+        if (self.op == 'd' and self.Cs_out in (4, 8, 16, 32) and out_mode == 2 and act == 0 and colsum is None
+                and dst.shape[0] == 1 and self.npass == 3):
+            # a handful of output columns (the critic scores): fp32 CUDA-core kernel instead of a 94 %-padded MMA tile
+            check(lib().mmdgan_dense_small_fwd(_ptr(src), nimg, self.Cs_in, _ptr(self.f['w']), self.f['kpad'], self.Cs_out,
+                                               float(alpha_k), _ptr(sigma), _ptr(bias), _ptr(dst), dst.shape[2], stream()))
+            return
         self._gemm(self.f, src, nimg, dst, self._fwd_geom(), sigma, alpha_k, bias, act, None, 0, None, colsum, colsumsq, 0, out_mode)
 
     def dgrad(self, dy, nimg, dst, sigma=None, alpha_k=1.0, aux=None, aux_mode=0, aux_wrap=None, colsum=None, colsum_rows=0,
@@ -331,7 +354,30 @@ def reduce_tiles(partials, T, Cc, out, scale=1.0):
 
 
 def colsum_small(x, rows, Cc, out):
-    check(lib().mmdgan_colsum_small(_ptr(x), rows, Cc, _ptr(out), stream()))
+    # column sums of a [rows, C] matrix = the tile reduction with one "tile" per row
+    check(lib().mmdgan_reduce_tiles(_ptr(x), rows, Cc, 1.0, _ptr(out), stream()))
+
+
+def build_refresh_jobs(pack_descs, permutes, device):
+    """Device-resident job table for mmdgan_refresh: pack_descs = [PackDesc], permutes = [(src, dst, n, C, HW)]."""
+    n = len(pack_descs) + len(permutes)
+    arr = (RefreshJob * n)()
+    max_elems = 1
+    for i, d in enumerate(pack_descs):
+        arr[i].kind = 0
+        arr[i].pack = d
+        max_elems = max(max_elems, d.rows_pad * d.kpad * d.classes)
+    for j, (src, dst, cnt, Cc, HW) in enumerate(permutes):
+        job = arr[len(pack_descs) + j]
+        job.kind = 1
+        job.src, job.dst = _ptr(src), _ptr(dst)
+        job.n, job.C, job.HW, job.inverse = cnt, Cc, HW, 0
+    blob = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    return blob, n, max_elems
+
+
+def refresh(blob, njobs, max_elems):
+    check(lib().mmdgan_refresh(C.c_void_p(blob.data_ptr()), njobs, max_elems, stream()))
 
 
 def sn_normalize(v, n, out, sigma_out=None, eps=1e-10):
