@@ -107,6 +107,7 @@ typedef struct mmdgan_gemm_desc {
     int out_mode;       /* 0 raw + lo plane, 1 rn-tf32 single plane, 2 raw single plane */
     int bn;             /* N tile: 16, 32, 64, 128, 256 */
     int npass;          /* 3 (fp32-grade tf32x3) or 1 (tf32) */
+    int cta_pair;       /* 1: tcgen05 cta_group::2 -- a 2-CTA cluster shares one 256 x bn tile (bn 128 or 256) */
     mmdgan_gemm_class cls[4];
 } mmdgan_gemm_desc;
 int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream);

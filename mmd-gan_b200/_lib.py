@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ('alpha_k', C.c_float), ('sigma', C.c_void_p), ('bias', C.c_void_p), ('act', C.c_int),
         ('aux', C.c_void_p), ('aux_mode', C.c_int), ('aux_wrap_at', C.c_longlong), ('aux_wrap_len', C.c_longlong),
         ('colsum', C.c_void_p), ('colsumsq', C.c_void_p), ('colsum_rows', C.c_longlong),
-        ('out_mode', C.c_int), ('bn', C.c_int), ('npass', C.c_int),
+        ('out_mode', C.c_int), ('bn', C.c_int), ('npass', C.c_int), ('cta_pair', C.c_int),
         ('cls', GemmClass * 4)]
 
 

@@ -11,7 +11,7 @@
 namespace mg {
 // conv_gemm.cu / wgrad_gemm.cu
 int launch_conv_gemm(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes, int bn,
-                     int npass, cudaStream_t st);
+                     int npass, int pair, cudaStream_t st);
 int launch_wgrad_gemm(const WgradParams& p, const float* plain, long long plain_plane, int splits, int bn, int npass,
                       cudaStream_t st);
 // mmd.cu
@@ -114,7 +114,7 @@ int mmdgan_permute_features(const float* src, float* dst, int n, int C, int HW, 
 
 int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg) {
     const long long m = static_cast<long long>(Nimg) * Hg * Wg;
-    return static_cast<int>((m + 127) / 128);
+    return static_cast<int>(((m + 127) / 128 + 1) / 2 * 2);   /* even: the CTA-pair kernel launches whole pairs */
 }
 
 int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
@@ -133,6 +133,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: pointers / plane offsets must be 16-byte aligned");
     if (d->npass == 3 && (d->src_plane == 0 || d->w_plane == 0)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: npass 3 needs lo planes");
     if (d->out_mode < 0 || d->out_mode > 2) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bad out_mode");
+    if (d->cta_pair && d->bn != 128 && d->bn != 256) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: cta_pair needs bn 128 or 256");
     const long long M = static_cast<long long>(d->Nimg) * d->Hg * d->Wg;
     if (M > 2000000000ll) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: too many rows");
     mg::ConvGemmParams p;
@@ -155,7 +156,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
         p.cls[i].oy = d->cls[i].oy; p.cls[i].ox = d->cls[i].ox; p.cls[i].ooy = d->cls[i].ooy; p.cls[i].oox = d->cls[i].oox;
         p.cls[i].wrow = d->cls[i].wrow;
     }
-    return wrap(mg::launch_conv_gemm(p, d->w, d->w_plane, d->w_rows, d->kpad, d->classes, d->bn, d->npass, S(stream)), "mmdgan_gather_gemm");
+    return wrap(mg::launch_conv_gemm(p, d->w, d->w_plane, d->w_rows, d->kpad, d->classes, d->bn, d->npass, d->cta_pair, S(stream)), "mmdgan_gather_gemm");
 }
 
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream) {

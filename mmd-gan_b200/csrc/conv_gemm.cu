@@ -15,6 +15,7 @@
 #include "conv_gemm.cuh"
 #include "tc_common.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace mg {
 
@@ -45,16 +46,19 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, uns
     }
 }
 
-template <int BN, int NPASS>
+// PAIR = true: two CTAs of a cluster (one TPC) share one 256 x BN tile through tcgen05 cta_group::2 -- each CTA gathers
+// its own 128 rows of A and stages HALF of the weight tile, so the L2 -> SM bytes per MMA drop by a quarter (BN = 128) to
+// a half (BN = 256) and each SM's tensor core reads only half of B from its own shared memory.
+template <int BN, int NPASS, bool PAIR>
 struct GemmCfg {
     static constexpr int NPL = (NPASS == 3) ? 2 : 1;
-    static constexpr int A_BYTES = kBM * kRowBytes;  // per plane
-    static constexpr int B_BYTES = BN * kRowBytes;
+    static constexpr int BROWS = PAIR ? BN / 2 : BN;      // weight rows staged by this CTA
+    static constexpr int A_BYTES = kBM * kRowBytes;       // per plane
+    static constexpr int B_BYTES = BROWS * kRowBytes;
     static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
     // budget for TWO resident CTAs per SM: the epilogue / prologue of one overlaps the main loop of the other
     static constexpr int STAGES_RAW = (kPipeBudget * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-    static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
     static constexpr int EN = BN > 128 ? 128 : BN;   // epilogue column group
     static constexpr int PITCH = EN * 4 + 16;        // staging row pitch in bytes
     static constexpr int STAGING_BYTES = kBM * PITCH;
@@ -62,9 +66,69 @@ struct GemmCfg {
     static constexpr int PROW_BYTES = kBM * 8;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES + RED_BYTES + PROW_BYTES ? PIPE_BYTES : STAGING_BYTES + RED_BYTES + PROW_BYTES;
-    static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
+
+// ---- cluster / cta_group::2 primitives (pair kernel only)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to the mbarrier of cluster CTA 0
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .b32 rb;\n\t"
+        "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [rb];\n\t}" ::"r"(
+            dst_smem),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "{\n\t.reg .b32 rb;\n\t"
+        "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [rb];\n\t}" ::"r"(
+            dst_smem),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of this thread arrives on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 1) return v > 0.f ? v : 0.1f * v;
@@ -79,21 +143,27 @@ __device__ __forceinline__ float act_grad_from_output(float a, int mode) {
     return 1.f;
 }
 
-template <int BN, int NPASS>
-__global__ void __launch_bounds__(kThreads, 2)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ ConvGemmParams p) {
-    using Cfg = GemmCfg<BN, NPASS>;
+// ATMA = true: the gathered operand is staged by TMA as well -- one 4-D box {16 channels, W, rows, images} per
+// (channel chunk, tap) lands exactly the 128 K-major rows of the tile, with out-of-bounds zero fill as SAME padding and
+// the traversal stride as the convolution stride.  Used whenever a 128-row tile is a whole number of image rows;
+// otherwise the four producer warps gather with cp.async (ATMA = false).
+template <int BN, int NPASS, bool PAIR, bool ATMA>
+__device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CUtensorMap& tmB1, const CUtensorMap& tmA0,
+                                               const CUtensorMap& tmA1, const ConvGemmParams& p) {
+    using Cfg = GemmCfg<BN, NPASS, PAIR>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool RELAY = PAIR && !ATMA;         // the peer's cp.async arrivals must be forwarded to the leader
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
-    uint64_t* full_bar = bars;
+    uint64_t* full_bar = bars;                    // single: A arrivals + B bytes.  pair: this CTA's A arrivals only
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* accum_bar = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint64_t* bfull_bar = bars + 2 * STAGES + 1;  // pair, leader: weight bytes of BOTH CTAs
+    uint64_t* peer_bar = bars + 3 * STAGES + 1;   // pair, leader: "the peer's A rows have landed"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * STAGES + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -101,23 +171,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
     const int tile_n = blockIdx.y;
     const GemmClass cls = p.cls[blockIdx.z];
     const int ksteps = p.ksteps;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmB0);
         if (NPL == 2) tma_prefetch_desc(&tmB1);
+        if (ATMA) {
+            tma_prefetch_desc(&tmA0);
+            if (NPL == 2) tma_prefetch_desc(&tmA1);
+        }
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], kProducerThreads + 1);
+            mbar_init(&full_bar[s], ATMA ? 1 : (PAIR ? kProducerThreads : kProducerThreads + 1));
             mbar_init(&empty_bar[s], 1);
+            if (PAIR) {
+                mbar_init(&bfull_bar[s], 1);
+                mbar_init(&peer_bar[s], 1);
+            }
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
     if (warp == 5) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+        } else {
+            tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -127,6 +210,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
     };
 
     if (warp < 4) {
+      if (!ATMA) {
         // ======================= A producers (gather) =======================
         const int t = threadIdx.x;
         const int chunk = t & 3;
@@ -185,26 +269,72 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
             // producers run ahead by as many stages as there are free slots and the MMA warp never waits on this loop
             cp_async_mbar_arrive_noinc(&full_bar[s]);
         }
+      }
     } else if (warp == 4) {
-        // ======================= B producer (TMA) =======================
+        // ======================= TMA producer: weights (and, with ATMA, the gathered operand) =======================
         if (lane == 0) {
-            const int row0 = cls.wrow + tile_n * BN;
+            const int row0 = cls.wrow + tile_n * BN + (PAIR ? static_cast<int>(rank) * Cfg::BROWS : 0);
+            // tile origin on the (image, row) grid; with ATMA a tile is a whole number of image rows
+            const int hw = p.Hg * p.Wg;
+            const int pix0 = tile_m * kBM;
+            const int n0 = pix0 / hw;
+            const int y0 = (pix0 - n0 * hw) / p.Wg;
+            const int ntaps = p.TH * p.TW;
+            const uint32_t a_bytes = ATMA ? NPL * Cfg::A_BYTES : 0u;
+            int cc = 0, tap = 0;
             for (int j = 0; j < ksteps; ++j) {
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 2);
-                mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES);
-                tma_load_2d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0);
-                if (NPL == 2) tma_load_2d(smem_u32(stage_b(s, 1)), &tmB1, &full_bar[s], j * kBK, row0);
+                const int ta = tap / p.TW, tb = tap - ta * p.TW;
+                const int cx = tb + cls.ox, cy = y0 * p.sy + ta + cls.oy, cch = cc * kBK;
+                if (PAIR) {
+                    // both CTAs load their operand shares; all bytes are credited to the leader's barrier
+                    uint64_t* bar = ATMA ? &full_bar[s] : &bfull_bar[s];
+                    if (rank == 0) mbar_arrive_expect_tx(bar, 2 * (NPL * Cfg::B_BYTES + a_bytes));
+                    tma_load_2d_pair(smem_u32(stage_b(s, 0)), &tmB0, bar, j * kBK, row0);
+                    if (NPL == 2) tma_load_2d_pair(smem_u32(stage_b(s, 1)), &tmB1, bar, j * kBK, row0);
+                    if (ATMA) {
+                        tma_load_4d_pair(smem_u32(stage_a(s, 0)), &tmA0, bar, cch, cx, cy, n0);
+                        if (NPL == 2) tma_load_4d_pair(smem_u32(stage_a(s, 1)), &tmA1, bar, cch, cx, cy, n0);
+                    }
+                } else {
+                    mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES + a_bytes);
+                    tma_load_2d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0);
+                    if (NPL == 2) tma_load_2d(smem_u32(stage_b(s, 1)), &tmB1, &full_bar[s], j * kBK, row0);
+                    if (ATMA) {
+                        tma_load_4d(smem_u32(stage_a(s, 0)), &tmA0, &full_bar[s], cch, cx, cy, n0);
+                        if (NPL == 2) tma_load_4d(smem_u32(stage_a(s, 1)), &tmA1, &full_bar[s], cch, cx, cy, n0);
+                    }
+                }
+                if (++tap == ntaps) { tap = 0; ++cc; }      // K order: (channel chunk, tap)
             }
         }
+    } else if (PAIR && rank != 0) {
+      if (RELAY) {
+        // ======================= peer CTA: relay "my A rows have landed" to the leader =======================
+        for (int j = 0; j < ksteps; ++j) {
+            const int s = j % STAGES;
+            const uint32_t ph = (j / STAGES) & 1;
+            mbar_wait_wd(&full_bar[s], ph, p.err, 5);
+            if (lane == 0) {
+                fence_proxy_async_smem();
+                mbar_arrive_remote(&peer_bar[s], 0);
+            }
+            __syncwarp();
+        }
+      }
     } else {
-        // ======================= MMA issuer =======================
-        constexpr uint32_t idesc = idesc_tf32(kBM, BN, 0, 0);
+        // ======================= MMA issuer (pair: the leader CTA issues for both) =======================
+        constexpr uint32_t idesc = idesc_tf32(PAIR ? 2 * kBM : kBM, BN, 0, 0);
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
             mbar_wait_wd(&full_bar[s], ph, p.err, 3);
+            if (RELAY) {
+                mbar_wait_wd(&peer_bar[s], ph, p.err, 6);
+                mbar_wait_wd(&bfull_bar[s], ph, p.err, 7);
+            }
             fence_proxy_async_smem();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
             tc_fence_after();
             if (lane == 0) {
@@ -220,14 +350,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
                         // K-major, SWIZZLE_64B (layout type 4): 8-row groups are 512 bytes apart; +32 bytes per K=8 slice
                         const uint64_t ad = smem_desc(abase + kk * 32, 16, 512, 4u);
                         const uint64_t bd = smem_desc(bbase + kk * 32, 16, 512, 4u);
-                        umma_tf32(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kk > 0) ? 1u : 0u);
+                        const uint32_t acc = (j > 0 || pass > 0 || kk > 0) ? 1u : 0u;
+                        if (PAIR) umma_tf32_pair(tmem_base, ad, bd, idesc, acc);
+                        else umma_tf32(tmem_base, ad, bd, idesc, acc);
                     }
                 }
-                umma_commit(&empty_bar[s]);
+                if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
             }
             __syncwarp();
         }
-        if (lane == 0) umma_commit(accum_bar);
+        if (lane == 0) {
+            if (PAIR) umma_commit_pair(accum_bar); else umma_commit(accum_bar);
+        }
         __syncwarp();
     }
 
@@ -341,11 +475,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
+}
+
+template <int BN, int NPASS, bool ATMA>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ ConvGemmParams p) {
+    conv_gemm_body<BN, NPASS, false, ATMA>(tmB0, tmB1, tmA0, tmA1, p);
+}
+
+template <int BN, int NPASS, bool ATMA>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 2)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                      const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ ConvGemmParams p) {
+    conv_gemm_body<BN, NPASS, true, ATMA>(tmB0, tmB1, tmA0, tmA1, p);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -381,33 +532,85 @@ int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long co
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-template <int BN, int NPASS>
-static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes,
-                      cudaStream_t st) {
-    using Cfg = GemmCfg<BN, NPASS>;
-    CUtensorMap t0, t1;
-    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, kBK, BN, 2)) return -4;
-    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, kBK, BN, 2)) return -4;
+// 4-D fp32 tensor map over an NHWC activation plane: dims {C, W, H, N}; box {16, bw, bh, bn} with traversal strides
+// {1, sx, sy, 1} (the box loads ceil(b/s) elements per strided dimension), 64-byte swizzle, zero OOB fill
+static int make_tmap_act(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh, int bn, int sx, int sy) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4, static_cast<cuuint64_t>(H) * W * C * 4};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// a 128-row tile is `hb` whole image rows of `nb` images: the gathered operand can be one TMA box per (chunk, tap)
+static bool atma_geometry(const ConvGemmParams& p, int* hb, int* nb) {
+    if (p.Cs % kBK != 0 || p.Wg <= 0 || kBM % p.Wg != 0) return false;
+    int rows = kBM / p.Wg;
+    if (rows <= p.Hg) {
+        if (p.Hg % rows != 0) return false;
+        *hb = rows; *nb = 1;
+    } else {
+        if (rows % p.Hg != 0) return false;
+        *hb = p.Hg; *nb = rows / p.Hg;
+    }
+    if (p.Wg * p.sx > 256 || *hb * p.sy > 256 || *nb > 256) return false;
+    return true;
+}
+
+template <int BN, int NPASS, bool PAIR, bool ATMA>
+static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes, int hb,
+                      int nb, cudaStream_t st) {
+    using Cfg = GemmCfg<BN, NPASS, PAIR>;
+    CUtensorMap t0, t1, a0, a1;
+    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, kBK, Cfg::BROWS, 2)) return -4;
+    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, kBK, Cfg::BROWS, 2)) return -4;
+    if (ATMA) {
+        if (make_tmap_act(&a0, p.src, p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy)) return -4;
+        if (make_tmap_act(&a1, p.src + (NPASS == 3 ? p.src_plane : 0), p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy))
+            return -4;
+    } else {
+        a0 = t0; a1 = t1;
+    }
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-            cudaSuccess)
-            return -4;
+        cudaError_t e = PAIR ? cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, NPASS, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)
+                             : cudaFuncSetAttribute(conv_gemm_kernel<BN, NPASS, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return -4;
         attr_done = true;
     }
-    dim3 grid((p.M + kBM - 1) / kBM, (p.Ncols + BN - 1) / BN, classes);
-    conv_gemm_kernel<BN, NPASS><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, p);
+    int tiles_m = (p.M + kBM - 1) / kBM;
+    if (PAIR) tiles_m = (tiles_m + 1) / 2 * 2;
+    dim3 grid(tiles_m, (p.Ncols + BN - 1) / BN, classes);
+    if (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, p);
+    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 // w: [planes][w_rows][kpad]; w_rows = classes * rows_per_class (rows_per_class a multiple of the N tile)
 int launch_conv_gemm(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes,
-                     int bn, int npass, cudaStream_t st) {
+                     int bn, int npass, int pair, cudaStream_t st) {
+    int hb = 0, nb = 0;
+    static int no_atma = -1;
+    if (no_atma < 0) { const char* e = getenv("MMDGAN_NO_ATMA"); no_atma = e ? atoi(e) : 0; }
+    const bool atma = !no_atma && atma_geometry(p, &hb, &nb);
 #define MG_CASE(B, N) \
-    if (bn == B && npass == N) return launch_cfg<B, N>(p, w, w_plane, w_rows, kpad, classes, st);
+    if (bn == B && npass == N && !pair) \
+        return atma ? launch_cfg<B, N, false, true>(p, w, w_plane, w_rows, kpad, classes, hb, nb, st) \
+                    : launch_cfg<B, N, false, false>(p, w, w_plane, w_rows, kpad, classes, hb, nb, st);
+#define MG_PAIR(B, N) \
+    if (bn == B && npass == N && pair) \
+        return atma ? launch_cfg<B, N, true, true>(p, w, w_plane, w_rows, kpad, classes, hb, nb, st) \
+                    : launch_cfg<B, N, true, false>(p, w, w_plane, w_rows, kpad, classes, hb, nb, st);
     MG_CASE(16, 3) MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3) MG_CASE(256, 3)
     MG_CASE(16, 1) MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1) MG_CASE(256, 1)
+    MG_PAIR(128, 3) MG_PAIR(256, 3) MG_PAIR(128, 1) MG_PAIR(256, 1)
 #undef MG_CASE
+#undef MG_PAIR
     return -1;
 }
 

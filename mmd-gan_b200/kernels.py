@@ -16,6 +16,8 @@ ACT = {'linear': 0, None: 0, 'lrelu': 1, 'relu': 2, 'tanh': 3}
 PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRAD, PACK_DENSE_FWD, PACK_DENSE_DGRAD = range(7)
 
 
+GEMM_PAIR = True        # use the CTA-pair (cta_group::2) gather-GEMM where the grid is large enough
+GEMM_PAIR_MIN_TILES = 256   # 128 x 128 output units; below that the single-CTA kernel fills the machine better
 GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
@@ -208,13 +210,20 @@ class LinearOp(object):
         d.aux, d.aux_mode = _ptr(aux), aux_mode
         d.aux_wrap_at, d.aux_wrap_len = aux_wrap if aux_wrap else (0, 0)
         d.colsum, d.colsumsq, d.colsum_rows = _ptr(colsum), _ptr(colsumsq), colsum_rows
-        bn = g['bn']
-        if GEMM_BN_MAX >= 256 and g['ncols'] % 256 == 0:
+        bn, pair = g['bn'], 0
+        m_tiles = (nimg * d.Hg * d.Wg + 127) // 128
+        if GEMM_PAIR and g['ncols'] % 128 == 0 and m_tiles * (g['ncols'] // 128) * g['classes'] >= GEMM_PAIR_MIN_TILES:
+            # tcgen05 cta_group::2: a 2-CTA cluster shares a 256 x bn tile (half the weight bytes per CTA).  bn = 256 doubles
+            # the epilogue per CTA: measured to pay off for plain forward epilogues and for very wide layers only
+            pair = 1
+            bn = 256 if (g['ncols'] % 256 == 0 and (g['ncols'] >= 512 or aux is None)) else 128
+        elif GEMM_BN_MAX >= 256 and g['ncols'] % 256 == 0:
             # 128 x 256 tiles halve the re-reads of the gathered operand, but leave only two pipeline stages per CTA and
             # double the epilogue: measured to pay off only while the grid still fills the 2 x 148 CTA slots
-            tiles = ((nimg * d.Hg * d.Wg + 127) // 128) * (g['ncols'] // 256) * g['classes']
+            tiles = m_tiles * (g['ncols'] // 256) * g['classes']
             if tiles >= 190 and (g['ncols'] >= 512 or aux is None):
                 bn = 256
+        d.cta_pair = pair
         d.out_mode, d.bn, d.npass = out_mode, bn, self.npass
         if out_mode == 0 and dst.shape[0] != 2:
             raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 needs a two-plane destination')
