@@ -39,8 +39,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, uns
     while (!mbar_try_wait(bar, parity)) {
         if (gtime_ns() - t0 > kWatchdogNs) {
             if (err) atomicExch(err, code);
-            printf("mmdgan: mbarrier watchdog (code %u) block (%d,%d,%d) thread %d\n", code, blockIdx.x, blockIdx.y,
-                   blockIdx.z, threadIdx.x);
+            printf("mmdgan: mbarrier watchdog (code %u) block %d thread %d\n", code, blockIdx.x, threadIdx.x);
             __trap();
         }
     }
@@ -167,11 +166,17 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x;
-    const int tile_n = blockIdx.y;
-    const GemmClass cls = p.cls[blockIdx.z];
-    const int ksteps = p.ksteps;
+    // linear block index -> (N tile, class, M tile), N tile fastest: every CTA that gathers the same input rows (the other
+    // N tiles, the other output-parity classes) is scheduled back to back, so the re-reads hit L2 instead of HBM
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    int lin = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_n = lin % p.tiles_n;
+    lin /= p.tiles_n;
+    const int cls_idx = lin % p.classes;
+    lin /= p.classes;
+    const int tile_m = PAIR ? lin * 2 + static_cast<int>(rank) : lin;
+    const GemmClass cls = p.cls[cls_idx];
+    const int ksteps = p.ksteps;
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmB0);
@@ -466,7 +471,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                         s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
                         s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
                     }
-                    const long long tl = static_cast<long long>(blockIdx.z) * gridDim.x + blockIdx.x;
+                    const long long tl = static_cast<long long>(cls_idx) * p.tiles_m + tile_m;
                     *reinterpret_cast<float4*>(p.colsum + tl * p.Ncols + col) = s1;
                     if (p.colsumsq) *reinterpret_cast<float4*>(p.colsumsq + tl * p.Ncols + col) = s2;
                 }
@@ -583,11 +588,14 @@ static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane
         if (e != cudaSuccess) return -4;
         attr_done = true;
     }
-    int tiles_m = (p.M + kBM - 1) / kBM;
-    if (PAIR) tiles_m = (tiles_m + 1) / 2 * 2;
-    dim3 grid(tiles_m, (p.Ncols + BN - 1) / BN, classes);
-    if (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, p);
-    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, p);
+    ConvGemmParams q = p;
+    q.tiles_m = (p.M + kBM - 1) / kBM;
+    if (PAIR) q.tiles_m = (q.tiles_m + 1) / 2 * 2;
+    q.tiles_n = (p.Ncols + BN - 1) / BN;
+    q.classes = classes;
+    dim3 grid(static_cast<unsigned>(q.tiles_m) * q.tiles_n * classes, 1, 1);
+    if (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, q);
+    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, q);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -39,6 +39,7 @@ struct ConvGemmParams {
     long long colsum_rows;   // only destination rows < colsum_rows are counted
     int out_mode;            // 0: raw + lo plane, 1: rn-tf32 single plane, 2: raw single plane
     unsigned int* err;       // device error flag (watchdog)
+    int tiles_m, tiles_n, classes;   // filled by the launcher: grid decomposition (linear block index)
     int debug;               // profiling experiments only: bit0 = skip the A gather, bit1 = skip the MMAs
     GemmClass cls[4];
 };

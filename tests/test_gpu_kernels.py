@@ -108,6 +108,15 @@ def test_linear_op_fwd_dgrad_wgrad(cuda, case, npass):
     assert abs(float(dots.sum()) - float((dw_ref * w).sum())) <= max(tol, 1e-4) * float(dw_ref.norm() * w.norm())
 
 
+@pytest.mark.parametrize('case', [c for c in CASES if c[2] % 128 == 0 or (c[0] != 'd' and c[1] % 128 == 0)], ids=str)
+def test_linear_op_cta_pair_kernel(cuda, case, monkeypatch):
+    """The tcgen05 cta_group::2 variant (normally selected only for large grids) forced on small problems: a 2-CTA
+    cluster shares one 256 x bn tile; the peer CTA's operands are credited to the leader's mbarrier."""
+    from mmdgan_b200 import kernels as K
+    monkeypatch.setattr(K, 'GEMM_PAIR_MIN_TILES', 1)
+    test_linear_op_fwd_dgrad_wgrad(cuda, case, 3)
+
+
 def test_dgrad_fused_activation_derivative_and_wrap(cuda):
     """dgrad epilogue: multiply by lrelu'(a) read from the layer input activation, with the 3B virtual-batch row wrap
     and column sums restricted to the first 2B images (bias gradient of the previous layer)."""
