@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import architectures as oa          # noqa: E402  (architecture dictionaries only)
+from mmdgan_b200 import experiments as oa   # noqa: E402
 from mmdgan_b200.engine import SNGanEngine      # noqa: E402
 
 

@@ -1,7 +1,7 @@
 """Per-launch CUDA-event timing of every tcgen05 GEMM launch of one eager step (which layer, which pass, TFLOP/s)."""
 import sys, json, torch
 sys.path.insert(0, '.')
-from oracle import architectures as oa
+from mmdgan_b200 import experiments as oa
 from mmdgan_b200 import kernels as K
 from mmdgan_b200.engine import SNGanEngine
 name = sys.argv[1] if len(sys.argv) > 1 else 'cifar'

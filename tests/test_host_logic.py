@@ -39,6 +39,13 @@ def test_layer_dsl_matches_oracle_shape_inference_and_sn_routing(name):
                 assert ly.sn_name == sp.sn_name
 
 
+def test_product_experiment_definitions_match_the_oracle_twin():
+    from mmdgan_b200 import experiments as ex
+    for name in ['cifar', 'stl', 'celeba', 'lsun']:
+        assert ex.ARCHITECTURES[name]() == oa.ARCHITECTURES[name]()
+    assert ex.tiny() == oa.tiny()
+
+
 def test_update_layer_design_defaults_and_errors():
     from mmdgan_b200.GeneralTools.layer_func import update_layer_design, Net, Routine
     d = update_layer_design({'name': 'l', 'out': 8})
