@@ -4,7 +4,8 @@ Same constructor and `training` signature as the reference (my_sngan.py:31-83, 3
 call: builds the nets from the architecture dictionary (init_net, 85-108), two Adam optimisers with constant learning
 rates lr_list = [lr_dis, lr_gen] (412-415), then runs `max_step` fused steps through agent.train; every step is the
 simultaneous update of my_sngan.py:424-426.  The data source replaces ReadTFRecords (input_func.py:721-965): `filename`
-may be an array / tensor of images (uint8 or float, NCHW), a callable batch function, or the string 'synthetic'.
+may be a TFRecord prefix as in the reference (read by GeneralTools/input_func.ReadTFRecords, no TensorFlow), an array /
+tensor of images (uint8 or float, NCHW), a callable batch function, or the string 'synthetic'.
 Only loss types 'rep' and 'rmb' (plus the fused siblings 'mmd_g', 'mgb') are on the hot path; penalties ('rep_gp',
 ...) raise NotImplementedError.
 """
@@ -70,14 +71,23 @@ class SNGan(object):
                 code_x.shape[0], batch_size)
         return {'x': code_x}
 
-    def _batch_fn(self, source, batch_size, num_instance):
+    def _batch_fn(self, source, batch_size, num_instance, reader_seed=None):
         import torch
         if callable(source):
             return source
+        if isinstance(source, (list, tuple)) or (isinstance(source, str) and source != 'synthetic'):
+            # TFRecord prefix(es) as in the reference (my_sngan.py:331-361): <FLAGS.DEFAULT_IN>/<name>.tfrecords
+            from ..GeneralTools.input_func import ReadTFRecords
+            from math import gcd
+            file_repeat = int(batch_size / gcd(num_instance, batch_size))           # my_sngan.py:383-385
+            reader = ReadTFRecords(source, int(self.input_size), num_labels=0, batch_size=batch_size, file_repeat=file_repeat,
+                                   seed=reader_seed)
+            reader.shape2image(self.channels, self.height, self.width)
+
+            def fn_records(step):
+                return torch.from_numpy(reader.next_batch()['x']), self.sample_codes(batch_size)['x']
+            return fn_records
         if isinstance(source, str):
-            if source != 'synthetic':
-                raise NotImplementedError('TFRecord input ({}) is a "next" row (SURVEY.md section 8 f2); pass an image '
-                                          'array, a batch function or "synthetic".'.format(source))
             g = torch.Generator().manual_seed(0)
             pool = torch.rand(max(batch_size * 4, 256), self.channels, self.height, self.width, generator=g) * 2.0 - 1.0
         else:
@@ -93,7 +103,7 @@ class SNGan(object):
         return fn
 
     def training(self, filename, agent, num_instance, lr_list, end_lr=1e-7, max_step=None, batch_size=64,
-                 sample_same_class=False, num_threads=7, gpu='/gpu:0', **engine_kwargs):
+                 sample_same_class=False, num_threads=7, gpu='/gpu:0', reader_seed=None, **engine_kwargs):
         """my_sngan.py:364-471."""
         self.step_per_epoch = int(np.floor(num_instance / batch_size))
         self.sample_same_class = sample_same_class
@@ -102,7 +112,7 @@ class SNGan(object):
         assert all(o['kind'] == 'adam' for o in opt_ops)
         engine = self.init_net(batch_size, lr_list, **engine_kwargs)
         FLAGS.print('loss_list name: {}.'.format(self.loss_names))
-        batch_fn = self._batch_fn(filename, batch_size, num_instance)
+        batch_fn = self._batch_fn(filename, batch_size, num_instance, reader_seed)
         losses = agent.train(engine, batch_fn, max_step, self.step_per_epoch, self.loss_names, force_print=self.force_print)
         self.global_step = engine.global_step
         self.force_print = False

@@ -118,5 +118,35 @@ def test_sngan_training_api_and_checkpoint(cuda, tmp_path):
     assert mdl2.global_step == 7
     with pytest.raises(NotImplementedError):
         SNGan(arch, loss_type='hinge')
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):        # input_func.py:775: 'File ... does not exist.'
         mdl.training('cifar_NCHW/cifar', agent, 64, [5e-4, 2e-4], max_step=1, batch_size=16)
+
+
+def test_sngan_training_from_tfrecords(cuda, tmp_path):
+    """The reference call `mdl.training(filename, ...)` with a TFRecord prefix (my_test_cifar.py) on a toy file: the
+    batches the engine trains on are those of ReadTFRecords (uint8 CHW bytes -> x / 127.5 - 1)."""
+    from oracle import architectures as oa
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200.GeneralTools.graph_func import Agent
+    from mmdgan_b200.GeneralTools import input_func as inp
+    from mmdgan_b200.DeepLearning.my_sngan import SNGan
+    FLAGS.DEFAULT_OUT = str(tmp_path) + '/'
+    FLAGS.DEFAULT_IN = str(tmp_path) + '/'
+    FLAGS.SILENT_MODE = True
+    arch = oa.tiny(act_k=2.6)
+    images = np.random.RandomState(1).randint(0, 256, size=(48, 3 * 8 * 8)).astype(np.uint8)
+    inp.my_np2tfrecord('toy_records', images)
+    runs = []
+    for source in ('toy_records', None):
+        agent = Agent('toy', 'rec{}'.format(len(runs)), load_ckpt=False, do_save=False, query_step=2, print_loss=True)
+        mdl = SNGan(arch, num_class=0, loss_type='rep', optimizer='adam')
+        torch.manual_seed(0)
+        np.random.seed(0)
+        if source is None:      # the same stream fed through the callable interface
+            reader = inp.ReadTFRecords('toy_records', 192, batch_size=16, file_repeat=1, seed=7)
+            reader.shape2image(3, 8, 8)
+            source = lambda step: (torch.from_numpy(reader.next_batch()['x']), mdl.sample_codes(16)['x'])
+            runs.append(mdl.training(source, agent, 48, [5e-4, 2e-4], max_step=4, batch_size=16))
+        else:
+            runs.append(mdl.training(source, agent, 48, [5e-4, 2e-4], max_step=4, batch_size=16, reader_seed=7))
+    assert all(np.isfinite(runs[0])) and list(runs[0]) == list(runs[1])
