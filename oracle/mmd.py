@@ -1,4 +1,4 @@
-"""Oracle (test infrastructure): rep / rmb MMD losses.  PARITY UNPINNED (see oracle/__init__.py).
+"""Oracle (test infrastructure): rep / rmb MMD losses.  Pinned against outputs of the reference's own Python run on oracle/tfshim (tests/golden/ref_*.npz; see oracle/__init__.py).
 
 Restates GeneralTools/math_func.py of the reference:
   get_squared_dist          math_func.py:767-858   (mode 'xxxyyy', Gram trick, clamp at 0)

@@ -1,6 +1,6 @@
 """Oracle (test infrastructure): layer DSL, spectral norm and the SNGan step on the CPU.
 
-PARITY UNPINNED (see oracle/__init__.py).  PyTorch-CPU restatement of:
+Pinned against outputs of the reference's own Python run on oracle/tfshim (tests/golden/ref_*.npz; see oracle/__init__.py).  PyTorch-CPU restatement of:
   update_layer_design / Layer default / Net / Routine   layer_func.py:1189-1275, 1611-1685, 2111-2150, 2207-2494
   ParametricOperation ops d / c / tc / bias / bn        layer_func.py:566-600, 709-783, 870-966
   weight_initializer / bias_initializer                 layer_func.py:14-80

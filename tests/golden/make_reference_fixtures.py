@@ -1,0 +1,252 @@
+"""Golden vectors produced by EXECUTING THE REFERENCE'S OWN PYTHON (run here: python tests/golden/make_reference_fixtures.py).
+
+/root/reference is TF-1.8 graph code and TensorFlow cannot be installed in this image, so the unmodified reference
+modules (GeneralTools/math_func.py, GeneralTools/layer_func.py, GeneralTools/graph_func.py, DeepLearning/my_sngan.py) are
+imported on top of `oracle/tfshim` -- an eager, PyTorch-CPU, float64 stand-in for the tf.* calls they make -- and their
+own functions are run:
+
+  ref_mmd_<loss>_<B>.npz   GANLoss.apply -> get_squared_dist, mmd_g, mmd_g_bounded, mixture_mmd_g   (math_func.py:767-858,
+                           1048-1069, 1288-1473, 2088-2658); losses and their score gradients
+  ref_sn_<case>.npz        SpectralNorm(sn_def).apply(kernel)  (math_func.py:397-749): sigma, the assign(in_rand, .) value in
+                           UPDATE_OPS, d sigma / d kernel, the use_u routing flag
+  ref_step_<net>_<loss>.npz  SNGan.init_net + SNGan.__gpu_task__ + multi_opt_config + apply_gradients + UPDATE_OPS
+                           (my_sngan.py:85-108, 259-323, 412-426; graph_func.py:478-575, 848-854): Net / Routine /
+                           ParametricOperation build the generator and discriminator from the architecture dictionary;
+                           losses, scores, generated images, every gradient, and every variable after the update.
+  ref_step_cifar_rep.npz, ref_step_cifar_rep_k27.npz   the same through the architecture dictionary parsed out of the reference's my_test_cifar.py
+                           (batch 4; gradients stored as norms plus a strided sample per variable to keep the file small;
+                           the initial variables are the oracle's seeded initialisation, so only the seed is stored)
+
+Inputs (seeds, initial variables) are the ones tests/golden/make_golden.py uses for the oracle-authored twins, so each
+ref_* file has the same keys as its twin and the same tests run against both.  Only the fixtures travel to the GPU box.
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get('MMDGAN_REFERENCE', '/root/reference')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tfshim'))
+sys.path.insert(0, REFERENCE)
+
+for _alias, _ty in (('int', int), ('float', float), ('bool', bool)):      # NumPy-1.x aliases the 2018 reference code uses
+    if _alias not in np.__dict__:
+        setattr(np, _alias, _ty)
+
+import torch                                   # noqa: E402
+import tensorflow as tf                        # noqa: E402  (oracle/tfshim)
+from GeneralTools import math_func as rmf      # noqa: E402  (the reference)
+from GeneralTools import graph_func as rgf     # noqa: E402
+from GeneralTools.misc_fun import FLAGS        # noqa: E402
+from DeepLearning.my_sngan import SNGan        # noqa: E402
+
+from oracle import architectures as oa         # noqa: E402
+from oracle import net as onet                 # noqa: E402
+import make_golden as mg                       # noqa: E402  (input generators shared with the oracle-authored twins)
+
+FLAGS.SILENT_MODE = True
+assert tf.__version__.endswith('tfshim')
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def ref_mmd_case(loss_type, b, w=(0.0, -1.0)):
+    base = mg.mmd_case(loss_type, b, w=w)                     # inputs (and the oracle's answers, discarded)
+    g = torch.tensor(base['gen'], dtype=torch.float64, requires_grad=True)
+    r = torch.tensor(base['real'], dtype=torch.float64, requires_grad=True)
+    loss = rmf.GANLoss(do_summary=False)
+    if loss_type in ('rep', 'rmb'):
+        lg, ld = loss.apply(g, r, loss_type, batch_size=b, d=g.shape[1], rep_weights=list(w))   # my_sngan.py:284-287
+    else:
+        lg, ld = loss.apply(g, r, loss_type, batch_size=b, d=g.shape[1])                        # my_sngan.py:289-290
+    dlg = torch.autograd.grad(lg, [g, r], retain_graph=True, allow_unused=True)
+    dld = torch.autograd.grad(ld, [g, r], allow_unused=True)
+    z = lambda t, ref: (torch.zeros_like(ref) if t is None else t).detach().numpy()
+    return dict(gen=base['gen'], real=base['real'], rep_weights=np.asarray(w), loss_gen=lg.detach().numpy(),
+                loss_dis=ld.detach().numpy(), dLg_dgen=z(dlg[0], g), dLg_ddata=z(dlg[1], r), dLd_dgen=z(dld[0], g),
+                dLd_ddata=z(dld[1], r))
+
+
+# ------------------------------------------------------------------------------------------------ spectral norm
+def ref_sn_case(op, cin, cout, hin, k, s, seed):
+    base = mg.sn_case(op, cin, cout, hin, k, s, seed)
+    tf.reset_default_graph()
+    w = torch.tensor(base['w'], dtype=torch.float64, requires_grad=True)
+    if op == 'd':
+        sn_def = {'op': 'd'}                                                         # layer_func.py:797-800
+    else:
+        hout = -(-hin // s)
+        sn_def = {'op': op, 'strides': s, 'dilation': 1, 'padding': 'SAME', 'data_format': 'NCHW',
+                  'input_shape': [64, cin, hin, hin], 'output_shape': [64, cout, hout, hout]}   # layer_func.py:804-809
+    sn = rmf.SpectralNorm(sn_def, 'SN', num_iter=1)
+    # the variable in_rand is created inside apply(); pre-seed the shim's variable store with the fixture's x
+    with tf.variable_scope('SN'):
+        x = tf.get_variable('in_rand', shape=list(base['x'].shape), initializer=lambda shape: torch.tensor(base['x'], dtype=torch.float64),
+                            trainable=False)
+    sigma = sn.apply(w)
+    assert tuple(sn.x.shape) == tuple(base['x'].shape) and sn.x is x
+    (upd,) = tf.get_collection(tf.GraphKeys.UPDATE_OPS)
+    (dsdw,) = torch.autograd.grad(sigma, w)
+    return dict(op=op, cin=cin, cout=cout, hin=hin, k=k, s=s, use_u=np.asarray(bool(sn.use_u)), w=base['w'], x=base['x'],
+                sigma=sigma.detach().numpy(), x_update=upd.value.detach().numpy(), dsigma_dw=dsdw.numpy())
+
+
+# ------------------------------------------------------------------------------------------------ the fused step
+def reference_architecture(script):
+    """The `architecture = {...}` literal of a my_test_*.py script, evaluated with the script's own act_k / w_nm."""
+    src = open(os.path.join(REFERENCE, script)).read()
+    tree = ast.parse(src)
+    env = {'np': np}
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) \
+                and node.targets[0].id in ('act_k', 'w_nm', 'architecture'):
+            exec(compile(ast.Module([node], []), script, 'exec'), env)
+    return env['architecture']
+
+
+class ReferenceRun(object):
+    """SNGan.training's graph section (my_sngan.py:402-426) executed eagerly, one construction per step."""
+
+    def __init__(self, architecture, loss_type, lr_list, rep_weights=(0.0, -1.0)):
+        tf.reset_default_graph()
+        self.mdl = SNGan(architecture, num_class=0, loss_type=loss_type, optimizer='adam', do_summary=False,
+                         rep_weights=list(rep_weights))
+        self.global_step = torch.zeros((), dtype=torch.int64)
+        _, self.opt_ops = rgf.multi_opt_config(list(lr_list), end_lr=1e-7, optimizer='adam', global_step=self.global_step)
+        self.code = None
+
+    def set_variables(self, values):
+        """Create the reference's variables under the reference's names with given initial values."""
+        store = tf.shim_variables()
+        assert not store
+        self._init_values = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64) for k, v in values.items()}
+
+    def build(self, data, code, batch_size):
+        """init_net + __gpu_task__ (is_training=True) with the code batch injected through tf.random_normal."""
+        tf._S.collections.clear()
+        self.mdl.init_net()                                                           # my_sngan.py:404
+        orig_rn = tf.random_normal
+        tf.random_normal = lambda shape, **kw: torch.as_tensor(code, dtype=torch.float64).reshape(tuple(shape))
+        orig_gv = tf.get_variable
+        init = getattr(self, '_init_values', None)
+
+        def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True, **kw):
+            full = '/'.join(tf._S.scope + [name])
+            if init is not None and full not in tf.shim_variables():
+                assert full in init, 'reference created a variable the oracle does not know: ' + full
+                v0 = init[full]
+                assert list(v0.shape) == ([shape] if isinstance(shape, int) else list(shape)), (full, list(v0.shape), shape)
+                initializer = lambda s: v0.clone()                                    # noqa: E731
+            return orig_gv(name, shape, dtype, initializer, trainable, **kw)
+        tf.get_variable = get_variable
+        try:
+            data_batch = {'x': torch.as_tensor(data, dtype=torch.float64)}
+            grads_list, loss_list = self.mdl.__gpu_task__(
+                batch_size=batch_size, is_training=True, data_batch=data_batch, opt_op=self.opt_ops)   # my_sngan.py:419-421
+        finally:
+            tf.random_normal = orig_rn
+            tf.get_variable = orig_gv
+        if init is not None:
+            missing = set(init) - set(tf.shim_variables())
+            assert not missing, 'oracle variables the reference never created: {}'.format(sorted(missing))
+        return grads_list, loss_list
+
+    def run(self, grads_list):
+        dis_op = self.opt_ops[0].apply_gradients(grads_list[0], global_step=self.global_step)   # my_sngan.py:424
+        gen_op = self.opt_ops[1].apply_gradients(grads_list[1])                                 # my_sngan.py:425
+        update_ops = tf.get_collection(tf.GraphKeys.UPDATE_OPS)                                 # graph_func.py:848
+        for op in [dis_op, gen_op] + update_ops:          # one sess.run: every value was computed from pre-update variables
+            op()
+
+
+def _named_grads(grads_and_vars):
+    names = {id(v): k for k, v in tf.shim_variables().items()}
+    return {names[id(v)]: (torch.zeros_like(v) if g is None else g).detach().numpy() for g, v in grads_and_vars}
+
+
+def ref_step_case(loss_type):
+    """Twin of make_golden.step_case: same architecture, initial variables, data and codes."""
+    base = mg.step_case(loss_type)
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    B = base['data'].shape[0]
+    run = ReferenceRun(arch, loss_type, lr_list=(5e-4, 2e-4))
+    init = {k.split(':', 1)[1]: v for k, v in base.items() if k.startswith('before:') or k.startswith('state_before:')}
+    run.set_variables(init)
+    grads_list, (lg, ld) = run.build(base['data'], base['code'], B)
+    out = {k: v for k, v in base.items() if k in ('data', 'code') or k.startswith('before:') or k.startswith('state_before:')}
+    out['loss_gen'], out['loss_dis'] = lg.detach().numpy(), ld.detach().numpy()
+    for k, v in list(_named_grads(grads_list[0]).items()) + list(_named_grads(grads_list[1]).items()):
+        out['grad:' + k] = v
+    # scores / images are intermediate tensors of __gpu_task__; recompute them with the reference's own nets
+    saved_updates = list(tf.get_collection(tf.GraphKeys.UPDATE_OPS))
+    gen_batch = run.mdl.Gen({'x': torch.as_tensor(base['code'], dtype=torch.float64)}, is_training=True)
+    dis_out = run.mdl.Dis(SNGan.concat_two_batches({'x': torch.as_tensor(base['data'], dtype=torch.float64)}, gen_batch), is_training=True)
+    out['x_gen'] = gen_batch['x'].detach().numpy()
+    out['scores'] = dis_out['x'].detach().numpy()
+    tf._S.collections[tf.GraphKeys.UPDATE_OPS] = saved_updates      # drop the BN update ops of the recomputation
+    run.run(grads_list)
+    store = tf.shim_variables()
+    for k in base:
+        if k.startswith('after:') or k.startswith('state_after:'):
+            out[k] = store[k.split(':', 1)[1]].detach().numpy()
+    assert int(run.global_step) == 1
+    return out
+
+
+SAMPLE = 257   # stride of the per-variable sample in the CIFAR fixture
+
+
+def ref_step_cifar(batch=4, seed=2, steps=2, act_k=None):
+    """The reference's own CIFAR architecture dictionary (my_test_cifar.py:12-38), `steps` consecutive fused steps.
+    act_k: optional override of the script's 64^(1/8) -- a larger multiplier spreads the scores so that the kernel
+    differences are O(1) and an fp32 implementation can be compared at 1e-3 (the *_k27 fixture)."""
+    arch = reference_architecture('my_test_cifar.py')
+    if act_k is not None:
+        for layer in arch['discriminator']:
+            layer['act_k'] = act_k
+    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=seed)        # only for the seeded initial variables
+    onet.warm_spectral_norm(m, 6)
+    init = {}
+    for d in (m.gen_params, m.dis_params, m.gen_state, m.dis_state):
+        init.update({k: v.detach().clone() for k, v in d.items()})
+    run = ReferenceRun(arch, 'rep', lr_list=(5e-4, 2e-4))
+    run.set_variables(init)
+    out = {'seed': np.asarray(seed), 'batch': np.asarray(batch), 'steps': np.asarray(steps), 'warm': np.asarray(6),
+           'act_k': np.asarray(arch['discriminator'][0]['act_k']),
+           'sample_stride': np.asarray(SAMPLE)}
+    for t in range(steps):
+        data, code = onet.synthetic_batch(arch, batch, seed=5 + 10 * t, dtype=torch.float32)
+        grads_list, (lg, ld) = run.build(data.double(), code.double(), batch)
+        out['loss_gen_%d' % t], out['loss_dis_%d' % t] = lg.detach().numpy(), ld.detach().numpy()
+        for k, v in list(_named_grads(grads_list[0]).items()) + list(_named_grads(grads_list[1]).items()):
+            out['grad_norm_%d:%s' % (t, k)] = np.asarray(np.linalg.norm(v.ravel()))
+            out['grad_sample_%d:%s' % (t, k)] = v.ravel()[::SAMPLE].copy()
+        run.run(grads_list)
+        for k, v in tf.shim_variables().items():
+            a = v.detach().numpy().ravel()
+            out['var_norm_%d:%s' % (t, k)] = np.asarray(np.linalg.norm(a))
+            out['var_sample_%d:%s' % (t, k)] = a[::SAMPLE].copy()
+    return out
+
+
+def main():
+    for lt in ('rep', 'rmb', 'mmd_g', 'mgb'):
+        for b in (2, 3, 64) if lt in ('rep', 'rmb') else (64,):
+            np.savez_compressed(os.path.join(HERE, 'ref_mmd_{}_{}.npz'.format(lt, b)), **ref_mmd_case(lt, b))
+    np.savez_compressed(os.path.join(HERE, 'ref_mmd_rep_256.npz'), **ref_mmd_case('rep', 256))
+    np.savez_compressed(os.path.join(HERE, 'ref_mmd_rmb_w_1_0.npz'), **ref_mmd_case('rmb', 32, w=(1.0, 0.0)))
+    cases = {'conv_k3s1_useu': ('c', 8, 16, 6, 3, 1), 'conv_k4s2_nouseu': ('c', 8, 16, 8, 4, 2), 'dense_nouseu': ('d', 64, 16, 1, 1, 1),
+             'dense_useu': ('d', 16, 32, 1, 1, 1), 'conv_image': ('c', 3, 8, 8, 3, 1)}
+    for i, (name, c) in enumerate(cases.items()):
+        np.savez_compressed(os.path.join(HERE, 'ref_sn_{}.npz'.format(name)), **ref_sn_case(*c, seed=10 + i))
+    for lt in ('rep', 'rmb'):
+        np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_{}.npz'.format(lt)), **ref_step_case(lt))
+    np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep.npz'), **ref_step_cifar())
+    np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep_k27.npz'), **ref_step_cifar(batch=8, act_k=2.7))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,5 +1,6 @@
-"""GPU: the CUDA path against the COMMITTED golden fixtures (no oracle at run time), and the reference-facing Python
-API (GANLoss autograd, SpectralNorm, SNGan.training + Agent + checkpoint round trip)."""
+"""GPU: the CUDA path against the COMMITTED golden fixtures (no oracle at run time) -- both the `ref_*.npz` family produced
+by executing the reference's own Python (tests/golden/make_reference_fixtures.py) and its oracle-authored twins -- and the
+reference-facing Python API (GANLoss autograd, SpectralNorm, SNGan.training + Agent + checkpoint round trip)."""
 import glob
 import os
 
@@ -11,17 +12,26 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
+def _fixtures(pattern):
+    return sorted(glob.glob(os.path.join(GOLD, pattern)) + glob.glob(os.path.join(GOLD, 'ref_' + pattern)))
+
+
+def _stem(path):
+    name = os.path.basename(path)
+    return name[4:] if name.startswith('ref_') else name
+
+
 def rel(a, b):
     a = torch.as_tensor(np.asarray(a)).double().reshape(-1)
     b = torch.as_tensor(np.asarray(b)).double().reshape(-1)
     return float((a - b).norm() / max(float(b.norm()), 1e-30))
 
 
-@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'mmd_*.npz'))), ids=os.path.basename)
+@pytest.mark.parametrize('path', _fixtures('mmd_*.npz'), ids=os.path.basename)
 def test_ganloss_autograd_against_golden(cuda, path):
     from mmdgan_b200.GeneralTools.math_func import GANLoss
     z = np.load(path)
-    lt = os.path.basename(path).split('_')[1]
+    lt = _stem(path).split('_')[1]
     lt = 'mmd_g' if lt == 'mmd' else lt
     g = torch.from_numpy(z['gen']).cuda().requires_grad_(True)
     r = torch.from_numpy(z['real']).cuda().requires_grad_(True)
@@ -34,7 +44,7 @@ def test_ganloss_autograd_against_golden(cuda, path):
     assert np.abs(r.grad.cpu().numpy() - (2 * z['dLg_ddata'] + 3 * z['dLd_ddata'])).max() < 1e-4 * gscale + 1e-9
 
 
-@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'sn_*.npz'))), ids=os.path.basename)
+@pytest.mark.parametrize('path', _fixtures('sn_*.npz'), ids=os.path.basename)
 def test_spectral_norm_class_against_golden(cuda, path):
     from mmdgan_b200.GeneralTools.math_func import SpectralNorm
     z = np.load(path)
@@ -55,11 +65,12 @@ def test_spectral_norm_class_against_golden(cuda, path):
     assert rel(sn.x.cpu().numpy(), z['x_update']) < 1e-4
 
 
+@pytest.mark.parametrize('family', ['', 'ref_'])
 @pytest.mark.parametrize('loss_type', ['rep', 'rmb'])
-def test_engine_step_against_golden(cuda, loss_type):
+def test_engine_step_against_golden(cuda, loss_type, family):
     from oracle import architectures as oa          # the architecture dictionary only
     from mmdgan_b200.engine import SNGanEngine
-    z = np.load(os.path.join(GOLD, 'step_tiny_{}.npz'.format(loss_type)))
+    z = np.load(os.path.join(GOLD, '{}step_tiny_{}.npz'.format(family, loss_type)))
     arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
     eng = SNGanEngine(arch, 8, loss_type=loss_type, use_graph=False)
     for net in (eng.G, eng.D):
@@ -150,3 +161,54 @@ def test_sngan_training_from_tfrecords(cuda, tmp_path):
         else:
             runs.append(mdl.training(source, agent, 48, [5e-4, 2e-4], max_step=4, batch_size=16, reader_seed=7))
     assert all(np.isfinite(runs[0])) and list(runs[0]) == list(runs[1])
+
+
+def test_engine_cifar_steps_against_reference_execution(cuda):
+    """The reference's own CIFAR architecture dictionary (parsed from my_test_cifar.py), two fused steps executed by the
+    reference's SNGan.__gpu_task__ / Net / SpectralNorm / GANLoss on top of oracle/tfshim (ref_step_cifar_rep_k27.npz;
+    act_k raised to 2.7 so that an fp32 evaluation of the kernel differences is well conditioned).  The fixture stores the
+    seed of the initial variables, the losses, and norm + strided sample of every gradient / updated variable."""
+    from oracle import architectures as oa
+    from oracle import net as onet                 # seeded initial variables and synthetic inputs only
+    from mmdgan_b200.engine import SNGanEngine
+    z = np.load(os.path.join(GOLD, 'ref_step_cifar_rep_k27.npz'))
+    arch = oa.cifar(act_k=float(z['act_k']))
+    B, stride = int(z['batch']), int(z['sample_stride'])
+    init = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=int(z['seed']))
+    onet.warm_spectral_norm(init, int(z['warm']))
+    eng = SNGanEngine(arch, B, loss_type='rep', use_graph=False)
+    before = {}
+    for net, params, state in ((eng.G, init.gen_params, init.gen_state), (eng.D, init.dis_params, init.dis_state)):
+        for k, v in params.items():
+            net.set_variable(k, v)
+            before[k] = v.numpy().ravel()[::stride]
+        for k, v in state.items():
+            net.set_state(k, v)
+        net.refresh()
+    for t in range(int(z['steps'])):
+        data, code = onet.synthetic_batch(arch, B, seed=5 + 10 * t, dtype=torch.float32)
+        lg, ld = eng.step(data, code)
+        tol = 1e-3 if t == 0 else 2e-2      # after one Adam update (lr * sign-like steps) the two trajectories differ slightly
+        assert abs(lg - float(z['loss_gen_%d' % t])) <= tol * abs(float(z['loss_gen_%d' % t])) + 1e-7
+        assert abs(ld - float(z['loss_dis_%d' % t])) <= tol * abs(float(z['loss_dis_%d' % t])) + 1e-7
+        if t > 0:
+            continue
+        gmax = max(float(z['grad_norm_0:' + n]) for n in eng.D.var_offsets)
+        num = den = 0.0
+        for net in (eng.G, eng.D):
+            for name in net.var_offsets:
+                got = net.get_grad(name).cpu().numpy().astype(np.float64)
+                ref_norm = float(z['grad_norm_0:' + name])
+                if ref_norm < 1e-6 * gmax:
+                    assert np.linalg.norm(got) < 1e-4 * gmax, name
+                    continue
+                assert abs(np.linalg.norm(got) - ref_norm) < 1e-3 * ref_norm, name
+                ref_s = z['grad_sample_0:' + name]
+                assert np.linalg.norm(got.ravel()[::stride] - ref_s) <= 1e-3 * np.linalg.norm(ref_s) + 1e-3 * ref_norm * (len(ref_s) / got.size) ** 0.5, name
+                var = net.get_variable(name).cpu().numpy().astype(np.float64).ravel()[::stride]
+                num += np.linalg.norm(var - z['var_sample_0:' + name]) ** 2
+                den += np.linalg.norm(z['var_sample_0:' + name] - before[name]) ** 2
+            for name in net.state_names():
+                got = net.get_state(name).cpu().numpy().astype(np.float64).ravel()[::stride]
+                assert rel(got, z['var_sample_0:' + name]) < 1e-3, name
+        assert (num / den) ** 0.5 < 2e-2

@@ -1,4 +1,8 @@
-"""CPU: the oracle reproduces the committed golden fixtures (tests/golden/, generated by make_golden.py)."""
+"""CPU: the oracle reproduces the committed golden fixtures in tests/golden/.
+
+Two families with identical keys: `ref_*.npz` were produced by EXECUTING THE REFERENCE'S OWN PYTHON (math_func.py,
+layer_func.py, my_sngan.py, graph_func.py imported unmodified on top of oracle/tfshim; make_reference_fixtures.py) --
+these pin the oracle to the reference; the un-prefixed twins were authored from the oracle itself (make_golden.py)."""
 import glob
 import os
 
@@ -13,17 +17,26 @@ from oracle import net as onet
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'mmd_*.npz'))), ids=os.path.basename)
+def _fixtures(pattern):
+    return sorted(glob.glob(os.path.join(GOLD, pattern)) + glob.glob(os.path.join(GOLD, 'ref_' + pattern)))
+
+
+def _stem(path):
+    name = os.path.basename(path)
+    return name[4:] if name.startswith('ref_') else name
+
+
+@pytest.mark.parametrize('path', _fixtures('mmd_*.npz'), ids=os.path.basename)
 def test_mmd_golden(path):
     z = np.load(path)
-    loss_type = os.path.basename(path).split('_')[1]
+    loss_type = _stem(path).split('_')[1]
     loss_type = 'mmd_g' if loss_type == 'mmd' else loss_type
     out = omm.gan_loss_with_grads(z['gen'], z['real'], loss_type, rep_weights=tuple(z['rep_weights']))
     for k in ['loss_gen', 'loss_dis', 'dLg_dgen', 'dLd_dgen', 'dLd_ddata', 'dLg_ddata']:
         assert np.allclose(out[k], z[k], rtol=0, atol=1e-13), k
 
 
-@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'sn_*.npz'))), ids=os.path.basename)
+@pytest.mark.parametrize('path', _fixtures('sn_*.npz'), ids=os.path.basename)
 def test_sn_golden(path):
     z = np.load(path)
     op = str(z['op'])
@@ -39,9 +52,10 @@ def test_sn_golden(path):
     assert np.allclose(ds.numpy(), z['dsigma_dw'], atol=1e-13)
 
 
+@pytest.mark.parametrize('family', ['', 'ref_'])
 @pytest.mark.parametrize('loss_type', ['rep', 'rmb'])
-def test_step_golden(loss_type):
-    z = np.load(os.path.join(GOLD, 'step_tiny_{}.npz'.format(loss_type)))
+def test_step_golden(loss_type, family):
+    z = np.load(os.path.join(GOLD, '{}step_tiny_{}.npz'.format(family, loss_type)))
     arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
     m = onet.OracleSNGan(arch, loss_type, dtype=torch.float64, seed=3)
     for store, pre in ((m.gen_params, 'before:'), (m.dis_params, 'before:'), (m.gen_state, 'state_before:'), (m.dis_state, 'state_before:')):
@@ -57,3 +71,43 @@ def test_step_golden(loss_type):
         assert np.allclose(v.numpy(), z['after:' + k], atol=1e-12), k
     for k, v in list(m.gen_state.items()) + list(m.dis_state.items()):
         assert np.allclose(v.numpy(), z['state_after:' + k], atol=1e-12), k
+
+
+def test_reference_fixture_families_are_complete():
+    """Every oracle-authored fixture has a reference-executed twin with the same keys."""
+    for path in glob.glob(os.path.join(GOLD, '*.npz')):
+        name = os.path.basename(path)
+        if name.startswith('ref_'):
+            continue
+        twin = os.path.join(GOLD, 'ref_' + name)
+        assert os.path.exists(twin), twin
+        assert set(np.load(twin).files) == set(np.load(path).files), name
+
+
+@pytest.mark.parametrize('name', ['ref_step_cifar_rep.npz', 'ref_step_cifar_rep_k27.npz'])
+def test_cifar_steps_against_reference_execution(name):
+    """Two consecutive fused steps of the reference's own CIFAR architecture dictionary (my_test_cifar.py:12-38, parsed
+    from the script) executed by the reference's SNGan.__gpu_task__ / Net / SpectralNorm / GANLoss (ref_step_cifar_rep.npz):
+    losses, every gradient and every variable after each update (norm + strided sample per variable)."""
+    z = np.load(os.path.join(GOLD, name))
+    arch = oa.cifar(act_k=float(z['act_k']))
+    B, stride = int(z['batch']), int(z['sample_stride'])
+    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=int(z['seed']))
+    onet.warm_spectral_norm(m, int(z['warm']))
+    for t in range(int(z['steps'])):
+        data, code = onet.synthetic_batch(arch, B, seed=5 + 10 * t, dtype=torch.float32)
+        data, code = data.double(), code.double()
+        lg, ld, gg, gd, _, _ = m.grads(data, code)
+        assert abs(float(lg) - float(z['loss_gen_%d' % t])) < 1e-12 and abs(float(ld) - float(z['loss_dis_%d' % t])) < 1e-12
+        gmax = max(float(z['grad_norm_%d:%s' % (t, k)]) for k in gd)
+        for k, v in list(gg.items()) + list(gd.items()):
+            ref_norm = float(z['grad_norm_%d:%s' % (t, k)])
+            assert abs(float(v.norm()) - ref_norm) <= 1e-9 * ref_norm + 1e-12 * gmax, k
+            assert np.allclose(v.numpy().ravel()[::stride], z['grad_sample_%d:%s' % (t, k)], rtol=1e-8, atol=1e-12 * gmax), k
+        m.step(data, code)
+        for store in (m.gen_params, m.dis_params, m.gen_state, m.dis_state):
+            for k, v in store.items():
+                # the score-layer bias gradient is analytically zero (the loss is translation invariant); Adam amplifies its
+                # round-off, so that one variable is compared with an absolute tolerance of one learning-rate step
+                atol = 1e-3 if k.endswith('l8_s/bias/bias') else 1e-10
+                assert np.allclose(v.detach().numpy().ravel()[::stride], z['var_sample_%d:%s' % (t, k)], rtol=1e-8, atol=atol), k
