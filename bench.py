@@ -249,15 +249,16 @@ def run_ours(args):
                 'traffic': None, 'peak_source': peaks['source'] + ' bf16 sustained (MEASURED_PEAKS.json)',
                 'kernel': 'conv_gemm(_pair)_kernel + wgrad_gemm_kernel: the {} batch-sized tcgen05 launches of one step'.format(len(evs)),
                 'gemm_ms_per_step': gemm_ms, 'eager_step_ms': t0.elapsed_time(t1), 'share_of_graph_step': gemm_ms / (ms_dev / args.steps),
-                'note': 'algorithmic FLOPs = (3G+7D) x 2 x B; tensor_passes={} tf32 MMAs per algorithmic FLOP (tf32 dense peak is '
-                        'half the bf16 peak), so frac <= {:.3f} by construction in this precision mode'.format(
-                            args.passes, 0.5 / args.passes)}
+                'note': ('algorithmic FLOPs = (3G+7D) x 2 x B; parity mode: forward launches (G+2D) issue 6 bf16 plane-pair MMAs per '
+                         'algorithmic FLOP, gradient launches (2G+5D) 3, i.e. 3.88 tensor FLOPs per algorithmic FLOP on average, '
+                         'so frac <= 0.258 by construction in this precision mode') if args.passes == 3 else
+                        'algorithmic FLOPs = (3G+7D) x 2 x B; single bf16 pass (speed mode, not parity grade)'}
 
     if rank == 0:
         line = {
             'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'tf32x3' if args.passes == 3 else 'tf32', 'data': 'synthetic',
+            'dtype': 'bf16x6 fwd / bf16x3 grad (bf16 planes, fp32 accumulate)' if args.passes == 3 else 'bf16', 'data': 'synthetic',
             'config': {'workload': '{} {}x{} SNGAN + {} MMD, batch {} per GPU, spectral norm on'.format(
                 name, arch['input'][0][1], arch['input'][0][2], loss_type, batch),
                 'global_batch': batch * world, 'parallelism': 'dp{}'.format(world),

@@ -6,18 +6,25 @@
  * with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
  *
  * Conventions: extern "C"; every function returns int (0 = ok, < 0 = MMDGAN_E*); mmdgan_last_error() gives the
- * thread-local message; all tensor arguments are caller-owned DEVICE pointers to contiguous fp32 (16-byte aligned);
- * `stream` is a cudaStream_t passed as void*; no allocation, no synchronisation and no host copies inside, so every
- * call is CUDA-graph capturable; workspaces are sized by the *_workspace() queries and provided by the caller.
+ * thread-local message; all tensor arguments are caller-owned DEVICE pointers to contiguous memory (16-byte aligned),
+ * fp32 unless typed mmdgan_bf16; `stream` is a cudaStream_t passed as void*; no allocation, no synchronisation and no
+ * host copies inside, so every call is CUDA-graph capturable; workspaces are sized by the *_workspace() queries and
+ * provided by the caller.
  *
- * Internal activation format ("planes"): NHWC, [plane][N*H*W][C] with C a multiple of 4.  Plane 0 holds the fp32
- * value, plane 1 (at + *_plane elements) holds lo = rn_tf32(x - trunc_tf32(x)); the tensor-core kernels multiply
- * x*w + x_lo*w + x*w_lo (npass = 3) to obtain fp32-grade products from the tf32 pipe.  npass = 1 is plain tf32.
+ * Internal GEMM-operand format ("planes"): NHWC, [plane][N*H*W][C] raw bf16 bits, C in {8, 16} or a multiple of 32,
+ * consecutive planes *_plane ELEMENTS apart (a multiple of 8).  An fp32 value x is carried as
+ *   p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1):
+ * three planes hold the fp32 value (error <= 2^-25 |x|), two planes 16 significand bits.  The tcgen05 kernels multiply
+ * plane pairs with fp32 accumulation: npass = 6 -> {00,01,10,02,20,11} (fp32-grade products: forward passes, whose
+ * errors the MMD loss amplifies), npass = 3 -> {00,01,10} (~2^-17: input / weight gradients, linear in the operands),
+ * npass = 1 -> {00} (plain bf16 speed mode).  A launch reads the first 3 / 2 / 1 planes of its operands.
  */
 #ifndef MMDGAN_B200_H
 #define MMDGAN_B200_H
 
 #include <stddef.h>
+
+typedef unsigned short mmdgan_bf16; /* raw bf16 bits */
 
 #ifdef __cplusplus
 extern "C" {
@@ -39,14 +46,18 @@ int mmdgan_check_device(void);
  * Layout at the boundary.  Replaces the NCHW float32 batch contract of ReadTFRecords
  * (GeneralTools/input_func.py:837-868) and tf.concat of real + generated batches (DeepLearning/my_sngan.py:244-256):
  * the real batch is written straight into rows [0, B) of the discriminator's 2B input buffer. */
-int mmdgan_nchw_to_nhwc(const float* src, float* dst, long long dst_plane, int N, int C, int H, int W, int Cpad, void* stream);
-int mmdgan_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int Cpad, void* stream);
-int mmdgan_make_lo_plane(const float* hi, float* lo, long long n, void* stream);
+int mmdgan_nchw_to_nhwc(const float* src, mmdgan_bf16* dst, long long dst_plane, int npl, int N, int C, int H, int W, int Cpad,
+                        void* stream);
+int mmdgan_nhwc_to_nchw(const mmdgan_bf16* src, long long src_plane, int npl, float* dst, int N, int C, int H, int W, int Cpad,
+                        void* stream);
+/* fp32 [n] <-> bf16 planes [npl][n] in the same element order */
+int mmdgan_to_planes(const float* x, mmdgan_bf16* dst, long long dst_plane, int npl, long long n, void* stream);
+int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, float* out, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Weight packing: canonical reference layouts (conv [k,k,Cin,Cout] layer_func.py:584, transposed conv
  * [k,k,Cout,Cin] layer_func.py:595, dense [in,out] layer_func.py:577) -> K-major GEMM operand [planes][classes *
- * rows_pad][kpad].  dst_plane = 0 writes one rn-tf32 plane (npass = 1). */
+ * rows_pad][kpad] of npl bf16 planes (3 for a forward operand, 2 for an input-gradient operand). */
 #define MMDGAN_PACK_CONV_FWD 0
 #define MMDGAN_PACK_CONV_DGRAD_S1 1
 #define MMDGAN_PACK_CONV_DGRAD_S2 2
@@ -56,8 +67,9 @@ int mmdgan_make_lo_plane(const float* hi, float* lo, long long n, void* stream);
 #define MMDGAN_PACK_DENSE_DGRAD 6
 typedef struct mmdgan_pack_desc {
     const float* w;
-    float* out;
+    mmdgan_bf16* out;
     long long plane;
+    int npl, pad0;
     int mode, k, Cin, Cout, Cs, rows_pad, kpad, classes;
     int in_C, in_HW, out_C, out_HW; /* dense: NCHW-flatten <-> NHWC-flatten feature permutation (HW <= 1: identity) */
 } mmdgan_pack_desc;
@@ -78,35 +90,38 @@ int mmdgan_permute_features(const float* src, float* dst, int n, int C, int HW, 
  * Gather-GEMM on tcgen05 tensor cores: tf.matmul / tf.nn.conv2d / tf.nn.conv2d_transpose forward
  * (GeneralTools/layer_func.py:909-928) and their input gradients (DeepLearning/my_sngan.py:301-304), with the
  * kernel * (act_k / sigma) scaling (layer_func.py:884-887), bias add (946-952), activation (104-167) or activation
- * derivative, tf32 hi/lo split and per-tile column sums fused into the epilogue. */
+ * derivative, bf16 plane split and per-tile column sums fused into the epilogue. */
 typedef struct mmdgan_gemm_class {
     int oy, ox, ooy, oox, wrow, pad0, pad1, pad2;
 } mmdgan_gemm_class;
 typedef struct mmdgan_gemm_desc {
-    const float* src;
+    const mmdgan_bf16* src;
     long long src_plane;
     int Nimg, Hs, Ws, Cs;
     int Hg, Wg, sy, sx, TH, TW;
-    const float* w; /* packed weights */
+    const mmdgan_bf16* w; /* packed weights */
     long long w_plane;
     long long w_rows; /* classes * rows_pad */
     int kpad, classes;
-    float* dst;
+    void* dst;          /* out_mode 0: mmdgan_bf16 planes [dst_npl][rows][Cd]; out_mode 2: float [rows][Cd] */
     long long dst_plane;
+    int dst_npl;        /* planes written in out_mode 0 (1..3) */
     int Hd, Wd, Cd, osy, osx, Ncols;
     float alpha_k;
     const float* sigma; /* alpha = sigma ? alpha_k / *sigma : alpha_k */
     const float* bias;
     int act;            /* 0 linear, 1 lrelu(0.1), 2 relu, 3 tanh */
-    const float* aux;   /* multiply by act'(aux) evaluated from the layer output */
-    int aux_mode;
+    const mmdgan_bf16* aux; /* planes of the layer OUTPUT a: the result is multiplied by act'(a) */
+    long long aux_plane;
+    int aux_npl;
+    int aux_mode;       /* 1 lrelu', 2 relu' (sign of plane 0), 3 tanh' = 1 - a^2 (all aux_npl planes) */
     long long aux_wrap_at, aux_wrap_len;
     float* colsum;      /* [tiles_m * classes][Ncols] or null */
     float* colsumsq;
     long long colsum_rows;
-    int out_mode;       /* 0 raw + lo plane, 1 rn-tf32 single plane, 2 raw single plane */
+    int out_mode;       /* 0 bf16 planes, 2 raw fp32 */
     int bn;             /* N tile: 16, 32, 64, 128, 256 */
-    int npass;          /* 3 (fp32-grade tf32x3) or 1 (tf32) */
+    int npass;          /* 6, 3 or 1 plane-pair products per k-block (see the header comment) */
     int cta_pair;       /* 1: tcgen05 cta_group::2 -- a 2-CTA cluster shares one 256 x bn tile (bn 128 or 256) */
     mmdgan_gemm_class cls[4];
 } mmdgan_gemm_desc;
@@ -115,24 +130,25 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream);
 int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg);
 
 /* out[m][n] = alpha * sum_k a[m][k] * wt[n][k] + bias[n] for N in {4,8,16,32} output columns (the critic's score layer,
- * tf.matmul at layer_func.py:909-911 with 16 outputs): fp32 CUDA-core kernel, wt = hi plane of the packed forward operand */
-int mmdgan_dense_small_fwd(const float* a, int rows, int K, const float* wt, int kpad, int N, float alpha_k, const float* sigma,
-                           const float* bias, float* out, int ldo, void* stream);
+ * tf.matmul at layer_func.py:909-911 with 16 outputs): fp32 CUDA-core kernel on the values reassembled from npl planes of
+ * the activation a and of the packed forward operand wt */
+int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int rows, int K, const mmdgan_bf16* wt, long long w_plane,
+                           int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream);
 
 /* Weight gradient: W[r][(t,c)] = sum_p P[p][r] * G[g(p,t)][c] (filter gradients of the ops above and the
  * d(sigma)/dW term of SpectralNorm, GeneralTools/math_func.py:661-672).  out: [splits][Cp][TH*TW*Cs]. */
 typedef struct mmdgan_wgrad_desc {
-    const float* plain; /* [planes][P][Cp] */
+    const mmdgan_bf16* plain; /* [planes][P][Cp] */
     long long plain_plane;
     long long P;
     int Cp;
-    const float* g;     /* gathered activation planes [Nimg*Hs*Ws][Cs] */
+    const mmdgan_bf16* g;     /* gathered activation planes [Nimg*Hs*Ws][Cs] */
     long long g_plane;
     int Nimg, Hs, Ws, Cs;
     int Hg, Wg, sy, sx, TH, TW, oy, ox;
     int splits;
     float* out;
-    int bn, npass;
+    int bn, npass;      /* bn 64 or 128; npass 3 or 1 */
 } mmdgan_wgrad_desc;
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream);
 
@@ -154,25 +170,27 @@ int mmdgan_sn_grad_combine(float* g, const float* s, const double* dots, int ndo
                            void* stream);
 int mmdgan_scale_by_sigma(float* g, const float* sigma, float act_k, long long n, void* stream);
 /* sigma = ||v||, out = v / (sigma + eps) as planes: SpectralNorm._l2_norm / _l2_normalize_ (math_func.py:639-659) */
-int mmdgan_sn_normalize(const float* v, long long n, float eps, float* sigma_out, float* out, long long out_plane, void* stream);
+int mmdgan_sn_normalize(const float* v, long long n, float eps, float* sigma_out, mmdgan_bf16* out, long long out_plane, int npl,
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Reductions of per-tile partial sums (bias gradients; deterministic order, double accumulation) */
 int mmdgan_reduce_tiles(const float* partials, int T, int C, float scale, float* out, void* stream);
 int mmdgan_colsum_small(const float* x, int rows, int C, float* out, void* stream);
+int mmdgan_colsum_planes(const mmdgan_bf16* x, long long plane, int npl, int rows, int C, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Batch normalisation: tf.layers.batch_normalization(axis=1, training, fused=True) (layer_func.py:953-966) */
 int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                        float* invstd, float* moving_mean, float* moving_var, void* stream);
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
-                    long long total, int act, float* out, long long out_plane, void* stream);
+                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, void* stream);
 int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int C, long long rows, int rows_per_block, int act, float* psum, float* psumx,
                          void* stream);
 int mmdgan_bn_bwd_apply(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
-                        const float* beta, const float* dbeta, const float* dgamma, int C, long long rows, int act, float* out,
-                        long long out_plane, void* stream);
+                        const float* beta, const float* dbeta, const float* dgamma, int C, long long rows, int act,
+                        mmdgan_bf16* out, long long out_plane, int npl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused pairwise squared distance -> Gaussian kernel(s) -> rep / rmb / mmd_g / mgb losses + score gradients

@@ -295,23 +295,26 @@ class SpectralNorm(object):
         x_is_input = self.use_u if self.sn_def['op'] != 'tc' else (not self.use_u)
         n_in = lop.Hin * lop.Win
         n_out = lop.Hout * lop.Wout
-        xp = K.new_planes(n_in if x_is_input else n_out, lop.Cs_in if x_is_input else lop.Cs_out, npass, kernel.device)
-        K.nchw_to_planes(self.x, xp, npass)
+        npl = K.mode_planes(npass)
+        raw = lambda rows, c: torch.zeros((1, rows, c), dtype=torch.float32, device=kernel.device)
+        xp = K.new_planes(n_in if x_is_input else n_out, lop.Cs_in if x_is_input else lop.Cs_out, npl, kernel.device)
+        K.nchw_to_planes(self.x, xp)
         sigma = torch.zeros(1, device=kernel.device)
         for _ in range(self.num_iter):
+            # both operators act as FORWARD maps here (sigma = ||F x||): fp32-grade products for either direction
             if x_is_input:
-                v = K.new_planes(n_out, lop.Cs_out, 1, kernel.device)
+                v = raw(n_out, lop.Cs_out)
                 lop.forward(xp, 1, v, out_mode=2)
-                y = K.new_planes(n_out, lop.Cs_out, npass, kernel.device)
+                y = K.new_planes(n_out, lop.Cs_out, npl, kernel.device)
                 K.sn_normalize(v, v.numel(), y, sigma_out=sigma, eps=FLAGS.EPSI)
-                w = K.new_planes(n_in, lop.Cs_in, 1, kernel.device)
-                lop.dgrad(y, 1, w, out_mode=2)
+                w = raw(n_in, lop.Cs_in)
+                lop.dgrad(y, 1, w, out_mode=2, npass=lop.fwd_npass)
             else:
-                v = K.new_planes(n_in, lop.Cs_in, 1, kernel.device)
-                lop.dgrad(xp, 1, v, out_mode=2)
-                y = K.new_planes(n_in, lop.Cs_in, npass, kernel.device)
+                v = raw(n_in, lop.Cs_in)
+                lop.dgrad(xp, 1, v, out_mode=2, npass=lop.fwd_npass)
+                y = K.new_planes(n_in, lop.Cs_in, npl, kernel.device)
                 K.sn_normalize(v, v.numel(), y, sigma_out=sigma, eps=FLAGS.EPSI)
-                w = K.new_planes(n_out, lop.Cs_out, 1, kernel.device)
+                w = raw(n_out, lop.Cs_out)
                 lop.forward(y, 1, w, out_mode=2)
             K.sn_normalize(w, w.numel(), xp, eps=FLAGS.EPSI)
         shp = list(self.x.shape)

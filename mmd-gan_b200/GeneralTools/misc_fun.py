@@ -15,7 +15,8 @@ class SetFlag(object):
         self.IMAGE_FORMAT_ALIAS = 'NCHW'
         self.WEIGHT_INITIALIZER = 'default'
         self.SPECTRAL_NORM_MODE = 'default'   # 'default' = 'PICO'; 'sn_paper' = PIM (not built yet: raises)
-        # B200 engine knobs (new): 3 = fp32-grade tf32x3 tensor-core products (parity mode), 1 = plain tf32
+        # B200 engine knobs (new): 3 = parity mode (fp32 values as bf16 planes: 6 plane-pair tensor-core products in the
+        # forward passes, 3 in the gradient passes), 1 = a single bf16 pass (speed mode, not parity grade)
         self.TENSOR_PASSES = 3
 
     def print(self, info, force_print=False):

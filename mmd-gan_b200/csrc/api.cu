@@ -10,17 +10,19 @@
 
 namespace mg {
 // conv_gemm.cu / wgrad_gemm.cu
-int launch_conv_gemm(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes, int bn,
+int launch_conv_gemm(const ConvGemmParams& p, const uint16_t* w, long long w_plane, long long w_rows, int kpad, int classes, int bn,
                      int npass, int pair, cudaStream_t st);
-int launch_wgrad_gemm(const WgradParams& p, const float* plain, long long plain_plane, int splits, int bn, int npass,
+int launch_wgrad_gemm(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, int bn, int npass,
                       cudaStream_t st);
 // mmd.cu
 int launch_mmd(const MmdParams& p, cudaStream_t st);
 int mmd_grid_blocks(int b);
 // elementwise.cu
-int l_nchw_to_nhwc(const float*, float*, long long, int, int, int, int, int, cudaStream_t);
-int l_nhwc_to_nchw(const float*, float*, int, int, int, int, int, cudaStream_t);
-int l_make_lo_plane(const float*, float*, long long, cudaStream_t);
+int l_nchw_to_nhwc(const float*, uint16_t*, long long, int, int, int, int, int, int, cudaStream_t);
+int l_nhwc_to_nchw(const uint16_t*, long long, int, float*, int, int, int, int, int, cudaStream_t);
+int l_to_planes(const float*, uint16_t*, long long, int, long long, cudaStream_t);
+int l_from_planes(const uint16_t*, long long, int, float*, long long, cudaStream_t);
+int l_colsum_planes(const uint16_t*, long long, int, int, int, float*, cudaStream_t);
 int l_pack_weights(const PackParams&, cudaStream_t);
 int l_permute_features(const float*, float*, int, int, int, int, cudaStream_t);
 int l_reduce_tiles(const float*, int, int, float, float*, cudaStream_t);
@@ -29,18 +31,19 @@ int wgrad_reduce_blocks(long long total);
 int l_wgrad_reduce(const WredParams&, cudaStream_t);
 int l_sn_grad_combine(float*, const float*, const double*, int, const float*, float, long long, cudaStream_t);
 int l_scale_by_sigma(float*, const float*, float, long long, cudaStream_t);
-int l_sn_normalize(const float*, long long, float, float*, float*, long long, cudaStream_t);
+int l_sn_normalize(const float*, long long, float, float*, uint16_t*, long long, int, cudaStream_t);
 int l_bn_finalize(const float*, const float*, int, int, long long, float, float, float*, float*, float*, float*, cudaStream_t);
-int l_bn_apply(const float*, const float*, const float*, const float*, const float*, int, long long, int, float*, long long,
+int l_bn_apply(const float*, const float*, const float*, const float*, const float*, int, long long, int, uint16_t*, long long, int,
                cudaStream_t);
 int l_bn_bwd_reduce(const float*, const float*, const float*, const float*, const float*, const float*, int, long long, int, int,
                     float*, float*, cudaStream_t);
 int l_bn_bwd_apply(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
-                   long long, int, float*, long long, cudaStream_t);
+                   long long, int, uint16_t*, long long, int, cudaStream_t);
 int l_adam(float*, float*, float*, const float*, long long, float, float, float, float, const int*, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
-int l_dense_small_fwd(const float*, int, int, const float*, int, int, float, const float*, const float*, float*, int, cudaStream_t);
+int l_dense_small_fwd(const uint16_t*, long long, int, int, int, const uint16_t*, long long, int, int, float, const float*, const float*, float*,
+                      int, cudaStream_t);
 int l_nan_flag(const float*, int, int*, cudaStream_t);
 }  // namespace mg
 
@@ -67,7 +70,10 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 extern "C" {
 
 const char* mmdgan_last_error(void) { return g_err; }
-int mmdgan_version(void) { return 100; }
+int mmdgan_version(void) { return 200; }
+
+static inline bool chan_ok(int c) { return c == 8 || c == 16 || (c > 0 && (c & 31) == 0); }
+static inline int npl_for(int npass) { return npass == 6 ? 3 : (npass == 3 ? 2 : 1); }
 
 int mmdgan_check_device(void) {
     int dev = 0;
@@ -78,30 +84,42 @@ int mmdgan_check_device(void) {
     return MMDGAN_OK;
 }
 
-int mmdgan_nchw_to_nhwc(const float* src, float* dst, long long dst_plane, int N, int C, int H, int W, int Cpad, void* stream) {
+int mmdgan_nchw_to_nhwc(const float* src, mmdgan_bf16* dst, long long dst_plane, int npl, int N, int C, int H, int W, int Cpad,
+                        void* stream) {
     if (!src || !dst) return fail(MMDGAN_EINVAL, "mmdgan_nchw_to_nhwc: null pointer");
-    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || (Cpad & 3)) return fail(MMDGAN_ESHAPE, "mmdgan_nchw_to_nhwc: bad shape");
-    return wrap(mg::l_nchw_to_nhwc(src, dst, dst_plane, N, C, H, W, Cpad, S(stream)), "mmdgan_nchw_to_nhwc");
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || (Cpad & 3) || npl < 1 || npl > 3 || (npl > 1 && dst_plane <= 0))
+        return fail(MMDGAN_ESHAPE, "mmdgan_nchw_to_nhwc: bad shape");
+    return wrap(mg::l_nchw_to_nhwc(src, dst, dst_plane, npl, N, C, H, W, Cpad, S(stream)), "mmdgan_nchw_to_nhwc");
 }
-int mmdgan_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int Cpad, void* stream) {
+int mmdgan_nhwc_to_nchw(const mmdgan_bf16* src, long long src_plane, int npl, float* dst, int N, int C, int H, int W, int Cpad,
+                        void* stream) {
     if (!src || !dst) return fail(MMDGAN_EINVAL, "mmdgan_nhwc_to_nchw: null pointer");
-    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C) return fail(MMDGAN_ESHAPE, "mmdgan_nhwc_to_nchw: bad shape");
-    return wrap(mg::l_nhwc_to_nchw(src, dst, N, C, H, W, Cpad, S(stream)), "mmdgan_nhwc_to_nchw");
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || npl < 1 || npl > 3 || (npl > 1 && src_plane <= 0))
+        return fail(MMDGAN_ESHAPE, "mmdgan_nhwc_to_nchw: bad shape");
+    return wrap(mg::l_nhwc_to_nchw(src, src_plane, npl, dst, N, C, H, W, Cpad, S(stream)), "mmdgan_nhwc_to_nchw");
 }
-int mmdgan_make_lo_plane(const float* hi, float* lo, long long n, void* stream) {
-    if (!hi || !lo) return fail(MMDGAN_EINVAL, "mmdgan_make_lo_plane: null pointer");
+int mmdgan_to_planes(const float* x, mmdgan_bf16* dst, long long dst_plane, int npl, long long n, void* stream) {
+    if (!x || !dst) return fail(MMDGAN_EINVAL, "mmdgan_to_planes: null pointer");
+    if (npl < 1 || npl > 3 || (npl > 1 && dst_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_to_planes: bad plane layout");
     if (n <= 0) return MMDGAN_OK;
-    return wrap(mg::l_make_lo_plane(hi, lo, n, S(stream)), "mmdgan_make_lo_plane");
+    return wrap(mg::l_to_planes(x, dst, dst_plane, npl, n, S(stream)), "mmdgan_to_planes");
+}
+int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, float* out, long long n, void* stream) {
+    if (!src || !out) return fail(MMDGAN_EINVAL, "mmdgan_from_planes: null pointer");
+    if (npl < 1 || npl > 3 || (npl > 1 && src_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_from_planes: bad plane layout");
+    if (n <= 0) return MMDGAN_OK;
+    return wrap(mg::l_from_planes(src, src_plane, npl, out, n, S(stream)), "mmdgan_from_planes");
 }
 
 int mmdgan_pack_weights(const mmdgan_pack_desc* d, void* stream) {
     if (!d || !d->w || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: null pointer");
     if (d->mode < 0 || d->mode > 6) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: unknown mode %d", d->mode);
-    if (d->rows_pad <= 0 || d->kpad <= 0 || (d->kpad & 31) || d->classes < 1 || d->classes > 4 || d->Cs <= 0 || (d->Cs & 3))
+    if (d->npl < 1 || d->npl > 3 || (d->npl > 1 && d->plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_pack_weights: bad plane layout");
+    if (d->rows_pad <= 0 || d->kpad <= 0 || (d->kpad & 31) || d->classes < 1 || d->classes > 4 || !chan_ok(d->Cs))
         return fail(MMDGAN_ESHAPE, "mmdgan_pack_weights: bad padded shape rows_pad=%d kpad=%d classes=%d Cs=%d", d->rows_pad, d->kpad,
                     d->classes, d->Cs);
     mg::PackParams p;
-    p.w = d->w; p.out = d->out; p.plane = d->plane; p.mode = d->mode; p.k = d->k; p.Cin = d->Cin; p.Cout = d->Cout; p.Cs = d->Cs;
+    p.w = d->w; p.out = d->out; p.plane = d->plane; p.npl = d->npl; p.pad0 = 0; p.mode = d->mode; p.k = d->k; p.Cin = d->Cin; p.Cout = d->Cout; p.Cs = d->Cs;
     p.rows_pad = d->rows_pad; p.kpad = d->kpad; p.classes = d->classes;
     p.in_C = d->in_C; p.in_HW = d->in_HW; p.out_C = d->out_C; p.out_HW = d->out_HW;
     return wrap(mg::l_pack_weights(p, S(stream)), "mmdgan_pack_weights");
@@ -119,31 +137,35 @@ int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg) {
 
 int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     if (!d || !d->src || !d->w || !d->dst) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: null pointer");
-    if (d->npass != 1 && d->npass != 3) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass must be 1 or 3");
+    if (d->npass != 1 && d->npass != 3 && d->npass != 6) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass must be 1, 3 or 6");
     if (d->bn != 16 && d->bn != 32 && d->bn != 64 && d->bn != 128 && d->bn != 256)
         return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bn must be 16/32/64/128/256");
-    if (d->Nimg <= 0 || d->Hs <= 0 || d->Ws <= 0 || d->Cs <= 0 || (d->Cs & 3) || d->Hg <= 0 || d->Wg <= 0 || d->TH <= 0 || d->TW <= 0)
+    if (d->Nimg <= 0 || d->Hs <= 0 || d->Ws <= 0 || !chan_ok(d->Cs) || d->Hg <= 0 || d->Wg <= 0 || d->TH <= 0 || d->TW <= 0)
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad source shape");
     if (d->kpad <= 0 || (d->kpad & 31) || d->kpad < d->TH * d->TW * d->Cs)
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: kpad %d does not cover %d taps x %d channels", d->kpad, d->TH * d->TW, d->Cs);
-    if (d->Cs > 16 && (d->Cs & 15)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: Cs must be < 16 or a multiple of 16");
     if (d->classes < 1 || d->classes > 4 || d->w_rows <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad class count");
     if (d->Ncols <= 0 || (d->Ncols & 3) || d->Cd < d->Ncols || (d->Cd & 3)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad output columns");
-    if (!al16(d->src) || !al16(d->dst) || !al16(d->w) || (d->src_plane & 3) || (d->dst_plane & 3) || (d->w_plane & 3))
+    if (!al16(d->src) || !al16(d->dst) || !al16(d->w) || (d->src_plane & 7) || (d->dst_plane & 7) || (d->w_plane & 7))
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: pointers / plane offsets must be 16-byte aligned");
-    if (d->npass == 3 && (d->src_plane == 0 || d->w_plane == 0)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: npass 3 needs lo planes");
-    if (d->out_mode < 0 || d->out_mode > 2) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bad out_mode");
+    if (d->npass > 1 && (d->src_plane <= 0 || d->w_plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: npass %d needs %d operand planes", d->npass, npl_for(d->npass));
+    if (d->out_mode != 0 && d->out_mode != 2) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bad out_mode");
+    if (d->out_mode == 0 && (d->dst_npl < 1 || d->dst_npl > 3 || (d->dst_npl > 1 && d->dst_plane <= 0)))
+        return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad destination plane layout");
+    if (d->aux && (d->aux_npl < 1 || d->aux_npl > 3 || (d->aux_npl > 1 && d->aux_plane <= 0) || !al16(d->aux)))
+        return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad aux plane layout");
     if (d->cta_pair && d->bn != 128 && d->bn != 256) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: cta_pair needs bn 128 or 256");
+    if (d->npass == 6 && d->bn == 256 && !d->cta_pair) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass 6 with bn 256 needs cta_pair");
     const long long M = static_cast<long long>(d->Nimg) * d->Hg * d->Wg;
     if (M > 2000000000ll) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: too many rows");
     mg::ConvGemmParams p;
     memset(&p, 0, sizeof(p));
     p.src = d->src; p.src_plane = d->src_plane; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
     p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.TH = d->TH; p.TW = d->TW;
-    p.M = static_cast<int>(M); p.ksteps = d->kpad / 16;
-    p.dst = d->dst; p.dst_plane = d->dst_plane; p.Hd = d->Hd; p.Wd = d->Wd; p.Cd = d->Cd; p.osy = d->osy; p.osx = d->osx;
+    p.M = static_cast<int>(M); p.ksteps = d->kpad / 32;
+    p.dst = d->dst; p.dst_plane = d->dst_plane; p.dst_npl = d->dst_npl; p.Hd = d->Hd; p.Wd = d->Wd; p.Cd = d->Cd; p.osy = d->osy; p.osx = d->osx;
     p.Ncols = d->Ncols; p.alpha_k = d->alpha_k; p.sigma = d->sigma; p.bias = d->bias; p.act = d->act;
-    p.aux = d->aux; p.aux_mode = d->aux_mode;
+    p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_mode = d->aux_mode;
     p.aux_wrap_at = d->aux_wrap_at > 0 ? d->aux_wrap_at : (1ll << 62); p.aux_wrap_len = d->aux_wrap_len;
     p.colsum = d->colsum; p.colsumsq = d->colsumsq; p.colsum_rows = d->colsum_rows > 0 ? d->colsum_rows : (1ll << 62);
     p.out_mode = d->out_mode; p.err = nullptr;
@@ -162,13 +184,13 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream) {
     if (!d || !d->plain || !d->g || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: null pointer");
     if (d->npass != 1 && d->npass != 3) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: npass must be 1 or 3");
-    if (d->bn != 32 && d->bn != 64 && d->bn != 128) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: bn must be 32/64/128");
-    if (d->P <= 0 || d->Cp <= 0 || (d->Cp & 3) || d->Cs <= 0 || (d->Cs & 3) || d->splits <= 0)
+    if (d->bn != 64 && d->bn != 128) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: bn must be 64/128");
+    if (d->P <= 0 || d->Cp <= 0 || (d->Cp & 7) || d->Cs <= 0 || (d->Cs & 7) || d->splits <= 0)
         return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: bad shape");
     if (d->P != static_cast<long long>(d->Nimg) * d->Hg * d->Wg) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: P != Nimg*Hg*Wg");
-    if (!al16(d->plain) || !al16(d->g) || !al16(d->out) || (d->plain_plane & 3) || (d->g_plane & 3))
+    if (!al16(d->plain) || !al16(d->g) || !al16(d->out) || (d->plain_plane & 7) || (d->g_plane & 7))
         return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: pointers / plane offsets must be 16-byte aligned");
-    if (d->npass == 3 && (d->plain_plane == 0 || d->g_plane == 0)) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: npass 3 needs lo planes");
+    if (d->npass == 3 && (d->plain_plane <= 0 || d->g_plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: npass 3 needs two operand planes");
     mg::WgradParams p;
     memset(&p, 0, sizeof(p));
     p.g = d->g; p.g_plane = d->g_plane; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
@@ -200,10 +222,11 @@ int mmdgan_scale_by_sigma(float* g, const float* sigma, float act_k, long long n
     if (!g || !sigma) return fail(MMDGAN_EINVAL, "mmdgan_scale_by_sigma: null pointer");
     return wrap(mg::l_scale_by_sigma(g, sigma, act_k, n, S(stream)), "mmdgan_scale_by_sigma");
 }
-int mmdgan_sn_normalize(const float* v, long long n, float eps, float* sigma_out, float* out, long long out_plane, void* stream) {
+int mmdgan_sn_normalize(const float* v, long long n, float eps, float* sigma_out, mmdgan_bf16* out, long long out_plane, int npl,
+                        void* stream) {
     if (!v || !out) return fail(MMDGAN_EINVAL, "mmdgan_sn_normalize: null pointer");
-    if (n <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_sn_normalize: empty vector");
-    return wrap(mg::l_sn_normalize(v, n, eps, sigma_out, out, out_plane, S(stream)), "mmdgan_sn_normalize");
+    if (n <= 0 || npl < 1 || npl > 3 || (npl > 1 && out_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_sn_normalize: bad shape");
+    return wrap(mg::l_sn_normalize(v, n, eps, sigma_out, out, out_plane, npl, S(stream)), "mmdgan_sn_normalize");
 }
 int mmdgan_reduce_tiles(const float* partials, int T, int C, float scale, float* out, void* stream) {
     if (!partials || !out) return fail(MMDGAN_EINVAL, "mmdgan_reduce_tiles: null pointer");
@@ -214,6 +237,11 @@ int mmdgan_colsum_small(const float* x, int rows, int C, float* out, void* strea
     if (!x || !out) return fail(MMDGAN_EINVAL, "mmdgan_colsum_small: null pointer");
     return wrap(mg::l_colsum_small(x, rows, C, out, S(stream)), "mmdgan_colsum_small");
 }
+int mmdgan_colsum_planes(const mmdgan_bf16* x, long long plane, int npl, int rows, int C, float* out, void* stream) {
+    if (!x || !out) return fail(MMDGAN_EINVAL, "mmdgan_colsum_planes: null pointer");
+    if (rows <= 0 || C <= 0 || npl < 1 || npl > 3 || (npl > 1 && plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_colsum_planes: bad shape");
+    return wrap(mg::l_colsum_planes(x, plane, npl, rows, C, out, S(stream)), "mmdgan_colsum_planes");
+}
 int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                        float* invstd, float* moving_mean, float* moving_var, void* stream) {
     if (!psum || !psq || !mean || !invstd) return fail(MMDGAN_EINVAL, "mmdgan_bn_finalize: null pointer");
@@ -221,10 +249,11 @@ int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long l
     return wrap(mg::l_bn_finalize(psum, psq, T, C, rows, eps, momentum, mean, invstd, moving_mean, moving_var, S(stream)), "mmdgan_bn_finalize");
 }
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
-                    long long total, int act, float* out, long long out_plane, void* stream) {
+                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, void* stream) {
     if (!z || !mean || !invstd || !gamma || !beta || !out) return fail(MMDGAN_EINVAL, "mmdgan_bn_apply: null pointer");
-    if (C <= 0 || (C & 3) || total <= 0 || total % C) return fail(MMDGAN_ESHAPE, "mmdgan_bn_apply: bad shape");
-    return wrap(mg::l_bn_apply(z, mean, invstd, gamma, beta, C, total, act, out, out_plane, S(stream)), "mmdgan_bn_apply");
+    if (C <= 0 || (C & 3) || total <= 0 || total % C || npl < 1 || npl > 3 || (npl > 1 && out_plane < total))
+        return fail(MMDGAN_ESHAPE, "mmdgan_bn_apply: bad shape");
+    return wrap(mg::l_bn_apply(z, mean, invstd, gamma, beta, C, total, act, out, out_plane, npl, S(stream)), "mmdgan_bn_apply");
 }
 int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int C, long long rows, int rows_per_block, int act, float* psum, float* psumx,
@@ -234,11 +263,11 @@ int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, con
     return wrap(mg::l_bn_bwd_reduce(da, z, mean, invstd, gamma, beta, C, rows, rows_per_block, act, psum, psumx, S(stream)), "mmdgan_bn_bwd_reduce");
 }
 int mmdgan_bn_bwd_apply(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
-                        const float* beta, const float* dbeta, const float* dgamma, int C, long long rows, int act, float* out,
-                        long long out_plane, void* stream) {
+                        const float* beta, const float* dbeta, const float* dgamma, int C, long long rows, int act,
+                        mmdgan_bf16* out, long long out_plane, int npl, void* stream) {
     if (!da || !z || !mean || !invstd || !gamma || !beta || !dbeta || !dgamma || !out) return fail(MMDGAN_EINVAL, "mmdgan_bn_bwd_apply: null pointer");
-    if (C <= 0 || rows <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_bn_bwd_apply: bad shape");
-    return wrap(mg::l_bn_bwd_apply(da, z, mean, invstd, gamma, beta, dbeta, dgamma, C, rows, act, out, out_plane, S(stream)), "mmdgan_bn_bwd_apply");
+    if (C <= 0 || rows <= 0 || npl < 1 || npl > 3 || (npl > 1 && out_plane < rows * C)) return fail(MMDGAN_ESHAPE, "mmdgan_bn_bwd_apply: bad shape");
+    return wrap(mg::l_bn_bwd_apply(da, z, mean, invstd, gamma, beta, dbeta, dgamma, C, rows, act, out, out_plane, npl, S(stream)), "mmdgan_bn_bwd_apply");
 }
 
 int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, float w1) {
@@ -311,12 +340,13 @@ int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long m
     static_assert(sizeof(mmdgan_refresh_job) == sizeof(mg::RefreshJob), "job layout");
     return wrap(mg::l_refresh(reinterpret_cast<const mg::RefreshJob*>(jobs_device), njobs, max_elems, S(stream)), "mmdgan_refresh");
 }
-int mmdgan_dense_small_fwd(const float* a, int rows, int K, const float* wt, int kpad, int N, float alpha_k, const float* sigma,
-                           const float* bias, float* out, int ldo, void* stream) {
+int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int rows, int K, const mmdgan_bf16* wt, long long w_plane,
+                           int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream) {
     if (!a || !wt || !out) return fail(MMDGAN_EINVAL, "mmdgan_dense_small_fwd: null pointer");
     if (rows <= 0 || K <= 0 || (K & 3) || kpad < K || (kpad & 3) || ldo < N) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad shape");
-    if (N != 4 && N != 8 && N != 16 && N != 32) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: N must be 4/8/16/32");
-    return wrap(mg::l_dense_small_fwd(a, rows, K, wt, kpad, N, alpha_k, sigma, bias, out, ldo, S(stream)), "mmdgan_dense_small_fwd");
+    if (npl < 1 || npl > 3 || (npl > 1 && (a_plane <= 0 || w_plane <= 0))) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad plane layout");
+    if (N != 8 && N != 16 && N != 32) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: N must be 8/16/32");
+    return wrap(mg::l_dense_small_fwd(a, a_plane, npl, rows, K, wt, w_plane, kpad, N, alpha_k, sigma, bias, out, ldo, S(stream)), "mmdgan_dense_small_fwd");
 }
 
 int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float beta1, float beta2, float eps,

@@ -2,13 +2,16 @@
 //
 //   D[m][n] = epilogue( alpha * sum_k A[m][k] * Bw[n][k] )
 //
-// A (activations, NHWC, hi/lo planes) is gathered tap by tap into 128-byte-swizzled K-major shared-memory tiles by
-// four producer warps with 16-byte cp.async (zero fill implements SAME padding and tile tails); Bw (weights, K-major
-// [rows][Kpad]) is staged by TMA; one elected thread issues tcgen05.mma kind::tf32 with the accumulator in TMEM.
-// With NPASS == 3 every k-block is multiplied three times (x*w + x_lo*w + x*w_lo) which recovers fp32-grade products
-// from the tf32 pipe (parity mode); NPASS == 1 is the plain tf32 speed mode.  The producer warps turn into the
-// epilogue: TMEM -> registers -> shared staging -> coalesced float4 stores with bias / activation / activation
-// derivative / tf32 hi-lo split and per-tile column sums (bias gradients, batch-norm statistics) fused in.
+// A (activations, NHWC, bf16 planes) is staged tap by tap into 64-byte-swizzled K-major shared-memory tiles -- by TMA as
+// one 4-D box per (channel chunk, tap) when a tile is a whole number of image rows, else by four producer warps with
+// 16-byte cp.async (zero fill implements SAME padding and tile tails); Bw (weights, K-major [rows][Kpad] bf16 planes)
+// is staged by TMA; one elected thread issues tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM).
+// An fp32 value is carried as up to three bf16 planes x = p0 + p1 + p2 (tc_common.cuh).  NPASS == 6 multiplies the plane
+// pairs {00, 01, 10, 02, 20, 11}: fp32-grade products (forward passes, whose errors the MMD loss amplifies);
+// NPASS == 3 multiplies {00, 01, 10}: ~2^-17 products (input gradients, linear in the operand); NPASS == 1 is the
+// plain bf16 speed mode.  The producer warps turn into the epilogue: TMEM -> registers -> shared staging -> coalesced
+// stores with bias / activation / activation derivative / bf16 plane split and per-tile column sums (bias gradients,
+// batch-norm statistics) fused in.
 //
 // Replaces the tf.matmul / tf.nn.conv2d / tf.nn.conv2d_transpose call sites of the reference
 // (GeneralTools/layer_func.py:909-928) and their gradients (DeepLearning/my_sngan.py:301-304).
@@ -21,8 +24,8 @@ namespace mg {
 
 static constexpr int kBM = 128;
 static constexpr int kPipeBudget = 96;  // KB of pipeline stages per CTA (two CTAs per SM)
-static constexpr int kBK = 16;         // fp32 elements of K per pipeline stage
-static constexpr int kRowBytes = 64;   // 16 fp32 = one 64-byte swizzle row (SWIZZLE_64B): 32 KB stages, two CTAs per SM
+static constexpr int kBK = 32;         // bf16 elements of K per pipeline stage
+static constexpr int kRowBytes = 64;   // 32 bf16 = one 64-byte swizzle row (SWIZZLE_64B)
 static constexpr int kProducerThreads = 128;
 static constexpr int kThreads = 192;
 static constexpr unsigned long long kWatchdogNs = 4000000000ull;
@@ -50,7 +53,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, uns
 // a half (BN = 256) and each SM's tensor core reads only half of B from its own shared memory.
 template <int BN, int NPASS, bool PAIR>
 struct GemmCfg {
-    static constexpr int NPL = (NPASS == 3) ? 2 : 1;
+    static constexpr int NPL = (NPASS == 6) ? 3 : ((NPASS == 3) ? 2 : 1);   // operand planes staged per k-block
     static constexpr int BROWS = PAIR ? BN / 2 : BN;      // weight rows staged by this CTA
     static constexpr int A_BYTES = kBM * kRowBytes;       // per plane
     static constexpr int B_BYTES = BROWS * kRowBytes;
@@ -87,23 +90,24 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
         "r"(rank)
         : "memory");
 }
-// TMA load into THIS CTA's shared memory whose completion bytes are credited to the mbarrier of cluster CTA 0
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+// TMA loads into THIS CTA's shared memory whose completion bytes are credited to the mbarrier of cluster CTA 0
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "{\n\t.reg .b32 rb;\n\t"
         "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [rb];\n\t}" ::"r"(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [rb];\n\t}" ::"r"(
             dst_smem),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                 int c4) {
     asm volatile(
         "{\n\t.reg .b32 rb;\n\t"
         "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [rb];\n\t}" ::"r"(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [rb];\n\t}" ::"r"(
             dst_smem),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
@@ -113,11 +117,11 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t nco
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -142,13 +146,12 @@ __device__ __forceinline__ float act_grad_from_output(float a, int mode) {
     return 1.f;
 }
 
-// ATMA = true: the gathered operand is staged by TMA as well -- one 4-D box {16 channels, W, rows, images} per
+// ATMA = true: the gathered operand is staged by TMA as well -- one 4-D box {32 channels, W, rows, images} per
 // (channel chunk, tap) lands exactly the 128 K-major rows of the tile, with out-of-bounds zero fill as SAME padding and
 // the traversal stride as the convolution stride.  Used whenever a 128-row tile is a whole number of image rows;
 // otherwise the four producer warps gather with cp.async (ATMA = false).
 template <int BN, int NPASS, bool PAIR, bool ATMA>
-__device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CUtensorMap& tmB1, const CUtensorMap& tmA0,
-                                               const CUtensorMap& tmA1, const ConvGemmParams& p) {
+__device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CUtensorMap& tmA0, const ConvGemmParams& p) {
     using Cfg = GemmCfg<BN, NPASS, PAIR>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
@@ -180,11 +183,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmB0);
-        if (NPL == 2) tma_prefetch_desc(&tmB1);
-        if (ATMA) {
-            tma_prefetch_desc(&tmA0);
-            if (NPL == 2) tma_prefetch_desc(&tmA1);
-        }
+        if (ATMA) tma_prefetch_desc(&tmA0);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], ATMA ? 1 : (PAIR ? kProducerThreads : kProducerThreads + 1));
             mbar_init(&empty_bar[s], 1);
@@ -241,10 +240,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 ib[i] = 0;
             }
         }
-        // K order: (channel chunk of CW = min(Cs, 16), tap, channel within chunk) -- taps innermost, so consecutive
-        // k-steps re-read neighbouring pixels of the SAME 64-byte channel chunk and hit L1
-        const int cw4 = (p.Cs >= 16 ? 16 : p.Cs) >> 2;   // 16-byte units per (chunk, tap) group
-        const int ncc = p.Cs / (cw4 * 4);
+        // K order: (channel chunk of CW = min(Cs, 32), tap, channel within chunk) -- taps innermost, so consecutive
+        // k-steps re-read neighbouring pixels of the SAME 64-byte channel chunk
+        const int cw4 = (p.Cs >= kBK ? kBK : p.Cs) >> 3;   // 16-byte units (8 bf16) per (chunk, tap) group
+        const int ncc = p.Cs / (cw4 * 8);
         const int ntaps = p.TH * p.TW;
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
@@ -264,11 +263,11 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 const int yy = by[i] + a;
                 const int xx = bx[i] + b;
                 const bool ok = tap_ok && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
-                const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 4) : 0;
+                const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 8) : 0;
                 const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 32 * i) * kRowBytes);
                 if (p.debug & 1) continue;
-                cp_async16(dsta, p.src + off, ok ? 16u : 0u);
-                if (NPL == 2) cp_async16(dsta + Cfg::A_BYTES, p.src + p.src_plane + off, ok ? 16u : 0u);
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) cp_async16(dsta + pl * Cfg::A_BYTES, p.src + pl * p.src_plane + off, ok ? 16u : 0u);
             }
             // asynchronous publication: the stage's full barrier gets this thread's arrival when its copies land, so the
             // producers run ahead by as many stages as there are free slots and the MMA warp never waits on this loop
@@ -297,20 +296,13 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                     // both CTAs load their operand shares; all bytes are credited to the leader's barrier
                     uint64_t* bar = ATMA ? &full_bar[s] : &bfull_bar[s];
                     if (rank == 0) mbar_arrive_expect_tx(bar, 2 * (NPL * Cfg::B_BYTES + a_bytes));
-                    tma_load_2d_pair(smem_u32(stage_b(s, 0)), &tmB0, bar, j * kBK, row0);
-                    if (NPL == 2) tma_load_2d_pair(smem_u32(stage_b(s, 1)), &tmB1, bar, j * kBK, row0);
-                    if (ATMA) {
-                        tma_load_4d_pair(smem_u32(stage_a(s, 0)), &tmA0, bar, cch, cx, cy, n0);
-                        if (NPL == 2) tma_load_4d_pair(smem_u32(stage_a(s, 1)), &tmA1, bar, cch, cx, cy, n0);
-                    }
+                    // the planes are the outermost tensor-map dimension: one box brings all NPL planes of the stage
+                    tma_load_3d_pair(smem_u32(stage_b(s, 0)), &tmB0, bar, j * kBK, row0, 0);
+                    if (ATMA) tma_load_5d_pair(smem_u32(stage_a(s, 0)), &tmA0, bar, cch, cx, cy, n0, 0);
                 } else {
                     mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES + a_bytes);
-                    tma_load_2d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0);
-                    if (NPL == 2) tma_load_2d(smem_u32(stage_b(s, 1)), &tmB1, &full_bar[s], j * kBK, row0);
-                    if (ATMA) {
-                        tma_load_4d(smem_u32(stage_a(s, 0)), &tmA0, &full_bar[s], cch, cx, cy, n0);
-                        if (NPL == 2) tma_load_4d(smem_u32(stage_a(s, 1)), &tmA1, &full_bar[s], cch, cx, cy, n0);
-                    }
+                    tma_load_3d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0, 0);
+                    if (ATMA) tma_load_5d(smem_u32(stage_a(s, 0)), &tmA0, &full_bar[s], cch, cx, cy, n0, 0);
                 }
                 if (++tap == ntaps) { tap = 0; ++cc; }      // K order: (channel chunk, tap)
             }
@@ -331,7 +323,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
       }
     } else {
         // ======================= MMA issuer (pair: the leader CTA issues for both) =======================
-        constexpr uint32_t idesc = idesc_tf32(PAIR ? 2 * kBM : kBM, BN, 0, 0);
+        constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * kBM : kBM, BN, 0, 0);
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
@@ -346,18 +338,19 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
 #pragma unroll
                 for (int pass = 0; pass < NPASS; ++pass) {
                     if ((p.debug & 2) && (j > 0 || pass > 0)) break;
-                    const int pa = (pass == 1) ? 1 : 0;
-                    const int pb = (pass == 2) ? 1 : 0;
+                    // plane pairs (a, b) in the order {00, 01, 10, 02, 20, 11}: NPASS 1 / 3 / 6 take a prefix
+                    const int pa = (pass == 2 || pass == 5) ? 1 : (pass == 4 ? 2 : 0);
+                    const int pb = (pass == 1 || pass == 5) ? 1 : (pass == 3 ? 2 : 0);
                     const uint32_t abase = smem_u32(stage_a(s, pa));
                     const uint32_t bbase = smem_u32(stage_b(s, pb));
 #pragma unroll
-                    for (int kk = 0; kk < kBK / 8; ++kk) {
-                        // K-major, SWIZZLE_64B (layout type 4): 8-row groups are 512 bytes apart; +32 bytes per K=8 slice
+                    for (int kk = 0; kk < kBK / 16; ++kk) {
+                        // K-major, SWIZZLE_64B (layout type 4): 8-row groups are 512 bytes apart; +32 bytes per K=16 slice
                         const uint64_t ad = smem_desc(abase + kk * 32, 16, 512, 4u);
                         const uint64_t bd = smem_desc(bbase + kk * 32, 16, 512, 4u);
                         const uint32_t acc = (j > 0 || pass > 0 || kk > 0) ? 1u : 0u;
-                        if (PAIR) umma_tf32_pair(tmem_base, ad, bd, idesc, acc);
-                        else umma_tf32(tmem_base, ad, bd, idesc, acc);
+                        if (PAIR) umma_bf16_pair(tmem_base, ad, bd, idesc, acc);
+                        else umma_bf16(tmem_base, ad, bd, idesc, acc);
                     }
                 }
                 if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
@@ -440,19 +433,17 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 v.w = apply_act(fmaf(v.w, alpha, bias4.w), p.act);
                 if (p.aux) {
                     const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
-                    const float4 a4 = *reinterpret_cast<const float4*>(p.aux + arow * p.Cd + col);
+                    // lrelu' / relu' need the sign only (plane 0 carries it); tanh' needs the value (all planes)
+                    const float4 a4 = load_planes4(p.aux, p.aux_plane, p.aux_mode == 3 ? p.aux_npl : 1, arow * p.Cd + col);
                     v.x *= act_grad_from_output(a4.x, p.aux_mode);
                     v.y *= act_grad_from_output(a4.y, p.aux_mode);
                     v.z *= act_grad_from_output(a4.z, p.aux_mode);
                     v.w *= act_grad_from_output(a4.w, p.aux_mode);
                 }
-                if (p.out_mode == 1) {
-                    v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
-                }
-                float* o = p.dst + prow * p.Cd + col;
-                *reinterpret_cast<float4*>(o) = v;
                 if (p.out_mode == 0)
-                    *reinterpret_cast<float4*>(o + p.dst_plane) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                    store_planes4(static_cast<bf16_t*>(p.dst) + prow * p.Cd + col, p.dst_plane, p.dst_npl, v);
+                else
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + prow * p.Cd + col) = v;
                 if (prow < p.colsum_rows) {
                     cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
                     cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
@@ -490,18 +481,16 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
 
 template <int BN, int NPASS, bool ATMA>
 __global__ void __launch_bounds__(kThreads, 2)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ ConvGemmParams p) {
-    conv_gemm_body<BN, NPASS, false, ATMA>(tmB0, tmB1, tmA0, tmA1, p);
+    conv_gemm_body<BN, NPASS, false, ATMA>(tmB0, tmA0, p);
 }
 
 template <int BN, int NPASS, bool ATMA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 2)
-conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                      const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmA0,
                       const __grid_constant__ ConvGemmParams p) {
-    conv_gemm_body<BN, NPASS, true, ATMA>(tmB0, tmB1, tmA0, tmA1, p);
+    conv_gemm_body<BN, NPASS, true, ATMA>(tmB0, tmA0, p);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -520,33 +509,37 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2D fp32 tensor map [rows][cols] (cols contiguous), box {box_cols, box_rows}, zero OOB fill
-// swizzle: 0 = 128B (16-byte chunks), 1 = 128B with 32-byte chunks (MN-major tf32 operands), 2 = 64B
-int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_cols,
-                 int box_rows, int swizzle) {
+// bf16 plane tensor map [planes][rows][cols] (cols contiguous): dims {cols, rows, planes}, box {box_cols, box_rows,
+// box_planes}, zero OOB fill.  swizzle: 0 = 128B, 2 = 64B
+int make_tmap_planes(CUtensorMap* m, const uint16_t* base, long long rows, long long cols, long long row_stride_elems,
+                     long long plane_stride_elems, int planes, int box_cols, int box_rows, int box_planes, int swizzle) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_stride_elems) * 4};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-    cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapSwizzle sw = swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-                                               : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride_elems) * 2, static_cast<cuuint64_t>(plane_stride_elems > 0 ? plane_stride_elems : rows * row_stride_elems) * 2};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_planes)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-// 4-D fp32 tensor map over an NHWC activation plane: dims {C, W, H, N}; box {16, bw, bh, bn} with traversal strides
-// {1, sx, sy, 1} (the box loads ceil(b/s) elements per strided dimension), 64-byte swizzle, zero OOB fill
-static int make_tmap_act(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh, int bn, int sx, int sy) {
+// 5-D bf16 tensor map over NHWC activation planes: dims {C, W, H, N, planes}; box {32, bw, bh, bn, npl} with traversal
+// strides {1, sx, sy, 1, 1} (the box loads ceil(b/s) elements per strided dimension), 64-byte swizzle, zero OOB fill
+static int make_tmap_act(CUtensorMap* m, const uint16_t* base, long long plane_stride_elems, int npl, int C, int W, int H, int N, int bw,
+                         int bh, int bn, int sx, int sy) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4, static_cast<cuuint64_t>(H) * W * C * 4};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn)};
-    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N),
+                          static_cast<cuuint64_t>(npl)};
+    const cuuint64_t img = static_cast<cuuint64_t>(H) * W * C * 2;
+    cuuint64_t strides[4] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, img,
+                             npl > 1 ? static_cast<cuuint64_t>(plane_stride_elems) * 2 : img * N};
+    cuuint32_t box[5] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn),
+                         static_cast<cuuint32_t>(npl)};
+    cuuint32_t estr[5] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
@@ -554,7 +547,7 @@ static int make_tmap_act(CUtensorMap* m, const float* base, int C, int W, int H,
 
 // a 128-row tile is `hb` whole image rows of `nb` images: the gathered operand can be one TMA box per (chunk, tap)
 static bool atma_geometry(const ConvGemmParams& p, int* hb, int* nb) {
-    if (p.Cs % kBK != 0 || p.Wg <= 0 || kBM % p.Wg != 0) return false;
+    if (p.Cs % kBK != 0 || p.Wg <= 0 || kBM % p.Wg != 0) return false;   // whole 32-channel chunks, whole image rows
     int rows = kBM / p.Wg;
     if (rows <= p.Hg) {
         if (p.Hg % rows != 0) return false;
@@ -568,18 +561,15 @@ static bool atma_geometry(const ConvGemmParams& p, int* hb, int* nb) {
 }
 
 template <int BN, int NPASS, bool PAIR, bool ATMA>
-static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes, int hb,
+static int launch_cfg(const ConvGemmParams& p, const uint16_t* w, long long w_plane, long long w_rows, int kpad, int classes, int hb,
                       int nb, cudaStream_t st) {
     using Cfg = GemmCfg<BN, NPASS, PAIR>;
-    CUtensorMap t0, t1, a0, a1;
-    if (make_tmap_2d(&t0, w, w_rows, kpad, kpad, kBK, Cfg::BROWS, 2)) return -4;
-    if (make_tmap_2d(&t1, w + (NPASS == 3 ? w_plane : 0), w_rows, kpad, kpad, kBK, Cfg::BROWS, 2)) return -4;
+    CUtensorMap t0, a0;
+    if (make_tmap_planes(&t0, w, w_rows, kpad, kpad, w_plane, Cfg::NPL, kBK, Cfg::BROWS, Cfg::NPL, 2)) return -4;
     if (ATMA) {
-        if (make_tmap_act(&a0, p.src, p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy)) return -4;
-        if (make_tmap_act(&a1, p.src + (NPASS == 3 ? p.src_plane : 0), p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy))
-            return -4;
+        if (make_tmap_act(&a0, p.src, p.src_plane, Cfg::NPL, p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy)) return -4;
     } else {
-        a0 = t0; a1 = t1;
+        a0 = t0;
     }
     static bool attr_done = false;
     if (!attr_done) {
@@ -594,13 +584,13 @@ static int launch_cfg(const ConvGemmParams& p, const float* w, long long w_plane
     q.tiles_n = (p.Ncols + BN - 1) / BN;
     q.classes = classes;
     dim3 grid(static_cast<unsigned>(q.tiles_m) * q.tiles_n * classes, 1, 1);
-    if (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, q);
-    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, a0, a1, q);
+    if (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
+    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 // w: [planes][w_rows][kpad]; w_rows = classes * rows_per_class (rows_per_class a multiple of the N tile)
-int launch_conv_gemm(const ConvGemmParams& p, const float* w, long long w_plane, long long w_rows, int kpad, int classes,
+int launch_conv_gemm(const ConvGemmParams& p, const uint16_t* w, long long w_plane, long long w_rows, int kpad, int classes,
                      int bn, int npass, int pair, cudaStream_t st) {
     int hb = 0, nb = 0;
     static int no_atma = -1;
@@ -614,9 +604,10 @@ int launch_conv_gemm(const ConvGemmParams& p, const float* w, long long w_plane,
     if (bn == B && npass == N && pair) \
         return atma ? launch_cfg<B, N, true, true>(p, w, w_plane, w_rows, kpad, classes, hb, nb, st) \
                     : launch_cfg<B, N, true, false>(p, w, w_plane, w_rows, kpad, classes, hb, nb, st);
+    MG_CASE(16, 6) MG_CASE(32, 6) MG_CASE(64, 6) MG_CASE(128, 6)
     MG_CASE(16, 3) MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3) MG_CASE(256, 3)
     MG_CASE(16, 1) MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1) MG_CASE(256, 1)
-    MG_PAIR(128, 3) MG_PAIR(256, 3) MG_PAIR(128, 1) MG_PAIR(256, 1)
+    MG_PAIR(128, 6) MG_PAIR(256, 6) MG_PAIR(128, 3) MG_PAIR(256, 3) MG_PAIR(128, 1) MG_PAIR(256, 1)
 #undef MG_CASE
 #undef MG_PAIR
     return -1;

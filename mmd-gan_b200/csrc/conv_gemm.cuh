@@ -15,29 +15,33 @@ struct GemmClass {
 
 // D[m][n] = act(alpha * sum_k A[m][k] * Bw[n][k] + bias[n]) (* act'(aux[m][n])),  m = (img, y, x) on an Hg x Wg grid,
 // k = (tap, channel); A is gathered from an NHWC activation, Bw is a K-major weight matrix read by TMA.
+// Operands are bf16 planes (tc_common.cuh); the result is written as bf16 planes or as raw fp32.
 struct ConvGemmParams {
-    const float* src;      // [planes][Nimg*Hs*Ws][Cs]
-    long long src_plane;   // elements between the hi and lo plane
-    int Nimg, Hs, Ws, Cs;  // Cs multiple of 4
+    const uint16_t* src;   // [planes][Nimg*Hs*Ws][Cs] bf16
+    long long src_plane;   // elements between consecutive planes
+    int Nimg, Hs, Ws, Cs;  // Cs in {8, 16} or a multiple of 32
     int Hg, Wg, sy, sx, TH, TW;
     int M;       // Nimg*Hg*Wg
     int ksteps;  // padded K / 32
-    float* dst;  // [planes][Nimg*Hd*Wd][Cd]
+    void* dst;   // out_mode 0: bf16 planes [dst_npl][Nimg*Hd*Wd][Cd]; out_mode 2: fp32 [Nimg*Hd*Wd][Cd]
     long long dst_plane;
+    int dst_npl;
     int Hd, Wd, Cd, osy, osx;
     int Ncols;               // valid output columns (multiple of 4)
     float alpha_k;           // alpha = sigma ? alpha_k / *sigma : alpha_k
     const float* sigma;
     const float* bias;       // [Ncols] or null
     int act;                 // 0 linear, 1 lrelu(0.1), 2 relu, 3 tanh
-    const float* aux;        // [rows][Cd] activation whose derivative multiplies the result, or null
-    int aux_mode;            // 1 lrelu', 2 relu', 3 tanh' (all evaluated from the layer OUTPUT)
+    const uint16_t* aux;     // bf16 planes [aux_npl][rows][Cd]: activation whose derivative multiplies the result, or null
+    long long aux_plane;
+    int aux_npl;
+    int aux_mode;            // 1 lrelu', 2 relu' (sign of plane 0), 3 tanh' (all planes; evaluated from the layer OUTPUT)
     long long aux_wrap_at;   // destination rows >= aux_wrap_at read aux at row - aux_wrap_len
     long long aux_wrap_len;
     float* colsum;           // [gridDim.x*gridDim.z][Ncols] per-tile column sums of the written values, or null
     float* colsumsq;         // same for squares, or null
     long long colsum_rows;   // only destination rows < colsum_rows are counted
-    int out_mode;            // 0: raw + lo plane, 1: rn-tf32 single plane, 2: raw single plane
+    int out_mode;            // 0: bf16 planes, 2: raw fp32
     unsigned int* err;       // device error flag (watchdog)
     int tiles_m, tiles_n, classes;   // filled by the launcher: grid decomposition (linear block index)
     int debug;               // profiling experiments only: bit0 = skip the A gather, bit1 = skip the MMAs
@@ -47,13 +51,13 @@ struct ConvGemmParams {
 // W[r][(t, c)] = sum_p P[p][r] * G[g(p, t)][c]:  P plain [pixels][Cp] (TMA, MN-major), G gathered NHWC activation.
 // blockIdx.z = split of the pixel range; every split writes its own partial tile.
 struct WgradParams {
-    const float* g;        // gathered activation [planes][Nimg*Hs*Ws][Cs]
+    const uint16_t* g;     // gathered activation, bf16 planes [planes][Nimg*Hs*Ws][Cs]
     long long g_plane;
     int Nimg, Hs, Ws, Cs;
     int Hg, Wg, sy, sx, TH, TW, oy, ox;   // pixel p = (img, y, x) on the plain operand's Hg x Wg grid
     long long P;           // number of plain pixels = Nimg*Hg*Wg
     long long p_per_split; // pixels per blockIdx.z (multiple of 32)
-    int Cp;                // plain channels (rows of the result)
+    int Cp;                // plain channels (rows of the result), multiple of 8
     int Ncols;             // TH*TW*Cs
     float* out;            // [splits][Cp][Ncols]
     unsigned int* err;
@@ -87,12 +91,14 @@ struct MmdParams {
 // Packed operand: [planes][classes*rows_pad][kpad], element (class, row, col) as documented per mode.
 struct PackParams {
     const float* w;   // canonical
-    float* out;       // packed hi plane
-    long long plane;  // lo plane offset (0: single rn-tf32 plane)
+    uint16_t* out;    // packed bf16 planes
+    long long plane;  // elements between planes
+    int npl;          // planes to write (3: forward operand, 2: input-gradient operand, 1: single-pass mode)
+    int pad0;
     int mode;         // PACK_* enum
     int k;            // spatial kernel size
     int Cin, Cout;    // of the layer op (dense: in / out features)
-    int Cs;           // channels per tap in the packed K index (>= source channels, multiple of 4)
+    int Cs;           // channels per tap in the packed K index (>= source channels; 8, 16 or a multiple of 32)
     int rows_pad, kpad, classes;
     int in_C, in_HW, out_C, out_HW;  // dense only: NCHW-flatten <-> NHWC-flatten permutation of features
 };

@@ -1,4 +1,4 @@
-// HBM-bound helper kernels of the SNGan step: layout changes at the boundary (NCHW <-> NHWC hi/lo planes), weight
+// HBM-bound helper kernels of the SNGan step: layout changes at the boundary (NCHW fp32 <-> NHWC bf16 planes), weight
 // packing into the GEMM operand layouts, batch-norm statistics / apply / backward, reductions of per-tile partial
 // sums (bias gradients, split-K weight gradients), the spectral-norm combine and the fused multi-tensor TF-Adam.
 // All reductions use fixed orders (no floating-point atomics) so a step is bit-reproducible run to run.
@@ -16,9 +16,9 @@ namespace mg {
 static inline int nblocks(long long n, int bs) { return static_cast<int>((n + bs - 1) / bs); }
 
 // ------------------------------------------------------------------------------------------------ layout
-// src NCHW [N][C][H][W] -> dst planes [N][H][W][Cp] (channels >= C zero); lo plane at dst + plane (skipped if 0)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, long long plane, int N, int C, int H,
-                                    int W, int Cp) {
+// src NCHW [N][C][H][W] fp32 -> dst bf16 planes [npl][N][H][W][Cp] (channels >= C zero)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16_t* __restrict__ dst, long long plane, int npl, int N, int C,
+                                    int H, int W, int Cp) {
     const long long total = static_cast<long long>(N) * H * W * Cp;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -29,12 +29,12 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
         const int h = static_cast<int>(r % H);
         const int n = static_cast<int>(r / H);
         const float v = c < C ? src[((static_cast<long long>(n) * C + c) * H + h) * W + w] : 0.f;
-        dst[i] = v;
-        if (plane) dst[i + plane] = tf32_lo(v);
+        store_planes(dst + i, plane, npl, v);
     }
 }
-// src [N][H][W][Cp] (hi plane) -> dst NCHW [N][C][H][W]
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C, int H, int W, int Cp) {
+// src bf16 planes [npl][N][H][W][Cp] -> dst NCHW [N][C][H][W] fp32 (sum of the planes)
+__global__ void nhwc_to_nchw_kernel(const bf16_t* __restrict__ src, long long plane, int npl, float* __restrict__ dst, int N, int C, int H,
+                                    int W, int Cp) {
     const long long total = static_cast<long long>(N) * C * H * W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -44,13 +44,19 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
         r /= H;
         const int c = static_cast<int>(r % C);
         const int n = static_cast<int>(r / C);
-        dst[i] = src[((static_cast<long long>(n) * H + h) * W + w) * Cp + c];
+        dst[i] = load_planes(src, plane, npl, ((static_cast<long long>(n) * H + h) * W + w) * Cp + c);
     }
 }
-__global__ void make_lo_plane_kernel(const float* __restrict__ hi, float* __restrict__ lo, long long n) {
+// fp32 [n] -> bf16 planes [npl][n] (same element order), and back
+__global__ void to_planes_kernel(const float* __restrict__ x, bf16_t* __restrict__ dst, long long plane, int npl, long long n) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
-        lo[i] = tf32_lo(hi[i]);
+        store_planes(dst + i, plane, npl, x[i]);
+}
+__global__ void from_planes_kernel(const bf16_t* __restrict__ src, long long plane, int npl, float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = load_planes(src, plane, npl, i);
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
@@ -70,8 +76,8 @@ __device__ __forceinline__ void pack_one(const PackParams& p, long long i) {
         const long long f = i - cls * per_class;
         const int row = static_cast<int>(f / p.kpad);
         const int col = static_cast<int>(f - static_cast<long long>(row) * p.kpad);
-        // K order of the gather-GEMM: (channel chunk of CW = min(Cs, 16), tap, channel within the chunk)
-        const int cw = p.Cs >= 16 ? 16 : p.Cs;
+        // K order of the gather-GEMM: (channel chunk of CW = min(Cs, 32), tap, channel within the chunk)
+        const int cw = p.Cs >= 32 ? 32 : p.Cs;
         const int ntaps = (p.mode == PACK_CONV_DGRAD_S2 || p.mode == PACK_TC_FWD) ? 4 : ((p.mode >= PACK_DENSE_FWD) ? 1 : p.k * p.k);
         const int grp = col / cw;
         const int cc = grp / ntaps;
@@ -122,12 +128,7 @@ __device__ __forceinline__ void pack_one(const PackParams& p, long long i) {
                 break;
             }
         }
-        if (p.plane) {
-            p.out[i] = v;
-            p.out[i + p.plane] = tf32_lo(v);
-        } else {
-            p.out[i] = tf32_rn(v);
-        }
+        store_planes(p.out + i, p.plane, p.npl, v);
     }
 }
 __global__ void pack_weights_kernel(const PackParams p) {
@@ -164,22 +165,23 @@ __global__ void refresh_kernel(const RefreshJob* __restrict__ jobs) {
 }
 
 // out[m][n] = alpha * sum_k A[m][k] * Wt[n][k] + bias[n] for a handful of output columns (the 16 critic scores):
-// fp32 FFMA, one block per row, float4 loads, warp-shuffle + shared-memory reduction.  The tensor-core tile would be
-// 94 % padding here (N = 16 of 128 lanes x 8192 deep on 4 CTAs).
+// fp32 FFMA on the values reassembled from the bf16 planes, one block per row, warp-shuffle + shared-memory reduction.
+// The tensor-core tile would be 94 % padding here (N = 16 of 128 lanes x 8192 deep on 4 CTAs).
 template <int N>
-__global__ void __launch_bounds__(256) dense_small_fwd_kernel(const float* __restrict__ a, int K, const float* __restrict__ wt, int kpad,
+__global__ void __launch_bounds__(256) dense_small_fwd_kernel(const bf16_t* __restrict__ a, long long a_plane, int npl, int K,
+                                                             const bf16_t* __restrict__ wt, long long w_plane, int kpad,
                                                              float alpha_k, const float* __restrict__ sigma,
                                                              const float* __restrict__ bias, float* __restrict__ out, int ldo) {
     __shared__ float red[8][N];
-    const float* arow = a + static_cast<long long>(blockIdx.x) * K;
+    const long long arow = static_cast<long long>(blockIdx.x) * K;
     float acc[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) acc[n] = 0.f;
     for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
-        const float4 x = *reinterpret_cast<const float4*>(arow + k);
+        const float4 x = load_planes4(a, a_plane, npl, arow + k);
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-            const float4 w = *reinterpret_cast<const float4*>(wt + static_cast<long long>(n) * kpad + k);
+            const float4 w = load_planes4(wt, w_plane, npl, static_cast<long long>(n) * kpad + k);
             acc[n] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[n]))));
         }
     }
@@ -222,6 +224,15 @@ __global__ void colsum_small_kernel(const float* __restrict__ x, int rows, int C
     if (c >= C) return;
     double s = 0.0;
     for (int r = 0; r < rows; ++r) s += static_cast<double>(x[static_cast<long long>(r) * C + c]);
+    out[c] = static_cast<float>(s);
+}
+
+// column sums of a small bf16-plane matrix x[npl][rows][C] (the [B, F] gradient of a dense layer with a per-feature bias)
+__global__ void colsum_planes_kernel(const bf16_t* __restrict__ x, long long plane, int npl, int rows, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += static_cast<double>(load_planes(x, plane, npl, static_cast<long long>(r) * C + c));
     out[c] = static_cast<float>(s);
 }
 
@@ -290,7 +301,7 @@ __global__ void scale_by_sigma_kernel(float* __restrict__ g, const float* __rest
 // ------------------------------------------------------------------------------------------------ spectral norm
 // sigma = ||v||, out planes = v / (sigma + eps); one block (v has at most a few 10^4 elements)
 __global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, float eps, float* __restrict__ sigma_out,
-                                    float* __restrict__ out, long long plane) {
+                                    bf16_t* __restrict__ out, long long plane, int npl) {
     __shared__ double red[1024];
     double s = 0.0;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) s += static_cast<double>(v[i]) * static_cast<double>(v[i]);
@@ -304,9 +315,7 @@ __global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, fl
     if (threadIdx.x == 0 && sigma_out) *sigma_out = nrm;
     const float inv = 1.0f / (nrm + eps);
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        const float y = v[i] * inv;
-        out[i] = y;
-        if (plane) out[i + plane] = tf32_lo(y);
+        store_planes(out + i, plane, npl, v[i] * inv);
     }
 }
 
@@ -341,10 +350,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
         moving_var[c] = moving_var[c] * momentum + static_cast<float>(var_u) * (1.0f - momentum);
     }
 }
-// a = act(gamma * (z - mean) * invstd + beta) -> hi/lo planes; z [rows][C] raw
+// a = act(gamma * (z - mean) * invstd + beta) -> bf16 planes; z [rows][C] raw fp32
 __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int C, long long total, int act,
-                                float* __restrict__ out, long long plane) {
+                                bf16_t* __restrict__ out, long long plane, int npl) {
     for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
         const int c = static_cast<int>(i % C);
@@ -357,8 +366,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
         y.z = fmaf((zv.z - mu.z) * is.z, g.z, b.z);
         y.w = fmaf((zv.w - mu.w) * is.w, g.w, b.w);
         if (act == 2) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-        *reinterpret_cast<float4*>(out + i) = y;
-        if (plane) *reinterpret_cast<float4*>(out + i + plane) = make_float4(tf32_lo(y.x), tf32_lo(y.y), tf32_lo(y.z), tf32_lo(y.w));
+        store_planes4(out + i, plane, npl, y);
     }
 }
 // per-block partial sums of dy and dy*xhat per channel; dy = da * act'(bn output); block handles a row slab
@@ -383,11 +391,11 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ da, const float* 
         psumx[static_cast<long long>(blockIdx.x) * C + c] = sx;
     }
 }
-// dz = gamma * invstd * (dy - mean(dy) - xhat * mean(dy*xhat)) -> hi/lo planes
+// dz = gamma * invstd * (dy - mean(dy) - xhat * mean(dy*xhat)) -> bf16 planes
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ dbeta, const float* __restrict__ dgamma, int C, long long rows, int act,
-                                    float* __restrict__ out, long long plane) {
+                                    bf16_t* __restrict__ out, long long plane, int npl) {
     const long long total = rows * C;
     const float inv_rows = 1.0f / static_cast<float>(rows);
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -398,8 +406,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* _
         float dy = da[i];
         if (act == 2 && fmaf(xh, g, beta[c]) <= 0.f) dy = 0.f;
         const float v = g * is * (dy - dbeta[c] * inv_rows - xh * dgamma[c] * inv_rows);
-        out[i] = v;
-        if (plane) out[i + plane] = tf32_lo(v);
+        store_planes(out + i, plane, npl, v);
     }
 }
 
@@ -438,16 +445,24 @@ static inline int grid_for(long long n) {
 }
 #define MG_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : -4)
 
-int l_nchw_to_nhwc(const float* src, float* dst, long long plane, int N, int C, int H, int W, int Cp, cudaStream_t st) {
-    nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(N) * H * W * Cp), kBS, 0, st>>>(src, dst, plane, N, C, H, W, Cp);
+int l_nchw_to_nhwc(const float* src, bf16_t* dst, long long plane, int npl, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+    nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(N) * H * W * Cp), kBS, 0, st>>>(src, dst, plane, npl, N, C, H, W, Cp);
     return MG_CHECK_LAUNCH();
 }
-int l_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int Cp, cudaStream_t st) {
-    nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * C * H * W), kBS, 0, st>>>(src, dst, N, C, H, W, Cp);
+int l_nhwc_to_nchw(const bf16_t* src, long long plane, int npl, float* dst, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+    nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * C * H * W), kBS, 0, st>>>(src, plane, npl, dst, N, C, H, W, Cp);
     return MG_CHECK_LAUNCH();
 }
-int l_make_lo_plane(const float* hi, float* lo, long long n, cudaStream_t st) {
-    make_lo_plane_kernel<<<grid_for(n), kBS, 0, st>>>(hi, lo, n);
+int l_to_planes(const float* x, bf16_t* dst, long long plane, int npl, long long n, cudaStream_t st) {
+    to_planes_kernel<<<grid_for(n), kBS, 0, st>>>(x, dst, plane, npl, n);
+    return MG_CHECK_LAUNCH();
+}
+int l_from_planes(const bf16_t* src, long long plane, int npl, float* out, long long n, cudaStream_t st) {
+    from_planes_kernel<<<grid_for(n), kBS, 0, st>>>(src, plane, npl, out, n);
+    return MG_CHECK_LAUNCH();
+}
+int l_colsum_planes(const bf16_t* x, long long plane, int npl, int rows, int C, float* out, cudaStream_t st) {
+    colsum_planes_kernel<<<nblocks(C, 128), 128, 0, st>>>(x, plane, npl, rows, C, out);
     return MG_CHECK_LAUNCH();
 }
 int l_pack_weights(const PackParams& p, cudaStream_t st) {
@@ -485,8 +500,8 @@ int l_scale_by_sigma(float* g, const float* sigma, float act_k, long long n, cud
     scale_by_sigma_kernel<<<grid_for(n), kBS, 0, st>>>(g, sigma, act_k, n);
     return MG_CHECK_LAUNCH();
 }
-int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, float* out, long long plane, cudaStream_t st) {
-    sn_normalize_kernel<<<1, 1024, 0, st>>>(v, n, eps, sigma_out, out, plane);
+int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, bf16_t* out, long long plane, int npl, cudaStream_t st) {
+    sn_normalize_kernel<<<1, 1024, 0, st>>>(v, n, eps, sigma_out, out, plane, npl);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
@@ -495,8 +510,8 @@ int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long r
     return MG_CHECK_LAUNCH();
 }
 int l_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C, long long total,
-               int act, float* out, long long plane, cudaStream_t st) {
-    bn_apply_kernel<<<grid_for(total / 4), kBS, 0, st>>>(z, mean, invstd, gamma, beta, C, total, act, out, plane);
+               int act, bf16_t* out, long long plane, int npl, cudaStream_t st) {
+    bn_apply_kernel<<<grid_for(total / 4), kBS, 0, st>>>(z, mean, invstd, gamma, beta, C, total, act, out, plane, npl);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
@@ -506,9 +521,9 @@ int l_bn_bwd_reduce(const float* da, const float* z, const float* mean, const fl
     return MG_CHECK_LAUNCH();
 }
 int l_bn_bwd_apply(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                   const float* dbeta, const float* dgamma, int C, long long rows, int act, float* out, long long plane,
+                   const float* dbeta, const float* dgamma, int C, long long rows, int act, bf16_t* out, long long plane, int npl,
                    cudaStream_t st) {
-    bn_bwd_apply_kernel<<<grid_for(rows * C), kBS, 0, st>>>(da, z, mean, invstd, gamma, beta, dbeta, dgamma, C, rows, act, out, plane);
+    bn_bwd_apply_kernel<<<grid_for(rows * C), kBS, 0, st>>>(da, z, mean, invstd, gamma, beta, dbeta, dgamma, C, rows, act, out, plane, npl);
     return MG_CHECK_LAUNCH();
 }
 int l_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float b1, float b2, float eps, const int* step,
@@ -521,12 +536,11 @@ int l_refresh(const RefreshJob* jobs, int njobs, long long max_elems, cudaStream
     refresh_kernel<<<grid, kBS, 0, st>>>(jobs);
     return MG_CHECK_LAUNCH();
 }
-int l_dense_small_fwd(const float* a, int rows, int K, const float* wt, int kpad, int N, float alpha_k, const float* sigma,
-                      const float* bias, float* out, int ldo, cudaStream_t st) {
-    if (N == 16) dense_small_fwd_kernel<16><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 8) dense_small_fwd_kernel<8><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 4) dense_small_fwd_kernel<4><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 32) dense_small_fwd_kernel<32><<<rows, 256, 0, st>>>(a, K, wt, kpad, alpha_k, sigma, bias, out, ldo);
+int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int rows, int K, const bf16_t* wt, long long w_plane, int kpad, int N,
+                      float alpha_k, const float* sigma, const float* bias, float* out, int ldo, cudaStream_t st) {
+    if (N == 16) dense_small_fwd_kernel<16><<<rows, 256, 0, st>>>(a, a_plane, npl, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 8) dense_small_fwd_kernel<8><<<rows, 256, 0, st>>>(a, a_plane, npl, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 32) dense_small_fwd_kernel<32><<<rows, 256, 0, st>>>(a, a_plane, npl, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
     else return -1;
     return MG_CHECK_LAUNCH();
 }

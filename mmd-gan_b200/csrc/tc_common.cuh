@@ -1,7 +1,9 @@
 // sm_100a primitives shared by the tensor-core kernels: mbarrier, TMA, tcgen05 (alloc / mma / commit / ld),
-// shared-memory matrix descriptors and the tf32 instruction descriptor.  Inline PTX only; no CUTLASS.
+// shared-memory matrix descriptors, the bf16 instruction descriptor and the fp32 -> bf16 plane split.
+// Inline PTX only; no CUTLASS.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -65,23 +67,22 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// ---------------------------------------------------------------- TMA (tiled, 2D)
+// ---------------------------------------------------------------- TMA (tiled; the bf16 planes are the outermost dimension)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
             dst_smem),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
             dst_smem),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 
@@ -99,12 +100,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate; issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs (kind::f16), fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -142,8 +143,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 layout): start address [0,14) in 16-byte units, leading-dim byte offset
 // [16,30), stride-dim byte offset [32,46), version (=1) [46,48), layout type [61,64) (2 = 128-byte swizzle).
-// layout_type: 2 = SWIZZLE_128B (16-byte chunks; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only
-// swizzle the hardware accepts for MN-major tf32 operands).
+// layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B (16-byte chunks XORed with the row index inside the 8-row group).
+// K-major operands: rows of one swizzle span, 8-row groups SBO bytes apart, LBO unused.  MN-major operands
+// (canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in bf16 elements): a 128-byte row holds 64 consecutive
+// M/N elements of one K index, 8 K rows form an atom, atoms are LBO bytes apart along M/N and SBO bytes apart along K.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
@@ -156,24 +159,71 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
 }
-// Instruction descriptor for kind::tf32 with fp32 accumulation: c_format F32 (1) at [4,6), a/b format TF32 (2) at
-// [7,10)/[10,13), a/b major (0 = K-major, 1 = MN-major) at 15/16, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+// Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation: c_format F32 (1) at [4,6), a/b format
+// BF16 (1) at [7,10)/[10,13), a/b major (0 = K-major, 1 = MN-major) at 15/16, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
            (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// ---------------------------------------------------------------- tf32 split
-// x = hi + lo with hi = x truncated to the tf32 mantissa (what the tensor core does to a raw fp32 word) and
-// lo = rn_tf32(x - hi).  Feeding (x, lo) planes to three tf32 MMAs (x*w + lo_x*w + x*lo_w) recovers fp32-grade
-// products (error ~2^-21) from the tf32 pipe.
-__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// ---------------------------------------------------------------- bf16 planes
+// x = p0 + p1 + p2 with p0 = bf16_rn(x), p1 = bf16_rn(x - p0), p2 = bf16_rn(x - p0 - p1): three planes carry 24
+// significand bits (the fp32 value, error <= 2^-25 |x|), two planes 16 bits.  The tensor-core kernels multiply plane
+// pairs: npass 6 = {00, 01, 10, 02, 20, 11} (fp32-grade products, dropped terms <= 2^-24), npass 3 = {00, 01, 10}
+// (error ~2^-17, used where the result is linear in the operand: input and weight gradients), npass 1 = {00}.
+typedef uint16_t bf16_t;   // raw bf16 bits
+
+__device__ __forceinline__ bf16_t f2bf(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf2f(bf16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }
+__device__ __forceinline__ void bf16_split3(float x, bf16_t& p0, bf16_t& p1, bf16_t& p2) {
+    p0 = f2bf(x);
+    const float r1 = x - bf2f(p0);
+    p1 = f2bf(r1);
+    p2 = f2bf(r1 - bf2f(p1));
 }
-__device__ __forceinline__ float tf32_lo(float x) { return tf32_rn(x - tf32_trunc(x)); }
+// store x as `npl` planes at dst[0], dst[plane], dst[2 * plane]
+__device__ __forceinline__ void store_planes(bf16_t* dst, long long plane, int npl, float x) {
+    bf16_t a, b, c;
+    bf16_split3(x, a, b, c);
+    dst[0] = a;
+    if (npl > 1) dst[plane] = b;
+    if (npl > 2) dst[2 * plane] = c;
+}
+// four consecutive elements (8-byte aligned): one 8-byte store per plane
+__device__ __forceinline__ void store_planes4(bf16_t* dst, long long plane, int npl, float4 v) {
+    bf16_t a[4], b[4], c[4];
+    bf16_split3(v.x, a[0], b[0], c[0]);
+    bf16_split3(v.y, a[1], b[1], c[1]);
+    bf16_split3(v.z, a[2], b[2], c[2]);
+    bf16_split3(v.w, a[3], b[3], c[3]);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(a[0] | (static_cast<uint32_t>(a[1]) << 16), a[2] | (static_cast<uint32_t>(a[3]) << 16));
+    if (npl > 1)
+        *reinterpret_cast<uint2*>(dst + plane) = make_uint2(b[0] | (static_cast<uint32_t>(b[1]) << 16), b[2] | (static_cast<uint32_t>(b[3]) << 16));
+    if (npl > 2)
+        *reinterpret_cast<uint2*>(dst + 2 * plane) = make_uint2(c[0] | (static_cast<uint32_t>(c[1]) << 16), c[2] | (static_cast<uint32_t>(c[3]) << 16));
+}
+__device__ __forceinline__ float load_planes(const bf16_t* src, long long plane, int npl, long long i) {
+    float v = bf2f(src[i]);
+    if (npl > 1) v += bf2f(src[i + plane]);
+    if (npl > 2) v += bf2f(src[i + 2 * plane]);
+    return v;
+}
+__device__ __forceinline__ float4 unpack_bf16x4(uint2 u) {
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ float4 load_planes4(const bf16_t* src, long long plane, int npl, long long i) {
+    float4 v = unpack_bf16x4(*reinterpret_cast<const uint2*>(src + i));
+    if (npl > 1) {
+        const float4 m = unpack_bf16x4(*reinterpret_cast<const uint2*>(src + i + plane));
+        v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
+    }
+    if (npl > 2) {
+        const float4 l = unpack_bf16x4(*reinterpret_cast<const uint2*>(src + i + 2 * plane));
+        v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+    }
+    return v;
+}
 
 }  // namespace mg

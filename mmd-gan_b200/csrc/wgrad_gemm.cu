@@ -2,11 +2,14 @@
 //
 //   W[r][(t, c)] = sum_p P[p][r] * G[g(p, t)][c]
 //
-// P is a plain [pixels][Cp] activation / gradient matrix, G an NHWC activation gathered tap by tap.  With NHWC
-// storage the contracted dimension (pixels) is the strided one, so BOTH operands are MN-major: P tiles are staged by
-// TMA (32 pixels x 32 channels boxes, 128-byte swizzle), G tiles by 16-byte cp.async with the same swizzle, and the
-// tcgen05.mma instruction descriptor carries the two transpose bits.  NPASS == 3 is the fp32-grade tf32x3 mode.
-// Every split writes its own partial tile; the reduction over splits is fused into the gradient-finalise kernel.
+// P is a plain [pixels][Cp] activation / gradient matrix, G an NHWC activation gathered tap by tap, both as bf16 planes.
+// With NHWC storage the contracted dimension (pixels) is the strided one, so BOTH operands are MN-major: a shared-
+// memory "chunk" is 32 pixel rows x 128 bytes (64 consecutive channels of one pixel per row, 128-byte swizzle); P
+// chunks are staged by TMA (one box {64 channels, 32 pixels, planes} per chunk), G chunks by 16-byte cp.async with the
+// same swizzle, and the tcgen05.mma instruction descriptor carries the two transpose bits.  NPASS == 3 multiplies the
+// plane pairs {00, 01, 10} (weight gradients are linear in both operands: ~2^-17 products suffice), NPASS == 1 is the
+// plain bf16 mode.  Every split writes its own fp32 partial tile; the reduction over splits is fused into the
+// gradient-finalise kernel.
 //
 // Replaces the filter gradients TF derives for tf.nn.conv2d / conv2d_transpose / matmul
 // (DeepLearning/my_sngan.py:301-304) and the d(sigma)/dW term of SpectralNorm (GeneralTools/math_func.py:661-672).
@@ -16,11 +19,11 @@
 
 namespace mg {
 
-int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long row_stride_elems, int box_cols,
-                 int box_rows, int swizzle);
+int make_tmap_planes(CUtensorMap* m, const uint16_t* base, long long rows, long long cols, long long row_stride_elems,
+                     long long plane_stride_elems, int planes, int box_cols, int box_rows, int box_planes, int swizzle);
 
 static constexpr int kWBM = 128;
-static constexpr int kWPix = 16;   // pixels (K) per pipeline stage: 32 KB stages at BN = 128, two CTAs per SM
+static constexpr int kWPix = 32;   // pixels (K) per pipeline stage: 32 KB stages at BN = 128 / two planes, two CTAs per SM
 static constexpr int kWProducers = 128;
 static constexpr int kWThreads = 192;
 static constexpr unsigned long long kWWatchdogNs = 4000000000ull;
@@ -46,10 +49,13 @@ __device__ __forceinline__ void w_mbar_wait(uint64_t* bar, uint32_t parity, unsi
 template <int BN, int NPASS>
 struct WgradCfg {
     static constexpr int NPL = (NPASS == 3) ? 2 : 1;
-    static constexpr int CHUNK_BYTES = kWPix * 128;             // one 32-channel chunk: kWPix pixels x 128 B
-    static constexpr int A_BYTES = 4 * CHUNK_BYTES;             // 4 channel chunks (M = 128)
-    static constexpr int B_BYTES = (BN / 32) * CHUNK_BYTES;     // BN/32 column chunks
-    static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+    static constexpr int CHUNK_BYTES = kWPix * 128;             // one 64-channel chunk of one plane: kWPix pixels x 128 B
+    static constexpr int MCH = kWBM / 64;                       // row chunks (M = 128)
+    static constexpr int NCH = BN / 64;                         // column chunks
+    // stage layout: [A chunk][plane] then [B chunk][plane]; the planes of one chunk are adjacent (one TMA box)
+    static constexpr int A_BYTES = MCH * NPL * CHUNK_BYTES;
+    static constexpr int B_BYTES = NCH * NPL * CHUNK_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;   // two CTAs per SM
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
     static constexpr int LAG = STAGES - 1 > 3 ? 3 : STAGES - 1;
@@ -60,12 +66,12 @@ struct WgradCfg {
 
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(kWThreads, 2)
-wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
-                  const __grid_constant__ WgradParams p) {
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ WgradParams p) {
     using Cfg = WgradCfg<BN, NPASS>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr int NCH = BN / 32;
+    constexpr int NCH = Cfg::NCH;
+    constexpr int MCH = Cfg::MCH;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,7 +92,6 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmP0);
-        if (NPL == 2) tma_prefetch_desc(&tmP1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], kWProducers + 1);
             mbar_init(&empty_bar[s], 1);
@@ -103,17 +108,18 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    auto stage_a = [&](int s, int pl) -> uint8_t* { return smem + s * Cfg::STAGE_BYTES + pl * Cfg::A_BYTES; };
-    auto stage_b = [&](int s, int pl) -> uint8_t* {
-        return smem + s * Cfg::STAGE_BYTES + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+    // chunk c, plane pl of the A / B operand of stage s
+    auto stage_a = [&](int s, int c, int pl) -> uint8_t* { return smem + s * Cfg::STAGE_BYTES + (c * NPL + pl) * Cfg::CHUNK_BYTES; };
+    auto stage_b = [&](int s, int c, int pl) -> uint8_t* {
+        return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + (c * NPL + pl) * Cfg::CHUNK_BYTES;
     };
 
     if (warp < 4) {
         // ======================= G producers (gather, MN-major) =======================
         const int t = threadIdx.x;
-        const int chunk = t & 7;
-        const int rbase = t >> 3;  // pixel row rbase (0..15) of the k-step
-        const int upt = p.Cs >> 2;
+        const int chunk = t & 7;   // 16-byte unit (8 channels) inside the 128-byte row
+        const int rbase = t >> 3;  // pixel rows rbase + 16*i of the k-step
+        const int upt = p.Cs >> 3; // 16-byte units per tap
         const int ntaps = p.TH * p.TW;
         int ta[NCH], tb[NCH], tcq[NCH];
         bool tok[NCH];
@@ -131,7 +137,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
             w_mbar_wait(&empty_bar[s], ph ^ 1, p.err, 11);
-            const uint32_t b0 = smem_u32(stage_b(s, 0));
+            const uint32_t b0 = smem_u32(stage_b(s, 0, 0));
 #pragma unroll
             for (int i = 0; i < kWPix / 16; ++i) {
                 const int r = rbase + 16 * i;
@@ -146,17 +152,18 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                 }
                 const int by = y * p.sy + p.oy;
                 const int bx = x * p.sx + p.ox;
-                // 32-byte-chunk swizzle: chunk pair index (chunk >> 1) ^ (row & 3), the 16-byte half keeps its place
-                const uint32_t drow = b0 + static_cast<uint32_t>(r * 128 + ((((chunk >> 1) ^ (r & 3)) << 1 | (chunk & 1)) << 4));
+                // SWIZZLE_128B: 16-byte unit index ^= row index inside the 8-row atom
+                const uint32_t drow = b0 + static_cast<uint32_t>(r * 128 + ((chunk ^ (r & 7)) << 4));
 #pragma unroll
                 for (int q = 0; q < NCH; ++q) {
                     const int yy = by + ta[q];
                     const int xx = bx + tb[q];
                     const bool ok = pok && tok[q] && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
                     const long long off =
-                        ok ? (static_cast<long long>(n * p.Hs * p.Ws + yy * p.Ws + xx) * p.Cs + tcq[q] * 4) : 0;
-                    cp_async16(drow + q * Cfg::CHUNK_BYTES, p.g + off, ok ? 16u : 0u);
-                    if (NPL == 2) cp_async16(drow + q * Cfg::CHUNK_BYTES + Cfg::B_BYTES, p.g + p.g_plane + off, ok ? 16u : 0u);
+                        ok ? (static_cast<long long>(n * p.Hs * p.Ws + yy * p.Ws + xx) * p.Cs + tcq[q] * 8) : 0;
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl)
+                        cp_async16(drow + (q * NPL + pl) * Cfg::CHUNK_BYTES, p.g + pl * p.g_plane + off, ok ? 16u : 0u);
                 }
             }
             cp_async_mbar_arrive_noinc(&full_bar[s]);   // asynchronous publication, see conv_gemm.cu
@@ -168,19 +175,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 w_mbar_wait(&empty_bar[s], ph ^ 1, p.err, 12);
-                mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::A_BYTES);
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES);
                 const int prow = static_cast<int>(p_begin + static_cast<long long>(j) * kWPix);
 #pragma unroll
-                for (int mc = 0; mc < 4; ++mc) {
-                    tma_load_2d(smem_u32(stage_a(s, 0)) + mc * Cfg::CHUNK_BYTES, &tmP0, &full_bar[s], tile_m * kWBM + mc * 32, prow);
-                    if (NPL == 2)
-                        tma_load_2d(smem_u32(stage_a(s, 1)) + mc * Cfg::CHUNK_BYTES, &tmP1, &full_bar[s], tile_m * kWBM + mc * 32, prow);
-                }
+                for (int mc = 0; mc < MCH; ++mc)   // one box = {64 channels, kWPix pixels, NPL planes}
+                    tma_load_3d(smem_u32(stage_a(s, mc, 0)), &tmP0, &full_bar[s], tile_m * kWBM + mc * 64, prow, 0);
             }
         }
     } else {
         // ======================= MMA issuer =======================
-        constexpr uint32_t idesc = idesc_tf32(kWBM, BN, 1, 1);
+        constexpr uint32_t idesc = idesc_bf16(kWBM, BN, 1, 1);
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
@@ -192,13 +196,15 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                 for (int pass = 0; pass < NPASS; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;
                     const int pb = (pass == 2) ? 1 : 0;
-                    const uint32_t abase = smem_u32(stage_a(s, pa));
-                    const uint32_t bbase = smem_u32(stage_b(s, pb));
+                    const uint32_t abase = smem_u32(stage_a(s, 0, pa));
+                    const uint32_t bbase = smem_u32(stage_b(s, 0, pb));
 #pragma unroll
-                    for (int kg = 0; kg < kWPix / 8; ++kg) {
-                        const uint64_t ad = smem_desc(abase + kg * 1024, Cfg::CHUNK_BYTES, 512, 1u);
-                        const uint64_t bd = smem_desc(bbase + kg * 1024, Cfg::CHUNK_BYTES, 512, 1u);
-                        umma_tf32(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kg > 0) ? 1u : 0u);
+                    for (int kg = 0; kg < kWPix / 16; ++kg) {
+                        // MN-major SWIZZLE_128B: one MMA covers K = 16 pixel rows = two 8-row atoms (SBO = 1024 bytes apart);
+                        // consecutive 64-channel chunks of the same plane are LBO = NPL chunks apart
+                        const uint64_t ad = smem_desc(abase + kg * 2048, NPL * Cfg::CHUNK_BYTES, 1024, 2u);
+                        const uint64_t bd = smem_desc(bbase + kg * 2048, NPL * Cfg::CHUNK_BYTES, 1024, 2u);
+                        umma_bf16(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kg > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -219,7 +225,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
         }
         float v[32];
 #pragma unroll 1
-        for (int cc = 0; cc < NCH; ++cc) {
+        for (int cc = 0; cc < BN / 32; ++cc) {
             if (ksteps > 0) {
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 32, v);
                 tmem_ld_wait();
@@ -247,11 +253,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
 }
 
 template <int BN, int NPASS>
-static int launch_wcfg(const WgradParams& p, const float* plain, long long plain_plane, int splits, cudaStream_t st) {
+static int launch_wcfg(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, cudaStream_t st) {
     using Cfg = WgradCfg<BN, NPASS>;
-    CUtensorMap t0, t1;
-    if (make_tmap_2d(&t0, plain, p.P, p.Cp, p.Cp, 32, kWPix, 1)) return -4;
-    if (make_tmap_2d(&t1, plain + (NPASS == 3 ? plain_plane : 0), p.P, p.Cp, p.Cp, 32, kWPix, 1)) return -4;
+    CUtensorMap t0;
+    if (make_tmap_planes(&t0, plain, p.P, p.Cp, p.Cp, plain_plane, Cfg::NPL, 64, kWPix, Cfg::NPL, 0)) return -4;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(wgrad_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
@@ -260,16 +265,16 @@ static int launch_wcfg(const WgradParams& p, const float* plain, long long plain
         attr_done = true;
     }
     dim3 grid((p.Cp + kWBM - 1) / kWBM, (p.Ncols + BN - 1) / BN, splits);
-    wgrad_gemm_kernel<BN, NPASS><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, t1, p);
+    wgrad_gemm_kernel<BN, NPASS><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
-int launch_wgrad_gemm(const WgradParams& p, const float* plain, long long plain_plane, int splits, int bn, int npass,
+int launch_wgrad_gemm(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, int bn, int npass,
                       cudaStream_t st) {
 #define MG_CASE(B, N) \
     if (bn == B && npass == N) return launch_wcfg<B, N>(p, plain, plain_plane, splits, st);
-    MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3)
-    MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1)
+    MG_CASE(64, 3) MG_CASE(128, 3)
+    MG_CASE(64, 1) MG_CASE(128, 1)
 #undef MG_CASE
     return -1;
 }

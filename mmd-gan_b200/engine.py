@@ -6,9 +6,10 @@ current weights it produces loss_gen / loss_dis, the discriminator gradients of 
 loss_gen (through D), applies both TF-Adam updates simultaneously, updates the batch-norm moving statistics and
 every spectral-norm `in_rand`.
 
-Data layout in HBM (all fp32): activations NHWC as hi/lo planes [2][N*H*W][C] (see include/mmdgan_b200.h);
-parameters, gradients and Adam slots as one flat buffer per net in the reference's canonical variable layouts;
-packed GEMM operands per layer, refreshed after every update.  The generator's last conv writes straight into rows
+Data layout in HBM: GEMM operands (activations, gradients, packed weights) NHWC as bf16 planes [npl][N*H*W][C] whose
+sum is the fp32 value (3 planes for values, 2 for gradients; include/mmdgan_b200.h); pre-batch-norm outputs, scores and
+reductions raw fp32; parameters, gradients and Adam slots fp32 as one flat buffer per net in the reference's canonical
+variable layouts; packed GEMM operands per layer, refreshed after every update.  The generator's last conv writes straight into rows
 [B, 2B) of the discriminator input (no tf.concat copy); the discriminator backward runs on a 3B "virtual batch"
 (rows: dL_D/d s_real, dL_D/d s_gen, dL_G/d s_gen) so that one dgrad chain serves both losses, while the weight
 gradients use the first 2B rows only.
@@ -147,7 +148,7 @@ class NetRuntime(object):
                 if len(shp) == 2:
                     c, hw = L.sn_flat
                     out = torch.empty(shp[1], device=self.device)
-                    K.permute_features(L.sn_x[0].reshape(-1)[:shp[1]].contiguous(), out, shp[1], c, hw, inverse=True)
+                    K.permute_features(K.planes_value(L.sn_x).reshape(-1)[:shp[1]].contiguous(), out, shp[1], c, hw, inverse=True)
                     return out.reshape(shp)
                 return K.planes_to_nchw(L.sn_x, 1, shp[1], shp[2], shp[3])
         raise KeyError(name)
@@ -164,13 +165,11 @@ class NetRuntime(object):
                 shp = L.ly.sn_x_shape
                 if len(shp) == 2:
                     c, hw = L.sn_flat
-                    tmp = torch.empty(shp[1], device=self.device)
+                    tmp = torch.zeros(L.sn_x.shape[1] * L.sn_x.shape[2], device=self.device)
                     K.permute_features(value.reshape(-1), tmp, shp[1], c, hw)
-                    L.sn_x.zero_()
-                    L.sn_x[0].reshape(-1)[:shp[1]].copy_(tmp)
-                    K.make_lo_plane(L.sn_x)
+                    K.to_planes(tmp, L.sn_x)
                 else:
-                    K.nchw_to_planes(value.reshape(shp), L.sn_x, self.npass)
+                    K.nchw_to_planes(value.reshape(shp), L.sn_x)
                 return
         raise KeyError(name)
 
@@ -236,9 +235,10 @@ class NetRuntime(object):
             L.sn_x_is_input = x_is_input
             r_x, c_x = (L.rows_in, L.Cs_in) if x_is_input else (L.rows_out, L.Cs_out)
             r_y, c_y = (L.rows_out, L.Cs_out) if x_is_input else (L.rows_in, L.Cs_in)
-            L.sn_x = K.new_planes(r_x, c_x, npass, dev)
-            L.sn_xnew = K.new_planes(r_x, c_x, npass, dev)
-            L.sn_y = K.new_planes(r_y, c_y, npass, dev)
+            npl = K.mode_planes(npass)
+            L.sn_x = K.new_planes(r_x, c_x, npl, dev)
+            L.sn_xnew = K.new_planes(r_x, c_x, npl, dev)
+            L.sn_y = K.new_planes(r_y, c_y, npl, dev)
             L.sn_v = torch.zeros((1, r_y, c_y), dtype=torch.float32, device=dev)
             L.sn_w = torch.zeros((1, r_x, c_x), dtype=torch.float32, device=dev)
             L.sigma = torch.ones(1, dtype=torch.float32, device=dev)
@@ -280,7 +280,9 @@ class SNGanEngine(object):
         self.device = torch.device(device)
         self.world_size, self.rank, self.pg = world_size, rank, process_group
         self.use_graph = use_graph
-        self.om = 0 if self.npass == 3 else 1      # plane outputs: raw + lo plane, or one rn-tf32 plane
+        if self.npass not in (1, 3):
+            raise ValueError('TENSOR_PASSES must be 3 (parity: bf16x6 forward / bf16x3 gradients) or 1 (single bf16 pass)')
+        self.om = 0                                # GEMM outputs that feed another GEMM are written as bf16 planes
         self.code_size = architecture['code'][0][0]
         self.channels, self.height, self.width = architecture['input'][0]
         self.score_size = architecture['discriminator'][-1]['out']
@@ -320,14 +322,15 @@ class SNGanEngine(object):
     def _alloc_buffers(self):
         B, dev, npass = self.B, self.device, self.npass
         HW = self.height * self.width
-        self.code_planes = K.new_planes(B, K.pad4(self.code_size), npass, dev)
+        nv, ng = K.mode_planes(npass, 'value'), K.mode_planes(npass, 'grad')
+        self.code_planes = K.new_planes(B, K.pad_c(self.code_size), nv, dev)
         # D input: rows [0, B*HW) real, [B*HW, 2B*HW) generated
-        self.x_all = K.new_planes(2 * B * HW, K.pad4(self.channels), npass, dev)
+        self.x_all = K.new_planes(2 * B * HW, K.pad_c(self.channels), nv, dev)
         # generator activations
         for i, L in enumerate(self.G.layers):
             last = i == len(self.G.layers) - 1
-            L.a = self.x_all[:, B * HW:, :] if last else K.new_planes(B * L.rows_out, L.Cs_out, npass, dev)
-            L.dz = K.new_planes(B * L.rows_out, L.Cs_out, npass, dev)
+            L.a = self.x_all[:, B * HW:, :] if last else K.new_planes(B * L.rows_out, L.Cs_out, nv, dev)
+            L.dz = K.new_planes(B * L.rows_out, L.Cs_out, ng, dev)
         # discriminator activations (2B) and gradients (3B virtual batch)
         for i, L in enumerate(self.D.layers):
             last = i == len(self.D.layers) - 1
@@ -335,8 +338,10 @@ class SNGanEngine(object):
                 L.a = torch.zeros((1, 2 * B, L.Cs_out), dtype=torch.float32, device=dev)      # scores, fp32
                 L.raw_out = True
             else:
-                L.a = K.new_planes(2 * B * L.rows_out, L.Cs_out, npass, dev)
-            L.dz = K.new_planes(3 * B * L.rows_out, L.Cs_out, npass, dev)
+                L.a = K.new_planes(2 * B * L.rows_out, L.Cs_out, nv, dev)
+            L.dz = K.new_planes(3 * B * L.rows_out, L.Cs_out, ng, dev)
+            if last:
+                L.dz_f32 = torch.zeros((3 * B, L.Cs_out), dtype=torch.float32, device=dev)    # score gradients from the MMD kernel
         # column-sum workspaces: the dgrad of layer i+1 produces dz of layer i
         for net, nb in ((self.G, B), (self.D, 3 * B)):
             for i, L in enumerate(net.layers[:-1]):
@@ -390,11 +395,11 @@ class SNGanEngine(object):
         if L.sn_x_is_input:
             lop.forward(L.sn_x, 1, L.sn_v, out_mode=2)
             K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
-            lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2)
+            lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2, npass=lop.fwd_npass)
             K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
             lop.wgrad(L.sn_x, L.sn_y, 1, L.sn_parts, L.sn_splits)
         else:
-            lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2)
+            lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2, npass=lop.fwd_npass)    # the adjoint is the FORWARD operator here: sigma = ||F^T x||
             K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
             lop.forward(L.sn_y, 1, L.sn_w, out_mode=2)
             K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
@@ -427,8 +432,8 @@ class SNGanEngine(object):
     # -------------------------------------------------------------------------------------------- step pieces
     def _phase_forward(self):
         B, HW = self.B, self.height * self.width
-        K.nchw_to_planes(self._dev_code, self.code_planes, self.npass)
-        K.nchw_to_planes(self._dev_data, self.x_all[:, :B * HW, :], self.npass)
+        K.nchw_to_planes(self._dev_code, self.code_planes)
+        K.nchw_to_planes(self._dev_data, self.x_all[:, :B * HW, :])
         joins = self._sn_power_iteration(fork=self.sn_fork)
         self._net_forward(self.G, self.code_planes, B)
         main = torch.cuda.current_stream(self.device)
@@ -439,13 +444,13 @@ class SNGanEngine(object):
     def _phase_loss(self):
         B = self.B
         s = self.D.layers[-1].a[0]                      # [2B, d]: rows [0,B) real, [B,2B) generated (my_sngan.py:279)
-        seed = self.D.layers[-1].dz                     # [2, 3B, d]
+        seed = self.D.layers[-1].dz_f32                 # fp32 [3B, d]: dL_D/ds_real, dL_D/ds_gen, dL_G/ds_gen
         if self.world_size > 1:
-            self.mmd(s[B:], s[:B], seed[0, 2 * B:], seed[0, B:2 * B], seed[0, :B], gen_all=self.gen_all, real_all=self.real_all,
+            self.mmd(s[B:], s[:B], seed[2 * B:], seed[B:2 * B], seed[:B], gen_all=self.gen_all, real_all=self.real_all,
                      row0=self.rank * B)
         else:
-            self.mmd(s[B:], s[:B], seed[0, 2 * B:], seed[0, B:2 * B], seed[0, :B])
-        K.make_lo_plane(seed)
+            self.mmd(s[B:], s[:B], seed[2 * B:], seed[B:2 * B], seed[:B])
+        K.to_planes(seed, self.D.layers[-1].dz)         # operand planes of the first input-gradient GEMM
 
     def _bias_grad_from_colsum(self, net, L, ncols_per_row_group):
         """bias gradient of layer L from the per-tile column sums of the dgrad that produced L.dz."""
@@ -471,7 +476,7 @@ class SNGanEngine(object):
         # ================= discriminator: loss_dis -> D variables (rows [0,2B)), loss_gen -> dx_fake (rows [2B,3B))
         last = D.layers[-1]
         if last.has_bias:
-            K.colsum_small(last.dz[0], 2 * B, last.Cs_out, self.tmp_vec)
+            K.colsum_small(last.dz_f32, 2 * B, last.Cs_out, self.tmp_vec)
             c, hw = D._feat_perm(last)
             K.permute_features(self.tmp_vec, D.view(D.g, last.ly.bias_name), last.Cout, c, hw, inverse=True)
         for i in range(len(D.layers) - 1, -1, -1):
@@ -482,7 +487,7 @@ class SNGanEngine(object):
             if i > 0:
                 P = D.layers[i - 1]
                 dzp = self._as_rows(P.dz, 3 * B * L.rows_in, L.Cs_in)
-                aux = self._as_rows(P.a, 2 * B * L.rows_in, L.Cs_in)[0]
+                aux = self._as_rows(P.a, 2 * B * L.rows_in, L.Cs_in)
                 L.lop.dgrad(L.dz, 3 * B, dzp, sigma=sig, alpha_k=L.act_k, aux=aux, aux_mode=P.act_code,
                             aux_wrap=(2 * B * L.rows_in, B * L.rows_in), colsum=P.cs if P.has_bias else None,
                             colsum_rows=2 * B * L.rows_in, out_mode=self.om)
@@ -491,7 +496,7 @@ class SNGanEngine(object):
             else:
                 gl = G.layers[-1]
                 L.lop.dgrad(L.dz[:, 2 * B * L.rows_out:, :], B, gl.dz, sigma=sig, alpha_k=L.act_k,
-                            aux=self.x_all[0, B * HW:, :], aux_mode=gl.act_code, colsum=gl.cs if gl.has_bias else None,
+                            aux=self.x_all[:, B * HW:, :], aux_mode=gl.act_code, colsum=gl.cs if gl.has_bias else None,
                             out_mode=self.om)
                 if gl.has_bias:
                     self._bias_grad_from_colsum(G, gl, L.Cs_in)
@@ -518,14 +523,14 @@ class SNGanEngine(object):
                 K.permute_features(P.dgamma_int, G.view(G.g, P.ly.bn_name('gamma')), P.Cout, c, hw, inverse=True)
             else:
                 dzp = self._as_rows(P.dz, B * L.rows_in, L.Cs_in)
-                aux = self._as_rows(P.a, B * L.rows_in, L.Cs_in)[0] if P.act_code != 0 else None
+                aux = self._as_rows(P.a, B * L.rows_in, L.Cs_in) if P.act_code != 0 else None
                 fused_cs = P.has_bias and P.op != 'd'
                 L.lop.dgrad(L.dz, B, dzp, aux=aux, aux_mode=P.act_code, colsum=P.cs if fused_cs else None, out_mode=self.om)
                 if fused_cs:
                     self._bias_grad_from_colsum(G, P, L.Cs_in)
                 elif P.has_bias:
                     # a dense layer's bias is per FEATURE: sum its [B, F] gradient over the batch only
-                    K.colsum_small(P.dz[0], B, P.Cs_out, self.tmp_vec)
+                    K.colsum_planes(P.dz, B, P.Cs_out, self.tmp_vec)
                     c, hw = G._feat_perm(P)
                     K.permute_features(self.tmp_vec, G.view(G.g, P.ly.bias_name), P.Cout, c, hw, inverse=True)
 
@@ -626,6 +631,6 @@ class SNGanEngine(object):
         """Generated images NCHW for the staged codes, training-mode batch norm (the step's own forward)."""
         B, HW = self.B, self.height * self.width
         self._dev_code.copy_(code_x)
-        K.nchw_to_planes(self._dev_code, self.code_planes, self.npass)
+        K.nchw_to_planes(self._dev_code, self.code_planes)
         self._net_forward(self.G, self.code_planes, B)
         return K.planes_to_nchw(self.x_all[:, B * HW:, :], B, self.channels, self.height, self.width)

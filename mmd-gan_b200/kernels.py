@@ -1,8 +1,9 @@
 """Torch-tensor level wrappers over the C ABI (include/mmdgan_b200.h): device memory and streams come from PyTorch,
 every computation is a kernel of libmmdgan_b200.so.  No fallback: a missing library or a non-CUDA tensor raises.
 
-Activation tensors ("planes") are [npl, rows, C] float32 CUDA tensors, NHWC row order, npl = 2 for the tf32x3
-(fp32-grade) mode and 1 for plain tf32; see the header for the hi/lo plane format.
+GEMM operands ("planes") are [npl, rows, C] bfloat16 CUDA tensors, NHWC row order: an fp32 value is the sum of its
+planes (3 planes = the fp32 value, 2 planes = 16 significand bits; include/mmdgan_b200.h).  Forward launches multiply six
+plane pairs (fp32-grade), input- and weight-gradient launches three.
 """
 import ctypes as C
 import math
@@ -38,8 +39,8 @@ def stream():
 def _ptr(t):
     if t is None:
         return None
-    if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32):
-        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32 tensor, got {} on {}'.format(t.dtype, t.device))
+    if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32, torch.bfloat16):
+        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32/bfloat16 tensor, got {} on {}'.format(t.dtype, t.device))
     if t.dim() == 3:
         # planes [npl, rows, C]: every plane must be a dense [rows, C] block; the plane stride is free (row views)
         if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
@@ -50,11 +51,28 @@ def _ptr(t):
 
 
 def plane_stride(t):
-    return t.stride(0) if t.shape[0] == 2 else 0
+    return t.stride(0) if t.shape[0] > 1 else 0
 
 
-def pad4(c):
-    return (c + 3) // 4 * 4
+def _planes(t):
+    if t.dtype != torch.bfloat16 or t.dim() != 3:
+        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected bfloat16 planes [npl, rows, C], got {} {}'.format(t.dtype, tuple(t.shape)))
+    return t
+
+
+def pad_c(c):
+    """Channel padding of a GEMM operand: 8 or 16 (one 16-byte unit or two), else whole 32-channel chunks."""
+    return 8 if c <= 8 else (16 if c <= 16 else (c + 31) // 32 * 32)
+
+
+def fwd_passes(npass):
+    """Engine precision mode (3 = parity, 1 = single bf16 pass) -> plane-pair products of a forward launch."""
+    return 6 if npass == 3 else 1
+
+
+def mode_planes(npass, kind='value'):
+    """Planes allocated for a tensor: values (activations, weights) carry 3, gradients 2; the single-pass mode 1."""
+    return 1 if npass == 1 else (3 if kind == 'value' else 2)
 
 
 def round_up(a, b):
@@ -68,32 +86,45 @@ def pick_bn(ncols, lo=16, hi=128):
     return bn
 
 
-def new_planes(rows, c, npass=3, device='cuda'):
-    return torch.zeros((2 if npass == 3 else 1, rows, c), dtype=torch.float32, device=device)
+def new_planes(rows, c, npl=3, device='cuda'):
+    return torch.zeros((npl, rows, c), dtype=torch.bfloat16, device=device)
 
 
 # ------------------------------------------------------------------------------------------------ layout
-def nchw_to_planes(x, dst, npass=3):
-    """x [N,C,H,W] (or [N,F]) -> dst planes [npl, N*H*W, Cpad]."""
+def nchw_to_planes(x, dst):
+    """x fp32 [N,C,H,W] (or [N,F]) -> dst bf16 planes [npl, N*H*W, Cpad]."""
     if x.dim() == 2:
         n, c = x.shape
         h = w = 1
     else:
         n, c, h, w = x.shape
-    check(lib().mmdgan_nchw_to_nhwc(_ptr(x), _ptr(dst), plane_stride(dst) if npass == 3 else 0, n, c, h, w, dst.shape[2], stream()))
+    _planes(dst)
+    check(lib().mmdgan_nchw_to_nhwc(_ptr(x), _ptr(dst), plane_stride(dst), dst.shape[0], n, c, h, w, dst.shape[2], stream()))
     return dst
 
 
 def planes_to_nchw(src, n, c, h, w):
+    _planes(src)
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
-    check(lib().mmdgan_nhwc_to_nchw(_ptr(src), _ptr(out), n, c, h, w, src.shape[2], stream()))
+    check(lib().mmdgan_nhwc_to_nchw(_ptr(src), plane_stride(src), src.shape[0], _ptr(out), n, c, h, w, src.shape[2], stream()))
     return out
 
 
-def make_lo_plane(t):
-    if t.shape[0] == 2:
-        check(lib().mmdgan_make_lo_plane(_ptr(t[0]), _ptr(t[1]), t[0].numel(), stream()))
-    return t
+def to_planes(x, dst):
+    """fp32 [rows, C] -> bf16 planes [npl, rows, C] (same element order)."""
+    _planes(dst)
+    n = dst.shape[1] * dst.shape[2]
+    assert x.numel() == n and x.dtype == torch.float32
+    check(lib().mmdgan_to_planes(_ptr(x), _ptr(dst), plane_stride(dst), dst.shape[0], n, stream()))
+    return dst
+
+
+def planes_value(src):
+    """bf16 planes [npl, rows, C] -> the fp32 values [rows, C] they carry."""
+    _planes(src)
+    out = torch.empty(src.shape[1:], dtype=torch.float32, device=src.device)
+    check(lib().mmdgan_from_planes(_ptr(src), plane_stride(src), src.shape[0], _ptr(out), out.numel(), stream()))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ linear ops
@@ -108,7 +139,9 @@ class LinearOp(object):
 
     def __init__(self, op, in_shape, out_shape, kernel=3, strides=1, npass=3, in_flat=None, out_flat=None, device='cuda'):
         self.op, self.k, self.s, self.npass, self.device = op, kernel, strides, npass, device
-        self.npl = 2 if npass == 3 else 1
+        self.fwd_npass = fwd_passes(npass)          # forward-type launches (errors amplified by the loss): 6 plane pairs
+        self.bwd_npass = 3 if npass == 3 else 1     # gradient launches (linear in the operands): 3 plane pairs
+        self.npl = mode_planes(npass)               # planes of the packed operands
         if op == 'd':
             self.Cin, self.Cout = in_shape[0], out_shape[0]
             self.Hin = self.Win = self.Hout = self.Wout = 1
@@ -125,7 +158,7 @@ class LinearOp(object):
                 assert self.Hin * strides == self.Hout and self.Win * strides == self.Wout
         else:
             raise AttributeError('layer op {} not supported.'.format(op))
-        self.Cs_in, self.Cs_out = pad4(self.Cin), pad4(self.Cout)
+        self.Cs_in, self.Cs_out = pad_c(self.Cin), pad_c(self.Cout)
         self.pad = 1 if op != 'd' else 0
         k = kernel
         # ---- forward / dgrad operand geometry
@@ -145,7 +178,7 @@ class LinearOp(object):
             g['bn'] = pick_bn(g['ncols'])
             g['rows_pad'] = round_up(g['ncols'], g['bn'])
             g['kpad'] = round_up(g['taps'] * g['Cs'], 32)
-            g['w'] = torch.zeros((self.npl, g['classes'] * g['rows_pad'], g['kpad']), dtype=torch.float32, device=device)
+            g['w'] = torch.zeros((self.npl, g['classes'] * g['rows_pad'], g['kpad']), dtype=torch.bfloat16, device=device)
         # ---- weight-gradient orientation: the small channel count goes to the N side
         if op == 'd':
             self.w_swapped = self.Cs_out < 32
@@ -164,7 +197,7 @@ class LinearOp(object):
         for g in (self.f, self.d):
             d = PackDesc()
             d.w, d.out = _ptr(w_canon), _ptr(g['w'])
-            d.plane = plane_stride(g['w'])
+            d.plane, d.npl = plane_stride(g['w']), g['w'].shape[0]
             d.mode, d.k, d.Cin, d.Cout, d.Cs = g['mode'], self.k, self.Cin, self.Cout, g['Cs']
             d.rows_pad, d.kpad, d.classes = g['rows_pad'], g['kpad'], g['classes']
             if self.op == 'd':
@@ -180,7 +213,7 @@ class LinearOp(object):
         for g in (self.f, self.d):
             d = PackDesc()
             d.w, d.out = _ptr(w_canon), _ptr(g['w'])
-            d.plane = plane_stride(g['w'])
+            d.plane, d.npl = plane_stride(g['w']), g['w'].shape[0]
             d.mode, d.k, d.Cin, d.Cout, d.Cs = g['mode'], self.k, self.Cin, self.Cout, g['Cs']
             d.rows_pad, d.kpad, d.classes = g['rows_pad'], g['kpad'], g['classes']
             if self.op == 'd':
@@ -192,8 +225,9 @@ class LinearOp(object):
 
     # -------------------------------------------------------------------------------------------- GEMM launches
     def _gemm(self, g, src, nimg, dst, geom, sigma, alpha_k, bias, act, aux, aux_mode, aux_wrap, colsum, colsumsq,
-              colsum_rows, out_mode):
+              colsum_rows, out_mode, npass):
         d = GemmDesc()
+        _planes(src)
         d.src, d.src_plane = _ptr(src), plane_stride(src)
         d.Nimg = nimg
         (d.Hs, d.Ws, d.Hg, d.Wg, d.sy, d.sx, d.TH, d.TW, d.Hd, d.Wd, d.osy, d.osx) = geom['dims']
@@ -202,12 +236,17 @@ class LinearOp(object):
         assert src.shape[1] >= nimg * d.Hs * d.Ws
         d.w, d.w_plane, d.w_rows = _ptr(g['w']), plane_stride(g['w']), g['w'].shape[1]
         d.kpad, d.classes = g['kpad'], g['classes']
-        d.dst, d.dst_plane = _ptr(dst), plane_stride(dst)
+        d.dst, d.dst_plane, d.dst_npl = _ptr(dst), plane_stride(dst), dst.shape[0]
+        if (out_mode == 0) != (dst.dtype == torch.bfloat16) or (out_mode == 2 and (dst.dtype != torch.float32 or dst.shape[0] != 1)):
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 writes bf16 planes, out_mode 2 one fp32 plane')
         d.Cd, d.Ncols = dst.shape[2], g['ncols']
         assert dst.shape[1] >= nimg * d.Hd * d.Wd and dst.shape[2] >= g['ncols']
         d.alpha_k = float(alpha_k)
         d.sigma, d.bias, d.act = _ptr(sigma), _ptr(bias), act
-        d.aux, d.aux_mode = _ptr(aux), aux_mode
+        if aux is not None:
+            _planes(aux)
+            d.aux, d.aux_plane, d.aux_npl = _ptr(aux), plane_stride(aux), aux.shape[0]
+        d.aux_mode = aux_mode
         d.aux_wrap_at, d.aux_wrap_len = aux_wrap if aux_wrap else (0, 0)
         d.colsum, d.colsumsq, d.colsum_rows = _ptr(colsum), _ptr(colsumsq), colsum_rows
         bn, pair = g['bn'], 0
@@ -217,16 +256,17 @@ class LinearOp(object):
             # the epilogue per CTA: measured to pay off for plain forward epilogues and for very wide layers only
             pair = 1
             bn = 256 if (g['ncols'] % 256 == 0 and (g['ncols'] >= 512 or aux is None)) else 128
-        elif GEMM_BN_MAX >= 256 and g['ncols'] % 256 == 0:
+        elif GEMM_BN_MAX >= 256 and g['ncols'] % 256 == 0 and npass != 6:
             # 128 x 256 tiles halve the re-reads of the gathered operand, but leave only two pipeline stages per CTA and
             # double the epilogue: measured to pay off only while the grid still fills the 2 x 148 CTA slots
             tiles = m_tiles * (g['ncols'] // 256) * g['classes']
             if tiles >= 190 and (g['ncols'] >= 512 or aux is None):
                 bn = 256
         d.cta_pair = pair
-        d.out_mode, d.bn, d.npass = out_mode, bn, self.npass
-        if out_mode == 0 and dst.shape[0] != 2:
-            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 needs a two-plane destination')
+        d.out_mode, d.bn, d.npass = out_mode, bn, npass
+        need = 3 if npass == 6 else (2 if npass == 3 else 1)
+        if src.shape[0] < need or g['w'].shape[0] < need:
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'npass {} needs {} operand planes'.format(npass, need))
         for i, (oy, ox, ooy, oox) in enumerate(geom['cls']):
             d.cls[i].oy, d.cls[i].ox, d.cls[i].ooy, d.cls[i].oox = oy, ox, ooy, oox
             d.cls[i].wrow = i * g['rows_pad']
@@ -262,18 +302,24 @@ class LinearOp(object):
         return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.d['classes']
 
     def forward(self, src, nimg, dst, sigma=None, alpha_k=1.0, bias=None, act=0, colsum=None, colsumsq=None, out_mode=0):
-        if (self.op == 'd' and self.Cs_out in (4, 8, 16, 32) and out_mode == 2 and act == 0 and colsum is None
-                and dst.shape[0] == 1 and self.npass == 3):
+        if (self.op == 'd' and self.Cs_out in (8, 16, 32) and out_mode == 2 and act == 0 and colsum is None
+                and self.npass == 3):
             # a handful of output columns (the critic scores): fp32 CUDA-core kernel instead of a 94 %-padded MMA tile
-            check(lib().mmdgan_dense_small_fwd(_ptr(src), nimg, self.Cs_in, _ptr(self.f['w']), self.f['kpad'], self.Cs_out,
-                                               float(alpha_k), _ptr(sigma), _ptr(bias), _ptr(dst), dst.shape[2], stream()))
+            _planes(src)
+            npl = min(src.shape[0], self.f['w'].shape[0])
+            check(lib().mmdgan_dense_small_fwd(_ptr(src), plane_stride(src), npl, nimg, self.Cs_in, _ptr(self.f['w']),
+                                               plane_stride(self.f['w']), self.f['kpad'], self.Cs_out, float(alpha_k), _ptr(sigma),
+                                               _ptr(bias), _ptr(dst), dst.shape[2], stream()))
             return
-        self._gemm(self.f, src, nimg, dst, self._fwd_geom(), sigma, alpha_k, bias, act, None, 0, None, colsum, colsumsq, 0, out_mode)
+        self._gemm(self.f, src, nimg, dst, self._fwd_geom(), sigma, alpha_k, bias, act, None, 0, None, colsum, colsumsq, 0, out_mode,
+                   self.fwd_npass)
 
     def dgrad(self, dy, nimg, dst, sigma=None, alpha_k=1.0, aux=None, aux_mode=0, aux_wrap=None, colsum=None, colsum_rows=0,
-              out_mode=0):
+              out_mode=0, npass=None):
+        """Input gradient (npass defaults to the 3-pair gradient mode; the spectral-norm power iteration, which uses the
+        adjoint as a FORWARD operator, passes the 6-pair mode)."""
         self._gemm(self.d, dy, nimg, dst, self._dgrad_geom(), sigma, alpha_k, None, 0, aux, aux_mode, aux_wrap, colsum, None,
-                   colsum_rows, out_mode)
+                   colsum_rows, out_mode, self.bwd_npass if npass is None else npass)
 
     # -------------------------------------------------------------------------------------------- weight gradient
     def wgrad_plan(self, nimg):
@@ -288,7 +334,7 @@ class LinearOp(object):
                 P, R, NC = nimg * self.Hout * self.Wout, self.Cs_out, self.k * self.k * self.Cs_in
         else:
             P, R, NC = nimg * self.Hin * self.Win, self.Cs_in, self.k * self.k * self.Cs_out
-        bn = pick_bn(NC, lo=32)
+        bn = pick_bn(NC, lo=64)
         tiles = ((R + 127) // 128) * ((NC + bn - 1) // bn)
         ksteps = (P + 31) // 32
         splits = max(1, min((296 + tiles - 1) // tiles, max(1, ksteps // 8)))
@@ -313,6 +359,8 @@ class LinearOp(object):
         else:
             plain, gath = x_in, dy
             geo = (self.Hout, self.Wout, self.Hin, self.Win, 2, 2, 4, 4, -1, -1)
+        _planes(plain)
+        _planes(gath)
         d.plain, d.plain_plane, d.P, d.Cp = _ptr(plain), plane_stride(plain), P, R
         assert plain.shape[2] == R and plain.shape[1] >= P
         d.g, d.g_plane = _ptr(gath), plane_stride(gath)
@@ -320,7 +368,7 @@ class LinearOp(object):
         d.Hs, d.Ws, d.Hg, d.Wg, d.sy, d.sx, d.TH, d.TW, d.oy, d.ox = geo
         d.Cs = gath.shape[2]
         assert d.TH * d.TW * d.Cs == NC
-        d.splits, d.out, d.bn, d.npass = splits, _ptr(partials), bn, self.npass
+        d.splits, d.out, d.bn, d.npass = splits, _ptr(partials), bn, self.bwd_npass
         assert partials.numel() >= splits * R * NC
         check(lib().mmdgan_wgrad_gemm(C.byref(d), stream()))
         return splits
@@ -367,6 +415,12 @@ def colsum_small(x, rows, Cc, out):
     check(lib().mmdgan_reduce_tiles(_ptr(x), rows, Cc, 1.0, _ptr(out), stream()))
 
 
+def colsum_planes(x, rows, Cc, out):
+    # column sums of the values carried by bf16 planes [npl, rows, C]
+    _planes(x)
+    check(lib().mmdgan_colsum_planes(_ptr(x), plane_stride(x), x.shape[0], rows, Cc, _ptr(out), stream()))
+
+
 def build_refresh_jobs(pack_descs, permutes, device):
     """Device-resident job table for mmdgan_refresh: pack_descs = [PackDesc], permutes = [(src, dst, n, C, HW)]."""
     n = len(pack_descs) + len(permutes)
@@ -390,7 +444,8 @@ def refresh(blob, njobs, max_elems):
 
 
 def sn_normalize(v, n, out, sigma_out=None, eps=1e-10):
-    check(lib().mmdgan_sn_normalize(_ptr(v), n, float(eps), _ptr(sigma_out), _ptr(out), plane_stride(out), stream()))
+    _planes(out)
+    check(lib().mmdgan_sn_normalize(_ptr(v), n, float(eps), _ptr(sigma_out), _ptr(out), plane_stride(out), out.shape[0], stream()))
 
 
 def sn_grad_combine(g, s, dots, ndots, sigma, act_k, n):
@@ -411,8 +466,9 @@ def bn_finalize(psum, psq, T, Cc, rows, mean, invstd, moving_mean=None, moving_v
 
 
 def bn_apply(z, mean, invstd, gamma, beta, Cc, total, act, out):
+    _planes(out)
     check(lib().mmdgan_bn_apply(_ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), Cc, total, act, _ptr(out),
-                                plane_stride(out), stream()))
+                                plane_stride(out), out.shape[0], stream()))
 
 
 def bn_bwd_reduce(da, z, mean, invstd, gamma, beta, Cc, rows, rows_per_block, act, psum, psumx):
@@ -421,8 +477,9 @@ def bn_bwd_reduce(da, z, mean, invstd, gamma, beta, Cc, rows, rows_per_block, ac
 
 
 def bn_bwd_apply(da, z, mean, invstd, gamma, beta, dbeta, dgamma, Cc, rows, act, out):
+    _planes(out)
     check(lib().mmdgan_bn_bwd_apply(_ptr(da), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(dbeta),
-                                    _ptr(dgamma), Cc, rows, act, _ptr(out), plane_stride(out), stream()))
+                                    _ptr(dgamma), Cc, rows, act, _ptr(out), plane_stride(out), out.shape[0], stream()))
 
 
 def adam(w, m, v, g, n, lr, step, beta1=0.5, beta2=0.999, eps=1e-8):

@@ -3,7 +3,7 @@ sys.path.insert(0, '.')
 import torch.nn.functional as F
 from oracle import net as onet
 from mmdgan_b200 import kernels as K
-from tests.test_gpu_kernels import _spec, rel, CASES
+from tests.test_gpu_kernels import _spec, rel, CASES, raw_to_nchw
 cuda = torch.device('cuda')
 for case in CASES:
   for npass in (3, 1):
@@ -20,12 +20,13 @@ for case in CASES:
     lop = K.LinearOp(op, in_shape, out_shape, k, s, npass=npass)
     wd = w.float().to(cuda).contiguous(); lop.pack(wd)
     hin_, hout_ = (1, 1) if op == 'd' else (in_shape[1], out_shape[1])
-    xs = K.new_planes(n * hin_ * hin_, lop.Cs_in, npass); K.nchw_to_planes(x.float().to(cuda).contiguous(), xs, npass)
-    yr = K.new_planes(n * hout_ * hout_, lop.Cs_out, 1)
+    nv, ng = K.mode_planes(npass, 'value'), K.mode_planes(npass, 'grad')
+    xs = K.new_planes(n * hin_ * hin_, lop.Cs_in, nv); K.nchw_to_planes(x.float().to(cuda).contiguous(), xs)
+    yr = torch.zeros((1, n * hout_ * hout_, lop.Cs_out), device=cuda)
     lop.forward(xs, n, yr, out_mode=2)
-    y2 = K.planes_to_nchw(yr, n, cout, hout_, hout_).reshape(y_ref.shape)
-    dys = K.new_planes(n * hout_ * hout_, lop.Cs_out, npass); K.nchw_to_planes(dy.float().to(cuda).contiguous(), dys, npass)
-    dxs = K.new_planes(n * hin_ * hin_, lop.Cs_in, 3)
+    y2 = raw_to_nchw(yr, n, cout, hout_, hout_).reshape(y_ref.shape)
+    dys = K.new_planes(n * hout_ * hout_, lop.Cs_out, ng); K.nchw_to_planes(dy.float().to(cuda).contiguous(), dys)
+    dxs = K.new_planes(n * hin_ * hin_, lop.Cs_in, 2)
     lop.dgrad(dys, n, dxs, out_mode=0)
     dx = K.planes_to_nchw(dxs, n, cin, hin_, hin_).reshape(dx_ref.shape)
     R, NC, bn, splits, P = lop.wgrad_plan(n)

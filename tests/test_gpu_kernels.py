@@ -1,6 +1,7 @@
 """Per-kernel parity on the GPU: every CUDA kernel, called through the C ABI, against the CPU oracle
-(float64) on the same seeded inputs.  Tolerances: 2e-5 normwise for the fp32-grade tf32x3 tensor-core mode and the
-CUDA-core kernels, 3e-3 for the opt-in plain tf32 mode (north-star parity bar is 1e-3 on the tf32x3 path)."""
+(float64) on the same seeded inputs.  Tolerances: 5e-5 normwise for the parity mode of the tensor-core kernels (bf16
+planes: six plane-pair products forward, three for the gradients) and the CUDA-core kernels, 1e-2 for the opt-in single
+bf16 pass (north-star parity bar is 1e-3 on the parity-mode path)."""
 import numpy as np
 import pytest
 import torch
@@ -12,13 +13,18 @@ from oracle import net as onet
 pytestmark = pytest.mark.gpu
 
 TOL3 = 5e-5
-TOL1 = 3e-3
+TOL1 = 1e-2
 
 
 def rel(a, b):
     a = torch.as_tensor(a).double().cpu()
     b = torch.as_tensor(b).double().cpu()
     return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def raw_to_nchw(t, n, c, h, w):
+    """fp32 NHWC rows [1, n*h*w, Cpad] -> [n, c, h, w]."""
+    return t[0].reshape(n, h, w, -1)[..., :c].permute(0, 3, 1, 2).contiguous()
 
 
 def _spec(op, cin, cout, hin, k, s):
@@ -66,8 +72,9 @@ def test_linear_op_fwd_dgrad_wgrad(cuda, case, npass):
     wd = w.float().to(cuda).contiguous()
     lop.pack(wd)
     hin_, hout_ = (1, 1) if op == 'd' else (in_shape[1], out_shape[1])
-    xs = K.new_planes(n * hin_ * hin_, lop.Cs_in, npass)
-    K.nchw_to_planes(x.float().to(cuda).contiguous(), xs, npass)
+    nv, ng = K.mode_planes(npass, 'value'), K.mode_planes(npass, 'grad')
+    xs = K.new_planes(n * hin_ * hin_, lop.Cs_in, nv)
+    K.nchw_to_planes(x.float().to(cuda).contiguous(), xs)
     # ---- forward with fused alpha, bias, lrelu
     ys = K.new_planes(n * hout_ * hout_, lop.Cs_out, 3)
     bias_d = torch.zeros(lop.Cs_out, device=cuda)
@@ -75,24 +82,24 @@ def test_linear_op_fwd_dgrad_wgrad(cuda, case, npass):
     lop.forward(xs, n, ys, alpha_k=alpha, bias=bias_d, act=1, out_mode=0)
     y = K.planes_to_nchw(ys, n, cout, hout_, hout_).reshape(y_act_ref.shape)
     assert rel(y, y_act_ref) < tol
-    # hi + lo reproduces the value to tf32 x tf32 precision
+    # the planes are a proper split: p1 + p2 is the bf16 rounding residual of p0
     lo = K.planes_to_nchw(ys[1:], n, cout, hout_, hout_).reshape(y_act_ref.shape)
-    assert float(lo.abs().max()) <= float(y.abs().max()) * 2.0 ** -10
+    assert float(lo.abs().max()) <= float(y.abs().max()) * 2.0 ** -8
     # ---- raw forward (out_mode 2) with column sums
     T = lop.fwd_tiles(n)
     cs = torch.zeros(T, lop.Cs_out, device=cuda)
     cq = torch.zeros(T, lop.Cs_out, device=cuda)
-    yr = K.new_planes(n * hout_ * hout_, lop.Cs_out, 1)
+    yr = torch.zeros((1, n * hout_ * hout_, lop.Cs_out), device=cuda)
     lop.forward(xs, n, yr, out_mode=2, colsum=cs, colsumsq=cq)
-    y2 = K.planes_to_nchw(yr, n, cout, hout_, hout_).reshape(y_ref.shape)
+    y2 = raw_to_nchw(yr, n, cout, hout_, hout_).reshape(y_ref.shape)
     assert rel(y2, y_ref.detach()) < tol
     red = [0] if op == 'd' else [0, 2, 3]
     assert rel(cs.sum(0)[:cout], y_ref.detach().sum(red)) < max(tol, 1e-4)
     assert rel(cq.sum(0)[:cout], (y_ref.detach() ** 2).sum(red)) < max(tol, 1e-4)
     # ---- input gradient
-    dys = K.new_planes(n * hout_ * hout_, lop.Cs_out, npass)
-    K.nchw_to_planes(dy.float().to(cuda).contiguous(), dys, npass)
-    dxs = K.new_planes(n * hin_ * hin_, lop.Cs_in, 3)
+    dys = K.new_planes(n * hout_ * hout_, lop.Cs_out, ng)
+    K.nchw_to_planes(dy.float().to(cuda).contiguous(), dys)
+    dxs = K.new_planes(n * hin_ * hin_, lop.Cs_in, 2)
     lop.dgrad(dys, n, dxs, out_mode=0)
     dx = K.planes_to_nchw(dxs, n, cin, hin_, hin_).reshape(dx_ref.shape)
     assert rel(dx, dx_ref) < tol
@@ -134,12 +141,12 @@ def test_dgrad_fused_activation_derivative_and_wrap(cuda):
     lop.pack(w.float().to(cuda).contiguous())
     aps = K.new_planes(2 * b * h * h, cin)
     K.nchw_to_planes(a_prev.float().to(cuda).contiguous(), aps)
-    dys = K.new_planes(3 * b * h * h, cout)
+    dys = K.new_planes(3 * b * h * h, cout, 2)
     K.nchw_to_planes(dy.float().to(cuda).contiguous(), dys)
-    dxs = K.new_planes(3 * b * h * h, cin)
+    dxs = K.new_planes(3 * b * h * h, cin, 2)
     T = lop.dgrad_tiles(3 * b)
     cs = torch.zeros(T, cin, device=cuda)
-    lop.dgrad(dys, 3 * b, dxs, aux=aps[0], aux_mode=1, aux_wrap=(2 * b * h * h, b * h * h), colsum=cs, colsum_rows=2 * b * h * h)
+    lop.dgrad(dys, 3 * b, dxs, aux=aps, aux_mode=1, aux_wrap=(2 * b * h * h, b * h * h), colsum=cs, colsum_rows=2 * b * h * h)
     dx = K.planes_to_nchw(dxs, 3 * b, cin, h, h)
     assert rel(dx, dx_ref) < TOL3
     assert rel(cs.sum(0), dx_ref[:2 * b].sum([0, 2, 3])) < 1e-4
@@ -241,9 +248,10 @@ def test_bn_adam_sn_elementwise(cuda):
     assert rel(mean_d, mean.detach()) < 1e-5
     assert rel(mm, 0.01 * mean.detach()) < 1e-5
     assert rel(mv, 0.99 + 0.01 * var.detach() * rows / (rows - 1)) < 1e-5
-    a = K.new_planes(rows, Cc)
+    a = K.new_planes(rows, Cc, 3)
     K.bn_apply(zd, mean_d, inv_d, gd, bd, Cc, rows * Cc, 2, a)
-    assert rel(a[0], a_ref.detach()) < 1e-5
+    assert rel(K.planes_value(a), a_ref.detach()) < 1e-5
+    assert rel(K.planes_value(a[:2]), a_ref.detach()) < 2e-5      # two planes carry 16 significand bits
     rpb = 32
     nb = (rows + rpb - 1) // rpb
     p1, p2 = torch.zeros(nb, Cc, device=cuda), torch.zeros(nb, Cc, device=cuda)
@@ -252,9 +260,9 @@ def test_bn_adam_sn_elementwise(cuda):
     K.reduce_tiles(p1, nb, Cc, dbeta)
     K.reduce_tiles(p2, nb, Cc, dgamma)
     assert rel(dbeta, db_ref) < 1e-5 and rel(dgamma, dg_ref) < 1e-5
-    dz = K.new_planes(rows, Cc)
+    dz = K.new_planes(rows, Cc, 2)
     K.bn_bwd_apply(dad, zd, mean_d, inv_d, gd, bd, dbeta, dgamma, Cc, rows, 2, dz)
-    assert rel(dz[0], dz_ref) < 2e-5
+    assert rel(K.planes_value(dz), dz_ref) < 2e-5
     # ---- TF-Adam against the oracle's restatement
     n = 1000
     p0, gr0 = torch.randn(n, generator=g), torch.randn(n, generator=g)
@@ -269,7 +277,13 @@ def test_bn_adam_sn_elementwise(cuda):
     assert torch.allclose(w.cpu(), params['p'], rtol=1e-5, atol=1e-7)
     # ---- l2 normalise
     vec = torch.randn(5000, generator=g).to(cuda)
-    out, sig = K.new_planes(1, 5000), torch.zeros(1, device=cuda)
-    K.sn_normalize(vec, 5000, out.view(2, -1), sigma_out=sig)
+    out, sig = K.new_planes(1, 5000, 3), torch.zeros(1, device=cuda)
+    K.sn_normalize(vec, 5000, out, sigma_out=sig)
     assert abs(float(sig) - float(vec.double().norm())) < 1e-5 * float(vec.norm())
-    assert rel(out[0].flatten(), vec / (vec.norm() + 1e-10)) < 1e-6
+    assert rel(K.planes_value(out).flatten(), vec / (vec.norm() + 1e-10)) < 1e-6
+    # ---- fp32 <-> bf16 planes round trip: three planes reproduce the fp32 value to 1 ulp, two planes to 2^-16
+    xf = (torch.randn(4096, generator=g) * torch.logspace(-20, 20, 4096)).to(cuda)
+    pl = K.new_planes(1, 4096, 3)
+    K.to_planes(xf, pl)
+    assert float(((K.planes_value(pl).flatten() - xf).abs() / xf.abs()).max()) <= 2.0 ** -23
+    assert float(((K.planes_value(pl[:2]).flatten() - xf).abs() / xf.abs()).max()) <= 2.0 ** -16

@@ -1,6 +1,7 @@
 """End-to-end parity of the fused SNGan step on the GPU against the CPU oracle (float64) on identical
 inputs / weights / state.  Tolerance: 1e-3 normwise relative (the north-star bar) for losses, scores, every gradient
-tensor, the spectral-norm and batch-norm state; observed errors of the tf32x3 path are ~1e-5."""
+tensor, the spectral-norm and batch-norm state; observed errors of the parity mode (bf16 planes: six plane-pair
+products forward, three for the gradients) are ~1e-5."""
 import numpy as np
 import pytest
 import torch
@@ -41,7 +42,7 @@ def engine_activation(eng, net, L, nimg):
     from mmdgan_b200 import kernels as K
     if L.op == 'd':
         c, hw = L.lop.out_flat
-        return L.a[0].reshape(nimg, hw, L.Cs_out // hw if hw > 1 else L.Cs_out)[:, :, :c].permute(0, 2, 1).reshape(nimg, -1).cpu()
+        return K.planes_value(L.a).reshape(nimg, hw, L.Cs_out // hw if hw > 1 else L.Cs_out)[:, :, :c].permute(0, 2, 1).reshape(nimg, -1).cpu()
     return K.planes_to_nchw(L.a, nimg, L.Cout, L.Hout, L.Wout).cpu()
 
 
@@ -183,9 +184,10 @@ def test_cuda_graph_replay_matches_eager(cuda):
     assert eng_g._graphs is not None and eng_g.kernel_launches_per_step > 0
 
 
-def test_tf32_single_pass_mode_is_close_but_not_parity_grade(cuda):
-    """npass=1 (opt-in speed mode) stays within 1e-1 on gradients (observed ~4e-2); it is NOT the parity configuration."""
+def test_single_bf16_pass_mode_is_close_but_not_parity_grade(cuda):
+    """npass=1 (opt-in speed mode: one bf16 plane, one product) follows the oracle only loosely (bf16 carries 8 significand
+    bits and the MMD loss amplifies score errors); it is NOT the parity configuration."""
     arch = oa.tiny(act_k=2.6)
     B = 16
     orc, eng = make_pair(arch, B, 'rep', npass=1)
-    check_step(orc, eng, arch, B, seed=5, tol=1e-1)
+    check_step(orc, eng, arch, B, seed=5, tol=5e-1)

@@ -77,11 +77,14 @@ def test_linear_op_launch_plans():
     lop = K.LinearOp('c', [64, 32, 32], [128, 16, 16], 4, 2, device='cpu')
     assert lop.d['classes'] == 4 and lop.d['taps'] == 4 and lop.d['kpad'] == 4 * 128
     assert lop._dgrad_geom()['cls'] == [(-1, -1, 0, 0), (-1, 0, 0, 1), (0, -1, 1, 0), (0, 0, 1, 1)]
-    # image layers: 3 channels padded to 4, weight gradient puts the small side on N
+    # image layers: 3 channels padded to 8 (one 16-byte unit of bf16), weight gradient puts the small side on N
     lop = K.LinearOp('c', [64, 32, 32], [3, 32, 32], 3, 1, device='cpu')
-    assert lop.Cs_out == 4 and lop.w_swapped and lop.f['bn'] == 16 and lop.wgrad_plan(8)[:2] == (64, 36)
+    assert lop.Cs_out == 8 and lop.w_swapped and lop.f['bn'] == 16 and lop.wgrad_plan(8)[:3] == (64, 72, 128)
     lop = K.LinearOp('c', [3, 32, 32], [64, 32, 32], 3, 1, device='cpu')
-    assert lop.Cs_in == 4 and not lop.w_swapped and lop.f['kpad'] == 64
+    assert lop.Cs_in == 8 and not lop.w_swapped and lop.f['kpad'] == 96
+    # operand planes: values (forward operands) carry three bf16 planes, six plane-pair products forward, three backward
+    assert lop.f['w'].dtype == torch.bfloat16 and lop.f['w'].shape[0] == 3 and (lop.fwd_npass, lop.bwd_npass) == (6, 3)
+    assert [K.pad_c(c) for c in (1, 3, 8, 9, 16, 17, 32, 33, 64, 100)] == [8, 8, 8, 16, 16, 32, 32, 64, 64, 128]
     # dense with NCHW-flatten permutation folded into the packed weights
     lop = K.LinearOp('d', [8192], [16], in_flat=(512, 16), device='cpu')
     assert lop.w_swapped and lop.in_flat == (512, 16) and lop.d['kpad'] == 32
@@ -129,7 +132,7 @@ def test_product_fails_loudly_without_cuda():
     from mmdgan_b200 import kernels as K
     from mmdgan_b200._lib import MmdganError
     with pytest.raises(MmdganError):
-        K.make_lo_plane(torch.zeros(2, 4, 4))
+        K.planes_value(torch.zeros(2, 4, 8, dtype=torch.bfloat16))
     from mmdgan_b200.GeneralTools.math_func import GANLoss
     with pytest.raises(RuntimeError):
         GANLoss().apply(torch.zeros(4, 16), torch.zeros(4, 16), 'rep', batch_size=4, d=16)
