@@ -148,7 +148,7 @@ typedef struct mmdgan_wgrad_desc {
     int Hg, Wg, sy, sx, TH, TW, oy, ox;
     int splits;
     float* out;
-    int bn, npass;      /* bn 64 or 128; npass 3 or 1 */
+    int bn, npass;      /* bn 64, 128 or 256; npass 3 or 1 */
 } mmdgan_wgrad_desc;
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream);
 

@@ -184,7 +184,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream) {
     if (!d || !d->plain || !d->g || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: null pointer");
     if (d->npass != 1 && d->npass != 3) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: npass must be 1 or 3");
-    if (d->bn != 64 && d->bn != 128) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: bn must be 64/128");
+    if (d->bn != 64 && d->bn != 128 && d->bn != 256) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: bn must be 64/128/256");
     if (d->P <= 0 || d->Cp <= 0 || (d->Cp & 7) || d->Cs <= 0 || (d->Cs & 7) || d->splits <= 0)
         return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: bad shape");
     if (d->P != static_cast<long long>(d->Nimg) * d->Hg * d->Wg) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: P != Nimg*Hg*Wg");

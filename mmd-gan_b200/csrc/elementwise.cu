@@ -228,12 +228,20 @@ __global__ void colsum_small_kernel(const float* __restrict__ x, int rows, int C
 }
 
 // column sums of a small bf16-plane matrix x[npl][rows][C] (the [B, F] gradient of a dense layer with a per-feature bias)
+// block = 32 columns x 32 row slices, double accumulation, fixed order
 __global__ void colsum_planes_kernel(const bf16_t* __restrict__ x, long long plane, int npl, int rows, int C, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ double red[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += static_cast<double>(load_planes(x, plane, npl, static_cast<long long>(r) * C + c));
-    out[c] = static_cast<float>(s);
+    if (c < C)
+        for (int r = threadIdx.y; r < rows; r += 32) s += static_cast<double>(load_planes(x, plane, npl, static_cast<long long>(r) * C + c));
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double a = 0.0;
+        for (int k = 0; k < 32; ++k) a += red[k][threadIdx.x];
+        out[c] = static_cast<float>(a);
+    }
 }
 
 __global__ void wgrad_reduce_kernel(const WredParams p) {
@@ -391,6 +399,51 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ da, const float* 
         psumx[static_cast<long long>(blockIdx.x) * C + c] = sx;
     }
 }
+// same sums, for C <= 1024: a thread owns four consecutive channels (float4 loads) of every (256 / (C/4))-th row of the
+// slab, the row groups are combined through shared memory in a fixed order
+__global__ void __launch_bounds__(256) bn_bwd_reduce_vec_kernel(const float* __restrict__ da, const float* __restrict__ z,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta, int C,
+                                                                long long rows, int rows_per_block, int act, float* __restrict__ psum,
+                                                                float* __restrict__ psumx) {
+    __shared__ float4 rs[256], rx[256];
+    const int cq = C >> 2, ng = 256 / cq;
+    const int c4 = threadIdx.x % cq, rg = threadIdx.x / cq;
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), sx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rg < ng) {
+        const int c = c4 * 4;
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+        for (long long r = r0 + rg; r < r1; r += ng) {
+            const float4 zv = *reinterpret_cast<const float4*>(z + r * C + c);
+            float4 dy = *reinterpret_cast<const float4*>(da + r * C + c);
+            const float4 xh = make_float4((zv.x - mu.x) * is.x, (zv.y - mu.y) * is.y, (zv.z - mu.z) * is.z, (zv.w - mu.w) * is.w);
+            if (act == 2) {
+                if (fmaf(xh.x, g.x, b.x) <= 0.f) dy.x = 0.f;
+                if (fmaf(xh.y, g.y, b.y) <= 0.f) dy.y = 0.f;
+                if (fmaf(xh.z, g.z, b.z) <= 0.f) dy.z = 0.f;
+                if (fmaf(xh.w, g.w, b.w) <= 0.f) dy.w = 0.f;
+            }
+            s.x += dy.x; s.y += dy.y; s.z += dy.z; s.w += dy.w;
+            sx.x = fmaf(dy.x, xh.x, sx.x); sx.y = fmaf(dy.y, xh.y, sx.y); sx.z = fmaf(dy.z, xh.z, sx.z); sx.w = fmaf(dy.w, xh.w, sx.w);
+        }
+    }
+    rs[threadIdx.x] = s;
+    rx[threadIdx.x] = sx;
+    __syncthreads();
+    if (rg == 0) {
+        for (int k = 1; k < ng; ++k) {
+            const float4 a = rs[k * cq + c4], bq = rx[k * cq + c4];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            sx.x += bq.x; sx.y += bq.y; sx.z += bq.z; sx.w += bq.w;
+        }
+        *reinterpret_cast<float4*>(psum + static_cast<long long>(blockIdx.x) * C + c4 * 4) = s;
+        *reinterpret_cast<float4*>(psumx + static_cast<long long>(blockIdx.x) * C + c4 * 4) = sx;
+    }
+}
 // dz = gamma * invstd * (dy - mean(dy) - xhat * mean(dy*xhat)) -> bf16 planes
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -462,7 +515,7 @@ int l_from_planes(const bf16_t* src, long long plane, int npl, float* out, long 
     return MG_CHECK_LAUNCH();
 }
 int l_colsum_planes(const bf16_t* x, long long plane, int npl, int rows, int C, float* out, cudaStream_t st) {
-    colsum_planes_kernel<<<nblocks(C, 128), 128, 0, st>>>(x, plane, npl, rows, C, out);
+    colsum_planes_kernel<<<nblocks(C, 32), dim3(32, 32), 0, st>>>(x, plane, npl, rows, C, out);
     return MG_CHECK_LAUNCH();
 }
 int l_pack_weights(const PackParams& p, cudaStream_t st) {
@@ -517,7 +570,10 @@ int l_bn_apply(const float* z, const float* mean, const float* invstd, const flo
 int l_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                     int C, long long rows, int rows_per_block, int act, float* psum, float* psumx, cudaStream_t st) {
     const int blocks = static_cast<int>((rows + rows_per_block - 1) / rows_per_block);
-    bn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, C, rows, rows_per_block, act, psum, psumx);
+    if ((C & 3) == 0 && C <= 1024 && 256 % (C >> 2) == 0)
+        bn_bwd_reduce_vec_kernel<<<blocks, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, C, rows, rows_per_block, act, psum, psumx);
+    else
+        bn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, C, rows, rows_per_block, act, psum, psumx);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_bwd_apply(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,

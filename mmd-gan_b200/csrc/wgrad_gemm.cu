@@ -273,8 +273,8 @@ int launch_wgrad_gemm(const WgradParams& p, const uint16_t* plain, long long pla
                       cudaStream_t st) {
 #define MG_CASE(B, N) \
     if (bn == B && npass == N) return launch_wcfg<B, N>(p, plain, plain_plane, splits, st);
-    MG_CASE(64, 3) MG_CASE(128, 3)
-    MG_CASE(64, 1) MG_CASE(128, 1)
+    MG_CASE(64, 3) MG_CASE(128, 3) MG_CASE(256, 3)
+    MG_CASE(64, 1) MG_CASE(128, 1) MG_CASE(256, 1)
 #undef MG_CASE
     return -1;
 }

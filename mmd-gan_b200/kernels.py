@@ -7,6 +7,7 @@ plane pairs (fp32-grade), input- and weight-gradient launches three.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -20,6 +21,7 @@ PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRA
 GEMM_PAIR = True        # use the CTA-pair (cta_group::2) gather-GEMM where the grid is large enough
 GEMM_PAIR_MIN_TILES = 256   # 128 x 128 output units; below that the single-CTA kernel fills the machine better
 GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
+WGRAD_BN_MAX = int(os.environ.get('MMDGAN_WGRAD_BN', '256'))   # widest N tile of the weight-gradient GEMM (64 / 128 / 256)
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
 
@@ -334,7 +336,7 @@ class LinearOp(object):
                 P, R, NC = nimg * self.Hout * self.Wout, self.Cs_out, self.k * self.k * self.Cs_in
         else:
             P, R, NC = nimg * self.Hin * self.Win, self.Cs_in, self.k * self.k * self.Cs_out
-        bn = pick_bn(NC, lo=64)
+        bn = pick_bn(NC, lo=64, hi=WGRAD_BN_MAX)
         tiles = ((R + 127) // 128) * ((NC + bn - 1) // bn)
         ksteps = (P + 31) // 32
         splits = max(1, min((296 + tiles - 1) // tiles, max(1, ksteps // 8)))
