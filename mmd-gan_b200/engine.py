@@ -309,7 +309,10 @@ class SNGanEngine(object):
         self._warm = False
         self._stream = torch.cuda.Stream(device=self.device)
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(8)]
+        self._grad_stream = torch.cuda.Stream(device=self.device)   # weight-gradient GEMMs + gradient finalisation
+        self._upd_stream = torch.cuda.Stream(device=self.device)    # the generator's Adam + refresh
         self.sn_fork = True
+        self.grad_fork = True
         # pinned staging for the end-to-end path
         self._pin_data = torch.empty((B, self.channels, self.height, self.width), dtype=torch.float32).pin_memory()
         self._pin_code = torch.empty((B, self.code_size), dtype=torch.float32).pin_memory()
@@ -471,18 +474,40 @@ class SNGanEngine(object):
             lop.wgrad_reduce(L.wg_parts, L.wg_splits, nimg, gview)
 
     def _phase_backward(self):
+        """Input-gradient chain on the main stream; everything that only FINALISES gradients (weight-gradient GEMMs, split-K
+        reductions, the spectral-norm combine, bias / batch-norm parameter reductions) is forked onto one in-order side
+        stream and joined before the optimiser, so the ~100 small launches overlap the GEMM chain instead of serialising it."""
         B, HW = self.B, self.height * self.width
         D, G = self.D, self.G
+        main = torch.cuda.current_stream(self.device)
+        side = self._grad_stream if self.grad_fork else main
+        pending = []          # closures that may run once everything issued so far on the main stream has completed
+
+        def flush():
+            if not pending:
+                return
+            if side is not main:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for fn in pending:
+                    fn()
+            del pending[:]
+
         # ================= discriminator: loss_dis -> D variables (rows [0,2B)), loss_gen -> dx_fake (rows [2B,3B))
         last = D.layers[-1]
         if last.has_bias:
-            K.colsum_small(last.dz_f32, 2 * B, last.Cs_out, self.tmp_vec)
-            c, hw = D._feat_perm(last)
-            K.permute_features(self.tmp_vec, D.view(D.g, last.ly.bias_name), last.Cout, c, hw, inverse=True)
+            def last_bias():
+                K.colsum_small(last.dz_f32, 2 * B, last.Cs_out, self.tmp_vec)
+                c, hw = D._feat_perm(last)
+                K.permute_features(self.tmp_vec, D.view(D.g, last.ly.bias_name), last.Cout, c, hw, inverse=True)
+            pending.append(last_bias)
         for i in range(len(D.layers) - 1, -1, -1):
             L = D.layers[i]
             x_in = D.layers[i - 1].a if i > 0 else self.x_all
-            self._weight_grad(D, L, x_in, L.dz, 2 * B)
+            pending.append(lambda L=L, x_in=x_in: self._weight_grad(D, L, x_in, L.dz, 2 * B))
+            flush()
             sig = L.sigma if L.has_sn else None
             if i > 0:
                 P = D.layers[i - 1]
@@ -492,19 +517,20 @@ class SNGanEngine(object):
                             aux_wrap=(2 * B * L.rows_in, B * L.rows_in), colsum=P.cs if P.has_bias else None,
                             colsum_rows=2 * B * L.rows_in, out_mode=self.om)
                 if P.has_bias:
-                    self._bias_grad_from_colsum(D, P, L.Cs_in)
+                    pending.append(lambda P=P, L=L: self._bias_grad_from_colsum(D, P, L.Cs_in))
             else:
                 gl = G.layers[-1]
                 L.lop.dgrad(L.dz[:, 2 * B * L.rows_out:, :], B, gl.dz, sigma=sig, alpha_k=L.act_k,
                             aux=self.x_all[:, B * HW:, :], aux_mode=gl.act_code, colsum=gl.cs if gl.has_bias else None,
                             out_mode=self.om)
                 if gl.has_bias:
-                    self._bias_grad_from_colsum(G, gl, L.Cs_in)
+                    pending.append(lambda gl=gl, L=L: self._bias_grad_from_colsum(G, gl, L.Cs_in))
         # ================= generator: loss_gen -> G variables
         for i in range(len(G.layers) - 1, -1, -1):
             L = G.layers[i]
             x_in = G.layers[i - 1].a if i > 0 else self.code_planes
-            self._weight_grad(G, L, x_in, L.dz, B)
+            pending.append(lambda L=L, x_in=x_in: self._weight_grad(G, L, x_in, L.dz, B))
+            flush()
             if i == 0:
                 break
             P = G.layers[i - 1]
@@ -518,31 +544,53 @@ class SNGanEngine(object):
                 K.reduce_tiles(P.bp2, P.nblk, P.Cs_out, P.dgamma_int)
                 K.bn_bwd_apply(P.da_raw, P.zraw, P.mean, P.invstd, P.gamma_int, P.beta_int, P.dbeta_int, P.dgamma_int, P.Cs_out,
                                rows, P.act_code, P.dz)
-                c, hw = G._feat_perm(P)
-                K.permute_features(P.dbeta_int, G.view(G.g, P.ly.bn_name('beta')), P.Cout, c, hw, inverse=True)
-                K.permute_features(P.dgamma_int, G.view(G.g, P.ly.bn_name('gamma')), P.Cout, c, hw, inverse=True)
+
+                def bn_params(P=P):
+                    c, hw = G._feat_perm(P)
+                    K.permute_features(P.dbeta_int, G.view(G.g, P.ly.bn_name('beta')), P.Cout, c, hw, inverse=True)
+                    K.permute_features(P.dgamma_int, G.view(G.g, P.ly.bn_name('gamma')), P.Cout, c, hw, inverse=True)
+                pending.append(bn_params)
             else:
                 dzp = self._as_rows(P.dz, B * L.rows_in, L.Cs_in)
                 aux = self._as_rows(P.a, B * L.rows_in, L.Cs_in) if P.act_code != 0 else None
                 fused_cs = P.has_bias and P.op != 'd'
                 L.lop.dgrad(L.dz, B, dzp, aux=aux, aux_mode=P.act_code, colsum=P.cs if fused_cs else None, out_mode=self.om)
                 if fused_cs:
-                    self._bias_grad_from_colsum(G, P, L.Cs_in)
+                    pending.append(lambda P=P, L=L: self._bias_grad_from_colsum(G, P, L.Cs_in))
                 elif P.has_bias:
                     # a dense layer's bias is per FEATURE: sum its [B, F] gradient over the batch only
-                    K.colsum_planes(P.dz, B, P.Cs_out, self.tmp_vec)
-                    c, hw = G._feat_perm(P)
-                    K.permute_features(self.tmp_vec, G.view(G.g, P.ly.bias_name), P.Cout, c, hw, inverse=True)
+                    def dense_bias(P=P):
+                        K.colsum_planes(P.dz, B, P.Cs_out, self.tmp_vec)
+                        c, hw = G._feat_perm(P)
+                        K.permute_features(self.tmp_vec, G.view(G.g, P.ly.bias_name), P.Cout, c, hw, inverse=True)
+                    pending.append(dense_bias)
+        flush()
+        if side is not main:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     def _phase_update(self):
         """Both Adam updates from the same forward pass, then UPDATE_OPS (my_sngan.py:424-426; graph_func.py:848-854)."""
-        for net, lr in ((self.D, self.lr_dis), (self.G, self.lr_gen)):
-            K.incr_step(net.step)
-            K.adam(net.w, net.m, net.v, net.g, net.n_flat, lr, net.step)
-            net.refresh()
-        for L in self.D.layers + self.G.layers:
-            if L.has_sn:
-                L.sn_x.copy_(L.sn_xnew)
+        main = torch.cuda.current_stream(self.device)
+        side = self._upd_stream if self.grad_fork else main
+        if side is not main:                      # the two optimisers touch disjoint buffers: run them concurrently
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+        for net, lr, st in ((self.D, self.lr_dis, main), (self.G, self.lr_gen, side)):
+            with torch.cuda.stream(st):
+                K.incr_step(net.step)
+                K.adam(net.w, net.m, net.v, net.g, net.n_flat, lr, net.step)
+                net.refresh()
+        with torch.cuda.stream(side):
+            for L in self.D.layers + self.G.layers:
+                if L.has_sn:
+                    L.sn_x.copy_(L.sn_xnew)
+        if side is not main:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
         K.nan_flag(self.mmd.losses, 2, self.nan_flag)
 
     # -------------------------------------------------------------------------------------------- collectives

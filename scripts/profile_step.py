@@ -8,7 +8,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else 'cifar'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 npass = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 arch = oa.ARCHITECTURES[name]()
-eng = SNGanEngine(arch, B, loss_type='rep', npass=npass, use_graph=False)
+eng = SNGanEngine(arch, B, loss_type="rep", npass=npass, use_graph=False)
+eng.sn_fork = eng.grad_fork = False   # single stream: every launch timed alone
 g = torch.Generator().manual_seed(0)
 data = (torch.rand(B, *arch['input'][0], generator=g) * 2 - 1).cuda(); code = torch.randn(B, 128, generator=g).cuda()
 recs = []
