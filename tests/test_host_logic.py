@@ -72,7 +72,7 @@ def test_linear_op_launch_plans():
     assert (lop.f['kpad'], lop.f['bn'], lop.f['rows_pad'], lop.f['classes']) == (1152, 128, 128, 1)
     assert lop._fwd_geom()['cls'] == [(-1, -1, 0, 0)] and lop._dgrad_geom()['cls'] == [(-1, -1, 0, 0)]
     R, NC, bn, splits, P = lop.wgrad_plan(512)
-    assert (R, NC, bn, P) == (128, 1152, 128, 512 * 256) and 1 <= splits <= P // 32
+    assert (R, NC, bn, P) == (128, 1152, 256, 512 * 256) and 1 <= splits <= P // 32
     # stride-2 conv: input gradient = four parity classes of 2x2 taps
     lop = K.LinearOp('c', [64, 32, 32], [128, 16, 16], 4, 2, device='cpu')
     assert lop.d['classes'] == 4 and lop.d['taps'] == 4 and lop.d['kpad'] == 4 * 128
