@@ -1,0 +1,78 @@
+"""Error budget of the tensor-core precision modes, measured on the CPU oracle (no GPU needed).
+
+Every GEMM operand (forward) and every gradient (backward) of the oracle's fused step is rounded the way a precision mode
+of the CUDA path rounds it, and the resulting losses / gradients are compared with the float64 oracle:
+  f32      plain fp32 oracle (the floor)
+  tf32x3   x = hi + lo with tf32 hi and lo (round-1's first kernels)
+  bf16x3   two bf16 planes everywhere (3 plane-pair products)
+  mixed    fp32-grade forward operands, two bf16 planes for the gradients  (what the engine ships: bf16x6 fwd / bf16x3 bwd)
+Result (CIFAR net, act_k 2.7, batch 8): the MMD loss amplifies forward (score) errors by 10^2..10^3, so bf16x3 forward
+passes give a median gradient error of 2.5e-3 (fails the 1e-3 bar) while gradient passes are linear and tolerate it:
+mixed = 7.5e-6.  Usage: python scripts/precision_budget.py
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, numpy as np
+from oracle import net as onet, architectures as oa
+torch.set_num_threads(8)
+def split16(x):
+    if x.dtype!=torch.float32: return x
+    hi=x.to(torch.bfloat16).float(); lo=(x-hi).to(torch.bfloat16).float()
+    return hi+lo
+def split_tf32x2(x):
+    if x.dtype!=torch.float32: return x
+    i=x.contiguous().view(torch.int32); hi=(i & ~0x1FFF).view(torch.float32)
+    lo=onet.round_tf32(x-hi); return hi+lo
+class R(torch.autograd.Function):
+    fn=None
+    @staticmethod
+    def forward(ctx,x): return R.fn(x)
+    @staticmethod
+    def backward(ctx,g): return R.fn(g)
+def run(mode, arch, B, seed):
+    if mode=='f64':
+        m=onet.OracleSNGan(arch,'rep',dtype=torch.float64,seed=3); onet._maybe_tf32=lambda x,on: x
+    else:
+        m=onet.OracleSNGan(arch,'rep',dtype=torch.float32,seed=3)
+        if mode=='f32': onet._maybe_tf32=lambda x,on: x
+        else:
+            R.fn={'bf16x3':split16,'tf32x3':split_tf32x2}[mode]
+            onet._maybe_tf32=lambda x,on: R.apply(x)
+    onet.warm_spectral_norm(m,6)
+    data,code=onet.synthetic_batch(arch,B,seed=seed,dtype=m.dtype)
+    lg,ld,gg,gd,_,_=m.grads(data,code)
+    return float(lg),float(ld),{**gg,**gd}
+for name,arch,B in (('tiny',oa.tiny(act_k=2.6),16),('cifar k2.7',oa.cifar(act_k=2.7),8),('cifar k1.68',oa.cifar(),8)):
+    ref=run('f64',arch,B,11)
+    for mode in ('f32','tf32x3','bf16x3'):
+        r=run(mode,arch,B,11)
+        errs=[]
+        gmax=max(float(v.norm()) for k,v in ref[2].items() if k.startswith('dis/'))
+        for k,v in ref[2].items():
+            if float(v.norm())<1e-6*gmax: continue
+            errs.append((float((r[2][k].double()-v).norm()/v.norm()),k))
+        errs.sort(reverse=True)
+        print(name,mode,'loss rel err %.2e %.2e'%(abs(r[0]-ref[0])/abs(ref[0]),abs(r[1]-ref[1])/abs(ref[1])),'worst grad %.2e %s  median %.2e'%(errs[0][0],errs[0][1],errs[len(errs)//2][0]))
+print('--- mixed: forward tf32x3, backward bf16x3')
+class RM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx,x): return split_tf32x2(x)
+    @staticmethod
+    def backward(ctx,g): return split16(g)
+def run_mixed(arch,B,seed):
+    m=onet.OracleSNGan(arch,'rep',dtype=torch.float32,seed=3)
+    onet._maybe_tf32=lambda x,on: RM.apply(x)
+    onet.warm_spectral_norm(m,6)
+    data,code=onet.synthetic_batch(arch,B,seed=seed,dtype=m.dtype)
+    lg,ld,gg,gd,_,_=m.grads(data,code)
+    return float(lg),float(ld),{**gg,**gd}
+for name,arch,B in (('tiny',oa.tiny(act_k=2.6),16),('cifar k2.7',oa.cifar(act_k=2.7),8)):
+    ref=run('f64',arch,B,11)
+    r=run_mixed(arch,B,11)
+    errs=[]
+    gmax=max(float(v.norm()) for k,v in ref[2].items() if k.startswith('dis/'))
+    for k,v in ref[2].items():
+        if float(v.norm())<1e-6*gmax: continue
+        errs.append((float((r[2][k].double()-v).norm()/v.norm()),k))
+    errs.sort(reverse=True)
+    print(name,'mixed','worst grad %.2e %s  median %.2e'%(errs[0][0],errs[0][1],errs[len(errs)//2][0]), errs[:4])
