@@ -1,16 +1,20 @@
 #!/bin/bash
-# ncu captures for profiles/ (run under gpurun, 1 GPU): launch list of the profiled steps + full sets of the dominant kernels
+# ncu captures for profiles/ (run under gpurun, 1 GPU): launch list of the profiled steps + full sets of the dominant kernels.
+# scripts/profile_step.py runs 3 warm-up steps and one measured eager step on a single stream.
 TAG=${1:-r1}
 mkdir -p gpurun_out
+if [ -z "$SKIP_LIST" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python scripts/profile_step.py cifar 256 3 > gpurun_out/events_${TAG}.txt 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm_pair_kernel -s 2 -c 2 -o gpurun_out/prof_${TAG}_conv_fwd -f \
     python scripts/profile_step.py cifar 256 3 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 30 -c 2 -o gpurun_out/prof_${TAG}_conv_dgrad -f \
-    python scripts/profile_step.py cifar 256 3 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:wgrad_gemm_kernel -s 12 -c 2 -o gpurun_out/prof_${TAG}_wgrad -f \
-    python scripts/profile_step.py cifar 256 3 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mmd_fused -s 1 -c 1 -o gpurun_out/prof_${TAG}_mmd -f \
-    python scripts/profile_step.py cifar 256 3 > /dev/null 2>&1
+fi
+cap() {  # name, demangled-name regex, launches to skip, launches to capture (keep the reports small: <= 64 MiB come back)
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 \
+      -o gpurun_out/prof_${TAG}_$1 -f python scripts/profile_step.py cifar 256 3 > /dev/null 2>&1
+}
+cap conv_fwd 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+6' 0 2          # D forward convs (6 plane-pair products)
+cap conv_dgrad 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3' 0 2        # D input gradients, N >= 256
+cap conv_dgrad_n64 'conv_gemm_kernel<[^0-9]*64[^0-9]+3[^0-9]+(1|true)' 0 2   # input gradient of the 64->128 stride-2 conv (N = 64)
+cap wgrad 'wgrad_gemm_kernel<[^0-9]*256[^0-9]+3' 8 2                 # first batch-sized weight gradients (8 batch-1 SN launches skipped)
+cap mmd 'mmd_fused' 0 1
 python scripts/profile_step.py cifar 256 3 > gpurun_out/events_${TAG}.txt 2>&1
 ls -la gpurun_out/ | tail -12
