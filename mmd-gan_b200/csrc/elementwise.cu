@@ -69,13 +69,9 @@ __device__ __forceinline__ int perm_feature(int j, int C, int HW) {  // internal
     return c * HW + hw;
 }
 
-__device__ __forceinline__ void pack_one(const PackParams& p, long long i) {
-    const long long per_class = static_cast<long long>(p.rows_pad) * p.kpad;
+// value of packed element (class cls, row, col) read from the canonical weights
+__device__ __forceinline__ float pack_value(const PackParams& p, int cls, int row, int col) {
     {
-        const int cls = static_cast<int>(i / per_class);
-        const long long f = i - cls * per_class;
-        const int row = static_cast<int>(f / p.kpad);
-        const int col = static_cast<int>(f - static_cast<long long>(row) * p.kpad);
         // K order of the gather-GEMM: (channel chunk of CW = min(Cs, 32), tap, channel within the chunk)
         const int cw = p.Cs >= 32 ? 32 : p.Cs;
         const int ntaps = (p.mode == PACK_CONV_DGRAD_S2 || p.mode == PACK_TC_FWD) ? 4 : ((p.mode >= PACK_DENSE_FWD) ? 1 : p.k * p.k);
@@ -128,14 +124,43 @@ __device__ __forceinline__ void pack_one(const PackParams& p, long long i) {
                 break;
             }
         }
-        store_planes(p.out + i, p.plane, p.npl, v);
+        return v;
     }
 }
-__global__ void pack_weights_kernel(const PackParams p) {
-    const long long total = static_cast<long long>(p.rows_pad) * p.kpad * p.classes;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        pack_one(p, i);
+// One 32 x 32 tile (rows x K columns) of a packed operand per block iteration, 256 threads.  The canonical layouts are
+// contiguous along the packed ROW index for half of the modes (conv forward, transposed-conv input gradient, dense
+// forward) and along the packed COLUMN index for the others; the tile is read along whichever index is contiguous in
+// the source and written along the columns (contiguous in the destination) through shared memory, so both sides of
+// the repack are coalesced.
+__device__ __forceinline__ void pack_tiles(const PackParams& p, float (*tile)[33]) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int rows_all = p.rows_pad * p.classes;
+    const int tr = (rows_all + 31) >> 5, tc = (p.kpad + 31) >> 5;
+    const bool row_contig = p.mode == PACK_CONV_FWD || p.mode == PACK_TC_DGRAD || p.mode == PACK_DENSE_FWD;
+    for (int tidx = blockIdx.x; tidx < tr * tc; tidx += gridDim.x) {
+        const int r0 = (tidx / tc) << 5, c0 = (tidx % tc) << 5;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // read: tx runs along the source-contiguous index
+            const int rr = row_contig ? tx : ty + 8 * j, cc = row_contig ? ty + 8 * j : tx;
+            const int grow = r0 + rr, col = c0 + cc;
+            float v = 0.f;
+            if (grow < rows_all && col < p.kpad) v = pack_value(p, grow / p.rows_pad, grow % p.rows_pad, col);
+            tile[rr][cc] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rr = ty + 8 * j, grow = r0 + rr, col = c0 + tx;
+            if (grow < rows_all && col < p.kpad)
+                store_planes(p.out + static_cast<long long>(grow) * p.kpad + col, p.plane, p.npl, tile[rr][tx]);
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackParams p) {
+    __shared__ float tile[32][33];
+    pack_tiles(p, tile);
 }
 
 // out[j'] = src[perm(j')]: canonical per-feature vector (bias / gamma / beta) -> internal NHWC-flatten order
@@ -148,14 +173,11 @@ __global__ void permute_features_kernel(const float* __restrict__ src, float* __
 
 // One launch refreshes every parameter-derived buffer of a net after an update: weight packing jobs and feature
 // permutation / padding jobs; blockIdx.y selects the job, the jobs live in device memory (built once at start-up).
-__device__ __forceinline__ void pack_one(const PackParams& p, long long i);
-__global__ void refresh_kernel(const RefreshJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(256) refresh_kernel(const RefreshJob* __restrict__ jobs) {
+    __shared__ float tile[32][33];
     const RefreshJob& job = jobs[blockIdx.y];
     if (job.kind == 0) {
-        const long long total = static_cast<long long>(job.pack.rows_pad) * job.pack.kpad * job.pack.classes;
-        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-             i += static_cast<long long>(gridDim.x) * blockDim.x)
-            pack_one(job.pack, i);
+        pack_tiles(job.pack, tile);
     } else {
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < job.n; j += gridDim.x * blockDim.x) {
             if (job.inverse) job.dst[perm_feature(j, job.C, job.HW)] = job.src[j];
@@ -167,38 +189,53 @@ __global__ void refresh_kernel(const RefreshJob* __restrict__ jobs) {
 // out[m][n] = alpha * sum_k A[m][k] * Wt[n][k] + bias[n] for a handful of output columns (the 16 critic scores):
 // fp32 FFMA on the values reassembled from the bf16 planes, one block per row, warp-shuffle + shared-memory reduction.
 // The tensor-core tile would be 94 % padding here (N = 16 of 128 lanes x 8192 deep on 4 CTAs).
-template <int N>
-__global__ void __launch_bounds__(256) dense_small_fwd_kernel(const bf16_t* __restrict__ a, long long a_plane, int npl, int K,
+template <int N, int R>
+__global__ void __launch_bounds__(256) dense_small_fwd_kernel(const bf16_t* __restrict__ a, long long a_plane, int npl, int rows, int K,
                                                              const bf16_t* __restrict__ wt, long long w_plane, int kpad,
                                                              float alpha_k, const float* __restrict__ sigma,
                                                              const float* __restrict__ bias, float* __restrict__ out, int ldo) {
-    __shared__ float red[8][N];
-    const long long arow = static_cast<long long>(blockIdx.x) * K;
-    float acc[N];
+    // R rows per block share every weight load (the weights are re-read once per R rows instead of once per row)
+    __shared__ float red[8][R][N];
+    const int row0 = blockIdx.x * R;
+    float acc[R][N];
 #pragma unroll
-    for (int n = 0; n < N; ++n) acc[n] = 0.f;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[r][n] = 0.f;
     for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
-        const float4 x = load_planes4(a, a_plane, npl, arow + k);
+        float4 x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            x[r] = row0 + r < rows ? load_planes4(a, a_plane, npl, static_cast<long long>(row0 + r) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int n = 0; n < N; ++n) {
             const float4 w = load_planes4(wt, w_plane, npl, static_cast<long long>(n) * kpad + k);
-            acc[n] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[n]))));
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                acc[r][n] = fmaf(x[r].x, w.x, fmaf(x[r].y, w.y, fmaf(x[r].z, w.z, fmaf(x[r].w, w.w, acc[r][n]))));
         }
     }
 #pragma unroll
-    for (int n = 0; n < N; ++n)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[r][n] += __shfl_xor_sync(0xffffffffu, acc[r][n], o);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0)
 #pragma unroll
-        for (int n = 0; n < N; ++n) red[warp][n] = acc[n];
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int n = 0; n < N; ++n) red[warp][r][n] = acc[r][n];
     __syncthreads();
-    if (threadIdx.x < N) {
-        float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        const float alpha = sigma ? alpha_k / __ldg(sigma) : alpha_k;
-        out[static_cast<long long>(blockIdx.x) * ldo + threadIdx.x] = fmaf(s, alpha, bias ? bias[threadIdx.x] : 0.f);
+    if (threadIdx.x < R * N) {
+        const int r = threadIdx.x / N, n = threadIdx.x % N;
+        if (row0 + r < rows) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += red[w][r][n];
+            const float alpha = sigma ? alpha_k / __ldg(sigma) : alpha_k;
+            out[static_cast<long long>(row0 + r) * ldo + n] = fmaf(s, alpha, bias ? bias[n] : 0.f);
+        }
     }
 }
 
@@ -451,6 +488,31 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* _
                                     bf16_t* __restrict__ out, long long plane, int npl) {
     const long long total = rows * C;
     const float inv_rows = 1.0f / static_cast<float>(rows);
+    if ((C & 3) == 0) {      // four consecutive channels per thread: 16-byte loads, 8-byte plane stores
+        for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < total;
+             i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+            const int c = static_cast<int>(i % C);
+            const float4 is = *reinterpret_cast<const float4*>(invstd + c), g = *reinterpret_cast<const float4*>(gamma + c);
+            const float4 mu = *reinterpret_cast<const float4*>(mean + c), b = *reinterpret_cast<const float4*>(beta + c);
+            const float4 db = *reinterpret_cast<const float4*>(dbeta + c), dg = *reinterpret_cast<const float4*>(dgamma + c);
+            const float4 zv = *reinterpret_cast<const float4*>(z + i);
+            float4 dy = *reinterpret_cast<const float4*>(da + i);
+            const float4 xh = make_float4((zv.x - mu.x) * is.x, (zv.y - mu.y) * is.y, (zv.z - mu.z) * is.z, (zv.w - mu.w) * is.w);
+            if (act == 2) {
+                if (fmaf(xh.x, g.x, b.x) <= 0.f) dy.x = 0.f;
+                if (fmaf(xh.y, g.y, b.y) <= 0.f) dy.y = 0.f;
+                if (fmaf(xh.z, g.z, b.z) <= 0.f) dy.z = 0.f;
+                if (fmaf(xh.w, g.w, b.w) <= 0.f) dy.w = 0.f;
+            }
+            float4 v;
+            v.x = g.x * is.x * (dy.x - db.x * inv_rows - xh.x * dg.x * inv_rows);
+            v.y = g.y * is.y * (dy.y - db.y * inv_rows - xh.y * dg.y * inv_rows);
+            v.z = g.z * is.z * (dy.z - db.z * inv_rows - xh.z * dg.z * inv_rows);
+            v.w = g.w * is.w * (dy.w - db.w * inv_rows - xh.w * dg.w * inv_rows);
+            store_planes4(out + i, plane, npl, v);
+        }
+        return;
+    }
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(i % C);
@@ -519,7 +581,7 @@ int l_colsum_planes(const bf16_t* x, long long plane, int npl, int rows, int C, 
     return MG_CHECK_LAUNCH();
 }
 int l_pack_weights(const PackParams& p, cudaStream_t st) {
-    pack_weights_kernel<<<grid_for(static_cast<long long>(p.rows_pad) * p.kpad * p.classes), kBS, 0, st>>>(p);
+    pack_weights_kernel<<<grid_for(static_cast<long long>(p.rows_pad) * p.kpad * p.classes / 4), kBS, 0, st>>>(p);
     return MG_CHECK_LAUNCH();
 }
 int l_permute_features(const float* src, float* dst, int n, int C, int HW, int inverse, cudaStream_t st) {
@@ -579,7 +641,8 @@ int l_bn_bwd_reduce(const float* da, const float* z, const float* mean, const fl
 int l_bn_bwd_apply(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                    const float* dbeta, const float* dgamma, int C, long long rows, int act, bf16_t* out, long long plane, int npl,
                    cudaStream_t st) {
-    bn_bwd_apply_kernel<<<grid_for(rows * C), kBS, 0, st>>>(da, z, mean, invstd, gamma, beta, dbeta, dgamma, C, rows, act, out, plane, npl);
+    bn_bwd_apply_kernel<<<grid_for((C & 3) == 0 ? rows * C / 4 : rows * C), kBS, 0, st>>>(da, z, mean, invstd, gamma, beta, dbeta, dgamma, C, rows, act, out,
+                                                                                        plane, npl);
     return MG_CHECK_LAUNCH();
 }
 int l_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float b1, float b2, float eps, const int* step,
@@ -588,15 +651,19 @@ int l_adam(float* w, float* m, float* v, const float* g, long long n, float lr, 
     return MG_CHECK_LAUNCH();
 }
 int l_refresh(const RefreshJob* jobs, int njobs, long long max_elems, cudaStream_t st) {
-    dim3 grid(grid_for(max_elems), njobs);
+    dim3 grid(grid_for(max_elems / 4), njobs);      // blocks stride over 32 x 32 tiles (1024 elements per block iteration)
     refresh_kernel<<<grid, kBS, 0, st>>>(jobs);
     return MG_CHECK_LAUNCH();
 }
 int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int rows, int K, const bf16_t* wt, long long w_plane, int kpad, int N,
                       float alpha_k, const float* sigma, const float* bias, float* out, int ldo, cudaStream_t st) {
-    if (N == 16) dense_small_fwd_kernel<16><<<rows, 256, 0, st>>>(a, a_plane, npl, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 8) dense_small_fwd_kernel<8><<<rows, 256, 0, st>>>(a, a_plane, npl, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 32) dense_small_fwd_kernel<32><<<rows, 256, 0, st>>>(a, a_plane, npl, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
+    // four rows per block while that still fills the machine, else one
+    const bool quad = rows >= 256;
+    const int blocks = quad ? (rows + 3) / 4 : rows;
+    if (N == 16 && quad) dense_small_fwd_kernel<16, 4><<<blocks, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 16) dense_small_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 8) dense_small_fwd_kernel<8, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 32) dense_small_fwd_kernel<32, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
     else return -1;
     return MG_CHECK_LAUNCH();
 }
