@@ -129,6 +129,35 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream);
 /* number of M tiles (rows of the colsum workspace per class) */
 int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg);
 
+/* Direct 3x3 / stride-1 / SAME convolution on the CUDA cores for layers with <= 4 channels on one side (the image layers:
+ * tf.nn.conv2d at layer_func.py:912-916 for D's first and G's last layer, and their input gradients, my_sngan.py:301-304).
+ * fp32 FMAs on the values reassembled from the planes (exact products: no plane-pair passes); weights are read from the
+ * layer's canonical fp32 array [k][k][Cin][Cout] through strides, mirrored (flip = 1) for an input gradient.
+ * Either Cout <= 4 and Cin % 16 == 0 (<= 128), or Cin <= 4 and Cout % 16 == 0 (<= 128).  colsum / aux: Cout <= 4 only. */
+typedef struct mmdgan_direct_desc {
+    const mmdgan_bf16* src;
+    long long src_plane;
+    int src_npl, Cs;
+    int N, H, W;
+    int Cin, Cout;
+    const float* w;
+    long long w_tap, w_in, w_out;
+    int flip;
+    void* dst;
+    long long dst_plane;
+    int dst_npl, Cd, out_mode;
+    float alpha_k;
+    const float* sigma;
+    const float* bias;
+    int act;
+    const mmdgan_bf16* aux;
+    long long aux_plane;
+    int aux_npl, aux_mode;
+    float* colsum; /* [mmdgan_direct_conv_blocks()][Cd] */
+} mmdgan_direct_desc;
+int mmdgan_direct_conv(const mmdgan_direct_desc* d, void* stream);
+int mmdgan_direct_conv_blocks(int N, int H, int W);
+
 /* out[m][n] = alpha * sum_k a[m][k] * wt[n][k] + bias[n] for N in {4,8,16,32} output columns (the critic's score layer,
  * tf.matmul at layer_func.py:909-911 with 16 outputs): fp32 CUDA-core kernel on the values reassembled from npl planes of
  * the activation a and of the packed forward operand wt */

@@ -49,6 +49,17 @@ class WgradDesc(C.Structure):
         ('out', C.c_void_p), ('bn', C.c_int), ('npass', C.c_int)]
 
 
+class DirectDesc(C.Structure):
+    _fields_ = [
+        ('src', C.c_void_p), ('src_plane', C.c_longlong), ('src_npl', C.c_int), ('Cs', C.c_int),
+        ('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int), ('Cout', C.c_int),
+        ('w', C.c_void_p), ('w_tap', C.c_longlong), ('w_in', C.c_longlong), ('w_out', C.c_longlong), ('flip', C.c_int),
+        ('dst', C.c_void_p), ('dst_plane', C.c_longlong), ('dst_npl', C.c_int), ('Cd', C.c_int), ('out_mode', C.c_int),
+        ('alpha_k', C.c_float), ('sigma', C.c_void_p), ('bias', C.c_void_p), ('act', C.c_int),
+        ('aux', C.c_void_p), ('aux_plane', C.c_longlong), ('aux_npl', C.c_int), ('aux_mode', C.c_int),
+        ('colsum', C.c_void_p)]
+
+
 class WredDesc(C.Structure):
     _fields_ = [
         ('partials', C.c_void_p), ('splits', C.c_int), ('R', C.c_int), ('NC', C.c_int), ('Cg', C.c_int),
@@ -96,6 +107,8 @@ SYMBOLS = {
     'mmdgan_permute_features': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'mmdgan_refresh': (_I, [_P, _I, _LL, _P]),
     'mmdgan_dense_small_fwd': (_I, [_P, _LL, _I, _I, _I, _P, _LL, _I, _I, _F, _P, _P, _P, _I, _P]),
+    'mmdgan_direct_conv': (_I, [C.POINTER(DirectDesc), _P]),
+    'mmdgan_direct_conv_blocks': (_I, [_I, _I, _I]),
     'mmdgan_gather_gemm': (_I, [C.POINTER(GemmDesc), _P]),
     'mmdgan_gather_gemm_tiles': (_I, [_I, _I, _I]),
     'mmdgan_wgrad_gemm': (_I, [C.POINTER(WgradDesc), _P]),

@@ -14,6 +14,9 @@ int launch_conv_gemm(const ConvGemmParams& p, const uint16_t* w, long long w_pla
                      int npass, int pair, cudaStream_t st);
 int launch_wgrad_gemm(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, int bn, int npass,
                       cudaStream_t st);
+// direct_conv.cu
+int launch_direct_conv(const DirectConvParams& p, cudaStream_t st);
+int direct_conv_blocks(int N, int H, int W);
 // mmd.cu
 int launch_mmd(const MmdParams& p, cudaStream_t st);
 int mmd_grid_blocks(int b);
@@ -179,6 +182,32 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
         p.cls[i].wrow = d->cls[i].wrow;
     }
     return wrap(mg::launch_conv_gemm(p, d->w, d->w_plane, d->w_rows, d->kpad, d->classes, d->bn, d->npass, d->cta_pair, S(stream)), "mmdgan_gather_gemm");
+}
+
+int mmdgan_direct_conv_blocks(int N, int H, int W) { return mg::direct_conv_blocks(N, H, W); }
+int mmdgan_direct_conv(const mmdgan_direct_desc* d, void* stream) {
+    if (!d || !d->src || !d->w || !d->dst) return fail(MMDGAN_EINVAL, "mmdgan_direct_conv: null pointer");
+    if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cs <= 0 || (d->Cs & 7) || d->Cd <= 0 || (d->Cd & 3))
+        return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: bad shape");
+    const bool ls = d->Cout >= 1 && d->Cout <= 4 && d->Cin > 0 && d->Cin % 16 == 0 && d->Cin <= 128 && d->Cs >= d->Cin && d->Cd >= 4;
+    const bool sl = d->Cin >= 1 && d->Cin <= 4 && d->Cout > 0 && d->Cout % 16 == 0 && d->Cout <= 128 && d->Cd >= d->Cout;
+    if (!ls && !sl) return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: needs <= 4 channels on one side and a multiple of 16 (<= 128) on the other");
+    if (sl && (d->aux || d->colsum)) return fail(MMDGAN_EINVAL, "mmdgan_direct_conv: aux / colsum need Cout <= 4");
+    if (d->src_npl < 1 || d->src_npl > 3 || (d->src_npl > 1 && d->src_plane <= 0) || (d->src_plane & 7) || !al16(d->src) || !al16(d->dst))
+        return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: bad source plane layout");
+    if (d->out_mode != 0 && d->out_mode != 2) return fail(MMDGAN_EINVAL, "mmdgan_direct_conv: bad out_mode");
+    if (d->out_mode == 0 && (d->dst_npl < 1 || d->dst_npl > 3 || (d->dst_npl > 1 && d->dst_plane <= 0)))
+        return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: bad destination plane layout");
+    if (d->aux && (d->aux_npl < 1 || d->aux_npl > 3 || (d->aux_npl > 1 && d->aux_plane <= 0)))
+        return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: bad aux plane layout");
+    mg::DirectConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = d->src; p.src_plane = d->src_plane; p.src_npl = d->src_npl; p.Cs = d->Cs; p.N = d->N; p.H = d->H; p.W = d->W;
+    p.Cin = d->Cin; p.Cout = d->Cout; p.w = d->w; p.w_tap = d->w_tap; p.w_in = d->w_in; p.w_out = d->w_out; p.flip = d->flip;
+    p.dst = d->dst; p.dst_plane = d->dst_plane; p.dst_npl = d->dst_npl; p.Cd = d->Cd; p.out_mode = d->out_mode;
+    p.alpha_k = d->alpha_k; p.sigma = d->sigma; p.bias = d->bias; p.act = d->act;
+    p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_mode = d->aux_mode; p.colsum = d->colsum;
+    return wrap(mg::launch_direct_conv(p, S(stream)), "mmdgan_direct_conv");
 }
 
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream) {

@@ -64,6 +64,29 @@ struct WgradParams {
 };
 
 
+// direct_conv.cu: 3x3 / stride 1 / SAME convolution with <= 4 channels on one side (the image layers), NHWC
+struct DirectConvParams {
+    const uint16_t* src;     // bf16 planes [src_npl][N*H*W][Cs]
+    long long src_plane;
+    int src_npl, Cs;
+    int N, H, W;
+    int Cin, Cout;           // real channel counts of THIS convolution (for an input gradient: Cout_layer -> Cin_layer)
+    const float* w;          // canonical fp32 weights of the layer, element (tap, in, out) at tap*w_tap + in*w_in + out*w_out
+    long long w_tap, w_in, w_out;
+    int flip;                // 1: taps mirrored (input gradient)
+    void* dst;               // out_mode 0: bf16 planes [dst_npl][N*H*W][Cd]; 2: fp32 [N*H*W][Cd]
+    long long dst_plane;
+    int dst_npl, Cd, out_mode;
+    float alpha_k;
+    const float* sigma;
+    const float* bias;       // [Cout] (padded) or null
+    int act;
+    const uint16_t* aux;     // planes [aux_npl][N*H*W][Cd] or null (LS only)
+    long long aux_plane;
+    int aux_npl, aux_mode;
+    float* colsum;           // [blocks][Cd] per-block column sums of the written values, or null (LS only)
+};
+
 // mmd.cu
 struct MmdParams {
     const float* gen_loc;   // [b][d]

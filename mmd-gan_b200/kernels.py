@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, WgradDesc, WredDesc, PackDesc, MmdDesc, RefreshJob
+from ._lib import GemmDesc, WgradDesc, WredDesc, PackDesc, MmdDesc, RefreshJob, DirectDesc
 
 ACT = {'linear': 0, None: 0, 'lrelu': 1, 'relu': 2, 'tanh': 3}
 PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRAD, PACK_DENSE_FWD, PACK_DENSE_DGRAD = range(7)
@@ -22,6 +22,7 @@ GEMM_PAIR = True        # use the CTA-pair (cta_group::2) gather-GEMM where the 
 GEMM_PAIR_MIN_TILES = 256   # 128 x 128 output units; below that the single-CTA kernel fills the machine better
 GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
 WGRAD_BN_MAX = int(os.environ.get('MMDGAN_WGRAD_BN', '256'))   # widest N tile of the weight-gradient GEMM (64 / 128 / 256)
+DIRECT_CONV = True     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
 
@@ -162,6 +163,14 @@ class LinearOp(object):
             raise AttributeError('layer op {} not supported.'.format(op))
         self.Cs_in, self.Cs_out = pad_c(self.Cin), pad_c(self.Cout)
         self.pad = 1 if op != 'd' else 0
+        # direct CUDA-core kernels of the forward / input-gradient pass: 'sl' (<= 4 -> many channels) or 'ls' (many -> <= 4)
+        self.direct_f = self.direct_d = None
+        self.w_canon = None
+        if op == 'c' and kernel == 3 and strides == 1 and DIRECT_CONV:
+            if self.Cin <= 4 and self.Cout % 16 == 0 and self.Cout <= 128:
+                self.direct_f, self.direct_d = 'sl', 'ls'
+            elif self.Cout <= 4 and self.Cin % 16 == 0 and self.Cin <= 128:
+                self.direct_f, self.direct_d = 'ls', 'sl'
         k = kernel
         # ---- forward / dgrad operand geometry
         if op == 'd':
@@ -195,6 +204,7 @@ class LinearOp(object):
     # -------------------------------------------------------------------------------------------- packing
     def pack_descs(self, w_canon):
         """The two packing jobs (forward, input-gradient operand) of this op as PackDesc structures."""
+        self.w_canon = w_canon
         out = []
         for g in (self.f, self.d):
             d = PackDesc()
@@ -212,6 +222,7 @@ class LinearOp(object):
 
     def pack(self, w_canon):
         """canonical weights -> forward and input-gradient GEMM operands (unscaled; act_k / sigma is an epilogue alpha)."""
+        self.w_canon = w_canon
         for g in (self.f, self.d):
             d = PackDesc()
             d.w, d.out = _ptr(w_canon), _ptr(g['w'])
@@ -295,11 +306,37 @@ class LinearOp(object):
                         cls=[(ph - 1, pw - 1, ph, pw) for ph in (0, 1) for pw in (0, 1)])
         return dict(dims=(self.Hout, self.Wout, self.Hin, self.Win, 2, 2, 4, 4, self.Hin, self.Win, 1, 1), cls=[(-1, -1, 0, 0)])
 
+    def _direct(self, fwd, src, nimg, dst, sigma, alpha_k, bias, act, aux, aux_mode, colsum, out_mode):
+        """3x3 / stride-1 image-channel layer on the CUDA cores (mmdgan_direct_conv): exact fp32 products."""
+        d = DirectDesc()
+        _planes(src)
+        d.src, d.src_plane, d.src_npl, d.Cs = _ptr(src), plane_stride(src), src.shape[0], src.shape[2]
+        d.N, d.H, d.W = nimg, self.Hin, self.Win
+        ci, co = self.Cin, self.Cout
+        d.w, d.w_tap = _ptr(self.w_canon), ci * co
+        if fwd:
+            d.Cin, d.Cout, d.w_in, d.w_out, d.flip = ci, co, co, 1, 0
+        else:
+            d.Cin, d.Cout, d.w_in, d.w_out, d.flip = co, ci, 1, co, 1
+        assert src.shape[1] >= nimg * self.Hin * self.Win and dst.shape[1] >= nimg * self.Hin * self.Win
+        if (out_mode == 0) != (dst.dtype == torch.bfloat16):
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 writes bf16 planes, out_mode 2 one fp32 plane')
+        d.dst, d.dst_plane, d.dst_npl, d.Cd, d.out_mode = _ptr(dst), plane_stride(dst), dst.shape[0], dst.shape[2], out_mode
+        d.alpha_k, d.sigma, d.bias, d.act = float(alpha_k), _ptr(sigma), _ptr(bias), act
+        if aux is not None:
+            _planes(aux)
+            d.aux, d.aux_plane, d.aux_npl = _ptr(aux), plane_stride(aux), aux.shape[0]
+        d.aux_mode = aux_mode
+        d.colsum = _ptr(colsum)
+        check(lib().mmdgan_direct_conv(C.byref(d), stream()))
+
     def fwd_tiles(self, nimg):
         g = self._fwd_geom()['dims']
         return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.f['classes']
 
     def dgrad_tiles(self, nimg):
+        if self.direct_d == 'ls':       # rows of the per-block column-sum workspace of the direct kernel
+            return lib().mmdgan_direct_conv_blocks(nimg, self.Hin, self.Win)
         g = self._dgrad_geom()['dims']
         return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.d['classes']
 
@@ -313,6 +350,8 @@ class LinearOp(object):
                                                plane_stride(self.f['w']), self.f['kpad'], self.Cs_out, float(alpha_k), _ptr(sigma),
                                                _ptr(bias), _ptr(dst), dst.shape[2], stream()))
             return
+        if self.direct_f and colsum is None and colsumsq is None and self.w_canon is not None:
+            return self._direct(True, src, nimg, dst, sigma, alpha_k, bias, act, None, 0, None, out_mode)
         self._gemm(self.f, src, nimg, dst, self._fwd_geom(), sigma, alpha_k, bias, act, None, 0, None, colsum, colsumsq, 0, out_mode,
                    self.fwd_npass)
 
@@ -320,6 +359,9 @@ class LinearOp(object):
               out_mode=0, npass=None):
         """Input gradient (npass defaults to the 3-pair gradient mode; the spectral-norm power iteration, which uses the
         adjoint as a FORWARD operator, passes the 6-pair mode)."""
+        if (self.direct_d and aux_wrap is None and not colsum_rows and self.w_canon is not None
+                and (self.direct_d == 'ls' or (aux is None and colsum is None))):
+            return self._direct(False, dy, nimg, dst, sigma, alpha_k, None, 0, aux, aux_mode, colsum, out_mode)
         self._gemm(self.d, dy, nimg, dst, self._dgrad_geom(), sigma, alpha_k, None, 0, aux, aux_mode, aux_wrap, colsum, None,
                    colsum_rows, out_mode, self.bwd_npass if npass is None else npass)
 

@@ -13,7 +13,7 @@ eng.sn_fork = eng.grad_fork = False   # single stream: every launch timed alone
 g = torch.Generator().manual_seed(0)
 data = (torch.rand(B, *arch['input'][0], generator=g) * 2 - 1).cuda(); code = torch.randn(B, 128, generator=g).cuda()
 recs = []
-og, ow = K.LinearOp._gemm, K.LinearOp.wgrad
+og, ow, od = K.LinearOp._gemm, K.LinearOp.wgrad, K.LinearOp._direct
 def tg(self, g_, src, nimg, dst, geom, *a, **kw):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(); r = og(self, g_, src, nimg, dst, geom, *a, **kw); e.record()
@@ -27,9 +27,16 @@ def tw(self, x_in, dy, nimg, partials, splits=None):
     R, NC, bn, sp, P = self.wgrad_plan(nimg)
     recs.append(('wgrad', self.op, self.Cin, self.Cout, self.Hin, nimg, R, NC, P, 2.0 * R * NC * P, s, e, (bn, r)))
     return r
+def td(self, fwd, src, nimg, dst, *a, **kw):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); r = od(self, fwd, src, nimg, dst, *a, **kw); e.record()
+    M = nimg * self.Hin * self.Win
+    recs.append(('fwd*' if fwd else 'dgrad*', self.op, self.Cin, self.Cout, self.Hin, nimg, M, self.Cout if fwd else self.Cin, 9 * (self.Cin if fwd else self.Cout),
+                 2.0 * M * 9 * self.Cin * self.Cout, s, e, 'direct'))
+    return r
 for it in range(3):
     eng.stage(data, code); eng.step_device()
-K.LinearOp._gemm, K.LinearOp.wgrad = tg, tw
+K.LinearOp._gemm, K.LinearOp.wgrad, K.LinearOp._direct = tg, tw, td
 recs.clear()
 eng.stage(data, code)
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

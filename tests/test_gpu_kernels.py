@@ -152,6 +152,60 @@ def test_dgrad_fused_activation_derivative_and_wrap(cuda):
     assert rel(cs.sum(0), dx_ref[:2 * b].sum([0, 2, 3])) < 1e-4
 
 
+def test_direct_conv_image_layers(cuda):
+    """The image-channel layers (3 -> 64, 64 -> 3) run as direct CUDA-core convolutions; here the input gradient of D's
+    first layer with everything the engine fuses into it: act_k / sigma, tanh'(x_gen) read from the planes, per-block
+    column sums (bias gradient of the generator's last layer) -- and agreement with the tensor-core path."""
+    from mmdgan_b200 import kernels as K
+    g = torch.Generator().manual_seed(21)
+    b, h = 3, 16
+    sp = _spec('c', 3, 64, h, 3, 1)
+    w = torch.randn(sp.kernel_shape, generator=g, dtype=torch.float64) * 0.1
+    dy = torch.randn(b, 64, h, h, generator=g, dtype=torch.float64)
+    xg = torch.tanh(torch.randn(b, 3, h, h, generator=g, dtype=torch.float64))
+    alpha_k, sigma = 0.9, 1.7
+    ref = F.conv_transpose2d(dy, w.permute(3, 2, 0, 1), padding=1) * (alpha_k / sigma) * (1.0 - xg * xg)
+    outs = []
+    for direct in (True, False):
+        K.DIRECT_CONV = direct
+        try:
+            lop = K.LinearOp('c', [3, h, h], [64, h, h], 3, 1)
+        finally:
+            K.DIRECT_CONV = True
+        assert (lop.direct_d == 'ls') == direct and (lop.direct_f == 'sl') == direct
+        lop.pack(w.float().to(cuda).contiguous())
+        dys = K.new_planes(b * h * h, 64, 2)
+        K.nchw_to_planes(dy.float().to(cuda).contiguous(), dys)
+        auxp = K.new_planes(b * h * h, 8, 3)
+        K.nchw_to_planes(xg.float().to(cuda).contiguous(), auxp)
+        dxs = K.new_planes(b * h * h, 8, 2)
+        cs = torch.zeros(lop.dgrad_tiles(b), 8, device=cuda)
+        lop.dgrad(dys, b, dxs, sigma=torch.tensor([sigma], device=cuda), alpha_k=alpha_k, aux=auxp, aux_mode=3, colsum=cs)
+        dx = K.planes_to_nchw(dxs, b, 3, h, h)
+        assert rel(dx, ref) < TOL3
+        assert rel(cs.sum(0)[:3], ref.sum([0, 2, 3])) < 1e-4 and float(cs[:, 3:].abs().max()) == 0.0
+        outs.append(dx)
+    assert rel(outs[0], outs[1]) < TOL3
+    # forward of G's last layer 64 -> 3 with bias + tanh, odd image size (partial 16 x 16 tiles)
+    h = 24
+    sp = _spec('c', 64, 3, h, 3, 1)
+    w = torch.randn(sp.kernel_shape, generator=g, dtype=torch.float64) * 0.05
+    x = torch.randn(2, 64, h, h, generator=g, dtype=torch.float64)
+    bias = torch.randn(3, generator=g, dtype=torch.float64) * 0.1
+    y_ref = torch.tanh(onet._op_forward(sp, x, w) + bias.view(1, -1, 1, 1))
+    lop = K.LinearOp('c', [64, h, h], [3, h, h], 3, 1)
+    assert lop.direct_f == 'ls'
+    lop.pack(w.float().to(cuda).contiguous())
+    xs = K.new_planes(2 * h * h, 64, 3)
+    K.nchw_to_planes(x.float().to(cuda).contiguous(), xs)
+    ys = K.new_planes(2 * h * h, 8, 3)
+    bias_d = torch.zeros(8, device=cuda)
+    bias_d[:3] = bias.float().to(cuda)
+    lop.forward(xs, 2, ys, bias=bias_d, act=3, out_mode=0)
+    assert rel(K.planes_to_nchw(ys, 2, 3, h, h), y_ref) < TOL3
+    assert float(K.planes_value(ys)[:, 3:].abs().max()) == 0.0
+
+
 MMD_CASES = [(2, 16), (3, 16), (64, 16), (200, 16), (256, 16), (96, 8), (40, 32), (130, 64), (33, 4)]
 
 
