@@ -19,9 +19,10 @@ PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRA
 
 
 GEMM_PAIR = True        # use the CTA-pair (cta_group::2) gather-GEMM where the grid is large enough
-GEMM_PAIR_MIN_TILES = 256   # 128 x 128 output units; below that the single-CTA kernel fills the machine better
+GEMM_PAIR_MIN_TILES = int(os.environ.get('MMDGAN_PAIR_MIN_TILES', '256'))   # 128 x 128 output units; below that the single-CTA kernel fills the machine better
 GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
 WGRAD_BN_MAX = int(os.environ.get('MMDGAN_WGRAD_BN', '256'))   # widest N tile of the weight-gradient GEMM (64 / 128 / 256)
+PAIR_BN256_AUX = int(os.environ.get('MMDGAN_BN256_AUX', '0'))   # experiment knob: 256-wide pair tiles for input gradients with N = 256
 DIRECT_CONV = True     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
@@ -268,7 +269,7 @@ class LinearOp(object):
             # tcgen05 cta_group::2: a 2-CTA cluster shares a 256 x bn tile (half the weight bytes per CTA).  bn = 256 doubles
             # the epilogue per CTA: measured to pay off for plain forward epilogues and for very wide layers only
             pair = 1
-            bn = 256 if (g['ncols'] % 256 == 0 and (g['ncols'] >= 512 or aux is None)) else 128
+            bn = 256 if (g['ncols'] % 256 == 0 and (g['ncols'] >= 512 or aux is None or PAIR_BN256_AUX)) else 128
         elif GEMM_BN_MAX >= 256 and g['ncols'] % 256 == 0 and npass != 6:
             # 128 x 256 tiles halve the re-reads of the gathered operand, but leave only two pipeline stages per CTA and
             # double the epilogue: measured to pay off only while the grid still fills the 2 x 148 CTA slots
