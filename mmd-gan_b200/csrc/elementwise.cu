@@ -658,7 +658,7 @@ int l_refresh(const RefreshJob* jobs, int njobs, long long max_elems, cudaStream
 int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int rows, int K, const bf16_t* wt, long long w_plane, int kpad, int N,
                       float alpha_k, const float* sigma, const float* bias, float* out, int ldo, cudaStream_t st) {
     // four rows per block while that still fills the machine, else one
-    const bool quad = rows >= 256;
+    const bool quad = false;    // measured (ncu, 512 rows): four rows per block leaves 128 blocks for 148 SMs and is 2x slower than one row per block
     const int blocks = quad ? (rows + 3) / 4 : rows;
     if (N == 16 && quad) dense_small_fwd_kernel<16, 4><<<blocks, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
     else if (N == 16) dense_small_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);

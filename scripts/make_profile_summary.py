@@ -20,7 +20,7 @@ if os.path.exists(lp):
     for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append('| `{}` | {} | {:.1f} | {:.1f}% |'.format(k, c, v / 1e3, 100 * v / tot))
     out.append('')
-for name in ['conv_fwd', 'conv_dgrad', 'wgrad', 'mmd']:
+for name in ['conv_fwd', 'conv_dgrad', 'conv_dgrad_n64', 'wgrad', 'mmd']:
     rep = 'gpurun_out/prof_{}_{}.ncu-rep'.format(tag, name)
     if os.path.exists(rep):
         txt = subprocess.run([sys.executable, 'scripts/ncu_top.py', rep, '12'], capture_output=True, text=True).stdout

@@ -11,10 +11,10 @@ cap() {  # name, demangled-name regex, launches to skip, launches to capture (ke
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 \
       -o gpurun_out/prof_${TAG}_$1 -f python scripts/profile_step.py cifar 256 3 > /dev/null 2>&1
 }
-cap conv_fwd 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+6' 0 2          # D forward convs (6 plane-pair products)
-cap conv_dgrad 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3' 0 2        # D input gradients, N >= 256
-cap conv_dgrad_n64 'conv_gemm_kernel<[^0-9]*64[^0-9]+3[^0-9]+(1|true)' 0 2   # input gradient of the 64->128 stride-2 conv (N = 64)
-cap wgrad 'wgrad_gemm_kernel<[^0-9]*256[^0-9]+3' 8 2                 # first batch-sized weight gradients (8 batch-1 SN launches skipped)
+cap conv_fwd 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+6' 0 1          # D forward convs (6 plane-pair products)
+cap conv_dgrad 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3[^0-9]+(1|true)' 0 1        # D input gradients, N >= 256
+cap conv_dgrad_n64 'conv_gemm_kernel<[^0-9]*64[^0-9]+3[^0-9]+(1|true)' 0 1   # input gradient of the 64->128 stride-2 conv (N = 64)
+cap wgrad 'wgrad_gemm_kernel<[^0-9]*256[^0-9]+3' 8 1                 # first batch-sized weight gradients (8 batch-1 SN launches skipped)
 cap mmd 'mmd_fused' 0 1
 python scripts/profile_step.py cifar 256 3 > gpurun_out/events_${TAG}.txt 2>&1
-ls -la gpurun_out/ | tail -12
+du -sh gpurun_out; ls -la gpurun_out/ | tail -12
