@@ -122,7 +122,7 @@ typedef struct mmdgan_gemm_desc {
     int out_mode;       /* 0 bf16 planes, 2 raw fp32 */
     int bn;             /* N tile: 16, 32, 64, 128, 256 */
     int npass;          /* 6, 3 or 1 plane-pair products per k-block (see the header comment) */
-    int cta_pair;       /* 1: tcgen05 cta_group::2 -- a 2-CTA cluster shares one 256 x bn tile (bn 128 or 256) */
+    int cta_pair;       /* 1: tcgen05 cta_group::2 -- a 2-CTA cluster shares one 256 x bn tile (bn 64, 128 or 256) */
     mmdgan_gemm_class cls[4];
 } mmdgan_gemm_desc;
 int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream);

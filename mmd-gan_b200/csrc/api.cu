@@ -157,7 +157,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad destination plane layout");
     if (d->aux && (d->aux_npl < 1 || d->aux_npl > 3 || (d->aux_npl > 1 && d->aux_plane <= 0) || !al16(d->aux)))
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad aux plane layout");
-    if (d->cta_pair && d->bn != 128 && d->bn != 256) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: cta_pair needs bn 128 or 256");
+    if (d->cta_pair && d->bn != 64 && d->bn != 128 && d->bn != 256) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: cta_pair needs bn 64, 128 or 256");
     if (d->npass == 6 && d->bn == 256 && !d->cta_pair) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass 6 with bn 256 needs cta_pair");
     const long long M = static_cast<long long>(d->Nimg) * d->Hg * d->Wg;
     if (M > 2000000000ll) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: too many rows");

@@ -658,7 +658,7 @@ int launch_conv_gemm(const ConvGemmParams& p, const uint16_t* w, long long w_pla
     MG_CASE(16, 6) MG_CASE(32, 6) MG_CASE(64, 6) MG_CASE(128, 6)
     MG_CASE(16, 3) MG_CASE(32, 3) MG_CASE(64, 3) MG_CASE(128, 3) MG_CASE(256, 3)
     MG_CASE(16, 1) MG_CASE(32, 1) MG_CASE(64, 1) MG_CASE(128, 1) MG_CASE(256, 1)
-    MG_PAIR(128, 6) MG_PAIR(256, 6) MG_PAIR(128, 3) MG_PAIR(256, 3) MG_PAIR(128, 1) MG_PAIR(256, 1)
+    MG_PAIR(64, 6) MG_PAIR(128, 6) MG_PAIR(256, 6) MG_PAIR(64, 3) MG_PAIR(128, 3) MG_PAIR(256, 3) MG_PAIR(64, 1) MG_PAIR(128, 1) MG_PAIR(256, 1)
 #undef MG_CASE
 #undef MG_PAIR
     return -1;

@@ -313,6 +313,7 @@ class SNGanEngine(object):
         self._upd_stream = torch.cuda.Stream(device=self.device)    # the generator's Adam + refresh
         self.sn_fork = True
         self.grad_fork = True
+        self._dis_updated = False
         # pinned staging for the end-to-end path
         self._pin_data = torch.empty((B, self.channels, self.height, self.width), dtype=torch.float32).pin_memory()
         self._pin_code = torch.empty((B, self.code_size), dtype=torch.float32).pin_memory()
@@ -525,6 +526,22 @@ class SNGanEngine(object):
                             out_mode=self.om)
                 if gl.has_bias:
                     pending.append(lambda gl=gl, L=L: self._bias_grad_from_colsum(G, gl, L.Cs_in))
+        # The discriminator's gradients are complete once its finalisation work has drained; its Adam update and operand
+        # refresh then run on the update stream WHILE the generator's backward pass proceeds (nothing below reads a
+        # discriminator weight).  Multi-GPU: the update has to wait for the gradient all-reduce, so it stays in _phase_update.
+        self._dis_updated = False
+        if side is not main and self.world_size == 1:
+            flush()
+            ev_side, ev_main = torch.cuda.Event(), torch.cuda.Event()
+            ev_side.record(side)
+            ev_main.record(main)       # the last kernel that reads a packed / canonical D weight (D's first layer input gradient)
+            self._upd_stream.wait_event(ev_side)
+            self._upd_stream.wait_event(ev_main)
+            with torch.cuda.stream(self._upd_stream):
+                K.incr_step(D.step)
+                K.adam(D.w, D.m, D.v, D.g, D.n_flat, self.lr_dis, D.step)
+                D.refresh()
+            self._dis_updated = True
         # ================= generator: loss_gen -> G variables
         for i in range(len(G.layers) - 1, -1, -1):
             L = G.layers[i]
@@ -578,11 +595,14 @@ class SNGanEngine(object):
             ev = torch.cuda.Event()
             ev.record(main)
             side.wait_event(ev)
-        for net, lr, st in ((self.D, self.lr_dis, main), (self.G, self.lr_gen, side)):
+        for net, lr, st in ((self.D, self.lr_dis, side), (self.G, self.lr_gen, main)):
+            if net is self.D and self._dis_updated:        # already enqueued on the update stream during the backward pass
+                continue
             with torch.cuda.stream(st):
                 K.incr_step(net.step)
                 K.adam(net.w, net.m, net.v, net.g, net.n_flat, lr, net.step)
                 net.refresh()
+        self._dis_updated = False
         with torch.cuda.stream(side):
             for L in self.D.layers + self.G.layers:
                 if L.has_sn:

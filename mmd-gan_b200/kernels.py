@@ -23,6 +23,7 @@ GEMM_PAIR_MIN_TILES = int(os.environ.get('MMDGAN_PAIR_MIN_TILES', '256'))   # 12
 GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
 WGRAD_BN_MAX = int(os.environ.get('MMDGAN_WGRAD_BN', '256'))   # widest N tile of the weight-gradient GEMM (64 / 128 / 256)
 PAIR_BN256_AUX = int(os.environ.get('MMDGAN_BN256_AUX', '0'))   # experiment knob: 256-wide pair tiles for input gradients with N = 256
+PAIR_N64 = int(os.environ.get('MMDGAN_PAIR_N64', '0'))   # CTA-pair tiles for N = 64 layers: measured slower (0.36 vs 0.33 ms), off
 DIRECT_CONV = True     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
@@ -270,6 +271,9 @@ class LinearOp(object):
             # the epilogue per CTA: measured to pay off for plain forward epilogues and for very wide layers only
             pair = 1
             bn = 256 if (g['ncols'] % 256 == 0 and (g['ncols'] >= 512 or aux is None or PAIR_BN256_AUX)) else 128
+        elif GEMM_PAIR and PAIR_N64 and g['ncols'] == 64 and m_tiles * g['classes'] >= GEMM_PAIR_MIN_TILES:
+            # N = 64 layers are bound by the traffic of the gathered operand: a CTA pair halves the weight bytes per CTA
+            pair, bn = 1, 64
         elif GEMM_BN_MAX >= 256 and g['ncols'] % 256 == 0 and npass != 6:
             # 128 x 256 tiles halve the re-reads of the gathered operand, but leave only two pipeline stages per CTA and
             # double the epilogue: measured to pay off only while the grid still fills the 2 x 148 CTA slots
