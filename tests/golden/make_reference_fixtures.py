@@ -13,7 +13,8 @@ own functions are run:
                            (my_sngan.py:85-108, 259-323, 412-426; graph_func.py:478-575, 848-854): Net / Routine /
                            ParametricOperation build the generator and discriminator from the architecture dictionary;
                            losses, scores, generated images, every gradient, and every variable after the update.
-  ref_step_cifar_rep.npz, ref_step_cifar_rep_k27.npz   the same through the architecture dictionary parsed out of the reference's my_test_cifar.py
+  ref_step_cifar_rep.npz, ref_step_cifar_rep_k27.npz, ref_step_stl_rmb.npz, ref_step_celeba_rep.npz, ref_step_lsun_rep.npz
+                           the same through the architecture dictionaries parsed out of the reference's my_test_*.py scripts
                            (batch 4; gradients stored as norms plus a strided sample per variable to keep the file small;
                            the initial variables are the oracle's seeded initialisation, so only the seed is stored)
 
@@ -50,6 +51,9 @@ import make_golden as mg                       # noqa: E402  (input generators s
 
 FLAGS.SILENT_MODE = True
 assert tf.__version__.endswith('tfshim')
+
+
+SAMPLE = 257   # stride of the per-variable sample in the CIFAR fixtures
 
 
 # ------------------------------------------------------------------------------------------------ losses
@@ -196,39 +200,37 @@ def ref_step_case(loss_type):
     return out
 
 
-SAMPLE = 257   # stride of the per-variable sample in the CIFAR fixture
-
-
-def ref_step_cifar(batch=4, seed=2, steps=2, act_k=None):
-    """The reference's own CIFAR architecture dictionary (my_test_cifar.py:12-38), `steps` consecutive fused steps.
+def ref_step_cifar(batch=4, seed=2, steps=2, act_k=None, script='my_test_cifar.py', loss_type='rep', lr_list=(5e-4, 2e-4), stride=SAMPLE):
+    """The reference's own architecture dictionary (my_test_cifar.py:12-38 by default; my_test_stl.py, my_test_celebA.py and
+    my_test_lsun.py for the other fixtures), `steps` consecutive fused steps.
     act_k: optional override of the script's 64^(1/8) -- a larger multiplier spreads the scores so that the kernel
     differences are O(1) and an fp32 implementation can be compared at 1e-3 (the *_k27 fixture)."""
-    arch = reference_architecture('my_test_cifar.py')
+    arch = reference_architecture(script)
     if act_k is not None:
         for layer in arch['discriminator']:
             layer['act_k'] = act_k
-    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=seed)        # only for the seeded initial variables
+    m = onet.OracleSNGan(arch, loss_type, dtype=torch.float64, seed=seed)        # only for the seeded initial variables
     onet.warm_spectral_norm(m, 6)
     init = {}
     for d in (m.gen_params, m.dis_params, m.gen_state, m.dis_state):
         init.update({k: v.detach().clone() for k, v in d.items()})
-    run = ReferenceRun(arch, 'rep', lr_list=(5e-4, 2e-4))
+    run = ReferenceRun(arch, loss_type, lr_list=lr_list)
     run.set_variables(init)
     out = {'seed': np.asarray(seed), 'batch': np.asarray(batch), 'steps': np.asarray(steps), 'warm': np.asarray(6),
-           'act_k': np.asarray(arch['discriminator'][0]['act_k']),
-           'sample_stride': np.asarray(SAMPLE)}
+           'act_k': np.asarray(arch['discriminator'][0]['act_k']), 'loss_type': np.asarray(loss_type), 'lr_list': np.asarray(lr_list),
+           'sample_stride': np.asarray(stride)}
     for t in range(steps):
         data, code = onet.synthetic_batch(arch, batch, seed=5 + 10 * t, dtype=torch.float32)
         grads_list, (lg, ld) = run.build(data.double(), code.double(), batch)
         out['loss_gen_%d' % t], out['loss_dis_%d' % t] = lg.detach().numpy(), ld.detach().numpy()
         for k, v in list(_named_grads(grads_list[0]).items()) + list(_named_grads(grads_list[1]).items()):
             out['grad_norm_%d:%s' % (t, k)] = np.asarray(np.linalg.norm(v.ravel()))
-            out['grad_sample_%d:%s' % (t, k)] = v.ravel()[::SAMPLE].copy()
+            out['grad_sample_%d:%s' % (t, k)] = v.ravel()[::stride].copy()
         run.run(grads_list)
         for k, v in tf.shim_variables().items():
             a = v.detach().numpy().ravel()
             out['var_norm_%d:%s' % (t, k)] = np.asarray(np.linalg.norm(a))
-            out['var_sample_%d:%s' % (t, k)] = a[::SAMPLE].copy()
+            out['var_sample_%d:%s' % (t, k)] = a[::stride].copy()
     return out
 
 
@@ -246,6 +248,13 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_{}.npz'.format(lt)), **ref_step_case(lt))
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep.npz'), **ref_step_cifar())
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep_k27.npz'), **ref_step_cifar(batch=8, act_k=2.7))
+    # the other shipped architecture dictionaries, parsed from the reference's scripts (one step, batch 2, sparse samples)
+    np.savez_compressed(os.path.join(HERE, 'ref_step_stl_rmb.npz'),
+                        **ref_step_cifar(batch=2, steps=1, script='my_test_stl.py', loss_type='rmb', lr_list=(2e-4, 2e-4), stride=1031))
+    np.savez_compressed(os.path.join(HERE, 'ref_step_celeba_rep.npz'),
+                        **ref_step_cifar(batch=2, steps=1, script='my_test_celebA.py', lr_list=(1e-4, 2e-4), stride=4099))
+    np.savez_compressed(os.path.join(HERE, 'ref_step_lsun_rep.npz'),
+                        **ref_step_cifar(batch=2, steps=1, script='my_test_lsun.py', lr_list=(2e-4, 1e-4), stride=4099))
 
 
 if __name__ == '__main__':

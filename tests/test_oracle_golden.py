@@ -84,15 +84,22 @@ def test_reference_fixture_families_are_complete():
         assert set(np.load(twin).files) == set(np.load(path).files), name
 
 
-@pytest.mark.parametrize('name', ['ref_step_cifar_rep.npz', 'ref_step_cifar_rep_k27.npz'])
-def test_cifar_steps_against_reference_execution(name):
-    """Two consecutive fused steps of the reference's own CIFAR architecture dictionary (my_test_cifar.py:12-38, parsed
-    from the script) executed by the reference's SNGan.__gpu_task__ / Net / SpectralNorm / GANLoss (ref_step_cifar_rep.npz):
-    losses, every gradient and every variable after each update (norm + strided sample per variable)."""
+REF_STEPS = [('ref_step_cifar_rep.npz', 'cifar'), ('ref_step_cifar_rep_k27.npz', 'cifar'), ('ref_step_stl_rmb.npz', 'stl'),
+             ('ref_step_celeba_rep.npz', 'celeba'), ('ref_step_lsun_rep.npz', 'lsun')]
+
+
+@pytest.mark.parametrize('name,arch_name', REF_STEPS, ids=[r[0] for r in REF_STEPS])
+def test_steps_against_reference_execution(name, arch_name):
+    """Consecutive fused steps of the reference's own architecture dictionaries (parsed out of my_test_cifar.py / my_test_stl.py /
+    my_test_celebA.py / my_test_lsun.py) executed by the reference's SNGan.__gpu_task__ / Net / SpectralNorm / GANLoss on
+    oracle/tfshim (tests/golden/make_reference_fixtures.py): losses, every gradient and every variable after each update
+    (norm + strided sample per variable).  The reference creates exactly the oracle's variable names (asserted at generation)."""
     z = np.load(os.path.join(GOLD, name))
-    arch = oa.cifar(act_k=float(z['act_k']))
+    arch = oa.ARCHITECTURES[arch_name](act_k=float(z['act_k']))
+    loss_type = str(z['loss_type']) if 'loss_type' in z.files else 'rep'
+    lr_list = tuple(float(v) for v in z['lr_list']) if 'lr_list' in z.files else (5e-4, 2e-4)
     B, stride = int(z['batch']), int(z['sample_stride'])
-    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=int(z['seed']))
+    m = onet.OracleSNGan(arch, loss_type, lr_list=lr_list, dtype=torch.float64, seed=int(z['seed']))
     onet.warm_spectral_norm(m, int(z['warm']))
     for t in range(int(z['steps'])):
         data, code = onet.synthetic_batch(arch, B, seed=5 + 10 * t, dtype=torch.float32)
@@ -109,5 +116,5 @@ def test_cifar_steps_against_reference_execution(name):
             for k, v in store.items():
                 # the score-layer bias gradient is analytically zero (the loss is translation invariant); Adam amplifies its
                 # round-off, so that one variable is compared with an absolute tolerance of one learning-rate step
-                atol = 1e-3 if k.endswith('l8_s/bias/bias') else 1e-10
+                atol = 1e-3 if k.endswith('_s/bias/bias') else 1e-10
                 assert np.allclose(v.detach().numpy().ravel()[::stride], z['var_sample_%d:%s' % (t, k)], rtol=1e-8, atol=atol), k
