@@ -18,13 +18,26 @@
  * plane pairs with fp32 accumulation: npass = 6 -> {00,01,10,02,20,11} (fp32-grade products: forward passes, whose
  * errors the MMD loss amplifies), npass = 3 -> {00,01,10} (~2^-17: input / weight gradients, linear in the operands),
  * npass = 1 -> {00} (plain bf16 speed mode).  A launch reads the first 3 / 2 / 1 planes of its operands.
+ *
+ * fp16 plane formats for the operands of FORWARD launches (`*_fmt` fields): fp16 has 11 significand bits, so TWO planes of
+ * scale * x carry 22 bits and npass = 3 is already fp32-grade (~2^-21) -- half the tensor work and two thirds of the
+ * operand bytes of the six-product bf16 mode.  MMDGAN_FMT_F16A (activations, spectral-norm vectors) stores 16 * x,
+ * MMDGAN_FMT_F16W (packed forward weights) 64 * x; the power-of-two factors keep the second plane of ordinary magnitudes in
+ * fp16's normal range and leave head-room up to |x| < 4094 / 1023 (conversions saturate, they never produce inf); the
+ * caller folds 1 / (16 * 64) into alpha_k.  The two operands of an MMA may have different formats (fp16 activations x bf16
+ * gradients in the weight-gradient GEMM).
  */
 #ifndef MMDGAN_B200_H
 #define MMDGAN_B200_H
 
 #include <stddef.h>
 
-typedef unsigned short mmdgan_bf16; /* raw bf16 bits */
+typedef unsigned short mmdgan_bf16; /* raw 16-bit plane element (bf16 bits, or fp16 bits in the MMDGAN_FMT_F16* formats) */
+#define MMDGAN_FMT_BF16 0
+#define MMDGAN_FMT_F16A 1 /* two fp16 planes of 16 * value */
+#define MMDGAN_FMT_F16W 2 /* two fp16 planes of 64 * value */
+#define MMDGAN_F16A_SCALE 16.0f
+#define MMDGAN_F16W_SCALE 64.0f
 
 #ifdef __cplusplus
 extern "C" {
@@ -46,13 +59,13 @@ int mmdgan_check_device(void);
  * Layout at the boundary.  Replaces the NCHW float32 batch contract of ReadTFRecords
  * (GeneralTools/input_func.py:837-868) and tf.concat of real + generated batches (DeepLearning/my_sngan.py:244-256):
  * the real batch is written straight into rows [0, B) of the discriminator's 2B input buffer. */
-int mmdgan_nchw_to_nhwc(const float* src, mmdgan_bf16* dst, long long dst_plane, int npl, int N, int C, int H, int W, int Cpad,
+int mmdgan_nchw_to_nhwc(const float* src, mmdgan_bf16* dst, long long dst_plane, int npl, int fmt, int N, int C, int H, int W, int Cpad,
                         void* stream);
-int mmdgan_nhwc_to_nchw(const mmdgan_bf16* src, long long src_plane, int npl, float* dst, int N, int C, int H, int W, int Cpad,
+int mmdgan_nhwc_to_nchw(const mmdgan_bf16* src, long long src_plane, int npl, int fmt, float* dst, int N, int C, int H, int W, int Cpad,
                         void* stream);
 /* fp32 [n] <-> bf16 planes [npl][n] in the same element order */
-int mmdgan_to_planes(const float* x, mmdgan_bf16* dst, long long dst_plane, int npl, long long n, void* stream);
-int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, float* out, long long n, void* stream);
+int mmdgan_to_planes(const float* x, mmdgan_bf16* dst, long long dst_plane, int npl, int fmt, long long n, void* stream);
+int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, int fmt, float* out, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Weight packing: canonical reference layouts (conv [k,k,Cin,Cout] layer_func.py:584, transposed conv
@@ -69,7 +82,7 @@ typedef struct mmdgan_pack_desc {
     const float* w;
     mmdgan_bf16* out;
     long long plane;
-    int npl, pad0;
+    int npl, fmt; /* fmt: MMDGAN_FMT_BF16 or MMDGAN_FMT_F16W */
     int mode, k, Cin, Cout, Cs, rows_pad, kpad, classes;
     int in_C, in_HW, out_C, out_HW; /* dense: NCHW-flatten <-> NHWC-flatten feature permutation (HW <= 1: identity) */
 } mmdgan_pack_desc;
@@ -103,9 +116,11 @@ typedef struct mmdgan_gemm_desc {
     long long w_plane;
     long long w_rows; /* classes * rows_pad */
     int kpad, classes;
+    int src_fmt, w_fmt; /* MMDGAN_FMT_* of src and w */
     void* dst;          /* out_mode 0: mmdgan_bf16 planes [dst_npl][rows][Cd]; out_mode 2: float [rows][Cd] */
     long long dst_plane;
     int dst_npl;        /* planes written in out_mode 0 (1..3) */
+    int dst_fmt;        /* MMDGAN_FMT_* of the planes written in out_mode 0 */
     int Hd, Wd, Cd, osy, osx, Ncols;
     float alpha_k;
     const float* sigma; /* alpha = sigma ? alpha_k / *sigma : alpha_k */
@@ -113,7 +128,7 @@ typedef struct mmdgan_gemm_desc {
     int act;            /* 0 linear, 1 lrelu(0.1), 2 relu, 3 tanh */
     const mmdgan_bf16* aux; /* planes of the layer OUTPUT a: the result is multiplied by act'(a) */
     long long aux_plane;
-    int aux_npl;
+    int aux_npl, aux_fmt;
     int aux_mode;       /* 1 lrelu', 2 relu' (sign of plane 0), 3 tanh' = 1 - a^2 (all aux_npl planes) */
     long long aux_wrap_at, aux_wrap_len;
     float* colsum;      /* [tiles_m * classes][Ncols] or null */
@@ -137,7 +152,7 @@ int mmdgan_gather_gemm_tiles(int Nimg, int Hg, int Wg);
 typedef struct mmdgan_direct_desc {
     const mmdgan_bf16* src;
     long long src_plane;
-    int src_npl, Cs;
+    int src_npl, Cs, src_fmt, dst_fmt, aux_fmt, pad0;
     int N, H, W;
     int Cin, Cout;
     const float* w;
@@ -161,8 +176,8 @@ int mmdgan_direct_conv_blocks(int N, int H, int W);
 /* out[m][n] = alpha * sum_k a[m][k] * wt[n][k] + bias[n] for N in {4,8,16,32} output columns (the critic's score layer,
  * tf.matmul at layer_func.py:909-911 with 16 outputs): fp32 CUDA-core kernel on the values reassembled from npl planes of
  * the activation a and of the packed forward operand wt */
-int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int rows, int K, const mmdgan_bf16* wt, long long w_plane,
-                           int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream);
+int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int a_fmt, int rows, int K, const mmdgan_bf16* wt,
+                           long long w_plane, int w_fmt, int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream);
 
 /* Weight gradient: W[r][(t,c)] = sum_p P[p][r] * G[g(p,t)][c] (filter gradients of the ops above and the
  * d(sigma)/dW term of SpectralNorm, GeneralTools/math_func.py:661-672).  out: [splits][Cp][TH*TW*Cs]. */
@@ -178,6 +193,7 @@ typedef struct mmdgan_wgrad_desc {
     int splits;
     float* out;
     int bn, npass;      /* bn 64, 128 or 256; npass 3 or 1 */
+    int p_fmt, g_fmt;   /* MMDGAN_FMT_* of plain / g; the partial tiles carry the product of the two format scales */
 } mmdgan_wgrad_desc;
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream);
 
@@ -185,6 +201,7 @@ int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream);
  * dots (optional, [mmdgan_wgrad_reduce_blocks()] doubles) receives per-block partial <G, W>. */
 typedef struct mmdgan_wred_desc {
     const float* partials;
+    float scale;  /* the summed partials are multiplied by this (1 / the format scales of the GEMM operands) */
     int splits, R, NC, Cg, Cvalid, Rvalid;
     int r_perm_C, r_perm_HW, c_perm_C, c_perm_HW; /* optional NHWC-flatten -> NCHW-flatten permutation of r / c */
     long long base, sr, st, sc;
@@ -200,7 +217,7 @@ int mmdgan_sn_grad_combine(float* g, const float* s, const double* dots, int ndo
 int mmdgan_scale_by_sigma(float* g, const float* sigma, float act_k, long long n, void* stream);
 /* sigma = ||v||, out = v / (sigma + eps) as planes: SpectralNorm._l2_norm / _l2_normalize_ (math_func.py:639-659) */
 int mmdgan_sn_normalize(const float* v, long long n, float eps, float* sigma_out, mmdgan_bf16* out, long long out_plane, int npl,
-                        void* stream);
+                        int fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Reductions of per-tile partial sums (bias gradients; deterministic order, double accumulation) */
@@ -213,7 +230,7 @@ int mmdgan_colsum_planes(const mmdgan_bf16* x, long long plane, int npl, int row
 int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                        float* invstd, float* moving_mean, float* moving_var, void* stream);
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
-                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, void* stream);
+                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, void* stream);
 int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int C, long long rows, int rows_per_block, int act, float* psum, float* psumx,
                          void* stream);

@@ -297,7 +297,9 @@ class SpectralNorm(object):
         n_out = lop.Hout * lop.Wout
         npl = K.mode_planes(npass)
         raw = lambda rows, c: torch.zeros((1, rows, c), dtype=torch.float32, device=kernel.device)
-        xp = K.new_planes(n_in if x_is_input else n_out, lop.Cs_in if x_is_input else lop.Cs_out, npl, kernel.device)
+        vp = lambda rows, c: K.new_value_planes(rows, c, npass, kernel.device)       # operand of the layer op (forward launch)
+        bp = lambda rows, c: K.new_planes(rows, c, npl, kernel.device)               # operand of the adjoint (bf16 x 6)
+        xp = (vp if x_is_input else bp)(n_in if x_is_input else n_out, lop.Cs_in if x_is_input else lop.Cs_out)
         K.nchw_to_planes(self.x, xp)
         sigma = torch.zeros(1, device=kernel.device)
         for _ in range(self.num_iter):
@@ -305,14 +307,14 @@ class SpectralNorm(object):
             if x_is_input:
                 v = raw(n_out, lop.Cs_out)
                 lop.forward(xp, 1, v, out_mode=2)
-                y = K.new_planes(n_out, lop.Cs_out, npl, kernel.device)
+                y = bp(n_out, lop.Cs_out)
                 K.sn_normalize(v, v.numel(), y, sigma_out=sigma, eps=FLAGS.EPSI)
                 w = raw(n_in, lop.Cs_in)
-                lop.dgrad(y, 1, w, out_mode=2, npass=lop.fwd_npass)
+                lop.dgrad(y, 1, w, out_mode=2, npass=lop.adj_npass)
             else:
                 v = raw(n_in, lop.Cs_in)
-                lop.dgrad(xp, 1, v, out_mode=2, npass=lop.fwd_npass)
-                y = K.new_planes(n_in, lop.Cs_in, npl, kernel.device)
+                lop.dgrad(xp, 1, v, out_mode=2, npass=lop.adj_npass)
+                y = vp(n_in, lop.Cs_in)
                 K.sn_normalize(v, v.numel(), y, sigma_out=sigma, eps=FLAGS.EPSI)
                 w = raw(n_out, lop.Cs_out)
                 lop.forward(y, 1, w, out_mode=2)

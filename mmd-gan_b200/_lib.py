@@ -29,11 +29,11 @@ class GemmDesc(C.Structure):
         ('Nimg', C.c_int), ('Hs', C.c_int), ('Ws', C.c_int), ('Cs', C.c_int),
         ('Hg', C.c_int), ('Wg', C.c_int), ('sy', C.c_int), ('sx', C.c_int), ('TH', C.c_int), ('TW', C.c_int),
         ('w', C.c_void_p), ('w_plane', C.c_longlong), ('w_rows', C.c_longlong),
-        ('kpad', C.c_int), ('classes', C.c_int),
-        ('dst', C.c_void_p), ('dst_plane', C.c_longlong), ('dst_npl', C.c_int),
+        ('kpad', C.c_int), ('classes', C.c_int), ('src_fmt', C.c_int), ('w_fmt', C.c_int),
+        ('dst', C.c_void_p), ('dst_plane', C.c_longlong), ('dst_npl', C.c_int), ('dst_fmt', C.c_int),
         ('Hd', C.c_int), ('Wd', C.c_int), ('Cd', C.c_int), ('osy', C.c_int), ('osx', C.c_int), ('Ncols', C.c_int),
         ('alpha_k', C.c_float), ('sigma', C.c_void_p), ('bias', C.c_void_p), ('act', C.c_int),
-        ('aux', C.c_void_p), ('aux_plane', C.c_longlong), ('aux_npl', C.c_int), ('aux_mode', C.c_int), ('aux_wrap_at', C.c_longlong), ('aux_wrap_len', C.c_longlong),
+        ('aux', C.c_void_p), ('aux_plane', C.c_longlong), ('aux_npl', C.c_int), ('aux_fmt', C.c_int), ('aux_mode', C.c_int), ('aux_wrap_at', C.c_longlong), ('aux_wrap_len', C.c_longlong),
         ('colsum', C.c_void_p), ('colsumsq', C.c_void_p), ('colsum_rows', C.c_longlong),
         ('out_mode', C.c_int), ('bn', C.c_int), ('npass', C.c_int), ('cta_pair', C.c_int),
         ('cls', GemmClass * 4)]
@@ -46,12 +46,13 @@ class WgradDesc(C.Structure):
         ('Nimg', C.c_int), ('Hs', C.c_int), ('Ws', C.c_int), ('Cs', C.c_int),
         ('Hg', C.c_int), ('Wg', C.c_int), ('sy', C.c_int), ('sx', C.c_int), ('TH', C.c_int), ('TW', C.c_int),
         ('oy', C.c_int), ('ox', C.c_int), ('splits', C.c_int),
-        ('out', C.c_void_p), ('bn', C.c_int), ('npass', C.c_int)]
+        ('out', C.c_void_p), ('bn', C.c_int), ('npass', C.c_int), ('p_fmt', C.c_int), ('g_fmt', C.c_int)]
 
 
 class DirectDesc(C.Structure):
     _fields_ = [
         ('src', C.c_void_p), ('src_plane', C.c_longlong), ('src_npl', C.c_int), ('Cs', C.c_int),
+        ('src_fmt', C.c_int), ('dst_fmt', C.c_int), ('aux_fmt', C.c_int), ('pad0', C.c_int),
         ('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int), ('Cout', C.c_int),
         ('w', C.c_void_p), ('w_tap', C.c_longlong), ('w_in', C.c_longlong), ('w_out', C.c_longlong), ('flip', C.c_int),
         ('dst', C.c_void_p), ('dst_plane', C.c_longlong), ('dst_npl', C.c_int), ('Cd', C.c_int), ('out_mode', C.c_int),
@@ -62,7 +63,7 @@ class DirectDesc(C.Structure):
 
 class WredDesc(C.Structure):
     _fields_ = [
-        ('partials', C.c_void_p), ('splits', C.c_int), ('R', C.c_int), ('NC', C.c_int), ('Cg', C.c_int),
+        ('partials', C.c_void_p), ('scale', C.c_float), ('splits', C.c_int), ('R', C.c_int), ('NC', C.c_int), ('Cg', C.c_int),
         ('Cvalid', C.c_int), ('Rvalid', C.c_int),
         ('r_perm_C', C.c_int), ('r_perm_HW', C.c_int), ('c_perm_C', C.c_int), ('c_perm_HW', C.c_int),
         ('base', C.c_longlong), ('sr', C.c_longlong), ('st', C.c_longlong), ('sc', C.c_longlong),
@@ -71,7 +72,7 @@ class WredDesc(C.Structure):
 
 class PackDesc(C.Structure):
     _fields_ = [
-        ('w', C.c_void_p), ('out', C.c_void_p), ('plane', C.c_longlong), ('npl', C.c_int), ('pad0', C.c_int),
+        ('w', C.c_void_p), ('out', C.c_void_p), ('plane', C.c_longlong), ('npl', C.c_int), ('fmt', C.c_int),
         ('mode', C.c_int), ('k', C.c_int), ('Cin', C.c_int), ('Cout', C.c_int), ('Cs', C.c_int),
         ('rows_pad', C.c_int), ('kpad', C.c_int), ('classes', C.c_int),
         ('in_C', C.c_int), ('in_HW', C.c_int), ('out_C', C.c_int), ('out_HW', C.c_int)]
@@ -99,14 +100,14 @@ SYMBOLS = {
     'mmdgan_last_error': (C.c_char_p, []),
     'mmdgan_version': (_I, []),
     'mmdgan_check_device': (_I, []),
-    'mmdgan_nchw_to_nhwc': (_I, [_P, _P, _LL, _I, _I, _I, _I, _I, _I, _P]),
-    'mmdgan_nhwc_to_nchw': (_I, [_P, _LL, _I, _P, _I, _I, _I, _I, _I, _P]),
-    'mmdgan_to_planes': (_I, [_P, _P, _LL, _I, _LL, _P]),
-    'mmdgan_from_planes': (_I, [_P, _LL, _I, _P, _LL, _P]),
+    'mmdgan_nchw_to_nhwc': (_I, [_P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'mmdgan_nhwc_to_nchw': (_I, [_P, _LL, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    'mmdgan_to_planes': (_I, [_P, _P, _LL, _I, _I, _LL, _P]),
+    'mmdgan_from_planes': (_I, [_P, _LL, _I, _I, _P, _LL, _P]),
     'mmdgan_pack_weights': (_I, [C.POINTER(PackDesc), _P]),
     'mmdgan_permute_features': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'mmdgan_refresh': (_I, [_P, _I, _LL, _P]),
-    'mmdgan_dense_small_fwd': (_I, [_P, _LL, _I, _I, _I, _P, _LL, _I, _I, _F, _P, _P, _P, _I, _P]),
+    'mmdgan_dense_small_fwd': (_I, [_P, _LL, _I, _I, _I, _I, _P, _LL, _I, _I, _I, _F, _P, _P, _P, _I, _P]),
     'mmdgan_direct_conv': (_I, [C.POINTER(DirectDesc), _P]),
     'mmdgan_direct_conv_blocks': (_I, [_I, _I, _I]),
     'mmdgan_gather_gemm': (_I, [C.POINTER(GemmDesc), _P]),
@@ -116,12 +117,12 @@ SYMBOLS = {
     'mmdgan_wgrad_reduce_blocks': (_I, [_LL]),
     'mmdgan_sn_grad_combine': (_I, [_P, _P, _P, _I, _P, _F, _LL, _P]),
     'mmdgan_scale_by_sigma': (_I, [_P, _P, _F, _LL, _P]),
-    'mmdgan_sn_normalize': (_I, [_P, _LL, _F, _P, _P, _LL, _I, _P]),
+    'mmdgan_sn_normalize': (_I, [_P, _LL, _F, _P, _P, _LL, _I, _I, _P]),
     'mmdgan_reduce_tiles': (_I, [_P, _I, _I, _F, _P, _P]),
     'mmdgan_colsum_small': (_I, [_P, _I, _I, _P, _P]),
     'mmdgan_colsum_planes': (_I, [_P, _LL, _I, _I, _I, _P, _P]),
     'mmdgan_bn_finalize': (_I, [_P, _P, _I, _I, _LL, _F, _F, _P, _P, _P, _P, _P]),
-    'mmdgan_bn_apply': (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _P, _LL, _I, _P]),
+    'mmdgan_bn_apply': (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _P, _LL, _I, _I, _P]),
     'mmdgan_bn_bwd_reduce': (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _P, _P, _P]),
     'mmdgan_bn_bwd_apply': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _LL, _I, _P, _LL, _I, _P]),
     'mmdgan_mmd_configure': (_I, [C.POINTER(MmdDesc), C.c_char_p, _F, _F]),

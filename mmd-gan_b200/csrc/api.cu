@@ -21,10 +21,10 @@ int direct_conv_blocks(int N, int H, int W);
 int launch_mmd(const MmdParams& p, cudaStream_t st);
 int mmd_grid_blocks(int b);
 // elementwise.cu
-int l_nchw_to_nhwc(const float*, uint16_t*, long long, int, int, int, int, int, int, cudaStream_t);
-int l_nhwc_to_nchw(const uint16_t*, long long, int, float*, int, int, int, int, int, cudaStream_t);
-int l_to_planes(const float*, uint16_t*, long long, int, long long, cudaStream_t);
-int l_from_planes(const uint16_t*, long long, int, float*, long long, cudaStream_t);
+int l_nchw_to_nhwc(const float*, uint16_t*, long long, int, int, int, int, int, int, int, cudaStream_t);
+int l_nhwc_to_nchw(const uint16_t*, long long, int, int, float*, int, int, int, int, int, cudaStream_t);
+int l_to_planes(const float*, uint16_t*, long long, int, int, long long, cudaStream_t);
+int l_from_planes(const uint16_t*, long long, int, int, float*, long long, cudaStream_t);
 int l_colsum_planes(const uint16_t*, long long, int, int, int, float*, cudaStream_t);
 int l_pack_weights(const PackParams&, cudaStream_t);
 int l_permute_features(const float*, float*, int, int, int, int, cudaStream_t);
@@ -34,9 +34,9 @@ int wgrad_reduce_blocks(long long total);
 int l_wgrad_reduce(const WredParams&, cudaStream_t);
 int l_sn_grad_combine(float*, const float*, const double*, int, const float*, float, long long, cudaStream_t);
 int l_scale_by_sigma(float*, const float*, float, long long, cudaStream_t);
-int l_sn_normalize(const float*, long long, float, float*, uint16_t*, long long, int, cudaStream_t);
+int l_sn_normalize(const float*, long long, float, float*, uint16_t*, long long, int, int, cudaStream_t);
 int l_bn_finalize(const float*, const float*, int, int, long long, float, float, float*, float*, float*, float*, cudaStream_t);
-int l_bn_apply(const float*, const float*, const float*, const float*, const float*, int, long long, int, uint16_t*, long long, int,
+int l_bn_apply(const float*, const float*, const float*, const float*, const float*, int, long long, int, uint16_t*, long long, int, int,
                cudaStream_t);
 int l_bn_bwd_reduce(const float*, const float*, const float*, const float*, const float*, const float*, int, long long, int, int,
                     float*, float*, cudaStream_t);
@@ -45,8 +45,8 @@ int l_bn_bwd_apply(const float*, const float*, const float*, const float*, const
 int l_adam(float*, float*, float*, const float*, long long, float, float, float, float, const int*, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
-int l_dense_small_fwd(const uint16_t*, long long, int, int, int, const uint16_t*, long long, int, int, float, const float*, const float*, float*,
-                      int, cudaStream_t);
+int l_dense_small_fwd(const uint16_t*, long long, int, int, int, int, const uint16_t*, long long, int, int, int, float, const float*, const float*,
+                      float*, int, cudaStream_t);
 int l_nan_flag(const float*, int, int*, cudaStream_t);
 }  // namespace mg
 
@@ -77,6 +77,7 @@ int mmdgan_version(void) { return 200; }
 
 static inline bool chan_ok(int c) { return c == 8 || c == 16 || (c > 0 && (c & 31) == 0); }
 static inline int npl_for(int npass) { return npass == 6 ? 3 : (npass == 3 ? 2 : 1); }
+static inline bool fmt_ok(int fmt, int npl) { return fmt == 0 ? (npl >= 1 && npl <= 3) : ((fmt == 1 || fmt == 2) && npl >= 1 && npl <= 2); }
 
 int mmdgan_check_device(void) {
     int dev = 0;
@@ -87,42 +88,42 @@ int mmdgan_check_device(void) {
     return MMDGAN_OK;
 }
 
-int mmdgan_nchw_to_nhwc(const float* src, mmdgan_bf16* dst, long long dst_plane, int npl, int N, int C, int H, int W, int Cpad,
+int mmdgan_nchw_to_nhwc(const float* src, mmdgan_bf16* dst, long long dst_plane, int npl, int fmt, int N, int C, int H, int W, int Cpad,
                         void* stream) {
     if (!src || !dst) return fail(MMDGAN_EINVAL, "mmdgan_nchw_to_nhwc: null pointer");
-    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || (Cpad & 3) || npl < 1 || npl > 3 || (npl > 1 && dst_plane <= 0))
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || (Cpad & 3) || !fmt_ok(fmt, npl) || (npl > 1 && dst_plane <= 0))
         return fail(MMDGAN_ESHAPE, "mmdgan_nchw_to_nhwc: bad shape");
-    return wrap(mg::l_nchw_to_nhwc(src, dst, dst_plane, npl, N, C, H, W, Cpad, S(stream)), "mmdgan_nchw_to_nhwc");
+    return wrap(mg::l_nchw_to_nhwc(src, dst, dst_plane, npl, fmt, N, C, H, W, Cpad, S(stream)), "mmdgan_nchw_to_nhwc");
 }
-int mmdgan_nhwc_to_nchw(const mmdgan_bf16* src, long long src_plane, int npl, float* dst, int N, int C, int H, int W, int Cpad,
+int mmdgan_nhwc_to_nchw(const mmdgan_bf16* src, long long src_plane, int npl, int fmt, float* dst, int N, int C, int H, int W, int Cpad,
                         void* stream) {
     if (!src || !dst) return fail(MMDGAN_EINVAL, "mmdgan_nhwc_to_nchw: null pointer");
-    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || npl < 1 || npl > 3 || (npl > 1 && src_plane <= 0))
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || !fmt_ok(fmt, npl) || (npl > 1 && src_plane <= 0))
         return fail(MMDGAN_ESHAPE, "mmdgan_nhwc_to_nchw: bad shape");
-    return wrap(mg::l_nhwc_to_nchw(src, src_plane, npl, dst, N, C, H, W, Cpad, S(stream)), "mmdgan_nhwc_to_nchw");
+    return wrap(mg::l_nhwc_to_nchw(src, src_plane, npl, fmt, dst, N, C, H, W, Cpad, S(stream)), "mmdgan_nhwc_to_nchw");
 }
-int mmdgan_to_planes(const float* x, mmdgan_bf16* dst, long long dst_plane, int npl, long long n, void* stream) {
+int mmdgan_to_planes(const float* x, mmdgan_bf16* dst, long long dst_plane, int npl, int fmt, long long n, void* stream) {
     if (!x || !dst) return fail(MMDGAN_EINVAL, "mmdgan_to_planes: null pointer");
-    if (npl < 1 || npl > 3 || (npl > 1 && dst_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_to_planes: bad plane layout");
+    if (!fmt_ok(fmt, npl) || (npl > 1 && dst_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_to_planes: bad plane layout");
     if (n <= 0) return MMDGAN_OK;
-    return wrap(mg::l_to_planes(x, dst, dst_plane, npl, n, S(stream)), "mmdgan_to_planes");
+    return wrap(mg::l_to_planes(x, dst, dst_plane, npl, fmt, n, S(stream)), "mmdgan_to_planes");
 }
-int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, float* out, long long n, void* stream) {
+int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, int fmt, float* out, long long n, void* stream) {
     if (!src || !out) return fail(MMDGAN_EINVAL, "mmdgan_from_planes: null pointer");
-    if (npl < 1 || npl > 3 || (npl > 1 && src_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_from_planes: bad plane layout");
+    if (!fmt_ok(fmt, npl) || (npl > 1 && src_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_from_planes: bad plane layout");
     if (n <= 0) return MMDGAN_OK;
-    return wrap(mg::l_from_planes(src, src_plane, npl, out, n, S(stream)), "mmdgan_from_planes");
+    return wrap(mg::l_from_planes(src, src_plane, npl, fmt, out, n, S(stream)), "mmdgan_from_planes");
 }
 
 int mmdgan_pack_weights(const mmdgan_pack_desc* d, void* stream) {
     if (!d || !d->w || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: null pointer");
     if (d->mode < 0 || d->mode > 6) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: unknown mode %d", d->mode);
-    if (d->npl < 1 || d->npl > 3 || (d->npl > 1 && d->plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_pack_weights: bad plane layout");
+    if ((d->fmt != 0 && d->fmt != 2) || !fmt_ok(d->fmt, d->npl) || (d->npl > 1 && d->plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_pack_weights: bad plane layout");
     if (d->rows_pad <= 0 || d->kpad <= 0 || (d->kpad & 31) || d->classes < 1 || d->classes > 4 || !chan_ok(d->Cs))
         return fail(MMDGAN_ESHAPE, "mmdgan_pack_weights: bad padded shape rows_pad=%d kpad=%d classes=%d Cs=%d", d->rows_pad, d->kpad,
                     d->classes, d->Cs);
     mg::PackParams p;
-    p.w = d->w; p.out = d->out; p.plane = d->plane; p.npl = d->npl; p.pad0 = 0; p.mode = d->mode; p.k = d->k; p.Cin = d->Cin; p.Cout = d->Cout; p.Cs = d->Cs;
+    p.w = d->w; p.out = d->out; p.plane = d->plane; p.npl = d->npl; p.fmt = d->fmt; p.mode = d->mode; p.k = d->k; p.Cin = d->Cin; p.Cout = d->Cout; p.Cs = d->Cs;
     p.rows_pad = d->rows_pad; p.kpad = d->kpad; p.classes = d->classes;
     p.in_C = d->in_C; p.in_HW = d->in_HW; p.out_C = d->out_C; p.out_HW = d->out_HW;
     return wrap(mg::l_pack_weights(p, S(stream)), "mmdgan_pack_weights");
@@ -151,11 +152,13 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     if (d->Ncols <= 0 || (d->Ncols & 3) || d->Cd < d->Ncols || (d->Cd & 3)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad output columns");
     if (!al16(d->src) || !al16(d->dst) || !al16(d->w) || (d->src_plane & 7) || (d->dst_plane & 7) || (d->w_plane & 7))
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: pointers / plane offsets must be 16-byte aligned");
+    if (d->src_fmt < 0 || d->src_fmt > 2 || d->w_fmt < 0 || d->w_fmt > 2 || (d->npass == 6 && (d->src_fmt || d->w_fmt)))
+        return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass 6 is the bf16 three-plane mode; fp16 plane operands use npass 3 or 1");
     if (d->npass > 1 && (d->src_plane <= 0 || d->w_plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: npass %d needs %d operand planes", d->npass, npl_for(d->npass));
     if (d->out_mode != 0 && d->out_mode != 2) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bad out_mode");
-    if (d->out_mode == 0 && (d->dst_npl < 1 || d->dst_npl > 3 || (d->dst_npl > 1 && d->dst_plane <= 0)))
+    if (d->out_mode == 0 && (!fmt_ok(d->dst_fmt, d->dst_npl) || (d->dst_npl > 1 && d->dst_plane <= 0)))
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad destination plane layout");
-    if (d->aux && (d->aux_npl < 1 || d->aux_npl > 3 || (d->aux_npl > 1 && d->aux_plane <= 0) || !al16(d->aux)))
+    if (d->aux && (!fmt_ok(d->aux_fmt, d->aux_npl) || (d->aux_npl > 1 && d->aux_plane <= 0) || !al16(d->aux)))
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad aux plane layout");
     if (d->cta_pair && d->bn != 64 && d->bn != 128 && d->bn != 256) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: cta_pair needs bn 64, 128 or 256");
     if (d->npass == 6 && d->bn == 256 && !d->cta_pair) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass 6 with bn 256 needs cta_pair");
@@ -163,12 +166,12 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     if (M > 2000000000ll) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: too many rows");
     mg::ConvGemmParams p;
     memset(&p, 0, sizeof(p));
-    p.src = d->src; p.src_plane = d->src_plane; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
+    p.src = d->src; p.src_plane = d->src_plane; p.src_fmt = d->src_fmt; p.w_fmt = d->w_fmt; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
     p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.TH = d->TH; p.TW = d->TW;
     p.M = static_cast<int>(M); p.ksteps = d->kpad / 32;
-    p.dst = d->dst; p.dst_plane = d->dst_plane; p.dst_npl = d->dst_npl; p.Hd = d->Hd; p.Wd = d->Wd; p.Cd = d->Cd; p.osy = d->osy; p.osx = d->osx;
+    p.dst = d->dst; p.dst_plane = d->dst_plane; p.dst_npl = d->dst_npl; p.dst_fmt = d->dst_fmt; p.Hd = d->Hd; p.Wd = d->Wd; p.Cd = d->Cd; p.osy = d->osy; p.osx = d->osx;
     p.Ncols = d->Ncols; p.alpha_k = d->alpha_k; p.sigma = d->sigma; p.bias = d->bias; p.act = d->act;
-    p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_mode = d->aux_mode;
+    p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_fmt = d->aux_fmt; p.aux_mode = d->aux_mode;
     p.aux_wrap_at = d->aux_wrap_at > 0 ? d->aux_wrap_at : (1ll << 62); p.aux_wrap_len = d->aux_wrap_len;
     p.colsum = d->colsum; p.colsumsq = d->colsumsq; p.colsum_rows = d->colsum_rows > 0 ? d->colsum_rows : (1ll << 62);
     p.out_mode = d->out_mode; p.err = nullptr;
@@ -193,16 +196,17 @@ int mmdgan_direct_conv(const mmdgan_direct_desc* d, void* stream) {
     const bool sl = d->Cin >= 1 && d->Cin <= 4 && d->Cout > 0 && d->Cout % 16 == 0 && d->Cout <= 128 && d->Cd >= d->Cout;
     if (!ls && !sl) return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: needs <= 4 channels on one side and a multiple of 16 (<= 128) on the other");
     if (sl && (d->aux || d->colsum)) return fail(MMDGAN_EINVAL, "mmdgan_direct_conv: aux / colsum need Cout <= 4");
-    if (d->src_npl < 1 || d->src_npl > 3 || (d->src_npl > 1 && d->src_plane <= 0) || (d->src_plane & 7) || !al16(d->src) || !al16(d->dst))
+    if (!fmt_ok(d->src_fmt, d->src_npl) || (d->src_npl > 1 && d->src_plane <= 0) || (d->src_plane & 7) || !al16(d->src) || !al16(d->dst))
         return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: bad source plane layout");
     if (d->out_mode != 0 && d->out_mode != 2) return fail(MMDGAN_EINVAL, "mmdgan_direct_conv: bad out_mode");
-    if (d->out_mode == 0 && (d->dst_npl < 1 || d->dst_npl > 3 || (d->dst_npl > 1 && d->dst_plane <= 0)))
+    if (d->out_mode == 0 && (!fmt_ok(d->dst_fmt, d->dst_npl) || (d->dst_npl > 1 && d->dst_plane <= 0)))
         return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: bad destination plane layout");
-    if (d->aux && (d->aux_npl < 1 || d->aux_npl > 3 || (d->aux_npl > 1 && d->aux_plane <= 0)))
+    if (d->aux && (!fmt_ok(d->aux_fmt, d->aux_npl) || (d->aux_npl > 1 && d->aux_plane <= 0)))
         return fail(MMDGAN_ESHAPE, "mmdgan_direct_conv: bad aux plane layout");
     mg::DirectConvParams p;
     memset(&p, 0, sizeof(p));
-    p.src = d->src; p.src_plane = d->src_plane; p.src_npl = d->src_npl; p.Cs = d->Cs; p.N = d->N; p.H = d->H; p.W = d->W;
+    p.src = d->src; p.src_plane = d->src_plane; p.src_npl = d->src_npl; p.Cs = d->Cs; p.src_fmt = d->src_fmt; p.dst_fmt = d->dst_fmt;
+    p.aux_fmt = d->aux_fmt; p.N = d->N; p.H = d->H; p.W = d->W;
     p.Cin = d->Cin; p.Cout = d->Cout; p.w = d->w; p.w_tap = d->w_tap; p.w_in = d->w_in; p.w_out = d->w_out; p.flip = d->flip;
     p.dst = d->dst; p.dst_plane = d->dst_plane; p.dst_npl = d->dst_npl; p.Cd = d->Cd; p.out_mode = d->out_mode;
     p.alpha_k = d->alpha_k; p.sigma = d->sigma; p.bias = d->bias; p.act = d->act;
@@ -219,10 +223,11 @@ int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream) {
     if (d->P != static_cast<long long>(d->Nimg) * d->Hg * d->Wg) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: P != Nimg*Hg*Wg");
     if (!al16(d->plain) || !al16(d->g) || !al16(d->out) || (d->plain_plane & 7) || (d->g_plane & 7))
         return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: pointers / plane offsets must be 16-byte aligned");
+    if (d->p_fmt < 0 || d->p_fmt > 2 || d->g_fmt < 0 || d->g_fmt > 2) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: bad plane format");
     if (d->npass == 3 && (d->plain_plane <= 0 || d->g_plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: npass 3 needs two operand planes");
     mg::WgradParams p;
     memset(&p, 0, sizeof(p));
-    p.g = d->g; p.g_plane = d->g_plane; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
+    p.g = d->g; p.g_plane = d->g_plane; p.p_fmt = d->p_fmt; p.g_fmt = d->g_fmt; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
     p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.TH = d->TH; p.TW = d->TW; p.oy = d->oy; p.ox = d->ox;
     p.P = d->P;
     long long per = (d->P + d->splits - 1) / d->splits;
@@ -237,7 +242,7 @@ int mmdgan_wgrad_reduce(const mmdgan_wred_desc* d, void* stream) {
     if (!d || !d->partials || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_reduce: null pointer");
     if (d->splits <= 0 || d->R <= 0 || d->NC <= 0 || d->Cg <= 0 || d->NC % d->Cg) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_reduce: bad shape");
     mg::WredParams p;
-    p.partials = d->partials; p.splits = d->splits; p.R = d->R; p.NC = d->NC; p.Cg = d->Cg; p.Cvalid = d->Cvalid;
+    p.partials = d->partials; p.scale = d->scale != 0.f ? d->scale : 1.f; p.splits = d->splits; p.R = d->R; p.NC = d->NC; p.Cg = d->Cg; p.Cvalid = d->Cvalid;
     p.Rvalid = d->Rvalid; p.r_perm_C = d->r_perm_C; p.r_perm_HW = d->r_perm_HW; p.c_perm_C = d->c_perm_C; p.c_perm_HW = d->c_perm_HW;
     p.base = d->base; p.sr = d->sr; p.st = d->st; p.sc = d->sc; p.w = d->w; p.out = d->out; p.dots = d->dots;
     return wrap(mg::l_wgrad_reduce(p, S(stream)), "mmdgan_wgrad_reduce");
@@ -252,10 +257,10 @@ int mmdgan_scale_by_sigma(float* g, const float* sigma, float act_k, long long n
     return wrap(mg::l_scale_by_sigma(g, sigma, act_k, n, S(stream)), "mmdgan_scale_by_sigma");
 }
 int mmdgan_sn_normalize(const float* v, long long n, float eps, float* sigma_out, mmdgan_bf16* out, long long out_plane, int npl,
-                        void* stream) {
+                        int fmt, void* stream) {
     if (!v || !out) return fail(MMDGAN_EINVAL, "mmdgan_sn_normalize: null pointer");
-    if (n <= 0 || npl < 1 || npl > 3 || (npl > 1 && out_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_sn_normalize: bad shape");
-    return wrap(mg::l_sn_normalize(v, n, eps, sigma_out, out, out_plane, npl, S(stream)), "mmdgan_sn_normalize");
+    if (n <= 0 || !fmt_ok(fmt, npl) || (npl > 1 && out_plane < n)) return fail(MMDGAN_ESHAPE, "mmdgan_sn_normalize: bad shape");
+    return wrap(mg::l_sn_normalize(v, n, eps, sigma_out, out, out_plane, npl, fmt, S(stream)), "mmdgan_sn_normalize");
 }
 int mmdgan_reduce_tiles(const float* partials, int T, int C, float scale, float* out, void* stream) {
     if (!partials || !out) return fail(MMDGAN_EINVAL, "mmdgan_reduce_tiles: null pointer");
@@ -278,11 +283,11 @@ int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long l
     return wrap(mg::l_bn_finalize(psum, psq, T, C, rows, eps, momentum, mean, invstd, moving_mean, moving_var, S(stream)), "mmdgan_bn_finalize");
 }
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
-                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, void* stream) {
+                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, void* stream) {
     if (!z || !mean || !invstd || !gamma || !beta || !out) return fail(MMDGAN_EINVAL, "mmdgan_bn_apply: null pointer");
-    if (C <= 0 || (C & 3) || total <= 0 || total % C || npl < 1 || npl > 3 || (npl > 1 && out_plane < total))
+    if (C <= 0 || (C & 3) || total <= 0 || total % C || !fmt_ok(fmt, npl) || (npl > 1 && out_plane < total))
         return fail(MMDGAN_ESHAPE, "mmdgan_bn_apply: bad shape");
-    return wrap(mg::l_bn_apply(z, mean, invstd, gamma, beta, C, total, act, out, out_plane, npl, S(stream)), "mmdgan_bn_apply");
+    return wrap(mg::l_bn_apply(z, mean, invstd, gamma, beta, C, total, act, out, out_plane, npl, fmt, S(stream)), "mmdgan_bn_apply");
 }
 int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int C, long long rows, int rows_per_block, int act, float* psum, float* psumx,
@@ -369,13 +374,13 @@ int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long m
     static_assert(sizeof(mmdgan_refresh_job) == sizeof(mg::RefreshJob), "job layout");
     return wrap(mg::l_refresh(reinterpret_cast<const mg::RefreshJob*>(jobs_device), njobs, max_elems, S(stream)), "mmdgan_refresh");
 }
-int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int rows, int K, const mmdgan_bf16* wt, long long w_plane,
-                           int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream) {
+int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int a_fmt, int rows, int K, const mmdgan_bf16* wt,
+                           long long w_plane, int w_fmt, int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream) {
     if (!a || !wt || !out) return fail(MMDGAN_EINVAL, "mmdgan_dense_small_fwd: null pointer");
     if (rows <= 0 || K <= 0 || (K & 3) || kpad < K || (kpad & 3) || ldo < N) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad shape");
-    if (npl < 1 || npl > 3 || (npl > 1 && (a_plane <= 0 || w_plane <= 0))) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad plane layout");
+    if (!fmt_ok(a_fmt, npl) || !fmt_ok(w_fmt, npl) || (npl > 1 && (a_plane <= 0 || w_plane <= 0))) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad plane layout");
     if (N != 8 && N != 16 && N != 32) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: N must be 8/16/32");
-    return wrap(mg::l_dense_small_fwd(a, a_plane, npl, rows, K, wt, w_plane, kpad, N, alpha_k, sigma, bias, out, ldo, S(stream)), "mmdgan_dense_small_fwd");
+    return wrap(mg::l_dense_small_fwd(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, N, alpha_k, sigma, bias, out, ldo, S(stream)), "mmdgan_dense_small_fwd");
 }
 
 int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float beta1, float beta2, float eps,

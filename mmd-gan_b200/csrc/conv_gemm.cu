@@ -323,7 +323,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
       }
     } else {
         // ======================= MMA issuer (pair: the leader CTA issues for both) =======================
-        constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * kBM : kBM, BN, 0, 0);
+        const uint32_t idesc = idesc_f16(PAIR ? 2 * kBM : kBM, BN, 0, 0, p.src_fmt, p.w_fmt);
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
@@ -484,14 +484,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 } else if (p.aux) {
                     // tanh' = 1 - a^2 needs the value (all planes): only the 3-channel image layer, read in place
                     const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
-                    const float4 a4 = load_planes4(p.aux, p.aux_plane, p.aux_npl, arow * p.Cd + col);
+                    const float4 a4 = load_vals4(p.aux, p.aux_plane, p.aux_npl, p.aux_fmt, arow * p.Cd + col);
                     v.x *= act_grad_from_output(a4.x, 3);
                     v.y *= act_grad_from_output(a4.y, 3);
                     v.z *= act_grad_from_output(a4.z, 3);
                     v.w *= act_grad_from_output(a4.w, 3);
                 }
                 if (p.out_mode == 0)
-                    store_planes4(static_cast<bf16_t*>(p.dst) + prow * p.Cd + col, p.dst_plane, p.dst_npl, v);
+                    store_vals4(static_cast<bf16_t*>(p.dst) + prow * p.Cd + col, p.dst_plane, p.dst_npl, p.dst_fmt, v);
                 else
                     *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + prow * p.Cd + col) = v;
                 if (prow < p.colsum_rows) {

@@ -17,15 +17,16 @@ struct GemmClass {
 // k = (tap, channel); A is gathered from an NHWC activation, Bw is a K-major weight matrix read by TMA.
 // Operands are bf16 planes (tc_common.cuh); the result is written as bf16 planes or as raw fp32.
 struct ConvGemmParams {
-    const uint16_t* src;   // [planes][Nimg*Hs*Ws][Cs] bf16
+    const uint16_t* src;   // [planes][Nimg*Hs*Ws][Cs], 16-bit planes in format src_fmt
     long long src_plane;   // elements between consecutive planes
+    int src_fmt, w_fmt;    // FMT_* of the gathered operand and of the packed weights (tc_common.cuh)
     int Nimg, Hs, Ws, Cs;  // Cs in {8, 16} or a multiple of 32
     int Hg, Wg, sy, sx, TH, TW;
     int M;       // Nimg*Hg*Wg
     int ksteps;  // padded K / 32
     void* dst;   // out_mode 0: bf16 planes [dst_npl][Nimg*Hd*Wd][Cd]; out_mode 2: fp32 [Nimg*Hd*Wd][Cd]
     long long dst_plane;
-    int dst_npl;
+    int dst_npl, dst_fmt;
     int Hd, Wd, Cd, osy, osx;
     int Ncols;               // valid output columns (multiple of 4)
     float alpha_k;           // alpha = sigma ? alpha_k / *sigma : alpha_k
@@ -34,7 +35,7 @@ struct ConvGemmParams {
     int act;                 // 0 linear, 1 lrelu(0.1), 2 relu, 3 tanh
     const uint16_t* aux;     // bf16 planes [aux_npl][rows][Cd]: activation whose derivative multiplies the result, or null
     long long aux_plane;
-    int aux_npl;
+    int aux_npl, aux_fmt;
     int aux_mode;            // 1 lrelu', 2 relu' (sign of plane 0), 3 tanh' (all planes; evaluated from the layer OUTPUT)
     long long aux_wrap_at;   // destination rows >= aux_wrap_at read aux at row - aux_wrap_len
     long long aux_wrap_len;
@@ -51,8 +52,9 @@ struct ConvGemmParams {
 // W[r][(t, c)] = sum_p P[p][r] * G[g(p, t)][c]:  P plain [pixels][Cp] (TMA, MN-major), G gathered NHWC activation.
 // blockIdx.z = split of the pixel range; every split writes its own partial tile.
 struct WgradParams {
-    const uint16_t* g;     // gathered activation, bf16 planes [planes][Nimg*Hs*Ws][Cs]
+    const uint16_t* g;     // gathered activation, 16-bit planes [planes][Nimg*Hs*Ws][Cs]
     long long g_plane;
+    int p_fmt, g_fmt;      // FMT_* of the plain and of the gathered operand (may differ: fp16 activations x bf16 gradients)
     int Nimg, Hs, Ws, Cs;
     int Hg, Wg, sy, sx, TH, TW, oy, ox;   // pixel p = (img, y, x) on the plain operand's Hg x Wg grid
     long long P;           // number of plain pixels = Nimg*Hg*Wg
@@ -66,9 +68,9 @@ struct WgradParams {
 
 // direct_conv.cu: 3x3 / stride 1 / SAME convolution with <= 4 channels on one side (the image layers), NHWC
 struct DirectConvParams {
-    const uint16_t* src;     // bf16 planes [src_npl][N*H*W][Cs]
+    const uint16_t* src;     // planes [src_npl][N*H*W][Cs] in format src_fmt
     long long src_plane;
-    int src_npl, Cs;
+    int src_npl, Cs, src_fmt, dst_fmt, aux_fmt, pad0;
     int N, H, W;
     int Cin, Cout;           // real channel counts of THIS convolution (for an input gradient: Cout_layer -> Cin_layer)
     const float* w;          // canonical fp32 weights of the layer, element (tap, in, out) at tap*w_tap + in*w_in + out*w_out
@@ -114,10 +116,10 @@ struct MmdParams {
 // Packed operand: [planes][classes*rows_pad][kpad], element (class, row, col) as documented per mode.
 struct PackParams {
     const float* w;   // canonical
-    uint16_t* out;    // packed bf16 planes
+    uint16_t* out;    // packed planes
     long long plane;  // elements between planes
-    int npl;          // planes to write (3: forward operand, 2: input-gradient operand, 1: single-pass mode)
-    int pad0;
+    int npl;          // planes to write
+    int fmt;          // FMT_BF16 or FMT_F16W
     int mode;         // PACK_* enum
     int k;            // spatial kernel size
     int Cin, Cout;    // of the layer op (dense: in / out features)
@@ -137,6 +139,7 @@ struct RefreshJob {
 // column = t*Cg + c.  Also emits per-block partial <G, W> (for the spectral-norm term) when dots != null.
 struct WredParams {
     const float* partials;
+    float scale;                     // the summed partials are multiplied by this (removes the fp16 plane scale)
     int splits, R, NC, Cg, Cvalid;   // channels c < Cvalid are real (Cg may be padded)
     int Rvalid;                      // rows r < Rvalid are real (R may be padded)
     int r_perm_C, r_perm_HW, c_perm_C, c_perm_HW;  // optional NHWC-flatten -> NCHW-flatten feature permutation (HW <= 1: none)

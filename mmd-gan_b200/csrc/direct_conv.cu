@@ -35,15 +35,24 @@ __device__ __forceinline__ float d_act_grad(float a, int mode) {
     if (mode == 3) return 1.f - a * a;
     return 1.f;
 }
-__device__ __forceinline__ void load8_planes(const bf16_t* src, long long plane, int npl, long long off, float* v) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    for (int pl = 0; pl < npl; ++pl) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + pl * plane + off));
+__device__ __forceinline__ void add8(const uint4 q, int fmt, float* v) {
+    if (fmt == FMT_BF16) {
         v[0] += __uint_as_float(q.x << 16); v[1] += __uint_as_float(q.x & 0xFFFF0000u);
         v[2] += __uint_as_float(q.y << 16); v[3] += __uint_as_float(q.y & 0xFFFF0000u);
         v[4] += __uint_as_float(q.z << 16); v[5] += __uint_as_float(q.z & 0xFFFF0000u);
         v[6] += __uint_as_float(q.w << 16); v[7] += __uint_as_float(q.w & 0xFFFF0000u);
+    } else {
+        const float4 a = unpack_f16x4(make_uint2(q.x, q.y)), b = unpack_f16x4(make_uint2(q.z, q.w));
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+}
+// sum of the planes (fp16 formats: still carrying the format's scale)
+__device__ __forceinline__ void load8_planes(const bf16_t* src, long long plane, int npl, int fmt, long long off, float* v) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int pl = 0; pl < npl; ++pl) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + pl * plane + off));
+        add8(q, fmt, v);
     }
 }
 
@@ -99,13 +108,7 @@ __global__ void __launch_bounds__(256) conv3x3_ls_kernel(const DirectConvParams 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = 0.f;
 #pragma unroll
-                for (int pl = 0; pl < 3; ++pl) {      // absent planes were fetched as zeros
-                    const uint4 q = raw[k][pl];
-                    v[0] += __uint_as_float(q.x << 16); v[1] += __uint_as_float(q.x & 0xFFFF0000u);
-                    v[2] += __uint_as_float(q.y << 16); v[3] += __uint_as_float(q.y & 0xFFFF0000u);
-                    v[4] += __uint_as_float(q.z << 16); v[5] += __uint_as_float(q.z & 0xFFFF0000u);
-                    v[6] += __uint_as_float(q.w << 16); v[7] += __uint_as_float(q.w & 0xFFFF0000u);
-                }
+                for (int pl = 0; pl < 3; ++pl) add8(raw[k][pl], p.src_fmt, v);      // absent planes were fetched as zeros
                 float4* d = reinterpret_cast<float4*>(tile + (u >> 1) * PITCH + (u & 1) * 8);
                 d[0] = make_float4(v[0], v[1], v[2], v[3]);
                 d[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -131,21 +134,21 @@ __global__ void __launch_bounds__(256) conv3x3_ls_kernel(const DirectConvParams 
     // ---- epilogue: alpha, bias, activation or activation derivative, planes / raw output, column sums
     const int gy = y0 + ly, gx = x0 + lx;
     const bool ok = gy < p.H && gx < p.W;
-    const float alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
+    const float alpha = (p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k) * fmt_inv_scale(p.src_fmt);   // the staged inputs carry the source scale
     float v[4] = {acc0, acc1, acc2, acc3};
     const long long prow = static_cast<long long>(n * p.H + gy) * p.W + gx;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
         v[o] = o < p.Cout ? d_act(fmaf(v[o], alpha, p.bias ? p.bias[o] : 0.f), p.act) : 0.f;
-        if (p.aux && ok && o < p.Cout) v[o] *= d_act_grad(load_planes(p.aux, p.aux_plane, p.aux_npl, prow * p.Cd + o), p.aux_mode);
+        if (p.aux && ok && o < p.Cout) v[o] *= d_act_grad(load_val(p.aux, p.aux_plane, p.aux_npl, p.aux_fmt, prow * p.Cd + o), p.aux_mode);
         if (!ok) v[o] = 0.f;
     }
     if (ok) {
         const float4 lo = make_float4(v[0], v[1], v[2], v[3]), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.out_mode == 0) {
             bf16_t* o = static_cast<bf16_t*>(p.dst) + prow * p.Cd;
-            store_planes4(o, p.dst_plane, p.dst_npl, lo);
-            for (int c = 4; c < p.Cd; c += 4) store_planes4(o + c, p.dst_plane, p.dst_npl, z4);
+            store_vals4(o, p.dst_plane, p.dst_npl, p.dst_fmt, lo);
+            for (int c = 4; c < p.Cd; c += 4) store_vals4(o + c, p.dst_plane, p.dst_npl, p.dst_fmt, z4);
         } else {
             float* o = static_cast<float*>(p.dst) + prow * p.Cd;
             *reinterpret_cast<float4*>(o) = lo;
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) conv3x3_sl_kernel(const DirectConvParams 
         const int gy = y0 + px / kDH - 1, gx = x0 + px % kDH - 1;
         float v[8];
         if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-            load8_planes(p.src, p.src_plane, p.src_npl, (static_cast<long long>(n * p.H + gy) * p.W + gx) * p.Cs, v);
+            load8_planes(p.src, p.src_plane, p.src_npl, p.src_fmt, (static_cast<long long>(n * p.H + gy) * p.W + gx) * p.Cs, v);
         else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(256) conv3x3_sl_kernel(const DirectConvParams 
         const float4 q = *reinterpret_cast<const float4*>(tile + ((ly + tap / 3) * kDH + lx + tap % 3) * 4);
         x[tap][0] = q.x; x[tap][1] = q.y; x[tap][2] = q.z;
     }
-    const float alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
+    const float alpha = (p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k) * fmt_inv_scale(p.src_fmt);   // the staged inputs carry the source scale
     for (int co0 = 0; co0 < CO; co0 += 16) {
         float acc[16];
 #pragma unroll
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(256) conv3x3_sl_kernel(const DirectConvParams 
             v.z = d_act(fmaf(a.z, alpha, bq.z), p.act);
             v.w = d_act(fmaf(a.w, alpha, bq.w), p.act);
             const long long o = (static_cast<long long>(n * p.H + gy) * p.W + gx) * p.Cd + co0 + 4 * q;
-            if (p.out_mode == 0) store_planes4(static_cast<bf16_t*>(p.dst) + o, p.dst_plane, p.dst_npl, v);
+            if (p.out_mode == 0) store_vals4(static_cast<bf16_t*>(p.dst) + o, p.dst_plane, p.dst_npl, p.dst_fmt, v);
             else *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + o) = v;
         }
     }

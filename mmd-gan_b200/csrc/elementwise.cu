@@ -17,8 +17,8 @@ static inline int nblocks(long long n, int bs) { return static_cast<int>((n + bs
 
 // ------------------------------------------------------------------------------------------------ layout
 // src NCHW [N][C][H][W] fp32 -> dst bf16 planes [npl][N][H][W][Cp] (channels >= C zero)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16_t* __restrict__ dst, long long plane, int npl, int N, int C,
-                                    int H, int W, int Cp) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16_t* __restrict__ dst, long long plane, int npl, int fmt, int N,
+                                    int C, int H, int W, int Cp) {
     const long long total = static_cast<long long>(N) * H * W * Cp;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -29,12 +29,12 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16_t* __res
         const int h = static_cast<int>(r % H);
         const int n = static_cast<int>(r / H);
         const float v = c < C ? src[((static_cast<long long>(n) * C + c) * H + h) * W + w] : 0.f;
-        store_planes(dst + i, plane, npl, v);
+        store_val(dst + i, plane, npl, fmt, v);
     }
 }
-// src bf16 planes [npl][N][H][W][Cp] -> dst NCHW [N][C][H][W] fp32 (sum of the planes)
-__global__ void nhwc_to_nchw_kernel(const bf16_t* __restrict__ src, long long plane, int npl, float* __restrict__ dst, int N, int C, int H,
-                                    int W, int Cp) {
+// src planes [npl][N][H][W][Cp] -> dst NCHW [N][C][H][W] fp32 (the values the planes carry)
+__global__ void nhwc_to_nchw_kernel(const bf16_t* __restrict__ src, long long plane, int npl, int fmt, float* __restrict__ dst, int N, int C,
+                                    int H, int W, int Cp) {
     const long long total = static_cast<long long>(N) * C * H * W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -44,19 +44,19 @@ __global__ void nhwc_to_nchw_kernel(const bf16_t* __restrict__ src, long long pl
         r /= H;
         const int c = static_cast<int>(r % C);
         const int n = static_cast<int>(r / C);
-        dst[i] = load_planes(src, plane, npl, ((static_cast<long long>(n) * H + h) * W + w) * Cp + c);
+        dst[i] = load_val(src, plane, npl, fmt, ((static_cast<long long>(n) * H + h) * W + w) * Cp + c);
     }
 }
 // fp32 [n] -> bf16 planes [npl][n] (same element order), and back
-__global__ void to_planes_kernel(const float* __restrict__ x, bf16_t* __restrict__ dst, long long plane, int npl, long long n) {
+__global__ void to_planes_kernel(const float* __restrict__ x, bf16_t* __restrict__ dst, long long plane, int npl, int fmt, long long n) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
-        store_planes(dst + i, plane, npl, x[i]);
+        store_val(dst + i, plane, npl, fmt, x[i]);
 }
-__global__ void from_planes_kernel(const bf16_t* __restrict__ src, long long plane, int npl, float* __restrict__ out, long long n) {
+__global__ void from_planes_kernel(const bf16_t* __restrict__ src, long long plane, int npl, int fmt, float* __restrict__ out, long long n) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
-        out[i] = load_planes(src, plane, npl, i);
+        out[i] = load_val(src, plane, npl, fmt, i);
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
@@ -153,7 +153,7 @@ __device__ __forceinline__ void pack_tiles(const PackParams& p, float (*tile)[33
         for (int j = 0; j < 4; ++j) {
             const int rr = ty + 8 * j, grow = r0 + rr, col = c0 + tx;
             if (grow < rows_all && col < p.kpad)
-                store_planes(p.out + static_cast<long long>(grow) * p.kpad + col, p.plane, p.npl, tile[rr][tx]);
+                store_val(p.out + static_cast<long long>(grow) * p.kpad + col, p.plane, p.npl, p.fmt, tile[rr][tx]);
         }
         __syncthreads();
     }
@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(256) refresh_kernel(const RefreshJob* __restri
 // fp32 FFMA on the values reassembled from the bf16 planes, one block per row, warp-shuffle + shared-memory reduction.
 // The tensor-core tile would be 94 % padding here (N = 16 of 128 lanes x 8192 deep on 4 CTAs).
 template <int N, int R>
-__global__ void __launch_bounds__(256) dense_small_fwd_kernel(const bf16_t* __restrict__ a, long long a_plane, int npl, int rows, int K,
-                                                             const bf16_t* __restrict__ wt, long long w_plane, int kpad,
+__global__ void __launch_bounds__(256) dense_small_fwd_kernel(const bf16_t* __restrict__ a, long long a_plane, int npl, int a_fmt, int rows,
+                                                             int K, const bf16_t* __restrict__ wt, long long w_plane, int w_fmt, int kpad,
                                                              float alpha_k, const float* __restrict__ sigma,
                                                              const float* __restrict__ bias, float* __restrict__ out, int ldo) {
     // R rows per block share every weight load (the weights are re-read once per R rows instead of once per row)
@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(256) dense_small_fwd_kernel(const bf16_t* __re
         float4 x[R];
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            x[r] = row0 + r < rows ? load_planes4(a, a_plane, npl, static_cast<long long>(row0 + r) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[r] = row0 + r < rows ? load_vals4(a, a_plane, npl, a_fmt, static_cast<long long>(row0 + r) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-            const float4 w = load_planes4(wt, w_plane, npl, static_cast<long long>(n) * kpad + k);
+            const float4 w = load_vals4(wt, w_plane, npl, w_fmt, static_cast<long long>(n) * kpad + k);
 #pragma unroll
             for (int r = 0; r < R; ++r)
                 acc[r][n] = fmaf(x[r].x, w.x, fmaf(x[r].y, w.y, fmaf(x[r].z, w.z, fmaf(x[r].w, w.w, acc[r][n]))));
@@ -300,7 +300,7 @@ __global__ void wgrad_reduce_kernel(const WredParams p) {
             s3 += p.partials[static_cast<long long>(z + 3) * total + i];
         }
         for (; z < p.splits; ++z) s0 += p.partials[static_cast<long long>(z) * total + i];
-        const float s = (s0 + s1) + (s2 + s3);
+        const float s = ((s0 + s1) + (s2 + s3)) * p.scale;
         const long long ci = p.base + perm_feature(r, p.r_perm_C, p.r_perm_HW) * p.sr + t * p.st +
                              perm_feature(c, p.c_perm_C, p.c_perm_HW) * p.sc;
         p.out[ci] = s;
@@ -346,7 +346,7 @@ __global__ void scale_by_sigma_kernel(float* __restrict__ g, const float* __rest
 // ------------------------------------------------------------------------------------------------ spectral norm
 // sigma = ||v||, out planes = v / (sigma + eps); one block (v has at most a few 10^4 elements)
 __global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, float eps, float* __restrict__ sigma_out,
-                                    bf16_t* __restrict__ out, long long plane, int npl) {
+                                    bf16_t* __restrict__ out, long long plane, int npl, int fmt) {
     __shared__ double red[1024];
     double s = 0.0;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) s += static_cast<double>(v[i]) * static_cast<double>(v[i]);
@@ -360,7 +360,7 @@ __global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, fl
     if (threadIdx.x == 0 && sigma_out) *sigma_out = nrm;
     const float inv = 1.0f / (nrm + eps);
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        store_planes(out + i, plane, npl, v[i] * inv);
+        store_val(out + i, plane, npl, fmt, v[i] * inv);
     }
 }
 
@@ -398,7 +398,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
 // a = act(gamma * (z - mean) * invstd + beta) -> bf16 planes; z [rows][C] raw fp32
 __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int C, long long total, int act,
-                                bf16_t* __restrict__ out, long long plane, int npl) {
+                                bf16_t* __restrict__ out, long long plane, int npl, int fmt) {
     for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
         const int c = static_cast<int>(i % C);
@@ -411,7 +411,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
         y.z = fmaf((zv.z - mu.z) * is.z, g.z, b.z);
         y.w = fmaf((zv.w - mu.w) * is.w, g.w, b.w);
         if (act == 2) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-        store_planes4(out + i, plane, npl, y);
+        store_vals4(out + i, plane, npl, fmt, y);
     }
 }
 // per-block partial sums of dy and dy*xhat per channel; dy = da * act'(bn output); block handles a row slab
@@ -560,20 +560,20 @@ static inline int grid_for(long long n) {
 }
 #define MG_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : -4)
 
-int l_nchw_to_nhwc(const float* src, bf16_t* dst, long long plane, int npl, int N, int C, int H, int W, int Cp, cudaStream_t st) {
-    nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(N) * H * W * Cp), kBS, 0, st>>>(src, dst, plane, npl, N, C, H, W, Cp);
+int l_nchw_to_nhwc(const float* src, bf16_t* dst, long long plane, int npl, int fmt, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+    nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(N) * H * W * Cp), kBS, 0, st>>>(src, dst, plane, npl, fmt, N, C, H, W, Cp);
     return MG_CHECK_LAUNCH();
 }
-int l_nhwc_to_nchw(const bf16_t* src, long long plane, int npl, float* dst, int N, int C, int H, int W, int Cp, cudaStream_t st) {
-    nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * C * H * W), kBS, 0, st>>>(src, plane, npl, dst, N, C, H, W, Cp);
+int l_nhwc_to_nchw(const bf16_t* src, long long plane, int npl, int fmt, float* dst, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+    nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * C * H * W), kBS, 0, st>>>(src, plane, npl, fmt, dst, N, C, H, W, Cp);
     return MG_CHECK_LAUNCH();
 }
-int l_to_planes(const float* x, bf16_t* dst, long long plane, int npl, long long n, cudaStream_t st) {
-    to_planes_kernel<<<grid_for(n), kBS, 0, st>>>(x, dst, plane, npl, n);
+int l_to_planes(const float* x, bf16_t* dst, long long plane, int npl, int fmt, long long n, cudaStream_t st) {
+    to_planes_kernel<<<grid_for(n), kBS, 0, st>>>(x, dst, plane, npl, fmt, n);
     return MG_CHECK_LAUNCH();
 }
-int l_from_planes(const bf16_t* src, long long plane, int npl, float* out, long long n, cudaStream_t st) {
-    from_planes_kernel<<<grid_for(n), kBS, 0, st>>>(src, plane, npl, out, n);
+int l_from_planes(const bf16_t* src, long long plane, int npl, int fmt, float* out, long long n, cudaStream_t st) {
+    from_planes_kernel<<<grid_for(n), kBS, 0, st>>>(src, plane, npl, fmt, out, n);
     return MG_CHECK_LAUNCH();
 }
 int l_colsum_planes(const bf16_t* x, long long plane, int npl, int rows, int C, float* out, cudaStream_t st) {
@@ -615,8 +615,8 @@ int l_scale_by_sigma(float* g, const float* sigma, float act_k, long long n, cud
     scale_by_sigma_kernel<<<grid_for(n), kBS, 0, st>>>(g, sigma, act_k, n);
     return MG_CHECK_LAUNCH();
 }
-int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, bf16_t* out, long long plane, int npl, cudaStream_t st) {
-    sn_normalize_kernel<<<1, 1024, 0, st>>>(v, n, eps, sigma_out, out, plane, npl);
+int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, bf16_t* out, long long plane, int npl, int fmt, cudaStream_t st) {
+    sn_normalize_kernel<<<1, 1024, 0, st>>>(v, n, eps, sigma_out, out, plane, npl, fmt);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
@@ -625,8 +625,8 @@ int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long r
     return MG_CHECK_LAUNCH();
 }
 int l_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C, long long total,
-               int act, bf16_t* out, long long plane, int npl, cudaStream_t st) {
-    bn_apply_kernel<<<grid_for(total / 4), kBS, 0, st>>>(z, mean, invstd, gamma, beta, C, total, act, out, plane, npl);
+               int act, bf16_t* out, long long plane, int npl, int fmt, cudaStream_t st) {
+    bn_apply_kernel<<<grid_for(total / 4), kBS, 0, st>>>(z, mean, invstd, gamma, beta, C, total, act, out, plane, npl, fmt);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
@@ -655,15 +655,15 @@ int l_refresh(const RefreshJob* jobs, int njobs, long long max_elems, cudaStream
     refresh_kernel<<<grid, kBS, 0, st>>>(jobs);
     return MG_CHECK_LAUNCH();
 }
-int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int rows, int K, const bf16_t* wt, long long w_plane, int kpad, int N,
-                      float alpha_k, const float* sigma, const float* bias, float* out, int ldo, cudaStream_t st) {
+int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int a_fmt, int rows, int K, const bf16_t* wt, long long w_plane, int w_fmt,
+                      int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, cudaStream_t st) {
     // four rows per block while that still fills the machine, else one
     const bool quad = false;    // measured (ncu, 512 rows): four rows per block leaves 128 blocks for 148 SMs and is 2x slower than one row per block
     const int blocks = quad ? (rows + 3) / 4 : rows;
-    if (N == 16 && quad) dense_small_fwd_kernel<16, 4><<<blocks, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 16) dense_small_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 8) dense_small_fwd_kernel<8, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 32) dense_small_fwd_kernel<32, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, rows, K, wt, w_plane, kpad, alpha_k, sigma, bias, out, ldo);
+    if (N == 16 && quad) dense_small_fwd_kernel<16, 4><<<blocks, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 16) dense_small_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 8) dense_small_fwd_kernel<8, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
+    else if (N == 32) dense_small_fwd_kernel<32, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
     else return -1;
     return MG_CHECK_LAUNCH();
 }

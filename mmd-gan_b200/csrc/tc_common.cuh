@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -159,12 +160,29 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
 }
-// Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation: c_format F32 (1) at [4,6), a/b format
-// BF16 (1) at [7,10)/[10,13), a/b major (0 = K-major, 1 = MN-major) at 15/16, N>>3 at [17,23), M>>4 at [24,29).
+// Plane formats (the `*_fmt` fields of the parameter blocks; include/mmdgan_b200.h):
+//   FMT_BF16  bf16 planes of the value itself (three planes = fp32, two = 16 significand bits): gradients, and every
+//             operand of the bf16-only modes
+//   FMT_F16A  two fp16 planes of 16 x value   (activations / spectral-norm vectors feeding FORWARD launches)
+//   FMT_F16W  two fp16 planes of 64 x value   (packed forward weights)
+// fp16 carries 11 significand bits, so two planes hold 22 bits and the three products {00, 01, 10} are fp32-grade
+// (~2^-21) at the FULL 16-bit tensor rate -- where bf16 needs three planes and six products.  The power-of-two scales keep
+// the second plane of ordinary magnitudes in fp16's normal range (|x| >= 2^-7 for activations, 2^-9 for weights; smaller
+// elements keep an ABSOLUTE accuracy of 2^-29 / 2^-31) and leave head-room up to |x| < 4094 / 1023; conversions
+// saturate instead of overflowing.  The products carry the factor 16 * 64, removed through the epilogue alpha.
+enum { FMT_BF16 = 0, FMT_F16A = 1, FMT_F16W = 2 };
+__host__ __device__ constexpr float fmt_scale(int fmt) { return fmt == FMT_F16A ? 16.f : (fmt == FMT_F16W ? 64.f : 1.f); }
+__host__ __device__ constexpr float fmt_inv_scale(int fmt) { return fmt == FMT_F16A ? 0.0625f : (fmt == FMT_F16W ? 0.015625f : 1.f); }
+
+// Instruction descriptor for kind::f16 with fp32 accumulation: c_format F32 (1) at [4,6), a/b format (0 = F16, 1 = BF16) at
+// [7,10)/[10,13) -- the two operands may differ --, a/b major (0 = K-major, 1 = MN-major) at 15/16, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
+    return (1u << 4) | ((a_fmt == FMT_BF16 ? 1u : 0u) << 7) | ((b_fmt == FMT_BF16 ? 1u : 0u) << 10) |
+           (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
-           (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
-           (static_cast<uint32_t>(M >> 4) << 24);
+    return idesc_f16(M, N, a_mn_major, b_mn_major, FMT_BF16, FMT_BF16);
 }
 
 // ---------------------------------------------------------------- bf16 planes
@@ -224,6 +242,71 @@ __device__ __forceinline__ float4 load_planes4(const bf16_t* src, long long plan
         v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
     }
     return v;
+}
+
+// ---------------------------------------------------------------- fp16 planes / format-generic access
+__device__ __forceinline__ uint16_t f2h_sat(float x) {
+    uint16_t h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+}
+__device__ __forceinline__ float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+// xs = scale * x (exact); p0 = fp16(xs), p1 = fp16(xs - p0)
+__device__ __forceinline__ void f16_split2(float xs, uint16_t& p0, uint16_t& p1) {
+    p0 = f2h_sat(xs);
+    p1 = f2h_sat(xs - h2f(p0));
+}
+__device__ __forceinline__ uint32_t pack16(uint16_t a, uint16_t b) { return a | (static_cast<uint32_t>(b) << 16); }
+// four consecutive elements in either format (npl planes; fp16 formats have at most two)
+__device__ __forceinline__ void store_vals4(bf16_t* dst, long long plane, int npl, int fmt, float4 v) {
+    if (fmt == FMT_BF16) {
+        store_planes4(dst, plane, npl, v);
+        return;
+    }
+    const float sc = fmt_scale(fmt);
+    uint16_t a[4], b[4];
+    f16_split2(v.x * sc, a[0], b[0]);
+    f16_split2(v.y * sc, a[1], b[1]);
+    f16_split2(v.z * sc, a[2], b[2]);
+    f16_split2(v.w * sc, a[3], b[3]);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack16(a[0], a[1]), pack16(a[2], a[3]));
+    if (npl > 1) *reinterpret_cast<uint2*>(dst + plane) = make_uint2(pack16(b[0], b[1]), pack16(b[2], b[3]));
+}
+__device__ __forceinline__ void store_val(bf16_t* dst, long long plane, int npl, int fmt, float x) {
+    if (fmt == FMT_BF16) {
+        store_planes(dst, plane, npl, x);
+        return;
+    }
+    uint16_t a, b;
+    f16_split2(x * fmt_scale(fmt), a, b);
+    dst[0] = a;
+    if (npl > 1) dst[plane] = b;
+}
+__device__ __forceinline__ float4 unpack_f16x4(uint2 u) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// the VALUE (already unscaled) carried by the planes
+__device__ __forceinline__ float4 load_vals4(const bf16_t* src, long long plane, int npl, int fmt, long long i) {
+    if (fmt == FMT_BF16) return load_planes4(src, plane, npl, i);
+    float4 v = unpack_f16x4(*reinterpret_cast<const uint2*>(src + i));
+    if (npl > 1) {
+        const float4 m = unpack_f16x4(*reinterpret_cast<const uint2*>(src + i + plane));
+        v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
+    }
+    const float is = fmt_inv_scale(fmt);
+    return make_float4(v.x * is, v.y * is, v.z * is, v.w * is);
+}
+__device__ __forceinline__ float load_val(const bf16_t* src, long long plane, int npl, int fmt, long long i) {
+    if (fmt == FMT_BF16) return load_planes(src, plane, npl, i);
+    float v = h2f(src[i]);
+    if (npl > 1) v += h2f(src[i + plane]);
+    return v * fmt_inv_scale(fmt);
+}
+// planes a launch reads from an operand in `fmt` for `npass` plane-pair products
+__host__ __device__ constexpr int fmt_planes(int fmt, int npass) {
+    return fmt == FMT_BF16 ? (npass == 6 ? 3 : (npass == 3 ? 2 : 1)) : (npass >= 3 ? 2 : 1);
 }
 
 }  // namespace mg

@@ -184,7 +184,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
         }
     } else {
         // ======================= MMA issuer =======================
-        constexpr uint32_t idesc = idesc_bf16(kWBM, BN, 1, 1);
+        const uint32_t idesc = idesc_f16(kWBM, BN, 1, 1, p.p_fmt, p.g_fmt);
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;

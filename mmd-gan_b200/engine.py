@@ -235,10 +235,14 @@ class NetRuntime(object):
             L.sn_x_is_input = x_is_input
             r_x, c_x = (L.rows_in, L.Cs_in) if x_is_input else (L.rows_out, L.Cs_out)
             r_y, c_y = (L.rows_out, L.Cs_out) if x_is_input else (L.rows_in, L.Cs_in)
+            # the vector that enters the layer op is a forward operand (value planes: fp16 in the parity mode); the one that
+            # enters the adjoint meets the bf16 input-gradient weights with six plane pairs
             npl = K.mode_planes(npass)
-            L.sn_x = K.new_planes(r_x, c_x, npl, dev)
-            L.sn_xnew = K.new_planes(r_x, c_x, npl, dev)
-            L.sn_y = K.new_planes(r_y, c_y, npl, dev)
+            vp = lambda r, c: K.new_value_planes(r, c, npass, dev)
+            bp = lambda r, c: K.new_planes(r, c, npl, dev)
+            L.sn_x = (vp if x_is_input else bp)(r_x, c_x)
+            L.sn_xnew = (vp if x_is_input else bp)(r_x, c_x)
+            L.sn_y = (bp if x_is_input else vp)(r_y, c_y)
             L.sn_v = torch.zeros((1, r_y, c_y), dtype=torch.float32, device=dev)
             L.sn_w = torch.zeros((1, r_x, c_x), dtype=torch.float32, device=dev)
             L.sigma = torch.ones(1, dtype=torch.float32, device=dev)
@@ -326,14 +330,15 @@ class SNGanEngine(object):
     def _alloc_buffers(self):
         B, dev, npass = self.B, self.device, self.npass
         HW = self.height * self.width
-        nv, ng = K.mode_planes(npass, 'value'), K.mode_planes(npass, 'grad')
-        self.code_planes = K.new_planes(B, K.pad_c(self.code_size), nv, dev)
+        ng = K.mode_planes(npass, 'grad')
+        vplanes = lambda rows, c: K.new_value_planes(rows, c, npass, dev)
+        self.code_planes = vplanes(B, K.pad_c(self.code_size))
         # D input: rows [0, B*HW) real, [B*HW, 2B*HW) generated
-        self.x_all = K.new_planes(2 * B * HW, K.pad_c(self.channels), nv, dev)
+        self.x_all = vplanes(2 * B * HW, K.pad_c(self.channels))
         # generator activations
         for i, L in enumerate(self.G.layers):
             last = i == len(self.G.layers) - 1
-            L.a = self.x_all[:, B * HW:, :] if last else K.new_planes(B * L.rows_out, L.Cs_out, nv, dev)
+            L.a = self.x_all[:, B * HW:, :] if last else vplanes(B * L.rows_out, L.Cs_out)
             L.dz = K.new_planes(B * L.rows_out, L.Cs_out, ng, dev)
         # discriminator activations (2B) and gradients (3B virtual batch)
         for i, L in enumerate(self.D.layers):
@@ -342,7 +347,7 @@ class SNGanEngine(object):
                 L.a = torch.zeros((1, 2 * B, L.Cs_out), dtype=torch.float32, device=dev)      # scores, fp32
                 L.raw_out = True
             else:
-                L.a = K.new_planes(2 * B * L.rows_out, L.Cs_out, nv, dev)
+                L.a = vplanes(2 * B * L.rows_out, L.Cs_out)
             L.dz = K.new_planes(3 * B * L.rows_out, L.Cs_out, ng, dev)
             if last:
                 L.dz_f32 = torch.zeros((3 * B, L.Cs_out), dtype=torch.float32, device=dev)    # score gradients from the MMD kernel
@@ -399,11 +404,11 @@ class SNGanEngine(object):
         if L.sn_x_is_input:
             lop.forward(L.sn_x, 1, L.sn_v, out_mode=2)
             K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
-            lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2, npass=lop.fwd_npass)
+            lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2, npass=lop.adj_npass)
             K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
             lop.wgrad(L.sn_x, L.sn_y, 1, L.sn_parts, L.sn_splits)
         else:
-            lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2, npass=lop.fwd_npass)    # the adjoint is the FORWARD operator here: sigma = ||F^T x||
+            lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2, npass=lop.adj_npass)    # the adjoint is the FORWARD operator here: sigma = ||F^T x||
             K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
             lop.forward(L.sn_y, 1, L.sn_w, out_mode=2)
             K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)

@@ -1,9 +1,12 @@
 """Torch-tensor level wrappers over the C ABI (include/mmdgan_b200.h): device memory and streams come from PyTorch,
 every computation is a kernel of libmmdgan_b200.so.  No fallback: a missing library or a non-CUDA tensor raises.
 
-GEMM operands ("planes") are [npl, rows, C] bfloat16 CUDA tensors, NHWC row order: an fp32 value is the sum of its
-planes (3 planes = the fp32 value, 2 planes = 16 significand bits; include/mmdgan_b200.h).  Forward launches multiply six
-plane pairs (fp32-grade), input- and weight-gradient launches three.
+GEMM operands ("planes") are [npl, rows, C] 16-bit CUDA tensors, NHWC row order (include/mmdgan_b200.h):
+  torch.bfloat16  the sum of the planes is the value (3 planes = fp32, 2 planes = 16 significand bits): gradients, and
+                  every operand when F16_FORWARD is off;
+  torch.float16   two planes whose sum is 16 x value (activations) or 64 x value (packed forward weights): the operands of
+                  forward launches -- 22 significand bits, so three plane-pair products are fp32-grade.
+Gradient launches multiply three bf16 plane pairs; the weight-gradient GEMM mixes fp16 activations with bf16 gradients.
 """
 import ctypes as C
 import math
@@ -22,6 +25,9 @@ GEMM_PAIR = True        # use the CTA-pair (cta_group::2) gather-GEMM where the 
 GEMM_PAIR_MIN_TILES = int(os.environ.get('MMDGAN_PAIR_MIN_TILES', '256'))   # 128 x 128 output units; below that the single-CTA kernel fills the machine better
 GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
 WGRAD_BN_MAX = int(os.environ.get('MMDGAN_WGRAD_BN', '256'))   # widest N tile of the weight-gradient GEMM (64 / 128 / 256)
+FMT_BF16, FMT_F16A, FMT_F16W = 0, 1, 2
+FMT_SCALE = {FMT_BF16: 1.0, FMT_F16A: 16.0, FMT_F16W: 64.0}
+F16_FORWARD = int(os.environ.get('MMDGAN_F16_FORWARD', '1'))   # parity mode: forward operands as two fp16 planes (3 products) instead of three bf16 planes (6)
 PAIR_BN256_AUX = int(os.environ.get('MMDGAN_BN256_AUX', '0'))   # experiment knob: 256-wide pair tiles for input gradients with N = 256
 PAIR_N64 = int(os.environ.get('MMDGAN_PAIR_N64', '0'))   # CTA-pair tiles for N = 64 layers: measured slower (0.36 vs 0.33 ms), off
 DIRECT_CONV = True     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
@@ -44,8 +50,8 @@ def stream():
 def _ptr(t):
     if t is None:
         return None
-    if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32, torch.bfloat16):
-        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32/bfloat16 tensor, got {} on {}'.format(t.dtype, t.device))
+    if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32, torch.bfloat16, torch.float16):
+        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32/bfloat16/float16 tensor, got {} on {}'.format(t.dtype, t.device))
     if t.dim() == 3:
         # planes [npl, rows, C]: every plane must be a dense [rows, C] block; the plane stride is free (row views)
         if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
@@ -60,9 +66,19 @@ def plane_stride(t):
 
 
 def _planes(t):
-    if t.dtype != torch.bfloat16 or t.dim() != 3:
-        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected bfloat16 planes [npl, rows, C], got {} {}'.format(t.dtype, tuple(t.shape)))
+    if t.dtype not in (torch.bfloat16, torch.float16) or t.dim() != 3 or (t.dtype == torch.float16 and t.shape[0] > 2):
+        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected bfloat16 / float16 planes [npl, rows, C], got {} {}'.format(t.dtype, tuple(t.shape)))
     return t
+
+
+def fmt_of(t, role='act'):
+    """Plane format of a tensor: bf16 planes, or fp16 planes scaled for activations ('act') / packed weights ('w')."""
+    return FMT_BF16 if t.dtype == torch.bfloat16 else (FMT_F16W if role == 'w' else FMT_F16A)
+
+
+def fmt_need(fmt, npass):
+    """Planes a launch with `npass` plane-pair products reads from an operand in format `fmt`."""
+    return (3 if npass == 6 else (2 if npass == 3 else 1)) if fmt == FMT_BF16 else (2 if npass >= 3 else 1)
 
 
 def pad_c(c):
@@ -72,7 +88,7 @@ def pad_c(c):
 
 def fwd_passes(npass):
     """Engine precision mode (3 = parity, 1 = single bf16 pass) -> plane-pair products of a forward launch."""
-    return 6 if npass == 3 else 1
+    return (3 if F16_FORWARD else 6) if npass == 3 else 1
 
 
 def mode_planes(npass, kind='value'):
@@ -91,8 +107,16 @@ def pick_bn(ncols, lo=16, hi=128):
     return bn
 
 
-def new_planes(rows, c, npl=3, device='cuda'):
-    return torch.zeros((npl, rows, c), dtype=torch.bfloat16, device=device)
+def new_planes(rows, c, npl=3, device='cuda', fmt=FMT_BF16):
+    return torch.zeros((npl, rows, c), dtype=torch.bfloat16 if fmt == FMT_BF16 else torch.float16, device=device)
+
+
+def new_value_planes(rows, c, npass=3, device='cuda'):
+    """Planes of a VALUE that feeds forward launches: two fp16 planes in the parity mode (three bf16 planes with
+    F16_FORWARD off, one bf16 plane in the single-pass mode)."""
+    if npass == 3 and F16_FORWARD:
+        return new_planes(rows, c, 2, device, FMT_F16A)
+    return new_planes(rows, c, mode_planes(npass, 'value'), device)
 
 
 # ------------------------------------------------------------------------------------------------ layout
@@ -104,14 +128,14 @@ def nchw_to_planes(x, dst):
     else:
         n, c, h, w = x.shape
     _planes(dst)
-    check(lib().mmdgan_nchw_to_nhwc(_ptr(x), _ptr(dst), plane_stride(dst), dst.shape[0], n, c, h, w, dst.shape[2], stream()))
+    check(lib().mmdgan_nchw_to_nhwc(_ptr(x), _ptr(dst), plane_stride(dst), dst.shape[0], fmt_of(dst), n, c, h, w, dst.shape[2], stream()))
     return dst
 
 
 def planes_to_nchw(src, n, c, h, w):
     _planes(src)
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
-    check(lib().mmdgan_nhwc_to_nchw(_ptr(src), plane_stride(src), src.shape[0], _ptr(out), n, c, h, w, src.shape[2], stream()))
+    check(lib().mmdgan_nhwc_to_nchw(_ptr(src), plane_stride(src), src.shape[0], fmt_of(src), _ptr(out), n, c, h, w, src.shape[2], stream()))
     return out
 
 
@@ -120,15 +144,15 @@ def to_planes(x, dst):
     _planes(dst)
     n = dst.shape[1] * dst.shape[2]
     assert x.numel() == n and x.dtype == torch.float32
-    check(lib().mmdgan_to_planes(_ptr(x), _ptr(dst), plane_stride(dst), dst.shape[0], n, stream()))
+    check(lib().mmdgan_to_planes(_ptr(x), _ptr(dst), plane_stride(dst), dst.shape[0], fmt_of(dst), n, stream()))
     return dst
 
 
-def planes_value(src):
-    """bf16 planes [npl, rows, C] -> the fp32 values [rows, C] they carry."""
+def planes_value(src, role='act'):
+    """planes [npl, rows, C] -> the fp32 values [rows, C] they carry."""
     _planes(src)
     out = torch.empty(src.shape[1:], dtype=torch.float32, device=src.device)
-    check(lib().mmdgan_from_planes(_ptr(src), plane_stride(src), src.shape[0], _ptr(out), out.numel(), stream()))
+    check(lib().mmdgan_from_planes(_ptr(src), plane_stride(src), src.shape[0], fmt_of(src, role), _ptr(out), out.numel(), stream()))
     return out
 
 
@@ -146,7 +170,9 @@ class LinearOp(object):
         self.op, self.k, self.s, self.npass, self.device = op, kernel, strides, npass, device
         self.fwd_npass = fwd_passes(npass)          # forward-type launches (errors amplified by the loss): 6 plane pairs
         self.bwd_npass = 3 if npass == 3 else 1     # gradient launches (linear in the operands): 3 plane pairs
-        self.npl = mode_planes(npass)               # planes of the packed operands
+        self.adj_npass = 6 if npass == 3 else 1     # the adjoint used as a FORWARD operator (spectral norm): bf16 x 6
+        self.npl = mode_planes(npass)               # planes of the bf16 packed operands
+        self._wg_scale = 1.0
         if op == 'd':
             self.Cin, self.Cout = in_shape[0], out_shape[0]
             self.Hin = self.Win = self.Hout = self.Wout = 1
@@ -191,7 +217,10 @@ class LinearOp(object):
             g['bn'] = pick_bn(g['ncols'])
             g['rows_pad'] = round_up(g['ncols'], g['bn'])
             g['kpad'] = round_up(g['taps'] * g['Cs'], 32)
-            g['w'] = torch.zeros((self.npl, g['classes'] * g['rows_pad'], g['kpad']), dtype=torch.bfloat16, device=device)
+            if g is self.f and npass == 3 and F16_FORWARD:
+                g['w'] = new_planes(g['classes'] * g['rows_pad'], g['kpad'], 2, device, FMT_F16W)
+            else:
+                g['w'] = new_planes(g['classes'] * g['rows_pad'], g['kpad'], self.npl, device)
         # ---- weight-gradient orientation: the small channel count goes to the N side
         if op == 'd':
             self.w_swapped = self.Cs_out < 32
@@ -211,7 +240,7 @@ class LinearOp(object):
         for g in (self.f, self.d):
             d = PackDesc()
             d.w, d.out = _ptr(w_canon), _ptr(g['w'])
-            d.plane, d.npl = plane_stride(g['w']), g['w'].shape[0]
+            d.plane, d.npl, d.fmt = plane_stride(g['w']), g['w'].shape[0], fmt_of(g['w'], 'w')
             d.mode, d.k, d.Cin, d.Cout, d.Cs = g['mode'], self.k, self.Cin, self.Cout, g['Cs']
             d.rows_pad, d.kpad, d.classes = g['rows_pad'], g['kpad'], g['classes']
             if self.op == 'd':
@@ -228,7 +257,7 @@ class LinearOp(object):
         for g in (self.f, self.d):
             d = PackDesc()
             d.w, d.out = _ptr(w_canon), _ptr(g['w'])
-            d.plane, d.npl = plane_stride(g['w']), g['w'].shape[0]
+            d.plane, d.npl, d.fmt = plane_stride(g['w']), g['w'].shape[0], fmt_of(g['w'], 'w')
             d.mode, d.k, d.Cin, d.Cout, d.Cs = g['mode'], self.k, self.Cin, self.Cout, g['Cs']
             d.rows_pad, d.kpad, d.classes = g['rows_pad'], g['kpad'], g['classes']
             if self.op == 'd':
@@ -244,6 +273,7 @@ class LinearOp(object):
         d = GemmDesc()
         _planes(src)
         d.src, d.src_plane = _ptr(src), plane_stride(src)
+        d.src_fmt, d.w_fmt = fmt_of(src), fmt_of(g['w'], 'w')
         d.Nimg = nimg
         (d.Hs, d.Ws, d.Hg, d.Wg, d.sy, d.sx, d.TH, d.TW, d.Hd, d.Wd, d.osy, d.osx) = geom['dims']
         d.Cs = g['Cs']
@@ -252,15 +282,16 @@ class LinearOp(object):
         d.w, d.w_plane, d.w_rows = _ptr(g['w']), plane_stride(g['w']), g['w'].shape[1]
         d.kpad, d.classes = g['kpad'], g['classes']
         d.dst, d.dst_plane, d.dst_npl = _ptr(dst), plane_stride(dst), dst.shape[0]
-        if (out_mode == 0) != (dst.dtype == torch.bfloat16) or (out_mode == 2 and (dst.dtype != torch.float32 or dst.shape[0] != 1)):
+        d.dst_fmt = fmt_of(dst) if out_mode == 0 else 0
+        if (out_mode == 0) != (dst.dtype in (torch.bfloat16, torch.float16)) or (out_mode == 2 and (dst.dtype != torch.float32 or dst.shape[0] != 1)):
             raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 writes bf16 planes, out_mode 2 one fp32 plane')
         d.Cd, d.Ncols = dst.shape[2], g['ncols']
         assert dst.shape[1] >= nimg * d.Hd * d.Wd and dst.shape[2] >= g['ncols']
-        d.alpha_k = float(alpha_k)
+        d.alpha_k = float(alpha_k) / (FMT_SCALE[d.src_fmt] * FMT_SCALE[d.w_fmt])     # the products carry the operands' plane scales
         d.sigma, d.bias, d.act = _ptr(sigma), _ptr(bias), act
         if aux is not None:
             _planes(aux)
-            d.aux, d.aux_plane, d.aux_npl = _ptr(aux), plane_stride(aux), aux.shape[0]
+            d.aux, d.aux_plane, d.aux_npl, d.aux_fmt = _ptr(aux), plane_stride(aux), aux.shape[0], fmt_of(aux)
         d.aux_mode = aux_mode
         d.aux_wrap_at, d.aux_wrap_len = aux_wrap if aux_wrap else (0, 0)
         d.colsum, d.colsumsq, d.colsum_rows = _ptr(colsum), _ptr(colsumsq), colsum_rows
@@ -282,9 +313,9 @@ class LinearOp(object):
                 bn = 256
         d.cta_pair = pair
         d.out_mode, d.bn, d.npass = out_mode, bn, npass
-        need = 3 if npass == 6 else (2 if npass == 3 else 1)
-        if src.shape[0] < need or g['w'].shape[0] < need:
-            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'npass {} needs {} operand planes'.format(npass, need))
+        if src.shape[0] < fmt_need(d.src_fmt, npass) or g['w'].shape[0] < fmt_need(d.w_fmt, npass) or (npass == 6 and (d.src_fmt or d.w_fmt)):
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'npass {} does not fit operands {} x {} / {} x {}'.format(
+                npass, src.shape[0], src.dtype, g['w'].shape[0], g['w'].dtype))
         for i, (oy, ox, ooy, oox) in enumerate(geom['cls']):
             d.cls[i].oy, d.cls[i].ox, d.cls[i].ooy, d.cls[i].oox = oy, ox, ooy, oox
             d.cls[i].wrow = i * g['rows_pad']
@@ -316,6 +347,7 @@ class LinearOp(object):
         d = DirectDesc()
         _planes(src)
         d.src, d.src_plane, d.src_npl, d.Cs = _ptr(src), plane_stride(src), src.shape[0], src.shape[2]
+        d.src_fmt = fmt_of(src)
         d.N, d.H, d.W = nimg, self.Hin, self.Win
         ci, co = self.Cin, self.Cout
         d.w, d.w_tap = _ptr(self.w_canon), ci * co
@@ -324,13 +356,14 @@ class LinearOp(object):
         else:
             d.Cin, d.Cout, d.w_in, d.w_out, d.flip = co, ci, 1, co, 1
         assert src.shape[1] >= nimg * self.Hin * self.Win and dst.shape[1] >= nimg * self.Hin * self.Win
-        if (out_mode == 0) != (dst.dtype == torch.bfloat16):
-            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 writes bf16 planes, out_mode 2 one fp32 plane')
+        if (out_mode == 0) != (dst.dtype in (torch.bfloat16, torch.float16)):
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 writes planes, out_mode 2 one fp32 plane')
         d.dst, d.dst_plane, d.dst_npl, d.Cd, d.out_mode = _ptr(dst), plane_stride(dst), dst.shape[0], dst.shape[2], out_mode
+        d.dst_fmt = fmt_of(dst) if out_mode == 0 else 0
         d.alpha_k, d.sigma, d.bias, d.act = float(alpha_k), _ptr(sigma), _ptr(bias), act
         if aux is not None:
             _planes(aux)
-            d.aux, d.aux_plane, d.aux_npl = _ptr(aux), plane_stride(aux), aux.shape[0]
+            d.aux, d.aux_plane, d.aux_npl, d.aux_fmt = _ptr(aux), plane_stride(aux), aux.shape[0], fmt_of(aux)
         d.aux_mode = aux_mode
         d.colsum = _ptr(colsum)
         check(lib().mmdgan_direct_conv(C.byref(d), stream()))
@@ -351,9 +384,9 @@ class LinearOp(object):
             # a handful of output columns (the critic scores): fp32 CUDA-core kernel instead of a 94 %-padded MMA tile
             _planes(src)
             npl = min(src.shape[0], self.f['w'].shape[0])
-            check(lib().mmdgan_dense_small_fwd(_ptr(src), plane_stride(src), npl, nimg, self.Cs_in, _ptr(self.f['w']),
-                                               plane_stride(self.f['w']), self.f['kpad'], self.Cs_out, float(alpha_k), _ptr(sigma),
-                                               _ptr(bias), _ptr(dst), dst.shape[2], stream()))
+            check(lib().mmdgan_dense_small_fwd(_ptr(src), plane_stride(src), npl, fmt_of(src), nimg, self.Cs_in, _ptr(self.f['w']),
+                                               plane_stride(self.f['w']), fmt_of(self.f['w'], 'w'), self.f['kpad'], self.Cs_out,
+                                               float(alpha_k), _ptr(sigma), _ptr(bias), _ptr(dst), dst.shape[2], stream()))
             return
         if self.direct_f and colsum is None and colsumsq is None and self.w_canon is not None:
             return self._direct(True, src, nimg, dst, sigma, alpha_k, bias, act, None, 0, None, out_mode)
@@ -418,6 +451,8 @@ class LinearOp(object):
         d.Cs = gath.shape[2]
         assert d.TH * d.TW * d.Cs == NC
         d.splits, d.out, d.bn, d.npass = splits, _ptr(partials), bn, self.bwd_npass
+        d.p_fmt, d.g_fmt = fmt_of(plain), fmt_of(gath)
+        self._wg_scale = 1.0 / (FMT_SCALE[d.p_fmt] * FMT_SCALE[d.g_fmt])      # removed by the wgrad_reduce that follows
         assert partials.numel() >= splits * R * NC
         check(lib().mmdgan_wgrad_gemm(C.byref(d), stream()))
         return splits
@@ -427,6 +462,7 @@ class LinearOp(object):
         R, NC, _, _, _ = self.wgrad_plan(nimg)
         d = WredDesc()
         d.partials, d.splits, d.R, d.NC = _ptr(partials), splits, R, NC
+        d.scale = self._wg_scale
         d.r_perm_C = d.c_perm_C = 1
         d.r_perm_HW = d.c_perm_HW = 1
         ci, co = self.Cin, self.Cout
@@ -467,6 +503,7 @@ def colsum_small(x, rows, Cc, out):
 def colsum_planes(x, rows, Cc, out):
     # column sums of the values carried by bf16 planes [npl, rows, C]
     _planes(x)
+    assert x.dtype == torch.bfloat16, 'gradients are bf16 planes'
     check(lib().mmdgan_colsum_planes(_ptr(x), plane_stride(x), x.shape[0], rows, Cc, _ptr(out), stream()))
 
 
@@ -494,7 +531,7 @@ def refresh(blob, njobs, max_elems):
 
 def sn_normalize(v, n, out, sigma_out=None, eps=1e-10):
     _planes(out)
-    check(lib().mmdgan_sn_normalize(_ptr(v), n, float(eps), _ptr(sigma_out), _ptr(out), plane_stride(out), out.shape[0], stream()))
+    check(lib().mmdgan_sn_normalize(_ptr(v), n, float(eps), _ptr(sigma_out), _ptr(out), plane_stride(out), out.shape[0], fmt_of(out), stream()))
 
 
 def sn_grad_combine(g, s, dots, ndots, sigma, act_k, n):
@@ -517,7 +554,7 @@ def bn_finalize(psum, psq, T, Cc, rows, mean, invstd, moving_mean=None, moving_v
 def bn_apply(z, mean, invstd, gamma, beta, Cc, total, act, out):
     _planes(out)
     check(lib().mmdgan_bn_apply(_ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), Cc, total, act, _ptr(out),
-                                plane_stride(out), out.shape[0], stream()))
+                                plane_stride(out), out.shape[0], fmt_of(out), stream()))
 
 
 def bn_bwd_reduce(da, z, mean, invstd, gamma, beta, Cc, rows, rows_per_block, act, psum, psumx):
@@ -527,6 +564,7 @@ def bn_bwd_reduce(da, z, mean, invstd, gamma, beta, Cc, rows, rows_per_block, ac
 
 def bn_bwd_apply(da, z, mean, invstd, gamma, beta, dbeta, dgamma, Cc, rows, act, out):
     _planes(out)
+    assert out.dtype == torch.bfloat16, 'gradients are bf16 planes'
     check(lib().mmdgan_bn_bwd_apply(_ptr(da), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(dbeta),
                                     _ptr(dgamma), Cc, rows, act, _ptr(out), plane_stride(out), out.shape[0], stream()))
 

@@ -21,7 +21,7 @@ for case in CASES:
     wd = w.float().to(cuda).contiguous(); lop.pack(wd)
     hin_, hout_ = (1, 1) if op == 'd' else (in_shape[1], out_shape[1])
     nv, ng = K.mode_planes(npass, 'value'), K.mode_planes(npass, 'grad')
-    xs = K.new_planes(n * hin_ * hin_, lop.Cs_in, nv); K.nchw_to_planes(x.float().to(cuda).contiguous(), xs)
+    xs = K.new_value_planes(n * hin_ * hin_, lop.Cs_in, npass); K.nchw_to_planes(x.float().to(cuda).contiguous(), xs)
     yr = torch.zeros((1, n * hout_ * hout_, lop.Cs_out), device=cuda)
     lop.forward(xs, n, yr, out_mode=2)
     y2 = raw_to_nchw(yr, n, cout, hout_, hout_).reshape(y_ref.shape)

@@ -73,7 +73,7 @@ def test_linear_op_fwd_dgrad_wgrad(cuda, case, npass):
     lop.pack(wd)
     hin_, hout_ = (1, 1) if op == 'd' else (in_shape[1], out_shape[1])
     nv, ng = K.mode_planes(npass, 'value'), K.mode_planes(npass, 'grad')
-    xs = K.new_planes(n * hin_ * hin_, lop.Cs_in, nv)
+    xs = K.new_value_planes(n * hin_ * hin_, lop.Cs_in, npass)      # forward operand: two fp16 planes in the parity mode
     K.nchw_to_planes(x.float().to(cuda).contiguous(), xs)
     # ---- forward with fused alpha, bias, lrelu
     ys = K.new_planes(n * hout_ * hout_, lop.Cs_out, 3)
@@ -196,9 +196,9 @@ def test_direct_conv_image_layers(cuda):
     lop = K.LinearOp('c', [64, h, h], [3, h, h], 3, 1)
     assert lop.direct_f == 'ls'
     lop.pack(w.float().to(cuda).contiguous())
-    xs = K.new_planes(2 * h * h, 64, 3)
+    xs = K.new_value_planes(2 * h * h, 64)
     K.nchw_to_planes(x.float().to(cuda).contiguous(), xs)
-    ys = K.new_planes(2 * h * h, 8, 3)
+    ys = K.new_value_planes(2 * h * h, 8)
     bias_d = torch.zeros(8, device=cuda)
     bias_d[:3] = bias.float().to(cuda)
     lop.forward(xs, 2, ys, bias=bias_d, act=3, out_mode=0)
@@ -306,6 +306,9 @@ def test_bn_adam_sn_elementwise(cuda):
     K.bn_apply(zd, mean_d, inv_d, gd, bd, Cc, rows * Cc, 2, a)
     assert rel(K.planes_value(a), a_ref.detach()) < 1e-5
     assert rel(K.planes_value(a[:2]), a_ref.detach()) < 2e-5      # two planes carry 16 significand bits
+    a16 = K.new_value_planes(rows, Cc)                            # two fp16 planes of 16 x value: 22 significand bits
+    K.bn_apply(zd, mean_d, inv_d, gd, bd, Cc, rows * Cc, 2, a16)
+    assert a16.dtype == torch.float16 and rel(K.planes_value(a16), a_ref.detach()) < 1e-6
     rpb = 32
     nb = (rows + rpb - 1) // rpb
     p1, p2 = torch.zeros(nb, Cc, device=cuda), torch.zeros(nb, Cc, device=cuda)
@@ -341,3 +344,12 @@ def test_bn_adam_sn_elementwise(cuda):
     K.to_planes(xf, pl)
     assert float(((K.planes_value(pl).flatten() - xf).abs() / xf.abs()).max()) <= 2.0 ** -23
     assert float(((K.planes_value(pl[:2]).flatten() - xf).abs() / xf.abs()).max()) <= 2.0 ** -16
+    # fp16 planes: 22 bits for ordinary magnitudes, absolute accuracy 2^-29 below, saturation (never inf) beyond +-4094
+    xa = torch.cat([torch.randn(4000, generator=g) * 3.0, torch.tensor([1e-6, -3e-9, 4000.0, -4090.0, 1e9, -1e9, 0.0, 1e-30])]).to(cuda)
+    ph = K.new_value_planes(1, xa.numel())
+    K.to_planes(xa, ph)
+    back = K.planes_value(ph).flatten()
+    assert bool(torch.isfinite(back).all())
+    ok = xa.abs() < 4094
+    assert float(((back - xa).abs()[ok] - (xa.abs()[ok] * 2.0 ** -21 + 2.0 ** -29)).max()) <= 0.0
+    assert float(back[-4]) > 4000.0 and float(back[-3]) < -4000.0          # saturated, finite
