@@ -24,8 +24,8 @@
  * operand bytes of the six-product bf16 mode.  MMDGAN_FMT_F16A (activations, spectral-norm vectors) stores 16 * x,
  * MMDGAN_FMT_F16W (packed forward weights) 64 * x; the power-of-two factors keep the second plane of ordinary magnitudes in
  * fp16's normal range and leave head-room up to |x| < 4094 / 1023 (conversions saturate, they never produce inf); the
- * caller folds 1 / (16 * 64) into alpha_k.  The two operands of an MMA may have different formats (fp16 activations x bf16
- * gradients in the weight-gradient GEMM).
+ * caller folds 1 / (16 * 64) into alpha_k.  The two operands of one MMA must have the SAME element type (measured: an fp16 x
+ * bf16 descriptor is an illegal instruction), so gradient launches read bf16 planes only (mmdgan_convert_planes).
  */
 #ifndef MMDGAN_B200_H
 #define MMDGAN_B200_H
@@ -66,6 +66,10 @@ int mmdgan_nhwc_to_nchw(const mmdgan_bf16* src, long long src_plane, int npl, in
 /* fp32 [n] <-> bf16 planes [npl][n] in the same element order */
 int mmdgan_to_planes(const float* x, mmdgan_bf16* dst, long long dst_plane, int npl, int fmt, long long n, void* stream);
 int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, int fmt, float* out, long long n, void* stream);
+/* planes in one format -> planes in another (the weight-gradient GEMM needs bf16 planes of the fp16 forward activations:
+ * an MMA cannot mix an fp16 operand with a bf16 one) */
+int mmdgan_convert_planes(const mmdgan_bf16* src, long long src_plane, int src_npl, int src_fmt, mmdgan_bf16* dst, long long dst_plane,
+                          int dst_npl, int dst_fmt, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Weight packing: canonical reference layouts (conv [k,k,Cin,Cout] layer_func.py:584, transposed conv
@@ -193,7 +197,7 @@ typedef struct mmdgan_wgrad_desc {
     int splits;
     float* out;
     int bn, npass;      /* bn 64, 128 or 256; npass 3 or 1 */
-    int p_fmt, g_fmt;   /* MMDGAN_FMT_* of plain / g; the partial tiles carry the product of the two format scales */
+    int p_fmt, g_fmt;   /* MMDGAN_FMT_* of plain / g (both bf16, or both fp16); the partial tiles carry the product of the format scales */
 } mmdgan_wgrad_desc;
 int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream);
 

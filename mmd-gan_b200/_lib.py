@@ -104,6 +104,7 @@ SYMBOLS = {
     'mmdgan_nhwc_to_nchw': (_I, [_P, _LL, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     'mmdgan_to_planes': (_I, [_P, _P, _LL, _I, _I, _LL, _P]),
     'mmdgan_from_planes': (_I, [_P, _LL, _I, _I, _P, _LL, _P]),
+    'mmdgan_convert_planes': (_I, [_P, _LL, _I, _I, _P, _LL, _I, _I, _LL, _P]),
     'mmdgan_pack_weights': (_I, [C.POINTER(PackDesc), _P]),
     'mmdgan_permute_features': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'mmdgan_refresh': (_I, [_P, _I, _LL, _P]),

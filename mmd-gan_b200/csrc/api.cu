@@ -26,6 +26,7 @@ int l_nhwc_to_nchw(const uint16_t*, long long, int, int, float*, int, int, int, 
 int l_to_planes(const float*, uint16_t*, long long, int, int, long long, cudaStream_t);
 int l_from_planes(const uint16_t*, long long, int, int, float*, long long, cudaStream_t);
 int l_colsum_planes(const uint16_t*, long long, int, int, int, float*, cudaStream_t);
+int l_convert_planes(const uint16_t*, long long, int, int, uint16_t*, long long, int, int, long long, cudaStream_t);
 int l_pack_weights(const PackParams&, cudaStream_t);
 int l_permute_features(const float*, float*, int, int, int, int, cudaStream_t);
 int l_reduce_tiles(const float*, int, int, float, float*, cudaStream_t);
@@ -115,6 +116,16 @@ int mmdgan_from_planes(const mmdgan_bf16* src, long long src_plane, int npl, int
     return wrap(mg::l_from_planes(src, src_plane, npl, fmt, out, n, S(stream)), "mmdgan_from_planes");
 }
 
+int mmdgan_convert_planes(const mmdgan_bf16* src, long long src_plane, int src_npl, int src_fmt, mmdgan_bf16* dst, long long dst_plane,
+                          int dst_npl, int dst_fmt, long long n, void* stream) {
+    if (!src || !dst) return fail(MMDGAN_EINVAL, "mmdgan_convert_planes: null pointer");
+    if (!fmt_ok(src_fmt, src_npl) || !fmt_ok(dst_fmt, dst_npl) || (src_npl > 1 && src_plane < n) || (dst_npl > 1 && dst_plane < n) || (n & 3) ||
+        !al16(src) || !al16(dst) || (src_plane & 3) || (dst_plane & 3))
+        return fail(MMDGAN_ESHAPE, "mmdgan_convert_planes: bad plane layout");
+    if (n <= 0) return MMDGAN_OK;
+    return wrap(mg::l_convert_planes(src, src_plane, src_npl, src_fmt, dst, dst_plane, dst_npl, dst_fmt, n, S(stream)), "mmdgan_convert_planes");
+}
+
 int mmdgan_pack_weights(const mmdgan_pack_desc* d, void* stream) {
     if (!d || !d->w || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: null pointer");
     if (d->mode < 0 || d->mode > 6) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: unknown mode %d", d->mode);
@@ -154,6 +165,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: pointers / plane offsets must be 16-byte aligned");
     if (d->src_fmt < 0 || d->src_fmt > 2 || d->w_fmt < 0 || d->w_fmt > 2 || (d->npass == 6 && (d->src_fmt || d->w_fmt)))
         return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: npass 6 is the bf16 three-plane mode; fp16 plane operands use npass 3 or 1");
+    if ((d->src_fmt == 0) != (d->w_fmt == 0)) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: both operands must be bf16 planes or both fp16 planes");
     if (d->npass > 1 && (d->src_plane <= 0 || d->w_plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: npass %d needs %d operand planes", d->npass, npl_for(d->npass));
     if (d->out_mode != 0 && d->out_mode != 2) return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bad out_mode");
     if (d->out_mode == 0 && (!fmt_ok(d->dst_fmt, d->dst_npl) || (d->dst_npl > 1 && d->dst_plane <= 0)))
@@ -223,7 +235,8 @@ int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream) {
     if (d->P != static_cast<long long>(d->Nimg) * d->Hg * d->Wg) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: P != Nimg*Hg*Wg");
     if (!al16(d->plain) || !al16(d->g) || !al16(d->out) || (d->plain_plane & 7) || (d->g_plane & 7))
         return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: pointers / plane offsets must be 16-byte aligned");
-    if (d->p_fmt < 0 || d->p_fmt > 2 || d->g_fmt < 0 || d->g_fmt > 2) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: bad plane format");
+    if (d->p_fmt < 0 || d->p_fmt > 2 || d->g_fmt < 0 || d->g_fmt > 2 || ((d->p_fmt == 0) != (d->g_fmt == 0)))
+        return fail(MMDGAN_EINVAL, "mmdgan_wgrad_gemm: both operands must be bf16 planes or both fp16 planes");
     if (d->npass == 3 && (d->plain_plane <= 0 || d->g_plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_gemm: npass 3 needs two operand planes");
     mg::WgradParams p;
     memset(&p, 0, sizeof(p));

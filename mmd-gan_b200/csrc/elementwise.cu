@@ -59,6 +59,15 @@ __global__ void from_planes_kernel(const bf16_t* __restrict__ src, long long pla
         out[i] = load_val(src, plane, npl, fmt, i);
 }
 
+// planes in one format -> planes in another (same element order), four elements per thread.  The tensor core cannot mix an
+// fp16 operand with a bf16 one, so the weight-gradient GEMM reads a bf16 re-split of the fp16 forward activations.
+__global__ void convert_planes_kernel(const bf16_t* __restrict__ src, long long sp, int snpl, int sfmt, bf16_t* __restrict__ dst,
+                                      long long dp, int dnpl, int dfmt, long long n) {
+    for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x * 4)
+        store_vals4(dst + i, dp, dnpl, dfmt, load_vals4(src, sp, snpl, sfmt, i));
+}
+
 // ------------------------------------------------------------------------------------------------ weight packing
 enum { PACK_CONV_FWD = 0, PACK_CONV_DGRAD_S1 = 1, PACK_CONV_DGRAD_S2 = 2, PACK_TC_FWD = 3, PACK_TC_DGRAD = 4,
        PACK_DENSE_FWD = 5, PACK_DENSE_DGRAD = 6 };
@@ -574,6 +583,11 @@ int l_to_planes(const float* x, bf16_t* dst, long long plane, int npl, int fmt, 
 }
 int l_from_planes(const bf16_t* src, long long plane, int npl, int fmt, float* out, long long n, cudaStream_t st) {
     from_planes_kernel<<<grid_for(n), kBS, 0, st>>>(src, plane, npl, fmt, out, n);
+    return MG_CHECK_LAUNCH();
+}
+int l_convert_planes(const bf16_t* src, long long sp, int snpl, int sfmt, bf16_t* dst, long long dp, int dnpl, int dfmt, long long n,
+                     cudaStream_t st) {
+    convert_planes_kernel<<<grid_for(n / 4), kBS, 0, st>>>(src, sp, snpl, sfmt, dst, dp, dnpl, dfmt, n);
     return MG_CHECK_LAUNCH();
 }
 int l_colsum_planes(const bf16_t* x, long long plane, int npl, int rows, int C, float* out, cudaStream_t st) {

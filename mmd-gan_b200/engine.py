@@ -243,6 +243,8 @@ class NetRuntime(object):
             L.sn_x = (vp if x_is_input else bp)(r_x, c_x)
             L.sn_xnew = (vp if x_is_input else bp)(r_x, c_x)
             L.sn_y = (bp if x_is_input else vp)(r_y, c_y)
+            # bf16 re-split of the fp16 vector for the d(sigma)/dW weight-gradient GEMM (an MMA cannot mix fp16 with bf16)
+            L.sn_b16 = K.new_planes(r_x if x_is_input else r_y, c_x if x_is_input else c_y, 2, dev)
             L.sn_v = torch.zeros((1, r_y, c_y), dtype=torch.float32, device=dev)
             L.sn_w = torch.zeros((1, r_x, c_x), dtype=torch.float32, device=dev)
             L.sigma = torch.ones(1, dtype=torch.float32, device=dev)
@@ -361,6 +363,10 @@ class SNGanEngine(object):
         gl, d0 = self.G.layers[-1], self.D.layers[0]
         gl.cs_T = d0.lop.dgrad_tiles(B)
         gl.cs = torch.zeros(gl.cs_T * d0.lop.d['ncols'], dtype=torch.float32, device=dev)
+        # bf16 re-split of a layer's fp16 input activation for its weight-gradient GEMM; one buffer: those GEMMs run in order on
+        # the gradient stream
+        acts = [self.x_all, self.code_planes] + [L.a for L in self.G.layers + self.D.layers if L.a.dtype == torch.float16]
+        self.wg_scratch = torch.zeros(2 * max(t.shape[1] * t.shape[2] for t in acts), dtype=torch.bfloat16, device=dev)
         self.tmp_vec = torch.zeros(max(max(L.Cs_out for L in self.G.layers), max(L.Cs_out for L in self.D.layers)) + 64,
                                    dtype=torch.float32, device=dev)
         if self.world_size > 1:
@@ -406,13 +412,15 @@ class SNGanEngine(object):
             K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
             lop.dgrad(L.sn_y, 1, L.sn_w, out_mode=2, npass=lop.adj_npass)
             K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
-            lop.wgrad(L.sn_x, L.sn_y, 1, L.sn_parts, L.sn_splits)
+            sx = K.convert_planes(L.sn_x, L.sn_b16) if L.sn_x.dtype == torch.float16 else L.sn_x
+            lop.wgrad(sx, L.sn_y, 1, L.sn_parts, L.sn_splits)
         else:
             lop.dgrad(L.sn_x, 1, L.sn_v, out_mode=2, npass=lop.adj_npass)    # the adjoint is the FORWARD operator here: sigma = ||F^T x||
             K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)
             lop.forward(L.sn_y, 1, L.sn_w, out_mode=2)
             K.sn_normalize(L.sn_w, L.sn_w.numel(), L.sn_xnew, eps=FLAGS.EPSI)
-            lop.wgrad(L.sn_y, L.sn_x, 1, L.sn_parts, L.sn_splits)
+            sy = K.convert_planes(L.sn_y, L.sn_b16) if L.sn_y.dtype == torch.float16 else L.sn_y
+            lop.wgrad(sy, L.sn_x, 1, L.sn_parts, L.sn_splits)
         lop.wgrad_reduce(L.sn_parts, L.sn_splits, 1, L.sn_S)
 
     def _sn_power_iteration(self, fork=True):
@@ -471,7 +479,7 @@ class SNGanEngine(object):
     def _weight_grad(self, net, L, x_in, dz, nimg):
         lop = L.lop
         x_in = self._as_rows(x_in, x_in.shape[1] * x_in.shape[2] // L.Cs_in, L.Cs_in)
-        lop.wgrad(x_in, dz, nimg, L.wg_parts, L.wg_splits)
+        lop.wgrad(x_in, dz, nimg, L.wg_parts, L.wg_splits, scratch=self.wg_scratch)
         gview = net.view(net.g, L.ly.kernel_name)
         if L.has_sn:
             nd = lop.wgrad_reduce(L.wg_parts, L.wg_splits, nimg, gview, w_canon=net.view(net.w, L.ly.kernel_name), dots=L.dots)

@@ -148,6 +148,17 @@ def to_planes(x, dst):
     return dst
 
 
+def convert_planes(src, dst, role='act'):
+    """Planes in one format -> planes in another, same [rows, C] (bf16 re-split of fp16 activations for the weight gradients)."""
+    _planes(src)
+    _planes(dst)
+    n = dst.shape[1] * dst.shape[2]
+    assert src.shape[1] * src.shape[2] == n
+    check(lib().mmdgan_convert_planes(_ptr(src), plane_stride(src), src.shape[0], fmt_of(src, role), _ptr(dst), plane_stride(dst),
+                                      dst.shape[0], fmt_of(dst, role), n, stream()))
+    return dst
+
+
 def planes_value(src, role='act'):
     """planes [npl, rows, C] -> the fp32 values [rows, C] they carry."""
     _planes(src)
@@ -422,8 +433,21 @@ class LinearOp(object):
         splits = max(1, min((296 + tiles - 1) // tiles, max(1, ksteps // 8)))
         return R, NC, bn, splits, P
 
-    def wgrad(self, x_in, dy, nimg, partials, splits=None):
-        """partials [splits, R, NC] <- weight-gradient GEMM of (layer input x_in, output gradient dy)."""
+    def wgrad(self, x_in, dy, nimg, partials, splits=None, scratch=None):
+        """partials [splits, R, NC] <- weight-gradient GEMM of (layer input x_in, output gradient dy).  An fp16-plane operand
+        (forward activations) is first re-split into two bf16 planes -- into `scratch` (a flat bf16 buffer) when given."""
+        ops = []
+        for i, t in enumerate((x_in, dy)):
+            if t.dtype == torch.float16:
+                n = t.shape[1] * t.shape[2]
+                if scratch is not None and i == 0:
+                    assert scratch.numel() >= 2 * n
+                    buf = scratch[:2 * n].view(2, t.shape[1], t.shape[2])
+                else:
+                    buf = new_planes(t.shape[1], t.shape[2], 2, t.device)
+                t = convert_planes(t, buf)
+            ops.append(t)
+        x_in, dy = ops
         R, NC, bn, sp, P = self.wgrad_plan(nimg)
         splits = splits or sp
         d = WgradDesc()
