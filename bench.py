@@ -253,16 +253,16 @@ def run_ours(args):
                 'kernel': 'conv_gemm(_pair)_kernel + wgrad_gemm_kernel (tcgen05) + conv3x3 direct kernels of the image layers: the {} batch-sized '
                           'launches that carry the 3G+7D FLOPs of one step'.format(len(evs)),
                 'gemm_ms_per_step': gemm_ms, 'eager_single_stream_step_ms': t0.elapsed_time(t1), 'share_of_eager_step': gemm_ms / t0.elapsed_time(t1),
-                'note': ('algorithmic FLOPs = (3G+7D) x 2 x B; parity mode: forward launches (G+2D) issue 6 bf16 plane-pair MMAs per '
-                         'algorithmic FLOP, gradient launches (2G+5D) 3, i.e. 3.88 tensor FLOPs per algorithmic FLOP on average, '
-                         'so frac <= 0.258 by construction in this precision mode') if args.passes == 3 else
+                'note': ('algorithmic FLOPs = (3G+7D) x 2 x B; parity mode: every tensor-core launch issues 3 plane-pair MMAs per '
+                         'algorithmic FLOP (forward: two fp16 planes per operand, gradients: two bf16 planes), so frac <= 0.333 by '
+                         'construction in this precision mode') if args.passes == 3 else
                         'algorithmic FLOPs = (3G+7D) x 2 x B; single bf16 pass (speed mode, not parity grade)'}
 
     if rank == 0:
         line = {
             'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16x6 fwd / bf16x3 grad (bf16 planes, fp32 accumulate)' if args.passes == 3 else 'bf16', 'data': 'synthetic',
+            'dtype': 'fp16x3 fwd / bf16x3 grad (two 16-bit planes per operand, three products, fp32 accumulate)' if args.passes == 3 else 'bf16', 'data': 'synthetic',
             'config': {'workload': '{} {}x{} SNGAN + {} MMD, batch {} per GPU, spectral norm on'.format(
                 name, arch['input'][0][1], arch['input'][0][2], loss_type, batch),
                 'global_batch': batch * world, 'parallelism': 'dp{}'.format(world),

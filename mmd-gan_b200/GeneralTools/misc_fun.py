@@ -15,8 +15,9 @@ class SetFlag(object):
         self.IMAGE_FORMAT_ALIAS = 'NCHW'
         self.WEIGHT_INITIALIZER = 'default'
         self.SPECTRAL_NORM_MODE = 'default'   # 'default' = 'PICO'; 'sn_paper' = PIM (not built yet: raises)
-        # B200 engine knobs (new): 3 = parity mode (fp32 values as bf16 planes: 6 plane-pair tensor-core products in the
-        # forward passes, 3 in the gradient passes), 1 = a single bf16 pass (speed mode, not parity grade)
+        # B200 engine knobs (new): 3 = parity mode (fp32 values as two 16-bit planes, three plane-pair tensor-core products:
+        # fp16 planes in the forward passes, bf16 planes in the gradient passes), 1 = a single bf16 pass (speed mode, not
+        # parity grade)
         self.TENSOR_PASSES = 3
 
     def print(self, info, force_print=False):

@@ -6,8 +6,9 @@ current weights it produces loss_gen / loss_dis, the discriminator gradients of 
 loss_gen (through D), applies both TF-Adam updates simultaneously, updates the batch-norm moving statistics and
 every spectral-norm `in_rand`.
 
-Data layout in HBM: GEMM operands (activations, gradients, packed weights) NHWC as bf16 planes [npl][N*H*W][C] whose
-sum is the fp32 value (3 planes for values, 2 for gradients; include/mmdgan_b200.h); pre-batch-norm outputs, scores and
+Data layout in HBM: GEMM operands NHWC as 16-bit planes [npl][N*H*W][C] whose sum is the (scaled) fp32 value: two fp16
+planes for everything that feeds a forward launch (activations, forward weights), two bf16 planes for gradients
+(include/mmdgan_b200.h); pre-batch-norm outputs, scores and
 reductions raw fp32; parameters, gradients and Adam slots fp32 as one flat buffer per net in the reference's canonical
 variable layouts; packed GEMM operands per layer, refreshed after every update.  The generator's last conv writes straight into rows
 [B, 2B) of the discriminator input (no tf.concat copy); the discriminator backward runs on a 3B "virtual batch"
@@ -287,7 +288,7 @@ class SNGanEngine(object):
         self.world_size, self.rank, self.pg = world_size, rank, process_group
         self.use_graph = use_graph
         if self.npass not in (1, 3):
-            raise ValueError('TENSOR_PASSES must be 3 (parity: bf16x6 forward / bf16x3 gradients) or 1 (single bf16 pass)')
+            raise ValueError('TENSOR_PASSES must be 3 (parity: fp16x3 forward / bf16x3 gradients) or 1 (single bf16 pass)')
         self.om = 0                                # GEMM outputs that feed another GEMM are written as bf16 planes
         self.code_size = architecture['code'][0][0]
         self.channels, self.height, self.width = architecture['input'][0]

@@ -1,7 +1,7 @@
 """Builds profiles/<tag>_summary.md from the ncu artefacts brought back in gpurun_out/ (run here, no GPU needed)."""
 import collections, csv, os, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
-out = ['# ncu summary {} (B200, CIFAR-10 32x32, B=256, bf16x6 fwd / bf16x3 grad; commands in scripts/ncu_step.sh)\n'.format(tag)]
+out = ['# ncu summary {} (B200, CIFAR-10 32x32, B=256, fp16x3 fwd / bf16x3 grad; commands in scripts/ncu_step.sh)\n'.format(tag)]
 lp = 'gpurun_out/launches_{}.csv'.format(tag)
 if os.path.exists(lp):
     rows = list(csv.reader(open(lp)))

@@ -21,9 +21,9 @@ def tg(self, g_, src, nimg, dst, geom, *a, **kw):
     kind = 'fwd' if g_ is self.f else 'dgrad'
     recs.append((kind, self.op, self.Cin, self.Cout, self.Hin, nimg, M, g_['ncols'], g_['kpad'], 2.0 * M * g_['ncols'] * g_['taps'] * g_['Cs'], s, e, g_['bn']))
     return r
-def tw(self, x_in, dy, nimg, partials, splits=None):
+def tw(self, x_in, dy, nimg, partials, splits=None, **kw):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record(); r = ow(self, x_in, dy, nimg, partials, splits); e.record()
+    s.record(); r = ow(self, x_in, dy, nimg, partials, splits, **kw); e.record()
     R, NC, bn, sp, P = self.wgrad_plan(nimg)
     recs.append(('wgrad', self.op, self.Cin, self.Cout, self.Hin, nimg, R, NC, P, 2.0 * R * NC * P, s, e, (bn, r)))
     return r

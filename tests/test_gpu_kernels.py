@@ -1,6 +1,6 @@
 """Per-kernel parity on the GPU: every CUDA kernel, called through the C ABI, against the CPU oracle
-(float64) on the same seeded inputs.  Tolerances: 5e-5 normwise for the parity mode of the tensor-core kernels (bf16
-planes: six plane-pair products forward, three for the gradients) and the CUDA-core kernels, 1e-2 for the opt-in single
+(float64) on the same seeded inputs.  Tolerances: 5e-5 normwise for the parity mode of the tensor-core kernels (two 16-bit
+planes per operand -- fp16 forward, bf16 gradients -- three plane-pair products) and the CUDA-core kernels, 1e-2 for the opt-in single
 bf16 pass (north-star parity bar is 1e-3 on the parity-mode path)."""
 import numpy as np
 import pytest

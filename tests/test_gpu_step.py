@@ -1,7 +1,7 @@
 """End-to-end parity of the fused SNGan step on the GPU against the CPU oracle (float64) on identical
 inputs / weights / state.  Tolerance: 1e-3 normwise relative (the north-star bar) for losses, scores, every gradient
-tensor, the spectral-norm and batch-norm state; observed errors of the parity mode (bf16 planes: six plane-pair
-products forward, three for the gradients) are ~1e-5."""
+tensor, the spectral-norm and batch-norm state; observed errors of the parity mode (two 16-bit planes per operand, fp16
+forward / bf16 gradients, three plane-pair products) are ~1e-5."""
 import numpy as np
 import pytest
 import torch
