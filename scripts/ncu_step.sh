@@ -11,8 +11,8 @@ cap() {  # name, demangled-name regex, launches to skip, launches to capture (ke
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 \
       -o gpurun_out/prof_${TAG}_$1 -f python scripts/profile_step.py cifar 256 3 > /dev/null 2>&1
 }
-cap conv_fwd 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+6' 0 1          # D forward convs (6 plane-pair products)
-cap conv_dgrad 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3[^0-9]+(1|true)' 0 1        # D input gradients, N >= 256
+cap conv_fwd 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3[^0-9]+(1|true)' 2 1     # 3rd launch of the step: D forward conv 256->256 @8x8, 512 images (two fp16 planes, 3 products)
+cap conv_dgrad 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3[^0-9]+(1|true)' 5 1   # 6th launch: D input gradient 512->512 @4x4, 768 rows-images (two bf16 planes, 3 products)
 cap conv_dgrad_n64 'conv_gemm_kernel<[^0-9]*64[^0-9]+3[^0-9]+(1|true)' 0 1   # input gradient of the 64->128 stride-2 conv (N = 64)
 cap wgrad 'wgrad_gemm_kernel<[^0-9]*256[^0-9]+3' 8 1                 # first batch-sized weight gradients (8 batch-1 SN launches skipped)
 cap mmd 'mmd_fused' 0 1
