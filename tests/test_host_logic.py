@@ -129,6 +129,40 @@ def test_cabi_argument_validation_without_a_gpu():
     assert lib.mmdgan_mmd_workspace(256) >= 64 * 6 * 4
 
 
+def test_cabi_plane_format_validation_without_a_gpu():
+    """One MMA cannot mix an fp16 operand with a bf16 one (measured on the B200: illegal instruction), and the six-product mode
+    is defined for three bf16 planes only: the C ABI rejects such descriptors before any CUDA call."""
+    from mmdgan_b200 import _lib
+    lib = _lib.load()
+    g = _lib.GemmDesc()
+    fake = 0x7f0000001000          # never dereferenced: validation fails first
+    g.src, g.w, g.dst = fake, fake, fake
+    g.src_plane = g.w_plane = g.dst_plane = 1 << 20
+    g.Nimg, g.Hs, g.Ws, g.Cs, g.Hg, g.Wg, g.sy, g.sx, g.TH, g.TW = 2, 8, 8, 64, 8, 8, 1, 1, 3, 3
+    g.kpad, g.classes, g.w_rows = 576, 1, 128
+    g.Hd, g.Wd, g.Cd, g.osy, g.osx, g.Ncols = 8, 8, 128, 1, 1, 128
+    g.out_mode, g.dst_npl, g.bn, g.npass = 0, 2, 128, 3
+    g.src_fmt, g.w_fmt = _lib_fmt('F16A'), _lib_fmt('BF16')
+    assert lib.mmdgan_gather_gemm(ctypes.byref(g), None) == _lib.MMDGAN_EINVAL
+    assert b'both operands must be' in lib.mmdgan_last_error()
+    g.src_fmt, g.w_fmt, g.npass = _lib_fmt('F16A'), _lib_fmt('F16W'), 6
+    assert lib.mmdgan_gather_gemm(ctypes.byref(g), None) == _lib.MMDGAN_EINVAL
+    assert b'npass 6 is the bf16 three-plane mode' in lib.mmdgan_last_error()
+    w = _lib.WgradDesc()
+    w.plain, w.g, w.out = fake, fake, fake
+    w.plain_plane = w.g_plane = 1 << 20
+    w.P, w.Cp, w.Nimg, w.Hs, w.Ws, w.Cs, w.Hg, w.Wg, w.sy, w.sx, w.TH, w.TW, w.splits = 128, 64, 2, 8, 8, 64, 8, 8, 1, 1, 3, 3, 1
+    w.bn, w.npass, w.p_fmt, w.g_fmt = 128, 3, _lib_fmt('BF16'), _lib_fmt('F16A')
+    assert lib.mmdgan_wgrad_gemm(ctypes.byref(w), None) == _lib.MMDGAN_EINVAL
+    assert b'both operands must be' in lib.mmdgan_last_error()
+    # fp16 formats carry at most two planes
+    assert lib.mmdgan_to_planes(fake, fake, 1 << 20, 3, _lib_fmt('F16A'), 1024, None) == _lib.MMDGAN_ESHAPE
+
+
+def _lib_fmt(name):
+    return {'BF16': 0, 'F16A': 1, 'F16W': 2}[name]
+
+
 def test_product_fails_loudly_without_cuda():
     """No CPU fallback: a CPU tensor reaching a kernel wrapper raises instead of silently computing."""
     from mmdgan_b200 import kernels as K
