@@ -28,6 +28,7 @@ WGRAD_BN_MAX = int(os.environ.get('MMDGAN_WGRAD_BN', '256'))   # widest N tile o
 FMT_BF16, FMT_F16A, FMT_F16W = 0, 1, 2
 FMT_SCALE = {FMT_BF16: 1.0, FMT_F16A: 16.0, FMT_F16W: 64.0}
 F16_FORWARD = int(os.environ.get('MMDGAN_F16_FORWARD', '1'))   # parity mode: forward operands as two fp16 planes (3 products) instead of three bf16 planes (6)
+WGRAD_CTAS = int(os.environ.get('MMDGAN_WGRAD_CTAS', '222'))   # CTAs a weight-gradient launch aims for (tiles x split-K slices)
 PAIR_BN256_AUX = int(os.environ.get('MMDGAN_BN256_AUX', '0'))   # experiment knob: 256-wide pair tiles for input gradients with N = 256
 PAIR_N64 = int(os.environ.get('MMDGAN_PAIR_N64', '0'))   # CTA-pair tiles for N = 64 layers: measured slower (0.36 vs 0.33 ms), off
 DIRECT_CONV = True     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
@@ -430,7 +431,7 @@ class LinearOp(object):
         bn = pick_bn(NC, lo=64, hi=WGRAD_BN_MAX)
         tiles = ((R + 127) // 128) * ((NC + bn - 1) // bn)
         ksteps = (P + 31) // 32
-        splits = max(1, min((296 + tiles - 1) // tiles, max(1, ksteps // 8)))
+        splits = max(1, min((WGRAD_CTAS + tiles - 1) // tiles, max(1, ksteps // 8)))
         return R, NC, bn, splits, P
 
     def wgrad(self, x_in, dy, nimg, partials, splits=None, scratch=None):
