@@ -268,7 +268,7 @@ def run_ours(args):
                 'global_batch': batch * world, 'parallelism': 'dp{}'.format(world),
                 'l2': 'per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush',
                 'tensor_passes': args.passes, 'cuda_graph': True, 'loss_last_step': last},
-            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
+            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(eng.kernel_launches_per_step * args.steps),
             'gpu_launches_per_step': int(eng.kernel_launches_per_step),

@@ -23,7 +23,8 @@
  * scale * x carry 22 bits and npass = 3 is already fp32-grade (~2^-21) -- half the tensor work and two thirds of the
  * operand bytes of the six-product bf16 mode.  MMDGAN_FMT_F16A (activations, spectral-norm vectors) stores 16 * x,
  * MMDGAN_FMT_F16W (packed forward weights) 64 * x; the power-of-two factors keep the second plane of ordinary magnitudes in
- * fp16's normal range and leave head-room up to |x| < 4094 / 1023 (conversions saturate, they never produce inf); the
+ * fp16's normal range and leave head-room up to |x| < 4094 / 1023 (conversions saturate, they never produce inf, and the
+ * producers report a saturation through the optional `sat_flag` so that the host can fail loudly); the
  * caller folds 1 / (16 * 64) into alpha_k.  The two operands of one MMA must have the SAME element type (measured: an fp16 x
  * bf16 descriptor is an illegal instruction), so gradient launches read bf16 planes only (mmdgan_convert_planes).
  */
@@ -141,6 +142,7 @@ typedef struct mmdgan_gemm_desc {
     int out_mode;       /* 0 bf16 planes, 2 raw fp32 */
     int bn;             /* N tile: 16, 32, 64, 128, 256 */
     int npass;          /* 6, 3 or 1 plane-pair products per k-block (see the header comment) */
+    int* sat_flag;      /* optional device int: set to 1 when a value written as fp16 planes exceeds the format's range */
     int cta_pair;       /* 1: tcgen05 cta_group::2 -- a 2-CTA cluster shares one 256 x bn tile (bn 64, 128 or 256) */
     mmdgan_gemm_class cls[4];
 } mmdgan_gemm_desc;
@@ -173,6 +175,7 @@ typedef struct mmdgan_direct_desc {
     long long aux_plane;
     int aux_npl, aux_mode;
     float* colsum; /* [mmdgan_direct_conv_blocks()][Cd] */
+    int* sat_flag; /* optional, as in mmdgan_gemm_desc */
 } mmdgan_direct_desc;
 int mmdgan_direct_conv(const mmdgan_direct_desc* d, void* stream);
 int mmdgan_direct_conv_blocks(int N, int H, int W);
@@ -234,7 +237,7 @@ int mmdgan_colsum_planes(const mmdgan_bf16* x, long long plane, int npl, int row
 int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                        float* invstd, float* moving_mean, float* moving_var, void* stream);
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
-                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, void* stream);
+                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, int* sat_flag, void* stream);
 int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int C, long long rows, int rows_per_block, int act, float* psum, float* psumx,
                          void* stream);

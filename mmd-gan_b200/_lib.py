@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ('alpha_k', C.c_float), ('sigma', C.c_void_p), ('bias', C.c_void_p), ('act', C.c_int),
         ('aux', C.c_void_p), ('aux_plane', C.c_longlong), ('aux_npl', C.c_int), ('aux_fmt', C.c_int), ('aux_mode', C.c_int), ('aux_wrap_at', C.c_longlong), ('aux_wrap_len', C.c_longlong),
         ('colsum', C.c_void_p), ('colsumsq', C.c_void_p), ('colsum_rows', C.c_longlong),
-        ('out_mode', C.c_int), ('bn', C.c_int), ('npass', C.c_int), ('cta_pair', C.c_int),
+        ('out_mode', C.c_int), ('bn', C.c_int), ('npass', C.c_int), ('sat_flag', C.c_void_p), ('cta_pair', C.c_int),
         ('cls', GemmClass * 4)]
 
 
@@ -58,7 +58,7 @@ class DirectDesc(C.Structure):
         ('dst', C.c_void_p), ('dst_plane', C.c_longlong), ('dst_npl', C.c_int), ('Cd', C.c_int), ('out_mode', C.c_int),
         ('alpha_k', C.c_float), ('sigma', C.c_void_p), ('bias', C.c_void_p), ('act', C.c_int),
         ('aux', C.c_void_p), ('aux_plane', C.c_longlong), ('aux_npl', C.c_int), ('aux_mode', C.c_int),
-        ('colsum', C.c_void_p)]
+        ('colsum', C.c_void_p), ('sat_flag', C.c_void_p)]
 
 
 class WredDesc(C.Structure):
@@ -123,7 +123,7 @@ SYMBOLS = {
     'mmdgan_colsum_small': (_I, [_P, _I, _I, _P, _P]),
     'mmdgan_colsum_planes': (_I, [_P, _LL, _I, _I, _I, _P, _P]),
     'mmdgan_bn_finalize': (_I, [_P, _P, _I, _I, _LL, _F, _F, _P, _P, _P, _P, _P]),
-    'mmdgan_bn_apply': (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _P, _LL, _I, _I, _P]),
+    'mmdgan_bn_apply': (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _P, _LL, _I, _I, _P, _P]),
     'mmdgan_bn_bwd_reduce': (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _P, _P, _P]),
     'mmdgan_bn_bwd_apply': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _LL, _I, _P, _LL, _I, _P]),
     'mmdgan_mmd_configure': (_I, [C.POINTER(MmdDesc), C.c_char_p, _F, _F]),

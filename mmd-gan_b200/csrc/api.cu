@@ -38,7 +38,7 @@ int l_scale_by_sigma(float*, const float*, float, long long, cudaStream_t);
 int l_sn_normalize(const float*, long long, float, float*, uint16_t*, long long, int, int, cudaStream_t);
 int l_bn_finalize(const float*, const float*, int, int, long long, float, float, float*, float*, float*, float*, cudaStream_t);
 int l_bn_apply(const float*, const float*, const float*, const float*, const float*, int, long long, int, uint16_t*, long long, int, int,
-               cudaStream_t);
+               int*, cudaStream_t);
 int l_bn_bwd_reduce(const float*, const float*, const float*, const float*, const float*, const float*, int, long long, int, int,
                     float*, float*, cudaStream_t);
 int l_bn_bwd_apply(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
@@ -186,7 +186,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_fmt = d->aux_fmt; p.aux_mode = d->aux_mode;
     p.aux_wrap_at = d->aux_wrap_at > 0 ? d->aux_wrap_at : (1ll << 62); p.aux_wrap_len = d->aux_wrap_len;
     p.colsum = d->colsum; p.colsumsq = d->colsumsq; p.colsum_rows = d->colsum_rows > 0 ? d->colsum_rows : (1ll << 62);
-    p.out_mode = d->out_mode; p.err = nullptr;
+    p.out_mode = d->out_mode; p.err = nullptr; p.sat_flag = d->sat_flag;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("MMDGAN_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -222,7 +222,7 @@ int mmdgan_direct_conv(const mmdgan_direct_desc* d, void* stream) {
     p.Cin = d->Cin; p.Cout = d->Cout; p.w = d->w; p.w_tap = d->w_tap; p.w_in = d->w_in; p.w_out = d->w_out; p.flip = d->flip;
     p.dst = d->dst; p.dst_plane = d->dst_plane; p.dst_npl = d->dst_npl; p.Cd = d->Cd; p.out_mode = d->out_mode;
     p.alpha_k = d->alpha_k; p.sigma = d->sigma; p.bias = d->bias; p.act = d->act;
-    p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_mode = d->aux_mode; p.colsum = d->colsum;
+    p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_mode = d->aux_mode; p.colsum = d->colsum; p.sat_flag = d->sat_flag;
     return wrap(mg::launch_direct_conv(p, S(stream)), "mmdgan_direct_conv");
 }
 
@@ -296,11 +296,11 @@ int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long l
     return wrap(mg::l_bn_finalize(psum, psq, T, C, rows, eps, momentum, mean, invstd, moving_mean, moving_var, S(stream)), "mmdgan_bn_finalize");
 }
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
-                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, void* stream) {
+                    long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, int* sat_flag, void* stream) {
     if (!z || !mean || !invstd || !gamma || !beta || !out) return fail(MMDGAN_EINVAL, "mmdgan_bn_apply: null pointer");
     if (C <= 0 || (C & 3) || total <= 0 || total % C || !fmt_ok(fmt, npl) || (npl > 1 && out_plane < total))
         return fail(MMDGAN_ESHAPE, "mmdgan_bn_apply: bad shape");
-    return wrap(mg::l_bn_apply(z, mean, invstd, gamma, beta, C, total, act, out, out_plane, npl, fmt, S(stream)), "mmdgan_bn_apply");
+    return wrap(mg::l_bn_apply(z, mean, invstd, gamma, beta, C, total, act, out, out_plane, npl, fmt, sat_flag, S(stream)), "mmdgan_bn_apply");
 }
 int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int C, long long rows, int rows_per_block, int act, float* psum, float* psumx,

@@ -490,9 +490,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                     v.z *= act_grad_from_output(a4.z, 3);
                     v.w *= act_grad_from_output(a4.w, 3);
                 }
-                if (p.out_mode == 0)
+                if (p.out_mode == 0) {
+                    note_saturation4(p.sat_flag, p.dst_fmt, v);
                     store_vals4(static_cast<bf16_t*>(p.dst) + prow * p.Cd + col, p.dst_plane, p.dst_npl, p.dst_fmt, v);
-                else
+                } else
                     *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + prow * p.Cd + col) = v;
                 if (prow < p.colsum_rows) {
                     cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;

@@ -44,6 +44,7 @@ struct ConvGemmParams {
     long long colsum_rows;   // only destination rows < colsum_rows are counted
     int out_mode;            // 0: bf16 planes, 2: raw fp32
     unsigned int* err;       // device error flag (watchdog)
+    int* sat_flag;           // set to 1 when a value written as fp16 planes saturates (or null)
     int tiles_m, tiles_n, classes;   // filled by the launcher: grid decomposition (linear block index)
     int debug;               // profiling experiments only: bit0 = skip the A gather, bit1 = skip the MMAs
     GemmClass cls[4];
@@ -87,6 +88,7 @@ struct DirectConvParams {
     long long aux_plane;
     int aux_npl, aux_mode;
     float* colsum;           // [blocks][Cd] per-block column sums of the written values, or null (LS only)
+    int* sat_flag;           // set to 1 when a value written as fp16 planes saturates (or null)
 };
 
 // mmd.cu

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) conv3x3_ls_kernel(const DirectConvParams 
         const float4 lo = make_float4(v[0], v[1], v[2], v[3]), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.out_mode == 0) {
             bf16_t* o = static_cast<bf16_t*>(p.dst) + prow * p.Cd;
+            note_saturation4(p.sat_flag, p.dst_fmt, lo);
             store_vals4(o, p.dst_plane, p.dst_npl, p.dst_fmt, lo);
             for (int c = 4; c < p.Cd; c += 4) store_vals4(o + c, p.dst_plane, p.dst_npl, p.dst_fmt, z4);
         } else {
@@ -250,8 +251,10 @@ __global__ void __launch_bounds__(256) conv3x3_sl_kernel(const DirectConvParams 
             v.z = d_act(fmaf(a.z, alpha, bq.z), p.act);
             v.w = d_act(fmaf(a.w, alpha, bq.w), p.act);
             const long long o = (static_cast<long long>(n * p.H + gy) * p.W + gx) * p.Cd + co0 + 4 * q;
-            if (p.out_mode == 0) store_vals4(static_cast<bf16_t*>(p.dst) + o, p.dst_plane, p.dst_npl, p.dst_fmt, v);
-            else *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + o) = v;
+            if (p.out_mode == 0) {
+                note_saturation4(p.sat_flag, p.dst_fmt, v);
+                store_vals4(static_cast<bf16_t*>(p.dst) + o, p.dst_plane, p.dst_npl, p.dst_fmt, v);
+            } else *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + o) = v;
         }
     }
 }

@@ -407,7 +407,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
 // a = act(gamma * (z - mean) * invstd + beta) -> bf16 planes; z [rows][C] raw fp32
 __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int C, long long total, int act,
-                                bf16_t* __restrict__ out, long long plane, int npl, int fmt) {
+                                bf16_t* __restrict__ out, long long plane, int npl, int fmt, int* __restrict__ sat_flag) {
     for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
         const int c = static_cast<int>(i % C);
@@ -420,6 +420,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
         y.z = fmaf((zv.z - mu.z) * is.z, g.z, b.z);
         y.w = fmaf((zv.w - mu.w) * is.w, g.w, b.w);
         if (act == 2) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        note_saturation4(sat_flag, fmt, y);
         store_vals4(out + i, plane, npl, fmt, y);
     }
 }
@@ -639,8 +640,8 @@ int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long r
     return MG_CHECK_LAUNCH();
 }
 int l_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C, long long total,
-               int act, bf16_t* out, long long plane, int npl, int fmt, cudaStream_t st) {
-    bn_apply_kernel<<<grid_for(total / 4), kBS, 0, st>>>(z, mean, invstd, gamma, beta, C, total, act, out, plane, npl, fmt);
+               int act, bf16_t* out, long long plane, int npl, int fmt, int* sat_flag, cudaStream_t st) {
+    bn_apply_kernel<<<grid_for(total / 4), kBS, 0, st>>>(z, mean, invstd, gamma, beta, C, total, act, out, plane, npl, fmt, sat_flag);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,

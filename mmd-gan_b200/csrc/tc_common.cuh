@@ -272,6 +272,13 @@ __device__ __forceinline__ void store_vals4(bf16_t* dst, long long plane, int np
     *reinterpret_cast<uint2*>(dst) = make_uint2(pack16(a[0], a[1]), pack16(a[2], a[3]));
     if (npl > 1) *reinterpret_cast<uint2*>(dst + plane) = make_uint2(pack16(b[0], b[1]), pack16(b[2], b[3]));
 }
+// fp16 planes saturate at |scale * x| = 65504 instead of overflowing; a producer that can see large values reports it here so
+// that the host can fail loudly (the precision claim of the fp16 formats holds below the saturation point only)
+__device__ __forceinline__ void note_saturation4(int* flag, int fmt, float4 v) {
+    if (flag == nullptr || fmt == FMT_BF16) return;
+    const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) * fmt_scale(fmt);
+    if (m > 65504.f) atomicExch(flag, 1);
+}
 __device__ __forceinline__ void store_val(bf16_t* dst, long long plane, int npl, int fmt, float x) {
     if (fmt == FMT_BF16) {
         store_planes(dst, plane, npl, x);

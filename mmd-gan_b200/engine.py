@@ -312,6 +312,10 @@ class SNGanEngine(object):
         self.mmd = K.MmdKernel(loss_type, self.rep_weights, b=B, device=self.device)
         self.global_step = 0
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # set by any producer whose value does not fit the fp16 forward planes (|activation| >= 4094): reported by step()
+        self.sat_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for L in self.G.layers + self.D.layers:
+            L.lop.sat_flag = self.sat_flag
         self._graphs = None
         self._warm = False
         self._stream = torch.cuda.Stream(device=self.device)
@@ -325,6 +329,7 @@ class SNGanEngine(object):
         self._pin_data = torch.empty((B, self.channels, self.height, self.width), dtype=torch.float32).pin_memory()
         self._pin_code = torch.empty((B, self.code_size), dtype=torch.float32).pin_memory()
         self._pin_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+        self._pin_sat = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._dev_data = torch.empty_like(self._pin_data, device=self.device)
         self._dev_code = torch.empty_like(self._pin_code, device=self.device)
         self.kernel_launches_per_step = None
@@ -394,7 +399,7 @@ class SNGanEngine(object):
                 if is_training:
                     K.bn_finalize(L.ps, L.pq, L.T_fwd, L.Cs_out, nimg * L.rows_out, L.mean, L.invstd, L.mm, L.mv)
                     K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
-                               L.act_code, L.a)
+                               L.act_code, L.a, sat_flag=self.sat_flag)
                 else:
                     raise NotImplementedError('{}: inference-mode batch norm is built in Routine runner'.format(L.ly.layer_scope))
             else:
@@ -699,8 +704,12 @@ class SNGanEngine(object):
         self.stage(data_x, code_x)
         self.step_device()
         self._pin_loss.copy_(self.mmd.losses, non_blocking=True)
+        self._pin_sat.copy_(self.sat_flag, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         lg, ld = float(self._pin_loss[0]), float(self._pin_loss[1])
+        if int(self._pin_sat[0]) != 0:
+            raise FloatingPointError('an activation exceeded the range of the fp16 forward planes (|x| >= 4094) at step {}: the parity '
+                                     'mode is not valid for this model state; run with MMDGAN_F16_FORWARD=0 (three bf16 planes)'.format(self.global_step))
         if check_nan:
             assert not (math.isnan(lg) or math.isnan(ld)), \
                 'Model diverged with loss = {} at step {}'.format([lg, ld], self.global_step)    # graph_func.py:856

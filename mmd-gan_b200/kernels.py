@@ -185,6 +185,7 @@ class LinearOp(object):
         self.adj_npass = 6 if npass == 3 else 1     # the adjoint used as a FORWARD operator (spectral norm): bf16 x 6
         self.npl = mode_planes(npass)               # planes of the bf16 packed operands
         self._wg_scale = 1.0
+        self.sat_flag = None                        # optional int32 device flag: a value written as fp16 planes saturated
         if op == 'd':
             self.Cin, self.Cout = in_shape[0], out_shape[0]
             self.Hin = self.Win = self.Hout = self.Wout = 1
@@ -325,6 +326,7 @@ class LinearOp(object):
                 bn = 256
         d.cta_pair = pair
         d.out_mode, d.bn, d.npass = out_mode, bn, npass
+        d.sat_flag = _ptr(self.sat_flag)
         if src.shape[0] < fmt_need(d.src_fmt, npass) or g['w'].shape[0] < fmt_need(d.w_fmt, npass) or (npass == 6 and (d.src_fmt or d.w_fmt)):
             raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'npass {} does not fit operands {} x {} / {} x {}'.format(
                 npass, src.shape[0], src.dtype, g['w'].shape[0], g['w'].dtype))
@@ -378,6 +380,7 @@ class LinearOp(object):
             d.aux, d.aux_plane, d.aux_npl, d.aux_fmt = _ptr(aux), plane_stride(aux), aux.shape[0], fmt_of(aux)
         d.aux_mode = aux_mode
         d.colsum = _ptr(colsum)
+        d.sat_flag = _ptr(self.sat_flag)
         check(lib().mmdgan_direct_conv(C.byref(d), stream()))
 
     def fwd_tiles(self, nimg):
@@ -576,10 +579,10 @@ def bn_finalize(psum, psq, T, Cc, rows, mean, invstd, moving_mean=None, moving_v
                                    _ptr(moving_mean), _ptr(moving_var), stream()))
 
 
-def bn_apply(z, mean, invstd, gamma, beta, Cc, total, act, out):
+def bn_apply(z, mean, invstd, gamma, beta, Cc, total, act, out, sat_flag=None):
     _planes(out)
     check(lib().mmdgan_bn_apply(_ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), Cc, total, act, _ptr(out),
-                                plane_stride(out), out.shape[0], fmt_of(out), stream()))
+                                plane_stride(out), out.shape[0], fmt_of(out), _ptr(sat_flag), stream()))
 
 
 def bn_bwd_reduce(da, z, mean, invstd, gamma, beta, Cc, rows, rows_per_block, act, psum, psumx):

@@ -191,3 +191,19 @@ def test_single_bf16_pass_mode_is_close_but_not_parity_grade(cuda):
     B = 16
     orc, eng = make_pair(arch, B, 'rep', npass=1)
     check_step(orc, eng, arch, B, seed=5, tol=5e-1)
+
+
+def test_fp16_plane_saturation_is_reported(cuda):
+    """The forward operands are fp16 planes of 16 x value: an activation beyond +-4094 cannot be represented.  The producers
+    saturate (never inf) and raise a device flag; step() turns it into a FloatingPointError instead of training on silently
+    clipped activations."""
+    arch = oa.tiny(act_k=2.6)
+    B = 8
+    orc, eng = make_pair(arch, B, 'rep')
+    data, code = onet.synthetic_batch(arch, B, seed=3, dtype=torch.float32)
+    eng.step(data, code)                                        # an ordinary step: no flag
+    name = eng.G.layers[0].ly.bias_name                          # push the generator's first activation far out of range
+    eng.G.set_variable(name, torch.full(eng.G.var_offsets[name][1], 1.0e4))
+    eng.G.refresh()
+    with pytest.raises(FloatingPointError):
+        eng.step(data, code, check_nan=False)
