@@ -2,16 +2,19 @@
 //
 //   D[m][n] = epilogue( alpha * sum_k A[m][k] * Bw[n][k] )
 //
-// A (activations, NHWC, bf16 planes) is staged tap by tap into 64-byte-swizzled K-major shared-memory tiles -- by TMA as
-// one 4-D box per (channel chunk, tap) when a tile is a whole number of image rows, else by four producer warps with
-// 16-byte cp.async (zero fill implements SAME padding and tile tails); Bw (weights, K-major [rows][Kpad] bf16 planes)
-// is staged by TMA; one elected thread issues tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM).
-// An fp32 value is carried as up to three bf16 planes x = p0 + p1 + p2 (tc_common.cuh).  NPASS == 6 multiplies the plane
-// pairs {00, 01, 10, 02, 20, 11}: fp32-grade products (forward passes, whose errors the MMD loss amplifies);
-// NPASS == 3 multiplies {00, 01, 10}: ~2^-17 products (input gradients, linear in the operand); NPASS == 1 is the
-// plain bf16 speed mode.  The producer warps turn into the epilogue: TMEM -> registers -> shared staging -> coalesced
-// stores with bias / activation / activation derivative / bf16 plane split and per-tile column sums (bias gradients,
-// batch-norm statistics) fused in.
+// A (activations, NHWC, 16-bit planes) is staged tap by tap into 64-byte-swizzled K-major shared-memory tiles -- by TMA
+// as one 5-D box {32 channels, W, rows, images, planes} per (channel chunk, tap) when a tile is a whole number of image
+// rows, else by four producer warps with 16-byte cp.async (zero fill implements SAME padding and tile tails); Bw
+// (weights, K-major [planes][rows][Kpad]) is staged by one 3-D TMA box; one elected thread issues tcgen05.mma kind::f16
+// (fp16 or bf16 in -- both operands the same type --, fp32 accumulate in TMEM).
+// An fp32 value is carried as the sum of 16-bit planes (tc_common.cuh).  NPASS == 3 multiplies the plane pairs {00, 01,
+// 10}: with two fp16 planes per operand (22 bits) that is fp32-grade -- the forward passes, whose errors the MMD loss
+// amplifies --, with two bf16 planes (16 bits) it is ~2^-17 -- input gradients, linear in the operand.  NPASS == 6
+// multiplies {00, 01, 10, 02, 20, 11} of three bf16 planes (fp32-grade without fp16's range limit: the spectral-norm
+// adjoint, and the forward passes when MMDGAN_F16_FORWARD=0); NPASS == 1 is the plain bf16 speed mode.  The producer
+// warps turn into the epilogue: TMEM -> registers -> shared staging -> coalesced stores with bias / activation /
+// activation derivative (signs prefetched as bit masks during the main loop) / plane split and per-tile column sums
+// (bias gradients, batch-norm statistics) fused in.
 //
 // Replaces the tf.matmul / tf.nn.conv2d / tf.nn.conv2d_transpose call sites of the reference
 // (GeneralTools/layer_func.py:909-928) and their gradients (DeepLearning/my_sngan.py:301-304).

@@ -2,7 +2,8 @@
 //
 //   W[r][(t, c)] = sum_p P[p][r] * G[g(p, t)][c]
 //
-// P is a plain [pixels][Cp] activation / gradient matrix, G an NHWC activation gathered tap by tap, both as bf16 planes.
+// P is a plain [pixels][Cp] activation / gradient matrix, G an NHWC activation gathered tap by tap, both as bf16 planes
+// (fp16 forward activations are re-split by convert_planes first: one MMA cannot mix fp16 with bf16).
 // With NHWC storage the contracted dimension (pixels) is the strided one, so BOTH operands are MN-major: a shared-
 // memory "chunk" is 32 pixel rows x 128 bytes (64 consecutive channels of one pixel per row, 128-byte swizzle); P
 // chunks are staged by TMA (one box {64 channels, 32 pixels, planes} per chunk), G chunks by 16-byte cp.async with the
