@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python scripts/dev/dbg_linear.py > gpurun_out/dbg_linear.txt 2>&1; echo "dbg_linear rc=$?"
+timeout 300 python tests/dev/dbg_linear.py > gpurun_out/dbg_linear.txt 2>&1; echo "dbg_linear rc=$?"
 grep " 3 fwd" gpurun_out/dbg_linear.txt | cut -c1-110; tail -3 gpurun_out/dbg_linear.txt | cut -c1-300
 for f in test_gpu_kernels test_gpu_golden_api test_gpu_step; do
   timeout 900 python -m pytest tests/$f.py -q -m gpu -x --timeout 600 > gpurun_out/$f.txt 2>&1; echo "$f rc=$?"; tail -4 gpurun_out/$f.txt | cut -c1-300

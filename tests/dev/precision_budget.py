@@ -8,10 +8,10 @@ of the CUDA path rounds it, and the resulting losses / gradients are compared wi
   mixed    forward operands as two fp16 planes of 16 x value (22 bits), two bf16 planes for the gradients (what the engine ships)
 Result (CIFAR net, act_k 2.7, batch 8): the MMD loss amplifies forward (score) errors by 10^2..10^3, so bf16x3 forward
 passes give a median gradient error of 2.5e-3 (fails the 1e-3 bar) while gradient passes are linear and tolerate it:
-mixed = 7.5e-6.  Usage: python scripts/precision_budget.py
+mixed = 7.5e-6.  Usage: python tests/dev/precision_budget.py   (test infrastructure: it drives the oracle)
 """
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, numpy as np
 from oracle import net as onet, architectures as oa
 torch.set_num_threads(8)
