@@ -22,16 +22,22 @@ def cifar_batch(B, seed):
     return torch.rand(B, 3, 32, 32, generator=g) * 2 - 1, torch.randn(B, 128, generator=g)
 
 
-def test_fullsize_cifar_steps_are_bit_reproducible(cuda):
-    """Batch 256, the shipped CIFAR architecture: four fused steps eager vs CUDA-graph replay give identical losses and
-    identical parameters (no floating-point atomics anywhere; side streams only reorder independent work)."""
+FULL_CONFIGS = [('cifar', 256, 'rep'), ('stl', 128, 'rmb'), ('celeba', 128, 'rep')]     # BASELINE.json configs[1..3], per-GPU batch
+
+
+@pytest.mark.parametrize('name,B,loss_type', FULL_CONFIGS, ids=[c[0] for c in FULL_CONFIGS])
+def test_fullsize_steps_are_bit_reproducible(cuda, name, B, loss_type):
+    """The shipped architectures at their benchmark batch sizes: fused steps eager vs CUDA-graph replay give identical losses
+    and identical parameters (no floating-point atomics anywhere; side streams only reorder independent work)."""
     from mmdgan_b200 import experiments as ex
     from mmdgan_b200.engine import SNGanEngine
-    B = 256
-    e1 = SNGanEngine(ex.cifar(), B, loss_type='rep', seed=7, use_graph=False)
-    e2 = SNGanEngine(ex.cifar(), B, loss_type='rep', seed=7, use_graph=True)
-    for it in range(4):
-        data, code = cifar_batch(B, 100 + it)
+    arch = ex.ARCHITECTURES[name]()
+    c, h, w = arch['input'][0]
+    e1 = SNGanEngine(arch, B, loss_type=loss_type, seed=7, use_graph=False)
+    e2 = SNGanEngine(arch, B, loss_type=loss_type, seed=7, use_graph=True)
+    for it in range(3):
+        g = torch.Generator().manual_seed(100 + it)
+        data, code = torch.rand(B, c, h, w, generator=g) * 2 - 1, torch.randn(B, arch['code'][0][0], generator=g)
         l1, l2 = e1.step(data, code), e2.step(data, code)
         assert l1 == l2, (it, l1, l2)
         assert np.isfinite(l1).all()
