@@ -82,15 +82,17 @@ class Layer(object):
         self.kernel_shape = None
         self.use_u = None
         self.sn_x_shape = None
+        self.sn_pim = False             # SPECTRAL_NORM_MODE 'sn_paper': the conv kernel as a [k*k*C, C'] matrix (layer_func.py:811-814)
 
     # ---- spectral-norm routing (math_func.py:470-528): integer compares, must match the reference bit for bit
     def _sn_routing(self):
         op = self.design['op']
-        if FLAGS.SPECTRAL_NORM_MODE not in {'default', 'PICO', 'pico'} and op in {'c', 'tc'}:
-            raise NotImplementedError('{}: SPECTRAL_NORM_MODE {} not built yet (SURVEY section 8 f4)'.format(
-                self.layer_scope, FLAGS.SPECTRAL_NORM_MODE))
-        if op == 'd':
-            num_in, num_out = self.kernel_shape
+        if FLAGS.SPECTRAL_NORM_MODE not in {'default', 'PICO', 'pico', 'sn_paper', 'PIM', 'pim'}:
+            raise NotImplementedError('{}: SPECTRAL_NORM_MODE {} is not implemented.'.format(self.layer_scope, FLAGS.SPECTRAL_NORM_MODE))
+        self.sn_pim = FLAGS.SPECTRAL_NORM_MODE in {'sn_paper', 'PIM', 'pim'} and op in {'c', 'tc'}
+        if op == 'd' or self.sn_pim:
+            # PIM: tf.reshape(kernel, (-1, kernel_shape[3])) then the dense routine (layer_func.py:811-814; math_func.py:477-486)
+            num_in, num_out = self.kernel_shape if op == 'd' else (int(np.prod(self.kernel_shape[:3])), self.kernel_shape[3])
             self.use_u = True if num_in <= num_out else False
             self.sn_x_shape = [1, num_in] if self.use_u else [1, num_out]
         else:

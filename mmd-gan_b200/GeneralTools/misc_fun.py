@@ -14,7 +14,7 @@ class SetFlag(object):
         self.IMAGE_FORMAT = 'channels_first'
         self.IMAGE_FORMAT_ALIAS = 'NCHW'
         self.WEIGHT_INITIALIZER = 'default'
-        self.SPECTRAL_NORM_MODE = 'default'   # 'default' = 'PICO'; 'sn_paper' = PIM (not built yet: raises)
+        self.SPECTRAL_NORM_MODE = 'default'   # 'default' = 'PICO' (power iteration on the conv operator); 'sn_paper' = PIM (on the reshaped kernel matrix)
         # B200 engine knobs (new): 3 = parity mode (fp32 values as two 16-bit planes, three plane-pair tensor-core products:
         # fp16 planes in the forward passes, bf16 planes in the gradient passes), 1 = a single bf16 pass (speed mode, not
         # parity grade)

@@ -232,10 +232,20 @@ class NetRuntime(object):
         L.cs_T = 0
         # ---- spectral norm state (batch-1 power iteration)
         if L.has_sn:
-            x_is_input = ly.use_u if L.op != 'tc' else (not ly.use_u)
+            L.sn_lop = lop
+            if ly.sn_pim:
+                # PIM ('sn_paper'): power iteration on the canonical kernel viewed as the [k*k*C, C'] matrix -- the same memory,
+                # so d(sigma)/dW lands in the canonical layout and the gradient combine is unchanged
+                rows, cols = int(np.prod(ly.kernel_shape[:3])), int(ly.kernel_shape[3])
+                L.sn_lop = K.LinearOp('d', [rows], [cols], npass=npass, device=dev)
+                x_is_input = ly.use_u
+                r_x, c_x = (1, L.sn_lop.Cs_in) if x_is_input else (1, L.sn_lop.Cs_out)
+                r_y, c_y = (1, L.sn_lop.Cs_out) if x_is_input else (1, L.sn_lop.Cs_in)
+            else:
+                x_is_input = ly.use_u if L.op != 'tc' else (not ly.use_u)
+                r_x, c_x = (L.rows_in, L.Cs_in) if x_is_input else (L.rows_out, L.Cs_out)
+                r_y, c_y = (L.rows_out, L.Cs_out) if x_is_input else (L.rows_in, L.Cs_in)
             L.sn_x_is_input = x_is_input
-            r_x, c_x = (L.rows_in, L.Cs_in) if x_is_input else (L.rows_out, L.Cs_out)
-            r_y, c_y = (L.rows_out, L.Cs_out) if x_is_input else (L.rows_in, L.Cs_in)
             # the vector that enters the layer op is a forward operand (value planes: fp16 in the parity mode); the one that
             # enters the adjoint meets the bf16 input-gradient weights with six plane pairs
             npl = K.mode_planes(npass)
@@ -249,12 +259,12 @@ class NetRuntime(object):
             L.sn_v = torch.zeros((1, r_y, c_y), dtype=torch.float32, device=dev)
             L.sn_w = torch.zeros((1, r_x, c_x), dtype=torch.float32, device=dev)
             L.sigma = torch.ones(1, dtype=torch.float32, device=dev)
-            Rs, NCs, _, sps, _ = lop.wgrad_plan(1)
+            Rs, NCs, _, sps, _ = L.sn_lop.wgrad_plan(1)
             L.sn_splits = sps
             L.sn_parts = z(sps * Rs * NCs)
             L.sn_S = z(lop.canon_numel)
-            if L.op == 'd':
-                L.sn_flat = (lop.in_flat if x_is_input else lop.out_flat)
+            if L.op == 'd' or ly.sn_pim:
+                L.sn_flat = (L.sn_lop.in_flat if x_is_input else L.sn_lop.out_flat)
         return L
 
     def refresh(self):
@@ -263,6 +273,8 @@ class NetRuntime(object):
             packs, perms = [], []
             for L in self.layers:
                 packs += L.lop.pack_descs(self.view(self.w, L.ly.kernel_name))
+                if L.has_sn and L.sn_lop is not L.lop:
+                    packs += L.sn_lop.pack_descs(self.view(self.w, L.ly.kernel_name))
                 c, hw = self._feat_perm(L)
                 if L.has_bias:
                     perms.append((self.view(self.w, L.ly.bias_name), L.bias_int, L.Cout, c, hw))
@@ -412,7 +424,7 @@ class SNGanEngine(object):
     def _sn_layer(self, L):
         """One PICO power iteration of one spectrally-normalised layer (math_func.py:661-672): sigma = ||F(x)||,
         x' = l2n(F^T(l2n(F(x)))) and S = d(sigma)/dW = wgrad(x, u)."""
-        lop = L.lop
+        lop = L.sn_lop
         if L.sn_x_is_input:
             lop.forward(L.sn_x, 1, L.sn_v, out_mode=2)
             K.sn_normalize(L.sn_v, L.sn_v.numel(), L.sn_y, sigma_out=L.sigma, eps=FLAGS.EPSI)

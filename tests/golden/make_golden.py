@@ -41,10 +41,10 @@ def sn_case(op, cin, cout, hin, k, s, seed):
                 sigma=sigma.detach().numpy(), x_update=x_upd.numpy(), dsigma_dw=dsdw.numpy())
 
 
-def step_case(loss_type):
+def step_case(loss_type, sn_mode='default'):
     arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
     B = 8
-    m = onet.OracleSNGan(arch, loss_type, dtype=torch.float64, seed=3)
+    m = onet.OracleSNGan(arch, loss_type, dtype=torch.float64, seed=3, sn_mode=sn_mode)
     onet.warm_spectral_norm(m, 6)
     data, code = onet.synthetic_batch(arch, B, seed=5, dtype=torch.float32)       # fp32-representable inputs
     data, code = data.double(), code.double()
@@ -80,6 +80,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'sn_{}.npz'.format(name)), **sn_case(*c, seed=10 + i))
     for lt in ('rep', 'rmb'):
         np.savez_compressed(os.path.join(HERE, 'step_tiny_{}.npz'.format(lt)), **step_case(lt))
+    np.savez_compressed(os.path.join(HERE, 'step_tiny_rep_pim.npz'), **step_case('rep', sn_mode='sn_paper'))
 
 
 if __name__ == '__main__':

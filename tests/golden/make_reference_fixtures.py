@@ -171,9 +171,11 @@ def _named_grads(grads_and_vars):
     return {names[id(v)]: (torch.zeros_like(v) if g is None else g).detach().numpy() for g, v in grads_and_vars}
 
 
-def ref_step_case(loss_type):
-    """Twin of make_golden.step_case: same architecture, initial variables, data and codes."""
-    base = mg.step_case(loss_type)
+def ref_step_case(loss_type, sn_mode='default'):
+    """Twin of make_golden.step_case: same architecture, initial variables, data and codes.  sn_mode 'sn_paper' runs the
+    reference with FLAGS.SPECTRAL_NORM_MODE = 'sn_paper' (power iteration on the reshaped kernel matrix, layer_func.py:811-814)."""
+    base = mg.step_case(loss_type, sn_mode)
+    FLAGS.SPECTRAL_NORM_MODE = sn_mode
     arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
     B = base['data'].shape[0]
     run = ReferenceRun(arch, loss_type, lr_list=(5e-4, 2e-4))
@@ -197,6 +199,7 @@ def ref_step_case(loss_type):
         if k.startswith('after:') or k.startswith('state_after:'):
             out[k] = store[k.split(':', 1)[1]].detach().numpy()
     assert int(run.global_step) == 1
+    FLAGS.SPECTRAL_NORM_MODE = 'default'
     return out
 
 
@@ -246,6 +249,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'ref_sn_{}.npz'.format(name)), **ref_sn_case(*c, seed=10 + i))
     for lt in ('rep', 'rmb'):
         np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_{}.npz'.format(lt)), **ref_step_case(lt))
+    np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_rep_pim.npz'), **ref_step_case('rep', sn_mode='sn_paper'))
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep.npz'), **ref_step_cifar())
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep_k27.npz'), **ref_step_cifar(batch=8, act_k=2.7))
     # the other shipped architecture dictionaries, parsed from the reference's scripts (one step, batch 2, sparse samples)

@@ -66,12 +66,16 @@ def test_spectral_norm_class_against_golden(cuda, path):
 
 
 @pytest.mark.parametrize('family', ['', 'ref_'])
-@pytest.mark.parametrize('loss_type', ['rep', 'rmb'])
-def test_engine_step_against_golden(cuda, loss_type, family):
+@pytest.mark.parametrize('loss_type', ['rep', 'rmb', 'rep_pim'])
+def test_engine_step_against_golden(cuda, loss_type, family, monkeypatch):
     from oracle import architectures as oa          # the architecture dictionary only
     from mmdgan_b200.engine import SNGanEngine
     z = np.load(os.path.join(GOLD, '{}step_tiny_{}.npz'.format(family, loss_type)))
     arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    if loss_type.endswith('_pim'):          # the reference's FLAGS.SPECTRAL_NORM_MODE = 'sn_paper'
+        from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+        monkeypatch.setattr(FLAGS, 'SPECTRAL_NORM_MODE', 'sn_paper')
+        loss_type = loss_type[:-4]
     eng = SNGanEngine(arch, 8, loss_type=loss_type, use_graph=False)
     for net in (eng.G, eng.D):
         for name in net.var_offsets:

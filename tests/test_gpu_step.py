@@ -20,10 +20,10 @@ def rel(a, b):
     return float((a - b).norm() / max(float(b.norm()), 1e-30))
 
 
-def make_pair(arch, B, loss_type, rep_weights=(0.0, -1.0), seed=3, warm=6, npass=3, use_graph=False):
+def make_pair(arch, B, loss_type, rep_weights=(0.0, -1.0), seed=3, warm=6, npass=3, use_graph=False, sn_mode='default'):
     """Oracle (float64) and engine holding the same variables and state."""
     from mmdgan_b200.engine import SNGanEngine
-    orc = onet.OracleSNGan(arch, loss_type, rep_weights=rep_weights, dtype=torch.float64, seed=seed)
+    orc = onet.OracleSNGan(arch, loss_type, rep_weights=rep_weights, dtype=torch.float64, seed=seed, sn_mode=sn_mode)
     if warm:
         onet.warm_spectral_norm(orc, warm)
     eng = SNGanEngine(arch, B, loss_type=loss_type, rep_weights=rep_weights, npass=npass, use_graph=use_graph)
@@ -109,6 +109,21 @@ def test_step_parity_tiny(cuda, loss_type):
     B = 16
     orc, eng = make_pair(arch, B, loss_type)
     check_step(orc, eng, arch, B, seed=5)
+
+
+def test_step_parity_pim_spectral_norm_mode(cuda, monkeypatch):
+    """FLAGS.SPECTRAL_NORM_MODE = 'sn_paper' (PIM, layer_func.py:811-814): the power iteration runs on the conv kernel reshaped
+    to the [k*k*Cin, Cout] matrix instead of the conv operator; routing (use_u) and in_rand shapes follow the dense rule."""
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    monkeypatch.setattr(FLAGS, 'SPECTRAL_NORM_MODE', 'sn_paper')
+    arch = oa.tiny(act_k=2.6)
+    B = 16
+    orc, eng = make_pair(arch, B, 'rep', sn_mode='sn_paper')
+    assert all(L.ly.sn_pim for L in eng.D.layers if L.op != 'd')
+    check_step(orc, eng, arch, B, seed=5)
+    arch = oa.cifar(act_k=2.7)
+    orc, eng = make_pair(arch, 4, 'rmb', sn_mode='sn_paper')
+    check_step(orc, eng, arch, 4, seed=6)
 
 
 def test_step_parity_tiny_first_step_unnormalised_in_rand(cuda):

@@ -96,6 +96,31 @@ def test_linear_op_launch_plans():
         K.LinearOp('sc', [8, 8, 8], [8, 8, 8], 3, 1, device='cpu')
 
 
+def test_spectral_norm_routing_pico_and_pim(monkeypatch):
+    """use_u / in_rand shapes: PICO compares the operator's input and output sizes (math_func.py:497-515), PIM
+    ('sn_paper') reshapes the kernel to [k*k*Cin, Cout] and follows the dense rule (layer_func.py:811-814, math_func.py:477-486)."""
+    from mmdgan_b200.GeneralTools.layer_func import Net, Routine
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200 import experiments as ex
+
+    def shapes():
+        r = Routine(Net(ex.cifar()['discriminator'], 'dis', 'channels_first'))
+        r.add_input_layers([64, 3, 32, 32], [0])
+        r.seq_links(list(range(8)))
+        r.add_output_layers([7])
+        return [(ly.use_u, ly.sn_x_shape, ly.sn_pim) for ly in r.ordered_layers()]
+    pico = shapes()
+    assert [p[0] for p in pico] == [True, False, True, False, True, False, True, False]       # SURVEY appendix A.2
+    assert pico[0][1] == [1, 3, 32, 32] and pico[1][1] == [1, 128, 16, 16] and pico[7][1] == [1, 16] and not any(p[2] for p in pico)
+    monkeypatch.setattr(FLAGS, 'SPECTRAL_NORM_MODE', 'sn_paper')
+    pim = shapes()
+    assert [p[1] for p in pim] == [[1, 27], [1, 128], [1, 128], [1, 256], [1, 256], [1, 512], [1, 512], [1, 16]]
+    assert [p[0] for p in pim] == [True] + [False] * 7 and [p[2] for p in pim] == [True] * 7 + [False]
+    monkeypatch.setattr(FLAGS, 'SPECTRAL_NORM_MODE', 'no_such_mode')
+    with pytest.raises(NotImplementedError):
+        shapes()
+
+
 def test_cabi_exports_every_declared_symbol():
     from mmdgan_b200 import _lib
     hdr = open(os.path.join(ROOT, 'include', 'mmdgan_b200.h')).read()

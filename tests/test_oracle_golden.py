@@ -53,11 +53,13 @@ def test_sn_golden(path):
 
 
 @pytest.mark.parametrize('family', ['', 'ref_'])
-@pytest.mark.parametrize('loss_type', ['rep', 'rmb'])
+@pytest.mark.parametrize('loss_type', ['rep', 'rmb', 'rep_pim'])
 def test_step_golden(loss_type, family):
     z = np.load(os.path.join(GOLD, '{}step_tiny_{}.npz'.format(family, loss_type)))
     arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
-    m = onet.OracleSNGan(arch, loss_type, dtype=torch.float64, seed=3)
+    # *_pim: FLAGS.SPECTRAL_NORM_MODE = 'sn_paper' in the reference (power iteration on the reshaped kernel matrix)
+    loss_type, sn_mode = (loss_type[:-4], 'sn_paper') if loss_type.endswith('_pim') else (loss_type, 'default')
+    m = onet.OracleSNGan(arch, loss_type, dtype=torch.float64, seed=3, sn_mode=sn_mode)
     for store, pre in ((m.gen_params, 'before:'), (m.dis_params, 'before:'), (m.gen_state, 'state_before:'), (m.dis_state, 'state_before:')):
         for k in list(store.keys()):
             store[k] = torch.from_numpy(z[pre + k])
