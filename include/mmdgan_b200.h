@@ -247,7 +247,8 @@ int mmdgan_bn_bwd_apply(const float* da, const float* z, const float* mean, cons
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused pairwise squared distance -> Gaussian kernel(s) -> rep / rmb / mmd_g / mgb losses + score gradients
- * (GeneralTools/math_func.py:767-858, 1048-1069, 1288-1473, 2160-2193, 2505-2550).  Row-block form for data
+ * (GeneralTools/math_func.py:767-858, 1048-1069, 1288-1473, 2160-2193, 2505-2550) and the t-distribution kernel mixture
+ * mmd_t (1087-1184, 2263-2275).  Row-block form for data
  * parallelism: local rows are rows [row0, row0+b) of the Bg global rows. */
 typedef struct mmdgan_mmd_desc {
     const float* gen_loc;
@@ -260,6 +261,8 @@ typedef struct mmdgan_mmd_desc {
     float cD[3];
     int bmode[3];
     float bval[3];
+    int family;    /* 0: Gaussian kernels, sigma[] = bandwidths; 1: t-distribution kernels (mmd_t), sigma[] = the alphas */
+    float beta;    /* t-distribution kernels only (math_func.py:2110) */
     float* sums;   /* [6] */
     float* losses; /* [2] loss_gen, loss_dis */
     float* dLg_dgen;
@@ -268,7 +271,7 @@ typedef struct mmdgan_mmd_desc {
     float* dLd_dreal;
     void* workspace; /* mmdgan_mmd_workspace(b) bytes, zeroed once before the first call */
 } mmdgan_mmd_desc;
-/* fills n_sigma / sigma / cD / bmode / bval for loss_type in {"rep","rmb","mmd_g","mgb"} and rep_weights (w0, w1);
+/* fills n_sigma / sigma / cD / bmode / bval / family / beta for loss_type in {"rep","rmb","mmd_g","mgb","mmd_t"} and rep_weights (w0, w1);
  * returns MMDGAN_EINVAL for unknown types or w0 - w1 != 1 (the reference's assert, math_func.py:1340) */
 int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, float w1);
 size_t mmdgan_mmd_workspace(int b);

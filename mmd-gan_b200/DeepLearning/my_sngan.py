@@ -44,7 +44,7 @@ class SNGan(object):
             raise NotImplementedError('Conditional models (num_class >= 2) are not on the hot path.')
         if image_transpose:
             raise NotImplementedError('image_transpose is not on the hot path.')
-        if loss_type not in {'rep', 'rmb', 'mmd_g', 'fixed_g', 'mgb'}:
+        if loss_type not in {'rep', 'rmb', 'mmd_g', 'fixed_g', 'mgb', 'mmd_t', 'fixed_t'}:
             raise NotImplementedError('loss_type {} is not on the hot path (rep / rmb).'.format(loss_type))
         self.engine = None
         self.Gen = None

@@ -164,10 +164,10 @@ class _FusedMmdLoss(torch.autograd.Function):
 
 
 class GANLoss(object):
-    """math_func.py:2088.  Hot-path loss types: 'rep', 'rmb' (and the siblings 'mmd_g' / 'fixed_g', 'mgb')."""
+    """math_func.py:2088.  Hot-path loss types: 'rep', 'rmb' (and the siblings 'mmd_g' / 'fixed_g', 'mgb', 'mmd_t' / 'fixed_t')."""
 
     FUSED = {'rep': 'rep', 'rep_mmd_g': 'rep', 'rmb': 'rmb', 'rep_b': 'rmb', 'rep_mmd_b': 'rmb',
-             'mmd_g': 'mmd_g', 'fixed_g': 'mmd_g', 'mgb': 'mgb'}
+             'mmd_g': 'mmd_g', 'fixed_g': 'mmd_g', 'mgb': 'mgb', 'mmd_t': 'mmd_t', 'fixed_t': 'mmd_t'}
 
     def __init__(self, do_summary=False):
         self.do_summary = do_summary
@@ -205,7 +205,7 @@ class GANLoss(object):
             self.sigma = kwargs['sigma']
         if 'rep_weights' in kwargs:
             self.repulsive_weights = list(kwargs['rep_weights'])
-        if loss_type in {'fixed_g', 'mmd_g', 'rep', 'rep_gp', 'rmb', 'rmb_gp', 'mgb'}:
+        if loss_type in {'fixed_g', 'mmd_g', 'fixed_t', 'mmd_t', 'rep', 'rep_gp', 'rmb', 'rmb_gp', 'mgb'}:
             assert self.batch_size is not None, 'GANLoss: batch_size must be provided'       # math_func.py:2589-2592
         if loss_type in {'rep_gp', 'rmb_gp', 'wasserstein'}:
             assert self.dis_penalty is not None, 'Discriminator penalty must be provided.'

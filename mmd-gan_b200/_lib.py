@@ -88,7 +88,7 @@ class MmdDesc(C.Structure):
         ('gen_loc', C.c_void_p), ('real_loc', C.c_void_p), ('gen_all', C.c_void_p), ('real_all', C.c_void_p),
         ('b', C.c_int), ('Bg', C.c_int), ('row0', C.c_int), ('d', C.c_int),
         ('n_sigma', C.c_int), ('sigma', C.c_float * 8), ('cD', C.c_float * 3), ('bmode', C.c_int * 3),
-        ('bval', C.c_float * 3),
+        ('bval', C.c_float * 3), ('family', C.c_int), ('beta', C.c_float),
         ('sums', C.c_void_p), ('losses', C.c_void_p),
         ('dLg_dgen', C.c_void_p), ('dLg_dreal', C.c_void_p), ('dLd_dgen', C.c_void_p), ('dLd_dreal', C.c_void_p),
         ('workspace', C.c_void_p)]

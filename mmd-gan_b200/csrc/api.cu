@@ -323,6 +323,8 @@ int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, fl
     for (int i = 0; i < 3; ++i) { d->bmode[i] = 0; d->bval[i] = 0.f; }
     d->n_sigma = 1;
     d->sigma[0] = 1.0f;
+    d->family = 0;
+    d->beta = 2.0f;
     const bool rep = !strcmp(loss_type, "rep") || !strcmp(loss_type, "rep_mmd_g");
     const bool rmb = !strcmp(loss_type, "rmb") || !strcmp(loss_type, "rep_b") || !strcmp(loss_type, "rep_mmd_b");
     if (rep || rmb) {
@@ -340,6 +342,14 @@ int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, fl
     if (!strcmp(loss_type, "mmd_g") || !strcmp(loss_type, "fixed_g")) { /* math_func.py:2160-2173, sigma list 2108 */
         d->n_sigma = 5;
         d->sigma[0] = 1.0f; d->sigma[1] = sqrtf(2.0f); d->sigma[2] = 2.0f; d->sigma[3] = sqrtf(8.0f); d->sigma[4] = 4.0f;
+        d->cD[0] = -1.0f; d->cD[1] = 2.0f; d->cD[2] = -1.0f;
+        return MMDGAN_OK;
+    }
+    if (!strcmp(loss_type, "mmd_t") || !strcmp(loss_type, "fixed_t")) { /* math_func.py:2263-2275, alpha list 2109, beta 2110 */
+        d->family = 1;
+        d->n_sigma = 5;
+        d->sigma[0] = 0.2f; d->sigma[1] = 0.5f; d->sigma[2] = 1.0f; d->sigma[3] = 2.0f; d->sigma[4] = 5.0f;
+        d->beta = 2.0f;
         d->cD[0] = -1.0f; d->cD[1] = 2.0f; d->cD[2] = -1.0f;
         return MMDGAN_OK;
     }
@@ -368,9 +378,18 @@ int mmdgan_mmd_fwd_bwd(const mmdgan_mmd_desc* d, void* stream) {
     memset(&p, 0, sizeof(p));
     p.gen_loc = d->gen_loc; p.real_loc = d->real_loc; p.gen_all = d->gen_all; p.real_all = d->real_all;
     p.b = d->b; p.Bg = d->Bg; p.row0 = d->row0; p.d = d->d; p.n_sigma = d->n_sigma;
+    if (d->family != 0 && d->family != 1) return fail(MMDGAN_EINVAL, "mmdgan_mmd_fwd_bwd: unknown kernel family");
+    if (d->family == 1 && !(d->beta > 0.f)) return fail(MMDGAN_EINVAL, "mmdgan_mmd_fwd_bwd: beta must be positive");
+    p.family = d->family;
+    p.inv_beta = d->family == 1 ? 1.0f / d->beta : 0.f;
     for (int i = 0; i < d->n_sigma; ++i) {
-        if (!(d->sigma[i] > 0.f)) return fail(MMDGAN_EINVAL, "mmdgan_mmd_fwd_bwd: sigma must be positive");
-        p.c_s[i] = 1.0f / (2.0f * d->sigma[i] * d->sigma[i]);
+        if (!(d->sigma[i] > 0.f)) return fail(MMDGAN_EINVAL, "mmdgan_mmd_fwd_bwd: sigma / alpha must be positive");
+        if (d->family == 0) {
+            p.c_s[i] = 1.0f / (2.0f * d->sigma[i] * d->sigma[i]);
+        } else {
+            p.c_s[i] = d->sigma[i];
+            p.c_t[i] = 1.0f / (d->sigma[i] * d->beta);
+        }
     }
     for (int i = 0; i < 3; ++i) { p.cD[i] = d->cD[i]; p.bmode[i] = d->bmode[i]; p.bval[i] = d->bval[i]; }
     p.sums = d->sums; p.losses = d->losses; p.dLg_dgen = d->dLg_dgen; p.dLg_dreal = d->dLg_dreal; p.dLd_dgen = d->dLd_dgen;

@@ -99,7 +99,10 @@ struct MmdParams {
     const float* real_all;  // [Bg][d]
     int b, Bg, row0, d;
     int n_sigma;
-    float c_s[8];      // 1 / (2 sigma^2)
+    int family;        // 0: Gaussian kernels exp(-d / (2 sigma^2)); 1: t-distribution kernels (1 + d / (alpha beta))^-alpha
+    float c_s[8];      // Gaussian: 1 / (2 sigma^2); t: alpha
+    float c_t[8];      // t: 1 / (alpha beta)
+    float inv_beta;    // t: 1 / beta
     float cD[3];       // loss_dis = cD[0] e_gg^b + cD[1] e_gr^b + cD[2] e_rr^b
     int bmode[3];      // 0 none, 1 lower bound (max), 2 upper bound (min)   [gg, gr, rr]
     float bval[3];

@@ -3,7 +3,8 @@
 // Replaces the ~40 TF ops of GANLoss._repulsive_mmd_g_ / _repulsive_mmd_g_bounded_ / _mmd_g_ / _mmd_g_bound_
 // (GeneralTools/math_func.py:2160-2193, 2505-2550): get_squared_dist (767-858, Gram trick with clamp at 0),
 // matrix_mean_wo_diagonal (1048-1069, the i == j entry is dropped from ALL three matrices), mmd_g (1288-1352),
-// mmd_g_bounded (1356-1431), mixture_mmd_g (1435-1473) and the backward pass TF derives from them.
+// mmd_g_bounded (1356-1431), mixture_mmd_g (1435-1473), mmd_t / mixture_mmd_t (1087-1184: t-distribution kernels
+// k = exp(-alpha log(d / (alpha beta) + 1))) and the backward pass TF derives from them.
 //
 // One warp owns one score row (a "row task": first the local generated rows, then the local real rows) and sweeps
 // every column of the (gathered) generated and real score matrices, which are staged tile by tile, transposed, in
@@ -129,11 +130,20 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
                 float ku = 0.f, kb = 0.f, dku = 0.f, dkb = 0.f;   // kernel sums and -(dK/dd) sums over sigma
                 for (int s = 0; s < p.n_sigma; ++s) {
                     const float cs = p.c_s[s];
-                    const float eu = exp2f(-dist * cs * kLog2e);
-                    const float eb = (bm == 0) ? eu : exp2f(-distb * cs * kLog2e);
-                    ku += eu; kb += eb;
-                    dku = fmaf(cs, eu, dku);
-                    dkb = fmaf(cs, eb, dkb);
+                    if (p.family == 0) {                 // Gaussian: k = exp(-cs d), -dk/dd = cs k
+                        const float eu = exp2f(-dist * cs * kLog2e);
+                        const float eb = (bm == 0) ? eu : exp2f(-distb * cs * kLog2e);
+                        ku += eu; kb += eb;
+                        dku = fmaf(cs, eu, dku);
+                        dkb = fmaf(cs, eb, dkb);
+                    } else {                             // t: k = u^-alpha with u = 1 + d / (alpha beta), -dk/dd = k / (beta u)
+                        const float uu = fmaf(dist, p.c_t[s], 1.0f), ub = fmaf(distb, p.c_t[s], 1.0f);
+                        const float eu = exp2f(-cs * log2f(uu));
+                        const float eb = (bm == 0) ? eu : exp2f(-cs * log2f(ub));
+                        ku += eu; kb += eb;
+                        dku = fmaf(eu, p.inv_beta / uu, dku);
+                        dkb = fmaf(eb, p.inv_beta / ub, dkb);
+                    }
                 }
                 // d dist / d x_i = 2 (x_i - y_j);  dK/dd = -dk
                 const float wG = -cG * mult * 2.0f * dku * m0;

@@ -118,6 +118,24 @@ def mixture_mmd_g(dist_xx, dist_xy, dist_yy, batch_size, sigma):
 
 
 MIX_SIGMA = [1.0, float(np.sqrt(2.0)), 2.0, float(np.sqrt(8.0)), 4.0]   # math_func.py:2108
+MIX_ALPHA = [0.2, 0.5, 1.0, 2.0, 5.0]                                   # math_func.py:2109 (mmd-t kernel scales)
+MIX_BETA = 2.0                                                          # math_func.py:2110
+
+
+def mmd_t(dist_xx, dist_xy, dist_yy, batch_size, alpha=1.0, beta=2.0):
+    """math_func.py:1087-1142: t-distribution kernel k = exp(-alpha * log(d / (beta * alpha) + 1))."""
+    k = lambda d: torch.exp(-alpha * torch.log(d / (beta * alpha) + 1.0))
+    m = float(batch_size)
+    return (matrix_mean_wo_diagonal(k(dist_xx), m) + matrix_mean_wo_diagonal(k(dist_yy), m)
+            - 2.0 * matrix_mean_wo_diagonal(k(dist_xy), m))
+
+
+def mixture_mmd_t(dist_xx, dist_xy, dist_yy, batch_size, alpha, beta=2.0):
+    """math_func.py:1145-1184 (fixed alpha list)."""
+    mmd = 0.0
+    for a in alpha:
+        mmd = mmd + mmd_t(dist_xx, dist_xy, dist_yy, batch_size, alpha=a, beta=beta)
+    return mmd
 
 
 def gan_loss(score_gen, score_data, loss_type, batch_size=None, rep_weights=(0.0, -1.0), sigma=None):
@@ -136,6 +154,9 @@ def gan_loss(score_gen, score_data, loss_type, batch_size=None, rep_weights=(0.0
                              custom_weights=rep_weights)
     if loss_type in {'fixed_g', 'mmd_g'}:                 # math_func.py:2160-2173
         lg = mixture_mmd_g(d_gg, d_gd, d_dd, batch_size, sigma=MIX_SIGMA if sigma is None else sigma)
+        return lg, -lg
+    if loss_type in {'fixed_t', 'mmd_t'}:                 # math_func.py:2263-2275
+        lg = mixture_mmd_t(d_gg, d_gd, d_dd, batch_size, alpha=MIX_ALPHA, beta=MIX_BETA)
         return lg, -lg
     if loss_type == 'mgb':                                # math_func.py:2175-2193
         lg = mmd_g(d_gg, d_gd, d_dd, batch_size, sigma=1.0)

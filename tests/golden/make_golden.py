@@ -69,7 +69,7 @@ def step_case(loss_type, sn_mode='default'):
 
 
 def main():
-    for lt in ('rep', 'rmb', 'mmd_g', 'mgb'):
+    for lt in ('rep', 'rmb', 'mmd_g', 'mgb', 'mmd_t'):
         for b in (2, 3, 64) if lt in ('rep', 'rmb') else (64,):
             np.savez_compressed(os.path.join(HERE, 'mmd_{}_{}.npz'.format(lt, b)), **mmd_case(lt, b))
     np.savez_compressed(os.path.join(HERE, 'mmd_rep_256.npz'), **mmd_case('rep', 256))

@@ -238,7 +238,7 @@ def ref_step_cifar(batch=4, seed=2, steps=2, act_k=None, script='my_test_cifar.p
 
 
 def main():
-    for lt in ('rep', 'rmb', 'mmd_g', 'mgb'):
+    for lt in ('rep', 'rmb', 'mmd_g', 'mgb', 'mmd_t'):
         for b in (2, 3, 64) if lt in ('rep', 'rmb') else (64,):
             np.savez_compressed(os.path.join(HERE, 'ref_mmd_{}_{}.npz'.format(lt, b)), **ref_mmd_case(lt, b))
     np.savez_compressed(os.path.join(HERE, 'ref_mmd_rep_256.npz'), **ref_mmd_case('rep', 256))

@@ -31,8 +31,8 @@ def rel(a, b):
 def test_ganloss_autograd_against_golden(cuda, path):
     from mmdgan_b200.GeneralTools.math_func import GANLoss
     z = np.load(path)
-    lt = _stem(path).split('_')[1]
-    lt = 'mmd_g' if lt == 'mmd' else lt
+    parts = _stem(path).split('_')
+    lt = 'mmd_' + parts[2] if parts[1] == 'mmd' else parts[1]               # mmd_<loss>_<B>.npz with loss in {rep, rmb, mgb, mmd_g, mmd_t}
     g = torch.from_numpy(z['gen']).cuda().requires_grad_(True)
     r = torch.from_numpy(z['real']).cuda().requires_grad_(True)
     loss_gen, loss_dis = GANLoss(False).apply(g, r, lt, batch_size=g.shape[0], d=g.shape[1], rep_weights=list(z['rep_weights']))

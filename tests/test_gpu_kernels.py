@@ -209,7 +209,7 @@ def test_direct_conv_image_layers(cuda):
 MMD_CASES = [(2, 16), (3, 16), (64, 16), (200, 16), (256, 16), (96, 8), (40, 32), (130, 64), (33, 4)]
 
 
-@pytest.mark.parametrize('loss_type', ['rep', 'rmb', 'mmd_g', 'mgb'])
+@pytest.mark.parametrize('loss_type', ['rep', 'rmb', 'mmd_g', 'mgb', 'mmd_t'])
 @pytest.mark.parametrize('bd', MMD_CASES, ids=[str(c) for c in MMD_CASES])
 def test_mmd_fused_parity(cuda, bd, loss_type):
     from mmdgan_b200 import kernels as K

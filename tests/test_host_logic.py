@@ -143,7 +143,9 @@ def test_cabi_argument_validation_without_a_gpu():
     assert list(d.bmode) == [1, 0, 2] and list(d.bval) == [0.25, 0.0, 4.0]
     assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rmb', 1.0, 0.0) == 0 and list(d.bmode) == [1, 0, 2]
     assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rmb', 2.0, 1.0) == 0 and list(d.bmode) == [1, 0, 1]
-    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'mmd_g', 0.0, 0.0) == 0 and d.n_sigma == 5
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'mmd_g', 0.0, 0.0) == 0 and d.n_sigma == 5 and d.family == 0
+    assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'mmd_t', 0.0, 0.0) == 0 and d.n_sigma == 5 and d.family == 1 and d.beta == 2.0
+    assert [round(v, 3) for v in d.sigma[:5]] == [0.2, 0.5, 1.0, 2.0, 5.0] and list(d.cD) == [-1.0, 2.0, -1.0]
     assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'rep', 0.0, 0.0) == _lib.MMDGAN_EINVAL
     assert b'w[0]-w[1] must be 1' in lib.mmdgan_last_error()
     assert lib.mmdgan_mmd_configure(ctypes.byref(d), b'hinge', 0.0, -1.0) == _lib.MMDGAN_EINVAL

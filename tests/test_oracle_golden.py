@@ -29,8 +29,8 @@ def _stem(path):
 @pytest.mark.parametrize('path', _fixtures('mmd_*.npz'), ids=os.path.basename)
 def test_mmd_golden(path):
     z = np.load(path)
-    loss_type = _stem(path).split('_')[1]
-    loss_type = 'mmd_g' if loss_type == 'mmd' else loss_type
+    parts = _stem(path).split('_')
+    loss_type = 'mmd_' + parts[2] if parts[1] == 'mmd' else parts[1]       # mmd_<loss>_<B>.npz with loss in {rep, rmb, mgb, mmd_g, mmd_t}
     out = omm.gan_loss_with_grads(z['gen'], z['real'], loss_type, rep_weights=tuple(z['rep_weights']))
     for k in ['loss_gen', 'loss_dis', 'dLg_dgen', 'dLd_dgen', 'dLd_ddata', 'dLg_ddata']:
         assert np.allclose(out[k], z[k], rtol=0, atol=1e-13), k

@@ -37,7 +37,7 @@ def test_rep_weights_assert():
         omm.gan_loss(x, x + 1, 'rep', rep_weights=(0.0, 0.0))
 
 
-@pytest.mark.parametrize('loss_type', ['rep', 'rmb', 'mmd_g', 'mgb'])
+@pytest.mark.parametrize('loss_type', ['rep', 'rmb', 'mmd_g', 'mgb', 'mmd_t'])
 def test_score_gradients_finite_differences(loss_type):
     rng = np.random.RandomState(3)
     g, r = rng.randn(6, 4) * 0.5, rng.randn(6, 4) * 0.5 + 0.1
