@@ -236,6 +236,11 @@ int mmdgan_colsum_planes(const mmdgan_bf16* x, long long plane, int npl, int row
  * Batch normalisation: tf.layers.batch_normalization(axis=1, training, fused=True) (layer_func.py:953-966) */
 int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                        float* invstd, float* moving_mean, float* moving_var, void* stream);
+/* Inference-mode statistics, tf.layers.batch_normalization(training=False) (reference layer_func.py:953-966 with
+ * is_training False, the eval_sampling graph of my_sngan.py:523-533): mean = moving_mean, invstd = 1/sqrt(moving_var + eps);
+ * mmdgan_bn_apply then normalises with them. */
+int mmdgan_bn_inference_stats(const float* moving_mean, const float* moving_var, int C, float eps, float* mean, float* invstd,
+                              void* stream);
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
                     long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, int* sat_flag, void* stream);
 int mmdgan_bn_bwd_reduce(const float* da, const float* z, const float* mean, const float* invstd, const float* gamma,

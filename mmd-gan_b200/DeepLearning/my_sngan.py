@@ -118,7 +118,50 @@ class SNGan(object):
         self.force_print = False
         return losses
 
-    def eval_sampling(self, *args, **kwargs):
-        raise NotImplementedError('eval_sampling / mdl_score need the Inception graph (out of scope, SURVEY.md 2.1 row 1b).')
+    def eval_sampling(self, filename, sub_folder, mesh_num=None, mesh_mode=0, if_invert=False, code_x=None, code_y=None,
+                      real_sample=False, sample_same_class=False, get_dis_score=True, do_sprite=True, do_embedding=False,
+                      ckpt_file=None, num_threads=7, data_source=None, **engine_kwargs):
+        """my_sngan.py:499-601: restore the latest (or the named) checkpoint, generate mesh_num[0] x mesh_num[1] samples with the
+        INFERENCE graph (moving-average batch norm), clip them to [-1, 1], optionally score real and generated samples with
+        the discriminator, and write the sample sprite(s) into the summary folder.  Returns a dictionary with the arrays the
+        reference evaluates (x_gen, x_real, s_x, s_gen) plus global_step and the sprite paths.  `data_source` overrides the
+        TFRecord prefix `filename` as the source of real samples (array / callable / 'synthetic', as in `training`)."""
+        import torch
+        from ..GeneralTools.graph_func import prepare_folder, rollback, write_sprite_wrapper
+        from ..GeneralTools.math_func import MeshCode
+        if do_embedding:
+            raise NotImplementedError('do_embedding writes a TensorBoard projector (graph_func.py:301-396): not on the hot path.')
+        ckpt_folder, summary_folder, _ = prepare_folder(filename, sub_folder=sub_folder)
+        if mesh_num is None:
+            mesh_num = (10, 10)
+        elif code_x is not None:
+            assert code_x.shape[0] == mesh_num[0] * mesh_num[1]
+        batch_size = mesh_num[0] * mesh_num[1]
+        engine = self.init_net(batch_size, **engine_kwargs)
+        global_step = rollback(engine, ckpt_folder, ckpt_file=ckpt_file)
+        out = {'global_step': global_step, 'x_real': None, 's_x': None, 's_gen': None, 'sprites': []}
+        if real_sample:
+            self.sample_same_class = sample_same_class
+            source = filename if data_source is None else data_source
+            out['x_real'] = self._batch_fn(source, batch_size, batch_size)(0)[0].float()
+        if code_x is None:
+            code_x = MeshCode(self.code_size, mesh_num=mesh_num).get_batch(mesh_mode, name='code_x')
+        code_batch = self.sample_codes(batch_size, code_x, code_y, name='code_te')
+        x_gen = engine.generate(code_batch['x'], is_training=False).clamp_(-1.0, 1.0)
+        if get_dis_score and real_sample:
+            scores = engine.discriminate(torch.cat([out['x_real'].to(x_gen.device), x_gen], 0))
+            out['s_x'], out['s_gen'] = scores[:batch_size].cpu().numpy(), scores[batch_size:].cpu().numpy()
+        out['x_gen'] = x_gen.cpu().numpy()
+        if out['x_real'] is not None:
+            out['x_real'] = out['x_real'].numpy()
+        if do_sprite:
+            tags = [('_r_', out['x_real'])] if real_sample else []
+            for tag, images in tags + [('_g_', out['x_gen'])]:
+                out['sprites'].append(write_sprite_wrapper(
+                    images, mesh_num, filename, file_folder=summary_folder,
+                    file_index=tag + sub_folder + '_' + str(global_step) + '_' + str(mesh_mode),
+                    if_invert=if_invert, image_format=FLAGS.IMAGE_FORMAT))
+        return out
 
-    mdl_score = eval_sampling
+    def mdl_score(self, *args, **kwargs):
+        raise NotImplementedError('mdl_score needs the Inception graph (out of scope, SURVEY.md 2.1 row 1b).')

@@ -99,6 +99,72 @@ def load_checkpoint(engine, path):
     return engine.global_step
 
 
+def rollback(engine, ckpt_folder, ckpt_file=None):
+    """graph_func.py:606-636 without the session: restore the engine's variables from the latest (or the named) checkpoint of
+    the folder and return its global step."""
+    path = get_ckpt(ckpt_folder, ckpt_file)
+    if path is None:
+        raise FileNotFoundError('No ckpt Model found at {}'.format(ckpt_folder))        # graph_func.py:633
+    step = load_checkpoint(engine, path)
+    FLAGS.print('Model reloaded from {}.'.format(path))
+    return step
+
+
+def sprite_array(images, mesh_num=None, if_invert=False):
+    """The uint8 mosaic the reference writes (graph_func.py:222-265): channels-last images [n, h, w(, c)], EACH image shifted
+    by its own minimum and divided by its own range (no guard: a constant image divides by zero exactly as there), optionally
+    inverted, laid out row-major on a mesh_num = (rows, columns) grid -- or, with mesh_num None, on the smallest square that
+    holds them, padded with black."""
+    x = np.asarray(images)
+    if x.ndim == 3:
+        x = x[..., None]
+    if x.shape[3] == 1:
+        x = np.repeat(x, 3, axis=3)
+    x = x.astype(np.float32)
+    flat = x.reshape(x.shape[0], -1)
+    flat = flat - flat.min(axis=1, keepdims=True)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        flat = flat / flat.max(axis=1, keepdims=True)
+    x = flat.reshape(x.shape)
+    if if_invert:
+        x = 1 - x
+    if mesh_num is None:
+        side = int(np.ceil(np.sqrt(x.shape[0])))
+        mesh_num = (side, side)
+        x = np.concatenate([x, np.zeros((side * side - x.shape[0],) + x.shape[1:], np.float32)], axis=0)
+    rows, cols = (int(m) for m in mesh_num)
+    n, h, w, c = x.shape
+    assert n == rows * cols, '{} images do not fill a {} x {} mesh'.format(n, rows, cols)
+    mosaic = x.reshape(rows, cols, h, w, c).transpose(0, 2, 1, 3, 4).reshape(rows * h, cols * w, c)
+    with np.errstate(invalid='ignore'):
+        return (mosaic * 255).astype(np.uint8)
+
+
+def write_sprite(sprite_path, images, mesh_num=None, if_invert=False):
+    """graph_func.py:222-266; the PNG is written with PIL (scipy.misc.imsave, which the reference calls, no longer exists)."""
+    from PIL import Image
+    Image.fromarray(sprite_array(images, mesh_num, if_invert)).save(sprite_path)
+
+
+def write_sprite_wrapper(images, mesh_num, filename, file_folder=None, file_index='', if_invert=False,
+                         image_format='channels_last'):
+    """graph_func.py:269-298: <file_folder>/<filename><file_index>.png; an existing file is kept (with a warning)."""
+    import warnings
+    if not isinstance(filename, str):
+        filename = filename[0]
+    if file_folder is None:
+        file_folder = FLAGS.DEFAULT_OUT
+    images = np.asarray(images)
+    if image_format in {'channels_first', 'NCHW'}:
+        images = np.transpose(images, axes=(0, 2, 3, 1))
+    sprite_path = os.path.join(file_folder, filename + file_index + '.png')
+    if os.path.isfile(sprite_path):
+        warnings.warn('This file already exists: ' + sprite_path)
+    else:
+        write_sprite(sprite_path, images, mesh_num=mesh_num, if_invert=if_invert)
+    return sprite_path
+
+
 class Agent(object):
     """graph_func.py:1144-1219.  train() is MySession.full_run for the `imbalanced_update is None` case."""
 

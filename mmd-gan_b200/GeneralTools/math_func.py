@@ -38,6 +38,63 @@ def spatial_shape_after_transpose_conv(input_spatial_shape, kernel_size, strides
 
 
 # ------------------------------------------------------------------------------------------------ matrix-level API
+class MeshCode(object):
+    """Latent codes laid out on a (rows, columns) mesh for sample sprites (math_func.py:220-335).  Host-side: the codes are a
+    [rows * columns, code_length] float32 tensor handed to SNGanEngine.generate."""
+
+    def __init__(self, code_length, mesh_num=None):
+        self.D = int(code_length)
+        self.mesh_num = (10, 10) if mesh_num is None else tuple(int(m) for m in mesh_num)
+
+    def get_batch(self, mesh_mode, name=None):
+        if mesh_mode == 0 or mesh_mode == 'random':
+            return self.by_random()
+        if mesh_mode == 1 or mesh_mode == 'sine':
+            return self.by_sine()
+        if mesh_mode == 2 or mesh_mode == 'feature':
+            return self.by_feature()
+        raise AttributeError('mesh_mode is not supported.')
+
+    def by_random(self, name=None):
+        return torch.randn(self.mesh_num[0] * self.mesh_num[1], self.D)
+
+    def by_sine(self, z_support=None, name=None):
+        """Great-arc interpolation between four supporting codes (math_func.py:257-291): with psi indexed by the mesh's second
+        axis (slow) and phi by its first (fast), both over [0, pi/4],
+        z = (cos(psi) z0 + sin(psi) z1) cos(phi) + (cos(psi) z2 + sin(psi) z3) sin(phi)."""
+        z = torch.randn(4, self.D) if z_support is None else torch.as_tensor(np.asarray(z_support), dtype=torch.float32)
+        assert tuple(z.shape) == (4, self.D), 'z_support must be [4, {}]'.format(self.D)
+        quarter = np.float32(np.pi / 4.0)
+        phi = torch.from_numpy(np.float32(quarter * np.linspace(0.0, 1.0, self.mesh_num[0])))
+        psi = torch.from_numpy(np.float32(quarter * np.linspace(0.0, 1.0, self.mesh_num[1])))
+        near = torch.cos(psi)[:, None] * z[0] + torch.sin(psi)[:, None] * z[1]           # [m1, D]
+        far = torch.cos(psi)[:, None] * z[2] + torch.sin(psi)[:, None] * z[3]
+        mesh = near[:, None, :] * torch.cos(phi)[None, :, None] + far[:, None, :] * torch.sin(phi)[None, :, None]
+        return mesh.reshape(self.mesh_num[0] * self.mesh_num[1], self.D)
+
+    def by_feature(self, grid=2.0, name=None):
+        """One code coordinate varies over [-grid, grid] per mesh row, all others zero; which coordinates is a random draw
+        (math_func.py:293-316: the kron(eye, mesh) pattern with its columns shuffled)."""
+        m0, m1 = self.mesh_num
+        assert m0 <= self.D, 'cannot mesh {} features of a {}-dimensional code'.format(m0, self.D)
+        steps = torch.from_numpy(np.float32(np.linspace(-grid, grid, m1)))
+        cols = torch.randperm(self.D)[:m0]
+        z = torch.zeros(m0, m1, self.D)
+        z[torch.arange(m0), :, cols] = steps
+        return z.reshape(m0 * m1, self.D)
+
+    def simple_grid(self, grid=None):
+        """Regular grid over a two-dimensional code, first coordinate slow (math_func.py:318-335); numpy."""
+        if self.D != 2:
+            raise AttributeError('Code length has to be two')
+        if grid is None:
+            grid = np.array([[-1.0, 1.0], [-1.0, 1.0]], dtype=np.float32)
+        x = np.linspace(grid[0][0], grid[0][1], self.mesh_num[0])
+        y = np.linspace(grid[1][0], grid[1][1], self.mesh_num[1])
+        xx, yy = np.meshgrid(x, y, indexing='ij')
+        return np.stack([xx.reshape(-1), yy.reshape(-1)], axis=1)
+
+
 def get_squared_dist(x, y=None, scale=None, z_score=False, mode='xxxyyy', name='squared_dist', do_summary=False,
                      scope_prefix=''):
     """Pairwise squared distances with the Gram trick and the clamp at zero (math_func.py:767-858)."""

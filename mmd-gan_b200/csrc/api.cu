@@ -37,6 +37,7 @@ int l_sn_grad_combine(float*, const float*, const double*, int, const float*, fl
 int l_scale_by_sigma(float*, const float*, float, long long, cudaStream_t);
 int l_sn_normalize(const float*, long long, float, float*, uint16_t*, long long, int, int, cudaStream_t);
 int l_bn_finalize(const float*, const float*, int, int, long long, float, float, float*, float*, float*, float*, cudaStream_t);
+int l_bn_inference_stats(const float*, const float*, int, float, float*, float*, cudaStream_t);
 int l_bn_apply(const float*, const float*, const float*, const float*, const float*, int, long long, int, uint16_t*, long long, int, int,
                int*, cudaStream_t);
 int l_bn_bwd_reduce(const float*, const float*, const float*, const float*, const float*, const float*, int, long long, int, int,
@@ -294,6 +295,12 @@ int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long l
     if (!psum || !psq || !mean || !invstd) return fail(MMDGAN_EINVAL, "mmdgan_bn_finalize: null pointer");
     if (T <= 0 || C <= 0 || rows <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_bn_finalize: bad shape");
     return wrap(mg::l_bn_finalize(psum, psq, T, C, rows, eps, momentum, mean, invstd, moving_mean, moving_var, S(stream)), "mmdgan_bn_finalize");
+}
+int mmdgan_bn_inference_stats(const float* moving_mean, const float* moving_var, int C, float eps, float* mean, float* invstd,
+                              void* stream) {
+    if (!moving_mean || !moving_var || !mean || !invstd) return fail(MMDGAN_EINVAL, "mmdgan_bn_inference_stats: null pointer");
+    if (C <= 0 || !(eps >= 0.0f)) return fail(MMDGAN_ESHAPE, "mmdgan_bn_inference_stats: bad shape");
+    return wrap(mg::l_bn_inference_stats(moving_mean, moving_var, C, eps, mean, invstd, S(stream)), "mmdgan_bn_inference_stats");
 }
 int mmdgan_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C,
                     long long total, int act, mmdgan_bf16* out, long long out_plane, int npl, int fmt, int* sat_flag, void* stream) {

@@ -404,6 +404,14 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
         moving_var[c] = moving_var[c] * momentum + static_cast<float>(var_u) * (1.0f - momentum);
     }
 }
+// inference-mode statistics (tf.layers.batch_normalization(training=False)): the moving averages normalise
+__global__ void bn_inference_stats_kernel(const float* __restrict__ moving_mean, const float* __restrict__ moving_var, int C, float eps,
+                                          float* __restrict__ mean, float* __restrict__ invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = moving_mean[c];
+    invstd[c] = static_cast<float>(1.0 / sqrt(static_cast<double>(moving_var[c]) + eps));
+}
 // a = act(gamma * (z - mean) * invstd + beta) -> bf16 planes; z [rows][C] raw fp32
 __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int C, long long total, int act,
@@ -637,6 +645,10 @@ int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, bf1
 int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                   float* invstd, float* mm, float* mv, cudaStream_t st) {
     bn_finalize_kernel<<<nblocks(C, 32), dim3(32, 32), 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv);
+    return MG_CHECK_LAUNCH();
+}
+int l_bn_inference_stats(const float* mm, const float* mv, int C, float eps, float* mean, float* invstd, cudaStream_t st) {
+    bn_inference_stats_kernel<<<nblocks(C, 128), 128, 0, st>>>(mm, mv, C, eps, mean, invstd);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_apply(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, int C, long long total,

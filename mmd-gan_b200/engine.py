@@ -412,8 +412,10 @@ class SNGanEngine(object):
                     K.bn_finalize(L.ps, L.pq, L.T_fwd, L.Cs_out, nimg * L.rows_out, L.mean, L.invstd, L.mm, L.mv)
                     K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
                                L.act_code, L.a, sat_flag=self.sat_flag)
-                else:
-                    raise NotImplementedError('{}: inference-mode batch norm is built in Routine runner'.format(L.ly.layer_scope))
+                else:                            # tf.layers.batch_normalization(training=False): the moving averages normalise
+                    K.bn_inference_stats(L.mm, L.mv, L.Cs_out, L.mean, L.invstd)
+                    K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
+                               L.act_code, L.a, sat_flag=self.sat_flag)
             else:
                 out_mode = 2 if getattr(L, 'raw_out', False) else self.om
                 lop.forward(src, nimg, L.a, sigma=sig, alpha_k=L.act_k, bias=L.bias_int if L.has_bias else None,
@@ -730,10 +732,49 @@ class SNGanEngine(object):
     def losses(self):
         return self.mmd.losses.clone()
 
-    def generate(self, code_x):
-        """Generated images NCHW for the staged codes, training-mode batch norm (the step's own forward)."""
+    def _check_saturation(self):
+        if int(self.sat_flag.item()) != 0:
+            raise FloatingPointError('an activation exceeded the range of the fp16 forward planes (|x| >= 4094); run with '
+                                     'MMDGAN_F16_FORWARD=0 (three bf16 planes)')
+
+    def generate(self, code_x, is_training=True):
+        """Generated images NCHW in [-1, 1] for `code_x` [n, code_size] (mdl.Gen(code_batch, is_training), my_sngan.py:270 and
+        :533).  is_training=True is the step's own forward (batch-statistics batch norm; n must be the engine's batch);
+        is_training=False is the eval_sampling graph: moving-average batch norm, per-sample, any n <= batch_size."""
         B, HW = self.B, self.height * self.width
-        self._dev_code.copy_(code_x)
+        code_x = torch.as_tensor(code_x, dtype=torch.float32)
+        n = code_x.shape[0]
+        if code_x.dim() != 2 or code_x.shape[1] != self.code_size:
+            raise ValueError('code_x must be [n, {}], got {}'.format(self.code_size, list(code_x.shape)))
+        if n > B or (is_training and n != B):
+            raise ValueError('{} codes for an engine of batch size {} (training-mode batch norm needs exactly the batch)'.format(n, B))
+        if n < B:
+            self._dev_code.zero_()
+        self._dev_code[:n].copy_(code_x)
         K.nchw_to_planes(self._dev_code, self.code_planes)
-        self._net_forward(self.G, self.code_planes, B)
-        return K.planes_to_nchw(self.x_all[:, B * HW:, :], B, self.channels, self.height, self.width)
+        for L in self.G.layers:                 # sigma of the current weights and in_rand (in_rand itself is not advanced)
+            if L.has_sn:
+                self._sn_layer(L)
+        self._net_forward(self.G, self.code_planes, B, is_training=is_training)
+        self._check_saturation()
+        return K.planes_to_nchw(self.x_all[:, B * HW:, :], B, self.channels, self.height, self.width)[:n]
+
+    def discriminate(self, x):
+        """Discriminator scores [n, d] of NCHW images `x`, n <= 2 * batch_size (mdl.Dis(batch, is_training=False),
+        my_sngan.py:548-551).  sigma of every spectrally-normalised layer comes from one power iteration on the stored
+        in_rand, which -- as in the reference's eval graph, where UPDATE_OPS are not run -- is left unchanged."""
+        B, HW = self.B, self.height * self.width
+        x = torch.as_tensor(x, dtype=torch.float32).to(self.device)
+        n = x.shape[0]
+        if list(x.shape[1:]) != [self.channels, self.height, self.width] or n > 2 * B:
+            raise ValueError('x must be [n <= {}, {}, {}, {}], got {}'.format(2 * B, self.channels, self.height, self.width, list(x.shape)))
+        buf = torch.zeros((2 * B, self.channels, self.height, self.width), device=self.device)
+        buf[:n].copy_(x)
+        K.nchw_to_planes(buf, self.x_all)
+        for L in self.D.layers:
+            if L.has_sn:
+                self._sn_layer(L)
+        self._net_forward(self.D, self.x_all, 2 * B, is_training=False)
+        self._check_saturation()
+        last = self.D.layers[-1]
+        return last.a[0][:n, :last.Cout].clone()

@@ -579,6 +579,11 @@ def bn_finalize(psum, psq, T, Cc, rows, mean, invstd, moving_mean=None, moving_v
                                    _ptr(moving_mean), _ptr(moving_var), stream()))
 
 
+def bn_inference_stats(moving_mean, moving_var, Cc, mean, invstd, eps=1e-3):
+    """tf.layers.batch_normalization(training=False): the moving averages normalise (layer_func.py:953-966)."""
+    check(lib().mmdgan_bn_inference_stats(_ptr(moving_mean), _ptr(moving_var), Cc, float(eps), _ptr(mean), _ptr(invstd), stream()))
+
+
 def bn_apply(z, mean, invstd, gamma, beta, Cc, total, act, out, sat_flag=None):
     _planes(out)
     check(lib().mmdgan_bn_apply(_ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), Cc, total, act, _ptr(out),

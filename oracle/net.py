@@ -443,6 +443,21 @@ class OracleSNGan(object):
         grads_gen = OrderedDict(zip(gp.keys(), [g.detach() for g in g_gen]))
         return loss_gen.detach(), loss_dis.detach(), grads_gen, grads_dis, upd_g, upd_d
 
+    def eval_sampling(self, code_x, data_x=None):
+        """The eval_sampling graph (my_sngan.py:533-551): generator with is_training=False (moving-average batch norm), samples
+        clipped to [-1, 1]; with real samples, the discriminator (is_training=False) on [real; clipped generated].  The
+        spectral-norm power iteration still runs (it is part of the kernel's graph) but its UPDATE_OPS are not applied."""
+        with torch.no_grad():
+            x_gen, _ = net_forward(self.gen_specs, self.gen_params, self.gen_state, code_x, False, self.sn_mode, self.tf32)
+            x_gen = x_gen.clamp(-1.0, 1.0)
+            out = {'x_gen': x_gen}
+            if data_x is not None:
+                b = data_x.shape[0]
+                s_all, _ = net_forward(self.dis_specs, self.dis_params, self.dis_state, torch.cat([data_x, x_gen], 0), False,
+                                       self.sn_mode, self.tf32)
+                out['s_x'], out['s_gen'] = s_all[:b], s_all[b:]
+        return out
+
     def step(self, data_x, code_x):
         """One fused sess.run of [losses, dis_op, gen_op, UPDATE_OPS, global_step] (graph_func.py:851-854)."""
         loss_gen, loss_dis, grads_gen, grads_dis, upd_g, upd_d = self.grads(data_x, code_x)

@@ -407,11 +407,11 @@ def abs(x, name=None):  # noqa: A001
 
 
 def sin(x, name=None):
-    return torch.sin(x)
+    return torch.sin(_t(x))
 
 
 def cos(x, name=None):
-    return torch.cos(x)
+    return torch.cos(_t(x))
 
 
 def less(x, y, name=None):
@@ -430,8 +430,8 @@ def where(cond, x=None, y=None, name=None):
     return torch.where(cond, x, y)
 
 
-def clip_by_value(x, lo, hi, name=None):
-    return torch.clamp(x, lo, hi)
+def clip_by_value(t, clip_value_min, clip_value_max, name=None):
+    return torch.clamp(t, clip_value_min, clip_value_max)
 
 
 def expand_dims(x, axis=None, name=None, dim=None):

@@ -68,6 +68,82 @@ def step_case(loss_type, sn_mode='default'):
     return out
 
 
+def mesh_codes_by_sine(z_support, mesh_num):
+    """MeshCode.by_sine (math_func.py:257-291), restated with numpy in float64."""
+    m0, m1 = mesh_num
+    phi = np.float32(np.pi / 4.0 * np.linspace(0.0, 1.0, m0)).astype(np.float64)
+    psi = np.float32(np.pi / 4.0 * np.linspace(0.0, 1.0, m1)).astype(np.float64)
+    z = np.asarray(z_support, dtype=np.float64)
+    out = np.zeros((m1, m0, z.shape[1]))
+    for j in range(m1):
+        for i in range(m0):
+            out[j, i] = (np.cos(psi[j]) * z[0] + np.sin(psi[j]) * z[1]) * np.cos(phi[i]) \
+                + (np.cos(psi[j]) * z[2] + np.sin(psi[j]) * z[3]) * np.sin(phi[i])
+    return out.reshape(m0 * m1, -1)
+
+
+def sprite_mosaic(images, mesh_num, if_invert):
+    """write_sprite (graph_func.py:222-265) restated with loops: per-image min / range scaling, row-major mesh, uint8."""
+    x = np.asarray(images, dtype=np.float32)
+    if x.ndim == 3:
+        x = x[..., None]
+    if x.shape[3] == 1:
+        x = np.concatenate([x, x, x], axis=3)
+    n, h, w, c = x.shape
+    rows, cols = mesh_num
+    out = np.zeros((rows * h, cols * w, c), dtype=np.uint8)
+    for i in range(n):
+        t = x[i] - x[i].min()
+        t = t / t.max()
+        if if_invert:
+            t = 1 - t
+        r, q = divmod(i, cols)
+        out[r * h:(r + 1) * h, q * w:(q + 1) * w] = (t * 255).astype(np.uint8)
+    return out
+
+
+def eval_inputs():
+    """Model state for the eval_sampling fixtures: the tiny model after one training step (step_tiny_rep's `after` variables),
+    with the batch-norm moving averages replaced by seeded non-trivial values so that inference-mode batch norm differs
+    visibly from the training-mode one; codes = a (2, 3) sine mesh over four seeded supporting codes."""
+    base = step_case('rep')
+    rng = np.random.RandomState(21)
+    out = {'mesh_num': np.asarray((2, 3))}
+    for k, v in base.items():
+        if k.startswith('after:'):
+            out['var:' + k.split(':', 1)[1]] = v
+        elif k.startswith('state_after:'):
+            name = k.split(':', 1)[1]
+            if name.endswith('moving_mean'):
+                v = (rng.randn(*v.shape) * 0.3).astype(np.float32).astype(np.float64)
+            elif name.endswith('moving_variance'):
+                v = rng.uniform(0.4, 1.6, size=v.shape).astype(np.float32).astype(np.float64)
+            out['state:' + name] = v
+    out['z_support'] = rng.randn(4, base['code'].shape[1]).astype(np.float32)
+    out['data'] = base['data'][:6]
+    return out
+
+
+def eval_case():
+    out = eval_inputs()
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=3)
+    for d in (m.gen_params, m.dis_params):
+        for k in d:
+            d[k] = torch.from_numpy(out['var:' + k]).double()
+    for d in (m.gen_state, m.dis_state):
+        for k in d:
+            d[k] = torch.from_numpy(out['state:' + k]).double()
+    code = mesh_codes_by_sine(out['z_support'], (2, 3))
+    out['code'] = code
+    res = m.eval_sampling(torch.from_numpy(code), torch.from_numpy(out['data']).double())
+    for k, v in res.items():
+        out[k] = v.numpy()
+    out['sprite'] = sprite_mosaic(np.transpose(out['x_gen'], (0, 2, 3, 1)), (2, 3), False)
+    out['sprite_inverted_gray'] = sprite_mosaic(out['x_gen'][:, 0], (3, 2), True)
+    return out
+
+
 def main():
     for lt in ('rep', 'rmb', 'mmd_g', 'mgb', 'mmd_t'):
         for b in (2, 3, 64) if lt in ('rep', 'rmb') else (64,):
@@ -81,6 +157,7 @@ def main():
     for lt in ('rep', 'rmb'):
         np.savez_compressed(os.path.join(HERE, 'step_tiny_{}.npz'.format(lt)), **step_case(lt))
     np.savez_compressed(os.path.join(HERE, 'step_tiny_rep_pim.npz'), **step_case('rep', sn_mode='sn_paper'))
+    np.savez_compressed(os.path.join(HERE, 'eval_tiny.npz'), **eval_case())
 
 
 if __name__ == '__main__':

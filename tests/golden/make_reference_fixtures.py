@@ -18,6 +18,9 @@ own functions are run:
                            (batch 4; gradients stored as norms plus a strided sample per variable to keep the file small;
                            the initial variables are the oracle's seeded initialisation, so only the seed is stored)
 
+  ref_eval_tiny.npz        SNGan.eval_sampling's graph section (my_sngan.py:523-551): MeshCode.by_sine codes, the generator and the
+                           discriminator with is_training=False, clipping; write_sprite's uint8 mosaics (graph_func.py:222-266)
+
 Inputs (seeds, initial variables) are the ones tests/golden/make_golden.py uses for the oracle-authored twins, so each
 ref_* file has the same keys as its twin and the same tests run against both.  Only the fixtures travel to the GPU box.
 """
@@ -237,6 +240,63 @@ def ref_step_cifar(batch=4, seed=2, steps=2, act_k=None, script='my_test_cifar.p
     return out
 
 
+def ref_eval_case():
+    """Twin of make_golden.eval_case: the reference's eval_sampling graph section (my_sngan.py:523-551) executed eagerly --
+    MeshCode.by_sine for the codes (math_func.py:257-291), sample_codes, __gpu_task__(is_training=False), clip_by_value,
+    Dis(concat_two_batches(...), is_training=False) -- and its write_sprite (graph_func.py:222-266), whose scipy.misc.imsave
+    call (gone from SciPy) is replaced by a capture of the uint8 array it is handed."""
+    import types
+    base = mg.eval_inputs()
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    run = ReferenceRun(arch, 'rep', lr_list=(5e-4, 2e-4))
+    init = {k.split(':', 1)[1]: v for k, v in base.items() if k.startswith('var:') or k.startswith('state:')}
+    mdl = run.mdl
+    tf._S.collections.clear()
+    mdl.init_net()
+    mesh_num = tuple(int(m) for m in base['mesh_num'])
+    code_x = rmf.MeshCode(mdl.code_size, mesh_num=mesh_num).by_sine(base['z_support'].astype(np.float64), name='code_x')
+    orig_gv = tf.get_variable
+
+    def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True, **kw):
+        full = '/'.join(tf._S.scope + [name])
+        if full not in tf.shim_variables():
+            v0 = torch.as_tensor(init[full], dtype=torch.float64)
+            initializer = lambda s: v0.clone()                                    # noqa: E731
+        return orig_gv(name, shape, dtype, initializer, trainable, **kw)
+    tf.get_variable = get_variable
+    try:
+        code_batch = mdl.sample_codes(mesh_num[0] * mesh_num[1], code_x, None, name='code_te')
+        gen_batch = mdl.__gpu_task__(code_batch=code_batch, is_training=False)
+        gen_batch['x'] = tf.clip_by_value(gen_batch['x'], clip_value_min=-1, clip_value_max=1)
+        data_batch = {'x': torch.as_tensor(base['data'], dtype=torch.float64)}
+        dis_out = mdl.Dis(mdl.concat_two_batches(data_batch, gen_batch), is_training=False)
+        s_x, s_gen = tf.split(dis_out['x'], num_or_size_splits=2, axis=0)
+    finally:
+        tf.get_variable = orig_gv
+    assert set(init) == set(tf.shim_variables()), set(init) ^ set(tf.shim_variables())
+    out = dict(base)
+    out['code'] = code_x.detach().numpy()
+    out['x_gen'], out['s_x'], out['s_gen'] = gen_batch['x'].detach().numpy(), s_x.detach().numpy(), s_gen.detach().numpy()
+    captured = []
+    import scipy
+    fake = types.ModuleType('scipy.misc')
+    fake.imsave = lambda path, arr: captured.append(np.array(arr))
+    saved = sys.modules.get('scipy.misc'), getattr(scipy, 'misc', None)
+    sys.modules['scipy.misc'], scipy.misc = fake, fake
+    try:
+        rgf.write_sprite('unused.png', np.transpose(out['x_gen'], (0, 2, 3, 1)), mesh_num=mesh_num, if_invert=False)
+        rgf.write_sprite('unused.png', out['x_gen'][:, 0], mesh_num=[3, 2], if_invert=True)
+    finally:
+        if saved[0] is not None:
+            sys.modules['scipy.misc'] = saved[0]
+        else:
+            del sys.modules['scipy.misc']
+        if saved[1] is not None:
+            scipy.misc = saved[1]
+    out['sprite'], out['sprite_inverted_gray'] = captured
+    return out
+
+
 def main():
     for lt in ('rep', 'rmb', 'mmd_g', 'mgb', 'mmd_t'):
         for b in (2, 3, 64) if lt in ('rep', 'rmb') else (64,):
@@ -250,6 +310,7 @@ def main():
     for lt in ('rep', 'rmb'):
         np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_{}.npz'.format(lt)), **ref_step_case(lt))
     np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_rep_pim.npz'), **ref_step_case('rep', sn_mode='sn_paper'))
+    np.savez_compressed(os.path.join(HERE, 'ref_eval_tiny.npz'), **ref_eval_case())
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep.npz'), **ref_step_cifar())
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep_k27.npz'), **ref_step_cifar(batch=8, act_k=2.7))
     # the other shipped architecture dictionaries, parsed from the reference's scripts (one step, batch 2, sparse samples)

@@ -137,6 +137,93 @@ def test_sngan_training_api_and_checkpoint(cuda, tmp_path):
         mdl.training('cifar_NCHW/cifar', agent, 64, [5e-4, 2e-4], max_step=1, batch_size=16)
 
 
+@pytest.mark.parametrize('family', ['', 'ref_'])
+def test_engine_inference_graph_against_golden(cuda, family):
+    """SNGan.eval_sampling's graph (my_sngan.py:533-551): generator and discriminator with is_training=False -- moving-average
+    batch norm, per-sample -- on the (2, 3) sine mesh of codes; the `ref_` fixture is the reference's own execution."""
+    from oracle import architectures as oa          # the architecture dictionary only
+    from mmdgan_b200.engine import SNGanEngine
+    from mmdgan_b200.GeneralTools.math_func import MeshCode
+    from mmdgan_b200.GeneralTools.graph_func import sprite_array
+    z = np.load(os.path.join(GOLD, family + 'eval_tiny.npz'))
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    eng = SNGanEngine(arch, 6, loss_type='rep', use_graph=False)
+    for net in (eng.G, eng.D):
+        for name in net.var_offsets:
+            net.set_variable(name, torch.from_numpy(z['var:' + name]))
+        for name in net.state_names():
+            net.set_state(name, torch.from_numpy(z['state:' + name]))
+        net.refresh()
+    code = MeshCode(16, mesh_num=(2, 3)).by_sine(z['z_support'])
+    assert rel(code.numpy(), z['code']) < 1e-6
+    x_gen = eng.generate(code, is_training=False).clamp(-1, 1)
+    assert rel(x_gen.cpu().numpy(), z['x_gen']) < 1e-3
+    before = {n: eng.D.get_state(n).clone() for n in eng.D.state_names()}
+    scores = eng.discriminate(torch.cat([torch.from_numpy(z['data']).cuda(), x_gen], 0))
+    assert rel(scores[:6].cpu().numpy(), z['s_x']) < 1e-3
+    assert rel(scores[6:].cpu().numpy(), z['s_gen']) < 1e-3
+    for n, v in before.items():                      # UPDATE_OPS are not run by the eval graph
+        assert torch.equal(eng.D.get_state(n), v), n
+    # per-sample: a smaller mesh gives the same images, and the training-mode graph differs (batch statistics)
+    x3 = eng.generate(code[:3], is_training=False)
+    assert torch.equal(x3, eng.generate(code, is_training=False)[:3])
+    assert rel(eng.generate(code).cpu().numpy(), z['x_gen']) > 1e-2
+    # the sprite of the CUDA samples: at most a few 8-bit levels flip against the float64 samples' mosaic
+    mosaic = sprite_array(np.transpose(x_gen.cpu().numpy(), (0, 2, 3, 1)), (2, 3))
+    diff = np.abs(mosaic.astype(np.int32) - z['sprite'].astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.05
+    with pytest.raises(ValueError):
+        eng.generate(code[:3])                       # training-mode batch norm needs the whole batch
+    with pytest.raises(ValueError):
+        eng.discriminate(torch.zeros(13, 3, 8, 8))
+
+
+def test_sngan_eval_sampling_api(cuda, tmp_path):
+    """train -> checkpoint -> eval_sampling (my_sngan.py:499-601): restores the checkpoint into a mesh-sized engine, writes the
+    `_g_` and `_r_` sprites under the summary folder with the reference's file names, returns samples and scores."""
+    from PIL import Image
+    from oracle import architectures as oa
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200.GeneralTools.graph_func import Agent, sprite_array
+    from mmdgan_b200.DeepLearning.my_sngan import SNGan
+    FLAGS.DEFAULT_OUT = str(tmp_path) + '/'
+    FLAGS.SILENT_MODE = True
+    arch = oa.tiny(act_k=2.6)
+    images = (np.random.RandomState(0).rand(64, 3, 8, 8) * 255).astype(np.uint8)
+    mdl = SNGan(arch, num_class=0, loss_type='rep', optimizer='adam')
+    with pytest.raises(FileNotFoundError):           # graph_func.py:633 'No ckpt Model found at ...'
+        mdl.eval_sampling('toy', 'sngan_rep', mesh_num=(3, 4), data_source=images)
+    agent = Agent('toy', 'sngan_rep', do_save=True, print_loss=False)
+    torch.manual_seed(0)
+    mdl.training(images, agent, 64, [5e-4, 2e-4], max_step=4, batch_size=16)
+    trained = {n: mdl.engine.G.get_variable(n).clone() for n in mdl.engine.G.var_offsets}
+    moving = {n: mdl.engine.G.get_state(n).clone() for n in mdl.engine.G.state_names()}
+    out = mdl.eval_sampling('toy', 'sngan_rep', mesh_num=(3, 4), mesh_mode=1, real_sample=True, data_source=images)
+    assert out['global_step'] == 4 and mdl.engine.B == 12
+    for n, v in trained.items():
+        assert torch.equal(mdl.engine.G.get_variable(n), v), n
+    for n, v in moving.items():
+        assert torch.equal(mdl.engine.G.get_state(n), v), n
+    assert out['x_gen'].shape == (12, 3, 8, 8) and np.abs(out['x_gen']).max() <= 1.0
+    assert out['s_x'].shape == out['s_gen'].shape == (12, arch['discriminator'][-1]['out'])
+    assert np.isfinite(out['s_x']).all() and np.isfinite(out['s_gen']).all()
+    names = sorted(os.path.basename(p) for p in out['sprites'])
+    assert names == ['toy_g_sngan_rep_4_1.png', 'toy_r_sngan_rep_4_1.png']
+    for p in out['sprites']:
+        assert os.path.dirname(p) == os.path.join(str(tmp_path), 'toy_log', 'sngan_rep')
+    png = np.asarray(Image.open([p for p in out['sprites'] if '_g_' in p][0]))
+    assert png.shape == (24, 32, 3)
+    assert np.array_equal(png, sprite_array(np.transpose(out['x_gen'], (0, 2, 3, 1)), (3, 4)))
+    # given codes; no real samples -> no scores, one sprite; an existing sprite is kept (warning), as in the reference
+    code = torch.randn(12, mdl.code_size)
+    with pytest.warns(UserWarning, match='already exists'):
+        out2 = mdl.eval_sampling('toy', 'sngan_rep', mesh_num=(3, 4), mesh_mode=1, code_x=code)
+    assert out2['s_x'] is None and out2['x_real'] is None and len(out2['sprites']) == 1
+    assert np.array_equal(out2['x_gen'], mdl.engine.generate(code, is_training=False).clamp(-1, 1).cpu().numpy())
+    with pytest.raises(NotImplementedError):
+        mdl.eval_sampling('toy', 'sngan_rep', do_embedding=True)
+
+
 def test_sngan_training_from_tfrecords(cuda, tmp_path):
     """The reference call `mdl.training(filename, ...)` with a TFRecord prefix (my_test_cifar.py) on a toy file: the
     batches the engine trains on are those of ReadTFRecords (uint8 CHW bytes -> x / 127.5 - 1)."""

@@ -217,3 +217,42 @@ def test_reference_style_matrix_functions_match_oracle():
     assert mf.spatial_shape_after_transpose_conv(6, 4, 2, 1, 'SAME') == 12
     with pytest.raises(AttributeError):
         mf.get_squared_dist(g, r, mode='zz')
+
+
+def test_mesh_codes_and_sprites_against_reference_fixture(tmp_path):
+    """Host side of eval_sampling: MeshCode (math_func.py:220-335) and write_sprite / write_sprite_wrapper
+    (graph_func.py:222-298) against the reference-executed fixture; no device work."""
+    import numpy as np
+    from PIL import Image
+    from mmdgan_b200.GeneralTools.math_func import MeshCode
+    from mmdgan_b200.GeneralTools.graph_func import sprite_array, write_sprite_wrapper
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_eval_tiny.npz'))
+    code = MeshCode(16, mesh_num=(2, 3)).by_sine(z['z_support'])
+    assert code.dtype == torch.float32 and np.allclose(code.numpy(), z['code'], atol=1e-6)
+    nhwc = np.transpose(z['x_gen'], (0, 2, 3, 1))
+    assert np.array_equal(sprite_array(nhwc, (2, 3)), z['sprite'])
+    assert np.array_equal(sprite_array(z['x_gen'][:, 0], [3, 2], if_invert=True), z['sprite_inverted_gray'])
+    # mesh_num None: smallest square, padded with black (graph_func.py:249-256)
+    sq = sprite_array(nhwc[:5])
+    assert sq.shape == (24, 24, 3) and not sq[16:, 8:].any() and np.array_equal(sq[:8, :24], z['sprite'][:8])
+    # the wrapper takes NCHW, names the file <filename><index>.png and keeps an existing file
+    path = write_sprite_wrapper(z['x_gen'], (2, 3), ['toy', 'other'], file_folder=str(tmp_path), file_index='_g_x_1_0', image_format='NCHW')
+    assert path == os.path.join(str(tmp_path), 'toy_g_x_1_0.png')
+    assert np.array_equal(np.asarray(Image.open(path)), z['sprite'])
+    with pytest.warns(UserWarning, match='already exists'):
+        write_sprite_wrapper(1.0 - z['x_gen'], (2, 3), 'toy', file_folder=str(tmp_path), file_index='_g_x_1_0', image_format='NCHW')
+    assert np.array_equal(np.asarray(Image.open(path)), z['sprite'])
+    # the other mesh modes
+    mc = MeshCode(16, mesh_num=(4, 5))
+    assert tuple(mc.get_batch('random').shape) == (20, 16) and tuple(mc.get_batch(1).shape) == (20, 16)
+    f = mc.get_batch(2).reshape(4, 5, 16)
+    cols = [int(f[i].abs().sum(0).argmax()) for i in range(4)]
+    assert len(set(cols)) == 4
+    for i, c in enumerate(cols):
+        assert np.allclose(f[i, :, c].numpy(), np.linspace(-2.0, 2.0, 5)) and int((f[i] != 0).sum()) == 4    # 0 is on the grid
+    with pytest.raises(AttributeError):
+        mc.get_batch(3)
+    g = MeshCode(2, mesh_num=(2, 3)).simple_grid()
+    assert np.allclose(g, [[-1, -1], [-1, 0], [-1, 1], [1, -1], [1, 0], [1, 1]])
+    with pytest.raises(AttributeError):
+        mc.simple_grid()

@@ -75,6 +75,31 @@ def test_step_golden(loss_type, family):
         assert np.allclose(v.numpy(), z['state_after:' + k], atol=1e-12), k
 
 
+@pytest.mark.parametrize('family', ['', 'ref_'])
+def test_eval_sampling_golden(family):
+    """The eval_sampling graph (my_sngan.py:533-551; generator and discriminator with is_training=False on a sine mesh of codes)
+    and write_sprite's mosaics (graph_func.py:222-266); `ref_` = the reference's own execution."""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden as mg
+    z = np.load(os.path.join(GOLD, family + 'eval_tiny.npz'))
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=3)
+    for store, pre in ((m.gen_params, 'var:'), (m.dis_params, 'var:'), (m.gen_state, 'state:'), (m.dis_state, 'state:')):
+        for k in list(store.keys()):
+            store[k] = torch.from_numpy(z[pre + k]).double()
+    code = mg.mesh_codes_by_sine(z['z_support'], tuple(z['mesh_num']))
+    assert np.allclose(code, z['code'], atol=1e-14)
+    state = {k: v.clone() for k, v in list(m.gen_state.items()) + list(m.dis_state.items())}
+    res = m.eval_sampling(torch.from_numpy(code), torch.from_numpy(z['data']).double())
+    for k in ('x_gen', 's_x', 's_gen'):
+        assert np.allclose(res[k].numpy(), z[k], atol=1e-12), k
+    for k, v in list(m.gen_state.items()) + list(m.dis_state.items()):
+        assert torch.equal(v, state[k]), k                       # no UPDATE_OPS in the eval graph
+    assert np.array_equal(mg.sprite_mosaic(np.transpose(z['x_gen'], (0, 2, 3, 1)), (2, 3), False), z['sprite'])
+    assert np.array_equal(mg.sprite_mosaic(z['x_gen'][:, 0], (3, 2), True), z['sprite_inverted_gray'])
+
+
 def test_reference_fixture_families_are_complete():
     """Every oracle-authored fixture has a reference-executed twin with the same keys."""
     for path in glob.glob(os.path.join(GOLD, '*.npz')):
