@@ -26,6 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the top forward kernel, from the committed
+# `ncu --set full` capture (profiles/r1v4_summary.md, section conv_fwd); a recorded profile value, not measured by bench.py
+NCU_TRAFFIC = {('cifar', 256): 36.068096e6 + 0.961536e6}
+NCU_TRAFFIC_NOTE = ('bytes of one conv_gemm_pair_kernel<256,3,1> launch (grid 256, 109 us under ncu; L2 hit rate 82%, DRAM at 4% of peak: '
+                    'the kernel is tensor/L2 bound, not HBM bound) from profiles/r1v4_summary.md; `achieved` aggregates all GEMM launches')
 WORKLOADS = {'cifar': ('cifar', 256, 'rep', (5e-4, 2e-4)), 'stl': ('stl', 128, 'rmb', (2e-4, 2e-4)),
              'celeba': ('celeba', 128, 'rep', (1e-4, 2e-4)), 'lsun': ('lsun', 128, 'rep', (2e-4, 1e-4))}
 # algorithmic cost per (real, fake) pair = 3G + 7D forward-equivalents, in GFLOP
@@ -249,7 +254,7 @@ def run_ours(args):
         flop_step = GFLOP_PER_PAIR[name] * 1e9 * batch
         achieved = flop_step / (gemm_ms / 1e3) / 1e12
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['sustained'],
-                'traffic': None, 'peak_source': peaks['source'] + ' bf16 sustained (MEASURED_PEAKS.json)',
+                'traffic': NCU_TRAFFIC.get((name, batch)), 'traffic_note': NCU_TRAFFIC_NOTE if (name, batch) in NCU_TRAFFIC else None, 'peak_source': peaks['source'] + ' bf16 sustained (MEASURED_PEAKS.json)',
                 'kernel': 'conv_gemm(_pair)_kernel + wgrad_gemm_kernel (tcgen05) + conv3x3 direct kernels of the image layers: the {} batch-sized '
                           'launches that carry the 3G+7D FLOPs of one step'.format(len(evs)),
                 'gemm_ms_per_step': gemm_ms, 'eager_single_stream_step_ms': t0.elapsed_time(t1), 'share_of_eager_step': gemm_ms / t0.elapsed_time(t1),

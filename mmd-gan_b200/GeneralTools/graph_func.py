@@ -166,7 +166,8 @@ def write_sprite_wrapper(images, mesh_num, filename, file_folder=None, file_inde
 
 
 class Agent(object):
-    """graph_func.py:1144-1219.  train() is MySession.full_run for the `imbalanced_update is None` case."""
+    """graph_func.py:1144-1219.  train() is MySession.full_run (graph_func.py:820-908): every step one fused engine step;
+    imbalanced_update = (k_dis, k_gen) selects per step which of the two optimisers is applied."""
 
     def __init__(self, filename, sub_folder, load_ckpt=False, do_trace=False, do_save=True, debug_mode=False, debug_step=800,
                  query_step=500, log_device=False, imbalanced_update=None, print_loss=True):
@@ -180,8 +181,15 @@ class Agent(object):
         self.query_step = query_step
         self.imbalanced_update = imbalanced_update
         self.print_loss = print_loss
+        if isinstance(imbalanced_update, str):
+            raise NotImplementedError("imbalanced_update='dynamic' serves sngan_mmd_rand_g only (graph_func.py:910-950): not on the hot path.")
         if imbalanced_update is not None:
-            raise NotImplementedError('Imbalanced update is not on the hot path (graph_func.py:876-908).')
+            if not isinstance(imbalanced_update, (list, tuple)):
+                raise AttributeError('Imbalanced_update not identified.')                     # my_sngan.py:445
+            assert len(imbalanced_update) == 2, 'Imbalanced_update length does not match that of op_list. Expected 2 got {}.'.format(
+                len(imbalanced_update))                                                       # graph_func.py:878-880
+            if 1 not in tuple(imbalanced_update):
+                raise AttributeError('One of the imbalanced_update must be 1.')               # my_sngan.py:439
 
     def train(self, engine, batch_fn, max_step, step_per_epoch, loss_names='<loss_gen>, <loss_dis>', force_print=False):
         """engine: SNGanEngine; batch_fn(step) -> (data NCHW float32 in [-1,1], codes [B, code_size]) host tensors."""
@@ -196,7 +204,10 @@ class Agent(object):
         loss_value = None
         for step in range(max_step):
             data_x, code_x = batch_fn(step)
-            loss_value = engine.step(data_x, code_x, check_nan=False)
+            # imbalanced update (graph_func.py:885-886): optimiser i runs when the global step is a multiple of imbalanced_update[i]
+            update = (True, True) if self.imbalanced_update is None else \
+                tuple(engine.global_step % int(k) == 0 for k in self.imbalanced_update)
+            loss_value = engine.step(data_x, code_x, check_nan=False, update=update)
             # check if model produces nan outcome (graph_func.py:856)
             assert not any(np.isnan(loss_value)), 'Model diverged with loss = {} at step {}'.format(loss_value, step)
             gs = engine.global_step

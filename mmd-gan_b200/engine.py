@@ -328,7 +328,8 @@ class SNGanEngine(object):
         self.sat_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         for L in self.G.layers + self.D.layers:
             L.lop.sat_flag = self.sat_flag
-        self._graphs = None
+        self._graph_cache = {}                   # update mask -> captured CUDA graphs
+        self.update_mask = (True, True)          # (run dis_op, run gen_op) of the step being enqueued
         self._warm = False
         self._stream = torch.cuda.Stream(device=self.device)
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(8)]
@@ -563,7 +564,7 @@ class SNGanEngine(object):
         # refresh then run on the update stream WHILE the generator's backward pass proceeds (nothing below reads a
         # discriminator weight).  Multi-GPU: the update has to wait for the gradient all-reduce, so it stays in _phase_update.
         self._dis_updated = False
-        if side is not main and self.world_size == 1:
+        if side is not main and self.world_size == 1 and self.update_mask[0]:
             flush()
             ev_side, ev_main = torch.cuda.Event(), torch.cuda.Event()
             ev_side.record(side)
@@ -628,7 +629,9 @@ class SNGanEngine(object):
             ev = torch.cuda.Event()
             ev.record(main)
             side.wait_event(ev)
-        for net, lr, st in ((self.D, self.lr_dis, side), (self.G, self.lr_gen, main)):
+        for net, lr, st, scheduled in ((self.D, self.lr_dis, side, self.update_mask[0]), (self.G, self.lr_gen, main, self.update_mask[1])):
+            if not scheduled:                              # imbalanced update: this optimiser is not run on this step (graph_func.py:885-886)
+                continue
             if net is self.D and self._dis_updated:        # already enqueued on the update stream during the backward pass
                 continue
             with torch.cuda.stream(st):
@@ -681,10 +684,18 @@ class SNGanEngine(object):
                 for fn in fns:
                     fn()
             graphs.append(g)
-        self._graphs = graphs
+        self._graph_cache[self.update_mask] = graphs
 
-    def step_device(self):
-        """One training step on the batch already staged in self._dev_data / self._dev_code (device resident)."""
+    @property
+    def _graphs(self):
+        """CUDA graphs of the ordinary step (both optimisers run); None until captured."""
+        return self._graph_cache.get((True, True))
+
+    def step_device(self, update=(True, True)):
+        """One training step on the batch already staged in self._dev_data / self._dev_code (device resident).
+        update = (run_dis, run_gen): which optimisers this step applies (Agent(imbalanced_update=...), graph_func.py:876-908);
+        losses, both gradient sets, UPDATE_OPS and the global step are the same either way.  One CUDA graph per mask."""
+        self.update_mask = (bool(update[0]), bool(update[1]))
         if not self.use_graph or not self._warm:
             # the first step always runs eagerly (it also sets the kernels' shared-memory attributes)
             n0 = K.LAUNCHES[0]
@@ -692,16 +703,17 @@ class SNGanEngine(object):
             self.kernel_launches_per_step = K.LAUNCHES[0] - n0
             self._warm = True
         else:
-            if self._graphs is None:
+            if self.update_mask not in self._graph_cache:
                 self._capture()
+            graphs = self._graph_cache[self.update_mask]
             if self.world_size > 1:
-                self._graphs[0].replay()
+                graphs[0].replay()
                 self._gather_scores()
-                self._graphs[1].replay()
+                graphs[1].replay()
                 self._allreduce_grads()
-                self._graphs[2].replay()
+                graphs[2].replay()
             else:
-                self._graphs[0].replay()
+                graphs[0].replay()
         self.global_step += 1
 
     def stage(self, data_x, code_x):
@@ -709,14 +721,14 @@ class SNGanEngine(object):
         self._dev_data.copy_(data_x, non_blocking=True)
         self._dev_code.copy_(code_x, non_blocking=True)
 
-    def step(self, data_x, code_x, check_nan=True):
+    def step(self, data_x, code_x, check_nan=True, update=(True, True)):
         """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis]."""
         if not (data_x.is_pinned() and code_x.is_pinned()):      # pageable host memory: stage through pinned buffers
             self._pin_data.copy_(data_x)
             self._pin_code.copy_(code_x)
             data_x, code_x = self._pin_data, self._pin_code
         self.stage(data_x, code_x)
-        self.step_device()
+        self.step_device(update)
         self._pin_loss.copy_(self.mmd.losses, non_blocking=True)
         self._pin_sat.copy_(self.sat_flag, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

@@ -458,11 +458,17 @@ class OracleSNGan(object):
                 out['s_x'], out['s_gen'] = s_all[:b], s_all[b:]
         return out
 
-    def step(self, data_x, code_x):
-        """One fused sess.run of [losses, dis_op, gen_op, UPDATE_OPS, global_step] (graph_func.py:851-854)."""
+    def step(self, data_x, code_x, imbalanced_update=None):
+        """One fused sess.run of [losses, dis_op, gen_op, UPDATE_OPS, global_step] (graph_func.py:851-854).
+        imbalanced_update = (k_dis, k_gen), one of them 1 (my_sngan.py:427-439): optimiser i is run only on the steps whose
+        global step is a multiple of k_i (graph_func.py:885-886); an optimiser that is not run keeps its slots and beta powers;
+        UPDATE_OPS and the global step (carried by the optimiser that runs every step) advance on every step."""
+        run_dis, run_gen = imbalanced_schedule(self.global_step, imbalanced_update)
         loss_gen, loss_dis, grads_gen, grads_dis, upd_g, upd_d = self.grads(data_x, code_x)
-        self.opt_dis.apply(self.dis_params, grads_dis)
-        self.opt_gen.apply(self.gen_params, grads_gen)
+        if run_dis:
+            self.opt_dis.apply(self.dis_params, grads_dis)
+        if run_gen:
+            self.opt_gen.apply(self.gen_params, grads_gen)
         for k, v in upd_g.items():
             self.gen_state[k] = v
         for k, v in upd_d.items():
@@ -471,6 +477,17 @@ class OracleSNGan(object):
         assert not (math.isnan(float(loss_gen)) or math.isnan(float(loss_dis))), \
             'Model diverged with loss = {} at step {}'.format([float(loss_gen), float(loss_dis)], self.global_step)
         return float(loss_gen), float(loss_dis)
+
+
+def imbalanced_schedule(global_step, imbalanced_update):
+    """Which of (dis_op, gen_op) a step runs (graph_func.py:876-886; my_sngan.py:423-439)."""
+    if imbalanced_update is None:
+        return True, True
+    assert len(imbalanced_update) == 2, 'Imbalanced_update length does not match that of op_list. Expected 2 got {}.'.format(
+        len(imbalanced_update))
+    if 1 not in tuple(imbalanced_update):
+        raise AttributeError('One of the imbalanced_update must be 1.')
+    return tuple(int(global_step) % int(k) == 0 for k in imbalanced_update)
 
 
 def synthetic_batch(arch, batch_size, seed=0, dtype=torch.float32):

@@ -68,6 +68,37 @@ def step_case(loss_type, sn_mode='default'):
     return out
 
 
+IMBALANCED = {'d1g2': (1, 2), 'd3g1': (3, 1)}
+
+
+def imbalanced_case(tag, steps=4):
+    """`steps` consecutive steps of the tiny model under Agent(imbalanced_update=...) (graph_func.py:876-908)."""
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    B = 8
+    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=3)
+    onet.warm_spectral_norm(m, 6)
+    out = {'imbalanced_update': np.asarray(IMBALANCED[tag]), 'steps': np.asarray(steps)}
+    for k, v in list(m.gen_params.items()) + list(m.dis_params.items()):
+        out['before:' + k] = v.numpy().copy()
+    for k, v in list(m.gen_state.items()) + list(m.dis_state.items()):
+        out['state_before:' + k] = v.numpy().copy()
+    prev = {k[7:]: v for k, v in out.items() if k.startswith('before:')}
+    for t in range(steps):
+        data, code = onet.synthetic_batch(arch, B, seed=5 + 10 * t, dtype=torch.float32)
+        out['data_%d' % t], out['code_%d' % t] = data.numpy(), code.numpy()
+        lg, ld = m.step(data.double(), code.double(), imbalanced_update=IMBALANCED[tag])
+        out['losses_%d' % t] = np.asarray([lg, ld])
+        for k, v in list(m.gen_params.items()) + list(m.dis_params.items()):     # per step: the size of each variable's update
+            out['delta_%d:%s' % (t, k)] = np.asarray(np.linalg.norm(v.numpy() - prev[k]))
+            prev[k] = v.numpy().copy()
+    for k, v in list(m.gen_params.items()) + list(m.dis_params.items()):
+        out['after:' + k] = v.numpy().copy()
+    for k, v in list(m.gen_state.items()) + list(m.dis_state.items()):
+        out['state_after:' + k] = v.numpy().copy()
+    out['global_step'] = np.asarray(m.global_step)
+    return out
+
+
 def mesh_codes_by_sine(z_support, mesh_num):
     """MeshCode.by_sine (math_func.py:257-291), restated with numpy in float64."""
     m0, m1 = mesh_num
@@ -158,6 +189,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'step_tiny_{}.npz'.format(lt)), **step_case(lt))
     np.savez_compressed(os.path.join(HERE, 'step_tiny_rep_pim.npz'), **step_case('rep', sn_mode='sn_paper'))
     np.savez_compressed(os.path.join(HERE, 'eval_tiny.npz'), **eval_case())
+    for tag in IMBALANCED:
+        np.savez_compressed(os.path.join(HERE, 'step_tiny_imbalanced_{}.npz'.format(tag)), **imbalanced_case(tag))
 
 
 if __name__ == '__main__':

@@ -18,6 +18,8 @@ own functions are run:
                            (batch 4; gradients stored as norms plus a strided sample per variable to keep the file small;
                            the initial variables are the oracle's seeded initialisation, so only the seed is stored)
 
+  ref_step_tiny_imbalanced_<tag>.npz   four steps under Agent(imbalanced_update=(k_dis, k_gen)): the op construction of
+                           my_sngan.py:427-439 and the per-step op selection of graph_func.py:876-908
   ref_eval_tiny.npz        SNGan.eval_sampling's graph section (my_sngan.py:523-551): MeshCode.by_sine codes, the generator and the
                            discriminator with is_training=False, clipping; write_sprite's uint8 mosaics (graph_func.py:222-266)
 
@@ -161,11 +163,21 @@ class ReferenceRun(object):
             assert not missing, 'oracle variables the reference never created: {}'.format(sorted(missing))
         return grads_list, loss_list
 
-    def run(self, grads_list):
-        dis_op = self.opt_ops[0].apply_gradients(grads_list[0], global_step=self.global_step)   # my_sngan.py:424
-        gen_op = self.opt_ops[1].apply_gradients(grads_list[1])                                 # my_sngan.py:425
-        update_ops = tf.get_collection(tf.GraphKeys.UPDATE_OPS)                                 # graph_func.py:848
-        for op in [dis_op, gen_op] + update_ops:          # one sess.run: every value was computed from pre-update variables
+    def run(self, grads_list, imbalanced_update=None):
+        if imbalanced_update is None or imbalanced_update[0] == 1:
+            dis_op = self.opt_ops[0].apply_gradients(grads_list[0], global_step=self.global_step)   # my_sngan.py:424, 431
+            gen_op = self.opt_ops[1].apply_gradients(grads_list[1])                                 # my_sngan.py:425, 432
+        elif imbalanced_update[1] == 1:
+            dis_op = self.opt_ops[0].apply_gradients(grads_list[0])                                 # my_sngan.py:435
+            gen_op = self.opt_ops[1].apply_gradients(grads_list[1], global_step=self.global_step)   # my_sngan.py:436
+        else:
+            raise AttributeError('One of the imbalanced_update must be 1.')                         # my_sngan.py:439
+        op_list = [dis_op, gen_op]
+        if imbalanced_update is not None:                                                           # graph_func.py:885-886
+            global_step_value = int(self.global_step)
+            op_list = [op_list[i] for i in range(2) if global_step_value % imbalanced_update[i] == 0]
+        update_ops = tf.get_collection(tf.GraphKeys.UPDATE_OPS)                                     # graph_func.py:848
+        for op in op_list + update_ops:          # one sess.run: every value was computed from pre-update variables
             op()
 
 
@@ -240,6 +252,33 @@ def ref_step_cifar(batch=4, seed=2, steps=2, act_k=None, script='my_test_cifar.p
     return out
 
 
+def ref_imbalanced_case(tag):
+    """Twin of make_golden.imbalanced_case: the reference's op construction for Agent(imbalanced_update=(k_dis, k_gen))
+    (my_sngan.py:427-439) and MySession.full_run's op selection per step (graph_func.py:876-908)."""
+    base = mg.imbalanced_case(tag)
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    imb = tuple(int(k) for k in base['imbalanced_update'])
+    run = ReferenceRun(arch, 'rep', lr_list=(5e-4, 2e-4))
+    run.set_variables({k.split(':', 1)[1]: v for k, v in base.items() if k.startswith('before:') or k.startswith('state_before:')})
+    out = {k: v for k, v in base.items() if k.split(':')[0].split('_')[0] not in ('after', 'delta', 'state', 'losses') or k.startswith('state_before:')}
+    prev = {k[7:]: v for k, v in base.items() if k.startswith('before:')}
+    for t in range(int(base['steps'])):
+        grads_list, (lg, ld) = run.build(base['data_%d' % t], base['code_%d' % t], base['data_%d' % t].shape[0])
+        out['losses_%d' % t] = np.asarray([float(lg.detach()), float(ld.detach())])
+        run.run(grads_list, imbalanced_update=imb)
+        store = tf.shim_variables()
+        for k in prev:
+            now = store[k].detach().numpy().copy()
+            out['delta_%d:%s' % (t, k)] = np.asarray(np.linalg.norm(now - prev[k]))
+            prev[k] = now
+    store = tf.shim_variables()
+    for k in base:
+        if k.startswith('state_after:') or k.startswith('after:'):
+            out[k] = store[k.split(':', 1)[1]].detach().numpy().copy()
+    out['global_step'] = np.asarray(int(run.global_step))
+    return out
+
+
 def ref_eval_case():
     """Twin of make_golden.eval_case: the reference's eval_sampling graph section (my_sngan.py:523-551) executed eagerly --
     MeshCode.by_sine for the codes (math_func.py:257-291), sample_codes, __gpu_task__(is_training=False), clip_by_value,
@@ -311,6 +350,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_{}.npz'.format(lt)), **ref_step_case(lt))
     np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_rep_pim.npz'), **ref_step_case('rep', sn_mode='sn_paper'))
     np.savez_compressed(os.path.join(HERE, 'ref_eval_tiny.npz'), **ref_eval_case())
+    for tag in mg.IMBALANCED:
+        np.savez_compressed(os.path.join(HERE, 'ref_step_tiny_imbalanced_{}.npz'.format(tag)), **ref_imbalanced_case(tag))
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep.npz'), **ref_step_cifar())
     np.savez_compressed(os.path.join(HERE, 'ref_step_cifar_rep_k27.npz'), **ref_step_cifar(batch=8, act_k=2.7))
     # the other shipped architecture dictionaries, parsed from the reference's scripts (one step, batch 2, sparse samples)

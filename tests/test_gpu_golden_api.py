@@ -224,6 +224,82 @@ def test_sngan_eval_sampling_api(cuda, tmp_path):
         mdl.eval_sampling('toy', 'sngan_rep', do_embedding=True)
 
 
+@pytest.mark.parametrize('use_graph', [False, True], ids=['eager', 'graph'])
+@pytest.mark.parametrize('family', ['', 'ref_'])
+@pytest.mark.parametrize('tag', ['d1g2', 'd3g1'])
+def test_engine_imbalanced_update_against_golden(cuda, tag, family, use_graph):
+    """Agent(imbalanced_update=(k_dis, k_gen)) (my_sngan.py:427-439; graph_func.py:876-908): four steps; the optimiser that is
+    not scheduled leaves its variables, Adam slots and step counter bit-identical; the fixture (`ref_` = the reference's own
+    execution) gives the losses, the size of every update and the final variables."""
+    from oracle import architectures as oa          # the architecture dictionary only
+    from mmdgan_b200.engine import SNGanEngine
+    z = np.load(os.path.join(GOLD, '{}step_tiny_imbalanced_{}.npz'.format(family, tag)))
+    imb = tuple(int(k) for k in z['imbalanced_update'])
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    eng = SNGanEngine(arch, 8, loss_type='rep', use_graph=use_graph)
+    for net in (eng.G, eng.D):
+        for name in net.var_offsets:
+            net.set_variable(name, torch.from_numpy(z['before:' + name]))
+        for name in net.state_names():
+            net.set_state(name, torch.from_numpy(z['state_before:' + name]))
+        net.refresh()
+    for t in range(int(z['steps'])):
+        update = tuple(eng.global_step % k == 0 for k in imb)
+        before = [(net.w.clone(), net.m.clone(), net.v.clone(), int(net.step)) for net in (eng.D, eng.G)]
+        lg, ld = eng.step(torch.from_numpy(z['data_%d' % t]), torch.from_numpy(z['code_%d' % t]), update=update)
+        # losses amplify the accumulated parameter differences of the earlier steps: 1e-3 on the first step, 5e-3 after
+        tol = 1e-3 if t == 0 else 5e-3
+        assert abs(lg - float(z['losses_%d' % t][0])) <= tol * abs(float(z['losses_%d' % t][0])) + 1e-7
+        assert abs(ld - float(z['losses_%d' % t][1])) <= tol * abs(float(z['losses_%d' % t][1])) + 1e-7
+        for (w0, m0, v0, s0), net, runs in zip(before, (eng.D, eng.G), update):
+            if not runs:
+                assert torch.equal(net.w, w0) and torch.equal(net.m, m0) and torch.equal(net.v, v0) and int(net.step) == s0
+            else:
+                assert int(net.step) == s0 + 1
+                for name in net.var_offsets:
+                    if name.endswith('_s/bias/bias'):
+                        continue
+                    off, shape = net.var_offsets[name]
+                    n = int(np.prod(shape))
+                    got = float((net.w[off:off + n] - w0[off:off + n]).double().norm())
+                    ref = float(z['delta_%d:%s' % (t, name)])
+                    assert abs(got - ref) <= 5e-2 * ref, (t, name, got, ref)
+    assert eng.global_step == int(z['global_step'])
+    if use_graph:
+        assert set(eng._graph_cache) == {tuple(t % k == 0 for k in imb) for t in range(1, int(z['steps']))}
+    num = den = 0.0
+    for net in (eng.G, eng.D):
+        for name in net.var_offsets:
+            got = net.get_variable(name).cpu().numpy().astype(np.float64)
+            num += np.linalg.norm(got - z['after:' + name]) ** 2
+            den += np.linalg.norm(z['after:' + name] - z['before:' + name]) ** 2
+        for name in net.state_names():
+            assert rel(net.get_state(name).cpu().numpy(), z['state_after:' + name]) < 1e-3, name
+    assert (num / den) ** 0.5 < 5e-2
+
+
+def test_agent_imbalanced_update_schedule(cuda, tmp_path):
+    from oracle import architectures as oa
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200.GeneralTools.graph_func import Agent
+    from mmdgan_b200.DeepLearning.my_sngan import SNGan
+    FLAGS.DEFAULT_OUT = str(tmp_path) + '/'
+    FLAGS.SILENT_MODE = True
+    images = (np.random.RandomState(0).rand(64, 3, 8, 8) * 255).astype(np.uint8)
+    agent = Agent('toy', 'sngan_rep', do_save=False, print_loss=False, imbalanced_update=(1, 3))
+    mdl = SNGan(oa.tiny(act_k=2.6), num_class=0, loss_type='rep', optimizer='adam')
+    torch.manual_seed(0)
+    losses = mdl.training(images, agent, 64, [5e-4, 2e-4], max_step=7, batch_size=16)
+    assert all(np.isfinite(losses)) and mdl.global_step == 7
+    assert int(mdl.engine.D.step) == 7 and int(mdl.engine.G.step) == 3          # global steps 0, 3, 6
+    with pytest.raises(AttributeError):
+        Agent('toy', 'x', imbalanced_update=(2, 3))
+    with pytest.raises(AssertionError):
+        Agent('toy', 'x', imbalanced_update=(1, 2, 1))
+    with pytest.raises(NotImplementedError):
+        Agent('toy', 'x', imbalanced_update='dynamic')
+
+
 def test_sngan_training_from_tfrecords(cuda, tmp_path):
     """The reference call `mdl.training(filename, ...)` with a TFRecord prefix (my_test_cifar.py) on a toy file: the
     batches the engine trains on are those of ReadTFRecords (uint8 CHW bytes -> x / 127.5 - 1)."""

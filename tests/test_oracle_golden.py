@@ -100,6 +100,37 @@ def test_eval_sampling_golden(family):
     assert np.array_equal(mg.sprite_mosaic(z['x_gen'][:, 0], (3, 2), True), z['sprite_inverted_gray'])
 
 
+@pytest.mark.parametrize('family', ['', 'ref_'])
+@pytest.mark.parametrize('tag', ['d1g2', 'd3g1'])
+def test_imbalanced_update_golden(tag, family):
+    """Agent(imbalanced_update=(k_dis, k_gen)) (my_sngan.py:427-439; graph_func.py:876-908): an optimiser runs on the steps whose
+    global step is a multiple of its k; the other variables, their Adam slots and beta powers stay put; UPDATE_OPS always run."""
+    z = np.load(os.path.join(GOLD, '{}step_tiny_imbalanced_{}.npz'.format(family, tag)))
+    arch = oa.tiny(channels=(16, 16), size=8, code=16, act_k=2.6)
+    imb = tuple(int(k) for k in z['imbalanced_update'])
+    m = onet.OracleSNGan(arch, 'rep', dtype=torch.float64, seed=3)
+    for store, pre in ((m.gen_params, 'before:'), (m.dis_params, 'before:'), (m.gen_state, 'state_before:'), (m.dis_state, 'state_before:')):
+        for k in list(store.keys()):
+            store[k] = torch.from_numpy(z[pre + k])
+    for t in range(int(z['steps'])):
+        prev = {k: v.clone() for k, v in list(m.gen_params.items()) + list(m.dis_params.items())}
+        lg, ld = m.step(torch.from_numpy(z['data_%d' % t]).double(), torch.from_numpy(z['code_%d' % t]).double(), imbalanced_update=imb)
+        assert np.allclose([lg, ld], z['losses_%d' % t], atol=1e-12)
+        for k, v in list(m.gen_params.items()) + list(m.dis_params.items()):
+            ref = float(z['delta_%d:%s' % (t, k)])
+            runs = t % imb[0 if k.startswith('dis/') else 1] == 0
+            assert (ref > 0) == runs, (t, k)
+            if not k.endswith('_s/bias/bias'):   # the score-layer bias gradient is analytically zero: Adam amplifies its round-off
+                assert abs(float((v - prev[k]).norm()) - ref) <= 1e-9 * ref + 1e-15, (t, k)
+    for k, v in list(m.gen_params.items()) + list(m.dis_params.items()):
+        assert np.allclose(v.numpy(), z['after:' + k], atol=4e-3 if k.endswith('_s/bias/bias') else 1e-12), k
+    for k, v in list(m.gen_state.items()) + list(m.dis_state.items()):
+        assert np.allclose(v.numpy(), z['state_after:' + k], atol=1e-12), k
+    assert m.global_step == int(z['global_step']) == int(z['steps'])
+    with pytest.raises(AttributeError):
+        onet.imbalanced_schedule(0, (2, 3))                  # my_sngan.py:439
+
+
 def test_reference_fixture_families_are_complete():
     """Every oracle-authored fixture has a reference-executed twin with the same keys."""
     for path in glob.glob(os.path.join(GOLD, '*.npz')):
