@@ -20,6 +20,7 @@ of the kernel matrices (exact gradients for its own rows, global 1/(B(B-1)) norm
 the flat gradient buffers (+ the six kernel sums).  Batch-norm statistics stay per rank (documented in DESIGN.md).
 """
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -333,7 +334,11 @@ class SNGanEngine(object):
         self._warm = False
         self._stream = torch.cuda.Stream(device=self.device)
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(8)]
-        self._grad_stream = torch.cuda.Stream(device=self.device)   # weight-gradient GEMMs + gradient finalisation
+        # weight-gradient GEMMs + gradient finalisation.  Its kernel nodes get the higher priority: the optimiser updates wait for
+        # the LAST weight gradient, so this stream -- not the input-gradient chain on the capture stream -- ends the step
+        # (measured: 4.40 ms/step with it, 4.49 without, 4.60 with the priorities the other way round)
+        self._grad_stream = torch.cuda.Stream(device=self.device,
+                                              priority=-1 if os.environ.get('MMDGAN_GRAD_PRIORITY', '1') == '1' else 0)
         self._upd_stream = torch.cuda.Stream(device=self.device)    # the generator's Adam + refresh
         self.sn_fork = True
         self.grad_fork = True
