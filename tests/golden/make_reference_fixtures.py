@@ -338,7 +338,7 @@ def ref_eval_case():
 
 def main():
     for lt in ('rep', 'rmb', 'mmd_g', 'mgb', 'mmd_t'):
-        for b in (2, 3, 64) if lt in ('rep', 'rmb') else (64,):
+        for b in (2, 3, 64, 128) if lt in ('rep', 'rmb') else (64,):
             np.savez_compressed(os.path.join(HERE, 'ref_mmd_{}_{}.npz'.format(lt, b)), **ref_mmd_case(lt, b))
     np.savez_compressed(os.path.join(HERE, 'ref_mmd_rep_256.npz'), **ref_mmd_case('rep', 256))
     np.savez_compressed(os.path.join(HERE, 'ref_mmd_rmb_w_1_0.npz'), **ref_mmd_case('rmb', 32, w=(1.0, 0.0)))
