@@ -256,3 +256,25 @@ def test_mesh_codes_and_sprites_against_reference_fixture(tmp_path):
     assert np.allclose(g, [[-1, -1], [-1, 0], [-1, 1], [1, -1], [1, 0], [1, 1]])
     with pytest.raises(AttributeError):
         mc.simple_grid()
+
+
+def test_checkpoint_folder_helpers(tmp_path, monkeypatch):
+    """prepare_folder (graph_func.py:161-180), get_ckpt (399-416: latest by global step, or the named file) and rollback's
+    error (633) -- host logic only, no engine."""
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200.GeneralTools.graph_func import prepare_folder, get_ckpt, rollback
+    monkeypatch.setattr(FLAGS, 'DEFAULT_OUT', str(tmp_path) + '/')
+    ckpt_folder, summary_folder, save_path = prepare_folder('cifar', sub_folder='sngan_rep')
+    assert ckpt_folder == os.path.join(str(tmp_path), 'cifar_ckpt', 'sngan_rep') and os.path.isdir(ckpt_folder)
+    assert summary_folder == os.path.join(str(tmp_path), 'cifar_log', 'sngan_rep') and os.path.isdir(summary_folder)
+    assert save_path == os.path.join(ckpt_folder, 'cifar.ckpt')
+    assert not os.path.isdir(prepare_folder('other', set_folder=False)[0])
+    assert get_ckpt(ckpt_folder) is None and get_ckpt(os.path.join(str(tmp_path), 'missing')) is None
+    for step in (5, 12, 100, 9):                     # numeric, not lexicographic, order
+        open('{}-{}.npz'.format(save_path, step), 'wb').close()
+    open(os.path.join(ckpt_folder, 'notes.txt'), 'w').close()
+    assert get_ckpt(ckpt_folder) == save_path + '-100.npz'
+    assert get_ckpt(ckpt_folder, 'cifar.ckpt-9.npz') == save_path + '-9.npz'
+    assert get_ckpt(ckpt_folder, 'cifar.ckpt-7.npz') is None
+    with pytest.raises(FileNotFoundError, match='No ckpt Model found'):
+        rollback(None, os.path.join(str(tmp_path), 'missing'))
