@@ -4,7 +4,9 @@
   NaN assert (856), loss print every query_step (860-866) and one checkpoint at the last step (869-871).
 
 The TF session / graph / summary machinery has no equivalent here: a "session" is an SNGanEngine whose step is a
-replayed CUDA graph.  Checkpoints are .npz files keyed by the reference's variable names.
+replayed CUDA graph.  Checkpoints are keyed by the reference's variable names, as .npz files or -- with
+FLAGS.CKPT_FORMAT = 'tf' -- in TensorFlow's own checkpoint container (tf_bundle.py), which is also what load_ckpt reads
+when the folder holds a model trained with the reference.
 """
 import os
 import time
@@ -48,9 +50,14 @@ def prepare_folder(filename, sub_folder='', set_folder=True):
     return ckpt_folder, summary_folder, save_path
 
 
-def save_checkpoint(engine, save_path, global_step):
+_BETA_NAMES = (('beta1_power', 'beta2_power'), ('beta1_power_1', 'beta2_power_1'))   # optimiser 0 = dis, 1 = gen (my_sngan.py:424-426)
+
+
+def collect_variables(engine, global_step, tf_names=False):
     """All global variables under the reference's names: weights, biases, BN gamma/beta/moving stats, SN in_rand, Adam
-    slots (<var>/Adam_i, <var>/Adam_i_1) and global_step (graph_func.py:708-717)."""
+    slots (<var>/Adam_i, <var>/Adam_i_1) and global_step (graph_func.py:708-717) as host arrays.  The number of updates each
+    optimiser has applied is kept as `<net>/adam_step`; with tf_names=True it is stored the way TF-1.8 `AdamOptimizer` keeps
+    it -- the non-slot variables beta1_power / beta2_power = beta ** (updates + 1) (suffix `_1` for the second optimiser)."""
     out = {'global_step': np.asarray(global_step, dtype=np.int32)}
     for i, net in enumerate((engine.D, engine.G)):        # Adam_0 = discriminator, Adam_1 = generator (my_sngan.py:414)
         for name in net.var_offsets:
@@ -61,42 +68,118 @@ def save_checkpoint(engine, save_path, global_step):
             out[name + '/Adam_{}_1'.format(i)] = net.v[off:off + n].reshape(shape).cpu().numpy()
         for name in net.state_names():
             out[name] = net.get_state(name).cpu().numpy()
-        out[net.name + '/adam_step'] = net.step.cpu().numpy()
-    path = '{}-{}.npz'.format(save_path, global_step)
-    np.savez(path, **out)
-    return path
+        steps = int(net.step.cpu().numpy().reshape(-1)[0])
+        if tf_names:
+            out[_BETA_NAMES[i][0]] = np.asarray(np.float32(0.5) ** np.float32(steps + 1), dtype=np.float32)
+            out[_BETA_NAMES[i][1]] = np.asarray(np.float32(0.999) ** np.float32(steps + 1), dtype=np.float32)
+        else:
+            out[net.name + '/adam_step'] = net.step.cpu().numpy()
+    return out
+
+
+def _adam_steps(z, i, net_name, global_step):
+    """Updates applied by optimiser i: `<net>/adam_step` (.npz), else recovered from TF's beta2_power = .999 ** (t + 1) while
+    that is a normal float32 (t < ~87 000; afterwards the bias correction is 1 to float32 precision and global_step serves)."""
+    key = net_name + '/adam_step'
+    if key in z:
+        return int(np.asarray(z[key]).reshape(-1)[0])
+    b2 = z.get(_BETA_NAMES[i][1]) if hasattr(z, 'get') else None
+    if b2 is not None and float(b2) > 1e-37:
+        return max(int(round(np.log(float(b2)) / np.log(0.999))) - 1, 0)
+    return int(global_step)
+
+
+def apply_variables(engine, z):
+    """Inverse of collect_variables.  Adam slots are optional (a checkpoint saved from an inference graph has none: the
+    moments then stay as they are)."""
+    import torch
+    gs = int(np.asarray(z['global_step']).reshape(-1)[0])
+    for i, net in enumerate((engine.D, engine.G)):
+        for name in net.var_offsets:
+            net.set_variable(name, torch.from_numpy(np.asarray(z[name])))
+            off, shape = net.var_offsets[name]
+            n = int(np.prod(shape))
+            km, kv = name + '/Adam_{}'.format(i), name + '/Adam_{}_1'.format(i)
+            if km in z and kv in z:
+                net.m[off:off + n].copy_(torch.from_numpy(np.asarray(z[km])).reshape(-1))
+                net.v[off:off + n].copy_(torch.from_numpy(np.asarray(z[kv])).reshape(-1))
+        for name in net.state_names():
+            net.set_state(name, torch.from_numpy(np.asarray(z[name])))
+        net.step.fill_(_adam_steps(z, i, net.name, gs))
+        net.refresh()
+    engine.global_step = gs
+    return gs
+
+
+def _is_tf_prefix(path):
+    return os.path.isfile(path + '.index')
+
+
+def save_checkpoint(engine, save_path, global_step, ckpt_format=None, max_to_keep=2):
+    """`<save_path>-<global_step>`: a .npz file (default) or, with ckpt_format='tf' (FLAGS.CKPT_FORMAT), the files
+    `tf.train.Saver(max_to_keep=2).save(sess, save_path, global_step)` writes (graph_func.py:708-717, 869-871): tensor
+    bundle + the folder's `checkpoint` state file, older bundles beyond max_to_keep removed."""
+    fmt = ckpt_format if ckpt_format is not None else getattr(FLAGS, 'CKPT_FORMAT', 'npz')
+    if fmt == 'npz':
+        path = '{}-{}.npz'.format(save_path, global_step)
+        np.savez(path, **collect_variables(engine, global_step))
+        return path
+    if fmt != 'tf':
+        raise AttributeError('Checkpoint format {} not supported.'.format(fmt))
+    from . import tf_bundle
+    prefix = '{}-{}'.format(save_path, global_step)
+    tf_bundle.write_bundle(prefix, collect_variables(engine, global_step, tf_names=True))
+    folder = os.path.dirname(prefix)
+    state = tf_bundle.read_checkpoint_state(folder)
+    kept = [p for p in (state[1] if state else []) if p != prefix and _is_tf_prefix(p)] + [prefix]
+    for old in kept[:-max_to_keep]:
+        for f in (old + '.index', old + '.data-00000-of-00001', old + '.meta'):
+            if os.path.isfile(f):
+                os.remove(f)
+    tf_bundle.write_checkpoint_state(folder, prefix, kept[-max_to_keep:])
+    return prefix
 
 
 def get_ckpt(ckpt_folder, ckpt_file=None):
-    """graph_func.py:399-416: latest checkpoint in the folder (or the named one)."""
+    """graph_func.py:399-416: latest checkpoint in the folder (or the named one).  Knows both containers: `<file>.ckpt-N.npz`
+    and TF bundles `<file>.ckpt-N{.index, .data-00000-of-00001}` (returned as the prefix, as TF does); the highest global step
+    wins, and a folder holding only TF files is resolved through its `checkpoint` state file first, like
+    tf.train.get_checkpoint_state."""
     if ckpt_file is not None:
         path = os.path.join(ckpt_folder, ckpt_file)
-        return path if os.path.exists(path) else None
+        return path if (os.path.exists(path) or _is_tf_prefix(path)) else None
     if not os.path.isdir(ckpt_folder):
         return None
-    cands = [f for f in os.listdir(ckpt_folder) if f.endswith('.npz') and '.ckpt-' in f]
+    cands = {}
+    for f in os.listdir(ckpt_folder):
+        if '.ckpt-' not in f:
+            continue
+        if f.endswith('.npz'):
+            stem = f[:-4]
+        elif f.endswith('.index'):
+            stem = f[:-6]
+        else:
+            continue
+        tail = stem.rsplit('-', 1)[1]
+        if tail.isdigit():
+            cands.setdefault(int(tail), []).append(f)
     if not cands:
-        return None
-    cands.sort(key=lambda f: int(f.rsplit('-', 1)[1].split('.')[0]))
-    return os.path.join(ckpt_folder, cands[-1])
+        from . import tf_bundle
+        state = tf_bundle.read_checkpoint_state(ckpt_folder)
+        return state[0] if state is not None and _is_tf_prefix(state[0]) else None
+    best = sorted(cands[max(cands)])               # same step in both containers: '.index' sorts first, the bundle wins
+    f = best[0]
+    return os.path.join(ckpt_folder, f[:-6] if f.endswith('.index') else f)
 
 
 def load_checkpoint(engine, path):
-    import torch
-    z = np.load(path)
-    for i, net in enumerate((engine.D, engine.G)):
-        for name in net.var_offsets:
-            net.set_variable(name, torch.from_numpy(z[name]))
-            off, shape = net.var_offsets[name]
-            n = int(np.prod(shape))
-            net.m[off:off + n].copy_(torch.from_numpy(z[name + '/Adam_{}'.format(i)]).reshape(-1))
-            net.v[off:off + n].copy_(torch.from_numpy(z[name + '/Adam_{}_1'.format(i)]).reshape(-1))
-        for name in net.state_names():
-            net.set_state(name, torch.from_numpy(z[name]))
-        net.step.copy_(torch.from_numpy(z[net.name + '/adam_step']))
-        net.refresh()
-    engine.global_step = int(z['global_step'])
-    return engine.global_step
+    """path: a .npz checkpoint or a TF bundle prefix (`.../cifar.ckpt-6284`)."""
+    if path.endswith('.npz') and os.path.isfile(path):
+        return apply_variables(engine, np.load(path))
+    if _is_tf_prefix(path):
+        from . import tf_bundle
+        return apply_variables(engine, tf_bundle.read_bundle(path))
+    raise FileNotFoundError('No ckpt Model found at {}'.format(path))
 
 
 def rollback(engine, ckpt_folder, ckpt_file=None):

@@ -19,6 +19,9 @@ class SetFlag(object):
         # fp16 planes in the forward passes, bf16 planes in the gradient passes), 1 = a single bf16 pass (speed mode, not
         # parity grade)
         self.TENSOR_PASSES = 3
+        # checkpoint container written by Agent.train (new): 'npz', or 'tf' = the tensor-bundle files tf.train.Saver writes
+        # (GeneralTools/tf_bundle.py); both are read back, whichever the folder holds
+        self.CKPT_FORMAT = 'npz'
 
     def print(self, info, force_print=False):
         if (not self.SILENT_MODE) or force_print:
