@@ -182,6 +182,33 @@ def load_checkpoint(engine, path):
     raise FileNotFoundError('No ckpt Model found at {}'.format(path))
 
 
+def print_tensor_in_ckpt(ckpt_folder, all_tensor_values=False, all_tensor_names=False):
+    """graph_func.py:419-443: list the variables of the latest checkpoint under FLAGS.DEFAULT_OUT/<ckpt_folder> (either
+    container), one `name (dtype) shape` line each as TF's inspect_checkpoint prints them; values on request.  Returns the
+    {name: (dtype, shape)} listing."""
+    if not isinstance(ckpt_folder, str):  # if list, use the name of the first file
+        ckpt_folder = ckpt_folder[0]
+    output_folder = os.path.join(FLAGS.DEFAULT_OUT, ckpt_folder)
+    print(output_folder)
+    path = get_ckpt(output_folder)
+    print(path)
+    if path is None:
+        raise FileNotFoundError('No ckpt Model found at {}'.format(output_folder))
+    if path.endswith('.npz') and os.path.isfile(path):
+        z = dict(np.load(path))
+        listing = {k: (v.dtype, tuple(v.shape)) for k, v in z.items()}
+    else:
+        from . import tf_bundle
+        listing = tf_bundle.list_bundle(path)
+        z = tf_bundle.read_bundle(path) if all_tensor_values else {}
+    for name in sorted(listing):
+        dtype, shape = listing[name]
+        print('{} ({}) {}'.format(name, dtype, list(shape)))
+        if all_tensor_values:
+            print(z[name])
+    return listing
+
+
 def rollback(engine, ckpt_folder, ckpt_file=None):
     """graph_func.py:606-636 without the session: restore the engine's variables from the latest (or the named) checkpoint of
     the folder and return its global step."""

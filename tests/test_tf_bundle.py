@@ -264,3 +264,20 @@ def test_load_reference_style_bundle_without_adam_slots(tmp_path, monkeypatch):
     folder = str(tmp_path)
     open(os.path.join(folder, 'lsun.ckpt-200000.npz'), 'wb').close()
     assert gf.get_ckpt(folder) == prefix
+
+
+def test_print_tensor_in_ckpt(tmp_path, monkeypatch, capsys):
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200.GeneralTools import graph_func as gf
+    monkeypatch.setattr(FLAGS, 'DEFAULT_OUT', str(tmp_path) + '/')
+    monkeypatch.setattr(FLAGS, 'SILENT_MODE', True)
+    folder, _, save_path = gf.prepare_folder('cifar', 'sngan_rep')
+    with pytest.raises(FileNotFoundError):
+        gf.print_tensor_in_ckpt('cifar_ckpt/sngan_rep')
+    gf.save_checkpoint(_FakeEngine(1), save_path, 3, ckpt_format='tf')
+    listing = gf.print_tensor_in_ckpt(['cifar_ckpt/sngan_rep'])
+    out = capsys.readouterr().out
+    assert 'dis/l1_f/kernel/kernel (float32) [3, 3, 3, 16]' in out and 'global_step (int32) []' in out
+    assert listing['gen/l1/kernel/kernel/Adam_1_1'] == (np.dtype(np.float32), (16, 64))
+    gf.save_checkpoint(_FakeEngine(1), save_path, 4, ckpt_format='npz')
+    assert gf.print_tensor_in_ckpt('cifar_ckpt/sngan_rep', all_tensor_values=True)['global_step'][1] == ()
