@@ -9,6 +9,8 @@ on), synthetic data, random-init weights.  A "step" is one fused training step (
 `value` is measured with the batch resident in HBM (CUDA-graph replay); `e2e` goes through SNGanEngine.step() with
 HOST tensors: pinned H2D of the batch and D2H of the two losses inside the timed region.  N > 1 (torchrun): the batch
 is sharded, weak scaling (256 images per GPU), scores all-gathered + one gradient all-reduce over NCCL.
+Besides `roofline` (the tcgen05 GEMM launches that carry the step's FLOPs) the N = 1 line carries `mmd_kernel`: BASELINE's second
+metric, the fused MMD kernel's algorithmic bytes (20 * B * d) over its launch time against the measured HBM peak.
 
 Reference arm (--impl reference): TensorFlow-1.8 cannot be installed in this image, so the reference's CPU path is the
 oracle (PyTorch-CPU restatement of the TF1 step, oracle/net.py) timed on the host cores; rank 0 only.
@@ -263,6 +265,35 @@ def run_ours(args):
                          'construction in this precision mode') if args.passes == 3 else
                         'algorithmic FLOPs = (3G+7D) x 2 x B; single bf16 pass (speed mode, not parity grade)'}
 
+    # ---- the fused MMD kernel alone (BASELINE's second metric): algorithmic bytes / launch time against the measured HBM peak
+    mmd_roof = None
+    if not args.no_roofline and world == 1:
+        try:
+            Bm = eng.B
+            sc = eng.D.layers[-1].a[0]                   # [2B, d] scores of the last step
+            sd = eng.D.layers[-1].dz_f32                 # [3B, d] score gradients
+            reps = 200
+            for _ in range(10):
+                eng.mmd(sc[Bm:], sc[:Bm], sd[2 * Bm:], sd[Bm:2 * Bm], sd[:Bm])
+            torch.cuda.synchronize(dev)
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for _ in range(reps):
+                eng.mmd(sc[Bm:], sc[:Bm], sd[2 * Bm:], sd[Bm:2 * Bm], sd[:Bm])
+            m1.record()
+            torch.cuda.synchronize(dev)
+            us = m0.elapsed_time(m1) * 1e3 / reps
+            dsc = int(sc.shape[1])
+            alg_bytes = 20 * Bm * dsc                    # read 2 x [B, d] fp32, write 3 x [B, d] fp32 gradients
+            gbs = alg_bytes / (us * 1e-6) / 1e9
+            mmd_roof = {'kernel': 'mmd_fused_kernel<{}>'.format(dsc), 'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s',
+                        'frac': gbs / peaks['hbm'], 'algorithmic_bytes': alg_bytes, 'us_per_launch': us, 'launches_timed': reps,
+                        'note': 'back-to-back launches on one stream (launch latency included); the {} KB of scores are L2-resident here as in '
+                                'the step, where the preceding launch writes them; at this size the kernel is launch/latency bound, not HBM '
+                                'bound (DESIGN.md section 5, profiles/r1v2_mmd_sweep.txt)'.format(alg_bytes // 1024)}
+        except Exception as exc:                         # the extra measurement must never cost the bench line
+            mmd_roof = {'error': '{}: {}'.format(type(exc).__name__, exc)}
+
     if rank == 0:
         line = {
             'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -281,6 +312,8 @@ def run_ours(args):
         }
         if roof:
             line['roofline'] = roof
+        if mmd_roof:
+            line['mmd_kernel'] = mmd_roof
         if world == 1 and not args.no_cpu_baseline:
             ips, ms, sample, cores = cpu_reference_throughput(name, batch, loss_type, lr, steps=2, warmup=1, budget_s=40.0)
             line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample,
