@@ -12,6 +12,10 @@
 //   mode 1  no swizzle, "row-linear": for each 16-byte K chunk a contiguous array rows x 16 B (core matrices of 8 rows
 //           = 128 contiguous bytes, SBO = 128, LBO = rows * 16), so that a row shift is start += shift * 16 B.
 //           Both assignments of (LBO, SBO) are tried.
+//   mode 2  SWIZZLE_128B, rows of 128 B (64 bf16), 8-row groups 1024 B apart: one operand row is exactly the 128-byte
+//           granule the base-offset field counts, so if the hardware derives the swizzle phase from (row index relative
+//           to the start address + base offset) rather than from absolute address bits, THIS layout still admits every
+//           row shift (mode 0 would then admit even shifts only).  Same two base-offset variants as mode 0.
 //
 // Build and run on the GPU box:
 //   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I mmd-gan_b200/csrc scripts/dev/probe_desc_shift.cu \
@@ -27,13 +31,13 @@ using namespace mg;
 
 static constexpr int kRows = 192;   // staged operand rows (128 MMA rows + up to 64 rows of shift)
 static constexpr int kN = 64;       // accumulator columns
-static constexpr int kK = 32;       // bf16 per row (two K = 16 MMAs)
+static constexpr int kK = 64;       // bf16 per logical row (modes 0 / 1 use the first 32: two K = 16 MMAs; mode 2 all 64: four)
 
 struct ProbeParams {
     const uint16_t* a;   // [kRows][kK] bf16 bits, logical order
     const uint16_t* b;   // [kN][kK]
     float* d;            // [128][kN]
-    int mode;            // 0 = SWIZZLE_64B, 1 = no swizzle (row-linear)
+    int mode;            // 0 = SWIZZLE_64B, 1 = no swizzle (row-linear), 2 = SWIZZLE_128B
     int variant;         // mode 0: 0 = base offset 0, 1 = base offset (start >> 7) & 7.  mode 1: 0 = (LBO = chunk stride, SBO = 128), 1 = swapped
     int shift;           // operand rows
 };
@@ -41,22 +45,24 @@ struct ProbeParams {
 __global__ void __launch_bounds__(128, 1) probe_kernel(const ProbeParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sa = smem;                          // kRows * 64 B = 12 KB
-    uint8_t* sb = smem + kRows * 64;             // kN * 64 B = 4 KB (1024-aligned: 12 KB is a multiple of 1024)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sb + kN * 64);
+    uint8_t* sa = smem;                          // kRows * 128 B = 24 KB at most
+    uint8_t* sb = smem + kRows * 128;            // kN * 128 B = 8 KB at most (1024-aligned: 24 KB is a multiple of 1024)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sb + kN * 128);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     // stage both operands through the generic proxy, 16 bytes (one K chunk of one row) at a time
-    for (int u = t; u < (kRows + kN) * 4; u += 128) {
-        const bool is_a = u < kRows * 4;
-        const int row = is_a ? u >> 2 : (u - kRows * 4) >> 2;
-        const int chunk = u & 3;
+    const int cpr = p.mode == 2 ? 8 : 4;         // 16-byte chunks per staged row
+    for (int u = t; u < (kRows + kN) * cpr; u += 128) {
+        const bool is_a = u < kRows * cpr;
+        const int row = (is_a ? u : u - kRows * cpr) / cpr;
+        const int chunk = u % cpr;
         const uint4 v = *reinterpret_cast<const uint4*>((is_a ? p.a : p.b) + row * kK + chunk * 8);
         uint8_t* base = is_a ? sa : sb;
         const int rows = is_a ? kRows : kN;
         uint32_t off;
         if (p.mode == 0) off = row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);   // absolute-address swizzle (bases are 1024-aligned)
+        else if (p.mode == 2) off = row * 128 + ((chunk ^ (row & 7)) << 4);
         else off = chunk * rows * 16 + row * 16;
         *reinterpret_cast<uint4*>(base + off) = v;
     }
@@ -76,9 +82,14 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const ProbeParams p) {
 
     if (t == 0) {
         const uint32_t idesc = idesc_bf16(128, kN, 0, 0);
-        for (int kk = 0; kk < 2; ++kk) {
+        for (int kk = 0; kk < (p.mode == 2 ? 4 : 2); ++kk) {
             uint64_t ad, bd;
-            if (p.mode == 0) {
+            if (p.mode == 2) {
+                const uint32_t astart = smem_u32(sa) + p.shift * 128 + kk * 32;
+                ad = smem_desc(astart, 16, 1024, 2u);
+                if (p.variant == 1) ad |= static_cast<uint64_t>((astart >> 7) & 7u) << 49;
+                bd = smem_desc(smem_u32(sb) + kk * 32, 16, 1024, 2u);
+            } else if (p.mode == 0) {
                 const uint32_t astart = smem_u32(sa) + p.shift * 64 + kk * 32;
                 ad = smem_desc(astart, 16, 512, 4u);
                 if (p.variant == 1) ad |= static_cast<uint64_t>((astart >> 7) & 7u) << 49;
@@ -130,12 +141,12 @@ int main() {
     cudaMalloc(&dd, 128 * kN * 4);
     cudaMemcpy(da, ab.data(), ab.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(db, bb.data(), bb.size() * 2, cudaMemcpyHostToDevice);
-    const int smem_bytes = kRows * 64 + kN * 64 + 64 + 1024;
+    const int smem_bytes = kRows * 128 + kN * 128 + 64 + 1024;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     const int shifts[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 18, 19, 33, 34, 35, 36, 64};
     std::vector<float> d(128 * kN);
     int failures = 0;
-    for (int mode = 0; mode < 2; ++mode)
+    for (int mode = 0; mode < 3; ++mode)
         for (int variant = 0; variant < 2; ++variant)
             for (int shift : shifts) {
                 cudaMemset(dd, 0xFF, 128 * kN * 4);
@@ -151,12 +162,12 @@ int main() {
                 for (int m = 0; m < 128; ++m)
                     for (int n = 0; n < kN; ++n) {
                         float ref = 0.f;
-                        for (int k = 0; k < kK; ++k) ref += a[(m + shift) * kK + k] * b[n * kK + k];
+                        for (int k = 0; k < (mode == 2 ? 64 : 32); ++k) ref += a[(m + shift) * kK + k] * b[n * kK + k];
                         if (d[m * kN + n] != ref) ++bad;
                     }
-                printf("mode %d (%s) variant %d shift %2d : %5d / %d mismatches%s\n", mode, mode == 0 ? "SWIZZLE_64B" : "row-linear ",
+                printf("mode %d (%s) variant %d shift %2d : %5d / %d mismatches%s\n", mode, mode == 0 ? "SWIZZLE_64B " : (mode == 1 ? "row-linear  " : "SWIZZLE_128B"),
                        variant, shift, bad, 128 * kN, bad ? "" : "  OK");
-                if (bad && shift == 0 && (mode == 0 ? variant == 0 : false)) ++failures;   // the control case must pass
+                if (bad && shift == 0 && mode != 1 && variant == 0) ++failures;   // the control case must pass
             }
     if (failures) printf("CONTROL CASE FAILED: the probe itself is wrong\n");
     return failures ? 1 : 0;
