@@ -12,7 +12,9 @@ This module reads and writes those three files in pure Python / numpy so that we
 loaded into the engine (and the other way round).  Third-party formats, restated from their published definitions
 (TensorFlow 1.8 `tensorflow/core/util/tensor_bundle`, `tensorflow/core/lib/io/table*`, `tensor_bundle.proto`): the
 reference repository ships no checkpoint, so there is NO TF-written file to pin this codec against -- the tests check the
-round trip, the block / footer structure against the format's constants and crc32c against its published check values.
+round trip, the block / footer structure against the format's constants, crc32c against its published check values, and
+the pieces TensorBoard's bundled TensorFlow stubs cover (protobuf-generated TensorShapeProto / VersionDef, the DataType enum,
+TF's masked crc32c) against those.
 Host-side code only; no arithmetic of the training step happens here.
 """
 import os

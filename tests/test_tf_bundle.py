@@ -281,3 +281,49 @@ def test_print_tensor_in_ckpt(tmp_path, monkeypatch, capsys):
     assert listing['gen/l1/kernel/kernel/Adam_1_1'] == (np.dtype(np.float32), (16, 64))
     gf.save_checkpoint(_FakeEngine(1), save_path, 4, ckpt_format='npz')
     assert gf.print_tensor_in_ckpt('cifar_ckpt/sngan_rep', all_tensor_values=True)['global_step'][1] == ()
+
+
+def test_against_tensorboards_tensorflow_protos_and_crc(tmp_path):
+    """Independent pins from Google's own code shipped with TensorBoard (tensorboard.compat): the protobuf-generated
+    TensorShapeProto / VersionDef serialisers, the DataType enum, TF's masked crc32c, and its TFRecord reader reading a file
+    written by input_func.write_tfrecords.  (tensor_bundle.proto itself is not part of TensorBoard.)"""
+    pytest.importorskip('tensorboard')
+    from tensorboard.compat.proto import tensor_shape_pb2, types_pb2, versions_pb2
+    from tensorboard.compat.tensorflow_stub import pywrap_tensorflow as pw
+    from mmdgan_b200.GeneralTools.input_func import masked_crc32c, write_tfrecords, encode_example
+    # the shape sub-message of BundleEntryProto (field 2) and the version sub-message of BundleHeaderProto (field 3)
+    for shape in ((), (7,), (3, 3, 128, 256), (0, 4), (1, 3, 32, 32)):
+        ref = tensor_shape_pb2.TensorShapeProto()
+        for dsize in shape:
+            ref.dim.add().size = dsize
+        ours = tb._encode_entry(1, shape, 0, 0, 0, 0)
+        fields = dict((f, v) for f, _, v in tb._parse_fields(ours))
+        assert bytes(fields[2]) == ref.SerializeToString(), shape
+        back = tensor_shape_pb2.TensorShapeProto.FromString(bytes(fields[2]))
+        assert [d.size for d in back.dim] == list(shape)
+    hdr = dict((f, v) for f, _, v in tb._parse_fields(tb._encode_header(1)))
+    assert bytes(hdr[3]) == versions_pb2.VersionDef(producer=1).SerializeToString() and hdr[1] == 1
+    enum = {np.float32: types_pb2.DT_FLOAT, np.float64: types_pb2.DT_DOUBLE, np.int32: types_pb2.DT_INT32,
+            np.uint8: types_pb2.DT_UINT8, np.int16: types_pb2.DT_INT16, np.int8: types_pb2.DT_INT8, np.int64: types_pb2.DT_INT64,
+            np.bool_: types_pb2.DT_BOOL, np.uint16: types_pb2.DT_UINT16, np.float16: types_pb2.DT_HALF,
+            np.uint32: types_pb2.DT_UINT32, np.uint64: types_pb2.DT_UINT64}
+    assert {np.dtype(k): v for k, v in enum.items()} == tb._DTYPE_ENUM
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 9, 1000):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert pw.masked_crc32c(data) == masked_crc32c(data) == tb.mask_crc(crc32c(data))
+    big = rng.integers(0, 256, 70000, dtype=np.uint8).tobytes()
+    assert pw.crc32c(big) == tb.crc32c_fast(big)
+    # TFRecord framing: TensorBoard's reader accepts what the writer of the input pipeline produces
+    recs = [encode_example({'x': rng.integers(0, 256, 3 * 8 * 8, dtype=np.uint8).tobytes()}) for _ in range(5)]
+    path = str(tmp_path / 'toy.tfrecords')
+    write_tfrecords(path, recs)
+    reader = pw.PyRecordReader_New(path)
+    got = []
+    while True:
+        try:
+            reader.GetNext()
+        except Exception:
+            break
+        got.append(reader.record())
+    assert got == recs
