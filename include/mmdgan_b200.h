@@ -288,6 +288,16 @@ int mmdgan_mmd_fwd_bwd(const mmdgan_mmd_desc* d, void* stream);
 int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float beta1, float beta2, float eps,
                 const int* step, void* stream);
 int mmdgan_incr_step(int* step, void* stream);
+/* Data-parallel form of the same update (new functionality, SURVEY.md 8e: the reference is single-GPU): gradient all-reduce
+ * FUSED with Adam through NVSwitch multicast.  The caller keeps g, w, m, v of one network in a symmetric allocation that is
+ * mapped on every rank and bound to a multicast object; `w`, `m`, `v` are THIS rank's replicas, `*_mc` the multicast addresses
+ * of the four buffers.  For elements [begin, end) (this rank's shard; multiples of 4, 16-byte aligned) the kernel loads the
+ * sum of all ranks' gradients (multimem.ld_reduce), applies the update above and stores the new w, m, v to every replica
+ * (multimem.st).  The caller brackets the call with a cross-rank barrier on the stream: all gradients written before, all
+ * parameters visible after. */
+int mmdgan_adam_allreduce_nvls(const float* w, const float* m, const float* v, const float* g_mc, float* w_mc, float* m_mc,
+                               float* v_mc, long long begin, long long end, float lr, float beta1, float beta2, float eps,
+                               const int* step, void* stream);
 /* device-side replacement of the per-step `assert not any(isnan(loss))` (GeneralTools/graph_func.py:856) */
 int mmdgan_nan_flag(const float* x, int n, int* flag, void* stream);
 

@@ -45,6 +45,8 @@ int l_bn_bwd_reduce(const float*, const float*, const float*, const float*, cons
 int l_bn_bwd_apply(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
                    long long, int, uint16_t*, long long, int, cudaStream_t);
 int l_adam(float*, float*, float*, const float*, long long, float, float, float, float, const int*, cudaStream_t);
+int l_adam_allreduce_nvls(const float*, const float*, const float*, const float*, float*, float*, float*, long long, long long, float, float, float,
+                          float, const int*, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
 int l_dense_small_fwd(const uint16_t*, long long, int, int, int, int, const uint16_t*, long long, int, int, int, float, const float*, const float*,
@@ -427,6 +429,18 @@ int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float
     if (!w || !m || !v || !g || !step) return fail(MMDGAN_EINVAL, "mmdgan_adam: null pointer");
     if (n <= 0) return MMDGAN_OK;
     return wrap(mg::l_adam(w, m, v, g, n, lr, beta1, beta2, eps, step, S(stream)), "mmdgan_adam");
+}
+int mmdgan_adam_allreduce_nvls(const float* w, const float* m, const float* v, const float* g_mc, float* w_mc, float* m_mc,
+                               float* v_mc, long long begin, long long end, float lr, float beta1, float beta2, float eps,
+                               const int* step, void* stream) {
+    if (!w || !m || !v || !g_mc || !w_mc || !m_mc || !v_mc || !step)
+        return fail(MMDGAN_EINVAL, "mmdgan_adam_allreduce_nvls: null pointer");
+    if (begin < 0 || end < begin || (begin & 3) || (end & 3))
+        return fail(MMDGAN_ESHAPE, "mmdgan_adam_allreduce_nvls: shard [%lld, %lld) must be a range of whole float4 groups", begin, end);
+    if (!al16(w) || !al16(m) || !al16(v) || !al16(g_mc) || !al16(w_mc) || !al16(m_mc) || !al16(v_mc))
+        return fail(MMDGAN_ESHAPE, "mmdgan_adam_allreduce_nvls: buffers must be 16-byte aligned");
+    return wrap(mg::l_adam_allreduce_nvls(w, m, v, g_mc, w_mc, m_mc, v_mc, begin, end, lr, beta1, beta2, eps, step, S(stream)),
+                "mmdgan_adam_allreduce_nvls");
 }
 int mmdgan_incr_step(int* step, void* stream) {
     if (!step) return fail(MMDGAN_EINVAL, "mmdgan_incr_step: null pointer");

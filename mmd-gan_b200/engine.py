@@ -67,7 +67,7 @@ class _LayerRT(object):
 class NetRuntime(object):
     """Parameters + per-layer kernel plans of one Net for a fixed number of samples per forward pass."""
 
-    def __init__(self, routine, nimg_fwd, nimg_bwd, npass, device, gen):
+    def __init__(self, routine, nimg_fwd, nimg_bwd, npass, device, gen, flat_alloc=None):
         self.routine = routine
         self.net = routine.net
         self.name = self.net.net_name
@@ -99,10 +99,16 @@ class NetRuntime(object):
             self.var_offsets[name] = (off, list(t.shape))
             off += (t.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.n_flat = off
-        self.w = torch.zeros(off, dtype=torch.float32, device=device)
-        self.g = torch.zeros(off, dtype=torch.float32, device=device)
-        self.m = torch.zeros(off, dtype=torch.float32, device=device)
-        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        # flat_alloc (data-parallel NVLS mode): g, w, m, v live in one symmetric allocation bound to an NVSwitch multicast
+        # object (parallel.SymmetricFlat); every view / pointer below is taken from these tensors, so nothing else changes
+        self.flat = flat_alloc(off) if flat_alloc is not None else None
+        if self.flat is not None:
+            self.w, self.g, self.m, self.v = self.flat.w, self.flat.g, self.flat.m, self.flat.v
+        else:
+            self.w = torch.zeros(off, dtype=torch.float32, device=device)
+            self.g = torch.zeros(off, dtype=torch.float32, device=device)
+            self.m = torch.zeros(off, dtype=torch.float32, device=device)
+            self.v = torch.zeros(off, dtype=torch.float32, device=device)
         for name, t in inits.items():
             self.view(self.w, name).copy_(t.reshape(-1).float())
         self.step = torch.zeros(1, dtype=torch.int32, device=device)
@@ -319,8 +325,14 @@ class SNGanEngine(object):
         self.Dis.seq_links(list(range(d_net.num_layers)))
         self.Dis.add_output_layers([d_net.num_layers - 1])
         gen = torch.Generator().manual_seed(seed)
-        self.G = NetRuntime(self.Gen, B, B, self.npass, self.device, gen)
-        self.D = NetRuntime(self.Dis, 2 * B, 3 * B, self.npass, self.device, gen)
+        # opt-in: gradient all-reduce fused with Adam through NVSwitch multicast (csrc/nvls.cu) instead of NCCL + adam_kernel
+        self.nvls = world_size > 1 and os.environ.get('MMDGAN_NVLS_ADAM', '0') == '1'
+        flat_alloc = None
+        if self.nvls:
+            from . import parallel
+            flat_alloc = lambda n: parallel.SymmetricFlat(n, self.device, process_group)      # noqa: E731
+        self.G = NetRuntime(self.Gen, B, B, self.npass, self.device, gen, flat_alloc)
+        self.D = NetRuntime(self.Dis, 2 * B, 3 * B, self.npass, self.device, gen, flat_alloc)
         self._alloc_buffers()
         self.mmd = K.MmdKernel(loss_type, self.rep_weights, b=B, device=self.device)
         self.global_step = 0
@@ -641,7 +653,15 @@ class SNGanEngine(object):
                 continue
             with torch.cuda.stream(st):
                 K.incr_step(net.step)
-                K.adam(net.w, net.m, net.v, net.g, net.n_flat, lr, net.step)
+                if self.nvls:
+                    # every rank's gradients are complete -> switch-reduced gradients, Adam on this rank's shard, new w / m / v
+                    # multicast to all replicas -> every replica complete before the packed operands are rebuilt from w
+                    f = net.flat
+                    f.barrier()
+                    K.adam_allreduce_nvls(net.w, net.m, net.v, f.g_mc, f.w_mc, f.m_mc, f.v_mc, f.begin, f.end, lr, net.step)
+                    f.barrier()
+                else:
+                    K.adam(net.w, net.m, net.v, net.g, net.n_flat, lr, net.step)
                 net.refresh()
         self._dis_updated = False
         with torch.cuda.stream(side):
@@ -661,7 +681,8 @@ class SNGanEngine(object):
 
     def _allreduce_grads(self):
         from . import parallel
-        parallel.allreduce_sum([self.D.g, self.G.g, self.mmd.sums], self.pg)
+        # NVLS mode: the parameter gradients are reduced inside the optimiser kernel; only the six kernel sums go through NCCL
+        parallel.allreduce_sum([self.mmd.sums] if self.nvls else [self.D.g, self.G.g, self.mmd.sums], self.pg)
         lg, ld = parallel.losses_from_sums(self.mmd.sums, [float(c) for c in self.mmd.desc.cD])
         self.mmd.losses[0] = lg
         self.mmd.losses[1] = ld
@@ -682,6 +703,8 @@ class SNGanEngine(object):
         torch.cuda.synchronize(self.device)
         segs = ([[self._phase_forward], [self._phase_loss, self._phase_backward], [self._phase_update]]
                 if self.world_size > 1 else [[self._phase_forward, self._phase_loss, self._phase_backward, self._phase_update]])
+        if self.nvls:
+            segs = segs[:2]      # the update phase holds cross-rank barriers: it is enqueued eagerly after the second graph
         graphs = []
         for fns in segs:
             g = torch.cuda.CUDAGraph()
@@ -716,7 +739,10 @@ class SNGanEngine(object):
                 self._gather_scores()
                 graphs[1].replay()
                 self._allreduce_grads()
-                graphs[2].replay()
+                if self.nvls:
+                    self._phase_update()
+                else:
+                    graphs[2].replay()
             else:
                 graphs[0].replay()
         self.global_step += 1

@@ -607,6 +607,14 @@ def adam(w, m, v, g, n, lr, step, beta1=0.5, beta2=0.999, eps=1e-8):
                             stream()))
 
 
+def adam_allreduce_nvls(w, m, v, g_mc, w_mc, m_mc, v_mc, begin, end, lr, step, beta1=0.5, beta2=0.999, eps=1e-8):
+    """Gradient all-reduce fused with Adam through NVSwitch multicast (csrc/nvls.cu).  w / m / v: this rank's replicas;
+    *_mc: integer multicast addresses of the four buffers; [begin, end): this rank's shard of the flat buffer."""
+    check(lib().mmdgan_adam_allreduce_nvls(_ptr(w), _ptr(m), _ptr(v), C.c_void_p(g_mc), C.c_void_p(w_mc), C.c_void_p(m_mc),
+                                           C.c_void_p(v_mc), int(begin), int(end), float(lr), float(beta1), float(beta2),
+                                           float(eps), _ptr(step), stream()))
+
+
 def incr_step(step):
     check(lib().mmdgan_incr_step(_ptr(step), stream()))
 

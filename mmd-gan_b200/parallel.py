@@ -8,6 +8,10 @@ SURVEY.md section 8(e).  The batch dimension is sharded; the only batch-coupled 
   * the parameter gradients and the six kernel sums -> one sum all-reduce per flat buffer (the local gradients are
     already normalised by the GLOBAL 1/(B(B-1)), so the sum is the global-batch gradient; no averaging).
 Batch-norm statistics stay per rank (per-GPU batch), as documented in DESIGN.md.
+
+Opt-in (MMDGAN_NVLS_ADAM=1): the gradient all-reduce and the Adam update become ONE kernel over NVSwitch multicast
+(csrc/nvls.cu).  SymmetricFlat below owns the [g | w | m | v] allocation of one network, mapped on every rank and bound to a
+multicast object through torch's symmetric-memory rendezvous (plumbing only: allocation, address exchange, stream barriers).
 """
 import torch
 import torch.distributed as dist
@@ -45,3 +49,39 @@ def losses_from_sums(sums, cD):
 def row_block(rank, b):
     """Global row range owned by `rank`."""
     return rank * b, (rank + 1) * b
+
+
+def shard_range(n_flat, rank, world):
+    """[begin, end) of `rank`'s share of a flat buffer of n_flat floats, in whole float4 groups."""
+    n4 = n_flat // 4
+    assert n4 * 4 == n_flat, 'flat parameter buffers are padded to whole float4 groups'
+    return (n4 * rank // world) * 4, (n4 * (rank + 1) // world) * 4
+
+
+class SymmetricFlat(object):
+    """g, w, m, v of one network in one symmetric allocation (4 x n_flat float32), the same size on every rank."""
+
+    def __init__(self, n_flat, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        self.n = int(n_flat)
+        self.buf = symm_mem.empty(4 * self.n, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        try:                                   # older releases need the group registered first; newer ones deprecate the call
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.handle = symm_mem.rendezvous(self.buf, group.group_name)
+        mc = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
+        if mc:
+            mc += int(getattr(self.handle, 'offset', 0) or 0)      # position of this tensor inside the mapped block
+        if mc == 0:
+            raise RuntimeError('MMDGAN_NVLS_ADAM=1 needs NVSwitch multicast (NVLS); this fabric / driver offers none')
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self.g, self.w, self.m, self.v = (self.buf[i * self.n:(i + 1) * self.n] for i in range(4))
+        self.g_mc, self.w_mc, self.m_mc, self.v_mc = (mc + 4 * i * self.n for i in range(4))
+        self.begin, self.end = shard_range(self.n, self.rank, self.world)
+
+    def barrier(self):
+        """Cross-rank barrier enqueued on the current stream (device side, through the allocation's signal pads)."""
+        self.handle.barrier(channel=0)

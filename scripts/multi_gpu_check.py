@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N scripts/multi_gpu_check.py : N-rank data-parallel step == single-rank step on the
 concatenated batch (a generator WITHOUT batch norm, so that per-rank BN statistics do not enter), and replicas stay
-bit-identical.  Prints 'MULTI_GPU_OK' on rank 0."""
+bit-identical.  Prints 'MULTI_GPU_OK' on rank 0.  With MMDGAN_NVLS_ADAM=1 in the environment the same checks run on the fused
+NVSwitch-multicast all-reduce + Adam kernel (csrc/nvls.cu); 'NVLS_UNAVAILABLE' if the fabric has no multicast."""
 import os
 import sys
 
@@ -31,7 +32,16 @@ def main():
     data = torch.rand(steps, world * b, 3, 8, 8, generator=g) * 2 - 1
     code = torch.randn(steps, world * b, arch['code'][0][0], generator=g)
     for use_graph in (False, True):
-        eng = SNGanEngine(arch, b, loss_type='rmb', device=dev, world_size=world, rank=rank, use_graph=use_graph, seed=5)
+        try:
+            eng = SNGanEngine(arch, b, loss_type='rmb', device=dev, world_size=world, rank=rank, use_graph=use_graph, seed=5)
+        except RuntimeError as exc:
+            if os.environ.get('MMDGAN_NVLS_ADAM') == '1' and 'NVLS' in str(exc):     # no multicast on this fabric: nothing to check
+                if rank == 0:
+                    print('NVLS_UNAVAILABLE {}'.format(exc), flush=True)
+                dist.destroy_process_group()
+                return
+            raise
+        assert eng.nvls == (os.environ.get('MMDGAN_NVLS_ADAM') == '1')
         ref = SNGanEngine(arch, world * b, loss_type='rmb', device=dev, use_graph=False, seed=5) if rank == 0 else None
         for it in range(steps):
             sl = slice(rank * b, (rank + 1) * b)

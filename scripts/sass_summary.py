@@ -3,7 +3,7 @@
 resource lines of the build logs.  Runs without a GPU:  python scripts/sass_summary.py > profiles/<tag>_sass_summary.md
 
 What the mnemonics prove (B200 profiling recipe): UTC*MMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA tensor loads,
-LDGSTS = cp.async, HMMA = the legacy mma.sync path (must be absent)."""
+LDGSTS = cp.async, LDGMC = multimem.ld_reduce (NVSwitch in-fabric reduction), HMMA = the legacy mma.sync path (must be absent)."""
 import collections
 import glob
 import os
@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'mmd-gan_b200', 'libmmdgan_b200.so')
-COLS = ['UTC*MMA', 'LDTM', 'UTMALDG', 'UTCBAR', 'SYNCS', 'LDGSTS', 'HMMA', 'MUFU.EX2', 'SHFL', 'LDG.E.128', 'STG.E.128']
+COLS = ['UTC*MMA', 'LDTM', 'UTMALDG', 'UTCBAR', 'SYNCS', 'LDGSTS', 'LDGMC', 'HMMA', 'MUFU.EX2', 'SHFL', 'LDG.E.128', 'STG.E.128']
 
 
 def demangle(names):
@@ -41,7 +41,7 @@ def main():
         c['total'] += 1
         if re.match(r'UTC[A-Z]*MMA', op):
             c['UTC*MMA'] += 1
-        for key in ('LDTM', 'UTMALDG', 'UTCBAR', 'SYNCS', 'LDGSTS', 'HMMA', 'MUFU.EX2', 'SHFL', 'LDG.E.128', 'STG.E.128'):
+        for key in ('LDTM', 'UTMALDG', 'UTCBAR', 'SYNCS', 'LDGSTS', 'LDGMC', 'HMMA', 'MUFU.EX2', 'SHFL', 'LDG.E.128', 'STG.E.128'):
             if op.startswith(key):
                 c[key] += 1
     names = demangle(order)
@@ -58,7 +58,8 @@ def main():
                 res[fn] = m.group(1)
     print('# Static SASS / ptxas summary of libmmdgan_b200.so (sm_100a; `python scripts/sass_summary.py`, no GPU needed)\n')
     print('`UTC*MMA` = tcgen05.mma, `LDTM` = tcgen05.ld, `UTMALDG` = TMA tensor load, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier,')
-    print('`LDGSTS` = cp.async, `HMMA` = legacy mma.sync (absent everywhere: no kernel falls back to the warp-level tensor path).\n')
+    print('`LDGSTS` = cp.async, `LDGMC` = multimem.ld_reduce (NVSwitch in-fabric reduction; multimem.st is an ordinary `STG...SYS` to the')
+    print('multicast address), `HMMA` = legacy mma.sync (absent everywhere: no kernel falls back to the warp-level tensor path).\n')
     print('| kernel | regs | SASS instr | ' + ' | '.join(COLS) + ' |')
     print('|---|---|---|' + '---|' * len(COLS))
     tot = collections.Counter()

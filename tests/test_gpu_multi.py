@@ -17,3 +17,4 @@ def test_two_rank_step_matches_single_rank(cuda):
            '--master-port', str(29600 + os.getpid() % 300), os.path.join(ROOT, 'scripts', 'multi_gpu_check.py')]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert 'MULTI_GPU_OK' in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+

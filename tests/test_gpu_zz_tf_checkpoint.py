@@ -49,3 +49,22 @@ def test_tf_container_checkpoint_resume_and_eval(cuda, tmp_path, monkeypatch):
     # eval_sampling restores the named bundle
     out = mdl2.eval_sampling('toy', 'sngan_rep', mesh_num=(3, 4), ckpt_file='toy.ckpt-5', do_sprite=False)
     assert out['global_step'] == 5 and out['x_gen'].shape == (12, 3, 8, 8) and np.isfinite(out['x_gen']).all()
+
+
+def test_two_rank_step_with_fused_nvls_allreduce_adam(cuda):
+    """The 2-rank equalities of tests/test_gpu_multi.py with the gradient all-reduce + Adam fused into one NVSwitch-multicast
+    kernel (MMDGAN_NVLS_ADAM=1, csrc/nvls.cu).  The path is opt-in and was written without access to a multi-GPU box, so the
+    test is opt-in too (MMDGAN_TEST_NVLS=1) until it has been run once."""
+    import subprocess
+    import sys
+    if os.environ.get('MMDGAN_TEST_NVLS') != '1':
+        pytest.skip('opt-in: set MMDGAN_TEST_NVLS=1 (needs 2 GPUs behind an NVSwitch)')
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(29900 + os.getpid() % 300), os.path.join(root, 'scripts', 'multi_gpu_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MMDGAN_NVLS_ADAM='1'))
+    if 'NVLS_UNAVAILABLE' in out.stdout:
+        pytest.skip('no NVSwitch multicast on this box')
+    assert 'MULTI_GPU_OK' in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

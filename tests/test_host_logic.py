@@ -153,6 +153,14 @@ def test_cabi_argument_validation_without_a_gpu():
     assert lib.mmdgan_gather_gemm(ctypes.byref(g), None) == _lib.MMDGAN_EINVAL          # null pointers: rejected before any CUDA call
     assert lib.mmdgan_mmd_fwd_bwd(ctypes.byref(d), None) == _lib.MMDGAN_EINVAL
     assert lib.mmdgan_adam(None, None, None, None, 10, 1e-3, 0.5, 0.999, 1e-8, None, None) == _lib.MMDGAN_EINVAL
+    # fused NVSwitch all-reduce + Adam (csrc/nvls.cu): argument validation happens before any CUDA call
+    nv = lib.mmdgan_adam_allreduce_nvls
+    assert nv(None, None, None, None, None, None, None, 0, 16, 1e-3, 0.5, 0.999, 1e-8, None, None) == _lib.MMDGAN_EINVAL
+    fake16, step = ctypes.c_void_p(4096), ctypes.c_void_p(8192)
+    assert nv(fake16, fake16, fake16, fake16, fake16, fake16, fake16, 2, 16, 1e-3, 0.5, 0.999, 1e-8, step, None) == _lib.MMDGAN_ESHAPE
+    assert b'whole float4 groups' in lib.mmdgan_last_error()
+    assert nv(fake16, fake16, fake16, ctypes.c_void_p(4100), fake16, fake16, fake16, 0, 16, 1e-3, 0.5, 0.999, 1e-8, step, None) == _lib.MMDGAN_ESHAPE
+    assert nv(fake16, fake16, fake16, fake16, fake16, fake16, fake16, 16, 16, 1e-3, 0.5, 0.999, 1e-8, step, None) == _lib.MMDGAN_OK   # empty shard
     assert lib.mmdgan_mmd_workspace(256) >= 64 * 6 * 4
 
 
@@ -278,3 +286,19 @@ def test_checkpoint_folder_helpers(tmp_path, monkeypatch):
     assert get_ckpt(ckpt_folder, 'cifar.ckpt-7.npz') is None
     with pytest.raises(FileNotFoundError, match='No ckpt Model found'):
         rollback(None, os.path.join(str(tmp_path), 'missing'))
+
+
+def test_nvls_shard_ranges_cover_the_flat_buffer():
+    """parallel.shard_range: the per-rank shards of the fused all-reduce + Adam kernel are disjoint whole-float4 ranges that
+    tile [0, n_flat) for every world size, also when n_flat / 4 is not a multiple of it."""
+    from mmdgan_b200.parallel import shard_range
+    for n_flat in (64, 64 * 3, 64 * 61, 6000000 // 64 * 64):
+        for world in (1, 2, 3, 4, 8):
+            pos = 0
+            for rank in range(world):
+                b, e = shard_range(n_flat, rank, world)
+                assert b == pos and e >= b and b % 4 == 0 and e % 4 == 0
+                pos = e
+            assert pos == n_flat
+    with pytest.raises(AssertionError):
+        shard_range(66, 0, 2)
