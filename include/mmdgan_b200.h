@@ -287,6 +287,11 @@ int mmdgan_mmd_fwd_bwd(const mmdgan_mmd_desc* d, void* stream);
  * (GeneralTools/graph_func.py:518-527; DeepLearning/my_sngan.py:424-426).  *step holds t for this update. */
 int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float beta1, float beta2, float eps,
                 const int* step, void* stream);
+/* Forward exchange of the data-parallel MMD loss through the same multicast mechanism (replaces the all-gather of the score
+ * blocks): s_local [2b, d] (rows [0, b) real, [b, 2b) generated, my_sngan.py:279) is stored to rows
+ * [rank * b, (rank + 1) * b) of real_all / gen_all on EVERY rank; `*_mc` are multicast addresses of two [world * b, d] fp32
+ * buffers of a symmetric allocation.  The caller brackets the call with a cross-rank barrier on the stream. */
+int mmdgan_scatter_scores_nvls(const float* s_local, int b, int d, int rank, float* gen_all_mc, float* real_all_mc, void* stream);
 int mmdgan_incr_step(int* step, void* stream);
 /* Data-parallel form of the same update (new functionality, SURVEY.md 8e: the reference is single-GPU): gradient all-reduce
  * FUSED with Adam through NVSwitch multicast.  The caller keeps g, w, m, v of one network in a symmetric allocation that is

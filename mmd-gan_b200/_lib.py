@@ -132,6 +132,7 @@ SYMBOLS = {
     'mmdgan_mmd_fwd_bwd': (_I, [C.POINTER(MmdDesc), _P]),
     'mmdgan_adam': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _P]),
     'mmdgan_adam_allreduce_nvls': (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _P, _P]),
+    'mmdgan_scatter_scores_nvls': (_I, [_P, _I, _I, _I, _P, _P, _P]),
     'mmdgan_incr_step': (_I, [_P, _P]),
     'mmdgan_nan_flag': (_I, [_P, _I, _P, _P]),
 }

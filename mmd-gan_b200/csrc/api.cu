@@ -47,6 +47,7 @@ int l_bn_bwd_apply(const float*, const float*, const float*, const float*, const
 int l_adam(float*, float*, float*, const float*, long long, float, float, float, float, const int*, cudaStream_t);
 int l_adam_allreduce_nvls(const float*, const float*, const float*, const float*, float*, float*, float*, long long, long long, float, float, float,
                           float, const int*, cudaStream_t);
+int l_scatter_scores_nvls(const float*, int, int, int, float*, float*, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
 int l_dense_small_fwd(const uint16_t*, long long, int, int, int, int, const uint16_t*, long long, int, int, int, float, const float*, const float*,
@@ -441,6 +442,12 @@ int mmdgan_adam_allreduce_nvls(const float* w, const float* m, const float* v, c
         return fail(MMDGAN_ESHAPE, "mmdgan_adam_allreduce_nvls: buffers must be 16-byte aligned");
     return wrap(mg::l_adam_allreduce_nvls(w, m, v, g_mc, w_mc, m_mc, v_mc, begin, end, lr, beta1, beta2, eps, step, S(stream)),
                 "mmdgan_adam_allreduce_nvls");
+}
+int mmdgan_scatter_scores_nvls(const float* s_local, int b, int d, int rank, float* gen_all_mc, float* real_all_mc, void* stream) {
+    if (!s_local || !gen_all_mc || !real_all_mc) return fail(MMDGAN_EINVAL, "mmdgan_scatter_scores_nvls: null pointer");
+    if (b <= 0 || d <= 0 || (d & 3) || rank < 0) return fail(MMDGAN_ESHAPE, "mmdgan_scatter_scores_nvls: b %d, d %d (multiple of 4), rank %d", b, d, rank);
+    if (!al16(s_local) || !al16(gen_all_mc) || !al16(real_all_mc)) return fail(MMDGAN_ESHAPE, "mmdgan_scatter_scores_nvls: buffers must be 16-byte aligned");
+    return wrap(mg::l_scatter_scores_nvls(s_local, b, d, rank, gen_all_mc, real_all_mc, S(stream)), "mmdgan_scatter_scores_nvls");
 }
 int mmdgan_incr_step(int* step, void* stream) {
     if (!step) return fail(MMDGAN_EINVAL, "mmdgan_incr_step: null pointer");

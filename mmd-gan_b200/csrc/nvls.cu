@@ -13,6 +13,8 @@
 // construction.  The four buffers live in ONE symmetric allocation per network ([g | w | m | v]); the host brackets the
 // launch with the allocation's device-side barriers (all gradients written before / all parameters visible after).
 //
+// The same switch feature carries the forward exchange of the MMD loss (scatter_scores_nvls_kernel below).
+//
 // Opt-in (MMDGAN_NVLS_ADAM=1, world size > 1, multicast-capable fabric); the default multi-GPU path is NCCL.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -58,6 +60,28 @@ __global__ void adam_allreduce_nvls_kernel(const float* w, const float* m, const
         multimem_st_f32x4(v_mc + i, vo);
         multimem_st_f32x4(w_mc + i, wo);
     }
+}
+
+// Score exchange of the data-parallel MMD loss (parallel.gather_scores: all-gather + two re-ordering copies) as ONE multicast
+// kernel: s_local [2b, d] holds this rank's scores, rows [0, b) real and [b, 2b) generated (my_sngan.py:279); they become rows
+// [rank * b, (rank + 1) * b) of real_all / gen_all on EVERY rank.  The host brackets the launch with cross-rank barriers.
+__global__ void scatter_scores_nvls_kernel(const float* __restrict__ s_local, int b, int d, int rank, float* gen_all_mc, float* real_all_mc) {
+    const int n4 = (2 * b * d) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+        const int e = q << 2;
+        const int row = e / d, col = e - row * d;
+        const float4 v = *reinterpret_cast<const float4*>(s_local + e);
+        float* dst = row < b ? real_all_mc + static_cast<long long>(rank * b + row) * d + col
+                             : gen_all_mc + static_cast<long long>(rank * b + row - b) * d + col;
+        multimem_st_f32x4(dst, v);
+    }
+}
+
+int l_scatter_scores_nvls(const float* s_local, int b, int d, int rank, float* gen_all_mc, float* real_all_mc, cudaStream_t st) {
+    const int n4 = (2 * b * d) >> 2;
+    if (n4 <= 0) return 0;
+    scatter_scores_nvls_kernel<<<(n4 + 255) / 256, 256, 0, st>>>(s_local, b, d, rank, gen_all_mc, real_all_mc);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 int l_adam_allreduce_nvls(const float* w, const float* m, const float* v, const float* g_mc, float* w_mc, float* m_mc, float* v_mc,

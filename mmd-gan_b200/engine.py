@@ -410,6 +410,10 @@ class SNGanEngine(object):
             self.s_gather = torch.zeros((self.world_size, 2 * B, d), dtype=torch.float32, device=dev)
             self.gen_all = torch.zeros((self.world_size * B, d), dtype=torch.float32, device=dev)
             self.real_all = torch.zeros((self.world_size * B, d), dtype=torch.float32, device=dev)
+            if self.nvls:        # the gathered score matrices live in a symmetric allocation: peers multicast their blocks into it
+                from . import parallel
+                self.sym_scores = parallel.SymmetricScores(B, d, dev, self.pg)
+                self.gen_all, self.real_all = self.sym_scores.gen_all, self.sym_scores.real_all
 
     # -------------------------------------------------------------------------------------------- forward passes
     @staticmethod
@@ -677,6 +681,9 @@ class SNGanEngine(object):
     # -------------------------------------------------------------------------------------------- collectives
     def _gather_scores(self):
         from . import parallel
+        if self.nvls:            # one multicast kernel between two device-side barriers instead of all-gather + two copies
+            self.sym_scores.scatter(self.D.layers[-1].a[0].contiguous())
+            return
         parallel.gather_scores(self.D.layers[-1].a[0], self.B, self.s_gather, self.gen_all, self.real_all, self.pg)
 
     def _allreduce_grads(self):

@@ -615,6 +615,12 @@ def adam_allreduce_nvls(w, m, v, g_mc, w_mc, m_mc, v_mc, begin, end, lr, step, b
                                            float(eps), _ptr(step), stream()))
 
 
+def scatter_scores_nvls(s_local, b, rank, gen_all_mc, real_all_mc):
+    """This rank's [2b, d] scores -> rows [rank*b, (rank+1)*b) of real_all / gen_all on every rank (csrc/nvls.cu)."""
+    check(lib().mmdgan_scatter_scores_nvls(_ptr(s_local), int(b), int(s_local.shape[1]), int(rank), C.c_void_p(gen_all_mc),
+                                           C.c_void_p(real_all_mc), stream()))
+
+
 def incr_step(step):
     check(lib().mmdgan_incr_step(_ptr(step), stream()))
 

@@ -58,25 +58,50 @@ def shard_range(n_flat, rank, world):
     return (n4 * rank // world) * 4, (n4 * (rank + 1) // world) * 4
 
 
+def _symmetric(numel, device, group):
+    """(tensor, handle, multicast address) of a zero-filled symmetric float32 allocation of `numel` elements."""
+    import torch.distributed._symmetric_memory as symm_mem
+    group = dist.group.WORLD if group is None else group
+    buf = symm_mem.empty(int(numel), dtype=torch.float32, device=device)
+    buf.zero_()
+    try:                                   # older releases need the group registered first; newer ones deprecate the call
+        symm_mem.enable_symm_mem_for_group(group.group_name)
+    except Exception:
+        pass
+    handle = symm_mem.rendezvous(buf, group.group_name)
+    mc = int(getattr(handle, 'multicast_ptr', 0) or 0)
+    if mc:
+        mc += int(getattr(handle, 'offset', 0) or 0)      # position of this tensor inside the mapped block
+    if mc == 0:
+        raise RuntimeError('MMDGAN_NVLS_ADAM=1 needs NVSwitch multicast (NVLS); this fabric / driver offers none')
+    return buf, handle, mc
+
+
+class SymmetricScores(object):
+    """gen_all / real_all [world * b, d] of the MMD loss in one symmetric allocation; scatter() replaces gather_scores()."""
+
+    def __init__(self, b, d, device, group=None):
+        world = dist.get_world_size(group)
+        n = world * b * d
+        self.buf, self.handle, mc = _symmetric(2 * n, device, group)
+        self.b, self.rank = b, self.handle.rank
+        self.gen_all, self.real_all = self.buf[:n].view(world * b, d), self.buf[n:].view(world * b, d)
+        self.gen_mc, self.real_mc = mc, mc + 4 * n
+
+    def scatter(self, s_local):
+        from . import kernels as K
+        self.handle.barrier(channel=0)         # every rank has finished reading the previous step's scores
+        K.scatter_scores_nvls(s_local, self.b, self.rank, self.gen_mc, self.real_mc)
+        self.handle.barrier(channel=0)         # every rank's block has landed everywhere
+        return self.gen_all, self.real_all
+
+
 class SymmetricFlat(object):
     """g, w, m, v of one network in one symmetric allocation (4 x n_flat float32), the same size on every rank."""
 
     def __init__(self, n_flat, device, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
-        group = dist.group.WORLD if group is None else group
         self.n = int(n_flat)
-        self.buf = symm_mem.empty(4 * self.n, dtype=torch.float32, device=device)
-        self.buf.zero_()
-        try:                                   # older releases need the group registered first; newer ones deprecate the call
-            symm_mem.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass
-        self.handle = symm_mem.rendezvous(self.buf, group.group_name)
-        mc = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
-        if mc:
-            mc += int(getattr(self.handle, 'offset', 0) or 0)      # position of this tensor inside the mapped block
-        if mc == 0:
-            raise RuntimeError('MMDGAN_NVLS_ADAM=1 needs NVSwitch multicast (NVLS); this fabric / driver offers none')
+        self.buf, self.handle, mc = _symmetric(4 * self.n, device, group)
         self.rank, self.world = self.handle.rank, self.handle.world_size
         self.g, self.w, self.m, self.v = (self.buf[i * self.n:(i + 1) * self.n] for i in range(4))
         self.g_mc, self.w_mc, self.m_mc, self.v_mc = (mc + 4 * i * self.n for i in range(4))

@@ -161,6 +161,10 @@ def test_cabi_argument_validation_without_a_gpu():
     assert b'whole float4 groups' in lib.mmdgan_last_error()
     assert nv(fake16, fake16, fake16, ctypes.c_void_p(4100), fake16, fake16, fake16, 0, 16, 1e-3, 0.5, 0.999, 1e-8, step, None) == _lib.MMDGAN_ESHAPE
     assert nv(fake16, fake16, fake16, fake16, fake16, fake16, fake16, 16, 16, 1e-3, 0.5, 0.999, 1e-8, step, None) == _lib.MMDGAN_OK   # empty shard
+    sc = lib.mmdgan_scatter_scores_nvls
+    assert sc(None, 8, 16, 0, fake16, fake16, None) == _lib.MMDGAN_EINVAL
+    assert sc(fake16, 8, 6, 0, fake16, fake16, None) == _lib.MMDGAN_ESHAPE and sc(fake16, 0, 16, 0, fake16, fake16, None) == _lib.MMDGAN_ESHAPE
+    assert sc(fake16, 8, 16, 1, ctypes.c_void_p(4104), fake16, None) == _lib.MMDGAN_ESHAPE
     assert lib.mmdgan_mmd_workspace(256) >= 64 * 6 * 4
 
 
