@@ -292,6 +292,10 @@ int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float
  * [rank * b, (rank + 1) * b) of real_all / gen_all on EVERY rank; `*_mc` are multicast addresses of two [world * b, d] fp32
  * buffers of a symmetric allocation.  The caller brackets the call with a cross-rank barrier on the stream. */
 int mmdgan_scatter_scores_nvls(const float* s_local, int b, int d, int rank, float* gen_all_mc, float* real_all_mc, void* stream);
+/* out[i] = sum over ranks of in[i] for a few floats (the six kernel sums e_gg, e_gr, e_rr, ... of the row-block MMD form,
+ * math_func.py:1048-1069 evaluated per rank): `in_mc` is the multicast address of a per-rank slot of a symmetric allocation,
+ * n a multiple of 4.  The caller places a cross-rank barrier between writing the slot and this call. */
+int mmdgan_allreduce_small_nvls(float* out, const float* in_mc, int n, void* stream);
 int mmdgan_incr_step(int* step, void* stream);
 /* Data-parallel form of the same update (new functionality, SURVEY.md 8e: the reference is single-GPU): gradient all-reduce
  * FUSED with Adam through NVSwitch multicast.  The caller keeps g, w, m, v of one network in a symmetric allocation that is

@@ -133,6 +133,7 @@ SYMBOLS = {
     'mmdgan_adam': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _P]),
     'mmdgan_adam_allreduce_nvls': (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _P, _P]),
     'mmdgan_scatter_scores_nvls': (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    'mmdgan_allreduce_small_nvls': (_I, [_P, _P, _I, _P]),
     'mmdgan_incr_step': (_I, [_P, _P]),
     'mmdgan_nan_flag': (_I, [_P, _I, _P, _P]),
 }

@@ -48,6 +48,7 @@ int l_adam(float*, float*, float*, const float*, long long, float, float, float,
 int l_adam_allreduce_nvls(const float*, const float*, const float*, const float*, float*, float*, float*, long long, long long, float, float, float,
                           float, const int*, cudaStream_t);
 int l_scatter_scores_nvls(const float*, int, int, int, float*, float*, cudaStream_t);
+int l_allreduce_small_nvls(float*, const float*, int, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
 int l_dense_small_fwd(const uint16_t*, long long, int, int, int, int, const uint16_t*, long long, int, int, int, float, const float*, const float*,
@@ -448,6 +449,11 @@ int mmdgan_scatter_scores_nvls(const float* s_local, int b, int d, int rank, flo
     if (b <= 0 || d <= 0 || (d & 3) || rank < 0) return fail(MMDGAN_ESHAPE, "mmdgan_scatter_scores_nvls: b %d, d %d (multiple of 4), rank %d", b, d, rank);
     if (!al16(s_local) || !al16(gen_all_mc) || !al16(real_all_mc)) return fail(MMDGAN_ESHAPE, "mmdgan_scatter_scores_nvls: buffers must be 16-byte aligned");
     return wrap(mg::l_scatter_scores_nvls(s_local, b, d, rank, gen_all_mc, real_all_mc, S(stream)), "mmdgan_scatter_scores_nvls");
+}
+int mmdgan_allreduce_small_nvls(float* out, const float* in_mc, int n, void* stream) {
+    if (!out || !in_mc) return fail(MMDGAN_EINVAL, "mmdgan_allreduce_small_nvls: null pointer");
+    if (n < 0 || (n & 3) || !al16(out) || !al16(in_mc)) return fail(MMDGAN_ESHAPE, "mmdgan_allreduce_small_nvls: n %d must be a multiple of 4, buffers 16-byte aligned", n);
+    return wrap(mg::l_allreduce_small_nvls(out, in_mc, n, S(stream)), "mmdgan_allreduce_small_nvls");
 }
 int mmdgan_incr_step(int* step, void* stream) {
     if (!step) return fail(MMDGAN_EINVAL, "mmdgan_incr_step: null pointer");

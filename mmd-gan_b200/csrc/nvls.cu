@@ -84,6 +84,19 @@ int l_scatter_scores_nvls(const float* s_local, int b, int d, int rank, float* g
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
+// Sum all-reduce of a handful of floats (the six kernel sums of the MMD loss): out[i] = sum over ranks of in[i], every rank
+// reading the switch-reduced value.  n is a multiple of 4; `in_mc` is the multicast address of the per-rank source slots.
+__global__ void allreduce_small_nvls_kernel(float* __restrict__ out, const float* in_mc, int n) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 < n) *reinterpret_cast<float4*>(out + q * 4) = multimem_ld_reduce_add_f32x4(in_mc + q * 4);
+}
+
+int l_allreduce_small_nvls(float* out, const float* in_mc, int n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    allreduce_small_nvls_kernel<<<(n / 4 + 63) / 64, 64, 0, st>>>(out, in_mc, n);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 int l_adam_allreduce_nvls(const float* w, const float* m, const float* v, const float* g_mc, float* w_mc, float* m_mc, float* v_mc,
                           long long begin, long long end, float lr, float b1, float b2, float eps, const int* step, cudaStream_t st) {
     const long long n4 = (end - begin) >> 2;

@@ -688,8 +688,10 @@ class SNGanEngine(object):
 
     def _allreduce_grads(self):
         from . import parallel
-        # NVLS mode: the parameter gradients are reduced inside the optimiser kernel; only the six kernel sums go through NCCL
-        parallel.allreduce_sum([self.mmd.sums] if self.nvls else [self.D.g, self.G.g, self.mmd.sums], self.pg)
+        if self.nvls:    # the parameter gradients are reduced inside the optimiser kernel, the six kernel sums by a multicast load
+            self.sym_scores.allreduce_sums(self.mmd.sums)
+        else:
+            parallel.allreduce_sum([self.D.g, self.G.g, self.mmd.sums], self.pg)
         lg, ld = parallel.losses_from_sums(self.mmd.sums, [float(c) for c in self.mmd.desc.cD])
         self.mmd.losses[0] = lg
         self.mmd.losses[1] = ld

@@ -621,6 +621,10 @@ def scatter_scores_nvls(s_local, b, rank, gen_all_mc, real_all_mc):
                                            C.c_void_p(real_all_mc), stream()))
 
 
+def allreduce_small_nvls(out, in_mc, n):
+    check(lib().mmdgan_allreduce_small_nvls(_ptr(out), C.c_void_p(in_mc), int(n), stream()))
+
+
 def incr_step(step):
     check(lib().mmdgan_incr_step(_ptr(step), stream()))
 

@@ -83,10 +83,12 @@ class SymmetricScores(object):
     def __init__(self, b, d, device, group=None):
         world = dist.get_world_size(group)
         n = world * b * d
-        self.buf, self.handle, mc = _symmetric(2 * n, device, group)
+        self.buf, self.handle, mc = _symmetric(2 * n + 8, device, group)      # + one 8-float slot for the kernel sums
         self.b, self.rank = b, self.handle.rank
-        self.gen_all, self.real_all = self.buf[:n].view(world * b, d), self.buf[n:].view(world * b, d)
+        self.gen_all, self.real_all = self.buf[:n].view(world * b, d), self.buf[n:2 * n].view(world * b, d)
         self.gen_mc, self.real_mc = mc, mc + 4 * n
+        self.sums_slot, self.sums_mc = self.buf[2 * n:2 * n + 8], mc + 8 * n
+        self.sums_out = torch.zeros(8, dtype=torch.float32, device=device)
 
     def scatter(self, s_local):
         from . import kernels as K
@@ -94,6 +96,15 @@ class SymmetricScores(object):
         K.scatter_scores_nvls(s_local, self.b, self.rank, self.gen_mc, self.real_mc)
         self.handle.barrier(channel=0)         # every rank's block has landed everywhere
         return self.gen_all, self.real_all
+
+    def allreduce_sums(self, sums):
+        """sums [6] (this rank's partial kernel sums) -> the global sums, in place, reduced inside the switch.  The slot is
+        rewritten only after the next step's scatter() barriers, i.e. after every rank has read it."""
+        from . import kernels as K
+        self.sums_slot[:sums.numel()].copy_(sums)
+        self.handle.barrier(channel=0)
+        K.allreduce_small_nvls(self.sums_out, self.sums_mc, 8)
+        sums.copy_(self.sums_out[:sums.numel()])
 
 
 class SymmetricFlat(object):

@@ -165,6 +165,9 @@ def test_cabi_argument_validation_without_a_gpu():
     assert sc(None, 8, 16, 0, fake16, fake16, None) == _lib.MMDGAN_EINVAL
     assert sc(fake16, 8, 6, 0, fake16, fake16, None) == _lib.MMDGAN_ESHAPE and sc(fake16, 0, 16, 0, fake16, fake16, None) == _lib.MMDGAN_ESHAPE
     assert sc(fake16, 8, 16, 1, ctypes.c_void_p(4104), fake16, None) == _lib.MMDGAN_ESHAPE
+    ar = lib.mmdgan_allreduce_small_nvls
+    assert ar(None, fake16, 8, None) == _lib.MMDGAN_EINVAL and ar(fake16, fake16, 6, None) == _lib.MMDGAN_ESHAPE
+    assert ar(fake16, fake16, 0, None) == _lib.MMDGAN_OK
     assert lib.mmdgan_mmd_workspace(256) >= 64 * 6 * 4
 
 
