@@ -302,6 +302,7 @@ def run_ours(args):
             'config': {'workload': '{} {}x{} SNGAN + {} MMD, batch {} per GPU, spectral norm on'.format(
                 name, arch['input'][0][1], arch['input'][0][2], loss_type, batch),
                 'global_batch': batch * world, 'parallelism': 'dp{}'.format(world),
+                'collectives': None if world == 1 else ('nvswitch multicast kernels (MMDGAN_NVLS_ADAM=1)' if eng.nvls else 'nccl all-gather + all-reduce'),
                 'l2': 'per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush',
                 'tensor_passes': args.passes, 'cuda_graph': True, 'loss_last_step': last},
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
