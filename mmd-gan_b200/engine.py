@@ -327,6 +327,9 @@ class SNGanEngine(object):
         gen = torch.Generator().manual_seed(seed)
         # opt-in: gradient all-reduce fused with Adam through NVSwitch multicast (csrc/nvls.cu) instead of NCCL + adam_kernel
         self.nvls = world_size > 1 and os.environ.get('MMDGAN_NVLS_ADAM', '0') == '1'
+        # opt-in on top of it: batch-norm statistics over the GLOBAL batch (sums exchanged through the same multicast loads), so
+        # that the data-parallel step equals the single-GPU step at the global batch size including the generator's batch norm
+        self.sync_bn = self.nvls and os.environ.get('MMDGAN_SYNC_BN', '0') == '1'
         flat_alloc = None
         if self.nvls:
             from . import parallel
@@ -412,7 +415,11 @@ class SNGanEngine(object):
             self.real_all = torch.zeros((self.world_size * B, d), dtype=torch.float32, device=dev)
             if self.nvls:        # the gathered score matrices live in a symmetric allocation: peers multicast their blocks into it
                 from . import parallel
-                self.sym_scores = parallel.SymmetricScores(B, d, dev, self.pg)
+                bn_layers = [L for L in self.G.layers if L.has_bn] if self.sync_bn else []
+                for k, L in enumerate(bn_layers):
+                    L.bn_slot = 2 * k            # slot 2k: sum x | sum x^2 (forward); slot 2k + 1: sum dy | sum dy * xhat (backward)
+                width = 2 * max([L.Cs_out for L in bn_layers] + [2])
+                self.sym_scores = parallel.SymmetricScores(B, d, dev, self.pg, stat_slots=2 * len(bn_layers), stat_width=width)
                 self.gen_all, self.real_all = self.sym_scores.gen_all, self.sym_scores.real_all
 
     # -------------------------------------------------------------------------------------------- forward passes
@@ -430,7 +437,16 @@ class SNGanEngine(object):
             sig = L.sigma if (L.has_sn and sigma_on) else None
             if L.has_bn:
                 lop.forward(src, nimg, L.zraw, sigma=sig, alpha_k=L.act_k, out_mode=2, colsum=L.ps, colsumsq=L.pq)
-                if is_training:
+                if is_training and self.sync_bn:
+                    c = L.Cs_out
+                    slot = self.sym_scores.stat_slot(L.bn_slot)
+                    K.reduce_tiles(L.ps, L.T_fwd, c, slot[:c])
+                    K.reduce_tiles(L.pq, L.T_fwd, c, slot[c:2 * c])
+                    tot = self.sym_scores.allreduce_stats(L.bn_slot, 2 * c)
+                    K.bn_finalize(tot[:c], tot[c:2 * c], 1, c, nimg * L.rows_out * self.world_size, L.mean, L.invstd, L.mm, L.mv)
+                    K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
+                               L.act_code, L.a, sat_flag=self.sat_flag)
+                elif is_training:
                     K.bn_finalize(L.ps, L.pq, L.T_fwd, L.Cs_out, nimg * L.rows_out, L.mean, L.invstd, L.mm, L.mv)
                     K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
                                L.act_code, L.a, sat_flag=self.sat_flag)
@@ -614,7 +630,18 @@ class SNGanEngine(object):
                                 P.bp1, P.bp2)
                 K.reduce_tiles(P.bp1, P.nblk, P.Cs_out, P.dbeta_int)
                 K.reduce_tiles(P.bp2, P.nblk, P.Cs_out, P.dgamma_int)
-                K.bn_bwd_apply(P.da_raw, P.zraw, P.mean, P.invstd, P.gamma_int, P.beta_int, P.dbeta_int, P.dgamma_int, P.Cs_out,
+                db, dg = P.dbeta_int, P.dgamma_int
+                if self.sync_bn:
+                    # dx needs the GLOBAL means of dy and dy * xhat: global sums / (world * rows) = (global sums / world) / rows;
+                    # the parameter gradients keep the local sums (the gradient reduction adds the ranks up)
+                    c = P.Cs_out
+                    slot = self.sym_scores.stat_slot(P.bn_slot + 1)
+                    slot[:c].copy_(P.dbeta_int)
+                    slot[c:2 * c].copy_(P.dgamma_int)
+                    tot = self.sym_scores.allreduce_stats(P.bn_slot + 1, 2 * c)
+                    tot.mul_(1.0 / self.world_size)
+                    db, dg = tot[:c], tot[c:2 * c]
+                K.bn_bwd_apply(P.da_raw, P.zraw, P.mean, P.invstd, P.gamma_int, P.beta_int, db, dg, P.Cs_out,
                                rows, P.act_code, P.dz)
 
                 def bn_params(P=P):

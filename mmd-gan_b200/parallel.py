@@ -80,10 +80,15 @@ def _symmetric(numel, device, group):
 class SymmetricScores(object):
     """gen_all / real_all [world * b, d] of the MMD loss in one symmetric allocation; scatter() replaces gather_scores()."""
 
-    def __init__(self, b, d, device, group=None):
+    def __init__(self, b, d, device, group=None, stat_slots=0, stat_width=0):
         world = dist.get_world_size(group)
         n = world * b * d
-        self.buf, self.handle, mc = _symmetric(2 * n + 8, device, group)      # + one 8-float slot for the kernel sums
+        assert stat_width % 4 == 0
+        # + one 8-float slot for the kernel sums + `stat_slots` slots of `stat_width` floats (batch-norm statistics)
+        self.buf, self.handle, mc = _symmetric(2 * n + 8 + stat_slots * stat_width, device, group)
+        self.world, self.stat_width = world, stat_width
+        self._stat0, self._stat0_mc = 2 * n + 8, mc + 4 * (2 * n + 8)
+        self.stat_out = torch.zeros(max(stat_slots * stat_width, 4), dtype=torch.float32, device=device)
         self.b, self.rank = b, self.handle.rank
         self.gen_all, self.real_all = self.buf[:n].view(world * b, d), self.buf[n:2 * n].view(world * b, d)
         self.gen_mc, self.real_mc = mc, mc + 4 * n
@@ -105,6 +110,19 @@ class SymmetricScores(object):
         self.handle.barrier(channel=0)
         K.allreduce_small_nvls(self.sums_out, self.sums_mc, 8)
         sums.copy_(self.sums_out[:sums.numel()])
+
+    def stat_slot(self, i):
+        """This rank's slot i (stat_width floats): write the local partial sums here, then allreduce_stats(i, width)."""
+        return self.buf[self._stat0 + i * self.stat_width:self._stat0 + (i + 1) * self.stat_width]
+
+    def allreduce_stats(self, i, width):
+        """The first `width` floats of slot i summed over all ranks (switch-reduced), as a local tensor.  A slot is rewritten
+        one step later, after several barriers: every rank has read it by then."""
+        from . import kernels as K
+        out = self.stat_out[i * self.stat_width:i * self.stat_width + width]
+        self.handle.barrier(channel=0)
+        K.allreduce_small_nvls(out, self._stat0_mc + 4 * i * self.stat_width, width)
+        return out
 
 
 class SymmetricFlat(object):

@@ -9,6 +9,8 @@ echo "== NCCL path" | tee gpurun_out/nvls_check.txt
 run 29711 scripts/multi_gpu_check.py 2>&1 | tail -5 | tee -a gpurun_out/nvls_check.txt
 echo "== NVLS path" | tee -a gpurun_out/nvls_check.txt
 MMDGAN_NVLS_ADAM=1 run 29712 scripts/multi_gpu_check.py 2>&1 | tail -25 | tee -a gpurun_out/nvls_check.txt
+echo "== NVLS path + global-batch batch norm" | tee -a gpurun_out/nvls_check.txt
+MMDGAN_NVLS_ADAM=1 MMDGAN_SYNC_BN=1 run 29715 scripts/multi_gpu_check.py 2>&1 | tail -25 | tee -a gpurun_out/nvls_check.txt
 echo "== bench, NCCL path" | tee -a gpurun_out/nvls_check.txt
 run 29713 bench.py --gpus $N --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench_nccl_$N.json
 echo "== bench, NVLS path" | tee -a gpurun_out/nvls_check.txt

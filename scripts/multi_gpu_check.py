@@ -26,7 +26,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
-    arch, b = arch_no_bn(), 8
+    # MMDGAN_SYNC_BN=1 (with MMDGAN_NVLS_ADAM=1): batch-norm statistics over the global batch -> the generator keeps its batch norm
+    arch, b = (oa.tiny(act_k=2.6) if os.environ.get('MMDGAN_SYNC_BN') == '1' else arch_no_bn()), 8
     g = torch.Generator().manual_seed(7)
     steps = 3
     data = torch.rand(steps, world * b, 3, 8, 8, generator=g) * 2 - 1
@@ -42,6 +43,7 @@ def main():
                 return
             raise
         assert eng.nvls == (os.environ.get('MMDGAN_NVLS_ADAM') == '1')
+        assert eng.sync_bn == (eng.nvls and os.environ.get('MMDGAN_SYNC_BN') == '1')
         ref = SNGanEngine(arch, world * b, loss_type='rmb', device=dev, use_graph=False, seed=5) if rank == 0 else None
         for it in range(steps):
             sl = slice(rank * b, (rank + 1) * b)
