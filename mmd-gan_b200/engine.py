@@ -682,6 +682,8 @@ class SNGanEngine(object):
                 continue
             if net is self.D and self._dis_updated:        # already enqueued on the update stream during the backward pass
                 continue
+            if self.nvls:
+                st = main        # cross-rank barriers: one stream, one order on every rank (no inversion through shared hardware queues)
             with torch.cuda.stream(st):
                 K.incr_step(net.step)
                 if self.nvls:
