@@ -2,7 +2,7 @@
 """bench.py -- images/sec of the fused SNGan training step (BASELINE.json metric) on N B200s of one node.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cifar|stl|celeba|lsun]
-                  [--batch B] [--passes 3|1] [--no-cpu-baseline] [--no-roofline]
+                  [--batch B] [--scaling weak|strong] [--passes 3|1] [--no-cpu-baseline] [--no-roofline]
 
 Own arm: workload = BASELINE.json configs[1] (CIFAR-10 32x32 SNGAN + repulsive MMD, batch 256 per GPU, spectral norm
 on), synthetic data, random-init weights.  A "step" is one fused training step ([losses, dis_op, gen_op, UPDATE_OPS]).
@@ -172,6 +172,10 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     name, batch, loss_type, lr = WORKLOADS[args.workload]
     batch = args.batch or batch
+    if args.scaling == 'strong':       # the workload's batch is the GLOBAL batch, split over the ranks (default: per-GPU batch, weak scaling)
+        if batch % world:
+            raise SystemExit('bench.py: --scaling strong needs the batch ({}) to be a multiple of the number of GPUs ({})'.format(batch, world))
+        batch //= world
     arch = oa.ARCHITECTURES[name]()
     eng = SNGanEngine(arch, batch, loss_type=loss_type, lr_list=lr, npass=args.passes, device=dev, world_size=world, rank=rank,
                       use_graph=True)
@@ -297,7 +301,7 @@ def run_ours(args):
     if rank == 0:
         line = {
             'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'fp16x3 fwd / bf16x3 grad (two 16-bit planes per operand, three products, fp32 accumulate)' if args.passes == 3 else 'bf16', 'data': 'synthetic',
             'config': {'workload': '{} {}x{} SNGAN + {} MMD, batch {} per GPU, spectral norm on'.format(
                 name, arch['input'][0][1], arch['input'][0][2], loss_type, batch),
@@ -332,6 +336,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cifar', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0)
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: the workload batch per GPU (default, what the driver runs); strong: the workload batch is global and split over the GPUs')
     ap.add_argument('--passes', type=int, default=3, choices=[1, 3])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
