@@ -821,7 +821,8 @@ class SNGanEngine(object):
     def generate(self, code_x, is_training=True):
         """Generated images NCHW in [-1, 1] for `code_x` [n, code_size] (mdl.Gen(code_batch, is_training), my_sngan.py:270 and
         :533).  is_training=True is the step's own forward (batch-statistics batch norm; n must be the engine's batch);
-        is_training=False is the eval_sampling graph: moving-average batch norm, per-sample, any n <= batch_size."""
+        is_training=False is the eval_sampling graph: moving-average batch norm, per-sample, any n <= batch_size.
+        (With MMDGAN_SYNC_BN=1 the is_training=True form is a collective: every rank has to call it.)"""
         B, HW = self.B, self.height * self.width
         code_x = torch.as_tensor(code_x, dtype=torch.float32)
         n = code_x.shape[0]
