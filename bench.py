@@ -28,11 +28,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the top forward kernel, from the committed
-# `ncu --set full` capture (profiles/r1v4_summary.md, section conv_fwd); a recorded profile value, not measured by bench.py
-NCU_TRAFFIC = {('cifar', 256): 36.068096e6 + 0.961536e6}
-NCU_TRAFFIC_NOTE = ('bytes of one conv_gemm_pair_kernel<256,3,1> launch (grid 256, 109 us under ncu; L2 hit rate 82%, DRAM at 4% of peak: '
-                    'the kernel is tensor/L2 bound, not HBM bound) from profiles/r1v4_summary.md; `achieved` aggregates all GEMM launches')
+
+
+def read_traffic(name, batch):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the top kernel, from the newest committed
+    `ncu --set full` capture: profiles/traffic.json, written by scripts/ncu_traffic.py together with the commit it was taken
+    at.  bench.py cannot measure it (no profiler inside a timed run); absent or for another workload -> None."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None, None
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get('workload') != name or int(t.get('batch', -1)) != int(batch):
+            return None, None
+        return float(t['dram_bytes']), t
+    except (ValueError, KeyError, OSError):
+        return None, None
+
+
+def workload_string(name, arch, loss_type, batch):
+    """The same string on both arms (the driver compares config.workload of the two lines)."""
+    return '{} {}x{} SNGAN + {} MMD, batch {} per GPU, spectral norm on'.format(name, arch['input'][0][1], arch['input'][0][2], loss_type, batch)
+
 WORKLOADS = {'cifar': ('cifar', 256, 'rep', (5e-4, 2e-4)), 'stl': ('stl', 128, 'rmb', (2e-4, 2e-4)),
              'celeba': ('celeba', 128, 'rep', (1e-4, 2e-4)), 'lsun': ('lsun', 128, 'rep', (2e-4, 1e-4))}
 # algorithmic cost per (real, fake) pair = 3G + 7D forward-equivalents (SURVEY.md section 8d), in GFLOP
@@ -139,13 +157,15 @@ def run_reference(args):
     name, batch, loss_type, lr = WORKLOADS[args.workload]
     batch = args.batch or batch
     ips, ms, sample, cores = cpu_reference_throughput(name, batch, loss_type, lr, args.steps, args.warmup)
+    from oracle import architectures as oa
     line = {
         'impl': 'reference', 'metric': 'images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '{} SNGAN + {} MMD, batch {}, spectral norm on'.format(name, loss_type, batch),
+        'config': {'workload': workload_string(name, oa.ARCHITECTURES[name](), loss_type, batch),
                    'note': 'TensorFlow 1.8 is not installable here; the reference CPU path is the PyTorch-CPU restatement of the '
-                           'TF1 step (oracle/net.py) on the host cores'},
+                           'TF1 step (oracle/net.py) on the host cores.  The reference is single-device: for --gpus N > 1 this arm '
+                           'still runs ONE host at the workload batch (it does not scale with N), while the repo arm is weak-scaled'},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -220,6 +240,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = float(t[0]), float(t[1])
     images = batch * world * args.steps
+    launches_weak = eng.kernel_launches_per_step
+    nvls_mode = eng.nvls
     value = images / (ms_dev / 1e3)
     e2e_value = images / (ms_e2e / 1e3)
     h2d = batch * (arch['input'][0][0] * arch['input'][0][1] * arch['input'][0][2] + arch['code'][0][0]) * 4
@@ -257,10 +279,11 @@ def run_ours(args):
             K.LinearOp._gemm, K.LinearOp.wgrad, K.LinearOp._direct = orig_gemm, orig_wgrad, orig_direct
             eng.sn_fork, eng.grad_fork = forks
         gemm_ms = sum(s.elapsed_time(e) for s, e in evs)
+        traffic, traffic_src = read_traffic(name, batch)
         flop_step = GFLOP_PER_PAIR[name] * 1e9 * batch
         achieved = flop_step / (gemm_ms / 1e3) / 1e12
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['sustained'],
-                'traffic': NCU_TRAFFIC.get((name, batch)), 'traffic_note': NCU_TRAFFIC_NOTE if (name, batch) in NCU_TRAFFIC else None, 'peak_source': peaks['source'] + ' bf16 sustained (MEASURED_PEAKS.json)',
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peaks['source'] + ' bf16 sustained (MEASURED_PEAKS.json)',
                 'kernel': 'conv_gemm(_pair)_kernel + wgrad_gemm_kernel (tcgen05) + conv3x3 direct kernels of the image layers: the {} batch-sized '
                           'launches that carry the 3G+7D FLOPs of one step'.format(len(evs)),
                 'gemm_ms_per_step': gemm_ms, 'eager_single_stream_step_ms': t0.elapsed_time(t1), 'share_of_eager_step': gemm_ms / t0.elapsed_time(t1),
@@ -298,27 +321,70 @@ def run_ours(args):
         except Exception as exc:                         # the extra measurement must never cost the bench line
             mmd_roof = {'error': '{}: {}'.format(type(exc).__name__, exc)}
 
+    # ---- N > 1: (1) a driver-run witness that the data-parallel step equals the single-process step on the concatenated batch,
+    # (2) the strong-scaling point (the workload batch as the GLOBAL batch, split over the ranks) next to the weak one
+    dp_check = strong = None
+    if world > 1 and not args.no_dp_check:
+        from mmdgan_b200 import parallel
+        try:
+            dp_check = parallel.dp_equals_single(world, rank, dev)
+        except Exception as exc:                          # the check must never cost the bench line; a failure is reported as such
+            dp_check = {'ok': False, 'error': '{}: {}'.format(type(exc).__name__, exc)}
+    if world > 1 and args.scaling == 'weak' and not args.no_strong and WORKLOADS[args.workload][1] % world == 0 and not args.batch:
+        try:
+            bs = WORKLOADS[args.workload][1] // world
+            del eng
+            torch.cuda.empty_cache()
+            eng_s = SNGanEngine(arch, bs, loss_type=loss_type, lr_list=lr, npass=args.passes, device=dev, world_size=world, rank=rank,
+                                use_graph=True)
+            pool_s = [(d[:bs].contiguous(), c[:bs].contiguous()) for d, c in pool]
+            for i in range(max(args.warmup, 3)):
+                eng_s.stage(*pool_s[i % len(pool_s)])
+                eng_s.step_device()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(args.steps):
+                eng_s.stage(*pool_s[i % len(pool_s)])
+                eng_s.step_device()
+            s1.record()
+            barrier()
+            t = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_s = float(t[0])
+            strong = {'scaling': 'strong', 'global_batch': bs * world, 'per_gpu_batch': bs, 'value': bs * world * args.steps / (ms_s / 1e3),
+                      'unit': 'images/s', 'ms_per_step': ms_s / args.steps, 'steps': args.steps,
+                      'note': 'BASELINE metric (1) read literally: global batch {} split over {} GPUs; device-resident, max over ranks'.format(bs * world, world)}
+            eng = eng_s
+        except Exception as exc:
+            strong = {'error': '{}: {}'.format(type(exc).__name__, exc)}
     if rank == 0:
         line = {
             'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'fp16x3 fwd / bf16x3 grad (two 16-bit planes per operand, three products, fp32 accumulate)' if args.passes == 3 else 'bf16', 'data': 'synthetic',
-            'config': {'workload': '{} {}x{} SNGAN + {} MMD, batch {} per GPU, spectral norm on'.format(
-                name, arch['input'][0][1], arch['input'][0][2], loss_type, batch),
+            'config': {'workload': workload_string(name, arch, loss_type, batch),
                 'global_batch': batch * world, 'parallelism': 'dp{}'.format(world),
-                'collectives': None if world == 1 else ('nvswitch multicast kernels (MMDGAN_NVLS_ADAM=1)' if eng.nvls else 'nccl all-gather + all-reduce'),
+                'collectives': None if world == 1 else ('nvswitch multicast kernels (MMDGAN_NVLS_ADAM=1)' if nvls_mode else 'nccl all-gather + all-reduce'),
                 'l2': 'per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush',
                 'tensor_passes': args.passes, 'cuda_graph': True, 'loss_last_step': last},
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(eng.kernel_launches_per_step * args.steps),
-            'gpu_launches_per_step': int(eng.kernel_launches_per_step),
+            'gpu_launches': int(launches_weak * args.steps),
+            'gpu_launches_per_step': int(launches_weak),
             'clocks': clocks,
         }
         if roof:
             line['roofline'] = roof
+            if mmd_roof:
+                roof['mmd'] = mmd_roof       # BASELINE's second metric, kept inside `roofline` so that parsers of the contract keys see it
         if mmd_roof:
             line['mmd_kernel'] = mmd_roof
+        if dp_check is not None:
+            line['dp_equals_single'] = bool(dp_check.get('ok'))
+            line['config']['dp_check'] = dp_check
+        if strong is not None:
+            line['config']['strong'] = strong
         if world == 1 and not args.no_cpu_baseline:
             ips, ms, sample, cores = cpu_reference_throughput(name, batch, loss_type, lr, steps=2, warmup=1, budget_s=40.0)
             line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample,
@@ -341,6 +407,8 @@ def main():
     ap.add_argument('--passes', type=int, default=3, choices=[1, 3])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--no-dp-check', action='store_true', help='N > 1: skip the data-parallel == single-process equality check')
+    ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the extra strong-scaling measurement (config.strong)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

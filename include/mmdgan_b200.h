@@ -234,8 +234,10 @@ int mmdgan_colsum_planes(const mmdgan_bf16* x, long long plane, int npl, int row
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Batch normalisation: tf.layers.batch_normalization(axis=1, training, fused=True) (layer_func.py:953-966) */
+/* bessel != 0: the moving variance is fed the Bessel-corrected batch variance (TF's fused kernel: rank-4 inputs); 0: the biased
+ * one (rank-2 inputs, for which TF 1.8 silently falls back from fused=True to nn.moments) */
 int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
-                       float* invstd, float* moving_mean, float* moving_var, void* stream);
+                       float* invstd, float* moving_mean, float* moving_var, int bessel, void* stream);
 /* Inference-mode statistics, tf.layers.batch_normalization(training=False) (reference layer_func.py:953-966 with
  * is_training False, the eval_sampling graph of my_sngan.py:523-533): mean = moving_mean, invstd = 1/sqrt(moving_var + eps);
  * mmdgan_bn_apply then normalises with them. */

@@ -238,14 +238,18 @@ class GANLoss(object):
         self.dis_scale = None
         self.debug_register = None
         self.sigma = [1.0, np.sqrt(2.0), 2.0, np.sqrt(8.0), 4.0]       # math_func.py:2108
+        self.alpha = [0.2, 0.5, 1, 2, 5.0]                              # math_func.py:2109
+        self.beta = 2.0                                                 # math_func.py:2110
         self.repulsive_weights = [0.0, -1.0]                            # math_func.py:2115
         self._kernels = {}
 
     def _kernel(self, loss_type, b, device):
         from .. import kernels as K
-        key = (loss_type, tuple(self.repulsive_weights), b, str(device))
+        key = (loss_type, tuple(self.repulsive_weights), b, str(device), tuple(float(s) for s in self.sigma),
+               tuple(float(a) for a in self.alpha), float(self.beta))
         if key not in self._kernels:
-            self._kernels[key] = K.MmdKernel(loss_type, self.repulsive_weights, b=b, device=device)
+            self._kernels[key] = K.MmdKernel(loss_type, self.repulsive_weights, b=b, device=device, sigma=self.sigma,
+                                             alpha=self.alpha, beta=self.beta)
         return self._kernels[key]
 
     def __call__(self, score_gen, score_data, loss_type='logistic', **kwargs):
@@ -260,6 +264,10 @@ class GANLoss(object):
             self.dis_scale = kwargs['dis_scale']
         if 'sigma' in kwargs:
             self.sigma = kwargs['sigma']
+        if 'alpha' in kwargs:
+            self.alpha = kwargs['alpha']
+        if 'beta' in kwargs:
+            self.beta = kwargs['beta']
         if 'rep_weights' in kwargs:
             self.repulsive_weights = list(kwargs['rep_weights'])
         if loss_type in {'fixed_g', 'mmd_g', 'fixed_t', 'mmd_t', 'rep', 'rep_gp', 'rmb', 'rmb_gp', 'mgb'}:
@@ -276,7 +284,8 @@ class GANLoss(object):
         self.loss_gen, self.loss_dis = _FusedMmdLoss.apply(score_gen, score_data, kern)
         if self.dis_penalty is not None:
             self.loss_dis = self.loss_dis + self.dis_penalty
-        if self.dis_scale is not None:
+        if self.dis_scale is not None and self.FUSED[loss_type] in ('rep', 'rmb'):
+            # math_func.py:2524-2525 (rep) and :2546-2547 (rmb); _mmd_g_ / _mmd_g_bound_ / _mmd_t_ never scale
             self.loss_dis = (self.loss_dis - 1.0) * self.dis_scale if self.FUSED[loss_type] == 'rep' else self.loss_dis * self.dis_scale
         return self.loss_gen, self.loss_dis
 

@@ -377,7 +377,10 @@ def read_bundle(prefix, names=None, check_crc=True):
 def write_checkpoint_state(folder, latest, all_paths=None):
     """<folder>/checkpoint as tf.train.update_checkpoint_state writes it (paths relative to the folder)."""
     all_paths = list(all_paths) if all_paths is not None else [latest]
-    rel = lambda p: os.path.relpath(p, folder) if os.path.isabs(p) else p      # noqa: E731
+    # always relative to the state file's folder (TF's generate_checkpoint_state_proto rewrites relative paths against
+    # save_dir): a cwd-relative prefix such as 'MMD-GAN/Results/x_ckpt/x.ckpt-3' must not be stored as is, because
+    # read_checkpoint_state joins every relative entry onto the folder
+    rel = lambda p: os.path.relpath(os.path.abspath(p), os.path.abspath(folder))      # noqa: E731
     lines = ['model_checkpoint_path: "{}"'.format(rel(latest))]
     lines += ['all_model_checkpoint_paths: "{}"'.format(rel(p)) for p in all_paths]
     with open(os.path.join(folder, 'checkpoint'), 'w') as f:

@@ -122,7 +122,7 @@ SYMBOLS = {
     'mmdgan_reduce_tiles': (_I, [_P, _I, _I, _F, _P, _P]),
     'mmdgan_colsum_small': (_I, [_P, _I, _I, _P, _P]),
     'mmdgan_colsum_planes': (_I, [_P, _LL, _I, _I, _I, _P, _P]),
-    'mmdgan_bn_finalize': (_I, [_P, _P, _I, _I, _LL, _F, _F, _P, _P, _P, _P, _P]),
+    'mmdgan_bn_finalize': (_I, [_P, _P, _I, _I, _LL, _F, _F, _P, _P, _P, _P, _I, _P]),
     'mmdgan_bn_inference_stats': (_I, [_P, _P, _I, _F, _P, _P, _P]),
     'mmdgan_bn_apply': (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _P, _LL, _I, _I, _P, _P]),
     'mmdgan_bn_bwd_reduce': (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _P, _P, _P]),

@@ -36,7 +36,7 @@ int l_wgrad_reduce(const WredParams&, cudaStream_t);
 int l_sn_grad_combine(float*, const float*, const double*, int, const float*, float, long long, cudaStream_t);
 int l_scale_by_sigma(float*, const float*, float, long long, cudaStream_t);
 int l_sn_normalize(const float*, long long, float, float*, uint16_t*, long long, int, int, cudaStream_t);
-int l_bn_finalize(const float*, const float*, int, int, long long, float, float, float*, float*, float*, float*, cudaStream_t);
+int l_bn_finalize(const float*, const float*, int, int, long long, float, float, float*, float*, float*, float*, int, cudaStream_t);
 int l_bn_inference_stats(const float*, const float*, int, float, float*, float*, cudaStream_t);
 int l_bn_apply(const float*, const float*, const float*, const float*, const float*, int, long long, int, uint16_t*, long long, int, int,
                int*, cudaStream_t);
@@ -295,10 +295,10 @@ int mmdgan_colsum_planes(const mmdgan_bf16* x, long long plane, int npl, int row
     return wrap(mg::l_colsum_planes(x, plane, npl, rows, C, out, S(stream)), "mmdgan_colsum_planes");
 }
 int mmdgan_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
-                       float* invstd, float* moving_mean, float* moving_var, void* stream) {
+                       float* invstd, float* moving_mean, float* moving_var, int bessel, void* stream) {
     if (!psum || !psq || !mean || !invstd) return fail(MMDGAN_EINVAL, "mmdgan_bn_finalize: null pointer");
     if (T <= 0 || C <= 0 || rows <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_bn_finalize: bad shape");
-    return wrap(mg::l_bn_finalize(psum, psq, T, C, rows, eps, momentum, mean, invstd, moving_mean, moving_var, S(stream)), "mmdgan_bn_finalize");
+    return wrap(mg::l_bn_finalize(psum, psq, T, C, rows, eps, momentum, mean, invstd, moving_mean, moving_var, bessel, S(stream)), "mmdgan_bn_finalize");
 }
 int mmdgan_bn_inference_stats(const float* moving_mean, const float* moving_var, int C, float eps, float* mean, float* invstd,
                               void* stream) {

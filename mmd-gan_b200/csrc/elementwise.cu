@@ -375,10 +375,11 @@ __global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, fl
 
 // ------------------------------------------------------------------------------------------------ batch norm
 // statistics from per-tile partial sums; moving stats as tf.layers.batch_normalization(fused=True): biased variance
-// normalises, the Bessel-corrected one feeds the moving average (momentum 0.99)
+// normalises; the moving average (momentum 0.99) is fed the Bessel-corrected variance for rank-4 inputs (fused kernel) and the
+// biased one for rank-2 inputs (TF 1.8 falls back to nn.moments there): `bessel`
 __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int T, int C, long long rows, float eps,
                                    float momentum, float* __restrict__ mean, float* __restrict__ invstd,
-                                   float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var, int bessel) {
     __shared__ double rs[32][33], rq[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0, q = 0.0;
@@ -399,7 +400,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
     mean[c] = static_cast<float>(mu);
     invstd[c] = static_cast<float>(1.0 / sqrt(var + eps));
     if (moving_mean) {
-        const double var_u = rows > 1 ? var * (static_cast<double>(rows) / (rows - 1)) : var;
+        const double var_u = (bessel && rows > 1) ? var * (static_cast<double>(rows) / (rows - 1)) : var;
         moving_mean[c] = moving_mean[c] * momentum + static_cast<float>(mu) * (1.0f - momentum);
         moving_var[c] = moving_var[c] * momentum + static_cast<float>(var_u) * (1.0f - momentum);
     }
@@ -643,8 +644,8 @@ int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, bf1
     return MG_CHECK_LAUNCH();
 }
 int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
-                  float* invstd, float* mm, float* mv, cudaStream_t st) {
-    bn_finalize_kernel<<<nblocks(C, 32), dim3(32, 32), 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv);
+                  float* invstd, float* mm, float* mv, int bessel, cudaStream_t st) {
+    bn_finalize_kernel<<<nblocks(C, 32), dim3(32, 32), 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv, bessel);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_inference_stats(const float* mm, const float* mv, int C, float eps, float* mean, float* invstd, cudaStream_t st) {

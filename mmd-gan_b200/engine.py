@@ -334,6 +334,15 @@ class SNGanEngine(object):
         if self.nvls:
             from . import parallel
             flat_alloc = lambda n: parallel.SymmetricFlat(n, self.device, process_group)      # noqa: E731
+        # The fused backward pass implements what the shipped experiments use: spectral normalisation in the discriminator only,
+        # batch norm in the generator only.  The layer DSL accepts the other combinations; training them
+        # here would silently use wrong gradients, so they are refused up front.
+        for ly in self.Gen.ordered_layers():
+            if ly.design.get('w_nm') == 's':
+                raise NotImplementedError('{}: spectral normalisation in the generator is not on the fused path'.format(ly.layer_scope))
+        for ly in self.Dis.ordered_layers():
+            if 'BN' in ly.ops:
+                raise NotImplementedError('{}: batch normalisation in the discriminator is not on the fused path'.format(ly.layer_scope))
         self.G = NetRuntime(self.Gen, B, B, self.npass, self.device, gen, flat_alloc)
         self.D = NetRuntime(self.Dis, 2 * B, 3 * B, self.npass, self.device, gen, flat_alloc)
         self._alloc_buffers()
@@ -430,8 +439,12 @@ class SNGanEngine(object):
         assert planes.shape[1] * planes.shape[2] == rows * c
         return planes.as_strided((npl, rows, c), (planes.stride(0), c, 1), planes.storage_offset())
 
-    def _net_forward(self, net, src, nimg, is_training=True, sigma_on=True):
+    def _net_forward(self, net, src, nimg, is_training=True, sigma_on=True, update_moving=True):
+        """update_moving=False: training-mode batch norm WITHOUT its UPDATE_OPS (the moving averages are assigned only by the
+        training sess.run, graph_func.py:848-854; a sampling call between steps must not advance them)."""
         for L in net.layers:
+            mm, mv = (L.mm, L.mv) if (L.has_bn and update_moving) else (None, None)
+            bessel = L.op != 'd'      # rank-2 batch norm (dense layer): TF 1.8 falls back from the fused kernel to nn.moments
             lop = L.lop
             src = self._as_rows(src, nimg * L.rows_in, L.Cs_in)
             sig = L.sigma if (L.has_sn and sigma_on) else None
@@ -443,11 +456,11 @@ class SNGanEngine(object):
                     K.reduce_tiles(L.ps, L.T_fwd, c, slot[:c])
                     K.reduce_tiles(L.pq, L.T_fwd, c, slot[c:2 * c])
                     tot = self.sym_scores.allreduce_stats(L.bn_slot, 2 * c)
-                    K.bn_finalize(tot[:c], tot[c:2 * c], 1, c, nimg * L.rows_out * self.world_size, L.mean, L.invstd, L.mm, L.mv)
+                    K.bn_finalize(tot[:c], tot[c:2 * c], 1, c, nimg * L.rows_out * self.world_size, L.mean, L.invstd, mm, mv, bessel=bessel)
                     K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
                                L.act_code, L.a, sat_flag=self.sat_flag)
                 elif is_training:
-                    K.bn_finalize(L.ps, L.pq, L.T_fwd, L.Cs_out, nimg * L.rows_out, L.mean, L.invstd, L.mm, L.mv)
+                    K.bn_finalize(L.ps, L.pq, L.T_fwd, L.Cs_out, nimg * L.rows_out, L.mean, L.invstd, mm, mv, bessel=bessel)
                     K.bn_apply(L.zraw, L.mean, L.invstd, L.gamma_int, L.beta_int, L.Cs_out, nimg * L.rows_out * L.Cs_out,
                                L.act_code, L.a, sat_flag=self.sat_flag)
                 else:                            # tf.layers.batch_normalization(training=False): the moving averages normalise
@@ -837,7 +850,7 @@ class SNGanEngine(object):
         for L in self.G.layers:                 # sigma of the current weights and in_rand (in_rand itself is not advanced)
             if L.has_sn:
                 self._sn_layer(L)
-        self._net_forward(self.G, self.code_planes, B, is_training=is_training)
+        self._net_forward(self.G, self.code_planes, B, is_training=is_training, update_moving=False)
         self._check_saturation()
         return K.planes_to_nchw(self.x_all[:, B * HW:, :], B, self.channels, self.height, self.width)[:n]
 

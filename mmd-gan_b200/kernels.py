@@ -574,9 +574,11 @@ def permute_features(src, dst, n, Cc, HW, inverse=False):
     check(lib().mmdgan_permute_features(_ptr(src), _ptr(dst), n, Cc, HW, 1 if inverse else 0, stream()))
 
 
-def bn_finalize(psum, psq, T, Cc, rows, mean, invstd, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99):
+def bn_finalize(psum, psq, T, Cc, rows, mean, invstd, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99, bessel=True):
+    """bessel: Bessel-corrected variance into the moving average (TF's fused kernel, rank-4 inputs); False for the rank-2 inputs
+    of a dense layer, where TF 1.8 falls back to nn.moments (biased)."""
     check(lib().mmdgan_bn_finalize(_ptr(psum), _ptr(psq), T, Cc, rows, float(eps), float(momentum), _ptr(mean), _ptr(invstd),
-                                   _ptr(moving_mean), _ptr(moving_var), stream()))
+                                   _ptr(moving_mean), _ptr(moving_var), 1 if bessel else 0, stream()))
 
 
 def bn_inference_stats(moving_mean, moving_var, Cc, mean, invstd, eps=1e-3):
@@ -637,9 +639,22 @@ def nan_flag(x, n, flag):
 class MmdKernel(object):
     """Configured fused MMD loss kernel (mmdgan_mmd_fwd_bwd); owns its small workspace."""
 
-    def __init__(self, loss_type, rep_weights=(0.0, -1.0), b=64, device='cuda'):
+    def __init__(self, loss_type, rep_weights=(0.0, -1.0), b=64, device='cuda', sigma=None, alpha=None, beta=None):
+        """sigma: bandwidth list of the Gaussian mixture ('mmd_g' / 'fixed_g', GANLoss.sigma, math_func.py:2108); alpha / beta:
+        scales and exponent offset of the t-distribution mixture ('mmd_t' / 'fixed_t', math_func.py:2109-2110).  None keeps the
+        reference defaults; the single-bandwidth losses (rep, rmb, mgb) are fixed at sigma = 1 as in the reference."""
         self.desc = MmdDesc()
         _lib.check(lib().mmdgan_mmd_configure(C.byref(self.desc), loss_type.encode(), float(rep_weights[0]), float(rep_weights[1])))
+        scales = sigma if self.desc.family == 0 else alpha
+        if scales is not None and self.desc.n_sigma > 1:
+            scales = [float(s) for s in scales]
+            if not 1 <= len(scales) <= 8 or min(scales) <= 0.0:
+                raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'the fused MMD kernel takes 1..8 positive kernel scales, got {}'.format(scales))
+            self.desc.n_sigma = len(scales)
+            for i in range(8):
+                self.desc.sigma[i] = scales[i] if i < len(scales) else 0.0
+        if beta is not None and self.desc.family == 1:
+            self.desc.beta = float(beta)
         self.b = b
         self.ws = torch.zeros(int(lib().mmdgan_mmd_workspace(b)) // 4 + 4, dtype=torch.float32, device=device)
         self.sums = torch.zeros(6, dtype=torch.float32, device=device)

@@ -139,3 +139,59 @@ class SymmetricFlat(object):
     def barrier(self):
         """Cross-rank barrier enqueued on the current stream (device side, through the allocation's signal pads)."""
         self.handle.barrier(channel=0)
+
+
+def dp_equals_single(world, rank, device, arch_name='cifar', b=8, steps=3, loss_type='rep', seed=5):
+    """Witness that the N-rank data-parallel step IS the single-process step: the same `steps` fused steps are run (a) by a
+    `world`-rank engine on `b` samples per rank (CUDA graphs + collectives, the path bench.py times) and (b), on rank 0, by a
+    single-process engine on the concatenated batch of world * b samples.  Checked: both losses of every step (1e-4 relative +
+    1e-6), the updated flat parameter buffers of both networks (2e-3 normwise: Adam's first steps are sign-like, so summation
+    order moves a few entries by 2 lr), and bit-identical replicas (torch.equal against rank 0's parameters, Adam slots and
+    spectral-norm state).  The generator's batch norm is removed for this check: batch-norm statistics are per rank by design
+    (DESIGN.md section 6), which is the one documented difference from the single-process step.  Collective: every rank calls."""
+    from . import experiments as oa
+    from .engine import SNGanEngine
+    arch = oa.ARCHITECTURES[arch_name]()
+    for ly in arch['generator']:
+        if ly.get('act_nm') == 'bn':
+            ly['act_nm'] = None
+    g = torch.Generator().manual_seed(7)
+    c, h, w = arch['input'][0]
+    data = torch.rand(steps, world * b, c, h, w, generator=g) * 2 - 1
+    code = torch.randn(steps, world * b, arch['code'][0][0], generator=g)
+    eng = SNGanEngine(arch, b, loss_type=loss_type, device=device, world_size=world, rank=rank, use_graph=True, seed=seed)
+    ref = SNGanEngine(arch, world * b, loss_type=loss_type, device=device, use_graph=False, seed=seed) if rank == 0 else None
+    out = {'ok': True, 'arch': arch_name + ' (generator batch norm removed: BN statistics are per rank by design)', 'ranks': world,
+           'per_rank_batch': b, 'steps': steps, 'loss_type': loss_type, 'max_loss_rel_diff': 0.0, 'param_rel_diff': {}}
+    sl = slice(rank * b, (rank + 1) * b)
+    for it in range(steps):
+        lg, ld = eng.step(data[it, sl], code[it, sl])
+        if rank == 0:
+            lg1, ld1 = ref.step(data[it], code[it])
+            for a, r in ((lg, lg1), (ld, ld1)):
+                diff = abs(a - r)
+                out['max_loss_rel_diff'] = max(out['max_loss_rel_diff'], diff / max(abs(r), 1e-30))
+                if diff > 1e-4 * abs(r) + 1e-6:
+                    out['ok'] = False
+    same = torch.ones(1, device=device)
+    for net in (eng.D, eng.G):
+        tensors = [net.w, net.m, net.v] + [L.sn_x.view(torch.int16).float() for L in net.layers if L.has_sn]
+        for t in tensors:
+            t0 = t.clone()
+            dist.broadcast(t0, 0)
+            if not torch.equal(t0, t):
+                same.zero_()
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out['replicas_bit_identical'] = bool(same.item() == 1.0)
+    if rank == 0:
+        for net, rnet in ((eng.D, ref.D), (eng.G, ref.G)):
+            rel = float((net.w - rnet.w).norm()) / max(float(rnet.w.norm()), 1e-30)
+            out['param_rel_diff'][net.name] = rel
+            if rel > 2e-3:
+                out['ok'] = False
+    out['ok'] = bool(out['ok'] and out['replicas_bit_identical'])
+    flag = torch.tensor([1.0 if out['ok'] else 0.0], device=device)
+    dist.broadcast(flag, 0)
+    out['ok'] = bool(flag.item() == 1.0) and out['replicas_bit_identical']
+    dist.barrier()
+    return out

@@ -360,7 +360,9 @@ def net_forward(specs, params, state, x, is_training=True, sn_mode='default', tf
                 var_b = x.var(red, unbiased=False)
                 shp = (1, -1) if x.dim() == 2 else (1, -1, 1, 1)
                 x = (x - mean.view(shp)) / torch.sqrt(var_b.view(shp) + BN_EPS) * g.view(shp) + b.view(shp)
-                var_u = var_b.detach() * (cnt / max(cnt - 1.0, 1.0))
+                # TF 1.8 uses the fused kernel (Bessel-corrected moving variance) for rank-4 inputs only; rank-2 inputs fall
+                # back to nn.moments and feed the biased variance into the moving average
+                var_u = var_b.detach() * (cnt / max(cnt - 1.0, 1.0)) if x.dim() == 4 else var_b.detach()
                 updates[sp.bn_name('moving_mean')] = mm * BN_MOMENTUM + mean.detach() * (1.0 - BN_MOMENTUM)
                 updates[sp.bn_name('moving_variance')] = mv * BN_MOMENTUM + var_u * (1.0 - BN_MOMENTUM)
             else:

@@ -643,8 +643,10 @@ class _Layers(object):
     def batch_normalization(inputs, axis=-1, momentum=0.99, epsilon=1e-3, center=True, scale=True, beta_initializer=None,
                             gamma_initializer=None, gamma_constraint=None, training=False, renorm=False, fused=None,
                             name=None, **kwargs):
-        """tf.layers.batch_normalization, fused kernel semantics: normalise with the biased batch variance, update the
-        moving variance with the Bessel-corrected one, moving = moving*momentum + batch*(1-momentum) via UPDATE_OPS."""
+        """tf.layers.batch_normalization: normalise with the biased batch variance; moving = moving*momentum + batch*(1-momentum)
+        via UPDATE_OPS.  TF 1.8 keeps `fused=True` only for rank-4 inputs (normalization.py build(): fused = ... and ndims == 4
+        ...): the fused kernel feeds the Bessel-corrected variance into the moving average, the nn.moments fallback taken by
+        rank-2 inputs (a dense layer followed by batch norm) the biased one."""
         x = inputs
         axis = axis % x.dim()
         C = x.shape[axis]
@@ -660,7 +662,7 @@ class _Layers(object):
             mean = x.mean(dim=red)
             var = ((x - mean.reshape(bshape)) ** 2).mean(dim=red)
             n = x.numel() // C
-            unbiased = var * (n / max(n - 1.0, 1.0))
+            unbiased = var * (n / max(n - 1.0, 1.0)) if (x.dim() == 4 and fused is not False) else var
             add_to_collection(GraphKeys.UPDATE_OPS, assign(mm, mm.detach() * momentum + mean.detach() * (1 - momentum)))
             add_to_collection(GraphKeys.UPDATE_OPS, assign(mv, mv.detach() * momentum + unbiased.detach() * (1 - momentum)))
         else:

@@ -1,0 +1,94 @@
+"""Parity of the fused step AT THE BASELINE OPERATING POINTS (BASELINE.json `configs`): the shipped `act_k` (64**(1/8) for the
+32x32 / 48x48 nets, 64**0.1 for the 64x64 nets: my_test_cifar.py:10, my_test_celebA.py:9) and the full batch sizes, against
+the float64 oracle on identical inputs / weights / state.
+
+  configs[0]  CIFAR-10 DCGAN G/D + rep, batch 64      (my_test_cifar.py:43-44 -- the reference's own operating point)
+  configs[1]  CIFAR-10 SNGAN + rep, batch 256
+  configs[2]  STL-10 48x48 + rmb, batch 128
+  configs[3/4] 64x64 net (CelebA / LSUN) + rep, per-GPU batch 128
+
+Compared at 1e-3 normwise (the north-star tolerance): the critic scores, the generated images, every spectral-norm sigma,
+every gradient tensor of both networks, and -- after the update phase -- the batch-norm moving statistics and every
+spectral-norm in_rand.  The losses are differences of kernel means that are ~1 at this operating point (pairwise distances
+<< 1 at random initialisation), so fp32 resolves them to ~1e-7 absolute only: they are held to tol * |L| + 2e-6.
+relu / lrelu units within fp32 rounding of zero may fall on either side of the kink (one flip among ~1e7 units moves every
+gradient below it by ~1e-3 normwise -- an fp32 PyTorch run differs from the float64 one by exactly that); as in
+test_gpu_step.py the oracle differentiates on the engine's side of such ties, the forward values are compared strictly, and
+the number of ties is bounded.
+
+Also: the CUDA path against the REFERENCE-EXECUTED fixtures at the shipped act_k (tests/golden/ref_step_{cifar_rep, stl_rmb,
+celeba_rep, lsun_rep}.npz, produced by running the reference's own SNGan.__gpu_task__ on oracle/tfshim)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import architectures as oa
+from oracle import net as onet
+
+from .test_gpu_step import check_step, make_pair, rel
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+POINTS = [('cifar', 64, 'rep', 'configs[0]'), ('cifar', 256, 'rep', 'configs[1]'), ('stl', 128, 'rmb', 'configs[2]'),
+          ('celeba', 128, 'rep', 'configs[3]/[4] per-GPU batch')]
+
+
+@pytest.mark.parametrize('name,B,loss_type,cfg', POINTS, ids=['{}_b{}_{}'.format(p[0], p[1], p[2]) for p in POINTS])
+def test_step_parity_at_baseline_operating_point(cuda, name, B, loss_type, cfg):
+    arch = oa.ARCHITECTURES[name]()                    # shipped act_k
+    shipped = 64.0 ** 0.1 if name in ('celeba', 'lsun') else 64.0 ** 0.125
+    assert abs(arch['discriminator'][0]['act_k'] - shipped) < 1e-12
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc, eng = make_pair(arch, B, loss_type)
+    check_step(orc, eng, arch, B, seed=11, loss_atol=2e-6, check_state=True)
+
+
+REF_STEPS = [('ref_step_cifar_rep.npz', 'cifar'), ('ref_step_stl_rmb.npz', 'stl'), ('ref_step_celeba_rep.npz', 'celeba'),
+             ('ref_step_lsun_rep.npz', 'lsun')]
+
+
+@pytest.mark.parametrize('fname,arch_name', REF_STEPS, ids=[r[0] for r in REF_STEPS])
+def test_engine_against_reference_executed_fixture_at_shipped_act_k(cuda, fname, arch_name):
+    """First fused step of each shipped architecture dictionary as executed by the reference's own Python (fixture: losses,
+    norm + strided sample of every gradient and of every variable / state after the update).  Against a frozen fixture relu
+    ties cannot be resolved, so -- as in test_engine_cifar_steps_against_reference_execution -- gradient norms are held to
+    1e-3 (discriminator) / 2e-2 (generator, downstream of every tie), strided samples to 2e-2; the state (in_rand, batch-norm
+    moving statistics) to 1e-3."""
+    from mmdgan_b200.engine import SNGanEngine
+    z = np.load(os.path.join(GOLD, fname))
+    arch = oa.ARCHITECTURES[arch_name](act_k=float(z['act_k']))
+    loss_type = str(z['loss_type']) if 'loss_type' in z.files else 'rep'
+    lr_list = tuple(float(v) for v in z['lr_list']) if 'lr_list' in z.files else (5e-4, 2e-4)
+    B, stride = int(z['batch']), int(z['sample_stride'])
+    init = onet.OracleSNGan(arch, loss_type, lr_list=lr_list, dtype=torch.float64, seed=int(z['seed']))
+    onet.warm_spectral_norm(init, int(z['warm']))
+    eng = SNGanEngine(arch, B, loss_type=loss_type, lr_list=lr_list, use_graph=False)
+    for net, params, state in ((eng.G, init.gen_params, init.gen_state), (eng.D, init.dis_params, init.dis_state)):
+        for k, v in params.items():
+            net.set_variable(k, v)
+        for k, v in state.items():
+            net.set_state(k, v)
+        net.refresh()
+    data, code = onet.synthetic_batch(arch, B, seed=5, dtype=torch.float32)
+    lg, ld = eng.step(data, code)
+    assert abs(lg - float(z['loss_gen_0'])) <= 1e-3 * abs(float(z['loss_gen_0'])) + 2e-6
+    assert abs(ld - float(z['loss_dis_0'])) <= 1e-3 * abs(float(z['loss_dis_0'])) + 2e-6
+    gmax = max(float(z['grad_norm_0:' + n]) for n in eng.D.var_offsets)
+    for net in (eng.G, eng.D):
+        for name in net.var_offsets:
+            got = net.get_grad(name).cpu().numpy().astype(np.float64)
+            ref_norm = float(z['grad_norm_0:' + name])
+            if ref_norm < 1e-6 * gmax:
+                assert np.linalg.norm(got) < 1e-4 * gmax, name
+                continue
+            tol = 1e-3 if name.startswith('dis/') else 2e-2
+            assert abs(np.linalg.norm(got) - ref_norm) < tol * ref_norm, (name, np.linalg.norm(got), ref_norm)
+            ref_s = z['grad_sample_0:' + name]
+            assert np.linalg.norm(got.ravel()[::stride] - ref_s) <= 2e-2 * np.linalg.norm(ref_s) + 2e-2 * ref_norm * (len(ref_s) / got.size) ** 0.5, name
+        for name in net.state_names():
+            got = net.get_state(name).cpu().numpy().astype(np.float64).ravel()[::stride]
+            assert rel(got, z['var_sample_0:' + name]) < 1e-3, name

@@ -302,6 +302,9 @@ def test_bn_adam_sn_elementwise(cuda):
     assert rel(mean_d, mean.detach()) < 1e-5
     assert rel(mm, 0.01 * mean.detach()) < 1e-5
     assert rel(mv, 0.99 + 0.01 * var.detach() * rows / (rows - 1)) < 1e-5
+    mm2, mv2 = torch.zeros(Cc, device=cuda), torch.ones(Cc, device=cuda)      # rank-2 batch norm: biased variance (nn.moments path)
+    K.bn_finalize(ps, pq, T, Cc, rows, mean_d, inv_d, mm2, mv2, bessel=False)
+    assert rel(mv2, 0.99 + 0.01 * var.detach()) < 1e-5
     a = K.new_planes(rows, Cc, 3)
     K.bn_apply(zd, mean_d, inv_d, gd, bd, Cc, rows * Cc, 2, a)
     assert rel(K.planes_value(a), a_ref.detach()) < 1e-5

@@ -56,7 +56,9 @@ def kink_masks(eng, B):
     return masks
 
 
-def check_step(orc, eng, arch, B, seed, tol=TOL, degenerate=False):
+def check_step(orc, eng, arch, B, seed, tol=TOL, degenerate=False, loss_atol=None, check_state=False):
+    """One forward + loss + backward of the engine against the float64 oracle on the same batch.  check_state=True also runs
+    the update phase and compares the UPDATE_OPS results (batch-norm moving statistics, every spectral-norm in_rand)."""
     data, code = onet.synthetic_batch(arch, B, seed=seed, dtype=torch.float64)
     eng.stage(data.float().cuda(), code.float().cuda())
     eng._phase_forward()
@@ -83,7 +85,7 @@ def check_step(orc, eng, arch, B, seed, tol=TOL, degenerate=False):
     s_ref = torch.cat([col['s_x'], col['s_gen']], 0).detach()
     assert rel(scores, s_ref) < tol
     # the kernel means are O(1): 2e-6 is the fp32 resolution of their differences
-    atol = 2e-6 if degenerate else 1e-7
+    atol = loss_atol if loss_atol is not None else (2e-6 if degenerate else 1e-7)
     assert abs(float(losses[0]) - float(lg)) <= tol * abs(float(lg)) + atol
     assert abs(float(losses[1]) - float(ld)) <= tol * abs(float(ld)) + atol
     x_gen = eng.generate(code.float().cuda()).cpu()
@@ -100,6 +102,13 @@ def check_step(orc, eng, arch, B, seed, tol=TOL, degenerate=False):
     for L in eng.D.layers:
         if L.has_sn:
             assert abs(float(L.sigma) - float(col[L.ly.layer_scope + '/sigma'].detach())) < tol * float(col[L.ly.layer_scope + '/sigma'].detach())
+    if check_state:
+        eng._phase_update()
+        torch.cuda.synchronize()
+        for net, upd in ((eng.G, ug), (eng.D, ud)):
+            assert set(upd.keys()) == set(net.state_names())
+            for name, ref in upd.items():
+                assert rel(net.get_state(name), ref.detach()) < tol, (name, rel(net.get_state(name), ref.detach()))
     return lg, ld, ug, ud
 
 

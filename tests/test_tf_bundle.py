@@ -149,6 +149,29 @@ def test_checkpoint_state_file(tmp_path):
     assert tb.read_checkpoint_state(folder) == (b, [a, b])
 
 
+def test_checkpoint_state_with_relative_default_out(tmp_path, monkeypatch):
+    """FLAGS.DEFAULT_OUT is relative by default ('MMD-GAN/Results/'): the state file must still hold folder-relative paths, so
+    that Saver(max_to_keep=2) pruning finds the older bundles and get_ckpt's state-file fallback resolves."""
+    from mmdgan_b200.GeneralTools.misc_fun import FLAGS
+    from mmdgan_b200.GeneralTools import graph_func as gf
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(FLAGS, 'DEFAULT_OUT', 'rel/sub/')
+    monkeypatch.setattr(FLAGS, 'CKPT_FORMAT', 'tf')
+    monkeypatch.setattr(FLAGS, 'SILENT_MODE', True)
+    folder, _, save_path = gf.prepare_folder('cifar', 'sngan_rep')
+    assert not os.path.isabs(save_path)
+    src = _FakeEngine(5)
+    for s in (1, 2, 3):
+        gf.save_checkpoint(src, save_path, s)
+    names = sorted(os.listdir(folder))
+    assert names == ['checkpoint', 'cifar.ckpt-2.data-00000-of-00001', 'cifar.ckpt-2.index',
+                     'cifar.ckpt-3.data-00000-of-00001', 'cifar.ckpt-3.index']
+    assert open(os.path.join(folder, 'checkpoint')).read().splitlines()[0] == 'model_checkpoint_path: "cifar.ckpt-3"'
+    latest, every = tb.read_checkpoint_state(folder)
+    assert os.path.isfile(latest + '.index') and all(os.path.isfile(p + '.index') for p in every)
+    assert os.path.samefile(latest + '.index', save_path + '-3.index')
+
+
 class _FakeNet(object):
     """The slice of engine.NetState the checkpoint helpers touch, on the CPU."""
 
