@@ -26,11 +26,14 @@
 namespace mg {
 
 static constexpr int kBM = 128;
-static constexpr int kPipeBudget = 96;  // KB of pipeline stages per CTA (two CTAs per SM)
+static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per block on sm_100
 static constexpr int kBK = 32;         // bf16 elements of K per pipeline stage
 static constexpr int kRowBytes = 64;   // 32 bf16 = one 64-byte swizzle row (SWIZZLE_64B)
-static constexpr int kProducerThreads = 128;
-static constexpr int kThreads = 192;
+static constexpr int kEpiThreads = 128;       // one epilogue group: warps 0-3 (group 0) / warps 6-9 (group 1); TMEM lane quarter = warp % 4
+static constexpr int kProducerThreads = 128;  // warps 10-13: cp.async gather producers (ATMA = false only)
+static constexpr int kThreadsTma = 320;       // epilogue group 0, TMA, MMA, epilogue group 1
+static constexpr int kThreadsGather = 448;    // + four gather warps
+static constexpr int kMaxStages = 8;
 static constexpr unsigned long long kWatchdogNs = 4000000000ull;
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -51,6 +54,184 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, uns
     }
 }
 
+// ---- epilogue building blocks
+template <int EN>
+struct EpiShape {
+    static constexpr int QPR = EN / 4;                              // float4 per staged row
+    static constexpr int ITERS = (kBM * QPR) / kEpiThreads;         // float4 per thread and column group
+    static constexpr int IPW = ITERS < 8 ? ITERS : 8;               // iterations per 32-bit word of sign bits (4 bits each)
+    static constexpr int WORDS = ITERS / IPW;
+    static constexpr int PITCH = EN * 4 + 16;                       // staging row pitch in bytes
+};
+struct EpiCtx {
+    const ConvGemmParams* p;
+    const uint8_t* stg;            // staged accumulator columns [128][PITCH]
+    const long long* prow_s;       // destination pixel of each tile row (-1: beyond M)
+    const uint32_t* abits_s;       // [NH * WORDS][128] sign bits
+    float4* red;                   // [2][128] column-sum scratch
+    float alpha, negslope, auxslope;
+    int col0, t, bar_id;
+    long long tl;                  // tile row of the column-sum workspace
+};
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return v > 0.f ? v : 0.1f * v;
+    if (act == 2) return v > 0.f ? v : 0.f;
+    if (act == 3) return tanhf(v);
+    return v;
+}
+__device__ __forceinline__ float act_grad_from_output(float a, int mode) {
+    if (mode == 1) return a > 0.f ? 1.f : 0.1f;
+    if (mode == 2) return a > 0.f ? 1.f : 0.f;
+    if (mode == 3) return 1.f - a * a;
+    return 1.f;
+}
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// per-tile column sums (bias gradients, batch-norm statistics): 128 partial float4 pairs -> QPR threads finish them
+template <int EN>
+__device__ __forceinline__ void epi_colsum(const EpiCtx& c, int col, bool col_ok, float4 cs, float4 cq) {
+    constexpr int QPR = EpiShape<EN>::QPR;
+    const ConvGemmParams& p = *c.p;
+    epi_bar(c.bar_id);                 // the scratch aliases the staging tile: every thread has finished reading its staged values
+    c.red[c.t] = cs;
+    c.red[kEpiThreads + c.t] = cq;
+    epi_bar(c.bar_id);
+    if (c.t < QPR && col_ok) {
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = c.t; k < kEpiThreads; k += QPR) {
+            const float4 a1 = c.red[k], a2 = c.red[kEpiThreads + k];
+            s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+            s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
+        }
+        *reinterpret_cast<float4*>(p.colsum + c.tl * p.Ncols + col) = s1;
+        if (p.colsumsq) *reinterpret_cast<float4*>(p.colsumsq + c.tl * p.Ncols + col) = s2;
+    }
+}
+// One column group of one tile, specialised: act in {linear, lrelu, relu} as max(v,0) + negslope * min(v,0); AUX = multiply by
+// the activation derivative given as sign bits; COLSUM = per-tile column sums; OUT 0 = two fp16 planes of 16 x value
+// (FMT_F16A), 1 = two bf16 planes, 2 = raw fp32.
+template <int EN, bool AUX, bool COLSUM, int OUT>
+__device__ __noinline__ void epi_group(const EpiCtx& c, int h) {
+    using S = EpiShape<EN>;
+    const ConvGemmParams& p = *c.p;
+    const int t = c.t;
+    const int colq = t % S::QPR;
+    const int col = c.col0 + h * EN + colq * 4;
+    const bool col_ok = col < p.Ncols;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float alpha = c.alpha, neg = c.negslope, aslope = c.auxslope;
+    const int Cd = p.Cd;
+    if (col_ok) {
+#pragma unroll
+        for (int w = 0; w < S::WORDS; ++w) {
+            const uint32_t sbits = AUX ? c.abits_s[(h * S::WORDS + w) * kEpiThreads + t] : 0u;
+#pragma unroll 4
+            for (int k = 0; k < S::IPW; ++k) {
+                const int r = (t + (w * S::IPW + k) * kEpiThreads) / S::QPR;
+                const long long prow = c.prow_s[r];
+                if (prow < 0) continue;
+                float4 v = *reinterpret_cast<const float4*>(c.stg + r * S::PITCH + colq * 16);
+                v.x = fmaf(v.x, alpha, bias4.x); v.y = fmaf(v.y, alpha, bias4.y);
+                v.z = fmaf(v.z, alpha, bias4.z); v.w = fmaf(v.w, alpha, bias4.w);
+                v.x = fmaf(neg, fminf(v.x, 0.f), fmaxf(v.x, 0.f)); v.y = fmaf(neg, fminf(v.y, 0.f), fmaxf(v.y, 0.f));
+                v.z = fmaf(neg, fminf(v.z, 0.f), fmaxf(v.z, 0.f)); v.w = fmaf(neg, fminf(v.w, 0.f), fmaxf(v.w, 0.f));
+                if (AUX) {
+                    const uint32_t b = sbits >> (4 * k);
+                    v.x *= (b & 1u) ? 1.f : aslope;
+                    v.y *= (b & 2u) ? 1.f : aslope;
+                    v.z *= (b & 4u) ? 1.f : aslope;
+                    v.w *= (b & 8u) ? 1.f : aslope;
+                }
+                const long long off = prow * Cd + col;
+                if (OUT == 0) {
+                    note_saturation4(p.sat_flag, FMT_F16A, v);
+                    store_vals4(static_cast<bf16_t*>(p.dst) + off, p.dst_plane, 2, FMT_F16A, v);
+                } else if (OUT == 1) {
+                    store_planes4(static_cast<bf16_t*>(p.dst) + off, p.dst_plane, 2, v);
+                } else {
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + off) = v;
+                }
+                if (COLSUM && prow < p.colsum_rows) {
+                    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+                    cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
+                    cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
+                }
+            }
+        }
+    }
+    if (COLSUM) epi_colsum<EN>(c, col, col_ok, cs, cq);
+}
+// the generic form: tanh, tanh' (needs the value of the aux activation), three-plane outputs, ...
+template <int EN>
+__device__ __noinline__ void epi_group_generic(const EpiCtx& c, int h) {
+    using S = EpiShape<EN>;
+    const ConvGemmParams& p = *c.p;
+    const int t = c.t;
+    const int colq = t % S::QPR;
+    const int col = c.col0 + h * EN + colq * 4;
+    const bool col_ok = col < p.Ncols;
+    const bool aux_bits = p.aux != nullptr && p.aux_mode != 3;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float alpha = c.alpha, slope = c.auxslope;
+#pragma unroll 1
+    for (int w = 0; w < S::WORDS; ++w) {
+        const uint32_t sbits = aux_bits ? c.abits_s[(h * S::WORDS + w) * kEpiThreads + t] : 0u;
+#pragma unroll 1
+        for (int k = 0; k < S::IPW; ++k) {
+            const int r = (t + (w * S::IPW + k) * kEpiThreads) / S::QPR;
+            const long long prow = c.prow_s[r];
+            if (prow < 0 || !col_ok || (p.debug & 4)) continue;
+            float4 v = *reinterpret_cast<const float4*>(c.stg + r * S::PITCH + colq * 16);
+            v.x = apply_act(fmaf(v.x, alpha, bias4.x), p.act);
+            v.y = apply_act(fmaf(v.y, alpha, bias4.y), p.act);
+            v.z = apply_act(fmaf(v.z, alpha, bias4.z), p.act);
+            v.w = apply_act(fmaf(v.w, alpha, bias4.w), p.act);
+            if (aux_bits) {
+                const uint32_t b = sbits >> (4 * k);
+                v.x *= (b & 1u) ? 1.f : slope;
+                v.y *= (b & 2u) ? 1.f : slope;
+                v.z *= (b & 4u) ? 1.f : slope;
+                v.w *= (b & 8u) ? 1.f : slope;
+            } else if (p.aux) {
+                // tanh' = 1 - a^2 needs the value (all planes): only the 3-channel image layer, read in place
+                const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
+                const float4 a4 = load_vals4(p.aux, p.aux_plane, p.aux_npl, p.aux_fmt, arow * p.Cd + col);
+                v.x *= act_grad_from_output(a4.x, 3);
+                v.y *= act_grad_from_output(a4.y, 3);
+                v.z *= act_grad_from_output(a4.z, 3);
+                v.w *= act_grad_from_output(a4.w, 3);
+            }
+            if (p.out_mode == 0) {
+                note_saturation4(p.sat_flag, p.dst_fmt, v);
+                store_vals4(static_cast<bf16_t*>(p.dst) + prow * p.Cd + col, p.dst_plane, p.dst_npl, p.dst_fmt, v);
+            } else
+                *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + prow * p.Cd + col) = v;
+            if (prow < p.colsum_rows) {
+                cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+                cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
+                cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
+            }
+        }
+    }
+    if (p.colsum) epi_colsum<EN>(c, col, col_ok, cs, cq);
+}
+
+// profiling experiments (MMDGAN_PROF=1): cycles a role spends waiting, per CTA
+__device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned code, long long* acc) {
+    if (acc == nullptr) { mbar_wait_wd(bar, parity, err, code); return; }
+    const long long t0 = clock64();
+    mbar_wait_wd(bar, parity, err, code);
+    *acc += clock64() - t0;
+}
+
+// PERSISTENT kernel: one CTA (or CTA pair) per SM loops over output tiles; the fp32 accumulator is DOUBLE-BUFFERED in TMEM
+// (2 x BN columns), so the epilogue warps drain tile i while the MMA warp already accumulates tile i + 1, the operand
+// pipeline never drains between tiles, and barrier init / TMEM allocation / tensor-map fetch happen once per SM instead of
+// once per tile.  The epilogue staging tile has its own shared memory (it no longer aliases the pipeline stages).
+//
 // PAIR = true: two CTAs of a cluster (one TPC) share one 256 x BN tile through tcgen05 cta_group::2 -- each CTA gathers
 // its own 128 rows of A and stages HALF of the weight tile, so the L2 -> SM bytes per MMA drop by a quarter (BN = 128) to
 // a half (BN = 256) and each SM's tensor core reads only half of B from its own shared memory.
@@ -61,18 +242,28 @@ struct GemmCfg {
     static constexpr int A_BYTES = kBM * kRowBytes;       // per plane
     static constexpr int B_BYTES = BROWS * kRowBytes;
     static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
-    // budget for TWO resident CTAs per SM: the epilogue / prologue of one overlaps the main loop of the other
-    static constexpr int STAGES_RAW = (kPipeBudget * 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-    static constexpr int EN = BN > 128 ? 128 : BN;   // epilogue column group
+    static constexpr int ACC_COLS = BN < 32 ? 32 : BN;    // TMEM columns of one accumulator
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;        // two accumulators (a power of two >= 64)
+    // epilogue column group: small, because every byte of shared memory that is not a pipeline stage costs operand bytes in
+    // flight (the L2 round trip is ~1.5 us; a stage is consumed every ~0.2 us at the full MMA rate)
+    static constexpr int EN = BN > 32 ? 32 : BN;
     static constexpr int PITCH = EN * 4 + 16;        // staging row pitch in bytes
     static constexpr int STAGING_BYTES = kBM * PITCH;
-    static constexpr int RED_BYTES = 2 * kProducerThreads * 16;
+    static constexpr int RED_BYTES = 2 * kEpiThreads * 16;   // column-sum scratch: ALIASES the staging tile (used after its last read)
+    static_assert(RED_BYTES <= STAGING_BYTES || BN < 32, "column-sum scratch must fit the staging tile");
+    static constexpr int STG_BYTES = STAGING_BYTES > RED_BYTES ? STAGING_BYTES : RED_BYTES;
     static constexpr int PROW_BYTES = kBM * 8;
+    static constexpr int ABITS_BYTES = (BN / EN) * EpiShape<EN>::WORDS * kEpiThreads * 4;   // activation-derivative sign bits of one tile
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int EPI_BYTES = STG_BYTES + PROW_BYTES + ABITS_BYTES;   // private to one epilogue group
+    static constexpr int FIXED_BYTES = 2 * EPI_BYTES + BAR_BYTES;
+    static constexpr int STAGES_RAW = (kSmemMax - 1024 /*align slack*/ - FIXED_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > kMaxStages ? kMaxStages : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES + RED_BYTES + PROW_BYTES ? PIPE_BYTES : STAGING_BYTES + RED_BYTES + PROW_BYTES;
-    static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + kBM * 8 /*destination rows*/;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int SMEM_NEED = 1024 + PIPE_BYTES + FIXED_BYTES;
+    // at least half of the SM's shared memory + 1 KB: ONE persistent CTA per SM (two of them must never queue for one SM's TMEM)
+    static constexpr int SMEM_BYTES = SMEM_NEED > kSmemMax / 2 + 1024 ? SMEM_NEED : kSmemMax / 2 + 1024;
+    static_assert(SMEM_BYTES <= kSmemMax, "shared-memory budget");
 };
 
 // ---- cluster / cta_group::2 primitives (pair kernel only)
@@ -136,23 +327,85 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
         : "memory");
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == 1) return v > 0.f ? v : 0.1f * v;
-    if (act == 2) return v > 0.f ? v : 0.f;
-    if (act == 3) return tanhf(v);
-    return v;
+// arrive on the mbarrier at this shared-memory offset in cluster CTA 0 (the pair's leader); rank 0 addresses itself
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) { mbar_arrive_remote(bar, 0); }
+// wait with cluster-scope acquire: the data the barrier publishes was written by the OTHER CTA of the pair
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
-__device__ __forceinline__ float act_grad_from_output(float a, int mode) {
-    if (mode == 1) return a > 0.f ? 1.f : 0.1f;
-    if (mode == 2) return a > 0.f ? 1.f : 0.f;
-    if (mode == 3) return 1.f - a * a;
-    return 1.f;
+__device__ __forceinline__ void st_shared_remote_u32(void* local_addr, uint32_t rank, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}" ::"r"(smem_u32(local_addr)),
+        "r"(rank), "r"(v)
+        : "memory");
 }
 
-// ATMA = true: the gathered operand is staged by TMA as well -- one 4-D box {32 channels, W, rows, images} per
+// ---- dynamic tile scheduler.  Tiles [0, nunits) are assigned statically (unit u starts with tile u); every further tile is a
+// ticket drawn from a global counter by the scheduler thread of the unit (the TMA thread of the single CTA / of the pair's
+// leader) and published to the other roles through a small ring in shared memory (pair: in both CTAs): tile_full[slot] says
+// "ring[slot] holds the id of the unit's lt-th tile (-1: no more tiles)", tile_empty[slot] that every consumer has read it.
+// A CTA that starts late (another stream's kernel still held its SM) simply draws fewer tickets: no tail imbalance.
+static constexpr int kRing = 8;
+template <bool PAIR>
+__device__ __forceinline__ int ring_read(const int* ring, uint64_t* tile_full, uint64_t* tile_empty, int lt, unsigned int* err) {
+    // called by one lane; returns the tile id of this unit's lt-th tile
+    const int slot = lt % kRing;
+    const uint32_t ph = (lt / kRing) & 1;
+    if (PAIR) {
+        if (!mbar_try_wait_cluster(&tile_full[slot], ph)) {
+            const unsigned long long t0 = gtime_ns();
+            while (!mbar_try_wait_cluster(&tile_full[slot], ph))
+                if (gtime_ns() - t0 > kWatchdogNs) {
+                    printf("mmdgan: tile ring watchdog block %d thread %d\n", blockIdx.x, threadIdx.x);
+                    __trap();
+                }
+        }
+    } else {
+        mbar_wait_wd(&tile_full[slot], ph, err, 9);
+    }
+    const int tile = *reinterpret_cast<const volatile int*>(ring + slot);
+    if (PAIR) mbar_arrive_leader(&tile_empty[slot]); else mbar_arrive(&tile_empty[slot]);
+    return tile;
+}
+// one lane reads, the warp gets the value
+template <bool PAIR>
+__device__ __forceinline__ int ring_read_warp(const int* ring, uint64_t* tile_full, uint64_t* tile_empty, int lt, unsigned int* err) {
+    int tile = 0;
+    if ((threadIdx.x & 31) == 0) tile = ring_read<PAIR>(ring, tile_full, tile_empty, lt, err);
+    return __shfl_sync(0xffffffffu, tile, 0);
+}
+
+
+struct TileCoord {
+    int tile_n, cls_idx, tile_m;
+};
+// linear tile index -> (N tile, class, M tile), N tile fastest: the CTAs that gather the same input rows (the other N tiles,
+// the other output-parity classes) run at the same time on neighbouring SMs, so the re-reads hit L2 instead of HBM
+template <bool PAIR>
+__device__ __forceinline__ TileCoord decode_tile(int lin, const ConvGemmParams& p, uint32_t rank) {
+    TileCoord c;
+    c.tile_n = lin % p.tiles_n;
+    lin /= p.tiles_n;
+    c.cls_idx = lin % p.classes;
+    lin /= p.classes;
+    c.tile_m = PAIR ? lin * 2 + static_cast<int>(rank) : lin;
+    return c;
+}
+
+// ATMA = true: the gathered operand is staged by TMA as well -- one 5-D box {32 channels, W, rows, images, planes} per
 // (channel chunk, tap) lands exactly the 128 K-major rows of the tile, with out-of-bounds zero fill as SAME padding and
 // the traversal stride as the convolution stride.  Used whenever a 128-row tile is a whole number of image rows;
-// otherwise the four producer warps gather with cp.async (ATMA = false).
+// otherwise four producer warps gather with cp.async (ATMA = false).
 template <int BN, int NPASS, bool PAIR, bool ATMA>
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CUtensorMap& tmA0, const ConvGemmParams& p) {
     using Cfg = GemmCfg<BN, NPASS, PAIR>;
@@ -162,26 +415,31 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
-    uint64_t* full_bar = bars;                    // single: A arrivals + B bytes.  pair: this CTA's A arrivals only
-    uint64_t* empty_bar = bars + STAGES;
-    uint64_t* accum_bar = bars + 2 * STAGES;
-    uint64_t* bfull_bar = bars + 2 * STAGES + 1;  // pair, leader: weight bytes of BOTH CTAs
-    uint64_t* peer_bar = bars + 3 * STAGES + 1;   // pair, leader: "the peer's A rows have landed"
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * STAGES + 2);
-
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // linear block index -> (N tile, class, M tile), N tile fastest: every CTA that gathers the same input rows (the other
-    // N tiles, the other output-parity classes) is scheduled back to back, so the re-reads hit L2 instead of HBM
+    // two epilogue groups of four warps alternate over the unit's tiles (group g drains accumulator g): every latency of the
+    // epilogue (sign prefetch, tcgen05.ld, staging, stores) has two tile times to hide in
+    const int egrp = warp >= 6 ? 1 : 0;
+    uint8_t* stg = smem + Cfg::PIPE_BYTES + egrp * Cfg::EPI_BYTES;           // epilogue staging tile of this thread's group
+    float4* red = reinterpret_cast<float4*>(stg);                            // column-sum scratch (aliases the staging tile)
+    long long* prow_s = reinterpret_cast<long long*>(stg + Cfg::STG_BYTES);
+    uint32_t* abits_s = reinterpret_cast<uint32_t*>(stg + Cfg::STG_BYTES + Cfg::PROW_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + 2 * Cfg::EPI_BYTES);
+    uint64_t* full_bar = bars;                          // single: A arrivals + B bytes.  pair: this CTA's A arrivals only
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* bfull_bar = bars + 2 * kMaxStages;        // pair, leader: weight bytes of BOTH CTAs
+    uint64_t* peer_bar = bars + 3 * kMaxStages;         // pair, leader: "the peer's A rows have landed"
+    uint64_t* accf_bar = bars + 4 * kMaxStages;         // [2] accumulator b is complete (MMA -> epilogue)
+    uint64_t* acce_bar = bars + 4 * kMaxStages + 2;     // [2] accumulator b is drained (epilogue -> MMA; pair: leader's, both CTAs arrive)
+    uint64_t* tile_full = bars + 4 * kMaxStages + 4;    // [kRing]
+    uint64_t* tile_empty = bars + 4 * kMaxStages + 4 + kRing;   // [kRing] (pair: the leader's; consumers of both CTAs arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 4 + 2 * kRing);
+    int* ring = reinterpret_cast<int*>(tmem_slot + 2);          // [kRing]
+
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-    int lin = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int tile_n = lin % p.tiles_n;
-    lin /= p.tiles_n;
-    const int cls_idx = lin % p.classes;
-    lin /= p.classes;
-    const int tile_m = PAIR ? lin * 2 + static_cast<int>(rank) : lin;
-    const GemmClass cls = p.cls[cls_idx];
+    const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int nunits = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int total = p.tiles_n * p.classes * (PAIR ? p.tiles_m / 2 : p.tiles_m);
     const int ksteps = p.ksteps;
 
     if (warp == 4 && lane == 0) {
@@ -195,7 +453,18 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 mbar_init(&peer_bar[s], 1);
             }
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&accf_bar[b], 1);
+            mbar_init(&acce_bar[b], PAIR ? 8 : 4);      // one arrival per epilogue warp (of both CTAs of a pair)
+        }
+        // consumers of a tile id: MMA warp + 8 epilogue warps (+ 4 gather warps); in the pair's peer CTA the TMA thread and the
+        // relay warp read it too
+        constexpr int kConsSelf = 1 + 8 + (ATMA ? 0 : 4);
+        constexpr int kConsPeer = 1 + 8 + (ATMA ? 0 : 4 + 1);
+        for (int r = 0; r < kRing; ++r) {
+            mbar_init(&tile_full[r], 1);
+            mbar_init(&tile_empty[r], PAIR ? kConsSelf + kConsPeer : kConsSelf);
+        }
         fence_barrier_init();
     }
     if (warp == 5) {
@@ -216,313 +485,369 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
         return smem + s * Cfg::STAGE_BYTES + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
     };
 
-    if (warp < 4) {
+    if (warp >= 10) {
       if (!ATMA) {
         // ======================= A producers (gather) =======================
-        const int t = threadIdx.x;
+        const int t = threadIdx.x - 320;
         const int chunk = t & 3;
         const int rbase = t >> 2;  // rows rbase + 32*i
         // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte address = (row >> 1) & 3
         const uint32_t swz_off = static_cast<uint32_t>((chunk ^ ((rbase >> 1) & 3)) << 4);
-        int by[4], bx[4], ib[4];  // by < -30000 marks an invalid row
         const int HgWg = p.Hg * p.Wg;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int m = tile_m * kBM + rbase + 32 * i;
-            if (m < p.M) {
-                int n = m / HgWg;
-                int rem = m - n * HgWg;
-                int y = rem / p.Wg;
-                int x = rem - y * p.Wg;
-                by[i] = y * p.sy + cls.oy;
-                bx[i] = x * p.sx + cls.ox;
-                ib[i] = n * p.Hs * p.Ws;
-            } else {
-                by[i] = -1000000;
-                bx[i] = 0;
-                ib[i] = 0;
-            }
-        }
         // K order: (channel chunk of CW = min(Cs, 32), tap, channel within chunk) -- taps innermost, so consecutive
         // k-steps re-read neighbouring pixels of the SAME 64-byte channel chunk
         const int cw4 = (p.Cs >= kBK ? kBK : p.Cs) >> 3;   // 16-byte units (8 bf16) per (chunk, tap) group
         const int ncc = p.Cs / (cw4 * 8);
         const int ntaps = p.TH * p.TW;
-        for (int j = 0; j < ksteps; ++j) {
-            const int s = j % STAGES;
-            const uint32_t ph = (j / STAGES) & 1;
-            mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 1);
-            const int u = j * 4 + chunk;
-            const int g = u / cw4;
-            const int cc = g / ntaps;
-            const int tap = g - cc * ntaps;
-            const int cq = cc * cw4 + (u - g * cw4);
-            const int a = tap / p.TW;
-            const int b = tap - a * p.TW;
-            const bool tap_ok = cc < ncc;
-            const uint32_t a0 = smem_u32(stage_a(s, 0)) + swz_off;
+        int it = 0;
+        for (int lt = 0;; ++lt) {
+            const int tile = ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err);
+            if (tile < 0) break;
+            const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
+            const GemmClass cls = p.cls[tc.cls_idx];
+            int by[4], bx[4], ib[4];  // by < -30000 marks an invalid row
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int yy = by[i] + a;
-                const int xx = bx[i] + b;
-                const bool ok = tap_ok && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
-                const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 8) : 0;
-                const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 32 * i) * kRowBytes);
-                if (p.debug & 1) continue;
-#pragma unroll
-                for (int pl = 0; pl < NPL; ++pl) cp_async16(dsta + pl * Cfg::A_BYTES, p.src + pl * p.src_plane + off, ok ? 16u : 0u);
+                int m = tc.tile_m * kBM + rbase + 32 * i;
+                if (m < p.M) {
+                    int n = m / HgWg;
+                    int rem = m - n * HgWg;
+                    int y = rem / p.Wg;
+                    int x = rem - y * p.Wg;
+                    by[i] = y * p.sy + cls.oy;
+                    bx[i] = x * p.sx + cls.ox;
+                    ib[i] = n * p.Hs * p.Ws;
+                } else {
+                    by[i] = -1000000;
+                    bx[i] = 0;
+                    ib[i] = 0;
+                }
             }
-            // asynchronous publication: the stage's full barrier gets this thread's arrival when its copies land, so the
-            // producers run ahead by as many stages as there are free slots and the MMA warp never waits on this loop
-            cp_async_mbar_arrive_noinc(&full_bar[s]);
+            for (int j = 0; j < ksteps; ++j, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 1);
+                const int u = j * 4 + chunk;
+                const int g = u / cw4;
+                const int cc = g / ntaps;
+                const int tap = g - cc * ntaps;
+                const int cq = cc * cw4 + (u - g * cw4);
+                const int a = tap / p.TW;
+                const int b = tap - a * p.TW;
+                const bool tap_ok = cc < ncc;
+                const uint32_t a0 = smem_u32(stage_a(s, 0)) + swz_off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int yy = by[i] + a;
+                    const int xx = bx[i] + b;
+                    const bool ok = tap_ok && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
+                    const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 8) : 0;
+                    const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 32 * i) * kRowBytes);
+                    if (p.debug & 1) continue;
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl) cp_async16(dsta + pl * Cfg::A_BYTES, p.src + pl * p.src_plane + off, ok ? 16u : 0u);
+                }
+                // asynchronous publication: the stage's full barrier gets this thread's arrival when its copies land, so the
+                // producers run ahead by as many stages as there are free slots and the MMA warp never waits on this loop
+                cp_async_mbar_arrive_noinc(&full_bar[s]);
+            }
         }
       }
     } else if (warp == 4) {
         // ======================= TMA producer: weights (and, with ATMA, the gathered operand) =======================
         if (lane == 0) {
-            const int row0 = cls.wrow + tile_n * BN + (PAIR ? static_cast<int>(rank) * Cfg::BROWS : 0);
-            // tile origin on the (image, row) grid; with ATMA a tile is a whole number of image rows
             const int hw = p.Hg * p.Wg;
-            const int pix0 = tile_m * kBM;
-            const int n0 = pix0 / hw;
-            const int y0 = (pix0 - n0 * hw) / p.Wg;
             const int ntaps = p.TH * p.TW;
             const uint32_t a_bytes = ATMA ? NPL * Cfg::A_BYTES : 0u;
-            int cc = 0, tap = 0;
-            for (int j = 0; j < ksteps; ++j) {
-                const int s = j % STAGES;
-                const uint32_t ph = (j / STAGES) & 1;
-                mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 2);
-                const int ta = tap / p.TW, tb = tap - ta * p.TW;
-                const int cx = tb + cls.ox, cy = y0 * p.sy + ta + cls.oy, cch = cc * kBK;
-                if (PAIR) {
-                    // both CTAs load their operand shares; all bytes are credited to the leader's barrier
-                    uint64_t* bar = ATMA ? &full_bar[s] : &bfull_bar[s];
-                    if (rank == 0) mbar_arrive_expect_tx(bar, 2 * (NPL * Cfg::B_BYTES + a_bytes));
-                    // the planes are the outermost tensor-map dimension: one box brings all NPL planes of the stage
-                    tma_load_3d_pair(smem_u32(stage_b(s, 0)), &tmB0, bar, j * kBK, row0, 0);
-                    if (ATMA) tma_load_5d_pair(smem_u32(stage_a(s, 0)), &tmA0, bar, cch, cx, cy, n0, 0);
+            const bool prof = p.prof != nullptr;
+            long long w_tma = 0, w_sched = 0;
+            const long long t_begin = clock64();
+            int it = 0;
+            for (int lt = 0;; ++lt) {
+                int tile;
+                if (PAIR && rank != 0) {
+                    tile = ring_read<PAIR>(ring, tile_full, tile_empty, lt, p.err);
                 } else {
-                    mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES + a_bytes);
-                    tma_load_3d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0, 0);
-                    if (ATMA) tma_load_5d(smem_u32(stage_a(s, 0)), &tmA0, &full_bar[s], cch, cx, cy, n0, 0);
+                    // ---- scheduler: next tile of this unit -> ring (of both CTAs of a pair)
+                    const int slot = lt % kRing;
+                    mbar_wait_wd(&tile_empty[slot], ((lt / kRing) & 1) ^ 1, p.err, 10);
+                    if (lt == 0) tile = unit;
+                    else {
+                        const long long ts0 = clock64();
+                        const unsigned int ticket = atomicAdd(p.sched, 1u);
+                        if (prof) w_sched += clock64() - ts0 + (ticket & 0);
+                        if (ticket == static_cast<unsigned int>(total - 1)) atomicExch(p.sched, 0u);   // the last draw of the launch re-arms the counter
+                        tile = static_cast<int>(ticket) + nunits;
+                    }
+                    if (tile >= total) tile = -1;
+                    ring[slot] = tile;
+                    if (PAIR) {
+                        st_shared_remote_u32(ring + slot, 1, static_cast<uint32_t>(tile));
+                        mbar_arrive_remote(&tile_full[slot], 1);
+                    }
+                    mbar_arrive(&tile_full[slot]);
                 }
-                if (++tap == ntaps) { tap = 0; ++cc; }      // K order: (channel chunk, tap)
+                if (tile < 0) break;
+                const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
+                const GemmClass cls = p.cls[tc.cls_idx];
+                const int row0 = cls.wrow + tc.tile_n * BN + (PAIR ? static_cast<int>(rank) * Cfg::BROWS : 0);
+                // tile origin on the (image, row) grid; with ATMA a tile is a whole number of image rows
+                const int pix0 = tc.tile_m * kBM;
+                const int n0 = pix0 / hw;
+                const int y0 = (pix0 - n0 * hw) / p.Wg;
+                int cc = 0, tap = 0;
+                for (int j = 0; j < ksteps; ++j, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait_prof(&empty_bar[s], ph ^ 1, p.err, 2, prof ? &w_tma : nullptr);
+                    const int ta = tap / p.TW, tb = tap - ta * p.TW;
+                    const int cx = tb + cls.ox, cy = y0 * p.sy + ta + cls.oy, cch = cc * kBK;
+                    if (PAIR) {
+                        // both CTAs load their operand shares; all bytes are credited to the leader's barrier
+                        uint64_t* bar = ATMA ? &full_bar[s] : &bfull_bar[s];
+                        if (rank == 0) mbar_arrive_expect_tx(bar, 2 * (NPL * Cfg::B_BYTES + a_bytes));
+                        // the planes are the outermost tensor-map dimension: one box brings all NPL planes of the stage
+                        tma_load_3d_pair(smem_u32(stage_b(s, 0)), &tmB0, bar, j * kBK, row0, 0);
+                        if (ATMA) tma_load_5d_pair(smem_u32(stage_a(s, 0)), &tmA0, bar, cch, cx, cy, n0, 0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES + a_bytes);
+                        tma_load_3d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0, 0);
+                        if (ATMA) tma_load_5d(smem_u32(stage_a(s, 0)), &tmA0, &full_bar[s], cch, cx, cy, n0, 0);
+                    }
+                    if (++tap == ntaps) { tap = 0; ++cc; }      // K order: (channel chunk, tap)
+                }
+            }
+            if (prof) {
+                p.prof[blockIdx.x * 8 + 0] = clock64() - t_begin;
+                p.prof[blockIdx.x * 8 + 1] = w_tma;
+                p.prof[blockIdx.x * 8 + 2] = w_sched;
             }
         }
-    } else if (PAIR && rank != 0) {
-      if (RELAY) {
-        // ======================= peer CTA: relay "my A rows have landed" to the leader =======================
-        for (int j = 0; j < ksteps; ++j) {
-            const int s = j % STAGES;
-            const uint32_t ph = (j / STAGES) & 1;
-            mbar_wait_wd(&full_bar[s], ph, p.err, 5);
+    } else if (warp == 5) {
+      if (PAIR && rank != 0) {
+        if (RELAY) {
+            // ======================= peer CTA: relay "my A rows have landed" to the leader =======================
+            int it = 0;
+            for (int lt = 0;; ++lt) {
+                if (ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err) < 0) break;
+                for (int j = 0; j < ksteps; ++j, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait_wd(&full_bar[s], ph, p.err, 5);
+                    if (lane == 0) {
+                        fence_proxy_async_smem();
+                        mbar_arrive_remote(&peer_bar[s], 0);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+      } else {
+        // ======================= MMA issuer (pair: the leader CTA issues for both) =======================
+        const uint32_t idesc = idesc_f16(PAIR ? 2 * kBM : kBM, BN, 0, 0, p.src_fmt, p.w_fmt);
+        int it = 0;
+        const bool prof = p.prof != nullptr;
+        long long w_full = 0, w_acce = 0, w_ring = 0;
+        int ntiles = 0;
+        for (int lt = 0;; ++lt) {
+            const long long tr0 = clock64();
+            if (ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err) < 0) break;
+            if (prof) w_ring += clock64() - tr0;
+            ++ntiles;
+            const int ab = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1;
+            mbar_wait_prof(&acce_bar[ab], aph ^ 1, p.err, 8, prof ? &w_acce : nullptr);      // the epilogue has drained this accumulator (first use: free)
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(ab * Cfg::ACC_COLS);
+            for (int j = 0; j < ksteps; ++j, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait_prof(&full_bar[s], ph, p.err, 3, prof ? &w_full : nullptr);
+                if (RELAY) {
+                    mbar_wait_wd(&peer_bar[s], ph, p.err, 6);
+                    mbar_wait_wd(&bfull_bar[s], ph, p.err, 7);
+                }
+                fence_proxy_async_smem();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int pass = 0; pass < NPASS; ++pass) {
+                        if ((p.debug & 2) && (j > 0 || pass > 0)) break;
+                        // plane pairs (a, b) in the order {00, 01, 10, 02, 20, 11}: NPASS 1 / 3 / 6 take a prefix
+                        const int pa = (pass == 2 || pass == 5) ? 1 : (pass == 4 ? 2 : 0);
+                        const int pb = (pass == 1 || pass == 5) ? 1 : (pass == 3 ? 2 : 0);
+                        const uint32_t abase = smem_u32(stage_a(s, pa));
+                        const uint32_t bbase = smem_u32(stage_b(s, pb));
+#pragma unroll
+                        for (int kk = 0; kk < kBK / 16; ++kk) {
+                            // K-major, SWIZZLE_64B (layout type 4): 8-row groups are 512 bytes apart; +32 bytes per K=16 slice
+                            const uint64_t ad = smem_desc(abase + kk * 32, 16, 512, 4u);
+                            const uint64_t bd = smem_desc(bbase + kk * 32, 16, 512, 4u);
+                            const uint32_t acc = (j > 0 || pass > 0 || kk > 0) ? 1u : 0u;
+                            if (PAIR) umma_bf16_pair(tmem_d, ad, bd, idesc, acc);
+                            else umma_bf16(tmem_d, ad, bd, idesc, acc);
+                        }
+                    }
+                    if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+                }
+                __syncwarp();
+            }
             if (lane == 0) {
-                fence_proxy_async_smem();
-                mbar_arrive_remote(&peer_bar[s], 0);
+                if (PAIR) umma_commit_pair(&accf_bar[ab]); else umma_commit(&accf_bar[ab]);
             }
             __syncwarp();
+        }
+        if (prof && lane == 0) {
+            p.prof[blockIdx.x * 8 + 3] = w_full;
+            p.prof[blockIdx.x * 8 + 4] = w_acce;
+            p.prof[blockIdx.x * 8 + 5] = w_ring;
+            p.prof[blockIdx.x * 8 + 6] = ntiles;
         }
       }
     } else {
-        // ======================= MMA issuer (pair: the leader CTA issues for both) =======================
-        const uint32_t idesc = idesc_f16(PAIR ? 2 * kBM : kBM, BN, 0, 0, p.src_fmt, p.w_fmt);
-        for (int j = 0; j < ksteps; ++j) {
-            const int s = j % STAGES;
-            const uint32_t ph = (j / STAGES) & 1;
-            mbar_wait_wd(&full_bar[s], ph, p.err, 3);
-            if (RELAY) {
-                mbar_wait_wd(&peer_bar[s], ph, p.err, 6);
-                mbar_wait_wd(&bfull_bar[s], ph, p.err, 7);
-            }
-            fence_proxy_async_smem();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
-            tc_fence_after();
-            if (lane == 0) {
-#pragma unroll
-                for (int pass = 0; pass < NPASS; ++pass) {
-                    if ((p.debug & 2) && (j > 0 || pass > 0)) break;
-                    // plane pairs (a, b) in the order {00, 01, 10, 02, 20, 11}: NPASS 1 / 3 / 6 take a prefix
-                    const int pa = (pass == 2 || pass == 5) ? 1 : (pass == 4 ? 2 : 0);
-                    const int pb = (pass == 1 || pass == 5) ? 1 : (pass == 3 ? 2 : 0);
-                    const uint32_t abase = smem_u32(stage_a(s, pa));
-                    const uint32_t bbase = smem_u32(stage_b(s, pb));
-#pragma unroll
-                    for (int kk = 0; kk < kBK / 16; ++kk) {
-                        // K-major, SWIZZLE_64B (layout type 4): 8-row groups are 512 bytes apart; +32 bytes per K=16 slice
-                        const uint64_t ad = smem_desc(abase + kk * 32, 16, 512, 4u);
-                        const uint64_t bd = smem_desc(bbase + kk * 32, 16, 512, 4u);
-                        const uint32_t acc = (j > 0 || pass > 0 || kk > 0) ? 1u : 0u;
-                        if (PAIR) umma_bf16_pair(tmem_base, ad, bd, idesc, acc);
-                        else umma_bf16(tmem_base, ad, bd, idesc, acc);
-                    }
-                }
-                if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
-            }
-            __syncwarp();
-        }
-        if (lane == 0) {
-            if (PAIR) umma_commit_pair(accum_bar); else umma_commit(accum_bar);
-        }
-        __syncwarp();
-    }
-
-    // ======================= epilogue (warps 0-3) =======================
-    // processed in column groups of EN <= 128 so that the staging tile fits the (now idle) pipeline buffers
-    if (warp < 4) {
+        // ======================= epilogue (warps 0-3), one tile behind the MMA warp =======================
+        // processed in column groups of EN <= 64 through a dedicated staging tile.  The per-element work lives in
+        // epi_group<...>, specialised for the launch kinds of the training step (compact straight-line loops: the generic,
+        // fully run-time-switched form of this code was instruction-fetch bound and slowed the MMA / TMA warps down with it).
         constexpr int EN = Cfg::EN;
-        const int row = warp * 32 + lane;
-        const int t = threadIdx.x;
-        uint8_t* stg = smem;  // the pipeline buffers are free once every MMA has completed
-        // destination pixel of this thread's row, computed once (two integer divisions) instead of per element; it lives
-        // outside the pipeline buffers so that it can be used while the main loop is still running
-        long long* prow_s = reinterpret_cast<long long*>(smem + Cfg::MAIN_BYTES + 512);
-        {
-            const int m = tile_m * kBM + row;
-            long long pr = -1;
-            if (m < p.M) {
-                const int hw = p.Hg * p.Wg;
-                const int n = m / hw;
-                const int rem = m - n * hw;
-                const int y = rem / p.Wg;
-                const int x = rem - y * p.Wg;
-                pr = (static_cast<long long>(n) * p.Hd + (y * p.osy + cls.ooy)) * p.Wd + (x * p.osx + cls.oox);
-            }
-            prow_s[row] = pr;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const float alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
-        constexpr int QPR = EN / 4;  // float4 per staged row
-        const int colq = t % QPR;
-        constexpr int ITERS = (kBM * QPR) / kProducerThreads;
         constexpr int NH = BN / EN;
-        constexpr int IPW = ITERS < 8 ? ITERS : 8;     // iterations per 32-bit word of sign bits (4 bits each)
-        constexpr int WORDS = ITERS / IPW;
-        // lrelu' / relu' need only the SIGN of the stored activation (plane 0).  The signs of every element this thread will
-        // write are fetched NOW -- while the main loop is still running (the epilogue warps are idle with TMA staging) --
-        // eight independent 8-byte loads in flight at a time, and kept as 4 bits per float4: the dependent global load per
-        // element that used to dominate the input-gradient epilogues (ncu: 30 % of all stall samples) is gone.
+        constexpr int WORDS = EpiShape<EN>::WORDS;
+        constexpr int IPW = EpiShape<EN>::IPW;
+        constexpr int QPR = EpiShape<EN>::QPR;
+        const int row = (warp & 3) * 32 + lane;                  // TMEM lane = accumulator row of this thread
+        const int t = egrp ? threadIdx.x - 192 : threadIdx.x;    // index inside the group
+        const int bar_id = 1 + egrp;
+        EpiCtx ctx;
+        ctx.bar_id = bar_id;
+        ctx.p = &p;
+        ctx.stg = stg;
+        ctx.prow_s = prow_s;
+        ctx.abits_s = abits_s;
+        ctx.red = red;
+        ctx.alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
+        ctx.negslope = p.act == 1 ? 0.1f : (p.act == 2 ? 0.f : 1.f);
+        ctx.auxslope = p.aux_mode == 1 ? 0.1f : 0.f;      // derivative on the non-positive side
+        ctx.t = t;
         const bool aux_bits = p.aux != nullptr && p.aux_mode != 3;
-        uint32_t abits[NH][WORDS];
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const int col = tile_n * BN + h * EN + colq * 4;
-#pragma unroll
-            for (int w = 0; w < WORDS; ++w) {
-                uint2 q[IPW];
-#pragma unroll
-                for (int k = 0; k < IPW; ++k) {
-                    const int e = t + (w * IPW + k) * kProducerThreads;
-                    const long long prow = prow_s[e / QPR];
-                    q[k] = make_uint2(0u, 0u);
-                    if (aux_bits && prow >= 0 && col < p.Ncols) {
-                        const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
-                        q[k] = __ldg(reinterpret_cast<const uint2*>(p.aux + arow * p.Cd + col));
-                    }
-                }
-                uint32_t bits = 0;
-#pragma unroll
-                for (int k = 0; k < IPW; ++k) {
-                    // bf16 > 0: sign bit clear and magnitude non-zero
-                    const uint32_t lo0 = q[k].x & 0xFFFFu, hi0 = q[k].x >> 16, lo1 = q[k].y & 0xFFFFu, hi1 = q[k].y >> 16;
-                    const uint32_t b = (lo0 - 1u < 0x7FFFu ? 1u : 0u) | (hi0 - 1u < 0x7FFFu ? 2u : 0u) |
-                                       (lo1 - 1u < 0x7FFFu ? 4u : 0u) | (hi1 - 1u < 0x7FFFu ? 8u : 0u);
-                    bits |= b << (4 * k);
-                }
-                abits[h][w] = bits;
-            }
+        // launch kind -> specialisation (anything else takes the generic path)
+        int kind = 0;
+        if (p.act != 3 && (p.aux == nullptr || aux_bits) && (p.out_mode == 2 || p.dst_npl == 2)) {
+            const int out = p.out_mode == 2 ? 2 : (p.dst_fmt == FMT_BF16 ? 1 : 0);
+            kind = 1 + out + 3 * (aux_bits ? 1 : 0) + 6 * (p.colsum ? 1 : 0);
         }
-        mbar_wait_wd(accum_bar, 0, p.err, 4);
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
+        for (int lt = 0;; ++lt) {
+            const int tile = ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err);
+            if (tile < 0) break;
+            if ((lt & 1) != egrp) continue;                    // the other group's tile
+            const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
+            const GemmClass cls = p.cls[tc.cls_idx];
+            const int ab = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1;
+            // destination pixel of this thread's row, computed once per tile (two integer divisions) instead of per element
+            epi_bar(bar_id);     // every warp of the group is done with the previous tile's prow_s / staging
             {
-                float v[32];
-                if (EN >= 32) {
-#pragma unroll 1
-                    for (int cc = 0; cc < EN / 32; ++cc) {
-                        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + h * EN + cc * 32, v);
-                        tmem_ld_wait();
-                        float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH + cc * 128);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                } else {
-                    tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
-                    tmem_ld_wait();
-                    float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                const int m = tc.tile_m * kBM + row;
+                long long pr = -1;
+                if (m < p.M) {
+                    const int hw = p.Hg * p.Wg;
+                    const int n = m / hw;
+                    const int rem = m - n * hw;
+                    const int y = rem / p.Wg;
+                    const int x = rem - y * p.Wg;
+                    pr = (static_cast<long long>(n) * p.Hd + (y * p.osy + cls.ooy)) * p.Wd + (x * p.osx + cls.oox);
                 }
+                prow_s[row] = pr;
             }
-            tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-
-            const int col = tile_n * BN + h * EN + colq * 4;
-            const bool col_ok = col < p.Ncols;
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
-            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float slope = p.aux_mode == 1 ? 0.1f : 0.f;      // derivative on the non-positive side
-#pragma unroll
-            for (int w = 0; w < WORDS; ++w) {
-              const uint32_t sbits = abits[h][w];
+            epi_bar(bar_id);
+            ctx.col0 = tc.tile_n * BN;
+            ctx.tl = static_cast<long long>(tc.cls_idx) * p.tiles_m + tc.tile_m;
+            // lrelu' / relu' need only the SIGN of the stored activation (plane 0).  The signs of every element this thread will
+            // write are fetched NOW -- before the accumulator is complete -- eight independent 8-byte loads in flight at a time,
+            // and parked in shared memory as 4 bits per float4: no dependent global load per element in the store loop.
+            if (aux_bits) {
+                const int colq = t % QPR;
 #pragma unroll 2
-              for (int k = 0; k < IPW; ++k) {
-                const int it = w * IPW + k;
-                const int e = t + it * kProducerThreads;
-                const int r = e / QPR;
-                const long long prow = prow_s[r];
-                if (prow < 0 || !col_ok || (p.debug & 4)) continue;
-                float4 v = *reinterpret_cast<const float4*>(stg + r * Cfg::PITCH + colq * 16);
-                v.x = apply_act(fmaf(v.x, alpha, bias4.x), p.act);
-                v.y = apply_act(fmaf(v.y, alpha, bias4.y), p.act);
-                v.z = apply_act(fmaf(v.z, alpha, bias4.z), p.act);
-                v.w = apply_act(fmaf(v.w, alpha, bias4.w), p.act);
-                if (aux_bits) {
-                    const uint32_t b = sbits >> (4 * k);
-                    v.x *= (b & 1u) ? 1.f : slope;
-                    v.y *= (b & 2u) ? 1.f : slope;
-                    v.z *= (b & 4u) ? 1.f : slope;
-                    v.w *= (b & 8u) ? 1.f : slope;
-                } else if (p.aux) {
-                    // tanh' = 1 - a^2 needs the value (all planes): only the 3-channel image layer, read in place
-                    const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
-                    const float4 a4 = load_vals4(p.aux, p.aux_plane, p.aux_npl, p.aux_fmt, arow * p.Cd + col);
-                    v.x *= act_grad_from_output(a4.x, 3);
-                    v.y *= act_grad_from_output(a4.y, 3);
-                    v.z *= act_grad_from_output(a4.z, 3);
-                    v.w *= act_grad_from_output(a4.w, 3);
-                }
-                if (p.out_mode == 0) {
-                    note_saturation4(p.sat_flag, p.dst_fmt, v);
-                    store_vals4(static_cast<bf16_t*>(p.dst) + prow * p.Cd + col, p.dst_plane, p.dst_npl, p.dst_fmt, v);
-                } else
-                    *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + prow * p.Cd + col) = v;
-                if (prow < p.colsum_rows) {
-                    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-                    cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
-                    cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
-                }
-              }
-            }
-            if (p.colsum) {
-                float4* red = reinterpret_cast<float4*>(smem + Cfg::STAGING_BYTES);
-                red[t] = cs;
-                red[kProducerThreads + t] = cq;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (t < QPR && col_ok) {
-                    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k = t; k < kProducerThreads; k += QPR) {
-                        const float4 a1 = red[k], a2 = red[kProducerThreads + k];
-                        s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
-                        s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
+                for (int hw_ = 0; hw_ < NH * WORDS; ++hw_) {
+                    const int h = hw_ / WORDS, w = hw_ - h * WORDS;
+                    const int col = ctx.col0 + h * EN + colq * 4;
+                    uint2 q[IPW];
+#pragma unroll
+                    for (int k = 0; k < IPW; ++k) {
+                        const int e = t + (w * IPW + k) * kEpiThreads;
+                        const long long prow = prow_s[e / QPR];
+                        q[k] = make_uint2(0u, 0u);
+                        if (prow >= 0 && col < p.Ncols) {
+                            const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
+                            q[k] = __ldg(reinterpret_cast<const uint2*>(p.aux + arow * p.Cd + col));
+                        }
                     }
-                    const long long tl = static_cast<long long>(cls_idx) * p.tiles_m + tile_m;
-                    *reinterpret_cast<float4*>(p.colsum + tl * p.Ncols + col) = s1;
-                    if (p.colsumsq) *reinterpret_cast<float4*>(p.colsumsq + tl * p.Ncols + col) = s2;
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int k = 0; k < IPW; ++k) {
+                        // bf16 / fp16 > 0: sign bit clear and magnitude non-zero
+                        const uint32_t lo0 = q[k].x & 0xFFFFu, hi0 = q[k].x >> 16, lo1 = q[k].y & 0xFFFFu, hi1 = q[k].y >> 16;
+                        const uint32_t b = (lo0 - 1u < 0x7FFFu ? 1u : 0u) | (hi0 - 1u < 0x7FFFu ? 2u : 0u) |
+                                           (lo1 - 1u < 0x7FFFu ? 4u : 0u) | (hi1 - 1u < 0x7FFFu ? 8u : 0u);
+                        bits |= b << (4 * k);
+                    }
+                    abits_s[hw_ * kEpiThreads + t] = bits;      // read back by the same thread only
                 }
             }
-            if (h + 1 < BN / EN) asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile is reused by the next group
+            if (p.prof != nullptr && t == 0 && egrp == 0) {
+                const long long te0 = clock64();
+                mbar_wait_wd(&accf_bar[ab], aph, p.err, 4);
+                p.prof[blockIdx.x * 8 + 7] += clock64() - te0;
+            } else
+                mbar_wait_wd(&accf_bar[ab], aph, p.err, 4);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(ab * Cfg::ACC_COLS);
+#pragma unroll 1
+            for (int h = 0; h < NH; ++h) {
+                {
+                    float v[32];
+                    if (EN >= 32) {
+#pragma unroll 1
+                        for (int cc = 0; cc < EN / 32; ++cc) {
+                            tmem_ld32(tmem_acc + h * EN + cc * 32, v);
+                            tmem_ld_wait();
+                            float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH + cc * 128);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    } else {
+                        tmem_ld16(tmem_acc, v);
+                        tmem_ld_wait();
+                        float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+                if (h == NH - 1) {
+                    // this warp has read its lanes of the accumulator: hand the buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_leader(&acce_bar[ab]); else mbar_arrive(&acce_bar[ab]);
+                    }
+                }
+                epi_bar(bar_id);
+                switch (kind) {
+                    case 1: epi_group<EN, false, false, 0>(ctx, h); break;     // forward conv -> fp16 planes
+                    case 2: epi_group<EN, false, false, 1>(ctx, h); break;     // -> bf16 planes
+                    case 3: epi_group<EN, false, false, 2>(ctx, h); break;     // -> raw fp32
+                    case 4: epi_group<EN, true, false, 0>(ctx, h); break;
+                    case 5: epi_group<EN, true, false, 1>(ctx, h); break;      // input gradient x activation derivative -> bf16 planes
+                    case 6: epi_group<EN, true, false, 2>(ctx, h); break;
+                    case 7: epi_group<EN, false, true, 0>(ctx, h); break;
+                    case 8: epi_group<EN, false, true, 1>(ctx, h); break;
+                    case 9: epi_group<EN, false, true, 2>(ctx, h); break;      // pre-batch-norm output + sum x, sum x^2
+                    case 10: epi_group<EN, true, true, 0>(ctx, h); break;
+                    case 11: epi_group<EN, true, true, 1>(ctx, h); break;      // input gradient + bias-gradient column sums
+                    case 12: epi_group<EN, true, true, 2>(ctx, h); break;
+                    default: epi_group_generic<EN>(ctx, h); break;
+                }
+                if (h + 1 < NH) epi_bar(bar_id);   // staging tile (and red) are reused by the next group
+            }
         }
     }
     tc_fence_before();
@@ -535,14 +860,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
 }
 
 template <int BN, int NPASS, bool ATMA>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(ATMA ? kThreadsTma : kThreadsGather, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ ConvGemmParams p) {
     conv_gemm_body<BN, NPASS, false, ATMA>(tmB0, tmA0, p);
 }
 
 template <int BN, int NPASS, bool ATMA>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 2)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATMA ? kThreadsTma : kThreadsGather, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmA0,
                       const __grid_constant__ ConvGemmParams p) {
     conv_gemm_body<BN, NPASS, true, ATMA>(tmB0, tmA0, p);
@@ -615,10 +940,36 @@ static bool atma_geometry(const ConvGemmParams& p, int* hb, int* nb) {
     return true;
 }
 
+// ticket counters of the dynamic tile scheduler: one 4-byte slot per launch, handed out round-robin from a per-device pool.
+// A kernel leaves its slot at zero (the last ticket drawn re-arms it), so a slot can be reused by any LATER launch; a CUDA
+// graph keeps the slot its kernel node was captured with.  The pool is far larger than the number of launches that can be
+// in flight at once, so two concurrently running kernels never share a slot.
+static constexpr unsigned kSchedSlots = 1u << 16;
+static unsigned int* sched_slot() {
+    static unsigned int* pool[64] = {};
+    static unsigned seq[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!pool[dev]) {
+        // first use happens on an eager launch (the engine's first step is never captured), so allocating here is legal
+        if (cudaMalloc(&pool[dev], kSchedSlots * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(pool[dev], 0, kSchedSlots * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    }
+    return pool[dev] + (seq[dev]++ % kSchedSlots);
+}
+static int num_sms() {
+    static int n[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!n[dev] && cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 148;
+    return n[dev];
+}
+
 template <int BN, int NPASS, bool PAIR, bool ATMA>
 static int launch_cfg(const ConvGemmParams& p, const uint16_t* w, long long w_plane, long long w_rows, int kpad, int classes, int hb,
                       int nb, cudaStream_t st) {
     using Cfg = GemmCfg<BN, NPASS, PAIR>;
+    constexpr int THREADS = ATMA ? kThreadsTma : kThreadsGather;
     CUtensorMap t0, a0;
     if (make_tmap_planes(&t0, w, w_rows, kpad, kpad, w_plane, Cfg::NPL, kBK, Cfg::BROWS, Cfg::NPL, 2)) return -4;
     if (ATMA) {
@@ -626,21 +977,70 @@ static int launch_cfg(const ConvGemmParams& p, const uint16_t* w, long long w_pl
     } else {
         a0 = t0;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = PAIR ? cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, NPASS, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)
-                             : cudaFuncSetAttribute(conv_gemm_kernel<BN, NPASS, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    static int max_units = 0;      // persistent CTAs (CTA pairs) that are co-resident on the device: one per SM (TPC)
+    if (!max_units) {
+        cudaError_t e;
+        if constexpr (PAIR) e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, NPASS, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        else e = cudaFuncSetAttribute(conv_gemm_kernel<BN, NPASS, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return -4;
-        attr_done = true;
+        const int sms = num_sms();
+        if constexpr (PAIR) {
+            int clusters = 0;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2), 1, 1);
+            cfg.blockDim = dim3(THREADS, 1, 1);
+            cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&clusters, conv_gemm_pair_kernel<BN, NPASS, ATMA>, &cfg) != cudaSuccess || clusters <= 0) {
+                (void)cudaGetLastError();
+                clusters = sms / 2;
+            }
+            max_units = clusters < sms / 2 ? clusters : sms / 2;
+        } else {
+            max_units = sms;
+        }
     }
     ConvGemmParams q = p;
     q.tiles_m = (p.M + kBM - 1) / kBM;
     if (PAIR) q.tiles_m = (q.tiles_m + 1) / 2 * 2;
     q.tiles_n = (p.Ncols + BN - 1) / BN;
     q.classes = classes;
-    dim3 grid(static_cast<unsigned>(q.tiles_m) * q.tiles_n * classes, 1, 1);
-    if (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
-    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
+    q.sched = sched_slot();
+    if (!q.sched) return -4;
+    static int prof_on = -1;
+    if (prof_on < 0) { const char* e = getenv("MMDGAN_PROF"); prof_on = e ? atoi(e) : 0; }
+    static long long* prof_buf = nullptr;
+    q.prof = nullptr;
+    if (prof_on && p.M >= 4096) {
+        if (!prof_buf) cudaMalloc(&prof_buf, 512 * 8 * sizeof(long long));
+        cudaMemsetAsync(prof_buf, 0, 512 * 8 * sizeof(long long), st);
+        q.prof = prof_buf;
+    }
+    const int total = q.tiles_n * classes * (PAIR ? q.tiles_m / 2 : q.tiles_m);
+    const int units = total < max_units ? total : max_units;
+    dim3 grid(static_cast<unsigned>(PAIR ? 2 * units : units), 1, 1);
+    if constexpr (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
+    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
+    if (q.prof) {       // profiling experiment: blocks the host; never on in the product path
+        static long long host[512 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, prof_buf, sizeof(host), cudaMemcpyDeviceToHost);
+        const int nb_ = static_cast<int>(grid.x);
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int lead = 0;
+        for (int b = 0; b < nb_ && b < 512; ++b) {
+            if (PAIR && (b & 1)) { a[0] += 0; continue; }
+            ++lead;
+            for (int k = 0; k < 8; ++k) a[k] += static_cast<double>(host[b * 8 + k]);
+        }
+        fprintf(stderr, "PROF bn=%d npass=%d pair=%d atma=%d stages=%d M=%d N=%d ksteps=%d classes=%d grid=%d tiles/unit=%.2f | cycles/unit: total %.0f tma_wait_empty %.0f sched %.0f | mma_wait_full %.0f mma_wait_acce %.0f mma_ring %.0f | epi0_wait_accf %.0f\n",
+                BN, NPASS, PAIR ? 1 : 0, ATMA ? 1 : 0, Cfg::STAGES, p.M, p.Ncols, p.ksteps, classes, nb_, a[6] / lead, a[0] / lead, a[1] / lead, a[2] / lead,
+                a[3] / lead, a[4] / lead, a[5] / lead, a[7] / lead);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

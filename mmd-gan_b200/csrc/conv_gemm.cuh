@@ -45,7 +45,9 @@ struct ConvGemmParams {
     int out_mode;            // 0: bf16 planes, 2: raw fp32
     unsigned int* err;       // device error flag (watchdog)
     int* sat_flag;           // set to 1 when a value written as fp16 planes saturates (or null)
-    int tiles_m, tiles_n, classes;   // filled by the launcher: grid decomposition (linear block index)
+    int tiles_m, tiles_n, classes;   // filled by the launcher: tile grid (linear tile index = ((tile_m [/ 2]) * classes + class) * tiles_n + tile_n)
+    long long* prof;                 // profiling experiments only (MMDGAN_PROF=1): per-CTA wait-cycle counters, else null
+    unsigned int* sched;             // filled by the launcher: ticket counter of the dynamic tile scheduler (zero between launches)
     int debug;               // profiling experiments only: bit0 = skip the A gather, bit1 = skip the MMAs
     GemmClass cls[4];
 };
