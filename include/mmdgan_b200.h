@@ -11,7 +11,7 @@
  * host copies inside, so every call is CUDA-graph capturable; workspaces are sized by the *_workspace() queries and
  * provided by the caller.
  *
- * Internal GEMM-operand format ("planes"): NHWC, [plane][N*H*W][C] raw bf16 bits, C in {8, 16} or a multiple of 32,
+ * Internal GEMM-operand format ("planes"): NHWC, [plane][N*H*W][C] raw bf16 bits, C in {8, 16, 32} or a multiple of 64,
  * consecutive planes *_plane ELEMENTS apart (a multiple of 8).  An fp32 value x is carried as
  *   p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1):
  * three planes hold the fp32 value (error <= 2^-25 |x|), two planes 16 significand bits.  The tcgen05 kernels multiply

@@ -81,7 +81,7 @@ extern "C" {
 const char* mmdgan_last_error(void) { return g_err; }
 int mmdgan_version(void) { return 200; }
 
-static inline bool chan_ok(int c) { return c == 8 || c == 16 || (c > 0 && (c & 31) == 0); }
+static inline bool chan_ok(int c) { return c == 8 || c == 16 || c == 32 || (c > 0 && (c & 63) == 0); }
 static inline int npl_for(int npass) { return npass == 6 ? 3 : (npass == 3 ? 2 : 1); }
 static inline bool fmt_ok(int fmt, int npl) { return fmt == 0 ? (npl >= 1 && npl <= 3) : ((fmt == 1 || fmt == 2) && npl >= 1 && npl <= 2); }
 
@@ -135,7 +135,7 @@ int mmdgan_pack_weights(const mmdgan_pack_desc* d, void* stream) {
     if (!d || !d->w || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: null pointer");
     if (d->mode < 0 || d->mode > 6) return fail(MMDGAN_EINVAL, "mmdgan_pack_weights: unknown mode %d", d->mode);
     if ((d->fmt != 0 && d->fmt != 2) || !fmt_ok(d->fmt, d->npl) || (d->npl > 1 && d->plane <= 0)) return fail(MMDGAN_ESHAPE, "mmdgan_pack_weights: bad plane layout");
-    if (d->rows_pad <= 0 || d->kpad <= 0 || (d->kpad & 31) || d->classes < 1 || d->classes > 4 || !chan_ok(d->Cs))
+    if (d->rows_pad <= 0 || d->kpad <= 0 || (d->kpad & 63) || d->classes < 1 || d->classes > 4 || !chan_ok(d->Cs))
         return fail(MMDGAN_ESHAPE, "mmdgan_pack_weights: bad padded shape rows_pad=%d kpad=%d classes=%d Cs=%d", d->rows_pad, d->kpad,
                     d->classes, d->Cs);
     mg::PackParams p;
@@ -162,7 +162,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
         return fail(MMDGAN_EINVAL, "mmdgan_gather_gemm: bn must be 16/32/64/128/256");
     if (d->Nimg <= 0 || d->Hs <= 0 || d->Ws <= 0 || !chan_ok(d->Cs) || d->Hg <= 0 || d->Wg <= 0 || d->TH <= 0 || d->TW <= 0)
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad source shape");
-    if (d->kpad <= 0 || (d->kpad & 31) || d->kpad < d->TH * d->TW * d->Cs)
+    if (d->kpad <= 0 || (d->kpad & 63) || d->kpad < d->TH * d->TW * d->Cs)
         return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: kpad %d does not cover %d taps x %d channels", d->kpad, d->TH * d->TW, d->Cs);
     if (d->classes < 1 || d->classes > 4 || d->w_rows <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad class count");
     if (d->Ncols <= 0 || (d->Ncols & 3) || d->Cd < d->Ncols || (d->Cd & 3)) return fail(MMDGAN_ESHAPE, "mmdgan_gather_gemm: bad output columns");
@@ -185,7 +185,7 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     memset(&p, 0, sizeof(p));
     p.src = d->src; p.src_plane = d->src_plane; p.src_fmt = d->src_fmt; p.w_fmt = d->w_fmt; p.Nimg = d->Nimg; p.Hs = d->Hs; p.Ws = d->Ws; p.Cs = d->Cs;
     p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.TH = d->TH; p.TW = d->TW;
-    p.M = static_cast<int>(M); p.ksteps = d->kpad / 32;
+    p.M = static_cast<int>(M); p.ksteps = d->kpad / mg::kGemmBK;
     p.dst = d->dst; p.dst_plane = d->dst_plane; p.dst_npl = d->dst_npl; p.dst_fmt = d->dst_fmt; p.Hd = d->Hd; p.Wd = d->Wd; p.Cd = d->Cd; p.osy = d->osy; p.osx = d->osx;
     p.Ncols = d->Ncols; p.alpha_k = d->alpha_k; p.sigma = d->sigma; p.bias = d->bias; p.act = d->act;
     p.aux = d->aux; p.aux_plane = d->aux_plane; p.aux_npl = d->aux_npl; p.aux_fmt = d->aux_fmt; p.aux_mode = d->aux_mode;

@@ -27,8 +27,12 @@ namespace mg {
 
 static constexpr int kBM = 128;
 static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per block on sm_100
-static constexpr int kBK = 32;         // bf16 elements of K per pipeline stage
-static constexpr int kRowBytes = 64;   // 32 bf16 = one 64-byte swizzle row (SWIZZLE_64B)
+// K per pipeline stage = 64 16-bit elements = one 128-byte swizzle row (SWIZZLE_128B).  With 64-byte rows (SWIZZLE_64B) the
+// tensor core's operand reads of a K = 16 slice (32 bytes of each of 8 rows) hit every shared-memory bank twice: measured
+// ~134 cycles per 256 x 128 x 16 MMA against the 64-cycle floor (role profiling, MMDGAN_PROF=1) -- the N <= 128 layers ran
+// at half rate.  In a 128-byte-swizzled atom the same slice spreads over all 32 banks.
+static constexpr int kBK = kGemmBK;    // 64
+static constexpr int kRowBytes = 128;
 static constexpr int kEpiThreads = 128;       // one epilogue group: warps 0-3 (group 0) / warps 6-9 (group 1); TMEM lane quarter = warp % 4
 static constexpr int kProducerThreads = 128;  // warps 10-13: cp.async gather producers (ATMA = false only)
 static constexpr int kThreadsTma = 320;       // epilogue group 0, TMA, MMA, epilogue group 1
@@ -55,24 +59,12 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, uns
 }
 
 // ---- epilogue building blocks
-template <int EN>
-struct EpiShape {
-    static constexpr int QPR = EN / 4;                              // float4 per staged row
-    static constexpr int ITERS = (kBM * QPR) / kEpiThreads;         // float4 per thread and column group
-    static constexpr int IPW = ITERS < 8 ? ITERS : 8;               // iterations per 32-bit word of sign bits (4 bits each)
-    static constexpr int WORDS = ITERS / IPW;
-    static constexpr int PITCH = EN * 4 + 16;                       // staging row pitch in bytes
-};
-struct EpiCtx {
-    const ConvGemmParams* p;
-    const uint8_t* stg;            // staged accumulator columns [128][PITCH]
-    const long long* prow_s;       // destination pixel of each tile row (-1: beyond M)
-    const uint32_t* abits_s;       // [NH * WORDS][128] sign bits
-    float4* red;                   // [2][128] column-sum scratch
-    float alpha, negslope, auxslope;
-    int col0, t, bar_id;
-    long long tl;                  // tile row of the column-sum workspace
-};
+// The epilogue is ROW-PER-THREAD and register-only: thread (warp % 4) * 32 + lane owns one accumulator row (= one output
+// pixel), pulls 32 columns at a time out of TMEM, applies alpha / bias / activation / activation derivative, converts and
+// writes its 64 (planes) or 128 (fp32) contiguous bytes per chunk straight to global memory.  No staging tile, no named
+// barrier per column group, no shared memory except the 4 x BN column-sum partials.  (The staged form needed ~5 barriers
+// and a serial 4-thread reduction per 32 columns: with MMAs switched off the N <= 128 launches ran no faster -- the
+// epilogue, at ~17 k cycles per 128 x 64 tile, was the bottleneck, not the tensor pipe.)
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 1) return v > 0.f ? v : 0.1f * v;
     if (act == 2) return v > 0.f ? v : 0.f;
@@ -86,138 +78,158 @@ __device__ __forceinline__ float act_grad_from_output(float a, int mode) {
     return 1.f;
 }
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-// per-tile column sums (bias gradients, batch-norm statistics): 128 partial float4 pairs -> QPR threads finish them
-template <int EN>
-__device__ __forceinline__ void epi_colsum(const EpiCtx& c, int col, bool col_ok, float4 cs, float4 cq) {
-    constexpr int QPR = EpiShape<EN>::QPR;
-    const ConvGemmParams& p = *c.p;
-    epi_bar(c.bar_id);                 // the scratch aliases the staging tile: every thread has finished reading its staged values
-    c.red[c.t] = cs;
-    c.red[kEpiThreads + c.t] = cq;
-    epi_bar(c.bar_id);
-    if (c.t < QPR && col_ok) {
-        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = c.t; k < kEpiThreads; k += QPR) {
-            const float4 a1 = c.red[k], a2 = c.red[kEpiThreads + k];
-            s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
-            s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
-        }
-        *reinterpret_cast<float4*>(p.colsum + c.tl * p.Ncols + col) = s1;
-        if (p.colsumsq) *reinterpret_cast<float4*>(p.colsumsq + c.tl * p.Ncols + col) = s2;
-    }
-}
-// One column group of one tile, specialised: act in {linear, lrelu, relu} as max(v,0) + negslope * min(v,0); AUX = multiply by
-// the activation derivative given as sign bits; COLSUM = per-tile column sums; OUT 0 = two fp16 planes of 16 x value
-// (FMT_F16A), 1 = two bf16 planes, 2 = raw fp32.
-template <int EN, bool AUX, bool COLSUM, int OUT>
-__device__ __noinline__ void epi_group(const EpiCtx& c, int h) {
-    using S = EpiShape<EN>;
-    const ConvGemmParams& p = *c.p;
-    const int t = c.t;
-    const int colq = t % S::QPR;
-    const int col = c.col0 + h * EN + colq * 4;
-    const bool col_ok = col < p.Ncols;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
-    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float alpha = c.alpha, neg = c.negslope, aslope = c.auxslope;
-    const int Cd = p.Cd;
-    if (col_ok) {
+
+// Sum over the 32 lanes of a warp of CW = 32 per-lane values, column by column: afterwards lane j holds the total of
+// column j.  Recursive halving: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
-        for (int w = 0; w < S::WORDS; ++w) {
-            const uint32_t sbits = AUX ? c.abits_s[(h * S::WORDS + w) * kEpiThreads + t] : 0u;
-#pragma unroll 4
-            for (int k = 0; k < S::IPW; ++k) {
-                const int r = (t + (w * S::IPW + k) * kEpiThreads) / S::QPR;
-                const long long prow = c.prow_s[r];
-                if (prow < 0) continue;
-                float4 v = *reinterpret_cast<const float4*>(c.stg + r * S::PITCH + colq * 16);
-                v.x = fmaf(v.x, alpha, bias4.x); v.y = fmaf(v.y, alpha, bias4.y);
-                v.z = fmaf(v.z, alpha, bias4.z); v.w = fmaf(v.w, alpha, bias4.w);
-                v.x = fmaf(neg, fminf(v.x, 0.f), fmaxf(v.x, 0.f)); v.y = fmaf(neg, fminf(v.y, 0.f), fmaxf(v.y, 0.f));
-                v.z = fmaf(neg, fminf(v.z, 0.f), fmaxf(v.z, 0.f)); v.w = fmaf(neg, fminf(v.w, 0.f), fmaxf(v.w, 0.f));
-                if (AUX) {
-                    const uint32_t b = sbits >> (4 * k);
-                    v.x *= (b & 1u) ? 1.f : aslope;
-                    v.y *= (b & 2u) ? 1.f : aslope;
-                    v.z *= (b & 4u) ? 1.f : aslope;
-                    v.w *= (b & 8u) ? 1.f : aslope;
-                }
-                const long long off = prow * Cd + col;
-                if (OUT == 0) {
-                    note_saturation4(p.sat_flag, FMT_F16A, v);
-                    store_vals4(static_cast<bf16_t*>(p.dst) + off, p.dst_plane, 2, FMT_F16A, v);
-                } else if (OUT == 1) {
-                    store_planes4(static_cast<bf16_t*>(p.dst) + off, p.dst_plane, 2, v);
-                } else {
-                    *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + off) = v;
-                }
-                if (COLSUM && prow < p.colsum_rows) {
-                    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-                    cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
-                    cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
-                }
-            }
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float keep = hi ? v[i + off] : v[i];
+            const float send = hi ? v[i] : v[i + off];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
     }
-    if (COLSUM) epi_colsum<EN>(c, col, col_ok, cs, cq);
+    return v[0];
 }
-// the generic form: tanh, tanh' (needs the value of the aux activation), three-plane outputs, ...
-template <int EN>
-__device__ __noinline__ void epi_group_generic(const EpiCtx& c, int h) {
-    using S = EpiShape<EN>;
+// CW = 16: lanes j and j + 16 both end with the total of column j
+__device__ __forceinline__ float warp_colsum16(float (&v)[32], int lane) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float keep = hi ? v[i + off] : v[i];
+            const float send = hi ? v[i] : v[i + off];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+struct EpiRow {
+    const ConvGemmParams* p;
+    long long prow;        // destination pixel of this thread's row (-1: beyond M)
+    long long arow;        // row of the aux activation (3B-wrap applied)
+    float alpha, negslope, auxslope;
+    float* part;           // [4 warps][2][BN] column-sum partials of this epilogue group
+    int warp4, lane, bn;
+};
+// One chunk of CW accumulator columns of one row.  OUT 0 = two fp16 planes of 16 x value (FMT_F16A), 1 = two bf16 planes,
+// 2 = raw fp32, 3 = anything else (store_val per element); AUX 0 none, 1 sign bits of plane 0 (lrelu' / relu'), 2 tanh'
+// from the value of the aux activation; GENERIC adds the run-time activation switch (tanh).
+template <int CW, int AUX, bool COLSUM, int OUT, bool GENERIC>
+__device__ __forceinline__ void epi_chunk(const EpiRow& c, float (&v)[32], const uint4 (&araw)[4], int col, int lcol) {
     const ConvGemmParams& p = *c.p;
-    const int t = c.t;
-    const int colq = t % S::QPR;
-    const int col = c.col0 + h * EN + colq * 4;
-    const bool col_ok = col < p.Ncols;
-    const bool aux_bits = p.aux != nullptr && p.aux_mode != 3;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
-    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float alpha = c.alpha, slope = c.auxslope;
-#pragma unroll 1
-    for (int w = 0; w < S::WORDS; ++w) {
-        const uint32_t sbits = aux_bits ? c.abits_s[(h * S::WORDS + w) * kEpiThreads + t] : 0u;
-#pragma unroll 1
-        for (int k = 0; k < S::IPW; ++k) {
-            const int r = (t + (w * S::IPW + k) * kEpiThreads) / S::QPR;
-            const long long prow = c.prow_s[r];
-            if (prow < 0 || !col_ok || (p.debug & 4)) continue;
-            float4 v = *reinterpret_cast<const float4*>(c.stg + r * S::PITCH + colq * 16);
-            v.x = apply_act(fmaf(v.x, alpha, bias4.x), p.act);
-            v.y = apply_act(fmaf(v.y, alpha, bias4.y), p.act);
-            v.z = apply_act(fmaf(v.z, alpha, bias4.z), p.act);
-            v.w = apply_act(fmaf(v.w, alpha, bias4.w), p.act);
-            if (aux_bits) {
-                const uint32_t b = sbits >> (4 * k);
-                v.x *= (b & 1u) ? 1.f : slope;
-                v.y *= (b & 2u) ? 1.f : slope;
-                v.z *= (b & 4u) ? 1.f : slope;
-                v.w *= (b & 8u) ? 1.f : slope;
-            } else if (p.aux) {
-                // tanh' = 1 - a^2 needs the value (all planes): only the 3-channel image layer, read in place
-                const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
-                const float4 a4 = load_vals4(p.aux, p.aux_plane, p.aux_npl, p.aux_fmt, arow * p.Cd + col);
-                v.x *= act_grad_from_output(a4.x, 3);
-                v.y *= act_grad_from_output(a4.y, 3);
-                v.z *= act_grad_from_output(a4.z, 3);
-                v.w *= act_grad_from_output(a4.w, 3);
-            }
-            if (p.out_mode == 0) {
-                note_saturation4(p.sat_flag, p.dst_fmt, v);
-                store_vals4(static_cast<bf16_t*>(p.dst) + prow * p.Cd + col, p.dst_plane, p.dst_npl, p.dst_fmt, v);
-            } else
-                *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + prow * p.Cd + col) = v;
-            if (prow < p.colsum_rows) {
-                cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-                cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
-                cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
-            }
+    const int nvalid = p.Ncols - col;        // > 0, a multiple of 4
+    const bool row_ok = c.prow >= 0;
+    // ---- alpha, bias, activation
+#pragma unroll
+    for (int q = 0; q < CW / 4; ++q) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && q * 4 < nvalid) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + q * 4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x = fmaf(v[q * 4 + e], c.alpha, bb[e]);
+            if (GENERIC) x = apply_act(x, p.act);
+            else x = fmaf(c.negslope, fminf(x, 0.f), fmaxf(x, 0.f));
+            v[q * 4 + e] = x;
         }
     }
-    if (p.colsum) epi_colsum<EN>(c, col, col_ok, cs, cq);
+    // ---- activation derivative
+    if (AUX == 1) {
+        const uint32_t w[16] = {araw[0].x, araw[0].y, araw[0].z, araw[0].w, araw[1].x, araw[1].y, araw[1].z, araw[1].w,
+                                araw[2].x, araw[2].y, araw[2].z, araw[2].w, araw[3].x, araw[3].y, araw[3].z, araw[3].w};
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const uint32_t h = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu);
+            v[j] *= (h - 1u < 0x7FFFu) ? 1.f : c.auxslope;      // 16-bit float > 0: sign clear, magnitude non-zero
+        }
+    } else if (AUX == 2) {
+        if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q)
+                if (q * 4 < nvalid) {
+                    const float4 a4 = load_vals4(p.aux, p.aux_plane, p.aux_npl, p.aux_fmt, c.arow * p.Cd + col + q * 4);
+                    v[q * 4] *= act_grad_from_output(a4.x, 3); v[q * 4 + 1] *= act_grad_from_output(a4.y, 3);
+                    v[q * 4 + 2] *= act_grad_from_output(a4.z, 3); v[q * 4 + 3] *= act_grad_from_output(a4.w, 3);
+                }
+        }
+    }
+    // ---- store this row's CW columns
+    if (row_ok) {
+        const long long off = c.prow * p.Cd + col;
+        if (OUT == 2) {
+            float* d = static_cast<float*>(p.dst) + off;
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q)
+                if (q * 4 < nvalid) *reinterpret_cast<float4*>(d + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else if (OUT == 3) {
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q)
+                if (q * 4 < nvalid) {
+                    const float4 x = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    note_saturation4(p.sat_flag, p.dst_fmt, x);
+                    store_vals4(static_cast<bf16_t*>(p.dst) + off + q * 4, p.dst_plane, p.dst_npl, p.dst_fmt, x);
+                }
+        } else {
+            // two 16-bit planes, 8 elements (16 bytes) per store
+            bf16_t* d0 = static_cast<bf16_t*>(p.dst) + off;
+            bf16_t* d1 = d0 + p.dst_plane;
+            float amax = 0.f;
+#pragma unroll
+            for (int o = 0; o < CW / 8; ++o) {
+                uint32_t w0[4], w1[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float xa = v[o * 8 + 2 * k], xb = v[o * 8 + 2 * k + 1];
+                    uint16_t a0, a1, b0, b1;
+                    if (OUT == 0) {
+                        f16_split2(xa * 16.f, a0, a1);
+                        f16_split2(xb * 16.f, b0, b1);
+                        amax = fmaxf(amax, fmaxf(fabsf(xa), fabsf(xb)));
+                    } else {
+                        a0 = f2bf(xa); a1 = f2bf(xa - bf2f(a0));
+                        b0 = f2bf(xb); b1 = f2bf(xb - bf2f(b0));
+                    }
+                    w0[k] = pack16(a0, b0);
+                    w1[k] = pack16(a1, b1);
+                }
+                if (o * 8 + 4 < nvalid) {
+                    *reinterpret_cast<uint4*>(d0 + o * 8) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+                    *reinterpret_cast<uint4*>(d1 + o * 8) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                } else if (o * 8 < nvalid) {
+                    *reinterpret_cast<uint2*>(d0 + o * 8) = make_uint2(w0[0], w0[1]);
+                    *reinterpret_cast<uint2*>(d1 + o * 8) = make_uint2(w1[0], w1[1]);
+                }
+            }
+            if (OUT == 0 && p.sat_flag != nullptr && amax * 16.f > 65504.f) atomicExch(p.sat_flag, 1);
+        }
+    }
+    // ---- per-tile column sums of the written values (bias gradients, batch-norm statistics)
+    if (COLSUM) {
+        const bool counted = row_ok && c.prow < p.colsum_rows;
+        float sq[32];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            if (!counted) v[j] = 0.f;
+            sq[j] = v[j] * v[j];
+        }
+        const float s1 = CW == 32 ? warp_colsum32(v, c.lane) : warp_colsum16(v, c.lane);
+        float s2 = 0.f;
+        if (p.colsumsq) s2 = CW == 32 ? warp_colsum32(sq, c.lane) : warp_colsum16(sq, c.lane);
+        if (c.lane < CW) {
+            c.part[(c.warp4 * 2 + 0) * c.bn + lcol + c.lane] = s1;
+            c.part[(c.warp4 * 2 + 1) * c.bn + lcol + c.lane] = s2;
+        }
+    }
 }
+
 
 // profiling experiments (MMDGAN_PROF=1): cycles a role spends waiting, per CTA
 __device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned code, long long* acc) {
@@ -244,18 +256,10 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
     static constexpr int ACC_COLS = BN < 32 ? 32 : BN;    // TMEM columns of one accumulator
     static constexpr int TMEM_COLS = 2 * ACC_COLS;        // two accumulators (a power of two >= 64)
-    // epilogue column group: small, because every byte of shared memory that is not a pipeline stage costs operand bytes in
-    // flight (the L2 round trip is ~1.5 us; a stage is consumed every ~0.2 us at the full MMA rate)
-    static constexpr int EN = BN > 32 ? 32 : BN;
-    static constexpr int PITCH = EN * 4 + 16;        // staging row pitch in bytes
-    static constexpr int STAGING_BYTES = kBM * PITCH;
-    static constexpr int RED_BYTES = 2 * kEpiThreads * 16;   // column-sum scratch: ALIASES the staging tile (used after its last read)
-    static_assert(RED_BYTES <= STAGING_BYTES || BN < 32, "column-sum scratch must fit the staging tile");
-    static constexpr int STG_BYTES = STAGING_BYTES > RED_BYTES ? STAGING_BYTES : RED_BYTES;
-    static constexpr int PROW_BYTES = kBM * 8;
-    static constexpr int ABITS_BYTES = (BN / EN) * EpiShape<EN>::WORDS * kEpiThreads * 4;   // activation-derivative sign bits of one tile
+    // Every byte of shared memory that is not a pipeline stage costs operand bytes in flight (the L2 round trip is ~1.5 us; a
+    // stage is consumed in 0.4 - 0.8 us at the full MMA rate): the register-only epilogue needs just the column-sum partials.
+    static constexpr int EPI_BYTES = 4 * 2 * BN * 4 < 1024 ? 1024 : 4 * 2 * BN * 4;   // [4 warps][sum, sum of squares][BN], per epilogue group
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int EPI_BYTES = STG_BYTES + PROW_BYTES + ABITS_BYTES;   // private to one epilogue group
     static constexpr int FIXED_BYTES = 2 * EPI_BYTES + BAR_BYTES;
     static constexpr int STAGES_RAW = (kSmemMax - 1024 /*align slack*/ - FIXED_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > kMaxStages ? kMaxStages : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
@@ -420,10 +424,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
     // two epilogue groups of four warps alternate over the unit's tiles (group g drains accumulator g): every latency of the
     // epilogue (sign prefetch, tcgen05.ld, staging, stores) has two tile times to hide in
     const int egrp = warp >= 6 ? 1 : 0;
-    uint8_t* stg = smem + Cfg::PIPE_BYTES + egrp * Cfg::EPI_BYTES;           // epilogue staging tile of this thread's group
-    float4* red = reinterpret_cast<float4*>(stg);                            // column-sum scratch (aliases the staging tile)
-    long long* prow_s = reinterpret_cast<long long*>(stg + Cfg::STG_BYTES);
-    uint32_t* abits_s = reinterpret_cast<uint32_t*>(stg + Cfg::STG_BYTES + Cfg::PROW_BYTES);
+    float* part = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES + egrp * Cfg::EPI_BYTES);   // column-sum partials of this thread's group
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + 2 * Cfg::EPI_BYTES);
     uint64_t* full_bar = bars;                          // single: A arrivals + B bytes.  pair: this CTA's A arrivals only
     uint64_t* empty_bar = bars + kMaxStages;
@@ -489,13 +490,13 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
       if (!ATMA) {
         // ======================= A producers (gather) =======================
         const int t = threadIdx.x - 320;
-        const int chunk = t & 3;
-        const int rbase = t >> 2;  // rows rbase + 32*i
-        // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte address = (row >> 1) & 3
-        const uint32_t swz_off = static_cast<uint32_t>((chunk ^ ((rbase >> 1) & 3)) << 4);
+        const int chunk = t & 7;   // 16-byte chunk of the 128-byte row
+        const int rbase = t >> 3;  // rows rbase + 16*i
+        // SWIZZLE_128B: 16-byte chunk index ^= bits [7,10) of the byte address = row & 7 (rows rbase + 16*i share it)
+        const uint32_t swz_off = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
         const int HgWg = p.Hg * p.Wg;
-        // K order: (channel chunk of CW = min(Cs, 32), tap, channel within chunk) -- taps innermost, so consecutive
-        // k-steps re-read neighbouring pixels of the SAME 64-byte channel chunk
+        // K order: (channel chunk of CW = min(Cs, 64), tap, channel within chunk) -- taps innermost, so consecutive
+        // k-steps re-read neighbouring pixels of the SAME 128-byte channel chunk
         const int cw4 = (p.Cs >= kBK ? kBK : p.Cs) >> 3;   // 16-byte units (8 bf16) per (chunk, tap) group
         const int ncc = p.Cs / (cw4 * 8);
         const int ntaps = p.TH * p.TW;
@@ -505,10 +506,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             if (tile < 0) break;
             const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
             const GemmClass cls = p.cls[tc.cls_idx];
-            int by[4], bx[4], ib[4];  // by < -30000 marks an invalid row
+            int by[8], bx[8], ib[8];  // by < -30000 marks an invalid row
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int m = tc.tile_m * kBM + rbase + 32 * i;
+            for (int i = 0; i < 8; ++i) {
+                int m = tc.tile_m * kBM + rbase + 16 * i;
                 if (m < p.M) {
                     int n = m / HgWg;
                     int rem = m - n * HgWg;
@@ -527,7 +528,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait_wd(&empty_bar[s], ph ^ 1, p.err, 1);
-                const int u = j * 4 + chunk;
+                const int u = j * 8 + chunk;
                 const int g = u / cw4;
                 const int cc = g / ntaps;
                 const int tap = g - cc * ntaps;
@@ -537,12 +538,12 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 const bool tap_ok = cc < ncc;
                 const uint32_t a0 = smem_u32(stage_a(s, 0)) + swz_off;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const int yy = by[i] + a;
                     const int xx = bx[i] + b;
                     const bool ok = tap_ok && yy >= 0 && yy < p.Hs && xx >= 0 && xx < p.Ws;
                     const long long off = ok ? (static_cast<long long>(ib[i] + yy * p.Ws + xx) * p.Cs + cq * 8) : 0;
-                    const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 32 * i) * kRowBytes);
+                    const uint32_t dsta = a0 + static_cast<uint32_t>((rbase + 16 * i) * kRowBytes);
                     if (p.debug & 1) continue;
 #pragma unroll
                     for (int pl = 0; pl < NPL; ++pl) cp_async16(dsta + pl * Cfg::A_BYTES, p.src + pl * p.src_plane + off, ok ? 16u : 0u);
@@ -680,9 +681,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                         const uint32_t bbase = smem_u32(stage_b(s, pb));
 #pragma unroll
                         for (int kk = 0; kk < kBK / 16; ++kk) {
-                            // K-major, SWIZZLE_64B (layout type 4): 8-row groups are 512 bytes apart; +32 bytes per K=16 slice
-                            const uint64_t ad = smem_desc(abase + kk * 32, 16, 512, 4u);
-                            const uint64_t bd = smem_desc(bbase + kk * 32, 16, 512, 4u);
+                            // K-major, SWIZZLE_128B (layout type 2): 8-row groups are 1024 bytes apart; +32 bytes per K=16 slice
+                            const uint64_t ad = smem_desc(abase + kk * 32, 16, 1024, 2u);
+                            const uint64_t bd = smem_desc(bbase + kk * 32, 16, 1024, 2u);
                             const uint32_t acc = (j > 0 || pass > 0 || kk > 0) ? 1u : 0u;
                             if (PAIR) umma_bf16_pair(tmem_d, ad, bd, idesc, acc);
                             else umma_bf16(tmem_d, ad, bd, idesc, acc);
@@ -705,36 +706,26 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
         }
       }
     } else {
-        // ======================= epilogue (warps 0-3), one tile behind the MMA warp =======================
-        // processed in column groups of EN <= 64 through a dedicated staging tile.  The per-element work lives in
-        // epi_group<...>, specialised for the launch kinds of the training step (compact straight-line loops: the generic,
-        // fully run-time-switched form of this code was instruction-fetch bound and slowed the MMA / TMA warps down with it).
-        constexpr int EN = Cfg::EN;
-        constexpr int NH = BN / EN;
-        constexpr int WORDS = EpiShape<EN>::WORDS;
-        constexpr int IPW = EpiShape<EN>::IPW;
-        constexpr int QPR = EpiShape<EN>::QPR;
-        const int row = (warp & 3) * 32 + lane;                  // TMEM lane = accumulator row of this thread
+        // ======================= epilogue (two groups of four warps), one / two tiles behind the MMA warp =======================
+        constexpr int CW = BN < 32 ? 16 : 32;         // accumulator columns per tcgen05.ld
+        constexpr int NCH = BN < 32 ? 1 : BN / 32;
         const int t = egrp ? threadIdx.x - 192 : threadIdx.x;    // index inside the group
         const int bar_id = 1 + egrp;
-        EpiCtx ctx;
-        ctx.bar_id = bar_id;
-        ctx.p = &p;
-        ctx.stg = stg;
-        ctx.prow_s = prow_s;
-        ctx.abits_s = abits_s;
-        ctx.red = red;
-        ctx.alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
-        ctx.negslope = p.act == 1 ? 0.1f : (p.act == 2 ? 0.f : 1.f);
-        ctx.auxslope = p.aux_mode == 1 ? 0.1f : 0.f;      // derivative on the non-positive side
-        ctx.t = t;
+        EpiRow er;
+        er.p = &p;
+        er.alpha = p.sigma ? p.alpha_k / __ldg(p.sigma) : p.alpha_k;
+        er.negslope = p.act == 1 ? 0.1f : (p.act == 2 ? 0.f : 1.f);
+        er.auxslope = p.aux_mode == 1 ? 0.1f : 0.f;      // derivative on the non-positive side
+        er.part = part;
+        er.warp4 = warp & 3;
+        er.lane = lane;
+        er.bn = BN;
+        const int row = (warp & 3) * 32 + lane;                  // TMEM lane = accumulator row of this thread
         const bool aux_bits = p.aux != nullptr && p.aux_mode != 3;
-        // launch kind -> specialisation (anything else takes the generic path)
-        int kind = 0;
-        if (p.act != 3 && (p.aux == nullptr || aux_bits) && (p.out_mode == 2 || p.dst_npl == 2)) {
-            const int out = p.out_mode == 2 ? 2 : (p.dst_fmt == FMT_BF16 ? 1 : 0);
-            kind = 1 + out + 3 * (aux_bits ? 1 : 0) + 6 * (p.colsum ? 1 : 0);
-        }
+        // launch kind -> specialisation of the per-chunk code (anything unusual takes the generic form)
+        const bool fast = p.act != 3 && (p.aux == nullptr || aux_bits) && (p.out_mode == 2 || p.dst_npl == 2);
+        const int out_kind = p.out_mode == 2 ? 2 : (p.dst_npl == 2 ? (p.dst_fmt == FMT_BF16 ? 1 : (p.dst_fmt == FMT_F16A ? 0 : 3)) : 3);
+        const int kind = (fast && out_kind != 3) ? 1 + out_kind + 3 * (aux_bits ? 1 : 0) + 6 * (p.colsum ? 1 : 0) : 0;
         for (int lt = 0;; ++lt) {
             const int tile = ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err);
             if (tile < 0) break;
@@ -743,8 +734,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             const GemmClass cls = p.cls[tc.cls_idx];
             const int ab = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
-            // destination pixel of this thread's row, computed once per tile (two integer divisions) instead of per element
-            epi_bar(bar_id);     // every warp of the group is done with the previous tile's prow_s / staging
+            // destination pixel of this thread's row
             {
                 const int m = tc.tile_m * kBM + row;
                 long long pr = -1;
@@ -756,43 +746,25 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                     const int x = rem - y * p.Wg;
                     pr = (static_cast<long long>(n) * p.Hd + (y * p.osy + cls.ooy)) * p.Wd + (x * p.osx + cls.oox);
                 }
-                prow_s[row] = pr;
+                er.prow = pr;
+                er.arow = pr >= p.aux_wrap_at ? pr - p.aux_wrap_len : pr;
             }
-            epi_bar(bar_id);
-            ctx.col0 = tc.tile_n * BN;
-            ctx.tl = static_cast<long long>(tc.cls_idx) * p.tiles_m + tc.tile_m;
-            // lrelu' / relu' need only the SIGN of the stored activation (plane 0).  The signs of every element this thread will
-            // write are fetched NOW -- before the accumulator is complete -- eight independent 8-byte loads in flight at a time,
-            // and parked in shared memory as 4 bits per float4: no dependent global load per element in the store loop.
-            if (aux_bits) {
-                const int colq = t % QPR;
-#pragma unroll 2
-                for (int hw_ = 0; hw_ < NH * WORDS; ++hw_) {
-                    const int h = hw_ / WORDS, w = hw_ - h * WORDS;
-                    const int col = ctx.col0 + h * EN + colq * 4;
-                    uint2 q[IPW];
+            const int col0 = tc.tile_n * BN;
+            // lrelu' / relu' need only the SIGN of the stored activation (plane 0): the 2 * CW bytes of this row's next chunk are
+            // fetched one chunk ahead (chunk 0: before the accumulator is complete), so no load is waited for in the store path
+            uint4 anext[4];
+            auto fetch_aux = [&](int ch) {
+                const int col = col0 + ch * CW;
 #pragma unroll
-                    for (int k = 0; k < IPW; ++k) {
-                        const int e = t + (w * IPW + k) * kEpiThreads;
-                        const long long prow = prow_s[e / QPR];
-                        q[k] = make_uint2(0u, 0u);
-                        if (prow >= 0 && col < p.Ncols) {
-                            const long long arow = prow >= p.aux_wrap_at ? prow - p.aux_wrap_len : prow;
-                            q[k] = __ldg(reinterpret_cast<const uint2*>(p.aux + arow * p.Cd + col));
-                        }
-                    }
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int k = 0; k < IPW; ++k) {
-                        // bf16 / fp16 > 0: sign bit clear and magnitude non-zero
-                        const uint32_t lo0 = q[k].x & 0xFFFFu, hi0 = q[k].x >> 16, lo1 = q[k].y & 0xFFFFu, hi1 = q[k].y >> 16;
-                        const uint32_t b = (lo0 - 1u < 0x7FFFu ? 1u : 0u) | (hi0 - 1u < 0x7FFFu ? 2u : 0u) |
-                                           (lo1 - 1u < 0x7FFFu ? 4u : 0u) | (hi1 - 1u < 0x7FFFu ? 8u : 0u);
-                        bits |= b << (4 * k);
-                    }
-                    abits_s[hw_ * kEpiThreads + t] = bits;      // read back by the same thread only
+                for (int k = 0; k < 4; ++k) {
+                    anext[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (k * 8 < CW && er.prow >= 0 && col + k * 8 < p.Ncols)
+                        anext[k] = __ldg(reinterpret_cast<const uint4*>(p.aux + er.arow * p.Cd + col + k * 8));
                 }
-            }
+            };
+#pragma unroll
+            for (int k = 0; k < 4; ++k) anext[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (aux_bits) fetch_aux(0);
             if (p.prof != nullptr && t == 0 && egrp == 0) {
                 const long long te0 = clock64();
                 mbar_wait_wd(&accf_bar[ab], aph, p.err, 4);
@@ -802,27 +774,17 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(ab * Cfg::ACC_COLS);
 #pragma unroll 1
-            for (int h = 0; h < NH; ++h) {
-                {
-                    float v[32];
-                    if (EN >= 32) {
-#pragma unroll 1
-                        for (int cc = 0; cc < EN / 32; ++cc) {
-                            tmem_ld32(tmem_acc + h * EN + cc * 32, v);
-                            tmem_ld_wait();
-                            float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH + cc * 128);
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int col = col0 + ch * CW;
+                uint4 araw[4];
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        }
-                    } else {
-                        tmem_ld16(tmem_acc, v);
-                        tmem_ld_wait();
-                        float4* d = reinterpret_cast<float4*>(stg + row * Cfg::PITCH);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                }
-                if (h == NH - 1) {
+                for (int k = 0; k < 4; ++k) araw[k] = anext[k];
+                if (aux_bits && ch + 1 < NCH && col + CW < p.Ncols) fetch_aux(ch + 1);      // in flight while this chunk is processed
+                float v[32];
+                if (CW == 32) tmem_ld32(tmem_acc + ch * 32, v);
+                else tmem_ld16(tmem_acc, v);
+                tmem_ld_wait();
+                if (ch == NCH - 1) {
                     // this warp has read its lanes of the accumulator: hand the buffer back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -830,23 +792,52 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                         if (PAIR) mbar_arrive_leader(&acce_bar[ab]); else mbar_arrive(&acce_bar[ab]);
                     }
                 }
-                epi_bar(bar_id);
+                if (col >= p.Ncols) continue;            // padding columns of the last N tile (uniform over the group)
+                const int lcol = ch * CW;
                 switch (kind) {
-                    case 1: epi_group<EN, false, false, 0>(ctx, h); break;     // forward conv -> fp16 planes
-                    case 2: epi_group<EN, false, false, 1>(ctx, h); break;     // -> bf16 planes
-                    case 3: epi_group<EN, false, false, 2>(ctx, h); break;     // -> raw fp32
-                    case 4: epi_group<EN, true, false, 0>(ctx, h); break;
-                    case 5: epi_group<EN, true, false, 1>(ctx, h); break;      // input gradient x activation derivative -> bf16 planes
-                    case 6: epi_group<EN, true, false, 2>(ctx, h); break;
-                    case 7: epi_group<EN, false, true, 0>(ctx, h); break;
-                    case 8: epi_group<EN, false, true, 1>(ctx, h); break;
-                    case 9: epi_group<EN, false, true, 2>(ctx, h); break;      // pre-batch-norm output + sum x, sum x^2
-                    case 10: epi_group<EN, true, true, 0>(ctx, h); break;
-                    case 11: epi_group<EN, true, true, 1>(ctx, h); break;      // input gradient + bias-gradient column sums
-                    case 12: epi_group<EN, true, true, 2>(ctx, h); break;
-                    default: epi_group_generic<EN>(ctx, h); break;
+                    case 1: epi_chunk<CW, 0, false, 0, false>(er, v, araw, col, lcol); break;     // forward conv -> fp16 planes
+                    case 2: epi_chunk<CW, 0, false, 1, false>(er, v, araw, col, lcol); break;     // -> bf16 planes
+                    case 3: epi_chunk<CW, 0, false, 2, false>(er, v, araw, col, lcol); break;     // -> raw fp32
+                    case 4: epi_chunk<CW, 1, false, 0, false>(er, v, araw, col, lcol); break;
+                    case 5: epi_chunk<CW, 1, false, 1, false>(er, v, araw, col, lcol); break;     // input gradient x activation derivative
+                    case 6: epi_chunk<CW, 1, false, 2, false>(er, v, araw, col, lcol); break;
+                    case 7: epi_chunk<CW, 0, true, 0, false>(er, v, araw, col, lcol); break;
+                    case 8: epi_chunk<CW, 0, true, 1, false>(er, v, araw, col, lcol); break;
+                    case 9: epi_chunk<CW, 0, true, 2, false>(er, v, araw, col, lcol); break;      // pre-batch-norm output + sum x, sum x^2
+                    case 10: epi_chunk<CW, 1, true, 0, false>(er, v, araw, col, lcol); break;
+                    case 11: epi_chunk<CW, 1, true, 1, false>(er, v, araw, col, lcol); break;     // input gradient + bias-gradient column sums
+                    case 12: epi_chunk<CW, 1, true, 2, false>(er, v, araw, col, lcol); break;
+                    default:
+                        if (p.colsum) {
+                            if (aux_bits) epi_chunk<CW, 1, true, 3, true>(er, v, araw, col, lcol);
+                            else if (p.aux) epi_chunk<CW, 2, true, 3, true>(er, v, araw, col, lcol);
+                            else epi_chunk<CW, 0, true, 3, true>(er, v, araw, col, lcol);
+                        } else {
+                            if (aux_bits) epi_chunk<CW, 1, false, 3, true>(er, v, araw, col, lcol);
+                            else if (p.aux) epi_chunk<CW, 2, false, 3, true>(er, v, araw, col, lcol);
+                            else epi_chunk<CW, 0, false, 3, true>(er, v, araw, col, lcol);
+                        }
+                        break;
                 }
-                if (h + 1 < NH) epi_bar(bar_id);   // staging tile (and red) are reused by the next group
+            }
+            if (p.colsum) {
+                // four per-warp partials per column -> the tile's column sums, fixed order
+                epi_bar(bar_id);
+                const long long tl = static_cast<long long>(tc.cls_idx) * p.tiles_m + tc.tile_m;
+                for (int cc = t; cc < BN; cc += kEpiThreads) {
+                    const int col = col0 + cc;
+                    if (col < p.Ncols) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            s1 += part[(w * 2 + 0) * BN + cc];
+                            s2 += part[(w * 2 + 1) * BN + cc];
+                        }
+                        p.colsum[tl * p.Ncols + col] = s1;
+                        if (p.colsumsq) p.colsumsq[tl * p.Ncols + col] = s2;
+                    }
+                }
+                epi_bar(bar_id);      // the partials are rewritten by the group's next tile
             }
         }
     }
@@ -905,8 +896,8 @@ int make_tmap_planes(CUtensorMap* m, const uint16_t* base, long long rows, long 
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-// 5-D bf16 tensor map over NHWC activation planes: dims {C, W, H, N, planes}; box {32, bw, bh, bn, npl} with traversal
-// strides {1, sx, sy, 1, 1} (the box loads ceil(b/s) elements per strided dimension), 64-byte swizzle, zero OOB fill
+// 5-D bf16 tensor map over NHWC activation planes: dims {C, W, H, N, planes}; box {64, bw, bh, bn, npl} with traversal
+// strides {1, sx, sy, 1, 1} (the box loads ceil(b/s) elements per strided dimension), 128-byte swizzle, zero OOB fill
 static int make_tmap_act(CUtensorMap* m, const uint16_t* base, long long plane_stride_elems, int npl, int C, int W, int H, int N, int bw,
                          int bh, int bn, int sx, int sy) {
     EncodeTiledFn enc = get_encode();
@@ -920,7 +911,7 @@ static int make_tmap_act(CUtensorMap* m, const uint16_t* base, long long plane_s
                          static_cast<cuuint32_t>(npl)};
     cuuint32_t estr[5] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
 }
@@ -971,7 +962,7 @@ static int launch_cfg(const ConvGemmParams& p, const uint16_t* w, long long w_pl
     using Cfg = GemmCfg<BN, NPASS, PAIR>;
     constexpr int THREADS = ATMA ? kThreadsTma : kThreadsGather;
     CUtensorMap t0, a0;
-    if (make_tmap_planes(&t0, w, w_rows, kpad, kpad, w_plane, Cfg::NPL, kBK, Cfg::BROWS, Cfg::NPL, 2)) return -4;
+    if (make_tmap_planes(&t0, w, w_rows, kpad, kpad, w_plane, Cfg::NPL, kBK, Cfg::BROWS, Cfg::NPL, 0)) return -4;
     if (ATMA) {
         if (make_tmap_act(&a0, p.src, p.src_plane, Cfg::NPL, p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy)) return -4;
     } else {

@@ -4,6 +4,10 @@
 
 namespace mg {
 
+// K elements per pipeline stage of the gather-GEMM = width of a channel chunk in its K order (channel chunk, tap, channel):
+// 64 16-bit elements = one 128-byte swizzle row.  The packed weights (pack_value, elementwise.cu) use the same constant.
+static constexpr int kGemmBK = 64;
+
 // One "class" of a gather-GEMM launch (blockIdx.z).  A k4/s2 transposed convolution is four classes, one per output
 // parity; everything else is one class.
 struct GemmClass {

@@ -81,8 +81,8 @@ __device__ __forceinline__ int perm_feature(int j, int C, int HW) {  // internal
 // value of packed element (class cls, row, col) read from the canonical weights
 __device__ __forceinline__ float pack_value(const PackParams& p, int cls, int row, int col) {
     {
-        // K order of the gather-GEMM: (channel chunk of CW = min(Cs, 32), tap, channel within the chunk)
-        const int cw = p.Cs >= 32 ? 32 : p.Cs;
+        // K order of the gather-GEMM: (channel chunk of CW = min(Cs, 64), tap, channel within the chunk)
+        const int cw = p.Cs >= kGemmBK ? kGemmBK : p.Cs;
         const int ntaps = (p.mode == PACK_CONV_DGRAD_S2 || p.mode == PACK_TC_FWD) ? 4 : ((p.mode >= PACK_DENSE_FWD) ? 1 : p.k * p.k);
         const int grp = col / cw;
         const int cc = grp / ntaps;

@@ -21,6 +21,7 @@ ACT = {'linear': 0, None: 0, 'lrelu': 1, 'relu': 2, 'tanh': 3}
 PACK_CONV_FWD, PACK_CONV_DGRAD_S1, PACK_CONV_DGRAD_S2, PACK_TC_FWD, PACK_TC_DGRAD, PACK_DENSE_FWD, PACK_DENSE_DGRAD = range(7)
 
 
+GEMM_BK = 64            # K elements per pipeline stage of the gather-GEMM = channel-chunk width of its K order (csrc/conv_gemm.cuh kGemmBK)
 GEMM_PAIR = True        # use the CTA-pair (cta_group::2) gather-GEMM where the grid is large enough
 GEMM_PAIR_MIN_TILES = int(os.environ.get('MMDGAN_PAIR_MIN_TILES', '256'))   # 128 x 128 output units; below that the single-CTA kernel fills the machine better
 GEMM_BN_MAX = 256    # widest N tile of the gather-GEMM (256 halves the A re-reads of wide layers)
@@ -83,8 +84,8 @@ def fmt_need(fmt, npass):
 
 
 def pad_c(c):
-    """Channel padding of a GEMM operand: 8 or 16 (one 16-byte unit or two), else whole 32-channel chunks."""
-    return 8 if c <= 8 else (16 if c <= 16 else (c + 31) // 32 * 32)
+    """Channel padding of a GEMM operand: 8, 16 or 32 (whole 16-byte units of one 128-byte K row), else whole 64-channel chunks."""
+    return 8 if c <= 8 else (16 if c <= 16 else (32 if c <= 32 else (c + 63) // 64 * 64))
 
 
 def fwd_passes(npass):
@@ -229,7 +230,7 @@ class LinearOp(object):
         for g in (self.f, self.d):
             g['bn'] = pick_bn(g['ncols'])
             g['rows_pad'] = round_up(g['ncols'], g['bn'])
-            g['kpad'] = round_up(g['taps'] * g['Cs'], 32)
+            g['kpad'] = round_up(g['taps'] * g['Cs'], GEMM_BK)
             if g is self.f and npass == 3 and F16_FORWARD:
                 g['w'] = new_planes(g['classes'] * g['rows_pad'], g['kpad'], 2, device, FMT_F16W)
             else:

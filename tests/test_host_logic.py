@@ -81,15 +81,15 @@ def test_linear_op_launch_plans():
     lop = K.LinearOp('c', [64, 32, 32], [3, 32, 32], 3, 1, device='cpu')
     assert lop.Cs_out == 8 and lop.w_swapped and lop.f['bn'] == 16 and lop.wgrad_plan(8)[:3] == (64, 72, 128)
     lop = K.LinearOp('c', [3, 32, 32], [64, 32, 32], 3, 1, device='cpu')
-    assert lop.Cs_in == 8 and not lop.w_swapped and lop.f['kpad'] == 96
+    assert lop.Cs_in == 8 and not lop.w_swapped and lop.f['kpad'] == 128      # 9 taps x 8 channels = 72 -> whole 64-element K blocks
     # operand planes: forward weights as two fp16 planes (three plane-pair products are fp32-grade), input-gradient weights as
     # three bf16 planes (three products for gradients, six when the adjoint acts as a forward operator in the spectral norm)
     assert lop.f['w'].dtype == torch.float16 and lop.f['w'].shape[0] == 2 and lop.d['w'].dtype == torch.bfloat16 and lop.d['w'].shape[0] == 3
     assert (lop.fwd_npass, lop.bwd_npass, lop.adj_npass) == (3, 3, 6)
-    assert [K.pad_c(c) for c in (1, 3, 8, 9, 16, 17, 32, 33, 64, 100)] == [8, 8, 8, 16, 16, 32, 32, 64, 64, 128]
+    assert [K.pad_c(c) for c in (1, 3, 8, 9, 16, 17, 32, 33, 64, 65, 100)] == [8, 8, 8, 16, 16, 32, 32, 64, 64, 128, 128]
     # dense with NCHW-flatten permutation folded into the packed weights
     lop = K.LinearOp('d', [8192], [16], in_flat=(512, 16), device='cpu')
-    assert lop.w_swapped and lop.in_flat == (512, 16) and lop.d['kpad'] == 32
+    assert lop.w_swapped and lop.in_flat == (512, 16) and lop.d['kpad'] == 64
     with pytest.raises(NotImplementedError):
         K.LinearOp('c', [8, 8, 8], [8, 8, 8], 5, 1, device='cpu')
     with pytest.raises(AttributeError):
