@@ -250,12 +250,23 @@ __device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, u
 template <int BN, int NPASS, bool PAIR>
 struct GemmCfg {
     static constexpr int NPL = (NPASS == 6) ? 3 : ((NPASS == 3) ? 2 : 1);   // operand planes staged per k-block
-    static constexpr int BROWS = PAIR ? BN / 2 : BN;      // weight rows staged by this CTA
+    // A tcgen05.mma with both operands in shared memory takes >= ~128 cycles whatever its N (measured 115-133 cycles per MMA
+    // for N = 64, 128 and 256 alike: role profiling, MMDGAN_PROF=1) -- only N = 256 runs at the full rate.  So for BN <= 128
+    // the two weight planes are CONCATENATED along N: one MMA per activation plane, A_a x [B_0 | B_1] with N = 2 BN, writes
+    // the two partial products into adjacent column blocks of the accumulator, and the epilogue adds the blocks.  Two MMAs of
+    // N = 2 BN per K = 16 slice instead of three of N = BN (and all four plane-pair products instead of three).
+    static constexpr bool CAT = NPASS == 3 && BN <= 128;
+    static constexpr int NMMA = CAT ? NPL * BN : BN;      // N of one MMA
+    // weight rows staged by this CTA per plane, and planes: a CAT pair gives each CTA ONE whole plane (CTA r = plane r = columns
+    // [r BN, (r + 1) BN) of the concatenated operand); otherwise a pair splits every plane in halves
+    static constexpr int BROWS = (PAIR && !CAT) ? BN / 2 : BN;
+    static constexpr int BPL = (PAIR && CAT) ? 1 : NPL;   // weight planes staged by this CTA
     static constexpr int A_BYTES = kBM * kRowBytes;       // per plane
-    static constexpr int B_BYTES = BROWS * kRowBytes;
-    static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
-    static constexpr int ACC_COLS = BN < 32 ? 32 : BN;    // TMEM columns of one accumulator
-    static constexpr int TMEM_COLS = 2 * ACC_COLS;        // two accumulators (a power of two >= 64)
+    static constexpr int B_BYTES = BROWS * kRowBytes;     // per plane
+    static constexpr int STAGE_BYTES = NPL * A_BYTES + BPL * B_BYTES;
+    static constexpr int NACC = CAT ? NPL : 1;            // column blocks of width BN the epilogue adds up
+    static constexpr int BUF_COLS = (NACC * BN) < 32 ? 32 : NACC * BN;   // TMEM columns of one tile's accumulator
+    static constexpr int TMEM_COLS = 2 * BUF_COLS;        // double-buffered: a power of two in [64, 512]
     // Every byte of shared memory that is not a pipeline stage costs operand bytes in flight (the L2 round trip is ~1.5 us; a
     // stage is consumed in 0.4 - 0.8 us at the full MMA rate): the register-only epilogue needs just the column-sum partials.
     static constexpr int EPI_BYTES = 4 * 2 * BN * 4 < 1024 ? 1024 : 4 * 2 * BN * 4;   // [4 warps][sum, sum of squares][BN], per epilogue group
@@ -321,6 +332,23 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand from TENSOR MEMORY (128 lanes x 8 columns per K = 16 slice of 16-bit elements), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // completion of all prior MMAs of this thread arrives on the mbarrier at this offset in BOTH CTAs of the pair
@@ -483,7 +511,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
 
     auto stage_a = [&](int s, int pl) -> uint8_t* { return smem + s * Cfg::STAGE_BYTES + pl * Cfg::A_BYTES; };
     auto stage_b = [&](int s, int pl) -> uint8_t* {
-        return smem + s * Cfg::STAGE_BYTES + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+        return smem + s * Cfg::STAGE_BYTES + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;      // pl < Cfg::BPL
     };
 
     if (warp >= 10) {
@@ -591,7 +619,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 if (tile < 0) break;
                 const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
                 const GemmClass cls = p.cls[tc.cls_idx];
-                const int row0 = cls.wrow + tc.tile_n * BN + (PAIR ? static_cast<int>(rank) * Cfg::BROWS : 0);
+                const int row0 = cls.wrow + tc.tile_n * BN + ((PAIR && !Cfg::CAT) ? static_cast<int>(rank) * Cfg::BROWS : 0);
                 // tile origin on the (image, row) grid; with ATMA a tile is a whole number of image rows
                 const int pix0 = tc.tile_m * kBM;
                 const int n0 = pix0 / hw;
@@ -606,12 +634,13 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                     if (PAIR) {
                         // both CTAs load their operand shares; all bytes are credited to the leader's barrier
                         uint64_t* bar = ATMA ? &full_bar[s] : &bfull_bar[s];
-                        if (rank == 0) mbar_arrive_expect_tx(bar, 2 * (NPL * Cfg::B_BYTES + a_bytes));
-                        // the planes are the outermost tensor-map dimension: one box brings all NPL planes of the stage
-                        tma_load_3d_pair(smem_u32(stage_b(s, 0)), &tmB0, bar, j * kBK, row0, 0);
+                        if (rank == 0) mbar_arrive_expect_tx(bar, 2 * (Cfg::BPL * Cfg::B_BYTES + a_bytes));
+                        // the planes are the outermost tensor-map dimension: one box brings all planes this CTA stages
+                        // (CAT: the one plane `rank`, all BN rows; else both planes of this CTA's half of the rows)
+                        tma_load_3d_pair(smem_u32(stage_b(s, 0)), &tmB0, bar, j * kBK, row0, Cfg::CAT ? static_cast<int>(rank) : 0);
                         if (ATMA) tma_load_5d_pair(smem_u32(stage_a(s, 0)), &tmA0, bar, cch, cx, cy, n0, 0);
                     } else {
-                        mbar_arrive_expect_tx(&full_bar[s], NPL * Cfg::B_BYTES + a_bytes);
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::BPL * Cfg::B_BYTES + a_bytes);
                         tma_load_3d(smem_u32(stage_b(s, 0)), &tmB0, &full_bar[s], j * kBK, row0, 0);
                         if (ATMA) tma_load_5d(smem_u32(stage_a(s, 0)), &tmA0, &full_bar[s], cch, cx, cy, n0, 0);
                     }
@@ -645,7 +674,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
         }
       } else {
         // ======================= MMA issuer (pair: the leader CTA issues for both) =======================
-        const uint32_t idesc = idesc_f16(PAIR ? 2 * kBM : kBM, BN, 0, 0, p.src_fmt, p.w_fmt);
+        const uint32_t idesc = idesc_f16(PAIR ? 2 * kBM : kBM, Cfg::NMMA, 0, 0, p.src_fmt, p.w_fmt);
         int it = 0;
         const bool prof = p.prof != nullptr;
         long long w_full = 0, w_acce = 0, w_ring = 0;
@@ -659,7 +688,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             const uint32_t aph = (lt >> 1) & 1;
             mbar_wait_prof(&acce_bar[ab], aph ^ 1, p.err, 8, prof ? &w_acce : nullptr);      // the epilogue has drained this accumulator (first use: free)
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(ab * Cfg::ACC_COLS);
+            const uint32_t tmem_buf = tmem_base + static_cast<uint32_t>(ab * Cfg::BUF_COLS);
             for (int j = 0; j < ksteps; ++j, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -671,22 +700,38 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 fence_proxy_async_smem();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
                 tc_fence_after();
                 if (lane == 0) {
-#pragma unroll
-                    for (int pass = 0; pass < NPASS; ++pass) {
-                        if ((p.debug & 2) && (j > 0 || pass > 0)) break;
-                        // plane pairs (a, b) in the order {00, 01, 10, 02, 20, 11}: NPASS 1 / 3 / 6 take a prefix
-                        const int pa = (pass == 2 || pass == 5) ? 1 : (pass == 4 ? 2 : 0);
-                        const int pb = (pass == 1 || pass == 5) ? 1 : (pass == 3 ? 2 : 0);
-                        const uint32_t abase = smem_u32(stage_a(s, pa));
-                        const uint32_t bbase = smem_u32(stage_b(s, pb));
+                    if (Cfg::CAT) {
+                        // one MMA per activation plane and K = 16 slice: A_a x [B_0 | B_1], N = NPL * BN
 #pragma unroll
                         for (int kk = 0; kk < kBK / 16; ++kk) {
-                            // K-major, SWIZZLE_128B (layout type 2): 8-row groups are 1024 bytes apart; +32 bytes per K=16 slice
-                            const uint64_t ad = smem_desc(abase + kk * 32, 16, 1024, 2u);
-                            const uint64_t bd = smem_desc(bbase + kk * 32, 16, 1024, 2u);
-                            const uint32_t acc = (j > 0 || pass > 0 || kk > 0) ? 1u : 0u;
-                            if (PAIR) umma_bf16_pair(tmem_d, ad, bd, idesc, acc);
-                            else umma_bf16(tmem_d, ad, bd, idesc, acc);
+                            const uint64_t bd = smem_desc(smem_u32(stage_b(s, 0)) + kk * 32, 16, 1024, 2u);
+#pragma unroll
+                            for (int pa = 0; pa < NPL; ++pa) {
+                                if ((p.debug & 2) && (j > 0 || kk > 0 || pa > 0)) break;
+                                const uint64_t ad = smem_desc(smem_u32(stage_a(s, pa)) + kk * 32, 16, 1024, 2u);
+                                const uint32_t acc = (j > 0 || kk > 0 || pa > 0) ? 1u : 0u;
+                                if (PAIR) umma_bf16_pair(tmem_buf, ad, bd, idesc, acc);
+                                else umma_bf16(tmem_buf, ad, bd, idesc, acc);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int pass = 0; pass < NPASS; ++pass) {
+                            if ((p.debug & 2) && (j > 0 || pass > 0)) break;
+                            // plane pairs (a, b) in the order {00, 01, 10, 02, 20, 11}: NPASS 1 / 3 / 6 take a prefix
+                            const int pa = (pass == 2 || pass == 5) ? 1 : (pass == 4 ? 2 : 0);
+                            const int pb = (pass == 1 || pass == 5) ? 1 : (pass == 3 ? 2 : 0);
+                            const uint32_t abase = smem_u32(stage_a(s, pa));
+                            const uint32_t bbase = smem_u32(stage_b(s, pb));
+#pragma unroll
+                            for (int kk = 0; kk < kBK / 16; ++kk) {
+                                // K-major, SWIZZLE_128B (layout type 2): 8-row groups are 1024 bytes apart; +32 bytes per K=16 slice
+                                const uint64_t ad = smem_desc(abase + kk * 32, 16, 1024, 2u);
+                                const uint64_t bd = smem_desc(bbase + kk * 32, 16, 1024, 2u);
+                                const uint32_t acc = (j > 0 || pass > 0 || kk > 0) ? 1u : 0u;
+                                if (PAIR) umma_bf16_pair(tmem_buf, ad, bd, idesc, acc);
+                                else umma_bf16(tmem_buf, ad, bd, idesc, acc);
+                            }
                         }
                     }
                     if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
@@ -772,7 +817,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             } else
                 mbar_wait_wd(&accf_bar[ab], aph, p.err, 4);
             tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(ab * Cfg::ACC_COLS);
+            const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(ab * Cfg::BUF_COLS);
 #pragma unroll 1
             for (int ch = 0; ch < NCH; ++ch) {
                 const int col = col0 + ch * CW;
@@ -783,6 +828,18 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                 float v[32];
                 if (CW == 32) tmem_ld32(tmem_acc + ch * 32, v);
                 else tmem_ld16(tmem_acc, v);
+                if (Cfg::NACC > 1) {
+                    // concatenated weight planes: column block a holds A x B_a; their sum is the result
+#pragma unroll
+                    for (int a = 1; a < Cfg::NACC; ++a) {
+                        float u[32];
+                        if (CW == 32) tmem_ld32(tmem_acc + a * BN + ch * 32, u);
+                        else tmem_ld16(tmem_acc + a * BN, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) v[j] += u[j];
+                    }
+                }
                 tmem_ld_wait();
                 if (ch == NCH - 1) {
                     // this warp has read its lanes of the accumulator: hand the buffer back to the MMA warp
@@ -962,7 +1019,7 @@ static int launch_cfg(const ConvGemmParams& p, const uint16_t* w, long long w_pl
     using Cfg = GemmCfg<BN, NPASS, PAIR>;
     constexpr int THREADS = ATMA ? kThreadsTma : kThreadsGather;
     CUtensorMap t0, a0;
-    if (make_tmap_planes(&t0, w, w_rows, kpad, kpad, w_plane, Cfg::NPL, kBK, Cfg::BROWS, Cfg::NPL, 0)) return -4;
+    if (make_tmap_planes(&t0, w, w_rows, kpad, kpad, w_plane, Cfg::NPL, kBK, Cfg::BROWS, Cfg::BPL, 0)) return -4;
     if (ATMA) {
         if (make_tmap_act(&a0, p.src, p.src_plane, Cfg::NPL, p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy)) return -4;
     } else {
