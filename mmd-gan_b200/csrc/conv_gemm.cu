@@ -592,6 +592,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             long long w_tma = 0, w_sched = 0;
             const long long t_begin = clock64();
             int it = 0;
+            int next_tile = unit;          // scheduler: the ticket of tile lt + 1 is drawn while tile lt is being loaded
             for (int lt = 0;; ++lt) {
                 int tile;
                 if (PAIR && rank != 0) {
@@ -600,15 +601,15 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                     // ---- scheduler: next tile of this unit -> ring (of both CTAs of a pair)
                     const int slot = lt % kRing;
                     mbar_wait_wd(&tile_empty[slot], ((lt / kRing) & 1) ^ 1, p.err, 10);
-                    if (lt == 0) tile = unit;
-                    else {
-                        const long long ts0 = clock64();
-                        const unsigned int ticket = atomicAdd(p.sched, 1u);
-                        if (prof) w_sched += clock64() - ts0 + (ticket & 0);
-                        if (ticket == static_cast<unsigned int>(total - 1)) atomicExch(p.sched, 0u);   // the last draw of the launch re-arms the counter
-                        tile = static_cast<int>(ticket) + nunits;
-                    }
+                    tile = next_tile;
                     if (tile >= total) tile = -1;
+                    else {
+                        // one atomic round trip (~1-2 k cycles) per tile, off the critical path: its result is first looked at
+                        // after this tile's loads have been issued
+                        const unsigned int ticket = atomicAdd(p.sched, 1u);
+                        if (ticket == static_cast<unsigned int>(total - 1)) atomicExch(p.sched, 0u);   // the last draw of the launch re-arms the counter
+                        next_tile = static_cast<int>(ticket) + nunits;
+                    }
                     ring[slot] = tile;
                     if (PAIR) {
                         st_shared_remote_u32(ring + slot, 1, static_cast<uint32_t>(tile));

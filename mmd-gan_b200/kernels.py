@@ -30,9 +30,9 @@ FMT_BF16, FMT_F16A, FMT_F16W = 0, 1, 2
 FMT_SCALE = {FMT_BF16: 1.0, FMT_F16A: 16.0, FMT_F16W: 64.0}
 F16_FORWARD = int(os.environ.get('MMDGAN_F16_FORWARD', '1'))   # parity mode: forward operands as two fp16 planes (3 products) instead of three bf16 planes (6)
 WGRAD_CTAS = int(os.environ.get('MMDGAN_WGRAD_CTAS', '222'))   # CTAs a weight-gradient launch aims for (tiles x split-K slices)
-PAIR_BN256_AUX = int(os.environ.get('MMDGAN_BN256_AUX', '0'))   # experiment knob: 256-wide pair tiles for input gradients with N = 256
+PAIR_BN256_AUX = int(os.environ.get('MMDGAN_BN256_AUX', '1'))   # 256-wide pair tiles for input gradients with N = 256 too (the persistent kernel hides their epilogue: 4.19 -> 4.15 ms)
 PAIR_N64 = int(os.environ.get('MMDGAN_PAIR_N64', '0'))   # CTA-pair tiles for N = 64 layers: measured slower (0.36 vs 0.33 ms), off
-DIRECT_CONV = True     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
+DIRECT_CONV = os.environ.get('MMDGAN_DIRECT_CONV', '1') == '1'     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
 
