@@ -182,9 +182,12 @@ int mmdgan_direct_conv_blocks(int N, int H, int W);
 
 /* out[m][n] = alpha * sum_k a[m][k] * wt[n][k] + bias[n] for N in {4,8,16,32} output columns (the critic's score layer,
  * tf.matmul at layer_func.py:909-911 with 16 outputs): fp32 CUDA-core kernel on the values reassembled from npl planes of
- * the activation a and of the packed forward operand wt */
+ * the activation a and of the packed forward operand wt.  Split over K slices of 1024: `workspace` (caller-owned, at least
+ * mmdgan_dense_small_workspace(rows, K, N) bytes) receives the slice partials, which a second small launch sums in a fixed order. */
 int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int a_fmt, int rows, int K, const mmdgan_bf16* wt,
-                           long long w_plane, int w_fmt, int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream);
+                           long long w_plane, int w_fmt, int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo,
+                           float* workspace, void* stream);
+size_t mmdgan_dense_small_workspace(int rows, int K, int N);
 
 /* Weight gradient: W[r][(t,c)] = sum_p P[p][r] * G[g(p,t)][c] (filter gradients of the ops above and the
  * d(sigma)/dW term of SpectralNorm, GeneralTools/math_func.py:661-672).  out: [splits][Cp][TH*TW*Cs]. */

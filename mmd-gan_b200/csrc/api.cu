@@ -51,8 +51,9 @@ int l_scatter_scores_nvls(const float*, int, int, int, float*, float*, cudaStrea
 int l_allreduce_small_nvls(float*, const float*, int, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
+long long dense_small_workspace(int rows, int K, int N);
 int l_dense_small_fwd(const uint16_t*, long long, int, int, int, int, const uint16_t*, long long, int, int, int, float, const float*, const float*,
-                      float*, int, cudaStream_t);
+                      float*, int, float*, cudaStream_t);
 int l_nan_flag(const float*, int, int*, cudaStream_t);
 }  // namespace mg
 
@@ -418,12 +419,17 @@ int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long m
     return wrap(mg::l_refresh(reinterpret_cast<const mg::RefreshJob*>(jobs_device), njobs, max_elems, S(stream)), "mmdgan_refresh");
 }
 int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int a_fmt, int rows, int K, const mmdgan_bf16* wt,
-                           long long w_plane, int w_fmt, int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, void* stream) {
-    if (!a || !wt || !out) return fail(MMDGAN_EINVAL, "mmdgan_dense_small_fwd: null pointer");
+                           long long w_plane, int w_fmt, int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo,
+                           float* workspace, void* stream) {
+    if (!a || !wt || !out || !workspace) return fail(MMDGAN_EINVAL, "mmdgan_dense_small_fwd: null pointer");
     if (rows <= 0 || K <= 0 || (K & 3) || kpad < K || (kpad & 3) || ldo < N) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad shape");
     if (!fmt_ok(a_fmt, npl) || !fmt_ok(w_fmt, npl) || (npl > 1 && (a_plane <= 0 || w_plane <= 0))) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: bad plane layout");
     if (N != 8 && N != 16 && N != 32) return fail(MMDGAN_ESHAPE, "mmdgan_dense_small_fwd: N must be 8/16/32");
-    return wrap(mg::l_dense_small_fwd(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, N, alpha_k, sigma, bias, out, ldo, S(stream)), "mmdgan_dense_small_fwd");
+    return wrap(mg::l_dense_small_fwd(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, N, alpha_k, sigma, bias, out, ldo, workspace, S(stream)), "mmdgan_dense_small_fwd");
+}
+size_t mmdgan_dense_small_workspace(int rows, int K, int N) {
+    if (rows <= 0 || K <= 0 || N <= 0) return 0;
+    return static_cast<size_t>(mg::dense_small_workspace(rows, K, N));
 }
 
 int mmdgan_adam(float* w, float* m, float* v, const float* g, long long n, float lr, float beta1, float beta2, float eps,

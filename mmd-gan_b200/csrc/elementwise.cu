@@ -136,40 +136,115 @@ __device__ __forceinline__ float pack_value(const PackParams& p, int cls, int ro
         return v;
     }
 }
-// One 32 x 32 tile (rows x K columns) of a packed operand per block iteration, 256 threads.  The canonical layouts are
-// contiguous along the packed ROW index for half of the modes (conv forward, transposed-conv input gradient, dense
-// forward) and along the packed COLUMN index for the others; the tile is read along whichever index is contiguous in
-// the source and written along the columns (contiguous in the destination) through shared memory, so both sides of
-// the repack are coalesced.
-__device__ __forceinline__ void pack_tiles(const PackParams& p, float (*tile)[33]) {
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+// ---- the same mapping split into its column part, its row part and the fetch, so that the integer divisions are done once per
+// tile column / tile row instead of once per element
+__device__ __forceinline__ void pack_col_info(const PackParams& p, int col, int& tap, int& ch) {
+    if (p.mode >= PACK_DENSE_FWD) {
+        const int lim = p.mode == PACK_DENSE_FWD ? p.Cin : p.Cout;
+        tap = col < lim ? 0 : (1 << 20);
+        ch = col < lim ? (p.mode == PACK_DENSE_FWD ? perm_feature(col, p.in_C, p.in_HW) : perm_feature(col, p.out_C, p.out_HW)) : 0;
+        return;
+    }
+    const int cw = p.Cs >= kGemmBK ? kGemmBK : p.Cs;
+    const int ntaps = (p.mode == PACK_CONV_DGRAD_S2 || p.mode == PACK_TC_FWD) ? 4 : p.k * p.k;
+    const int grp = col / cw;
+    const int cc = grp / ntaps;
+    tap = grp - cc * ntaps;
+    ch = cc * cw + (col - grp * cw);
+    const int chlim = (p.mode == PACK_CONV_FWD || p.mode == PACK_TC_FWD) ? p.Cin : p.Cout;
+    if (ch >= p.Cs || ch >= chlim) tap = 1 << 20;   // K padding / channel padding
+}
+// row part: (class, source row index, valid)
+__device__ __forceinline__ void pack_row_info(const PackParams& p, int grow, int& cls, int& row) {
+    cls = grow / p.rows_pad;
+    row = grow - cls * p.rows_pad;
+    const int rlim = (p.mode == PACK_CONV_FWD || p.mode == PACK_TC_FWD || p.mode == PACK_DENSE_FWD) ? p.Cout : p.Cin;
+    if (row >= rlim) { row = -1; return; }
+    if (p.mode == PACK_DENSE_FWD) row = perm_feature(row, p.out_C, p.out_HW);
+    else if (p.mode == PACK_DENSE_DGRAD) row = perm_feature(row, p.in_C, p.in_HW);
+}
+__device__ __forceinline__ float pack_fetch(const PackParams& p, int cls, int row, int tap, int ch) {
+    if (row < 0 || tap >= (1 << 20)) return 0.f;
+    const int ph = cls >> 1, pw = cls & 1;
+    switch (p.mode) {
+        case PACK_CONV_FWD: {
+            const int kh = tap / p.k, kw = tap - kh * p.k;
+            return p.w[((static_cast<long long>(kh) * p.k + kw) * p.Cin + ch) * p.Cout + row];
+        }
+        case PACK_CONV_DGRAD_S1: {
+            const int a = tap / p.k, b = tap - a * p.k;
+            return p.w[((static_cast<long long>(p.k - 1 - a) * p.k + (p.k - 1 - b)) * p.Cin + row) * p.Cout + ch];
+        }
+        case PACK_CONV_DGRAD_S2: {
+            const int a = tap >> 1, b = tap & 1;
+            return p.w[((static_cast<long long>(3 - ph - 2 * a) * 4 + (3 - pw - 2 * b)) * p.Cin + row) * p.Cout + ch];
+        }
+        case PACK_TC_FWD: {
+            const int a = tap >> 1, b = tap & 1;
+            return p.w[((static_cast<long long>(3 - ph - 2 * a) * 4 + (3 - pw - 2 * b)) * p.Cout + row) * p.Cin + ch];
+        }
+        case PACK_TC_DGRAD: {
+            const int kh = tap / p.k, kw = tap - kh * p.k;
+            return p.w[((static_cast<long long>(kh) * p.k + kw) * p.Cout + ch) * p.Cin + row];
+        }
+        case PACK_DENSE_FWD: return p.w[static_cast<long long>(ch) * p.Cout + row];      // ch = permuted input feature, row = permuted output
+        case PACK_DENSE_DGRAD: return p.w[static_cast<long long>(row) * p.Cout + ch];    // row = permuted input feature, ch = permuted output
+    }
+    return 0.f;
+}
+
+// One 32 x 64 tile (rows x K columns = one channel chunk) of a packed operand per block iteration, 256 threads.  The
+// canonical layouts are contiguous along the packed ROW index for half of the modes (conv forward, transposed-conv input
+// gradient, dense forward) and along the packed COLUMN index for the others; the tile is read along whichever index is
+// contiguous in the source and written along the columns (contiguous in the destination) through shared memory -- eight
+// consecutive K elements per thread, one 8-byte store per plane and quadruple -- so both sides of the repack are coalesced.
+struct PackSmem {
+    float tile[32][68];
+    int ctap[64], cch[64], rcls[32], rrow[32];
+};
+__device__ __forceinline__ void pack_tiles(const PackParams& p, PackSmem& sm) {
+    const int t = threadIdx.x;
     const int rows_all = p.rows_pad * p.classes;
-    const int tr = (rows_all + 31) >> 5, tc = (p.kpad + 31) >> 5;
+    const int tr = (rows_all + 31) >> 5, tc = (p.kpad + 63) >> 6;
     const bool row_contig = p.mode == PACK_CONV_FWD || p.mode == PACK_TC_DGRAD || p.mode == PACK_DENSE_FWD;
     for (int tidx = blockIdx.x; tidx < tr * tc; tidx += gridDim.x) {
-        const int r0 = (tidx / tc) << 5, c0 = (tidx % tc) << 5;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            // read: tx runs along the source-contiguous index
-            const int rr = row_contig ? tx : ty + 8 * j, cc = row_contig ? ty + 8 * j : tx;
-            const int grow = r0 + rr, col = c0 + cc;
-            float v = 0.f;
-            if (grow < rows_all && col < p.kpad) v = pack_value(p, grow / p.rows_pad, grow % p.rows_pad, col);
-            tile[rr][cc] = v;
+        const int r0 = (tidx / tc) << 5, c0 = (tidx % tc) << 6;
+        if (t < 64) {
+            int tap = 1 << 20, ch = 0;
+            if (c0 + t < p.kpad) pack_col_info(p, c0 + t, tap, ch);
+            sm.ctap[t] = tap;
+            sm.cch[t] = ch;
+        } else if (t < 96) {
+            int cls = 0, row = -1;
+            if (r0 + t - 64 < rows_all) pack_row_info(p, r0 + t - 64, cls, row);
+            sm.rcls[t - 64] = cls;
+            sm.rrow[t - 64] = row;
         }
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int rr = ty + 8 * j, grow = r0 + rr, col = c0 + tx;
-            if (grow < rows_all && col < p.kpad)
-                store_val(p.out + static_cast<long long>(grow) * p.kpad + col, p.plane, p.npl, p.fmt, tile[rr][tx]);
+        for (int j = 0; j < 8; ++j) {
+            // read: consecutive lanes run along the source-contiguous index
+            const int rr = row_contig ? (t & 31) : (t >> 6) + 4 * j;
+            const int cc = row_contig ? (t >> 5) + 8 * j : (t & 63);
+            sm.tile[rr][cc] = pack_fetch(p, sm.rcls[rr], sm.rrow[rr], sm.ctap[cc], sm.cch[cc]);
+        }
+        __syncthreads();
+        {
+            const int rr = t >> 3, cg = (t & 7) * 8, grow = r0 + rr, col = c0 + cg;
+            if (grow < rows_all && col < p.kpad) {
+                const float4 a = *reinterpret_cast<const float4*>(&sm.tile[rr][cg]);
+                const float4 b = *reinterpret_cast<const float4*>(&sm.tile[rr][cg + 4]);
+                bf16_t* o = p.out + static_cast<long long>(grow) * p.kpad + col;
+                store_vals4(o, p.plane, p.npl, p.fmt, a);
+                store_vals4(o + 4, p.plane, p.npl, p.fmt, b);
+            }
         }
         __syncthreads();
     }
 }
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackParams p) {
-    __shared__ float tile[32][33];
-    pack_tiles(p, tile);
+    __shared__ __align__(16) PackSmem sm;
+    pack_tiles(p, sm);
 }
 
 // out[j'] = src[perm(j')]: canonical per-feature vector (bias / gamma / beta) -> internal NHWC-flatten order
@@ -183,10 +258,10 @@ __global__ void permute_features_kernel(const float* __restrict__ src, float* __
 // One launch refreshes every parameter-derived buffer of a net after an update: weight packing jobs and feature
 // permutation / padding jobs; blockIdx.y selects the job, the jobs live in device memory (built once at start-up).
 __global__ void __launch_bounds__(256) refresh_kernel(const RefreshJob* __restrict__ jobs) {
-    __shared__ float tile[32][33];
+    __shared__ __align__(16) PackSmem sm;
     const RefreshJob& job = jobs[blockIdx.y];
     if (job.kind == 0) {
-        pack_tiles(job.pack, tile);
+        pack_tiles(job.pack, sm);
     } else {
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < job.n; j += gridDim.x * blockDim.x) {
             if (job.inverse) job.dst[perm_feature(j, job.C, job.HW)] = job.src[j];
@@ -195,57 +270,76 @@ __global__ void __launch_bounds__(256) refresh_kernel(const RefreshJob* __restri
     }
 }
 
-// out[m][n] = alpha * sum_k A[m][k] * Wt[n][k] + bias[n] for a handful of output columns (the 16 critic scores):
-// fp32 FFMA on the values reassembled from the bf16 planes, one block per row, warp-shuffle + shared-memory reduction.
-// The tensor-core tile would be 94 % padding here (N = 16 of 128 lanes x 8192 deep on 4 CTAs).
-template <int N, int R>
+// out[m][n] = alpha * sum_k A[m][k] * Wt[n][k] + bias[n] for a handful of output columns (the 16 critic scores): fp32 FFMA on
+// the values reassembled from the 16-bit planes.  The tensor-core tile would be 94 % padding here (N = 16 of 128 lanes x
+// 8192 deep on 4 CTAs).  Split K: block (row group of 128 / N rows, K slice of 1024) -- every thread owns 4 consecutive k, issues
+// all its 8-byte plane loads at once (A: 128 / N rows, W: N rows), forms the 128 partial products of its k quadruple, and the
+// block reduces them with the recursive-halving lane transpose (124 shuffles for 128 values) + one shared-memory pass.  The
+// K-slice partials [slices][rows][N] are summed in a fixed order by dense_small_finish_kernel (deterministic, no atomics).
+// (The first version, one block per row sweeping all of K, re-read the 0.5 MB of weights 512 times and took ~90 us on the
+// critical path between the discriminator forward and the loss.)
+static constexpr int kDsSlice = 1024;
+template <int N>
 __global__ void __launch_bounds__(256) dense_small_fwd_kernel(const bf16_t* __restrict__ a, long long a_plane, int npl, int a_fmt, int rows,
                                                              int K, const bf16_t* __restrict__ wt, long long w_plane, int w_fmt, int kpad,
-                                                             float alpha_k, const float* __restrict__ sigma,
-                                                             const float* __restrict__ bias, float* __restrict__ out, int ldo) {
-    // R rows per block share every weight load (the weights are re-read once per R rows instead of once per row)
-    __shared__ float red[8][R][N];
-    const int row0 = blockIdx.x * R;
-    float acc[R][N];
+                                                             float* __restrict__ partials) {
+    constexpr int kDsRows = 128 / N;               // rows per block: 16 / 8 / 4
+    constexpr int V = kDsRows * N;                 // 128 partial products per thread
+    __shared__ float red[8][V];
+    const int row0 = blockIdx.x * kDsRows;
+    const int slice = blockIdx.y;
+    const int k = slice * kDsSlice + threadIdx.x * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[V];
+    if (k < K) {
+        float4 x[kDsRows];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int n = 0; n < N; ++n) acc[r][n] = 0.f;
-    for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
-        float4 x[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < kDsRows; ++r)
             x[r] = row0 + r < rows ? load_vals4(a, a_plane, npl, a_fmt, static_cast<long long>(row0 + r) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int n = 0; n < N; ++n) {
             const float4 w = load_vals4(wt, w_plane, npl, w_fmt, static_cast<long long>(n) * kpad + k);
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                acc[r][n] = fmaf(x[r].x, w.x, fmaf(x[r].y, w.y, fmaf(x[r].z, w.z, fmaf(x[r].w, w.w, acc[r][n]))));
+            for (int r = 0; r < kDsRows; ++r)
+                acc[r * N + n] = fmaf(x[r].x, w.x, fmaf(x[r].y, w.y, fmaf(x[r].z, w.z, x[r].w * w.w)));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    }
+    // lane transpose-reduce: after the steps lane l holds the warp totals of values [l * V/32, (l + 1) * V/32)
+#pragma unroll
+    for (int off = 16, n = V / 2; off >= 1; off >>= 1, n >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float keep = hi ? acc[i + n] : acc[i];
+            const float send = hi ? acc[i] : acc[i + n];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
     }
+    constexpr int PER = V / 32;
+    // lane l ends up with the block of values whose index has bit pattern (b4 b3 b2 b1 b0) = l in its top five bits
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int n = 0; n < N; ++n)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[r][n] += __shfl_xor_sync(0xffffffffu, acc[r][n], o);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0)
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int n = 0; n < N; ++n) red[warp][r][n] = acc[r][n];
+    for (int i = 0; i < PER; ++i) red[warp][lane * PER + i] = acc[i];
     __syncthreads();
-    if (threadIdx.x < R * N) {
-        const int r = threadIdx.x / N, n = threadIdx.x % N;
-        if (row0 + r < rows) {
-            float s = 0.f;
-            for (int w = 0; w < 8; ++w) s += red[w][r][n];
-            const float alpha = sigma ? alpha_k / __ldg(sigma) : alpha_k;
-            out[static_cast<long long>(row0 + r) * ldo + n] = fmaf(s, alpha, bias ? bias[n] : 0.f);
-        }
+    for (int i = threadIdx.x; i < V; i += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][i];
+        const int r = i / N, n = i - r * N;
+        if (row0 + r < rows) partials[(static_cast<long long>(slice) * rows + row0 + r) * N + n] = s;
     }
+}
+__global__ void dense_small_finish_kernel(const float* __restrict__ partials, int slices, int rows, int N, float alpha_k,
+                                          const float* __restrict__ sigma, const float* __restrict__ bias, float* __restrict__ out, int ldo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * N) return;
+    float s = 0.f;
+    for (int t = 0; t < slices; ++t) s += partials[static_cast<long long>(t) * rows * N + i];
+    const float alpha = sigma ? alpha_k / __ldg(sigma) : alpha_k;
+    const int r = i / N, n = i - r * N;
+    out[static_cast<long long>(r) * ldo + n] = fmaf(s, alpha, bias ? bias[n] : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
@@ -683,16 +777,21 @@ int l_refresh(const RefreshJob* jobs, int njobs, long long max_elems, cudaStream
     refresh_kernel<<<grid, kBS, 0, st>>>(jobs);
     return MG_CHECK_LAUNCH();
 }
+long long dense_small_workspace(int rows, int K, int N) {
+    const long long slices = (K + kDsSlice - 1) / kDsSlice;
+    return slices * rows * N * static_cast<long long>(sizeof(float));
+}
 int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int a_fmt, int rows, int K, const bf16_t* wt, long long w_plane, int w_fmt,
-                      int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, cudaStream_t st) {
-    // four rows per block while that still fills the machine, else one
-    const bool quad = false;    // measured (ncu, 512 rows): four rows per block leaves 128 blocks for 148 SMs and is 2x slower than one row per block
-    const int blocks = quad ? (rows + 3) / 4 : rows;
-    if (N == 16 && quad) dense_small_fwd_kernel<16, 4><<<blocks, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 16) dense_small_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 8) dense_small_fwd_kernel<8, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
-    else if (N == 32) dense_small_fwd_kernel<32, 1><<<rows, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, alpha_k, sigma, bias, out, ldo);
+                      int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo, float* workspace,
+                      cudaStream_t st) {
+    const int slices = (K + kDsSlice - 1) / kDsSlice;
+    const int rpb = 128 / N;
+    const dim3 grid((rows + rpb - 1) / rpb, slices, 1);
+    if (N == 16) dense_small_fwd_kernel<16><<<grid, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, workspace);
+    else if (N == 8) dense_small_fwd_kernel<8><<<grid, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, workspace);
+    else if (N == 32) dense_small_fwd_kernel<32><<<grid, 256, 0, st>>>(a, a_plane, npl, a_fmt, rows, K, wt, w_plane, w_fmt, kpad, workspace);
     else return -1;
+    dense_small_finish_kernel<<<nblocks(static_cast<long long>(rows) * N, 256), 256, 0, st>>>(workspace, slices, rows, N, alpha_k, sigma, bias, out, ldo);
     return MG_CHECK_LAUNCH();
 }
 int l_incr_step(int* step, cudaStream_t st) {

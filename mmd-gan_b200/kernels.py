@@ -187,6 +187,7 @@ class LinearOp(object):
         self.npl = mode_planes(npass)               # planes of the bf16 packed operands
         self._wg_scale = 1.0
         self.sat_flag = None                        # optional int32 device flag: a value written as fp16 planes saturated
+        self._ds_ws = None                          # workspace of the split-K small-N dense kernel
         if op == 'd':
             self.Cin, self.Cout = in_shape[0], out_shape[0]
             self.Hin = self.Win = self.Hout = self.Wout = 1
@@ -400,9 +401,12 @@ class LinearOp(object):
             # a handful of output columns (the critic scores): fp32 CUDA-core kernel instead of a 94 %-padded MMA tile
             _planes(src)
             npl = min(src.shape[0], self.f['w'].shape[0])
+            need = int(lib().mmdgan_dense_small_workspace(nimg, self.Cs_in, self.Cs_out)) // 4
+            if self._ds_ws is None or self._ds_ws.numel() < need:        # K-slice partials; sized on the first (eager) call
+                self._ds_ws = torch.empty(need, dtype=torch.float32, device=src.device)
             check(lib().mmdgan_dense_small_fwd(_ptr(src), plane_stride(src), npl, fmt_of(src), nimg, self.Cs_in, _ptr(self.f['w']),
                                                plane_stride(self.f['w']), fmt_of(self.f['w'], 'w'), self.f['kpad'], self.Cs_out,
-                                               float(alpha_k), _ptr(sigma), _ptr(bias), _ptr(dst), dst.shape[2], stream()))
+                                               float(alpha_k), _ptr(sigma), _ptr(bias), _ptr(dst), dst.shape[2], _ptr(self._ds_ws), stream()))
             return
         if self.direct_f and colsum is None and colsumsq is None and self.w_canon is not None:
             return self._direct(True, src, nimg, dst, sigma, alpha_k, bias, act, None, 0, None, out_mode)
