@@ -230,7 +230,10 @@ def run_ours(args):
     e2.record()
     last = None
     for i in range(args.steps):
-        last = eng.step(*host[i % len(host)])
+        # the training loop's call (Agent.train): this step's batch + the next one, whose H2D copy overlaps this step.  Every
+        # batch is copied from pinned host memory exactly once, inside the timed region
+        nxt = host[(i + 1) % len(host)] if i + 1 < args.steps else None
+        last = eng.step(*host[i % len(host)], prefetch=nxt)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -299,14 +302,22 @@ def run_ours(args):
             Bm = eng.B
             sc = eng.D.layers[-1].a[0]                   # [2B, d] scores of the last step
             sd = eng.D.layers[-1].dz_f32                 # [3B, d] score gradients
-            reps = 200
+            reps, per_graph = 200, 20
             for _ in range(10):
                 eng.mmd(sc[Bm:], sc[:Bm], sd[2 * Bm:], sd[Bm:2 * Bm], sd[:Bm])
             torch.cuda.synchronize(dev)
+            # 20 launches per CUDA graph, 10 replays: the device time of a launch, not the host's ctypes call rate
+            gmm = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.graph(gmm, stream=side):
+                for _ in range(per_graph):
+                    eng.mmd(sc[Bm:], sc[:Bm], sd[2 * Bm:], sd[Bm:2 * Bm], sd[:Bm])
+            gmm.replay()
+            torch.cuda.synchronize(dev)
             m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             m0.record()
-            for _ in range(reps):
-                eng.mmd(sc[Bm:], sc[:Bm], sd[2 * Bm:], sd[Bm:2 * Bm], sd[:Bm])
+            for _ in range(reps // per_graph):
+                gmm.replay()
             m1.record()
             torch.cuda.synchronize(dev)
             us = m0.elapsed_time(m1) * 1e3 / reps
@@ -315,9 +326,9 @@ def run_ours(args):
             gbs = alg_bytes / (us * 1e-6) / 1e9
             mmd_roof = {'kernel': 'mmd_fused_kernel<{}>'.format(dsc), 'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s',
                         'frac': gbs / peaks['hbm'], 'algorithmic_bytes': alg_bytes, 'us_per_launch': us, 'launches_timed': reps,
-                        'note': 'back-to-back launches on one stream (launch latency included); the {} KB of scores are L2-resident here as in '
-                                'the step, where the preceding launch writes them; at this size the kernel is launch/latency bound, not HBM '
-                                'bound (DESIGN.md section 5, profiles/r1v2_mmd_sweep.txt)'.format(alg_bytes // 1024)}
+                        'note': 'back-to-back launches replayed from a CUDA graph (device time per launch, launch latency included); the {} KB '
+                                'of scores are L2-resident here as in the step, where the preceding launch writes them; at this size the '
+                                'kernel is launch/latency bound, not HBM bound (DESIGN.md section 5, profiles/r2_mmd_sweep.txt)'.format(alg_bytes // 1024)}
         except Exception as exc:                         # the extra measurement must never cost the bench line
             mmd_roof = {'error': '{}: {}'.format(type(exc).__name__, exc)}
 

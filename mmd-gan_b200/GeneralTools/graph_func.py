@@ -312,12 +312,15 @@ class Agent(object):
                 FLAGS.print('No ckpt found; variables initialised.', force_print)
         start_time = time.time()
         loss_value = None
+        nxt = batch_fn(0) if max_step > 0 else None
         for step in range(max_step):
-            data_x, code_x = batch_fn(step)
+            data_x, code_x = nxt
+            # the next batch is produced now and its host -> device copy overlaps this step (engine.step(prefetch=...))
+            nxt = batch_fn(step + 1) if step + 1 < max_step else None
             # imbalanced update (graph_func.py:885-886): optimiser i runs when the global step is a multiple of imbalanced_update[i]
             update = (True, True) if self.imbalanced_update is None else \
                 tuple(engine.global_step % int(k) == 0 for k in self.imbalanced_update)
-            loss_value = engine.step(data_x, code_x, check_nan=False, update=update)
+            loss_value = engine.step(data_x, code_x, check_nan=False, update=update, prefetch=nxt)
             # check if model produces nan outcome (graph_func.py:856)
             assert not any(np.isnan(loss_value)), 'Model diverged with loss = {} at step {}'.format(loss_value, step)
             gs = engine.global_step

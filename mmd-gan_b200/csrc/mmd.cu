@@ -6,12 +6,22 @@
 // mmd_g_bounded (1356-1431), mixture_mmd_g (1435-1473), mmd_t / mixture_mmd_t (1087-1184: t-distribution kernels
 // k = exp(-alpha log(d / (alpha beta) + 1))) and the backward pass TF derives from them.
 //
-// One warp owns one score row (a "row task": first the local generated rows, then the local real rows) and sweeps
-// every column of the (gathered) generated and real score matrices, which are staged tile by tile, transposed, in
-// shared memory with float4 coalesced loads.  The gradient of a row needs only that row's kernel values
+// A "row task" is one score row (first the local generated rows, then the local real rows) against every column of the
+// (gathered) generated and real score matrices.  The gradient of a row needs only that row's kernel values
 //   grad_i = (sum_j w_ij) x_i - sum_j w_ij y_j
-// so no B x B matrix is ever written.  Lanes split the columns, warp shuffles reduce, the last block to finish
-// reduces the per-block kernel sums in a fixed order (deterministic) and writes the two losses.
+// so no B x B matrix is ever written.
+//
+// Shape of the launch (round 2; the first version gave one warp a whole row and took ~14-22 us at B = 256, 4x a launch):
+//   * the grid is sized to ONE wave: rows-per-block = ceil(2b / #SMs) rounded up to a power of two (4 at b = 256: 128 blocks of
+//     256 threads), and the 8 / rpb warps of a row split its columns, so every SM works from the first cycle;
+//   * the column tile (256 rows of both matrices) is staged ROW-major with a pitch of D + 4 floats: one thread loads one
+//     score row (four 16-byte loads), keeps its squared norm, and a lane later reads "its" column as D / 4 conflict-free
+//     LDS.128 -- used for the dot product AND the gradient accumulation (the transposed layout of the first version cost
+//     2 D scalar shared-memory loads per pair);
+//   * the 2 D gradient accumulators are reduced across a warp with the recursive-halving lane transpose (2 D - 1 shuffles
+//     instead of 2 D x 5), the six scalars with butterflies, the warps of a row through shared memory;
+//   * the last block sums the per-block kernel sums with 32 lanes per sum (fixed order: deterministic) and writes the losses.
+// Kernel family / bandwidth count are template parameters for the hot case (one Gaussian bandwidth: rep, rmb, mgb).
 //
 // Row-block (multi-GPU) form: the local rows are rows [row0, row0 + b) of the global index space; "diagonal" means
 // equal GLOBAL index and the normalisation uses the global batch.
@@ -21,24 +31,46 @@
 
 namespace mg {
 
-
-static constexpr int kTJ = 128;
+static constexpr int kTJ = 256;          // columns (score rows of the gathered matrices) per shared-memory tile
 static constexpr int kWarps = 8;
+static constexpr int kMmdThreads = kWarps * 32;
 static constexpr float kLog2e = 1.4426950408889634f;
 
-template <int D>
-__global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams p) {
-    extern __shared__ float sm[];
-    constexpr int PITCH = kTJ + 1;
-    float* gT = sm;                    // [D][PITCH]
-    float* rT = gT + D * PITCH;        // [D][PITCH]
-    float* gN = rT + D * PITCH;        // [kTJ]
-    float* rN = gN + kTJ;              // [kTJ]
-    float* wsum = rN + kTJ;            // [kWarps][6]
+// Sum over the lanes of a warp of V per-lane values: afterwards lane l holds the totals of values [l * V / 32, (l + 1) * V / 32)
+// in v[0 .. V / 32) (V >= 32, a power of two).
+template <int V>
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[V], int lane) {
+#pragma unroll
+    for (int off = 16, n = V / 2; off >= 1; off >>= 1, n >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float keep = hi ? v[i + n] : v[i];
+            const float send = hi ? v[i] : v[i + n];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// SIMPLE: Gaussian family with one bandwidth (rep / rmb / mgb)
+template <int D, bool SIMPLE>
+__global__ void __launch_bounds__(kMmdThreads) mmd_fused_kernel(const MmdParams p, const int rpb) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int PITCH = D + 4;                  // floats: 16-byte aligned rows, conflict-free LDS.128 for consecutive rows
+    constexpr int V = 2 * D;                      // gradient accumulators per thread (generator-loss and discriminator-loss sums)
+    constexpr int NR = V + 8;                     // reduced values per row task: V sums, aG, aD, four kernel sums (+2 pad)
+    float* gS = sm;                               // [kTJ][PITCH]
+    float* rS = gS + kTJ * PITCH;                 // [kTJ][PITCH]
+    float* gN = rS + kTJ * PITCH;                 // [kTJ]
+    float* rN = gN + kTJ;                         // [kTJ]
+    float* red = rN + kTJ;                        // [kWarps][NR]
+    float* tot = red + kWarps * NR;               // [rpb <= 8][NR]
     __shared__ bool is_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int task = blockIdx.x * kWarps + warp;
+    const int wpr = kWarps / rpb;                 // warps per row task
+    const int task = blockIdx.x * rpb + warp / wpr;
+    const int sub = warp % wpr;                   // this warp's share of the columns
     const bool active = task < 2 * p.b;
     const bool is_g = task < p.b;
     const int li = is_g ? task : task - p.b;
@@ -51,7 +83,7 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
         const float* xr = (is_g ? p.gen_loc : p.real_loc) + static_cast<long long>(li) * D;
 #pragma unroll
         for (int k = 0; k < D; k += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(xr + k);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + k));
             xi[k] = v.x; xi[k + 1] = v.y; xi[k + 2] = v.z; xi[k + 3] = v.w;
         }
 #pragma unroll
@@ -62,9 +94,9 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
     }
 
     float aG = 0.f, aD = 0.f;
-    float tG[D], tD[D];
+    float tv[V];                                  // [0, D): sum w_G y ; [D, 2D): sum w_D y
 #pragma unroll
-    for (int k = 0; k < D; ++k) { tG[k] = 0.f; tD[k] = 0.f; }
+    for (int k = 0; k < V; ++k) tv[k] = 0.f;
     float s_same_u = 0.f, s_same_b = 0.f, s_gr_u = 0.f, s_gr_b = 0.f;
 
     // the matrix a G-row meets in the "same" sweep is gg (index 0), an R-row meets rr (index 2)
@@ -72,31 +104,25 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
     const float cD_same = p.cD[same_idx], cD_gr = p.cD[1];
     const int bm_same = p.bmode[same_idx], bm_gr = p.bmode[1];
     const float bv_same = p.bval[same_idx], bv_gr = p.bval[1];
+    const float cs0 = p.c_s[0];
 
     for (int j0 = 0; j0 < p.Bg; j0 += kTJ) {
-        __syncthreads();
-        // ---- stage kTJ rows of both matrices, transposed (float4 coalesced global reads)
-        constexpr int QPR = D / 4;
-        for (int e = threadIdx.x; e < 2 * kTJ * QPR; e += blockDim.x) {
-            const int which = e / (kTJ * QPR);
-            const int f = e - which * kTJ * QPR;
-            const int r = f / QPR, q = f - r * QPR;
-            const int j = j0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < p.Bg) v = *reinterpret_cast<const float4*>((which ? p.real_all : p.gen_all) + static_cast<long long>(j) * D + q * 4);
-            float* T = which ? rT : gT;
-            T[(q * 4 + 0) * PITCH + r] = v.x;
-            T[(q * 4 + 1) * PITCH + r] = v.y;
-            T[(q * 4 + 2) * PITCH + r] = v.z;
-            T[(q * 4 + 3) * PITCH + r] = v.w;
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < 2 * kTJ; e += blockDim.x) {
+        if (j0 > 0) __syncthreads();
+        // ---- stage kTJ rows of both matrices: one thread, one row (D / 4 coalesced 16-byte loads), norm on the fly
+        for (int e = threadIdx.x; e < 2 * kTJ; e += kMmdThreads) {
             const int which = e / kTJ, r = e - which * kTJ;
-            const float* T = which ? rT : gT;
+            const int j = j0 + r;
+            float* dst = (which ? rS : gS) + r * PITCH;
             float n = 0.f;
+            if (j < p.Bg) {
+                const float* src = (which ? p.real_all : p.gen_all) + static_cast<long long>(j) * D;
 #pragma unroll
-            for (int k = 0; k < D; ++k) n = fmaf(T[k * PITCH + r], T[k * PITCH + r], n);
+                for (int k = 0; k < D; k += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+                    *reinterpret_cast<float4*>(dst + k) = v;
+                    n = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, n))));
+                }
+            }
             (which ? rN : gN)[r] = n;
         }
         __syncthreads();
@@ -106,7 +132,7 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
         for (int sweep = 0; sweep < 2; ++sweep) {
             // sweep 0: same-set matrix (gg for a G row, rr for an R row); sweep 1: the cross matrix gr
             const bool same = sweep == 0;
-            const float* T = (same == is_g) ? gT : rT;
+            const float* S = (same == is_g) ? gS : rS;
             const float* N = (same == is_g) ? gN : rN;
             const float cDm = same ? cD_same : cD_gr;
             const int bm = same ? bm_same : bm_gr;
@@ -114,13 +140,19 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
             // d(mean)/d(row): the row appears in two ordered pairs of a same-set matrix, once in the cross matrix
             const float mult = same ? 2.0f * c : c;
             const float cG = same ? 1.0f : -2.0f;   // loss_gen = e_gg + e_rr - 2 e_gr
-#pragma unroll 1
-            for (int jj = lane; jj < kTJ; jj += 32) {
-                const int j = j0 + jj;
-                if (j >= p.Bg || j == gi) continue;
+            const int jend = min(kTJ, p.Bg - j0);
+#pragma unroll 2
+            for (int jj = sub * 32 + lane; jj < jend; jj += wpr * 32) {
+                if (j0 + jj == gi) continue;
+                float y[D];
+#pragma unroll
+                for (int k = 0; k < D; k += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(S + jj * PITCH + k);
+                    y[k] = v.x; y[k + 1] = v.y; y[k + 2] = v.z; y[k + 3] = v.w;
+                }
                 float dot = 0.f;
 #pragma unroll
-                for (int k = 0; k < D; ++k) dot = fmaf(xi[k], T[k * PITCH + jj], dot);
+                for (int k = 0; k < D; ++k) dot = fmaf(xi[k], y[k], dot);
                 const float raw = ni - 2.0f * dot + N[jj];
                 const float dist = fmaxf(raw, 0.0f);
                 const float m0 = raw >= 0.0f ? 1.0f : 0.0f;       // tf.maximum passes the gradient on ties
@@ -128,21 +160,28 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
                 if (bm == 1) { distb = fmaxf(dist, bv); mb = dist >= bv ? 1.0f : 0.0f; }
                 else if (bm == 2) { distb = fminf(dist, bv); mb = dist <= bv ? 1.0f : 0.0f; }
                 float ku = 0.f, kb = 0.f, dku = 0.f, dkb = 0.f;   // kernel sums and -(dK/dd) sums over sigma
-                for (int s = 0; s < p.n_sigma; ++s) {
-                    const float cs = p.c_s[s];
-                    if (p.family == 0) {                 // Gaussian: k = exp(-cs d), -dk/dd = cs k
-                        const float eu = exp2f(-dist * cs * kLog2e);
-                        const float eb = (bm == 0) ? eu : exp2f(-distb * cs * kLog2e);
-                        ku += eu; kb += eb;
-                        dku = fmaf(cs, eu, dku);
-                        dkb = fmaf(cs, eb, dkb);
-                    } else {                             // t: k = u^-alpha with u = 1 + d / (alpha beta), -dk/dd = k / (beta u)
-                        const float uu = fmaf(dist, p.c_t[s], 1.0f), ub = fmaf(distb, p.c_t[s], 1.0f);
-                        const float eu = exp2f(-cs * log2f(uu));
-                        const float eb = (bm == 0) ? eu : exp2f(-cs * log2f(ub));
-                        ku += eu; kb += eb;
-                        dku = fmaf(eu, p.inv_beta / uu, dku);
-                        dkb = fmaf(eb, p.inv_beta / ub, dkb);
+                if (SIMPLE) {
+                    ku = exp2f(-dist * cs0 * kLog2e);
+                    kb = (bm == 0) ? ku : exp2f(-distb * cs0 * kLog2e);
+                    dku = cs0 * ku;
+                    dkb = cs0 * kb;
+                } else {
+                    for (int s = 0; s < p.n_sigma; ++s) {
+                        const float cs = p.c_s[s];
+                        if (p.family == 0) {                 // Gaussian: k = exp(-cs d), -dk/dd = cs k
+                            const float eu = exp2f(-dist * cs * kLog2e);
+                            const float eb = (bm == 0) ? eu : exp2f(-distb * cs * kLog2e);
+                            ku += eu; kb += eb;
+                            dku = fmaf(cs, eu, dku);
+                            dkb = fmaf(cs, eb, dkb);
+                        } else {                             // t: k = u^-alpha with u = 1 + d / (alpha beta), -dk/dd = k / (beta u)
+                            const float uu = fmaf(dist, p.c_t[s], 1.0f), ub = fmaf(distb, p.c_t[s], 1.0f);
+                            const float eu = exp2f(-cs * log2f(uu));
+                            const float eb = (bm == 0) ? eu : exp2f(-cs * log2f(ub));
+                            ku += eu; kb += eb;
+                            dku = fmaf(eu, p.inv_beta / uu, dku);
+                            dkb = fmaf(eb, p.inv_beta / ub, dkb);
+                        }
                     }
                 }
                 // d dist / d x_i = 2 (x_i - y_j);  dK/dd = -dk
@@ -151,9 +190,8 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
                 aG += wG; aD += wD;
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    const float y = T[k * PITCH + jj];
-                    tG[k] = fmaf(wG, y, tG[k]);
-                    tD[k] = fmaf(wD, y, tD[k]);
+                    tv[k] = fmaf(wG, y[k], tv[k]);
+                    tv[D + k] = fmaf(wD, y[k], tv[D + k]);
                 }
                 if (same) { s_same_u += ku; s_same_b += kb; }
                 else if (is_g) { s_gr_u += ku; s_gr_b += kb; }
@@ -161,7 +199,7 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
         }
     }
 
-    // ---- warp reductions
+    // ---- warp reductions: lane transpose for the 2 D gradient sums, butterflies for the six scalars
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         aG += __shfl_xor_sync(0xffffffffu, aG, o);
@@ -170,37 +208,71 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
         s_same_b += __shfl_xor_sync(0xffffffffu, s_same_b, o);
         s_gr_u += __shfl_xor_sync(0xffffffffu, s_gr_u, o);
         s_gr_b += __shfl_xor_sync(0xffffffffu, s_gr_b, o);
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            tG[k] += __shfl_xor_sync(0xffffffffu, tG[k], o);
-            tD[k] += __shfl_xor_sync(0xffffffffu, tD[k], o);
-        }
     }
-    if (active && lane == 0) {
-        float* og = is_g ? p.dLg_dgen : p.dLg_dreal;
-        float* od = is_g ? p.dLd_dgen : p.dLd_dreal;
+    float* rw = red + warp * NR;
+    if (V >= 32) {
+        warp_transpose_sum<V>(tv, lane);
+        constexpr int PER = V / 32 > 0 ? V / 32 : 1;
 #pragma unroll
-        for (int k = 0; k < D; k += 4) {
-            if (og) *reinterpret_cast<float4*>(og + static_cast<long long>(li) * D + k) =
-                make_float4(aG * xi[k] - tG[k], aG * xi[k + 1] - tG[k + 1], aG * xi[k + 2] - tG[k + 2], aG * xi[k + 3] - tG[k + 3]);
-            if (od) *reinterpret_cast<float4*>(od + static_cast<long long>(li) * D + k) =
-                make_float4(aD * xi[k] - tD[k], aD * xi[k + 1] - tD[k + 1], aD * xi[k + 2] - tD[k + 2], aD * xi[k + 3] - tD[k + 3]);
+        for (int i = 0; i < PER; ++i) rw[lane * PER + i] = tv[i];
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tv[k] += __shfl_xor_sync(0xffffffffu, tv[k], o);
         }
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < V; ++k) rw[k] = tv[k];
     }
     if (lane == 0) {
-        float* w = wsum + warp * 6;
-        // order: gg_u, gr_u, rr_u, gg_b, gr_b, rr_b
-        w[0] = (active && is_g) ? s_same_u : 0.f;
-        w[1] = (active && is_g) ? s_gr_u : 0.f;
-        w[2] = (active && !is_g) ? s_same_u : 0.f;
-        w[3] = (active && is_g) ? s_same_b : 0.f;
-        w[4] = (active && is_g) ? s_gr_b : 0.f;
-        w[5] = (active && !is_g) ? s_same_b : 0.f;
+        rw[V] = aG; rw[V + 1] = aD;
+        // order: gg_u, gr_u, rr_u (unbounded) / gg_b, gr_b, rr_b are assembled per row below
+        rw[V + 2] = s_same_u; rw[V + 3] = s_same_b; rw[V + 4] = s_gr_u; rw[V + 5] = s_gr_b;
     }
     __syncthreads();
+    // ---- the warps of a row task -> one total per value
+    for (int e = threadIdx.x; e < rpb * NR; e += kMmdThreads) {
+        const int r = e / NR, k = e - r * NR;
+        float s = 0.f;
+        for (int w = 0; w < wpr; ++w) s += red[(r * wpr + w) * NR + k];
+        tot[e] = s;
+    }
+    __syncthreads();
+    // ---- gradients of the block's rows: grad = a x_i - sum w y
+    for (int e = threadIdx.x; e < rpb * V; e += kMmdThreads) {
+        const int r = e / V, k = e - r * V;
+        const int tk = blockIdx.x * rpb + r;
+        if (tk >= 2 * p.b) continue;
+        const bool g_row = tk < p.b;
+        const int row = g_row ? tk : tk - p.b;
+        const bool dpart = k >= D;
+        const int kk = dpart ? k - D : k;
+        float* out = dpart ? (g_row ? p.dLd_dgen : p.dLd_dreal) : (g_row ? p.dLg_dgen : p.dLg_dreal);
+        if (out == nullptr) continue;
+        const float x = __ldg((g_row ? p.gen_loc : p.real_loc) + static_cast<long long>(row) * D + kk);
+        const float a = tot[r * NR + V + (dpart ? 1 : 0)];
+        out[static_cast<long long>(row) * D + kk] = a * x - tot[r * NR + k];
+    }
+    // ---- kernel sums of the block (order: gg_u, gr_u, rr_u, gg_b, gr_b, rr_b)
     if (threadIdx.x < 6) {
         float s = 0.f;
-        for (int w = 0; w < kWarps; ++w) s += wsum[w * 6 + threadIdx.x];
+        for (int r = 0; r < rpb; ++r) {
+            const int tk = blockIdx.x * rpb + r;
+            if (tk >= 2 * p.b) continue;
+            const bool g_row = tk < p.b;
+            const float* t = tot + r * NR + V + 2;      // same_u, same_b, gr_u, gr_b
+            float v = 0.f;
+            switch (threadIdx.x) {
+                case 0: v = g_row ? t[0] : 0.f; break;
+                case 1: v = g_row ? t[2] : 0.f; break;
+                case 2: v = g_row ? 0.f : t[0]; break;
+                case 3: v = g_row ? t[1] : 0.f; break;
+                case 4: v = g_row ? t[3] : 0.f; break;
+                default: v = g_row ? 0.f : t[1]; break;
+            }
+            s += v;
+        }
         p.partials[blockIdx.x * 6 + threadIdx.x] = s;
     }
     __threadfence();
@@ -212,36 +284,58 @@ __global__ void __launch_bounds__(kWarps * 32) mmd_fused_kernel(const MmdParams 
     __syncthreads();
     if (is_last) {
         __threadfence();
-        if (threadIdx.x < 6) {
+        // six sums over gridDim.x blocks: warp w < 6 owns sum w, its lanes stride over the blocks (fixed order)
+        if (warp < 6) {
             float s = 0.f;
-            for (unsigned int blk = 0; blk < gridDim.x; ++blk) s += __ldcg(p.partials + blk * 6 + threadIdx.x);
-            wsum[threadIdx.x] = s * c;
-            p.sums[threadIdx.x] = s * c;
+            for (unsigned int blk = lane; blk < gridDim.x; blk += 32) s += __ldcg(p.partials + blk * 6 + warp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                red[warp] = s * c;
+                p.sums[warp] = s * c;
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            p.losses[0] = wsum[0] + wsum[2] - 2.0f * wsum[1];
-            p.losses[1] = p.cD[0] * wsum[3] + p.cD[1] * wsum[4] + p.cD[2] * wsum[5];
+            p.losses[0] = red[0] + red[2] - 2.0f * red[1];
+            p.losses[1] = p.cD[0] * red[3] + p.cD[1] * red[4] + p.cD[2] * red[5];
             *p.counter = 0u;
         }
     }
 }
 
+// rows per block: one wave on the device (<= #SMs blocks) as long as that needs <= 8 rows per block, a power of two so that the
+// eight warps divide evenly
+static int mmd_rows_per_block(int b) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int rpb = 1;
+    while (rpb < 8 && (2 * b + rpb - 1) / rpb > sms) rpb *= 2;
+    return rpb;
+}
+
 template <int D>
 static int launch_mmd_d(const MmdParams& p, cudaStream_t st) {
-    const size_t smem = (2 * D * (kTJ + 1) + 2 * kTJ + kWarps * 6) * sizeof(float);
+    const size_t smem = (2 * kTJ * (D + 4) + 2 * kTJ + kWarps * (2 * D + 8) + 8 * (2 * D + 8)) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done && smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(mmd_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        if (cudaFuncSetAttribute(mmd_fused_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(mmd_fused_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
             return -4;
         attr_done = true;
     }
-    const int grid = (2 * p.b + kWarps - 1) / kWarps;
-    mmd_fused_kernel<D><<<grid, kWarps * 32, smem, st>>>(p);
+    const int rpb = mmd_rows_per_block(p.b);
+    const int grid = (2 * p.b + rpb - 1) / rpb;
+    if (p.family == 0 && p.n_sigma == 1) mmd_fused_kernel<D, true><<<grid, kMmdThreads, smem, st>>>(p, rpb);
+    else mmd_fused_kernel<D, false><<<grid, kMmdThreads, smem, st>>>(p, rpb);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
-int mmd_grid_blocks(int b) { return (2 * b + kWarps - 1) / kWarps; }
+// upper bound of the grid over every rows-per-block choice (workspace sizing: 6 floats per block)
+int mmd_grid_blocks(int b) { return 2 * b; }
 
 int launch_mmd(const MmdParams& p, cudaStream_t st) {
     switch (p.d) {

@@ -374,6 +374,13 @@ class SNGanEngine(object):
         self._pin_sat = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._dev_data = torch.empty_like(self._pin_data, device=self.device)
         self._dev_code = torch.empty_like(self._pin_code, device=self.device)
+        # host -> device prefetch of the NEXT batch (step(..., prefetch=...)): copy stream + two staging buffers
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage_bufs = [(torch.empty_like(self._dev_data), torch.empty_like(self._dev_code)) for _ in range(2)]
+        self._pin_bufs = [(torch.empty_like(self._pin_data).pin_memory(), torch.empty_like(self._pin_code).pin_memory()) for _ in range(2)]
+        self._prefetched = None                  # (data tensor, code tensor, buffer index, event) of the batch in flight
+        self._slot_free = [None, None]           # event: the last device-to-device read of a staging slot
+        self._stage_next = 0
         self.kernel_launches_per_step = None
 
     # -------------------------------------------------------------------------------------------- buffers
@@ -803,14 +810,53 @@ class SNGanEngine(object):
         self._dev_data.copy_(data_x, non_blocking=True)
         self._dev_code.copy_(code_x, non_blocking=True)
 
-    def step(self, data_x, code_x, check_nan=True, update=(True, True)):
-        """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis]."""
-        if not (data_x.is_pinned() and code_x.is_pinned()):      # pageable host memory: stage through pinned buffers
-            self._pin_data.copy_(data_x)
-            self._pin_code.copy_(code_x)
-            data_x, code_x = self._pin_data, self._pin_code
-        self.stage(data_x, code_x)
+    def prefetch(self, data_x, code_x):
+        """Start the host -> device copy of a FUTURE batch on the copy stream (it overlaps the step that is running); the
+        step() call that is later given the same two tensors picks the staged copy up instead of copying again."""
+        k = self._stage_next
+        self._stage_next ^= 1
+        dd, dc = self._stage_bufs[k]
+        if not (data_x.is_pinned() and code_x.is_pinned()):      # pageable host memory: through this slot's pinned buffers
+            pd, pc = self._pin_bufs[k]
+            pd.copy_(data_x)
+            pc.copy_(code_x)
+            src_d, src_c = pd, pc
+        else:
+            src_d, src_c = data_x, code_x
+        ev = torch.cuda.Event()
+        # the staging slot was last read by the device-to-device copy of two steps ago: wait for THAT copy only (waiting for the
+        # compute stream would put the transfer behind the step it is meant to overlap)
+        if self._slot_free[k] is not None:
+            self._copy_stream.wait_event(self._slot_free[k])
+        with torch.cuda.stream(self._copy_stream):
+            dd.copy_(src_d, non_blocking=True)
+            dc.copy_(src_c, non_blocking=True)
+            ev.record(self._copy_stream)
+        self._prefetched = (data_x, code_x, k, ev)
+
+    def step(self, data_x, code_x, check_nan=True, update=(True, True), prefetch=None):
+        """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis].
+        prefetch = (next_data, next_code): the host -> device copy of the NEXT step's batch is started right after this step has
+        been enqueued, so that it overlaps the step instead of preceding the next one (the copy is still made once per step)."""
+        pf = self._prefetched
+        if pf is not None and pf[0] is data_x and pf[1] is code_x:
+            self._prefetched = None
+            dd, dc = self._stage_bufs[pf[2]]
+            torch.cuda.current_stream(self.device).wait_event(pf[3])
+            self._dev_data.copy_(dd, non_blocking=True)          # device-to-device, ~2 us
+            self._dev_code.copy_(dc, non_blocking=True)
+            self._slot_free[pf[2]] = torch.cuda.Event()
+            self._slot_free[pf[2]].record(torch.cuda.current_stream(self.device))
+        else:
+            self._prefetched = None
+            if not (data_x.is_pinned() and code_x.is_pinned()):      # pageable host memory: stage through pinned buffers
+                self._pin_data.copy_(data_x)
+                self._pin_code.copy_(code_x)
+                data_x, code_x = self._pin_data, self._pin_code
+            self.stage(data_x, code_x)
         self.step_device(update)
+        if prefetch is not None:
+            self.prefetch(prefetch[0], prefetch[1])
         self._pin_loss.copy_(self.mmd.losses, non_blocking=True)
         self._pin_sat.copy_(self.sat_flag, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

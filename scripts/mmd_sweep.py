@@ -23,16 +23,23 @@ for loss in ('rep', 'rmb'):
             real = (torch.randn(B, d, generator=g) * 0.35 + 0.1).to(dev)
             mk = K.MmdKernel(loss, (0.0, -1.0), b=B)
             out = [torch.zeros(B, d, device=dev) for _ in range(3)]
-            n = 200 if B <= 4096 else 20
+            per, reps = (20, 10) if B <= 4096 else (4, 5)
             for _ in range(5):
                 mk(gen, real, out[0], out[1], out[2])
             torch.cuda.synchronize()
+            # launches replayed from a CUDA graph: device time per launch, not the host's call rate
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=torch.cuda.Stream()):
+                for _ in range(per):
+                    mk(gen, real, out[0], out[1], out[2])
+            graph.replay()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(n):
-                mk(gen, real, out[0], out[1], out[2])
+            for _ in range(reps):
+                graph.replay()
             e1.record()
             torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / n
+            us = e0.elapsed_time(e1) * 1e3 / (per * reps)
             gbs = 20.0 * B * d / (us * 1e-6) / 1e9
             print('%-5s %6d %4d %10.2f %12.2f %10.5f %14.2f' % (loss, B, d, us, gbs, gbs / peak, 3.0 * B * B / (us * 1e-6) / 1e9))
