@@ -285,6 +285,9 @@ typedef struct mmdgan_mmd_desc {
  * returns MMDGAN_EINVAL for unknown types or w0 - w1 != 1 (the reference's assert, math_func.py:1340) */
 int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, float w1);
 size_t mmdgan_mmd_workspace(int b);
+/* data-parallel step: the two losses from the six GLOBAL kernel sums (after their all-reduce):
+ * loss_gen = e_gg + e_rr - 2 e_gr (math_func.py:1342), loss_dis = cD0 e_gg^b + cD1 e_gr^b + cD2 e_rr^b (math_func.py:1421) */
+int mmdgan_losses_from_sums(const float* sums, float cD0, float cD1, float cD2, float* losses, void* stream);
 int mmdgan_mmd_fwd_bwd(const mmdgan_mmd_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

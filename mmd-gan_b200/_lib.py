@@ -110,6 +110,7 @@ SYMBOLS = {
     'mmdgan_refresh': (_I, [_P, _I, _LL, _P]),
     'mmdgan_dense_small_fwd': (_I, [_P, _LL, _I, _I, _I, _I, _P, _LL, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P]),
     'mmdgan_dense_small_workspace': (C.c_size_t, [_I, _I, _I]),
+    'mmdgan_losses_from_sums': (_I, [_P, _F, _F, _F, _P, _P]),
     'mmdgan_direct_conv': (_I, [C.POINTER(DirectDesc), _P]),
     'mmdgan_direct_conv_blocks': (_I, [_I, _I, _I]),
     'mmdgan_gather_gemm': (_I, [C.POINTER(GemmDesc), _P]),

@@ -50,6 +50,7 @@ int l_adam_allreduce_nvls(const float*, const float*, const float*, const float*
 int l_scatter_scores_nvls(const float*, int, int, int, float*, float*, cudaStream_t);
 int l_allreduce_small_nvls(float*, const float*, int, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
+int l_losses_from_sums(const float*, float, float, float, float*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
 long long dense_small_workspace(int rows, int K, int N);
 int l_dense_small_fwd(const uint16_t*, long long, int, int, int, int, const uint16_t*, long long, int, int, int, float, const float*, const float*,
@@ -373,6 +374,10 @@ int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, fl
         return MMDGAN_OK;
     }
     return fail(MMDGAN_EINVAL, "Not implemented.");  /* math_func.py:2651 */
+}
+int mmdgan_losses_from_sums(const float* sums, float cD0, float cD1, float cD2, float* losses, void* stream) {
+    if (!sums || !losses) return fail(MMDGAN_EINVAL, "mmdgan_losses_from_sums: null pointer");
+    return wrap(mg::l_losses_from_sums(sums, cD0, cD1, cD2, losses, S(stream)), "mmdgan_losses_from_sums");
 }
 size_t mmdgan_mmd_workspace(int b) {
     if (b <= 0) return 0;

@@ -794,6 +794,14 @@ int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int a_fmt, in
     dense_small_finish_kernel<<<nblocks(static_cast<long long>(rows) * N, 256), 256, 0, st>>>(workspace, slices, rows, N, alpha_k, sigma, bias, out, ldo);
     return MG_CHECK_LAUNCH();
 }
+__global__ void losses_from_sums_kernel(const float* __restrict__ sums, float c0, float c1, float c2, float* __restrict__ losses) {
+    losses[0] = sums[0] + sums[2] - 2.0f * sums[1];
+    losses[1] = c0 * sums[3] + c1 * sums[4] + c2 * sums[5];
+}
+int l_losses_from_sums(const float* sums, float c0, float c1, float c2, float* losses, cudaStream_t st) {
+    losses_from_sums_kernel<<<1, 1, 0, st>>>(sums, c0, c1, c2, losses);
+    return MG_CHECK_LAUNCH();
+}
 int l_incr_step(int* step, cudaStream_t st) {
     incr_step_kernel<<<1, 1, 0, st>>>(step);
     return MG_CHECK_LAUNCH();

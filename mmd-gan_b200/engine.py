@@ -106,7 +106,10 @@ class NetRuntime(object):
             self.w, self.g, self.m, self.v = self.flat.w, self.flat.g, self.flat.m, self.flat.v
         else:
             self.w = torch.zeros(off, dtype=torch.float32, device=device)
-            self.g = torch.zeros(off, dtype=torch.float32, device=device)
+            # ALIGN spare floats behind the gradients: the generator's tail carries the six MMD kernel sums, so that the data-parallel
+            # step reduces them in the SAME all-reduce as the gradients (the optimiser only ever sees the first n_flat entries)
+            self.g_all = torch.zeros(off + ALIGN, dtype=torch.float32, device=device)
+            self.g = self.g_all[:off]
             self.m = torch.zeros(off, dtype=torch.float32, device=device)
             self.v = torch.zeros(off, dtype=torch.float32, device=device)
         for name, t in inits.items():
@@ -347,6 +350,9 @@ class SNGanEngine(object):
         self.D = NetRuntime(self.Dis, 2 * B, 3 * B, self.npass, self.device, gen, flat_alloc)
         self._alloc_buffers()
         self.mmd = K.MmdKernel(loss_type, self.rep_weights, b=B, device=self.device)
+        if world_size > 1 and not self.nvls:
+            self.mmd.sums = self.G.g_all[self.G.n_flat:self.G.n_flat + 6]      # reduced together with the generator's gradients
+        self._comm_work = None
         self.global_step = 0
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         # set by any producer whose value does not fit the fp16 forward planes (|activation| >= 4094): reported by step()
@@ -565,10 +571,12 @@ class SNGanEngine(object):
         else:
             lop.wgrad_reduce(L.wg_parts, L.wg_splits, nimg, gview)
 
-    def _phase_backward(self):
+    def _phase_backward(self, part='all'):
         """Input-gradient chain on the main stream; everything that only FINALISES gradients (weight-gradient GEMMs, split-K
         reductions, the spectral-norm combine, bias / batch-norm parameter reductions) is forked onto one in-order side
-        stream and joined before the optimiser, so the ~100 small launches overlap the GEMM chain instead of serialising it."""
+        stream and joined before the optimiser, so the ~100 small launches overlap the GEMM chain instead of serialising it.
+        part = 'dis' / 'gen': the data-parallel step captures the discriminator half and the generator half as separate graphs,
+        so that the all-reduce of the discriminator's gradients runs while the generator's are still being computed."""
         B, HW = self.B, self.height * self.width
         D, G = self.D, self.G
         main = torch.cuda.current_stream(self.device)
@@ -589,13 +597,13 @@ class SNGanEngine(object):
 
         # ================= discriminator: loss_dis -> D variables (rows [0,2B)), loss_gen -> dx_fake (rows [2B,3B))
         last = D.layers[-1]
-        if last.has_bias:
+        if part != 'gen' and last.has_bias:
             def last_bias():
                 K.colsum_small(last.dz_f32, 2 * B, last.Cs_out, self.tmp_vec)
                 c, hw = D._feat_perm(last)
                 K.permute_features(self.tmp_vec, D.view(D.g, last.ly.bias_name), last.Cout, c, hw, inverse=True)
             pending.append(last_bias)
-        for i in range(len(D.layers) - 1, -1, -1):
+        for i in (range(len(D.layers) - 1, -1, -1) if part != 'gen' else ()):
             L = D.layers[i]
             x_in = D.layers[i - 1].a if i > 0 else self.x_all
             pending.append(lambda L=L, x_in=x_in: self._weight_grad(D, L, x_in, L.dz, 2 * B))
@@ -621,7 +629,14 @@ class SNGanEngine(object):
         # refresh then run on the update stream WHILE the generator's backward pass proceeds (nothing below reads a
         # discriminator weight).  Multi-GPU: the update has to wait for the gradient all-reduce, so it stays in _phase_update.
         self._dis_updated = False
-        if side is not main and self.world_size == 1 and self.update_mask[0]:
+        if part == 'dis':
+            flush()
+            if side is not main:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
+            return
+        if side is not main and self.world_size == 1 and self.update_mask[0] and part == 'all':
             flush()
             ev_side, ev_main = torch.cuda.Event(), torch.cuda.Event()
             ev_side.record(side)
@@ -689,7 +704,16 @@ class SNGanEngine(object):
             ev.record(side)
             main.wait_event(ev)
 
-    def _phase_update(self):
+    def _phase_update_dis(self):
+        """Data-parallel step only: the discriminator's optimiser + operand refresh as a graph of its own, replayed on the update
+        stream as soon as its gradients' all-reduce has completed -- concurrently with the generator's backward pass."""
+        if not self.update_mask[0]:
+            return
+        K.incr_step(self.D.step)
+        K.adam(self.D.w, self.D.m, self.D.v, self.D.g, self.D.n_flat, self.lr_dis, self.D.step)
+        self.D.refresh()
+
+    def _phase_update(self, skip_dis=False):
         """Both Adam updates from the same forward pass, then UPDATE_OPS (my_sngan.py:424-426; graph_func.py:848-854)."""
         main = torch.cuda.current_stream(self.device)
         side = self._upd_stream if self.grad_fork else main
@@ -697,7 +721,7 @@ class SNGanEngine(object):
             ev = torch.cuda.Event()
             ev.record(main)
             side.wait_event(ev)
-        for net, lr, st, scheduled in ((self.D, self.lr_dis, side, self.update_mask[0]), (self.G, self.lr_gen, main, self.update_mask[1])):
+        for net, lr, st, scheduled in ((self.D, self.lr_dis, side, self.update_mask[0] and not skip_dis), (self.G, self.lr_gen, main, self.update_mask[1])):
             if not scheduled:                              # imbalanced update: this optimiser is not run on this step (graph_func.py:885-886)
                 continue
             if net is self.D and self._dis_updated:        # already enqueued on the update stream during the backward pass
@@ -735,15 +759,28 @@ class SNGanEngine(object):
             return
         parallel.gather_scores(self.D.layers[-1].a[0], self.B, self.s_gather, self.gen_all, self.real_all, self.pg)
 
+    def _allreduce_dis_async(self):
+        """The discriminator's gradients are final after the first backward graph: their all-reduce is started now, on NCCL's
+        own stream, and overlaps the generator's backward pass (joined in _allreduce_grads)."""
+        import torch.distributed as dist
+        if not self.nvls:
+            self._comm_work = dist.all_reduce(self.D.g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
+    def _join_dis_allreduce(self):
+        """Make the CURRENT stream wait for the discriminator's all-reduce (issued by _allreduce_dis_async)."""
+        if self._comm_work is not None:
+            self._comm_work.wait()
+            self._comm_work = None
+
     def _allreduce_grads(self):
         from . import parallel
         if self.nvls:    # the parameter gradients are reduced inside the optimiser kernel, the six kernel sums by a multicast load
             self.sym_scores.allreduce_sums(self.mmd.sums)
         else:
-            parallel.allreduce_sum([self.D.g, self.G.g, self.mmd.sums], self.pg)
-        lg, ld = parallel.losses_from_sums(self.mmd.sums, [float(c) for c in self.mmd.desc.cD])
-        self.mmd.losses[0] = lg
-        self.mmd.losses[1] = ld
+            # ONE call for the generator's gradients and the six kernel sums (the tail of the same buffer)
+            parallel.allreduce_sum([self.G.g_all], self.pg)
+            self._join_dis_allreduce()
+        K.losses_from_sums(self.mmd.sums, [float(c) for c in self.mmd.desc.cD], self.mmd.losses)
 
     # -------------------------------------------------------------------------------------------- public API
     def _run_phases(self):
@@ -751,18 +788,83 @@ class SNGanEngine(object):
         if self.world_size > 1:
             self._gather_scores()
         self._phase_loss()
-        self._phase_backward()
         if self.world_size > 1:
+            self._phase_backward('dis')
+            self._allreduce_dis_async()
+            self._phase_backward('gen')
             self._allreduce_grads()
+        else:
+            self._phase_backward()
         self._phase_update()
+
+    def _run_phases_overlapped(self):
+        """The data-parallel step as it is captured into ONE graph: like _run_phases, with the discriminator's optimiser forked
+        onto the update stream behind its all-reduce (concurrent with the generator's backward pass)."""
+        main = torch.cuda.current_stream(self.device)
+        self._phase_forward()
+        self._gather_scores()
+        self._phase_loss()
+        self._phase_backward('dis')
+        self._allreduce_dis_async()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._upd_stream.wait_event(ev)                # fork (capture: the update stream joins the graph here)
+        with torch.cuda.stream(self._upd_stream):
+            self._join_dis_allreduce()
+            self._phase_update_dis()
+        self._phase_backward('gen')
+        self._allreduce_grads()
+        main.wait_stream(self._upd_stream)
+        self._phase_update(skip_dis=True)
+
+    def _replay_data_parallel(self, graphs):
+        """The captured data-parallel step: four collective-free graphs around the collectives; the discriminator's optimiser is a
+        fifth graph replayed on the update stream behind its all-reduce, while the generator's backward pass runs."""
+        main = torch.cuda.current_stream(self.device)
+        if len(graphs) == 1:                       # the whole step, collectives included, is one graph
+            graphs[0].replay()
+            return
+        graphs[0].replay()                         # forward
+        self._gather_scores()
+        graphs[1].replay()                         # loss + discriminator backward
+        self._allreduce_dis_async()
+        if self.nvls:
+            graphs[2].replay()                     # generator backward
+            self._allreduce_grads()
+            self._phase_update()                   # holds cross-rank barriers: enqueued eagerly
+            return
+        with torch.cuda.stream(self._upd_stream):
+            self._join_dis_allreduce()             # the update stream (not the compute stream) waits for the all-reduce
+            graphs[4].replay()                     # discriminator optimiser + operand refresh
+        graphs[2].replay()                         # generator backward
+        self._allreduce_grads()                    # generator gradients + the six kernel sums
+        main.wait_stream(self._upd_stream)
+        graphs[3].replay()                         # generator optimiser, UPDATE_OPS
 
     def _capture(self):
         """Capture the step (or, multi-GPU, its three collective-free segments) into CUDA graphs."""
         torch.cuda.synchronize(self.device)
-        segs = ([[self._phase_forward], [self._phase_loss, self._phase_backward], [self._phase_update]]
+        segs = ([[self._phase_forward], [self._phase_loss, lambda: self._phase_backward('dis')], [lambda: self._phase_backward('gen')],
+                 [lambda: self._phase_update(skip_dis=True)], [self._phase_update_dis]]
                 if self.world_size > 1 else [[self._phase_forward, self._phase_loss, self._phase_backward, self._phase_update]])
         if self.nvls:
-            segs = segs[:2]      # the update phase holds cross-rank barriers: it is enqueued eagerly after the second graph
+            segs = segs[:3]      # the update phase holds cross-rank barriers: it is enqueued eagerly after the third graph
+        self._dp_one_graph = False
+        if self.world_size > 1 and not self.nvls and os.environ.get('MMDGAN_DP_ONE_GRAPH', '0') == '1':
+            # EXPERIMENT, off by default: the whole data-parallel step INCLUDING its NCCL collectives as one CUDA graph (no host
+            # launch gaps at the graph boundaries; the all-reduce of the discriminator's gradients forked onto NCCL's stream inside
+            # the graph).  Measured on 2 B200: 4.35 instead of 4.42 ms per step, but the processes then hung at teardown /
+            # when eager collectives followed (two 420 s timeouts) -- not shipped.  Falls back if the capture is refused.
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._stream):
+                    self._run_phases_overlapped()
+                self._graph_cache[self.update_mask] = [g]
+                self._dp_one_graph = True
+                return
+            except Exception as exc:      # noqa: BLE001 -- any capture failure: use the segmented form
+                self._dp_one_graph_error = '{}: {}'.format(type(exc).__name__, exc)
+                torch.cuda.synchronize(self.device)
         graphs = []
         for fns in segs:
             g = torch.cuda.CUDAGraph()
@@ -793,14 +895,7 @@ class SNGanEngine(object):
                 self._capture()
             graphs = self._graph_cache[self.update_mask]
             if self.world_size > 1:
-                graphs[0].replay()
-                self._gather_scores()
-                graphs[1].replay()
-                self._allreduce_grads()
-                if self.nvls:
-                    self._phase_update()
-                else:
-                    graphs[2].replay()
+                self._replay_data_parallel(graphs)
             else:
                 graphs[0].replay()
         self.global_step += 1

@@ -632,6 +632,10 @@ def allreduce_small_nvls(out, in_mc, n):
     check(lib().mmdgan_allreduce_small_nvls(_ptr(out), C.c_void_p(in_mc), int(n), stream()))
 
 
+def losses_from_sums(sums, cD, losses):
+    check(lib().mmdgan_losses_from_sums(_ptr(sums), float(cD[0]), float(cD[1]), float(cD[2]), _ptr(losses), stream()))
+
+
 def incr_step(step):
     check(lib().mmdgan_incr_step(_ptr(step), stream()))
 

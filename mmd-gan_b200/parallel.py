@@ -21,16 +21,16 @@ def gather_scores(s_local, b, gather_buf, gen_all, real_all, group=None):
     """s_local [2b, d] (rows [0,b) real, [b,2b) generated) -> real_all / gen_all [world*b, d] in global row order."""
     world = dist.get_world_size(group)
     d = s_local.shape[1]
-    flat = gather_buf.view(world * 2 * b, d)
     try:
-        dist.all_gather_into_tensor(flat, s_local.contiguous(), group=group)
+        # straight into the global row order: rank r's block lands at rows [r*b, (r+1)*b) of each matrix -- no re-ordering copies
+        dist.all_gather_into_tensor(real_all, s_local[:b], group=group)
+        dist.all_gather_into_tensor(gen_all, s_local[b:2 * b], group=group)
     except (RuntimeError, NotImplementedError):       # backends without the flat variant
         parts = [torch.empty_like(s_local) for _ in range(world)]
         dist.all_gather(parts, s_local.contiguous(), group=group)
-        flat.copy_(torch.cat(parts, 0))
-    g = gather_buf.view(world, 2 * b, d)
-    real_all.copy_(g[:, :b, :].reshape(world * b, d))
-    gen_all.copy_(g[:, b:, :].reshape(world * b, d))
+        g = torch.stack(parts, 0)
+        real_all.copy_(g[:, :b, :].reshape(world * b, d))
+        gen_all.copy_(g[:, b:, :].reshape(world * b, d))
     return gen_all, real_all
 
 
