@@ -285,6 +285,13 @@ typedef struct mmdgan_mmd_desc {
  * returns MMDGAN_EINVAL for unknown types or w0 - w1 != 1 (the reference's assert, math_func.py:1340) */
 int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, float w1);
 size_t mmdgan_mmd_workspace(int b);
+/* N(0, 1) samples on the device: replaces tf.random_normal([batch_size, code_size]) of SNGan.sample_codes (reference
+ * DeepLearning/my_sngan.py:122-124).  Philox-4x32-10 keyed by `seed`, counter = (quadruple index, *draw_counter), Box-Muller.
+ * draw_counter (device, may be null = 0) is read by the kernel, so a captured graph draws fresh codes on every replay once
+ * mmdgan_incr_counter follows it.  raw_words (may be null) receives the four Philox words per quadruple (tests). */
+int mmdgan_sample_normal(float* out, long long n, unsigned long long seed, const unsigned long long* draw_counter, unsigned int* raw_words,
+                         void* stream);
+int mmdgan_incr_counter(unsigned long long* counter, void* stream);
 /* data-parallel step: the two losses from the six GLOBAL kernel sums (after their all-reduce):
  * loss_gen = e_gg + e_rr - 2 e_gr (math_func.py:1342), loss_dis = cD0 e_gg^b + cD1 e_gr^b + cD2 e_rr^b (math_func.py:1421) */
 int mmdgan_losses_from_sums(const float* sums, float cD0, float cD1, float cD2, float* losses, void* stream);

@@ -64,7 +64,18 @@ class SNGan(object):
         """my_sngan.py:111-149 for num_class < 2: N(0, 1) codes."""
         import torch
         if code_x is None:
-            code_x = torch.randn(batch_size, self.code_size)
+            # the device generator the training step itself uses (engine._phase_forward): Philox keyed by torch's seed, one
+            # draw per call -- a loop that feeds these codes back sees exactly the codes the engine would draw on its own
+            from .. import kernels as K
+            if not torch.cuda.is_available():
+                raise RuntimeError('sample_codes: codes are drawn on the GPU (this framework has no CPU path); pass code_x')
+            if getattr(self, '_code_seed', None) != int(torch.initial_seed()):
+                self._code_seed, self._code_draws = int(torch.initial_seed()), 0
+            out = torch.empty(batch_size, self.code_size, dtype=torch.float32, device='cuda')
+            ctr = torch.tensor([self._code_draws], dtype=torch.int64, device='cuda')
+            K.sample_normal(out, self._code_seed, ctr)
+            self._code_draws += 1
+            code_x = out.cpu()
         else:
             code_x = torch.as_tensor(code_x).float()
             assert code_x.shape[0] == batch_size, 'Input code_x size {} does not match batch_size {}'.format(
@@ -85,7 +96,7 @@ class SNGan(object):
             reader.shape2image(self.channels, self.height, self.width)
 
             def fn_records(step):
-                return torch.from_numpy(reader.next_batch()['x']), self.sample_codes(batch_size)['x']
+                return torch.from_numpy(reader.next_batch()['x']), None       # codes: drawn on the device inside the step
             return fn_records
         if isinstance(source, str):
             g = torch.Generator().manual_seed(0)
@@ -99,7 +110,7 @@ class SNGan(object):
 
         def fn(step):
             idx = (torch.arange(batch_size) + step * batch_size) % n
-            return pool[idx], self.sample_codes(batch_size)['x']
+            return pool[idx], None                                            # codes: drawn on the device inside the step
         return fn
 
     def training(self, filename, agent, num_instance, lr_list, end_lr=1e-7, max_step=None, batch_size=64,

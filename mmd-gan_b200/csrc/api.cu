@@ -50,6 +50,8 @@ int l_adam_allreduce_nvls(const float*, const float*, const float*, const float*
 int l_scatter_scores_nvls(const float*, int, int, int, float*, float*, cudaStream_t);
 int l_allreduce_small_nvls(float*, const float*, int, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
+int l_sample_normal(float*, long long, unsigned long long, const unsigned long long*, uint32_t*, cudaStream_t);
+int l_incr_u64(unsigned long long*, cudaStream_t);
 int l_losses_from_sums(const float*, float, float, float, float*, cudaStream_t);
 int l_refresh(const RefreshJob*, int, long long, cudaStream_t);
 long long dense_small_workspace(int rows, int K, int N);
@@ -374,6 +376,15 @@ int mmdgan_mmd_configure(mmdgan_mmd_desc* d, const char* loss_type, float w0, fl
         return MMDGAN_OK;
     }
     return fail(MMDGAN_EINVAL, "Not implemented.");  /* math_func.py:2651 */
+}
+int mmdgan_sample_normal(float* out, long long n, unsigned long long seed, const unsigned long long* draw_counter, unsigned int* raw_words,
+                         void* stream) {
+    if (!out || n <= 0) return fail(MMDGAN_EINVAL, "mmdgan_sample_normal: null pointer / empty request");
+    return wrap(mg::l_sample_normal(out, n, seed, draw_counter, raw_words, S(stream)), "mmdgan_sample_normal");
+}
+int mmdgan_incr_counter(unsigned long long* counter, void* stream) {
+    if (!counter) return fail(MMDGAN_EINVAL, "mmdgan_incr_counter: null pointer");
+    return wrap(mg::l_incr_u64(counter, S(stream)), "mmdgan_incr_counter");
 }
 int mmdgan_losses_from_sums(const float* sums, float cD0, float cD1, float cD2, float* losses, void* stream) {
     if (!sums || !losses) return fail(MMDGAN_EINVAL, "mmdgan_losses_from_sums: null pointer");

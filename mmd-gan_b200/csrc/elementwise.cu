@@ -794,6 +794,59 @@ int l_dense_small_fwd(const bf16_t* a, long long a_plane, int npl, int a_fmt, in
     dense_small_finish_kernel<<<nblocks(static_cast<long long>(rows) * N, 256), 256, 0, st>>>(workspace, slices, rows, N, alpha_k, sigma, bias, out, ldo);
     return MG_CHECK_LAUNCH();
 }
+// ------------------------------------------------------------------------------------------------ code sampling
+// tf.random_normal([batch, code_size]) inside the training graph (reference my_sngan.py:122-124): N(0, 1) codes drawn ON THE
+// DEVICE.  Philox-4x32-10 (Salmon et al., SC'11; the generator behind tf.random_normal and curand) keyed by the run seed,
+// counter = (element quadruple index, 0, draw counter lo, draw counter hi) with the draw counter read from device memory, so
+// a captured CUDA graph produces fresh codes on every replay; Box-Muller turns the four 32-bit words into four normals.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+// u in (0, 1]: (x + 1) * 2^-32 computed in fp32 from the top 24 bits so that it never rounds to 0
+__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+__global__ void sample_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, const unsigned long long* __restrict__ draw,
+                                     uint32_t* __restrict__ raw) {
+    const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;      // quadruple index
+    if (q * 4 >= n) return;
+    const unsigned long long d = draw ? *draw : 0ull;
+    uint32_t c[4] = {static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), static_cast<uint32_t>(d), static_cast<uint32_t>(d >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float r = sqrtf(-2.0f * logf(u01(c[2 * h])));
+        float s, co;
+        sincospif(2.0f * u01(c[2 * h + 1]), &s, &co);
+        z[2 * h] = r * co;
+        z[2 * h + 1] = r * s;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (q * 4 + k < n) {
+            out[q * 4 + k] = z[k];
+            if (raw) raw[q * 4 + k] = c[k];
+        }
+}
+__global__ void incr_u64_kernel(unsigned long long* c) { *c += 1ull; }
+int l_sample_normal(float* out, long long n, unsigned long long seed, const unsigned long long* draw, uint32_t* raw, cudaStream_t st) {
+    sample_normal_kernel<<<nblocks((n + 3) / 4, 256), 256, 0, st>>>(out, n, seed, draw, raw);
+    return MG_CHECK_LAUNCH();
+}
+int l_incr_u64(unsigned long long* c, cudaStream_t st) {
+    incr_u64_kernel<<<1, 1, 0, st>>>(c);
+    return MG_CHECK_LAUNCH();
+}
 __global__ void losses_from_sums_kernel(const float* __restrict__ sums, float c0, float c1, float c2, float* __restrict__ losses) {
     losses[0] = sums[0] + sums[2] - 2.0f * sums[1];
     losses[1] = c0 * sums[3] + c1 * sums[4] + c2 * sums[5];

@@ -384,6 +384,11 @@ class SNGanEngine(object):
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._stage_bufs = [(torch.empty_like(self._dev_data), torch.empty_like(self._dev_code)) for _ in range(2)]
         self._pin_bufs = [(torch.empty_like(self._pin_data).pin_memory(), torch.empty_like(self._pin_code).pin_memory()) for _ in range(2)]
+        # codes drawn on the device (tf.random_normal inside the graph, my_sngan.py:122-124): Philox keyed by torch's seed at
+        # construction, one draw counter per step in device memory so that the captured graph stays replayable
+        self.code_seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * int(rank)) & 0xFFFFFFFFFFFFFFFF     # every rank its own stream
+        self.code_draw = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.device_codes = False                # set per step: True when step() / stage() is given no codes
         self._prefetched = None                  # (data tensor, code tensor, buffer index, event) of the batch in flight
         self._slot_free = [None, None]           # event: the last device-to-device read of a staging slot
         self._stage_next = 0
@@ -533,6 +538,9 @@ class SNGanEngine(object):
     # -------------------------------------------------------------------------------------------- step pieces
     def _phase_forward(self):
         B, HW = self.B, self.height * self.width
+        if self.device_codes:                     # SNGan.sample_codes: z ~ N(0, 1) drawn here, no host round trip
+            K.sample_normal(self._dev_code, self.code_seed, self.code_draw)
+            K.incr_counter(self.code_draw)
         K.nchw_to_planes(self._dev_code, self.code_planes)
         K.nchw_to_planes(self._dev_data, self.x_all[:, :B * HW, :])
         joins = self._sn_power_iteration(fork=self.sn_fork)
@@ -859,7 +867,7 @@ class SNGanEngine(object):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self._stream):
                     self._run_phases_overlapped()
-                self._graph_cache[self.update_mask] = [g]
+                self._graph_cache[self._graph_key()] = [g]
                 self._dp_one_graph = True
                 return
             except Exception as exc:      # noqa: BLE001 -- any capture failure: use the segmented form
@@ -872,12 +880,15 @@ class SNGanEngine(object):
                 for fn in fns:
                     fn()
             graphs.append(g)
-        self._graph_cache[self.update_mask] = graphs
+        self._graph_cache[self._graph_key()] = graphs
+
+    def _graph_key(self):
+        return self.update_mask + (self.device_codes,)
 
     @property
     def _graphs(self):
         """CUDA graphs of the ordinary step (both optimisers run); None until captured."""
-        return self._graph_cache.get((True, True))
+        return self._graph_cache.get((True, True, False)) or self._graph_cache.get((True, True, True))
 
     def step_device(self, update=(True, True)):
         """One training step on the batch already staged in self._dev_data / self._dev_code (device resident).
@@ -891,19 +902,22 @@ class SNGanEngine(object):
             self.kernel_launches_per_step = K.LAUNCHES[0] - n0
             self._warm = True
         else:
-            if self.update_mask not in self._graph_cache:
+            if self._graph_key() not in self._graph_cache:
                 self._capture()
-            graphs = self._graph_cache[self.update_mask]
+            graphs = self._graph_cache[self._graph_key()]
             if self.world_size > 1:
                 self._replay_data_parallel(graphs)
             else:
                 graphs[0].replay()
         self.global_step += 1
 
-    def stage(self, data_x, code_x):
-        """Put one batch on the device ({'x': NCHW float32 in [-1, 1]} contract of input_func.py:837-868)."""
+    def stage(self, data_x, code_x=None):
+        """Put one batch on the device ({'x': NCHW float32 in [-1, 1]} contract of input_func.py:837-868).  code_x = None: the
+        step draws its codes on the device (SNGan.sample_codes with code_x=None, my_sngan.py:122-124)."""
         self._dev_data.copy_(data_x, non_blocking=True)
-        self._dev_code.copy_(code_x, non_blocking=True)
+        self.device_codes = code_x is None
+        if code_x is not None:
+            self._dev_code.copy_(code_x, non_blocking=True)
 
     def prefetch(self, data_x, code_x):
         """Start the host -> device copy of a FUTURE batch on the copy stream (it overlaps the step that is running); the
@@ -911,11 +925,12 @@ class SNGanEngine(object):
         k = self._stage_next
         self._stage_next ^= 1
         dd, dc = self._stage_bufs[k]
-        if not (data_x.is_pinned() and code_x.is_pinned()):      # pageable host memory: through this slot's pinned buffers
+        if not (data_x.is_pinned() and (code_x is None or code_x.is_pinned())):      # pageable host memory: through this slot's pinned buffers
             pd, pc = self._pin_bufs[k]
             pd.copy_(data_x)
-            pc.copy_(code_x)
-            src_d, src_c = pd, pc
+            if code_x is not None:
+                pc.copy_(code_x)
+            src_d, src_c = pd, (pc if code_x is not None else None)
         else:
             src_d, src_c = data_x, code_x
         ev = torch.cuda.Event()
@@ -925,12 +940,14 @@ class SNGanEngine(object):
             self._copy_stream.wait_event(self._slot_free[k])
         with torch.cuda.stream(self._copy_stream):
             dd.copy_(src_d, non_blocking=True)
-            dc.copy_(src_c, non_blocking=True)
+            if src_c is not None:
+                dc.copy_(src_c, non_blocking=True)
             ev.record(self._copy_stream)
         self._prefetched = (data_x, code_x, k, ev)
 
-    def step(self, data_x, code_x, check_nan=True, update=(True, True), prefetch=None):
-        """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis].
+    def step(self, data_x, code_x=None, check_nan=True, update=(True, True), prefetch=None):
+        """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis].  code_x = None: the
+        codes are drawn on the device inside the step (the reference's in-graph tf.random_normal); tests inject code_x.
         prefetch = (next_data, next_code): the host -> device copy of the NEXT step's batch is started right after this step has
         been enqueued, so that it overlaps the step instead of preceding the next one (the copy is still made once per step)."""
         pf = self._prefetched
@@ -939,15 +956,19 @@ class SNGanEngine(object):
             dd, dc = self._stage_bufs[pf[2]]
             torch.cuda.current_stream(self.device).wait_event(pf[3])
             self._dev_data.copy_(dd, non_blocking=True)          # device-to-device, ~2 us
-            self._dev_code.copy_(dc, non_blocking=True)
+            self.device_codes = code_x is None
+            if code_x is not None:
+                self._dev_code.copy_(dc, non_blocking=True)
             self._slot_free[pf[2]] = torch.cuda.Event()
             self._slot_free[pf[2]].record(torch.cuda.current_stream(self.device))
         else:
             self._prefetched = None
-            if not (data_x.is_pinned() and code_x.is_pinned()):      # pageable host memory: stage through pinned buffers
+            if not (data_x.is_pinned() and (code_x is None or code_x.is_pinned())):      # pageable host memory: stage through pinned buffers
                 self._pin_data.copy_(data_x)
-                self._pin_code.copy_(code_x)
-                data_x, code_x = self._pin_data, self._pin_code
+                data_x = self._pin_data
+                if code_x is not None:
+                    self._pin_code.copy_(code_x)
+                    code_x = self._pin_code
             self.stage(data_x, code_x)
         self.step_device(update)
         if prefetch is not None:

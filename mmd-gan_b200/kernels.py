@@ -52,8 +52,8 @@ def stream():
 def _ptr(t):
     if t is None:
         return None
-    if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32, torch.bfloat16, torch.float16):
-        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32/bfloat16/float16 tensor, got {} on {}'.format(t.dtype, t.device))
+    if not t.is_cuda or t.dtype not in (torch.float32, torch.float64, torch.int32, torch.int64, torch.bfloat16, torch.float16):
+        raise _lib.MmdganError(_lib.MMDGAN_EINVAL, 'expected a CUDA float32/float64/int32/int64/bfloat16/float16 tensor, got {} on {}'.format(t.dtype, t.device))
     if t.dim() == 3:
         # planes [npl, rows, C]: every plane must be a dense [rows, C] block; the plane stride is free (row views)
         if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
@@ -630,6 +630,15 @@ def scatter_scores_nvls(s_local, b, rank, gen_all_mc, real_all_mc):
 
 def allreduce_small_nvls(out, in_mc, n):
     check(lib().mmdgan_allreduce_small_nvls(_ptr(out), C.c_void_p(in_mc), int(n), stream()))
+
+
+def sample_normal(out, seed, draw_counter=None, raw=None):
+    """out (float32, any shape) <- N(0, 1) samples drawn on the device (Philox-4x32-10 + Box-Muller; csrc/elementwise.cu)."""
+    check(lib().mmdgan_sample_normal(_ptr(out), out.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(draw_counter), _ptr(raw), stream()))
+
+
+def incr_counter(counter):
+    check(lib().mmdgan_incr_counter(_ptr(counter), stream()))
 
 
 def losses_from_sums(sums, cD, losses):

@@ -266,7 +266,7 @@ def test_engine_imbalanced_update_against_golden(cuda, tag, family, use_graph):
                     assert abs(got - ref) <= 5e-2 * ref, (t, name, got, ref)
     assert eng.global_step == int(z['global_step'])
     if use_graph:
-        assert set(eng._graph_cache) == {tuple(t % k == 0 for k in imb) for t in range(1, int(z['steps']))}
+        assert {key[:2] for key in eng._graph_cache} == {tuple(t % k == 0 for k in imb) for t in range(1, int(z['steps']))}
     num = den = 0.0
     for net in (eng.G, eng.D):
         for name in net.var_offsets:
