@@ -77,6 +77,12 @@ __device__ __forceinline__ float act_grad_from_output(float a, int mode) {
     if (mode == 3) return 1.f - a * a;
     return 1.f;
 }
+// 256-bit global stores / loads (sm_100: STG.256 / LDG.256): a thread's 32 bytes fill one whole sector per instruction
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                 "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // Sum over the 32 lanes of a warp of CW = 32 per-lane values, column by column: afterwards lane j holds the total of
@@ -164,11 +170,22 @@ __device__ __forceinline__ void epi_chunk(const EpiRow& c, float (&v)[32], const
     // ---- store this row's CW columns
     if (row_ok) {
         const long long off = c.prow * p.Cd + col;
+        const bool wide = (p.Cd & 15) == 0 && (col & 15) == 0;      // 32-byte aligned rows: 256-bit stores
         if (OUT == 2) {
             float* d = static_cast<float*>(p.dst) + off;
 #pragma unroll
-            for (int q = 0; q < CW / 4; ++q)
-                if (q * 4 < nvalid) *reinterpret_cast<float4*>(d + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            for (int q8 = 0; q8 < CW / 8; ++q8) {
+                if (wide && q8 * 8 + 8 <= nvalid) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(v[q8 * 8 + k]);
+                    st_global_v8(d + q8 * 8, w);
+                } else {
+#pragma unroll
+                    for (int q = 2 * q8; q < 2 * q8 + 2; ++q)
+                        if (q * 4 < nvalid) *reinterpret_cast<float4*>(d + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                }
+            }
         } else if (OUT == 3) {
 #pragma unroll
             for (int q = 0; q < CW / 4; ++q)
@@ -183,11 +200,12 @@ __device__ __forceinline__ void epi_chunk(const EpiRow& c, float (&v)[32], const
             bf16_t* d1 = d0 + p.dst_plane;
             float amax = 0.f;
 #pragma unroll
-            for (int o = 0; o < CW / 8; ++o) {
-                uint32_t w0[4], w1[4];
+            for (int o16 = 0; o16 < (CW + 15) / 16; ++o16) {
+                uint32_t w0[8], w1[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float xa = v[o * 8 + 2 * k], xb = v[o * 8 + 2 * k + 1];
+                for (int k = 0; k < 8; ++k) {
+                    const int j = o16 * 16 + 2 * k;
+                    const float xa = j < CW ? v[j < 32 ? j : 0] : 0.f, xb = j + 1 < CW ? v[j + 1 < 32 ? j + 1 : 0] : 0.f;
                     uint16_t a0, a1, b0, b1;
                     if (OUT == 0) {
                         f16_split2(xa * 16.f, a0, a1);
@@ -200,12 +218,23 @@ __device__ __forceinline__ void epi_chunk(const EpiRow& c, float (&v)[32], const
                     w0[k] = pack16(a0, b0);
                     w1[k] = pack16(a1, b1);
                 }
-                if (o * 8 + 4 < nvalid) {
-                    *reinterpret_cast<uint4*>(d0 + o * 8) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-                    *reinterpret_cast<uint4*>(d1 + o * 8) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-                } else if (o * 8 < nvalid) {
-                    *reinterpret_cast<uint2*>(d0 + o * 8) = make_uint2(w0[0], w0[1]);
-                    *reinterpret_cast<uint2*>(d1 + o * 8) = make_uint2(w1[0], w1[1]);
+                const int e0 = o16 * 16;       // first element of this 32-byte group
+                if (wide && e0 + 16 <= nvalid && e0 + 16 <= CW) {
+                    st_global_v8(d0 + e0, w0);
+                    st_global_v8(d1 + e0, w1);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int e = e0 + 8 * h;
+                        if (e >= CW) continue;
+                        if (e + 4 < nvalid) {
+                            *reinterpret_cast<uint4*>(d0 + e) = make_uint4(w0[4 * h], w0[4 * h + 1], w0[4 * h + 2], w0[4 * h + 3]);
+                            *reinterpret_cast<uint4*>(d1 + e) = make_uint4(w1[4 * h], w1[4 * h + 1], w1[4 * h + 2], w1[4 * h + 3]);
+                        } else if (e < nvalid) {
+                            *reinterpret_cast<uint2*>(d0 + e) = make_uint2(w0[4 * h], w0[4 * h + 1]);
+                            *reinterpret_cast<uint2*>(d1 + e) = make_uint2(w1[4 * h], w1[4 * h + 1]);
+                        }
+                    }
                 }
             }
             if (OUT == 0 && p.sat_flag != nullptr && amax * 16.f > 65504.f) atomicExch(p.sat_flag, 1);
