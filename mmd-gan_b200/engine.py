@@ -801,6 +801,10 @@ class SNGanEngine(object):
             self._allreduce_dis_async()
             self._phase_backward('gen')
             self._allreduce_grads()
+        elif os.environ.get('MMDGAN_FORCE_SPLIT', '0') == '1':
+            # experiment (single GPU): the data-parallel step's join between the two backward halves, without any collective
+            self._phase_backward('dis')
+            self._phase_backward('gen')
         else:
             self._phase_backward()
         self._phase_update()
@@ -871,6 +875,19 @@ class SNGanEngine(object):
                 self._dp_one_graph = True
                 return
             except Exception as exc:      # noqa: BLE001 -- any capture failure: use the segmented form
+                self._dp_one_graph_error = '{}: {}'.format(type(exc).__name__, exc)
+                torch.cuda.synchronize(self.device)
+        if self.nvls and os.environ.get('MMDGAN_NVLS_ONE_GRAPH', '0') == '1':
+            # EXPERIMENT: the NVSwitch-multicast step has no NCCL call at all -- its exchanges are kernels with device-side barriers
+            # on the symmetric allocation's signal pads -- so the whole data-parallel step can be ONE graph.
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._stream):
+                    self._run_phases()
+                self._graph_cache[self._graph_key()] = [g]
+                self._dp_one_graph = True
+                return
+            except Exception as exc:      # noqa: BLE001
                 self._dp_one_graph_error = '{}: {}'.format(type(exc).__name__, exc)
                 torch.cuda.synchronize(self.device)
         graphs = []
