@@ -258,13 +258,21 @@ def run_ours(args):
         evs = []
         orig_gemm, orig_wgrad, orig_direct = K.LinearOp._gemm, K.LinearOp.wgrad, K.LinearOp._direct
 
+        depth = [0]
+
         def timed(fn):
             def wrapper(*a, **kw):
-                if a[3] == 1:        # batch-1 spectral-norm launches: side streams, not part of the 3G+7D FLOP count
+                # batch-1 spectral-norm launches: side streams, not part of the 3G+7D FLOP count.  Nested calls (an image layer
+                # runs as im2col / tap-sum + an inner dense GEMM) are timed once, at the outermost level
+                if a[3] == 1 or depth[0] > 0:
                     return fn(*a, **kw)
+                depth[0] += 1
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                r = fn(*a, **kw)
+                try:
+                    r = fn(*a, **kw)
+                finally:
+                    depth[0] -= 1
                 e.record()
                 evs.append((s, e))
                 return r

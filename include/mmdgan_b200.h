@@ -178,6 +178,15 @@ typedef struct mmdgan_direct_desc {
     int* sat_flag; /* optional, as in mmdgan_gemm_desc */
 } mmdgan_direct_desc;
 int mmdgan_direct_conv(const mmdgan_direct_desc* d, void* stream);
+/* The many -> few direction of the same two layers (forward of C -> 3, input gradient of 3 -> C; tf.nn.conv2d at
+ * layer_func.py:912-916 and its input gradient) as a dense [C -> 27] product over 27 = 9 taps x 3 channels on mmdgan_gather_gemm
+ * followed by this kernel: from T (fp32 [pixels][32], column tap * 3 + c) it forms
+ * y[p][c] = act(alpha * sum_tap T[p +- off(tap)][tap * 3 + c] + bias[c]) (* act'(aux)), writes planes (channels >= 3 zero) or raw
+ * fp32 and, optionally, per-block column sums [mmdgan_tapsum_blocks][Cd].  flip = 1: minus (input gradient). */
+int mmdgan_tapsum3x3_small(const float* T, int N, int H, int W, int flip, float alpha_k, const float* sigma, const float* bias, int act,
+                           const mmdgan_bf16* aux, long long aux_plane, int aux_npl, int aux_fmt, int aux_mode, void* dst, long long dst_plane,
+                           int dst_npl, int dst_fmt, int Cd, int out_mode, float* colsum, int* sat_flag, void* stream);
+int mmdgan_tapsum_blocks(int N, int H, int W);
 int mmdgan_direct_conv_blocks(int N, int H, int W);
 
 /* out[m][n] = alpha * sum_k a[m][k] * wt[n][k] + bias[n] for N in {4,8,16,32} output columns (the critic's score layer,

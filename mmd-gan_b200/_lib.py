@@ -111,6 +111,8 @@ SYMBOLS = {
     'mmdgan_dense_small_fwd': (_I, [_P, _LL, _I, _I, _I, _I, _P, _LL, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P]),
     'mmdgan_dense_small_workspace': (C.c_size_t, [_I, _I, _I]),
     'mmdgan_losses_from_sums': (_I, [_P, _F, _F, _F, _P, _P]),
+    'mmdgan_tapsum3x3_small': (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _LL, _I, _I, _I, _P, _LL, _I, _I, _I, _I, _P, _P, _P]),
+    'mmdgan_tapsum_blocks': (_I, [_I, _I, _I]),
     'mmdgan_sample_normal': (_I, [_P, _LL, C.c_ulonglong, _P, _P, _P]),
     'mmdgan_incr_counter': (_I, [_P, _P]),
     'mmdgan_direct_conv': (_I, [C.POINTER(DirectDesc), _P]),

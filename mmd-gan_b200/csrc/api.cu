@@ -50,6 +50,9 @@ int l_adam_allreduce_nvls(const float*, const float*, const float*, const float*
 int l_scatter_scores_nvls(const float*, int, int, int, float*, float*, cudaStream_t);
 int l_allreduce_small_nvls(float*, const float*, int, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
+int tapsum_blocks(int N, int H, int W);
+int launch_tapsum27(const float*, int, int, int, int, float, const float*, const float*, int, const uint16_t*, long long, int, int, int, void*, long long,
+                    int, int, int, int, float*, int*, cudaStream_t);
 int l_sample_normal(float*, long long, unsigned long long, const unsigned long long*, uint32_t*, cudaStream_t);
 int l_incr_u64(unsigned long long*, cudaStream_t);
 int l_losses_from_sums(const float*, float, float, float, float*, cudaStream_t);
@@ -208,6 +211,18 @@ int mmdgan_gather_gemm(const mmdgan_gemm_desc* d, void* stream) {
     return wrap(mg::launch_conv_gemm(p, d->w, d->w_plane, d->w_rows, d->kpad, d->classes, d->bn, d->npass, d->cta_pair, S(stream)), "mmdgan_gather_gemm");
 }
 
+int mmdgan_tapsum_blocks(int N, int H, int W) { return mg::tapsum_blocks(N, H, W); }
+int mmdgan_tapsum3x3_small(const float* T, int N, int H, int W, int flip, float alpha_k, const float* sigma, const float* bias, int act,
+                           const mmdgan_bf16* aux, long long aux_plane, int aux_npl, int aux_fmt, int aux_mode, void* dst, long long dst_plane,
+                           int dst_npl, int dst_fmt, int Cd, int out_mode, float* colsum, int* sat_flag, void* stream) {
+    if (!T || !dst) return fail(MMDGAN_EINVAL, "mmdgan_tapsum3x3_small: null pointer");
+    if (N <= 0 || H <= 0 || W <= 0 || Cd < 4 || (Cd & 3)) return fail(MMDGAN_ESHAPE, "mmdgan_tapsum3x3_small: bad shape");
+    if (out_mode != 0 && out_mode != 2) return fail(MMDGAN_EINVAL, "mmdgan_tapsum3x3_small: bad out_mode");
+    if (out_mode == 0 && (!fmt_ok(dst_fmt, dst_npl) || (dst_npl > 1 && dst_plane <= 0))) return fail(MMDGAN_ESHAPE, "mmdgan_tapsum3x3_small: bad destination plane layout");
+    if (aux && (!fmt_ok(aux_fmt, aux_npl) || (aux_npl > 1 && aux_plane <= 0))) return fail(MMDGAN_ESHAPE, "mmdgan_tapsum3x3_small: bad aux plane layout");
+    return wrap(mg::launch_tapsum27(T, N, H, W, flip, alpha_k, sigma, bias, act, aux, aux_plane, aux_npl, aux_fmt, aux_mode, dst, dst_plane, dst_npl,
+                                    dst_fmt, Cd, out_mode, colsum, sat_flag, S(stream)), "mmdgan_tapsum3x3_small");
+}
 int mmdgan_direct_conv_blocks(int N, int H, int W) { return mg::direct_conv_blocks(N, H, W); }
 int mmdgan_direct_conv(const mmdgan_direct_desc* d, void* stream) {
     if (!d || !d->src || !d->w || !d->dst) return fail(MMDGAN_EINVAL, "mmdgan_direct_conv: null pointer");

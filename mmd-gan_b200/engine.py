@@ -292,6 +292,8 @@ class NetRuntime(object):
                     perms.append((self.view(self.w, L.ly.bn_name('gamma')), L.gamma_int, L.Cout, c, hw))
                     perms.append((self.view(self.w, L.ly.bn_name('beta')), L.beta_int, L.Cout, c, hw))
             self._jobs = K.build_refresh_jobs(packs, perms, self.device)
+        for L in self.layers:
+            L.lop.pre_refresh()
         K.refresh(*self._jobs)
 
 
@@ -432,7 +434,12 @@ class SNGanEngine(object):
         # bf16 re-split of a layer's fp16 input activation for its weight-gradient GEMM; one buffer: those GEMMs run in order on
         # the gradient stream
         acts = [self.x_all, self.code_planes] + [L.a for L in self.G.layers + self.D.layers if L.a.dtype == torch.float16]
-        self.wg_scratch = torch.zeros(2 * max(t.shape[1] * t.shape[2] for t in acts), dtype=torch.bfloat16, device=dev)
+        need = max(t.shape[1] * t.shape[2] for t in acts)
+        for net, nimg in ((self.G, B), (self.D, 2 * B)):        # image layers as 27-column dense products: [pixels][32] operands
+            for L in net.layers:
+                if L.lop.img_op is not None:
+                    need = max(need, nimg * L.rows_in * 32)
+        self.wg_scratch = torch.zeros(2 * need, dtype=torch.bfloat16, device=dev)
         self.tmp_vec = torch.zeros(max(max(L.Cs_out for L in self.G.layers), max(L.Cs_out for L in self.D.layers)) + 64,
                                    dtype=torch.float32, device=dev)
         if self.world_size > 1:

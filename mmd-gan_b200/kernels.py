@@ -32,6 +32,7 @@ F16_FORWARD = int(os.environ.get('MMDGAN_F16_FORWARD', '1'))   # parity mode: fo
 WGRAD_CTAS = int(os.environ.get('MMDGAN_WGRAD_CTAS', '222'))   # CTAs a weight-gradient launch aims for (tiles x split-K slices)
 PAIR_BN256_AUX = int(os.environ.get('MMDGAN_BN256_AUX', '1'))   # 256-wide pair tiles for input gradients with N = 256 too (the persistent kernel hides their epilogue: 4.19 -> 4.15 ms)
 PAIR_N64 = int(os.environ.get('MMDGAN_PAIR_N64', '0'))   # CTA-pair tiles for N = 64 layers: measured slower (0.36 vs 0.33 ms), off
+IMG_GEMM = os.environ.get('MMDGAN_IMG_GEMM', '1') == '1'     # the image-channel layers as 1x1 GEMMs over 27 = 9 taps x 3 channels (im2col27 / tapsum27)
 DIRECT_CONV = os.environ.get('MMDGAN_DIRECT_CONV', '1') == '1'     # image-channel 3x3 layers (<= 4 channels on one side): direct CUDA-core convolution instead of the GEMM
 LAUNCHES = [0]   # kernels launched through the C ABI since import (bench.py reports the per-step count)
 
@@ -214,6 +215,17 @@ class LinearOp(object):
                 self.direct_f, self.direct_d = 'sl', 'ls'
             elif self.Cout <= 4 and self.Cin % 16 == 0 and self.Cin <= 128:
                 self.direct_f, self.direct_d = 'ls', 'sl'
+        # round 2: the many -> few direction of those two layers as a dense product over 27 = 9 taps x 3 channels on the tensor-core
+        # GEMM + the tap-sum kernel (csrc/direct_conv.cu, second half)
+        self.img_op = None
+        if self.direct_f and IMG_GEMM and min(self.Cin, self.Cout) == 3 and npass == 3:
+            self.img_few_in = self.Cin <= 3
+            cm = self.Cout if self.img_few_in else self.Cin
+            self.img_op = LinearOp('d', [27], [cm], npass=npass, device=device) if self.img_few_in else \
+                LinearOp('d', [cm], [27], npass=npass, device=device)
+            # many -> few: the dense layer's canonical matrix [C][(kh, kw, co)] is a permuted copy of the conv kernel [kh, kw, C, co]
+            self.img_wp = None if self.img_few_in else torch.zeros(cm * 27, dtype=torch.float32, device=device)
+            self._img_bufs = {}
         k = kernel
         # ---- forward / dgrad operand geometry
         if op == 'd':
@@ -264,11 +276,53 @@ class LinearOp(object):
             else:
                 d.in_C = d.in_HW = d.out_C = d.out_HW = 1
             out.append(d)
+        if self.img_op is not None:
+            out += self.img_op.pack_descs(self.img_canon())
         return out
+
+    # -------------------------------------------------------------------------------------------- image layers as 1x1 GEMMs
+    def img_canon(self):
+        """Canonical [in][out] matrix of the dense stand-in: the conv kernel itself ([3,3,3,C] = [27][C]) or its permuted copy."""
+        return self.w_canon if self.img_few_in else self.img_wp
+
+    def pre_refresh(self):
+        """many -> few: [kh, kw, C, co] -> [C][(kh, kw, co)] before the packing launch (one small copy kernel, capturable)."""
+        if self.img_op is not None and not self.img_few_in and self.w_canon is not None:
+            cm, cf = self.Cin, self.Cout
+            self.img_wp.view(cm, 3, 3, 3)[:, :, :, :cf].copy_(self.w_canon.view(3, 3, cm, cf).permute(2, 0, 1, 3))
+
+    def _img_buf(self, key, maker):
+        if key not in self._img_bufs:
+            self._img_bufs[key] = maker()
+        return self._img_bufs[key]
+
+    def _img_tapsum(self, T, nimg, flip, dst, sigma, alpha_k, bias, act, aux, aux_mode, colsum, out_mode):
+        if (out_mode == 0) != (dst.dtype in (torch.bfloat16, torch.float16)):
+            raise _lib.MmdganError(_lib.MMDGAN_ESHAPE, 'out_mode 0 writes planes, out_mode 2 one fp32 plane')
+        a = (_ptr(aux), plane_stride(aux), aux.shape[0], fmt_of(aux)) if aux is not None else (None, 0, 0, 0)
+        check(lib().mmdgan_tapsum3x3_small(_ptr(T), nimg, self.Hin, self.Win, 1 if flip else 0, float(alpha_k), _ptr(sigma), _ptr(bias), act,
+                                           a[0], a[1], a[2], a[3], aux_mode, _ptr(dst), plane_stride(dst), dst.shape[0],
+                                           fmt_of(dst) if out_mode == 0 else 0, dst.shape[2], out_mode, _ptr(colsum), _ptr(self.sat_flag), stream()))
+
+    def _img(self, fwd, src, nimg, dst, sigma, alpha_k, bias, act, aux, aux_mode, colsum, out_mode):
+        px = nimg * self.Hin * self.Win
+        op = self.img_op
+        op.sat_flag = self.sat_flag
+        rows = lambda t, c: t.as_strided((t.shape[0], px, c), (t.stride(0), c, 1), t.storage_offset())
+        assert fwd != self.img_few_in       # many -> few only: forward of C -> 3, or input gradient of 3 -> C
+        T = self._img_buf(('T', nimg, fwd), lambda: torch.zeros((1, px, 32), dtype=torch.float32, device=src.device))
+        if fwd:
+            op.forward(rows(src, src.shape[2]), px, T, out_mode=2)
+        else:
+            op.dgrad(rows(src, src.shape[2]), px, T, out_mode=2)
+        self._img_tapsum(T, nimg, not fwd, dst, sigma, alpha_k, bias, act, aux, aux_mode, colsum, out_mode)
 
     def pack(self, w_canon):
         """canonical weights -> forward and input-gradient GEMM operands (unscaled; act_k / sigma is an epilogue alpha)."""
         self.w_canon = w_canon
+        if self.img_op is not None:
+            self.pre_refresh()
+            self.img_op.pack(self.img_canon())
         for g in (self.f, self.d):
             d = PackDesc()
             d.w, d.out = _ptr(w_canon), _ptr(g['w'])
@@ -359,7 +413,12 @@ class LinearOp(object):
         return dict(dims=(self.Hout, self.Wout, self.Hin, self.Win, 2, 2, 4, 4, self.Hin, self.Win, 1, 1), cls=[(-1, -1, 0, 0)])
 
     def _direct(self, fwd, src, nimg, dst, sigma, alpha_k, bias, act, aux, aux_mode, colsum, out_mode):
-        """3x3 / stride-1 image-channel layer on the CUDA cores (mmdgan_direct_conv): exact fp32 products."""
+        """3x3 / stride-1 image-channel layer.  many -> few channels (forward of C -> 3, input gradient of 3 -> C): a dense [C -> 27]
+        product on the tensor-core GEMM + the tap-sum kernel (measured 0.057 / 0.058 ms against 0.091 / 0.087 for the direct kernel);
+        few -> many and the weight gradients stay on the direct CUDA-core kernel / the general weight-gradient GEMM (the im2col27 +
+        dense [27 -> C] form was measured SLOWER there: 0.173 vs 0.150 ms forward, 0.110 vs 0.077 ms weight gradient)."""
+        if self.img_op is not None and fwd != self.img_few_in:
+            return self._img(fwd, src, nimg, dst, sigma, alpha_k, bias, act, aux, aux_mode, colsum, out_mode)
         d = DirectDesc()
         _planes(src)
         d.src, d.src_plane, d.src_npl, d.Cs = _ptr(src), plane_stride(src), src.shape[0], src.shape[2]
@@ -390,14 +449,16 @@ class LinearOp(object):
         return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.f['classes']
 
     def dgrad_tiles(self, nimg):
-        if self.direct_d == 'ls':       # rows of the per-block column-sum workspace of the direct kernel
+        if self.direct_d == 'ls':       # rows of the per-block column-sum workspace of the direct / tap-sum kernel
+            if self.img_op is not None and self.img_few_in:
+                return lib().mmdgan_tapsum_blocks(nimg, self.Hin, self.Win)
             return lib().mmdgan_direct_conv_blocks(nimg, self.Hin, self.Win)
         g = self._dgrad_geom()['dims']
         return lib().mmdgan_gather_gemm_tiles(nimg, g[2], g[3]) * self.d['classes']
 
     def forward(self, src, nimg, dst, sigma=None, alpha_k=1.0, bias=None, act=0, colsum=None, colsumsq=None, out_mode=0):
         if (self.op == 'd' and self.Cs_out in (8, 16, 32) and out_mode == 2 and act == 0 and colsum is None
-                and self.npass == 3):
+                and self.npass == 3 and nimg <= 4096):      # (many rows x few columns, e.g. the 27-column image stand-in: tensor cores)
             # a handful of output columns (the critic scores): fp32 CUDA-core kernel instead of a 94 %-padded MMA tile
             _planes(src)
             npl = min(src.shape[0], self.f['w'].shape[0])

@@ -14,7 +14,9 @@ g = torch.Generator().manual_seed(0)
 data = (torch.rand(B, *arch['input'][0], generator=g) * 2 - 1).cuda(); code = torch.randn(B, 128, generator=g).cuda()
 recs = []
 og, ow, od = K.LinearOp._gemm, K.LinearOp.wgrad, K.LinearOp._direct
+DEPTH = [0]      # nested calls (an image layer = im2col / tap-sum + an inner dense GEMM) are timed at the outermost level only
 def tg(self, g_, src, nimg, dst, geom, *a, **kw):
+    if DEPTH[0] > 0: return og(self, g_, src, nimg, dst, geom, *a, **kw)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(); r = og(self, g_, src, nimg, dst, geom, *a, **kw); e.record()
     d = geom['dims']; M = nimg * d[2] * d[3] * g_['classes']
@@ -22,14 +24,19 @@ def tg(self, g_, src, nimg, dst, geom, *a, **kw):
     recs.append((kind, self.op, self.Cin, self.Cout, self.Hin, nimg, M, g_['ncols'], g_['kpad'], 2.0 * M * g_['ncols'] * g_['taps'] * g_['Cs'], s, e, g_['bn']))
     return r
 def tw(self, x_in, dy, nimg, partials, splits=None, **kw):
+    if DEPTH[0] > 0: return ow(self, x_in, dy, nimg, partials, splits, **kw)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    DEPTH[0] += 1
     s.record(); r = ow(self, x_in, dy, nimg, partials, splits, **kw); e.record()
+    DEPTH[0] -= 1
     R, NC, bn, sp, P = self.wgrad_plan(nimg)
     recs.append(('wgrad', self.op, self.Cin, self.Cout, self.Hin, nimg, R, NC, P, 2.0 * R * NC * P, s, e, (bn, r)))
     return r
 def td(self, fwd, src, nimg, dst, *a, **kw):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    DEPTH[0] += 1
     s.record(); r = od(self, fwd, src, nimg, dst, *a, **kw); e.record()
+    DEPTH[0] -= 1
     M = nimg * self.Hin * self.Win
     recs.append(('fwd*' if fwd else 'dgrad*', self.op, self.Cin, self.Cout, self.Hin, nimg, M, self.Cout if fwd else self.Cin, 9 * (self.Cin if fwd else self.Cout),
                  2.0 * M * 9 * self.Cin * self.Cout, s, e, 'direct'))

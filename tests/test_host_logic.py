@@ -79,9 +79,14 @@ def test_linear_op_launch_plans():
     assert lop._dgrad_geom()['cls'] == [(-1, -1, 0, 0), (-1, 0, 0, 1), (0, -1, 1, 0), (0, 0, 1, 1)]
     # image layers: 3 channels padded to 8 (one 16-byte unit of bf16), weight gradient puts the small side on N
     lop = K.LinearOp('c', [64, 32, 32], [3, 32, 32], 3, 1, device='cpu')
+    # round 2: both directions of the 3-channel layers run as dense products over 27 = 9 taps x 3 channels (im2col27 / tapsum27 + the
+    # tensor-core GEMM): the weight gradient is the dense one, 8 * 1024 pixels contracted
     assert lop.Cs_out == 8 and lop.w_swapped and lop.f['bn'] == 16 and lop.wgrad_plan(8)[:3] == (64, 72, 128)
+    # round 2: the many -> few direction (here the forward pass) runs as a dense [64 -> 27] product + the tap-sum kernel
+    assert lop.img_op is not None and not lop.img_few_in and lop.img_op.f['ncols'] == 32
     lop = K.LinearOp('c', [3, 32, 32], [64, 32, 32], 3, 1, device='cpu')
     assert lop.Cs_in == 8 and not lop.w_swapped and lop.f['kpad'] == 128      # 9 taps x 8 channels = 72 -> whole 64-element K blocks
+    assert lop.img_few_in and lop.img_op.d['ncols'] == 32       # its input gradient is the many -> few direction
     # operand planes: forward weights as two fp16 planes (three plane-pair products are fp32-grade), input-gradient weights as
     # three bf16 planes (three products for gradients, six when the adjoint acts as a forward operator in the spectral norm)
     assert lop.f['w'].dtype == torch.float16 and lop.f['w'].shape[0] == 2 and lop.d['w'].dtype == torch.bfloat16 and lop.d['w'].shape[0] == 3
