@@ -313,23 +313,35 @@ class Agent(object):
         start_time = time.time()
         loss_value = None
         nxt = batch_fn(0) if max_step > 0 else None
+
+        def finish(pending, step):
+            # losses of an enqueued step; check if model produces nan outcome (graph_func.py:856)
+            value = engine.result(pending, check_nan=False)
+            assert not any(np.isnan(value)), 'Model diverged with loss = {} at step {}'.format(value, step)
+            gs = pending[2]
+            if gs % self.query_step == (self.query_step - 1) and self.print_loss:
+                epoch = step // max(step_per_epoch, 1)
+                FLAGS.print('Epoch {}, global steps {}, loss_list {}'.format(
+                    epoch, gs, ['{}'.format(['<{:.2f}>'.format(l) for l in value])]))
+            return value
+
+        pending = None
         for step in range(max_step):
             data_x, code_x = nxt
-            # the next batch is produced now and its host -> device copy overlaps this step (engine.step(prefetch=...))
+            # the next batch is produced now and its host -> device copy overlaps this step (engine.step_async(prefetch=...))
             nxt = batch_fn(step + 1) if step + 1 < max_step else None
             # imbalanced update (graph_func.py:885-886): optimiser i runs when the global step is a multiple of imbalanced_update[i]
             update = (True, True) if self.imbalanced_update is None else \
                 tuple(engine.global_step % int(k) == 0 for k in self.imbalanced_update)
-            loss_value = engine.step(data_x, code_x, check_nan=False, update=update, prefetch=nxt)
-            # check if model produces nan outcome (graph_func.py:856)
-            assert not any(np.isnan(loss_value)), 'Model diverged with loss = {} at step {}'.format(loss_value, step)
-            gs = engine.global_step
-            if gs % self.query_step == (self.query_step - 1) and self.print_loss:
-                epoch = step // max(step_per_epoch, 1)
-                FLAGS.print('Epoch {}, global steps {}, loss_list {}'.format(
-                    epoch, gs, ['{}'.format(['<{:.2f}>'.format(l) for l in loss_value])]))
-            if step == max_step - 1 and self.do_save:
-                save_checkpoint(engine, self.save_path, gs)
+            # step i + 1 is enqueued before the losses of step i are read: the device never waits for the host's per-step work
+            enqueued = engine.step_async(data_x, code_x, update=update, prefetch=nxt)
+            if pending is not None:
+                loss_value = finish(pending, step - 1)
+            pending = enqueued
+        if pending is not None:
+            loss_value = finish(pending, max_step - 1)
+            if self.do_save:
+                save_checkpoint(engine, self.save_path, engine.global_step)
         duration = time.time() - start_time
         FLAGS.print('Training for {} steps took {:.3f} sec.'.format(max_step, duration))     # graph_func.py:945-946
         return loss_value

@@ -391,6 +391,9 @@ class SNGanEngine(object):
         self.code_seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * int(rank)) & 0xFFFFFFFFFFFFFFFF     # every rank its own stream
         self.code_draw = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.device_codes = False                # set per step: True when step() / stage() is given no codes
+        self._pin_res = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]      # results of the two steps in flight
+        self._pin_flag = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._res_next = 0
         self._prefetched = None                  # (data tensor, code tensor, buffer index, event) of the batch in flight
         self._slot_free = [None, None]           # event: the last device-to-device read of a staging slot
         self._stage_next = 0
@@ -969,45 +972,54 @@ class SNGanEngine(object):
             ev.record(self._copy_stream)
         self._prefetched = (data_x, code_x, k, ev)
 
-    def step(self, data_x, code_x=None, check_nan=True, update=(True, True), prefetch=None):
-        """End-to-end step from HOST tensors: H2D of the batch, the fused step, D2H of [loss_gen, loss_dis].  code_x = None: the
-        codes are drawn on the device inside the step (the reference's in-graph tf.random_normal); tests inject code_x.
-        prefetch = (next_data, next_code): the host -> device copy of the NEXT step's batch is started right after this step has
-        been enqueued, so that it overlaps the step instead of preceding the next one (the copy is still made once per step)."""
+    def step_async(self, data_x, code_x=None, update=(True, True), prefetch=None):
+        """Enqueue one end-to-end step from HOST tensors -- H2D of the batch (picked up from an earlier prefetch() of the same
+        tensors, else started now), the fused step, D2H of [loss_gen, loss_dis] and of the saturation flag -- WITHOUT waiting for
+        it; result() returns the losses.  A training loop that enqueues step i + 1 before it reads the losses of step i keeps
+        the device busy across the host's per-step work (Agent.train does; the reference's per-step NaN assert then fires one step
+        later).  code_x = None: the codes are drawn on the device inside the step (the reference's in-graph tf.random_normal).
+        prefetch = (next_data, next_code): the copy of the NEXT batch is started behind this step's launch and overlaps it."""
         pf = self._prefetched
-        if pf is not None and pf[0] is data_x and pf[1] is code_x:
-            self._prefetched = None
-            dd, dc = self._stage_bufs[pf[2]]
-            torch.cuda.current_stream(self.device).wait_event(pf[3])
-            self._dev_data.copy_(dd, non_blocking=True)          # device-to-device, ~2 us
-            self.device_codes = code_x is None
-            if code_x is not None:
-                self._dev_code.copy_(dc, non_blocking=True)
-            self._slot_free[pf[2]] = torch.cuda.Event()
-            self._slot_free[pf[2]].record(torch.cuda.current_stream(self.device))
-        else:
-            self._prefetched = None
-            if not (data_x.is_pinned() and (code_x is None or code_x.is_pinned())):      # pageable host memory: stage through pinned buffers
-                self._pin_data.copy_(data_x)
-                data_x = self._pin_data
-                if code_x is not None:
-                    self._pin_code.copy_(code_x)
-                    code_x = self._pin_code
-            self.stage(data_x, code_x)
+        if not (pf is not None and pf[0] is data_x and pf[1] is code_x):
+            self.prefetch(data_x, code_x)
+            pf = self._prefetched
+        self._prefetched = None
+        main = torch.cuda.current_stream(self.device)
+        dd, dc = self._stage_bufs[pf[2]]
+        main.wait_event(pf[3])
+        self._dev_data.copy_(dd, non_blocking=True)          # device-to-device, ~2 us
+        self.device_codes = code_x is None
+        if code_x is not None:
+            self._dev_code.copy_(dc, non_blocking=True)
+        self._slot_free[pf[2]] = torch.cuda.Event()
+        self._slot_free[pf[2]].record(main)
         self.step_device(update)
         if prefetch is not None:
             self.prefetch(prefetch[0], prefetch[1])
-        self._pin_loss.copy_(self.mmd.losses, non_blocking=True)
-        self._pin_sat.copy_(self.sat_flag, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        lg, ld = float(self._pin_loss[0]), float(self._pin_loss[1])
-        if int(self._pin_sat[0]) != 0:
+        k = self._res_next
+        self._res_next ^= 1
+        self._pin_res[k].copy_(self.mmd.losses, non_blocking=True)
+        self._pin_flag[k].copy_(self.sat_flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        return (k, ev, self.global_step)
+
+    def result(self, pending, check_nan=True):
+        """[loss_gen, loss_dis] of a step enqueued by step_async (waits for it)."""
+        k, ev, gs = pending
+        ev.synchronize()
+        lg, ld = float(self._pin_res[k][0]), float(self._pin_res[k][1])
+        if int(self._pin_flag[k][0]) != 0:
             raise FloatingPointError('an activation exceeded the range of the fp16 forward planes (|x| >= 4094) at step {}: the parity '
-                                     'mode is not valid for this model state; run with MMDGAN_F16_FORWARD=0 (three bf16 planes)'.format(self.global_step))
+                                     'mode is not valid for this model state; run with MMDGAN_F16_FORWARD=0 (three bf16 planes)'.format(gs))
         if check_nan:
             assert not (math.isnan(lg) or math.isnan(ld)), \
-                'Model diverged with loss = {} at step {}'.format([lg, ld], self.global_step)    # graph_func.py:856
+                'Model diverged with loss = {} at step {}'.format([lg, ld], gs)    # graph_func.py:856
         return lg, ld
+
+    def step(self, data_x, code_x=None, check_nan=True, update=(True, True), prefetch=None):
+        """One end-to-end step from HOST tensors, synchronously: step_async + result."""
+        return self.result(self.step_async(data_x, code_x, update=update, prefetch=prefetch), check_nan=check_nan)
 
     def losses(self):
         return self.mmd.losses.clone()
