@@ -443,6 +443,17 @@ class SNGanEngine(object):
                 if L.lop.img_op is not None:
                     need = max(need, nimg * L.rows_in * 32)
         self.wg_scratch = torch.zeros(2 * need, dtype=torch.bfloat16, device=dev)
+        # bf16 re-split ("twin") of every fp16 activation that is a weight-gradient operand (an MMA cannot mix fp16 with bf16).  The
+        # twins are written DURING THE FORWARD PASS on the conversion stream, where the device has a free stream, instead of in
+        # front of each weight-gradient GEMM on the gradient stream, which is the critical path of the backward pass (measured:
+        # the 28 conversions cost 0.35 ms of step time there).
+        self._twins = {}
+        if os.environ.get('MMDGAN_TWINS', '1') == '1':
+            operands = [self.x_all, self.code_planes] + [L.a for L in self.G.layers[:-1] + self.D.layers[:-1] if L.a.dtype == torch.float16]
+            for t in operands:
+                self._twins[t.data_ptr()] = torch.zeros((2, t.shape[1], t.shape[2]), dtype=torch.bfloat16, device=dev)
+        self._cvt_stream = torch.cuda.Stream(device=dev)
+        self._cvt_event = None
         self.tmp_vec = torch.zeros(max(max(L.Cs_out for L in self.G.layers), max(L.Cs_out for L in self.D.layers)) + 64,
                                    dtype=torch.float32, device=dev)
         if self.world_size > 1:
@@ -500,7 +511,24 @@ class SNGanEngine(object):
                 lop.forward(src, nimg, L.a, sigma=sig, alpha_k=L.act_k, bias=L.bias_int if L.has_bias else None,
                             act=L.act_code, out_mode=out_mode)
             src = L.a
+            if is_training and update_moving:
+                self._make_twin(L.a)
         return src
+
+    def _make_twin(self, t):
+        """bf16 twin of an fp16 activation, on the conversion stream (forked from the current stream, joined by the gradient
+        stream before its first weight-gradient GEMM)."""
+        tw = self._twins.get(t.data_ptr()) if t.dtype == torch.float16 else None
+        if tw is None:
+            return
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._cvt_stream.wait_event(ev)
+        with torch.cuda.stream(self._cvt_stream):
+            K.convert_planes(t, tw)
+            self._cvt_event = torch.cuda.Event()
+            self._cvt_event.record(self._cvt_stream)
 
     def _sn_layer(self, L):
         """One PICO power iteration of one spectrally-normalised layer (math_func.py:661-672): sigma = ||F(x)||,
@@ -554,11 +582,16 @@ class SNGanEngine(object):
         K.nchw_to_planes(self._dev_code, self.code_planes)
         K.nchw_to_planes(self._dev_data, self.x_all[:, :B * HW, :])
         joins = self._sn_power_iteration(fork=self.sn_fork)
+        self._make_twin(self.code_planes)
         self._net_forward(self.G, self.code_planes, B)
+        self._make_twin(self.x_all)              # real rows from the input conversion, generated rows from G's last layer
         main = torch.cuda.current_stream(self.device)
         for ev in joins:
             main.wait_event(ev)
         self._net_forward(self.D, self.x_all, 2 * B)
+        if self._cvt_event is not None:          # join: the step's later phases (and the end of a captured graph) see the twins
+            main.wait_event(self._cvt_event)
+            self._cvt_event = None
 
     def _phase_loss(self):
         B = self.B
@@ -581,6 +614,9 @@ class SNGanEngine(object):
     def _weight_grad(self, net, L, x_in, dz, nimg):
         lop = L.lop
         x_in = self._as_rows(x_in, x_in.shape[1] * x_in.shape[2] // L.Cs_in, L.Cs_in)
+        tw = self._twins.get(x_in.data_ptr()) if x_in.dtype == torch.float16 else None
+        if tw is not None:                       # written during the forward pass
+            x_in = self._as_rows(tw, x_in.shape[1], x_in.shape[2])
         lop.wgrad(x_in, dz, nimg, L.wg_parts, L.wg_splits, scratch=self.wg_scratch)
         gview = net.view(net.g, L.ly.kernel_name)
         if L.has_sn:

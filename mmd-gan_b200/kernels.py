@@ -151,12 +151,18 @@ def to_planes(x, dst):
     return dst
 
 
+_SKIP_CONVERT = os.environ.get('MMDGAN_SKIP_CONVERT', '0') == '1'
+_SKIP_WRED = os.environ.get('MMDGAN_SKIP_WRED', '0') == '1'
+
+
 def convert_planes(src, dst, role='act'):
     """Planes in one format -> planes in another, same [rows, C] (bf16 re-split of fp16 activations for the weight gradients)."""
     _planes(src)
     _planes(dst)
     n = dst.shape[1] * dst.shape[2]
     assert src.shape[1] * src.shape[2] == n
+    if _SKIP_CONVERT:       # timing experiment only (wrong results): what the re-split pass costs inside the step
+        return dst
     check(lib().mmdgan_convert_planes(_ptr(src), plane_stride(src), src.shape[0], fmt_of(src, role), _ptr(dst), plane_stride(dst),
                                       dst.shape[0], fmt_of(dst, role), n, stream()))
     return dst
@@ -580,7 +586,8 @@ class LinearOp(object):
             d.Cg, d.Cvalid, d.Rvalid = self.Cs_out, co, ci
             d.base, d.sr, d.st, d.sc = 0, 1, co * ci, ci
         d.w, d.out, d.dots = _ptr(w_canon), _ptr(out_canon), _ptr(dots)
-        check(lib().mmdgan_wgrad_reduce(C.byref(d), stream()))
+        if not _SKIP_WRED:      # (timing experiment only when skipped)
+            check(lib().mmdgan_wgrad_reduce(C.byref(d), stream()))
         return lib().mmdgan_wgrad_reduce_blocks(R * NC)
 
 
