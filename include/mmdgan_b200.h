@@ -230,6 +230,22 @@ typedef struct mmdgan_wred_desc {
 } mmdgan_wred_desc;
 int mmdgan_wgrad_reduce(const mmdgan_wred_desc* d, void* stream);
 int mmdgan_wgrad_reduce_blocks(long long total);
+/* the same for every layer of a net in ONE launch: jobs_device = device array of njobs mmdgan_wred_desc, block_start_device =
+ * njobs + 1 ints (job j owns blocks [start[j], start[j+1]) = mmdgan_wgrad_reduce_blocks(R * NC) of them, which is also the length
+ * of its `dots`), total_blocks = start[njobs] */
+int mmdgan_wgrad_reduce_batched(const void* jobs_device, const int* block_start_device, int njobs, int total_blocks, void* stream);
+/* mmdgan_sn_grad_combine for several layers in one launch; a job is {float* g; const float* s; const double* dots; const float* sigma;
+ * long long n; int ndots; float act_k;} (40 bytes) in device memory */
+typedef struct mmdgan_sn_combine_job {
+    float* g;
+    const float* s;
+    const double* dots;
+    const float* sigma;
+    long long n;
+    int ndots;
+    float act_k;
+} mmdgan_sn_combine_job;
+int mmdgan_sn_grad_combine_batched(const void* jobs_device, int njobs, int blocks, void* stream);
 /* grad = m*G - (m/sigma)*<G,W>*S with m = act_k/sigma: gradient through kernel * act_k / SpectralNorm(kernel) */
 int mmdgan_sn_grad_combine(float* g, const float* s, const double* dots, int ndots, const float* sigma, float act_k, long long n,
                            void* stream);

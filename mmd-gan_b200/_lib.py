@@ -70,6 +70,11 @@ class WredDesc(C.Structure):
         ('w', C.c_void_p), ('out', C.c_void_p), ('dots', C.c_void_p)]
 
 
+class SnCombineJob(C.Structure):
+    _fields_ = [('g', C.c_void_p), ('s', C.c_void_p), ('dots', C.c_void_p), ('sigma', C.c_void_p), ('n', C.c_longlong),
+                ('ndots', C.c_int), ('act_k', C.c_float)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [
         ('w', C.c_void_p), ('out', C.c_void_p), ('plane', C.c_longlong), ('npl', C.c_int), ('fmt', C.c_int),
@@ -111,6 +116,8 @@ SYMBOLS = {
     'mmdgan_dense_small_fwd': (_I, [_P, _LL, _I, _I, _I, _I, _P, _LL, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P]),
     'mmdgan_dense_small_workspace': (C.c_size_t, [_I, _I, _I]),
     'mmdgan_losses_from_sums': (_I, [_P, _F, _F, _F, _P, _P]),
+    'mmdgan_wgrad_reduce_batched': (_I, [_P, _P, _I, _I, _P]),
+    'mmdgan_sn_grad_combine_batched': (_I, [_P, _I, _I, _P]),
     'mmdgan_tapsum3x3_small': (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _LL, _I, _I, _I, _P, _LL, _I, _I, _I, _I, _P, _P, _P]),
     'mmdgan_tapsum_blocks': (_I, [_I, _I, _I]),
     'mmdgan_sample_normal': (_I, [_P, _LL, C.c_ulonglong, _P, _P, _P]),

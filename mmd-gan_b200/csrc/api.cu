@@ -50,6 +50,8 @@ int l_adam_allreduce_nvls(const float*, const float*, const float*, const float*
 int l_scatter_scores_nvls(const float*, int, int, int, float*, float*, cudaStream_t);
 int l_allreduce_small_nvls(float*, const float*, int, cudaStream_t);
 int l_incr_step(int*, cudaStream_t);
+int l_wgrad_reduce_batched(const WredParams*, const int*, int, int, cudaStream_t);
+int l_sn_grad_combine_batched(const void*, int, int, cudaStream_t);
 int tapsum_blocks(int N, int H, int W);
 int launch_tapsum27(const float*, int, int, int, int, float, const float*, const float*, int, const uint16_t*, long long, int, int, int, void*, long long,
                     int, int, int, int, float*, int*, cudaStream_t);
@@ -275,6 +277,18 @@ int mmdgan_wgrad_gemm(const mmdgan_wgrad_desc* d, void* stream) {
 }
 
 int mmdgan_wgrad_reduce_blocks(long long total) { return mg::wgrad_reduce_blocks(total); }
+int mmdgan_wgrad_reduce_batched(const void* jobs_device, const int* block_start_device, int njobs, int total_blocks, void* stream) {
+    if (!jobs_device || !block_start_device) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_reduce_batched: null pointer");
+    if (njobs <= 0 || total_blocks <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_reduce_batched: empty job table");
+    static_assert(sizeof(mmdgan_wred_desc) == sizeof(mg::WredParams), "job layout");
+    return wrap(mg::l_wgrad_reduce_batched(static_cast<const mg::WredParams*>(jobs_device), block_start_device, njobs, total_blocks, S(stream)),
+                "mmdgan_wgrad_reduce_batched");
+}
+int mmdgan_sn_grad_combine_batched(const void* jobs_device, int njobs, int blocks, void* stream) {
+    if (!jobs_device) return fail(MMDGAN_EINVAL, "mmdgan_sn_grad_combine_batched: null pointer");
+    if (njobs <= 0 || blocks <= 0 || njobs > 65535) return fail(MMDGAN_ESHAPE, "mmdgan_sn_grad_combine_batched: bad job table");
+    return wrap(mg::l_sn_grad_combine_batched(jobs_device, njobs, blocks, S(stream)), "mmdgan_sn_grad_combine_batched");
+}
 int mmdgan_wgrad_reduce(const mmdgan_wred_desc* d, void* stream) {
     if (!d || !d->partials || !d->out) return fail(MMDGAN_EINVAL, "mmdgan_wgrad_reduce: null pointer");
     if (d->splits <= 0 || d->R <= 0 || d->NC <= 0 || d->Cg <= 0 || d->NC % d->Cg) return fail(MMDGAN_ESHAPE, "mmdgan_wgrad_reduce: bad shape");

@@ -384,30 +384,44 @@ __global__ void colsum_planes_kernel(const bf16_t* __restrict__ x, long long pla
     }
 }
 
-__global__ void wgrad_reduce_kernel(const WredParams p) {
-    __shared__ double red[256];
+__device__ __forceinline__ void wgrad_reduce_body(const WredParams& p, int block, int nblocks_, double* red) {
+    // four consecutive elements per thread (NC is a multiple of 8: same row, same tap), 16-byte loads, four partial tiles in
+    // flight per accumulator set: the kernel is a latency-bound sum over up to 56 partial tiles
     const long long total = static_cast<long long>(p.R) * p.NC;
     double dot = 0.0;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    for (long long i = (block * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < total;
+         i += static_cast<long long>(nblocks_) * blockDim.x * 4) {
         const int r = static_cast<int>(i / p.NC);
         const int col = static_cast<int>(i - static_cast<long long>(r) * p.NC);
         const int t = col / p.Cg, c = col - t * p.Cg;
         if (c >= p.Cvalid || r >= p.Rvalid) continue;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+        const float* base = p.partials + i;
         int z = 0;
-        for (; z + 4 <= p.splits; z += 4) {     // four independent loads in flight; the summation order stays fixed
-            s0 += p.partials[static_cast<long long>(z) * total + i];
-            s1 += p.partials[static_cast<long long>(z + 1) * total + i];
-            s2 += p.partials[static_cast<long long>(z + 2) * total + i];
-            s3 += p.partials[static_cast<long long>(z + 3) * total + i];
+        for (; z + 4 <= p.splits; z += 4) {     // the summation order stays fixed
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(base + static_cast<long long>(z) * total));
+            const float4 b = __ldcs(reinterpret_cast<const float4*>(base + static_cast<long long>(z + 1) * total));
+            const float4 cc = __ldcs(reinterpret_cast<const float4*>(base + static_cast<long long>(z + 2) * total));
+            const float4 d = __ldcs(reinterpret_cast<const float4*>(base + static_cast<long long>(z + 3) * total));
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+            s2.x += cc.x; s2.y += cc.y; s2.z += cc.z; s2.w += cc.w;
+            s3.x += d.x; s3.y += d.y; s3.z += d.z; s3.w += d.w;
         }
-        for (; z < p.splits; ++z) s0 += p.partials[static_cast<long long>(z) * total + i];
-        const float s = ((s0 + s1) + (s2 + s3)) * p.scale;
-        const long long ci = p.base + perm_feature(r, p.r_perm_C, p.r_perm_HW) * p.sr + t * p.st +
-                             perm_feature(c, p.c_perm_C, p.c_perm_HW) * p.sc;
-        p.out[ci] = s;
-        if (p.w) dot += static_cast<double>(s) * static_cast<double>(p.w[ci]);
+        for (; z < p.splits; ++z) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(base + static_cast<long long>(z) * total));
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        }
+        const float v[4] = {((s0.x + s1.x) + (s2.x + s3.x)) * p.scale, ((s0.y + s1.y) + (s2.y + s3.y)) * p.scale,
+                            ((s0.z + s1.z) + (s2.z + s3.z)) * p.scale, ((s0.w + s1.w) + (s2.w + s3.w)) * p.scale};
+        const long long rbase = p.base + perm_feature(r, p.r_perm_C, p.r_perm_HW) * p.sr + t * p.st;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (c + e >= p.Cvalid) break;
+            const long long ci = rbase + perm_feature(c + e, p.c_perm_C, p.c_perm_HW) * p.sc;
+            p.out[ci] = v[e];
+            if (p.w) dot += static_cast<double>(v[e]) * static_cast<double>(p.w[ci]);
+        }
     }
     if (p.dots) {
         red[threadIdx.x] = dot;
@@ -416,8 +430,53 @@ __global__ void wgrad_reduce_kernel(const WredParams p) {
             if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
             __syncthreads();
         }
-        if (threadIdx.x == 0) p.dots[blockIdx.x] = red[0];
+        if (threadIdx.x == 0) p.dots[block] = red[0];
     }
+}
+__global__ void wgrad_reduce_kernel(const WredParams p) {
+    __shared__ double red[256];
+    wgrad_reduce_body(p, blockIdx.x, gridDim.x, red);
+}
+// Every layer of a net in ONE launch (after its last weight-gradient GEMM): job j owns blocks [start[j], start[j + 1]).  The 28
+// per-layer launches of a step were latency bound (each sums up to 56 partials per element, 10-19 us for a few MB) and cost
+// 0.3 ms of step time; batched, their latencies overlap.
+__global__ void wgrad_reduce_batched_kernel(const WredParams* __restrict__ jobs, const int* __restrict__ start, int njobs) {
+    __shared__ double red[256];
+    int j = 0;
+    while (j + 1 < njobs && static_cast<int>(blockIdx.x) >= start[j + 1]) ++j;
+    wgrad_reduce_body(jobs[j], blockIdx.x - start[j], start[j + 1] - start[j], red);
+}
+struct SnCombineJob {
+    float* g;
+    const float* s;
+    const double* dots;
+    const float* sigma;
+    long long n;
+    int ndots;
+    float act_k;
+};
+__device__ __forceinline__ void sn_grad_combine_body(float* g, const float* s, const double* dots, int ndots, const float* sigma, float act_k,
+                                                     long long n, int block, int nblocks_, double* red) {
+    double d = 0.0;
+    for (int i = threadIdx.x; i < ndots; i += blockDim.x) d += dots[i];     // fixed order per thread, fixed tree below
+    red[threadIdx.x] = d;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double dsum = red[0];
+    const float sg = *sigma;
+    const float m = act_k / sg;
+    const float coef = static_cast<float>(static_cast<double>(m) / static_cast<double>(sg) * dsum);
+    for (long long i = block * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(nblocks_) * blockDim.x)
+        g[i] = m * g[i] - coef * s[i];
+}
+// blockIdx.y = job
+__global__ void sn_grad_combine_batched_kernel(const SnCombineJob* __restrict__ jobs) {
+    __shared__ double red[256];
+    const SnCombineJob j = jobs[blockIdx.y];
+    sn_grad_combine_body(j.g, j.s, j.dots, j.ndots, j.sigma, j.act_k, j.n, blockIdx.x, gridDim.x, red);
 }
 // grad = m * G - (m / sigma) * <G, W> * S,  m = act_k / sigma  (layer_func.py:884-918 differentiated)
 __global__ void sn_grad_combine_kernel(float* __restrict__ g, const float* __restrict__ s, const double* __restrict__ dots, int ndots,
@@ -722,6 +781,14 @@ int wgrad_reduce_blocks(long long total) {
 }
 int l_wgrad_reduce(const WredParams& p, cudaStream_t st) {
     wgrad_reduce_kernel<<<wgrad_reduce_blocks(static_cast<long long>(p.R) * p.NC), 256, 0, st>>>(p);
+    return MG_CHECK_LAUNCH();
+}
+int l_wgrad_reduce_batched(const WredParams* jobs, const int* start, int njobs, int total_blocks, cudaStream_t st) {
+    wgrad_reduce_batched_kernel<<<total_blocks, 256, 0, st>>>(jobs, start, njobs);
+    return MG_CHECK_LAUNCH();
+}
+int l_sn_grad_combine_batched(const void* jobs, int njobs, int blocks, cudaStream_t st) {
+    sn_grad_combine_batched_kernel<<<dim3(blocks, njobs), kBS, 0, st>>>(static_cast<const SnCombineJob*>(jobs));
     return MG_CHECK_LAUNCH();
 }
 int l_sn_grad_combine(float* g, const float* s, const double* dots, int ndots, const float* sigma, float act_k, long long n,

@@ -559,6 +559,13 @@ class LinearOp(object):
 
     def wgrad_reduce(self, partials, splits, nimg, out_canon, w_canon=None, dots=None):
         """split partials -> gradient in the canonical (reference) weight layout; optional per-block <G, W>."""
+        d, nblocks = self.wgrad_reduce_desc(partials, splits, nimg, out_canon, w_canon, dots)
+        if not _SKIP_WRED:      # (timing experiment only when skipped)
+            check(lib().mmdgan_wgrad_reduce(C.byref(d), stream()))
+        return nblocks
+
+    def wgrad_reduce_desc(self, partials, splits, nimg, out_canon, w_canon=None, dots=None):
+        """(descriptor, number of blocks = length of `dots`) of that reduction, for a single launch or a batched job table."""
         R, NC, _, _, _ = self.wgrad_plan(nimg)
         d = WredDesc()
         d.partials, d.splits, d.R, d.NC = _ptr(partials), splits, R, NC
@@ -585,13 +592,50 @@ class LinearOp(object):
         else:                       # tc: r = ci, t = (kh,kw), c = co ; canon [k,k,Cout,Cin]
             d.Cg, d.Cvalid, d.Rvalid = self.Cs_out, co, ci
             d.base, d.sr, d.st, d.sc = 0, 1, co * ci, ci
-        d.w, d.out, d.dots = _ptr(w_canon), _ptr(out_canon), _ptr(dots)
-        if not _SKIP_WRED:      # (timing experiment only when skipped)
-            check(lib().mmdgan_wgrad_reduce(C.byref(d), stream()))
-        return lib().mmdgan_wgrad_reduce_blocks(R * NC)
+        d.w, d.out, d.dots = (w_canon.data_ptr() if w_canon is not None else None), out_canon.data_ptr(), (dots.data_ptr() if dots is not None else None)
+        for t in (w_canon, out_canon, dots):
+            _ptr(t)             # validation only
+        return d, lib().mmdgan_wgrad_reduce_blocks(R * NC)
 
 
 # ------------------------------------------------------------------------------------------------ small wrappers
+def build_wred_jobs(descs_blocks, device):
+    """Device job table of mmdgan_wgrad_reduce_batched: [(WredDesc, nblocks)] -> (blob, start, njobs, total blocks)."""
+    n = len(descs_blocks)
+    arr = (WredDesc * n)()
+    start = [0]
+    for i, (d, nb) in enumerate(descs_blocks):
+        arr[i] = d
+        start.append(start[-1] + int(nb))
+    blob = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    st = torch.tensor(start, dtype=torch.int32, device=device)
+    return blob, st, n, start[-1]
+
+
+def wgrad_reduce_batched(blob, start, njobs, total):
+    if not _SKIP_WRED:
+        check(lib().mmdgan_wgrad_reduce_batched(C.c_void_p(blob.data_ptr()), _ptr(start), njobs, total, stream()))
+
+
+def build_sn_combine_jobs(items, device):
+    """items: [(g, s, dots, ndots, sigma, act_k, n)] -> (blob, njobs, blocks)."""
+    n = len(items)
+    arr = (_lib.SnCombineJob * n)()
+    blocks = 1
+    for i, (g, s, dots, ndots, sigma, act_k, cnt) in enumerate(items):
+        for t in (g, s, dots, sigma):
+            _ptr(t)
+        arr[i].g, arr[i].s, arr[i].dots, arr[i].sigma = g.data_ptr(), s.data_ptr(), dots.data_ptr(), sigma.data_ptr()
+        arr[i].n, arr[i].ndots, arr[i].act_k = int(cnt), int(ndots), float(act_k)
+        blocks = max(blocks, min(1184, (int(cnt) + 1023) // 1024))
+    blob = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    return blob, n, blocks
+
+
+def sn_grad_combine_batched(blob, njobs, blocks):
+    check(lib().mmdgan_sn_grad_combine_batched(C.c_void_p(blob.data_ptr()), njobs, blocks, stream()))
+
+
 def reduce_tiles(partials, T, Cc, out, scale=1.0):
     check(lib().mmdgan_reduce_tiles(_ptr(partials), T, Cc, float(scale), _ptr(out), stream()))
 
