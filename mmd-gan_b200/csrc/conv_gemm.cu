@@ -310,107 +310,6 @@ struct GemmCfg {
     static_assert(SMEM_BYTES <= kSmemMax, "shared-memory budget");
 };
 
-// ---- cluster / cta_group::2 primitives (pair kernel only)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-        "r"(rank)
-        : "memory");
-}
-// TMA loads into THIS CTA's shared memory whose completion bytes are credited to the mbarrier of cluster CTA 0
-__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "{\n\t.reg .b32 rb;\n\t"
-        "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [rb];\n\t}" ::"r"(
-            dst_smem),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                                 int c4) {
-    asm volatile(
-        "{\n\t.reg .b32 rb;\n\t"
-        "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [rb];\n\t}" ::"r"(
-            dst_smem),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// A operand from TENSOR MEMORY (128 lanes x 8 columns per K = 16 slice of 16-bit elements), B from shared memory
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// completion of all prior MMAs of this thread arrives on the mbarrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-        "h"(static_cast<uint16_t>(3))
-        : "memory");
-}
-
-// arrive on the mbarrier at this shared-memory offset in cluster CTA 0 (the pair's leader); rank 0 addresses itself
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) { mbar_arrive_remote(bar, 0); }
-// wait with cluster-scope acquire: the data the barrier publishes was written by the OTHER CTA of the pair
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void st_shared_remote_u32(void* local_addr, uint32_t rank, uint32_t v) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "st.shared::cluster.u32 [ra], %2;\n\t}" ::"r"(smem_u32(local_addr)),
-        "r"(rank), "r"(v)
-        : "memory");
-}
-
 // ---- dynamic tile scheduler.  Tiles [0, nunits) are assigned statically (unit u starts with tile u); every further tile is a
 // ticket drawn from a global counter by the scheduler thread of the unit (the TMA thread of the single CTA / of the pair's
 // leader) and published to the other roles through a small ring in shared memory (pair: in both CTAs): tile_full[slot] says
@@ -985,7 +884,7 @@ int make_tmap_planes(CUtensorMap* m, const uint16_t* base, long long rows, long 
 
 // 5-D bf16 tensor map over NHWC activation planes: dims {C, W, H, N, planes}; box {64, bw, bh, bn, npl} with traversal
 // strides {1, sx, sy, 1, 1} (the box loads ceil(b/s) elements per strided dimension), 128-byte swizzle, zero OOB fill
-static int make_tmap_act(CUtensorMap* m, const uint16_t* base, long long plane_stride_elems, int npl, int C, int W, int H, int N, int bw,
+int make_tmap_act(CUtensorMap* m, const uint16_t* base, long long plane_stride_elems, int npl, int C, int W, int H, int N, int bw,
                          int bh, int bn, int sx, int sy) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;

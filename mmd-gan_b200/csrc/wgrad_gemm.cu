@@ -12,6 +12,13 @@
 // plain bf16 mode.  Every split writes its own fp32 partial tile; the reduction over splits is fused into the
 // gradient-finalise kernel.
 //
+// GTMA: when a 32-pixel k-step is a whole number of image rows (W in {4, 8, 16, 32}) and the gathered operand has whole
+// 64-channel chunks, the G chunks are staged by TMA too -- one 5-D box {64 channels, W, rows, images, planes} per
+// (column chunk, k-step), strided and zero-filled by the tensor map -- so no thread touches operand bytes.
+// PAIR (GTMA only, result rows a multiple of 256): two CTAs of a cluster form one 256 x BN tile with cta_group::2 MMAs;
+// each CTA stages its own 128 result rows of P but only HALF of the G columns, which cuts the L2 -> SM operand traffic
+// per MMA cycle by a third (the kernel is bound by that traffic: 64 B/clk/SM at the full MMA rate without pairing).
+//
 // Replaces the filter gradients TF derives for tf.nn.conv2d / conv2d_transpose / matmul
 // (DeepLearning/my_sngan.py:301-304) and the d(sigma)/dW term of SpectralNorm (GeneralTools/math_func.py:661-672).
 #include "conv_gemm.cuh"
@@ -22,6 +29,8 @@ namespace mg {
 
 int make_tmap_planes(CUtensorMap* m, const uint16_t* base, long long rows, long long cols, long long row_stride_elems,
                      long long plane_stride_elems, int planes, int box_cols, int box_rows, int box_planes, int swizzle);
+int make_tmap_act(CUtensorMap* m, const uint16_t* base, long long plane_stride_elems, int npl, int C, int W, int H, int N, int bw,
+                  int bh, int bn, int sx, int sy);
 
 static constexpr int kWBM = 128;
 static constexpr int kWPix = 32;   // pixels (K) per pipeline stage: 32 KB stages at BN = 128 / two planes, two CTAs per SM
@@ -47,12 +56,12 @@ __device__ __forceinline__ void w_mbar_wait(uint64_t* bar, uint32_t parity, unsi
     }
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool PAIR = false>
 struct WgradCfg {
     static constexpr int NPL = (NPASS == 3) ? 2 : 1;
     static constexpr int CHUNK_BYTES = kWPix * 128;             // one 64-channel chunk of one plane: kWPix pixels x 128 B
     static constexpr int MCH = kWBM / 64;                       // row chunks (M = 128)
-    static constexpr int NCH = BN / 64;                         // column chunks
+    static constexpr int NCH = (PAIR ? BN / 2 : BN) / 64;       // column chunks THIS CTA stages (a pair splits the columns)
     // stage layout: [A chunk][plane] then [B chunk][plane]; the planes of one chunk are adjacent (one TMA box)
     static constexpr int A_BYTES = MCH * NPL * CHUNK_BYTES;
     static constexpr int B_BYTES = NCH * NPL * CHUNK_BYTES;
@@ -65,10 +74,10 @@ struct WgradCfg {
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-template <int BN, int NPASS>
-__global__ void __launch_bounds__(kWThreads, 2)
-wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ WgradParams p) {
-    using Cfg = WgradCfg<BN, NPASS>;
+template <int BN, int NPASS, bool GTMA, bool PAIR>
+__device__ __forceinline__ void wgrad_body(const CUtensorMap& tmP0, const CUtensorMap& tmG0, const WgradParams& p) {
+    static_assert(!PAIR || GTMA, "the CTA-pair form has no cp.async gather");
+    using Cfg = WgradCfg<BN, NPASS, PAIR>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NCH = Cfg::NCH;
@@ -84,8 +93,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x;
+    const int tile_m = blockIdx.x;      // PAIR: the cluster spans two consecutive row tiles
     const int tile_n = blockIdx.y;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const long long p_begin = static_cast<long long>(blockIdx.z) * p.p_per_split;
     long long p_end = p_begin + p.p_per_split;
     if (p_end > p.P) p_end = p.P;
@@ -93,19 +103,24 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmP0);
+        if (GTMA) tma_prefetch_desc(&tmG0);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], kWProducers + 1);
+            mbar_init(&full_bar[s], GTMA ? 1 : kWProducers + 1);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
     if (warp == 5) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+        } else {
+            tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -116,6 +131,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
     };
 
     if (warp < 4) {
+      if (!GTMA) {
         // ======================= G producers (gather, MN-major) =======================
         const int t = threadIdx.x;
         const int chunk = t & 7;   // 16-byte unit (8 channels) inside the 128-byte row
@@ -169,23 +185,66 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
             }
             cp_async_mbar_arrive_noinc(&full_bar[s]);   // asynchronous publication, see conv_gemm.cu
         }
+      }
     } else if (warp == 4) {
-        // ======================= P producer (TMA, MN-major) =======================
+        // ======================= P producer (TMA, MN-major); with GTMA the G chunks as well =======================
         if (lane == 0) {
+            // GTMA: column chunk q of this CTA is (tap, 64-channel chunk); a k-step is `rows` image rows of `nb` images
+            int gch[NCH], gx[NCH], gy[NCH];
+            int img = 0, y = 0, ystep = 0, nstep = 0;
+            if (GTMA) {
+                const int ntaps = p.TH * p.TW;
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    const int col = tile_n * BN + (PAIR ? static_cast<int>(rank) * (BN / 2) : 0) + q * 64;
+                    const int tap = col / p.Cs;
+                    const int ta = tap / p.TW;
+                    gch[q] = col - tap * p.Cs;
+                    gx[q] = tap - ta * p.TW + p.ox;
+                    gy[q] = tap < ntaps ? ta + p.oy : (1 << 20);      // a tap past the filter: the whole box is out of bounds (zeros)
+                }
+                const int rows = kWPix / p.Wg;
+                ystep = rows < p.Hg ? rows : 0;                       // rows >= Hg: whole images per k-step
+                nstep = rows < p.Hg ? 0 : rows / p.Hg;
+                const int hw = p.Hg * p.Wg;
+                img = static_cast<int>(p_begin / hw);
+                y = static_cast<int>(p_begin - static_cast<long long>(img) * hw) / p.Wg;
+            }
             for (int j = 0; j < ksteps; ++j) {
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 w_mbar_wait(&empty_bar[s], ph ^ 1, p.err, 12);
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES);
                 const int prow = static_cast<int>(p_begin + static_cast<long long>(j) * kWPix);
+                if (PAIR) {
+                    // both CTAs load their shares; all bytes are credited to the leader's barrier
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
 #pragma unroll
-                for (int mc = 0; mc < MCH; ++mc)   // one box = {64 channels, kWPix pixels, NPL planes}
-                    tma_load_3d(smem_u32(stage_a(s, mc, 0)), &tmP0, &full_bar[s], tile_m * kWBM + mc * 64, prow, 0);
+                    for (int mc = 0; mc < MCH; ++mc)
+                        tma_load_3d_pair(smem_u32(stage_a(s, mc, 0)), &tmP0, &full_bar[s], tile_m * kWBM + mc * 64, prow, 0);
+#pragma unroll
+                    for (int q = 0; q < NCH; ++q)
+                        tma_load_5d_pair(smem_u32(stage_b(s, q, 0)), &tmG0, &full_bar[s], gch[q], gx[q], y * p.sy + gy[q], img, 0);
+                } else {
+                    mbar_arrive_expect_tx(&full_bar[s], GTMA ? Cfg::STAGE_BYTES : Cfg::A_BYTES);
+#pragma unroll
+                    for (int mc = 0; mc < MCH; ++mc)   // one box = {64 channels, kWPix pixels, NPL planes}
+                        tma_load_3d(smem_u32(stage_a(s, mc, 0)), &tmP0, &full_bar[s], tile_m * kWBM + mc * 64, prow, 0);
+                    if (GTMA) {
+#pragma unroll
+                        for (int q = 0; q < NCH; ++q)
+                            tma_load_5d(smem_u32(stage_b(s, q, 0)), &tmG0, &full_bar[s], gch[q], gx[q], y * p.sy + gy[q], img, 0);
+                    }
+                }
+                if (GTMA) {
+                    y += ystep;
+                    if (y >= p.Hg) { y = 0; ++img; }
+                    img += nstep;
+                }
             }
         }
-    } else {
-        // ======================= MMA issuer =======================
-        const uint32_t idesc = idesc_f16(kWBM, BN, 1, 1, p.p_fmt, p.g_fmt);
+    } else if (!PAIR || rank == 0) {
+        // ======================= MMA issuer (the pair's leader issues for both CTAs) =======================
+        const uint32_t idesc = idesc_f16(PAIR ? 2 * kWBM : kWBM, BN, 1, 1, p.p_fmt, p.g_fmt);
         for (int j = 0; j < ksteps; ++j) {
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
@@ -205,14 +264,18 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
                         // consecutive 64-channel chunks of the same plane are LBO = NPL chunks apart
                         const uint64_t ad = smem_desc(abase + kg * 2048, NPL * Cfg::CHUNK_BYTES, 1024, 2u);
                         const uint64_t bd = smem_desc(bbase + kg * 2048, NPL * Cfg::CHUNK_BYTES, 1024, 2u);
-                        umma_bf16(tmem_base, ad, bd, idesc, (j > 0 || pass > 0 || kg > 0) ? 1u : 0u);
+                        const uint32_t acc = (j > 0 || pass > 0 || kg > 0) ? 1u : 0u;
+                        if (PAIR) umma_bf16_pair(tmem_base, ad, bd, idesc, acc);
+                        else umma_bf16(tmem_base, ad, bd, idesc, acc);
                     }
                 }
-                umma_commit(&empty_bar[s]);
+                if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
             }
             __syncwarp();
         }
-        if (lane == 0) umma_commit(accum_bar);
+        if (lane == 0) {
+            if (PAIR) umma_commit_pair(accum_bar); else umma_commit(accum_bar);
+        }
         __syncwarp();
     }
 
@@ -246,37 +309,85 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
+template <int BN, int NPASS, bool GTMA>
+__global__ void __launch_bounds__(kWThreads, 2)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmG0,
+                  const __grid_constant__ WgradParams p) {
+    wgrad_body<BN, NPASS, GTMA, false>(tmP0, tmG0, p);
+}
 template <int BN, int NPASS>
-static int launch_wcfg(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, cudaStream_t st) {
-    using Cfg = WgradCfg<BN, NPASS>;
-    CUtensorMap t0;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 2)
+wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmG0,
+                       const __grid_constant__ WgradParams p) {
+    wgrad_body<BN, NPASS, true, true>(tmP0, tmG0, p);
+}
+
+// a 32-pixel k-step is `hb` whole image rows of `nb` images, and the gathered operand has whole 64-channel chunks
+static bool gtma_geometry(const WgradParams& p, int* hb, int* nb) {
+    if (p.Cs % 64 != 0 || p.Wg <= 0 || kWPix % p.Wg != 0) return false;
+    const int rows = kWPix / p.Wg;
+    if (rows <= p.Hg) {
+        if (p.Hg % rows != 0) return false;
+        *hb = rows; *nb = 1;
+    } else {
+        if (rows % p.Hg != 0) return false;
+        *hb = p.Hg; *nb = rows / p.Hg;
+    }
+    if (p.p_per_split % (static_cast<long long>(rows >= p.Hg ? p.Hg : rows) * p.Wg * (*nb)) != 0) return false;
+    return p.Wg * p.sx <= 256 && *hb * p.sy <= 256;
+}
+
+template <int BN, int NPASS, bool GTMA, bool PAIR>
+static int launch_wcfg(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, int hb, int nb, cudaStream_t st) {
+    using Cfg = WgradCfg<BN, NPASS, PAIR>;
+    CUtensorMap t0, g0;
     if (make_tmap_planes(&t0, plain, p.P, p.Cp, p.Cp, plain_plane, Cfg::NPL, 64, kWPix, Cfg::NPL, 0)) return -4;
+    if (GTMA) {
+        if (make_tmap_act(&g0, p.g, p.g_plane, Cfg::NPL, p.Cs, p.Ws, p.Hs, p.Nimg, p.Wg * p.sx, hb * p.sy, nb, p.sx, p.sy)) return -4;
+    } else {
+        g0 = t0;
+    }
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(wgrad_gemm_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-            cudaSuccess)
-            return -4;
+        cudaError_t e;
+        if constexpr (PAIR) e = cudaFuncSetAttribute(wgrad_gemm_pair_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        else e = cudaFuncSetAttribute(wgrad_gemm_kernel<BN, NPASS, GTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return -4;
         attr_done = true;
     }
     dim3 grid((p.Cp + kWBM - 1) / kWBM, (p.Ncols + BN - 1) / BN, splits);
-    wgrad_gemm_kernel<BN, NPASS><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, p);
+    if constexpr (PAIR) wgrad_gemm_pair_kernel<BN, NPASS><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, g0, p);
+    else wgrad_gemm_kernel<BN, NPASS, GTMA><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, g0, p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 int launch_wgrad_gemm(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, int bn, int npass,
                       cudaStream_t st) {
+    static int no_gtma = -1, no_pair = -1;
+    if (no_gtma < 0) { const char* e = getenv("MMDGAN_WGRAD_NO_GTMA"); no_gtma = e ? atoi(e) : 0; }
+    if (no_pair < 0) { const char* e = getenv("MMDGAN_WGRAD_NO_PAIR"); no_pair = e ? atoi(e) : 0; }
+    int hb = 0, nb = 0;
+    const bool gtma = !no_gtma && gtma_geometry(p, &hb, &nb);
+    const bool pair = gtma && !no_pair && bn >= 128 && p.Cp % (2 * kWBM) == 0;
 #define MG_CASE(B, N) \
-    if (bn == B && npass == N) return launch_wcfg<B, N>(p, plain, plain_plane, splits, st);
+    if (bn == B && npass == N) \
+        return gtma ? launch_wcfg<B, N, true, false>(p, plain, plain_plane, splits, hb, nb, st) \
+                    : launch_wcfg<B, N, false, false>(p, plain, plain_plane, splits, hb, nb, st);
+#define MG_PAIR(B, N) \
+    if (bn == B && npass == N && pair) return launch_wcfg<B, N, true, true>(p, plain, plain_plane, splits, hb, nb, st);
+    MG_PAIR(128, 3) MG_PAIR(256, 3) MG_PAIR(128, 1) MG_PAIR(256, 1)
     MG_CASE(64, 3) MG_CASE(128, 3) MG_CASE(256, 3)
     MG_CASE(64, 1) MG_CASE(128, 1) MG_CASE(256, 1)
 #undef MG_CASE
+#undef MG_PAIR
     return -1;
 }
 
