@@ -92,16 +92,18 @@ typedef struct mmdgan_pack_desc {
     int in_C, in_HW, out_C, out_HW; /* dense: NCHW-flatten <-> NHWC-flatten feature permutation (HW <= 1: identity) */
 } mmdgan_pack_desc;
 int mmdgan_pack_weights(const mmdgan_pack_desc* d, void* stream);
-/* every parameter-derived buffer of a net in ONE launch after an optimiser update: `jobs_device` is an array of jobs in
- * DEVICE memory (kind 0 = pack weights, kind 1 = permute / pad a per-feature vector), built once at start-up */
+/* every parameter-derived buffer of a net in ONE launch after an optimiser update: `jobs_device` is an array of at most 256
+ * jobs in DEVICE memory (kind 0 = pack weights, kind 1 = permute / pad a per-feature vector), built once at start-up; job j
+ * owns the blocks [block_start_j, block_start_{j+1}) of the flat grid of `total_blocks` blocks (block_start ascending, first 0;
+ * a pack job gets one block per 32 x 64 tile of its packed operand) */
 typedef struct mmdgan_refresh_job {
-    int kind, pad0;
+    int kind, block_start;
     mmdgan_pack_desc pack;
     const float* src;
     float* dst;
     int n, C, HW, inverse;
 } mmdgan_refresh_job;
-int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long max_elems, void* stream);
+int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long total_blocks, void* stream);
 int mmdgan_permute_features(const float* src, float* dst, int n, int C, int HW, int inverse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

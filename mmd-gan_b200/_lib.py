@@ -84,7 +84,7 @@ class PackDesc(C.Structure):
 
 
 class RefreshJob(C.Structure):
-    _fields_ = [('kind', C.c_int), ('pad0', C.c_int), ('pack', PackDesc), ('src', C.c_void_p), ('dst', C.c_void_p),
+    _fields_ = [('kind', C.c_int), ('block_start', C.c_int), ('pack', PackDesc), ('src', C.c_void_p), ('dst', C.c_void_p),
                 ('n', C.c_int), ('C', C.c_int), ('HW', C.c_int), ('inverse', C.c_int)]
 
 

@@ -456,12 +456,12 @@ int mmdgan_mmd_fwd_bwd(const mmdgan_mmd_desc* d, void* stream) {
     return wrap(mg::launch_mmd(p, S(stream)), "mmdgan_mmd_fwd_bwd");
 }
 
-int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long max_elems, void* stream) {
+int mmdgan_refresh(const mmdgan_refresh_job* jobs_device, int njobs, long long total_blocks, void* stream) {
     if (!jobs_device) return fail(MMDGAN_EINVAL, "mmdgan_refresh: null pointer");
     if (njobs <= 0) return MMDGAN_OK;
-    if (njobs > 65535 || max_elems <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_refresh: bad job count");
+    if (njobs > 256 || total_blocks <= 0) return fail(MMDGAN_ESHAPE, "mmdgan_refresh: bad job count");
     static_assert(sizeof(mmdgan_refresh_job) == sizeof(mg::RefreshJob), "job layout");
-    return wrap(mg::l_refresh(reinterpret_cast<const mg::RefreshJob*>(jobs_device), njobs, max_elems, S(stream)), "mmdgan_refresh");
+    return wrap(mg::l_refresh(reinterpret_cast<const mg::RefreshJob*>(jobs_device), njobs, total_blocks, S(stream)), "mmdgan_refresh");
 }
 int mmdgan_dense_small_fwd(const mmdgan_bf16* a, long long a_plane, int npl, int a_fmt, int rows, int K, const mmdgan_bf16* wt,
                            long long w_plane, int w_fmt, int kpad, int N, float alpha_k, const float* sigma, const float* bias, float* out, int ldo,

@@ -436,6 +436,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
     if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched only kernel parameters and on-chip state: from here on the previous kernel's results are read
+    pdl_wait();
+    pdl_launch_dependents();
 
     auto stage_a = [&](int s, int pl) -> uint8_t* { return smem + s * Cfg::STAGE_BYTES + pl * Cfg::A_BYTES; };
     auto stage_b = [&](int s, int pl) -> uint8_t* {
@@ -1000,8 +1003,10 @@ static int launch_cfg(const ConvGemmParams& p, const uint16_t* w, long long w_pl
     const int total = q.tiles_n * classes * (PAIR ? q.tiles_m / 2 : q.tiles_m);
     const int units = total < max_units ? total : max_units;
     dim3 grid(static_cast<unsigned>(PAIR ? 2 * units : units), 1, 1);
-    if constexpr (PAIR) conv_gemm_pair_kernel<BN, NPASS, ATMA><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
-    else conv_gemm_kernel<BN, NPASS, ATMA><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(t0, a0, q);
+    cudaError_t le;
+    if constexpr (PAIR) le = launch_pdl(conv_gemm_pair_kernel<BN, NPASS, ATMA>, grid, dim3(THREADS), Cfg::SMEM_BYTES, st, t0, a0, q);
+    else le = launch_pdl(conv_gemm_kernel<BN, NPASS, ATMA>, grid, dim3(THREADS), Cfg::SMEM_BYTES, st, t0, a0, q);
+    if (le != cudaSuccess) return -4;
     if (q.prof) {       // profiling experiment: blocks the host; never on in the product path
         static long long host[512 * 8];
         cudaStreamSynchronize(st);

@@ -140,7 +140,7 @@ struct PackParams {
 };
 struct RefreshJob {
     int kind;   // 0: pack weights, 1: permute / pad a per-feature vector
-    int pad0;
+    int block_start;   // first block of the flat grid that works on this job (ascending over the job table)
     PackParams pack;
     const float* src;
     float* dst;

@@ -202,12 +202,12 @@ struct PackSmem {
     float tile[32][68];
     int ctap[64], cch[64], rcls[32], rrow[32];
 };
-__device__ __forceinline__ void pack_tiles(const PackParams& p, PackSmem& sm) {
+__device__ __forceinline__ void pack_tiles(const PackParams& p, PackSmem& sm, int blk, int nblk) {
     const int t = threadIdx.x;
     const int rows_all = p.rows_pad * p.classes;
     const int tr = (rows_all + 31) >> 5, tc = (p.kpad + 63) >> 6;
     const bool row_contig = p.mode == PACK_CONV_FWD || p.mode == PACK_TC_DGRAD || p.mode == PACK_DENSE_FWD;
-    for (int tidx = blockIdx.x; tidx < tr * tc; tidx += gridDim.x) {
+    for (int tidx = blk; tidx < tr * tc; tidx += nblk) {
         const int r0 = (tidx / tc) << 5, c0 = (tidx % tc) << 6;
         if (t < 64) {
             int tap = 1 << 20, ch = 0;
@@ -244,7 +244,7 @@ __device__ __forceinline__ void pack_tiles(const PackParams& p, PackSmem& sm) {
 }
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackParams p) {
     __shared__ __align__(16) PackSmem sm;
-    pack_tiles(p, sm);
+    pack_tiles(p, sm, blockIdx.x, gridDim.x);
 }
 
 // out[j'] = src[perm(j')]: canonical per-feature vector (bias / gamma / beta) -> internal NHWC-flatten order
@@ -256,16 +256,23 @@ __global__ void permute_features_kernel(const float* __restrict__ src, float* __
 }
 
 // One launch refreshes every parameter-derived buffer of a net after an update: weight packing jobs and feature
-// permutation / padding jobs; blockIdx.y selects the job, the jobs live in device memory (built once at start-up).
-__global__ void __launch_bounds__(256) refresh_kernel(const RefreshJob* __restrict__ jobs) {
+// permutation / padding jobs.  The jobs live in device memory (built once at start-up); job j owns the blocks
+// [block_start_j, block_start_{j+1}) of a flat grid, sized to its own tile count.  (A 2-D grid of (largest job's blocks) x jobs
+// launched 41 000 blocks for the discriminator, three quarters of them without a tile: 83 us of block scheduling.)
+__global__ void __launch_bounds__(256) refresh_kernel(const RefreshJob* __restrict__ jobs, int njobs) {
     __shared__ __align__(16) PackSmem sm;
-    const RefreshJob& job = jobs[blockIdx.y];
+    const int bx = static_cast<int>(blockIdx.x);
+    // the job of this block = number of jobs whose first block is <= blockIdx.x, minus one (njobs <= 256: one lookup per thread)
+    const int j = __syncthreads_count(static_cast<int>(threadIdx.x) < njobs && bx >= jobs[threadIdx.x].block_start) - 1;
+    const RefreshJob& job = jobs[j];
+    const int blk = bx - job.block_start;
+    const int nblk = (j + 1 < njobs ? jobs[j + 1].block_start : static_cast<int>(gridDim.x)) - job.block_start;
     if (job.kind == 0) {
-        pack_tiles(job.pack, sm);
+        pack_tiles(job.pack, sm, blk, nblk);
     } else {
-        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < job.n; j += gridDim.x * blockDim.x) {
-            if (job.inverse) job.dst[perm_feature(j, job.C, job.HW)] = job.src[j];
-            else job.dst[j] = job.src[perm_feature(j, job.C, job.HW)];
+        for (int i = blk * blockDim.x + threadIdx.x; i < job.n; i += nblk * blockDim.x) {
+            if (job.inverse) job.dst[perm_feature(i, job.C, job.HW)] = job.src[i];
+            else job.dst[i] = job.src[perm_feature(i, job.C, job.HW)];
         }
     }
 }
@@ -349,7 +356,13 @@ __global__ void reduce_tiles_kernel(const float* __restrict__ partials, int T, i
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
     if (c < C)
-        for (int t = threadIdx.y; t < T; t += 32) s += static_cast<double>(partials[static_cast<long long>(t) * C + c]);
+        for (int t = threadIdx.y; t < T; t += 32 * 8) {      // eight loads in flight, summed in the original order
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = t + 32 * k < T ? partials[static_cast<long long>(t + 32 * k) * C + c] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += static_cast<double>(v[k]);
+        }
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
@@ -537,9 +550,19 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0, q = 0.0;
     if (c < C)
-        for (int t = threadIdx.y; t < T; t += 32) {
-            s += static_cast<double>(psum[static_cast<long long>(t) * C + c]);
-            q += static_cast<double>(psq[static_cast<long long>(t) * C + c]);
+        for (int t = threadIdx.y; t < T; t += 32 * 8) {      // sixteen loads in flight, summed in the original order
+            float a[8], b[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = t + 32 * k < T;
+                a[k] = ok ? psum[static_cast<long long>(t + 32 * k) * C + c] : 0.f;
+                b[k] = ok ? psq[static_cast<long long>(t + 32 * k) * C + c] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s += static_cast<double>(a[k]);
+                q += static_cast<double>(b[k]);
+            }
         }
     rs[threadIdx.y][threadIdx.x] = s;
     rq[threadIdx.y][threadIdx.x] = q;
@@ -839,9 +862,9 @@ int l_adam(float* w, float* m, float* v, const float* g, long long n, float lr, 
     adam_kernel<<<grid_for(n), kBS, 0, st>>>(w, m, v, g, n, lr, b1, b2, eps, step);
     return MG_CHECK_LAUNCH();
 }
-int l_refresh(const RefreshJob* jobs, int njobs, long long max_elems, cudaStream_t st) {
-    dim3 grid(grid_for(max_elems / 4), njobs);      // blocks stride over 32 x 32 tiles (1024 elements per block iteration)
-    refresh_kernel<<<grid, kBS, 0, st>>>(jobs);
+int l_refresh(const RefreshJob* jobs, int njobs, long long total_blocks, cudaStream_t st) {
+    if (njobs <= 0 || njobs > 256 || total_blocks <= 0) return -1;
+    refresh_kernel<<<static_cast<unsigned>(total_blocks), kBS, 0, st>>>(jobs, njobs);
     return MG_CHECK_LAUNCH();
 }
 long long dense_small_workspace(int rows, int K, int N) {

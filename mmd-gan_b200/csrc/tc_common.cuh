@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace mg {
 
@@ -416,5 +417,35 @@ __device__ __forceinline__ void st_shared_remote_u32(void* local_addr, uint32_t 
         "r"(rank), "r"(v)
         : "memory");
 }
+
+// ---- programmatic dependent launch.  A kernel launched with launch_pdl() may start (be scheduled, run its prologue: barrier
+// initialisation, TMEM allocation, descriptor prefetch) while the kernel before it in the stream is still draining;
+// pdl_wait() blocks until every prerequisite grid has COMPLETED and its memory is visible, so everything after it sees
+// ordinary stream order.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as all of this grid's CTAs
+// have passed it.  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MMDGAN_PDL"); on = e ? atoi(e) : 1; }
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace mg

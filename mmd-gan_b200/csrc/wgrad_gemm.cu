@@ -123,6 +123,8 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap& tmP0, const CUtens
     if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+    pdl_launch_dependents();
 
     // chunk c, plane pl of the A / B operand of stage s
     auto stage_a = [&](int s, int c, int pl) -> uint8_t* { return smem + s * Cfg::STAGE_BYTES + (c * NPL + pl) * Cfg::CHUNK_BYTES; };
@@ -364,9 +366,10 @@ static int launch_wcfg(const WgradParams& p, const uint16_t* plain, long long pl
         attr_done = true;
     }
     dim3 grid((p.Cp + kWBM - 1) / kWBM, (p.Ncols + BN - 1) / BN, splits);
-    if constexpr (PAIR) wgrad_gemm_pair_kernel<BN, NPASS><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, g0, p);
-    else wgrad_gemm_kernel<BN, NPASS, GTMA><<<grid, kWThreads, Cfg::SMEM_BYTES, st>>>(t0, g0, p);
-    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    cudaError_t le;
+    if constexpr (PAIR) le = launch_pdl(wgrad_gemm_pair_kernel<BN, NPASS>, grid, dim3(kWThreads), Cfg::SMEM_BYTES, st, t0, g0, p);
+    else le = launch_pdl(wgrad_gemm_kernel<BN, NPASS, GTMA>, grid, dim3(kWThreads), Cfg::SMEM_BYTES, st, t0, g0, p);
+    return le == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 int launch_wgrad_gemm(const WgradParams& p, const uint16_t* plain, long long plain_plane, int splits, int bn, int npass,

@@ -653,25 +653,31 @@ def colsum_planes(x, rows, Cc, out):
 
 
 def build_refresh_jobs(pack_descs, permutes, device):
-    """Device-resident job table for mmdgan_refresh: pack_descs = [PackDesc], permutes = [(src, dst, n, C, HW)]."""
+    """Device-resident job table for mmdgan_refresh: pack_descs = [PackDesc], permutes = [(src, dst, n, C, HW)].
+    Returns (table, njobs, total_blocks): job j owns blocks [block_start_j, block_start_{j+1}) of the flat grid -- one block per
+    32 x 64 tile of a packed operand (at most 2048 per job: larger operands stride), one per 256 features of a vector."""
     n = len(pack_descs) + len(permutes)
+    assert 0 < n <= 256
     arr = (RefreshJob * n)()
-    max_elems = 1
+    start = 0
     for i, d in enumerate(pack_descs):
         arr[i].kind = 0
         arr[i].pack = d
-        max_elems = max(max_elems, d.rows_pad * d.kpad * d.classes)
+        arr[i].block_start = start
+        start += max(1, min(2048, ((d.rows_pad * d.classes + 31) // 32) * ((d.kpad + 63) // 64)))
     for j, (src, dst, cnt, Cc, HW) in enumerate(permutes):
         job = arr[len(pack_descs) + j]
         job.kind = 1
+        job.block_start = start
         job.src, job.dst = _ptr(src), _ptr(dst)
         job.n, job.C, job.HW, job.inverse = cnt, Cc, HW, 0
+        start += max(1, min(64, (int(cnt) + 255) // 256))
     blob = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
-    return blob, n, max_elems
+    return blob, n, start
 
 
-def refresh(blob, njobs, max_elems):
-    check(lib().mmdgan_refresh(C.c_void_p(blob.data_ptr()), njobs, max_elems, stream()))
+def refresh(blob, njobs, total_blocks):
+    check(lib().mmdgan_refresh(C.c_void_p(blob.data_ptr()), njobs, total_blocks, stream()))
 
 
 def sn_normalize(v, n, out, sigma_out=None, eps=1e-10):

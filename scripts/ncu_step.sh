@@ -20,7 +20,9 @@ cap conv_fwd 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3[^0-9]+(1|true)' 2 1     #
 cap conv_dgrad 'conv_gemm_pair_kernel<[^0-9]*256[^0-9]+3[^0-9]+(1|true)' 5 1   # 6th launch: D input gradient 512->512 @4x4, 768 rows-images (two bf16 planes, 3 products)
 cap conv_n128 'conv_gemm_pair_kernel<[^0-9]*128[^0-9]+3[^0-9]+(1|true)' 2 1    # a 256 x 128 pair tile launch with concatenated weight planes
 cap conv_dgrad_n64 'conv_gemm_kernel<[^0-9]*64[^0-9]+3[^0-9]+(1|true)' 0 1   # N = 64 (G transposed conv 128->64 forward / D 64->128 input gradient)
-cap wgrad 'wgrad_gemm_kernel<[^0-9]*256[^0-9]+3' 8 1                 # first batch-sized weight gradients (8 batch-1 SN launches skipped)
+cap wgrad 'wgrad_gemm_kernel<[^0-9]*256[^0-9]+3' 3 1                 # a 128-row weight-gradient tile launch (TMA-staged gather), batch-1 SN launches skipped
+cap wgrad_pair 'wgrad_gemm_pair_kernel<[^0-9]*256[^0-9]+3' 12 3      # a 256-row CTA-pair weight-gradient launch
+cap refresh 'refresh_kernel' 0 2                                     # operand refresh of D and of G after the update
 cap mmd 'mmd_' 0 1
 python scripts/profile_step.py cifar 256 3 > gpurun_out/events_${TAG}.txt 2>&1
 du -sh gpurun_out; ls -la gpurun_out/ | tail -16

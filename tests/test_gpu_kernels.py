@@ -44,6 +44,12 @@ CASES = [
     ('tc', 512, 256, 4, 4, 2, 2),
     ('d', 128, 512, 1, 1, 1, 7),
     ('d', 2048, 16, 1, 1, 1, 9),
+    # weight-gradient kernel variants: TMA-staged gather + CTA pair over several k-steps and images; a 4x4 grid with an odd
+    # image count (the last 32-pixel k-step is half out of bounds); stride 2 on a 16-wide output grid; a 64-wide grid (cp.async path)
+    ('c', 256, 256, 8, 3, 1, 6),
+    ('tc', 512, 256, 4, 4, 2, 5),
+    ('c', 128, 256, 32, 4, 2, 2),
+    ('c', 64, 64, 64, 3, 1, 1),
 ]
 
 
