@@ -543,23 +543,28 @@ __global__ void sn_normalize_kernel(const float* __restrict__ v, long long n, fl
 // statistics from per-tile partial sums; moving stats as tf.layers.batch_normalization(fused=True): biased variance
 // normalises; the moving average (momentum 0.99) is fed the Bessel-corrected variance for rank-4 inputs (fused kernel) and the
 // biased one for rank-2 inputs (TF 1.8 falls back to nn.moments there): `bessel`
-__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int T, int C, long long rows, float eps,
-                                   float momentum, float* __restrict__ mean, float* __restrict__ invstd,
-                                   float* __restrict__ moving_mean, float* __restrict__ moving_var, int bessel) {
-    __shared__ double rs[32][33], rq[32][33];
-    const int c = blockIdx.x * 32 + threadIdx.x;
+// CPB channels per block, 1024 / CPB tile slices per channel: a layer with few channels and many tiles (64 channels x 2048
+// tiles) gets 8 blocks of 128 slices instead of 2 blocks of 32 (48 us on the forward critical path).
+template <int CPB>
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int T, int C,
+                                                           long long rows, float eps, float momentum, float* __restrict__ mean,
+                                                           float* __restrict__ invstd, float* __restrict__ moving_mean,
+                                                           float* __restrict__ moving_var, int bessel) {
+    constexpr int RT = 1024 / CPB;
+    __shared__ double rs[RT][CPB + 1], rq[RT][CPB + 1];
+    const int c = blockIdx.x * CPB + threadIdx.x;
     double s = 0.0, q = 0.0;
     if (c < C)
-        for (int t = threadIdx.y; t < T; t += 32 * 8) {      // sixteen loads in flight, summed in the original order
-            float a[8], b[8];
+        for (int t = threadIdx.y; t < T; t += RT * 4) {      // eight loads in flight, summed in a fixed order
+            float a[4], b[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const bool ok = t + 32 * k < T;
-                a[k] = ok ? psum[static_cast<long long>(t + 32 * k) * C + c] : 0.f;
-                b[k] = ok ? psq[static_cast<long long>(t + 32 * k) * C + c] : 0.f;
+            for (int k = 0; k < 4; ++k) {
+                const bool ok = t + RT * k < T;
+                a[k] = ok ? psum[static_cast<long long>(t + RT * k) * C + c] : 0.f;
+                b[k] = ok ? psq[static_cast<long long>(t + RT * k) * C + c] : 0.f;
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 s += static_cast<double>(a[k]);
                 q += static_cast<double>(b[k]);
             }
@@ -567,6 +572,14 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
     rs[threadIdx.y][threadIdx.x] = s;
     rq[threadIdx.y][threadIdx.x] = q;
     __syncthreads();
+    // fold the RT slices down to 32 in parallel, then one thread per channel adds the 32 in order
+    for (int half = RT / 2; half >= 32; half >>= 1) {
+        if (threadIdx.y < half) {
+            rs[threadIdx.y][threadIdx.x] += rs[threadIdx.y + half][threadIdx.x];
+            rq[threadIdx.y][threadIdx.x] += rq[threadIdx.y + half][threadIdx.x];
+        }
+        __syncthreads();
+    }
     if (threadIdx.y != 0 || c >= C) return;
     s = 0.0; q = 0.0;
     for (int k = 0; k < 32; ++k) { s += rs[k][threadIdx.x]; q += rq[k][threadIdx.x]; }
@@ -829,7 +842,10 @@ int l_sn_normalize(const float* v, long long n, float eps, float* sigma_out, bf1
 }
 int l_bn_finalize(const float* psum, const float* psq, int T, int C, long long rows, float eps, float momentum, float* mean,
                   float* invstd, float* mm, float* mv, int bessel, cudaStream_t st) {
-    bn_finalize_kernel<<<nblocks(C, 32), dim3(32, 32), 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv, bessel);
+    if (T >= 256)
+        bn_finalize_kernel<8><<<nblocks(C, 8), dim3(8, 128), 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv, bessel);
+    else
+        bn_finalize_kernel<32><<<nblocks(C, 32), dim3(32, 32), 0, st>>>(psum, psq, T, C, rows, eps, momentum, mean, invstd, mm, mv, bessel);
     return MG_CHECK_LAUNCH();
 }
 int l_bn_inference_stats(const float* mm, const float* mv, int C, float eps, float* mean, float* invstd, cudaStream_t st) {
