@@ -317,11 +317,15 @@ struct GemmCfg {
 // A CTA that starts late (another stream's kernel still held its SM) simply draws fewer tickets: no tail imbalance.
 static constexpr int kRing = 8;
 template <bool PAIR>
-__device__ __forceinline__ int ring_read(const int* ring, uint64_t* tile_full, uint64_t* tile_empty, int lt, unsigned int* err) {
-    // called by one lane; returns the tile id of this unit's lt-th tile
+__device__ __forceinline__ int ring_read(const int* ring, uint64_t* tile_full, uint64_t* tile_empty, int lt, unsigned int* err,
+                                         uint32_t rank = 0) {
+    // called by one lane; returns the tile id of this unit's lt-th tile.  Only the pair's PEER CTA needs cluster scope (its ring
+    // copy is written from the leader, its "read" arrival goes to the leader's barrier); the leader's own consumers share a CTA
+    // with the scheduler and use the plain CTA-scope wait / arrive on the same barriers.
     const int slot = lt % kRing;
     const uint32_t ph = (lt / kRing) & 1;
-    if (PAIR) {
+    const bool remote = PAIR && rank != 0;
+    if (remote) {
         if (!mbar_try_wait_cluster(&tile_full[slot], ph)) {
             const unsigned long long t0 = gtime_ns();
             while (!mbar_try_wait_cluster(&tile_full[slot], ph))
@@ -334,14 +338,15 @@ __device__ __forceinline__ int ring_read(const int* ring, uint64_t* tile_full, u
         mbar_wait_wd(&tile_full[slot], ph, err, 9);
     }
     const int tile = *reinterpret_cast<const volatile int*>(ring + slot);
-    if (PAIR) mbar_arrive_leader(&tile_empty[slot]); else mbar_arrive(&tile_empty[slot]);
+    if (remote) mbar_arrive_leader(&tile_empty[slot]); else mbar_arrive(&tile_empty[slot]);
     return tile;
 }
 // one lane reads, the warp gets the value
 template <bool PAIR>
-__device__ __forceinline__ int ring_read_warp(const int* ring, uint64_t* tile_full, uint64_t* tile_empty, int lt, unsigned int* err) {
+__device__ __forceinline__ int ring_read_warp(const int* ring, uint64_t* tile_full, uint64_t* tile_empty, int lt, unsigned int* err,
+                                              uint32_t rank = 0) {
     int tile = 0;
-    if ((threadIdx.x & 31) == 0) tile = ring_read<PAIR>(ring, tile_full, tile_empty, lt, err);
+    if ((threadIdx.x & 31) == 0) tile = ring_read<PAIR>(ring, tile_full, tile_empty, lt, err, rank);
     return __shfl_sync(0xffffffffu, tile, 0);
 }
 
@@ -461,7 +466,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
         const int ntaps = p.TH * p.TW;
         int it = 0;
         for (int lt = 0;; ++lt) {
-            const int tile = ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err);
+            const int tile = ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err, rank);
             if (tile < 0) break;
             const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
             const GemmClass cls = p.cls[tc.cls_idx];
@@ -524,29 +529,31 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             const long long t_begin = clock64();
             int it = 0;
             int next_tile = unit;          // scheduler: the ticket of tile lt + 1 is drawn while tile lt is being loaded
+            unsigned int ticket = 0;
+            bool drawn = false;
             for (int lt = 0;; ++lt) {
                 int tile;
                 if (PAIR && rank != 0) {
-                    tile = ring_read<PAIR>(ring, tile_full, tile_empty, lt, p.err);
+                    tile = ring_read<PAIR>(ring, tile_full, tile_empty, lt, p.err, rank);
                 } else {
                     // ---- scheduler: next tile of this unit -> ring (of both CTAs of a pair)
                     const int slot = lt % kRing;
                     mbar_wait_wd(&tile_empty[slot], ((lt / kRing) & 1) ^ 1, p.err, 10);
-                    tile = next_tile;
-                    if (tile >= total) tile = -1;
-                    else {
-                        // one atomic round trip (~1-2 k cycles) per tile, off the critical path: its result is first looked at
-                        // after this tile's loads have been issued
-                        const unsigned int ticket = atomicAdd(p.sched, 1u);
+                    if (drawn) {       // the ticket drawn one tile ago: its atomic round trip (~1-2 k cycles) ran under that tile's loads
                         if (ticket == static_cast<unsigned int>(total - 1)) atomicExch(p.sched, 0u);   // the last draw of the launch re-arms the counter
                         next_tile = static_cast<int>(ticket) + nunits;
                     }
+                    tile = next_tile < total ? next_tile : -1;
                     ring[slot] = tile;
                     if (PAIR) {
                         st_shared_remote_u32(ring + slot, 1, static_cast<uint32_t>(tile));
                         mbar_arrive_remote(&tile_full[slot], 1);
                     }
                     mbar_arrive(&tile_full[slot]);
+                    // the draw for the tile after this one is issued AFTER the publication and not looked at until the next
+                    // iteration: neither the consumers nor this tile's first loads wait for the atomic
+                    drawn = tile >= 0;
+                    if (drawn) ticket = atomicAdd(p.sched, 1u);
                 }
                 if (tile < 0) break;
                 const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
@@ -591,7 +598,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
             // ======================= peer CTA: relay "my A rows have landed" to the leader =======================
             int it = 0;
             for (int lt = 0;; ++lt) {
-                if (ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err) < 0) break;
+                if (ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err, rank) < 0) break;
                 for (int j = 0; j < ksteps; ++j, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -613,7 +620,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
         int ntiles = 0;
         for (int lt = 0;; ++lt) {
             const long long tr0 = clock64();
-            if (ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err) < 0) break;
+            if (ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err, rank) < 0) break;
             if (prof) w_ring += clock64() - tr0;
             ++ntiles;
             const int ab = lt & 1;
@@ -704,7 +711,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
         const int out_kind = p.out_mode == 2 ? 2 : (p.dst_npl == 2 ? (p.dst_fmt == FMT_BF16 ? 1 : (p.dst_fmt == FMT_F16A ? 0 : 3)) : 3);
         const int kind = (fast && out_kind != 3) ? 1 + out_kind + 3 * (aux_bits ? 1 : 0) + 6 * (p.colsum ? 1 : 0) : 0;
         for (int lt = 0;; ++lt) {
-            const int tile = ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err);
+            const int tile = ring_read_warp<PAIR>(ring, tile_full, tile_empty, lt, p.err, rank);
             if (tile < 0) break;
             if ((lt & 1) != egrp) continue;                    // the other group's tile
             const TileCoord tc = decode_tile<PAIR>(tile, p, rank);
