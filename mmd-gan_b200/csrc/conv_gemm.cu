@@ -785,7 +785,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmB0, const CU
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (PAIR) mbar_arrive_leader(&acce_bar[ab]); else mbar_arrive(&acce_bar[ab]);
+                        if (PAIR && rank != 0) mbar_arrive_leader(&acce_bar[ab]); else mbar_arrive(&acce_bar[ab]);      // the leader arrives locally (a remote arrive on the own CTA is slow)
                     }
                 }
                 if (col >= p.Ncols) continue;            // padding columns of the last N tile (uniform over the group)
