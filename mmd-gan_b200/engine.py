@@ -469,6 +469,24 @@ class SNGanEngine(object):
                 width = 2 * max([L.Cs_out for L in bn_layers] + [2])
                 self.sym_scores = parallel.SymmetricScores(B, d, dev, self.pg, stat_slots=2 * len(bn_layers), stat_width=width)
                 self.gen_all, self.real_all = self.sym_scores.gen_all, self.sym_scores.real_all
+            # The all-reduce of the discriminator's gradients runs BESIDE the generator's backward pass.  With NCCL's default
+            # channel count its CTAs (one SM each, scattered over the TPCs) keep the persistent CTA-pair GEMMs off part of the
+            # GPU for the length of the transfer: measured on 2 B200 (scripts/dp_phase_times.py), the generator's backward graph
+            # takes 0.74-0.76 ms next to the all-reduce against 0.58 ms alone; with that one all-reduce on its own communicator
+            # capped at 4 CTAs it takes 0.65 ms (step 4.14 -> 3.97 ms).  EXPERIMENT, off by default (MMDGAN_AR_CTAS=<n> turns it
+            # on): a bench.py run with the second communicator hung until its timeout once, unexplained -- not shipped.
+            self.pg_overlap = self.pg
+            ar_ctas = int(os.environ.get('MMDGAN_AR_CTAS', '0'))
+            if not self.nvls and ar_ctas > 0:
+                import torch.distributed as dist
+                try:
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = ar_ctas
+                    opts.config.min_ctas = 1
+                    ranks = dist.get_process_group_ranks(self.pg) if self.pg is not None else list(range(dist.get_world_size()))
+                    self.pg_overlap = dist.new_group(ranks=ranks, backend='nccl', pg_options=opts)
+                except (AttributeError, RuntimeError, TypeError):      # a backend without these options (gloo in the CPU tests)
+                    self.pg_overlap = self.pg
 
     # -------------------------------------------------------------------------------------------- forward passes
     @staticmethod
@@ -833,7 +851,7 @@ class SNGanEngine(object):
         own stream, and overlaps the generator's backward pass (joined in _allreduce_grads)."""
         import torch.distributed as dist
         if not self.nvls:
-            self._comm_work = dist.all_reduce(self.D.g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self._comm_work = dist.all_reduce(self.D.g, op=dist.ReduceOp.SUM, group=self.pg_overlap, async_op=True)
 
     def _join_dis_allreduce(self):
         """Make the CURRENT stream wait for the discriminator's all-reduce (issued by _allreduce_dis_async)."""
