@@ -880,10 +880,6 @@ class SNGanEngine(object):
             self._allreduce_dis_async()
             self._phase_backward('gen')
             self._allreduce_grads()
-        elif os.environ.get('MMDGAN_FORCE_SPLIT', '0') == '1':
-            # experiment (single GPU): the data-parallel step's join between the two backward halves, without any collective
-            self._phase_backward('dis')
-            self._phase_backward('gen')
         else:
             self._phase_backward()
         self._phase_update()

@@ -151,18 +151,12 @@ def to_planes(x, dst):
     return dst
 
 
-_SKIP_CONVERT = os.environ.get('MMDGAN_SKIP_CONVERT', '0') == '1'
-_SKIP_WRED = os.environ.get('MMDGAN_SKIP_WRED', '0') == '1'
-
-
 def convert_planes(src, dst, role='act'):
     """Planes in one format -> planes in another, same [rows, C] (bf16 re-split of fp16 activations for the weight gradients)."""
     _planes(src)
     _planes(dst)
     n = dst.shape[1] * dst.shape[2]
     assert src.shape[1] * src.shape[2] == n
-    if _SKIP_CONVERT:       # timing experiment only (wrong results): what the re-split pass costs inside the step
-        return dst
     check(lib().mmdgan_convert_planes(_ptr(src), plane_stride(src), src.shape[0], fmt_of(src, role), _ptr(dst), plane_stride(dst),
                                       dst.shape[0], fmt_of(dst, role), n, stream()))
     return dst
@@ -560,8 +554,7 @@ class LinearOp(object):
     def wgrad_reduce(self, partials, splits, nimg, out_canon, w_canon=None, dots=None):
         """split partials -> gradient in the canonical (reference) weight layout; optional per-block <G, W>."""
         d, nblocks = self.wgrad_reduce_desc(partials, splits, nimg, out_canon, w_canon, dots)
-        if not _SKIP_WRED:      # (timing experiment only when skipped)
-            check(lib().mmdgan_wgrad_reduce(C.byref(d), stream()))
+        check(lib().mmdgan_wgrad_reduce(C.byref(d), stream()))
         return nblocks
 
     def wgrad_reduce_desc(self, partials, splits, nimg, out_canon, w_canon=None, dots=None):
@@ -613,8 +606,7 @@ def build_wred_jobs(descs_blocks, device):
 
 
 def wgrad_reduce_batched(blob, start, njobs, total):
-    if not _SKIP_WRED:
-        check(lib().mmdgan_wgrad_reduce_batched(C.c_void_p(blob.data_ptr()), _ptr(start), njobs, total, stream()))
+    check(lib().mmdgan_wgrad_reduce_batched(C.c_void_p(blob.data_ptr()), _ptr(start), njobs, total, stream()))
 
 
 def build_sn_combine_jobs(items, device):
