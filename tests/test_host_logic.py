@@ -314,3 +314,30 @@ def test_nvls_shard_ranges_cover_the_flat_buffer():
             assert pos == n_flat
     with pytest.raises(AssertionError):
         shard_range(66, 0, 2)
+
+
+def test_refresh_job_table_partitions_the_flat_grid():
+    """mmdgan_refresh: job j owns the blocks [block_start_j, block_start_{j+1}) of one flat grid (the kernel looks its job up from
+    this table); the table is built on the host once per network.  Vector jobs and the split-K reduction tables carry device
+    pointers and are exercised by the GPU step tests."""
+    from mmdgan_b200 import _lib
+    from mmdgan_b200 import kernels as K
+    lib = _lib.load()
+    packs = []
+    for rows_pad, kpad, classes in ((128, 1152, 1), (64, 512, 4), (16, 64, 1), (4096, 8192, 1)):
+        d = _lib.PackDesc()
+        d.rows_pad, d.kpad, d.classes = rows_pad, kpad, classes
+        packs.append(d)
+    blob, n, total = K.build_refresh_jobs(packs, [], 'cpu')
+    arr = (_lib.RefreshJob * n).from_buffer_copy(blob.numpy().tobytes())
+    starts = [arr[i].block_start for i in range(n)]
+    # one block per 32 x 64 tile of a packed operand, at most 2048 per job (larger operands stride)
+    sizes = [4 * 18, 8 * 8, 1 * 1, 2048]
+    assert n == 4 and starts == [sum(sizes[:i]) for i in range(4)] and total == sum(sizes)
+    assert [arr[i].kind for i in range(n)] == [0, 0, 0, 0] and arr[1].pack.classes == 4 and arr[3].pack.kpad == 8192
+    with pytest.raises(K._lib.MmdganError):          # a vector job needs device memory: the builder refuses a host tensor
+        K.build_refresh_jobs(packs, [(torch.zeros(8), torch.zeros(8), 8, 0, 0)], 'cpu')
+    # a table the kernel cannot index (more jobs than threads of a block) or an empty grid is refused without touching the device
+    assert lib.mmdgan_refresh(ctypes.c_void_p(blob.data_ptr()), 257, 10, None) == _lib.MMDGAN_ESHAPE
+    assert lib.mmdgan_refresh(ctypes.c_void_p(blob.data_ptr()), n, 0, None) == _lib.MMDGAN_ESHAPE
+    assert lib.mmdgan_refresh(None, n, total, None) == _lib.MMDGAN_EINVAL
