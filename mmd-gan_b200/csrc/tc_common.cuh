@@ -406,7 +406,8 @@ __device__ __forceinline__ void st_shared_remote_u32(void* local_addr, uint32_t 
 // pdl_wait() blocks until every prerequisite grid has COMPLETED and its memory is visible, so everything after it sees
 // ordinary stream order.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as all of this grid's CTAs
 // have passed it.  Both are no-ops for a launch without the attribute.  OPT-IN (MMDGAN_PDL=1): measured gain 0.01-0.02 ms per
-// step (noise level) -- the persistent kernels leave no launch gap to hide -- so the attribute is not set by default.
+// step (noise level) -- the persistent kernels leave no launch gap to hide -- and two of 16 bench runs with the attribute on
+// hung (none of 50+ without it; not understood), so the attribute is not set by default.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -473,8 +473,8 @@ class SNGanEngine(object):
             # channel count its CTAs (one SM each, scattered over the TPCs) keep the persistent CTA-pair GEMMs off part of the
             # GPU for the length of the transfer: measured on 2 B200 (scripts/dp_phase_times.py), the generator's backward graph
             # takes 0.74-0.76 ms next to the all-reduce against 0.58 ms alone; with that one all-reduce on its own communicator
-            # capped at 4 CTAs it takes 0.65 ms (step 4.14 -> 3.97 ms).  EXPERIMENT, off by default (MMDGAN_AR_CTAS=<n> turns it
-            # on): a bench.py run with the second communicator hung until its timeout once, unexplained -- not shipped.
+            # capped at 4 CTAs it takes 0.65 ms (sum of segments 4.14 -> 3.97 ms).  EXPERIMENT, off by default (MMDGAN_AR_CTAS=<n>
+            # turns it on): in the whole bench line the gain did not show (4.00 / 4.05 ms against 3.98-4.09 ms), DESIGN.md section 6.
             self.pg_overlap = self.pg
             ar_ctas = int(os.environ.get('MMDGAN_AR_CTAS', '0'))
             if not self.nvls and ar_ctas > 0:
